@@ -1,0 +1,188 @@
+// Chains -> alignment regions for one (read, conversion) task:
+//   mem_chain2region   lib/aln/memchain.c:873-904
+//   mem_chain2region1  lib/aln/memchain.c:742-871
+//   left/right_extend_seed_set_align_*  memchain.c:613-730, mem_chain_reference_span :585-605,
+//   cal_max_gap :576-582, asymmetric_flt_seed :138-149, bns_fetch_seq bntseq.c:428-452.
+// The reference window of a chain is never materialised: target bases are decoded straight
+// from the 2-bit packed forward reference (reverse strand = complement read backwards,
+// bntseq.c:411-416), which stays L2-resident for the few hundred bases a chain touches.
+#pragma once
+#include "bsq_chain.h"
+#include "bsq_ksw.h"
+
+BSQ_HD int bsq_pac_base(const uint8_t *pac, int64_t l) { return pac[l >> 2] >> ((~l & 3) << 1) & 3; }
+
+// base at forward-reverse coordinate pos in [0, 2*l_pac)
+BSQ_HD int bsq_ref_base(const bsq_devidx_t &ix, int64_t pos) {
+  return pos < ix.l_pac ? bsq_pac_base(ix.pac, pos) : 3 - bsq_pac_base(ix.pac, (ix.l_pac << 1) - 1 - pos);
+}
+
+BSQ_HD int bsq_cal_max_gap(const bsq_devopt_t &opt, int qlen) {
+  int l_del = (int)((double)(qlen * opt.a - opt.o_del) / opt.e_del + 1.);
+  int l_ins = (int)((double)(qlen * opt.a - opt.o_ins) / opt.e_ins + 1.);
+  int l = l_del > l_ins ? l_del : l_ins;
+  l = l > 1 ? l : 1;
+  return l < opt.w << 1 ? l : opt.w << 1;
+}
+
+struct bsq_q_fwd { const uint8_t *q; BSQ_HD int operator()(int j) const { return q[j]; } };
+struct bsq_q_rev { const uint8_t *q; int last; BSQ_HD int operator()(int j) const { return q[last - j]; } };
+struct bsq_t_fwd { const bsq_devidx_t *ix; int64_t p0; BSQ_HD int operator()(int i) const { return bsq_ref_base(*ix, p0 + i); } };
+struct bsq_t_rev { const bsq_devidx_t *ix; int64_t p0; BSQ_HD int operator()(int i) const { return bsq_ref_base(*ix, p0 - i); } };
+
+// mem_chain2region1 for one seed list.  regs[reg0..*n_regs) are the regions of this task so far.
+BSQ_HD void bsq_chain2region1(const bsq_devopt_t &opt, const bsq_devidx_t &ix, int64_t rmax0, int64_t rmax1, int rid,
+                              int l_query, const uint8_t *query, const bsq_seed_t *seeds, int n_seeds, int parent,
+                              float frac_rep, uint64_t *srt, bsq_ksw_scratch_t &ksw, bsq_reg_t *regs, int *n_regs) {
+  const int8_t *mat = parent ? opt.ctmat : opt.gamat;
+  for (int i = 0; i < n_seeds; ++i) srt[i] = (uint64_t)(uint32_t)seeds[i].len << 32 | (uint32_t)i;  // score == len
+  struct u64_less { BSQ_HD bool operator()(uint64_t a, uint64_t b) const { return a < b; } };
+  bsq_introsort(srt, (int64_t)n_seeds, u64_less());
+  for (int k = n_seeds - 1; k >= 0; --k) {
+    const bsq_seed_t &s = seeds[(uint32_t)srt[k]];
+    // asymmetric_flt_seed: reject ref T/read C and ref A/read G inside the seed
+    {
+      bool bad = false;
+      for (int i = 0; i < s.len; ++i) {
+        const int r = bsq_ref_base(ix, s.rbeg + i), qv = query[s.qbeg + i];
+        if ((r == 3 && qv == 1) || (r == 0 && qv == 2)) { bad = true; break; }
+      }
+      if (bad) continue;
+    }
+    // was this seed already covered by an earlier extension?
+    int u;
+    for (u = 0; u < *n_regs; ++u) {
+      const bsq_reg_t &reg = regs[u];
+      if (s.rbeg < reg.rb || s.rbeg + s.len > reg.re || s.qbeg < reg.qb || s.qbeg + s.len > reg.qe) continue;
+      if ((double)(s.len - reg.seedlen0) > .1 * l_query) continue;
+      int qd = s.qbeg - reg.qb;
+      int64_t rd = s.rbeg - reg.rb;
+      int max_gap = bsq_cal_max_gap(opt, (int)(qd < rd ? qd : rd));
+      int w = max_gap < reg.w ? max_gap : reg.w;
+      if (qd - rd < w && rd - qd < w) break;
+      qd = reg.qe - (s.qbeg + s.len);
+      rd = reg.re - (s.rbeg + s.len);
+      max_gap = bsq_cal_max_gap(opt, (int)(qd < rd ? qd : rd));
+      w = max_gap < reg.w ? max_gap : reg.w;
+      if (qd - rd < w && rd - qd < w) break;
+    }
+    if (u < *n_regs) {
+      // almost contained: extend anyway only if an overlapping seed sits on another diagonal
+      int i;
+      for (i = k + 1; i < n_seeds; ++i) {
+        if (srt[i] == 0) continue;
+        const bsq_seed_t &t = seeds[(uint32_t)srt[i]];
+        if ((double)t.len < s.len * .95) continue;
+        if (s.qbeg <= t.qbeg && s.qbeg + s.len - t.qbeg >= s.len >> 2 && t.qbeg - s.qbeg != t.rbeg - s.rbeg) break;
+        if (t.qbeg <= s.qbeg && t.qbeg + t.len - s.qbeg >= s.len >> 2 && s.qbeg - t.qbeg != s.rbeg - t.rbeg) break;
+      }
+      if (i == n_seeds) { srt[k] = 0; continue; }
+    }
+    // ---- extension ----
+    bsq_reg_t &reg = regs[(*n_regs)++];
+    int aw0 = opt.w, aw1 = opt.w;
+    reg.rb = reg.re = 0; reg.qb = reg.qe = 0; reg.w = opt.w; reg.score = reg.truesc = -1; reg.rid = rid;
+    reg.seedcov = 0; reg.seedlen0 = 0; reg.frac_rep = 0.f; reg.bss = reg.parent = 0; reg.pad_[0] = reg.pad_[1] = 0;
+    if (s.qbeg == 0) {
+      reg.score = reg.truesc = s.len * opt.a; reg.qb = 0; reg.rb = s.rbeg;
+    } else {
+      bsq_q_rev qa; qa.q = query; qa.last = s.qbeg - 1;
+      bsq_t_rev ta; ta.ix = &ix; ta.p0 = s.rbeg - 1;
+      const int tlen = (int)(s.rbeg - rmax0);
+      bsq_ext_result_t r;
+      r.score = 0; r.qle = r.tle = r.gtle = 0; r.gscore = -1; r.max_off = 0;
+      for (int i = 0; i < 2; ++i) {
+        const int prev = reg.score;
+        aw0 = opt.w << i;
+        r = bsq_ksw_extend(s.qbeg, qa, tlen, ta, mat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, aw0, opt.pen_clip5,
+                           opt.zdrop, s.len * opt.a, ksw);
+        reg.score = r.score;
+        if (reg.score == prev || r.max_off < (aw0 >> 1) + (aw0 >> 2)) break;
+      }
+      if (r.gscore <= 0 || r.gscore <= reg.score - opt.pen_clip5) {
+        reg.qb = s.qbeg - r.qle; reg.rb = s.rbeg - r.tle; reg.truesc = reg.score;
+      } else {
+        reg.qb = 0; reg.rb = s.rbeg - r.gtle; reg.truesc = r.gscore;
+      }
+    }
+    if (s.qbeg + s.len == l_query) {
+      reg.qe = l_query; reg.re = s.rbeg + s.len;
+    } else {
+      const int sc0 = reg.score, qe = s.qbeg + s.len;
+      bsq_q_fwd qa; qa.q = query + qe;
+      bsq_t_fwd ta; ta.ix = &ix; ta.p0 = s.rbeg + s.len;
+      const int tlen = (int)(rmax1 - (s.rbeg + s.len));
+      bsq_ext_result_t r;
+      r.score = 0; r.qle = r.tle = r.gtle = 0; r.gscore = -1; r.max_off = 0;
+      for (int i = 0; i < 2; ++i) {
+        const int prev = reg.score;
+        aw1 = opt.w << i;
+        r = bsq_ksw_extend(l_query - qe, qa, tlen, ta, mat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, aw1,
+                           opt.pen_clip3, opt.zdrop, sc0, ksw);
+        reg.score = r.score;
+        if (reg.score == prev || r.max_off < (aw1 >> 1) + (aw1 >> 2)) break;
+      }
+      if (r.gscore <= 0 || r.gscore <= reg.score - opt.pen_clip3) {
+        reg.qe = qe + r.qle; reg.re = s.rbeg + s.len + r.tle; reg.truesc += reg.score - sc0;
+      } else {
+        reg.qe = l_query; reg.re = s.rbeg + s.len + r.gtle; reg.truesc += r.gscore - sc0;
+      }
+    }
+    reg.bss = (uint8_t)bsq_getbss(ix, parent, reg.rb);
+    reg.parent = (uint8_t)parent;
+    if (bsq_getbss(ix, parent, reg.re) != reg.bss) { --(*n_regs); continue; }  // crosses the strand boundary
+    int cov = 0;
+    for (int i = 0; i < n_seeds; ++i) {
+      const bsq_seed_t &t = seeds[i];
+      if (t.qbeg >= reg.qb && t.qbeg + t.len <= reg.qe && t.rbeg >= reg.rb && t.rbeg + t.len <= reg.re) cov += t.len;
+    }
+    reg.seedcov = cov;
+    reg.w = aw0 > aw1 ? aw0 : aw1;
+    reg.seedlen0 = s.len;
+    reg.frac_rep = frac_rep;
+  }
+}
+
+// mem_chain2region for one task.  Returns the number of regions written to regs[].
+BSQ_HD int bsq_chain2region(const bsq_devopt_t &opt, const bsq_devidx_t &ix, int parent, int l_query, const uint8_t *query,
+                            const bsq_chain_t *chains, int n_chains, const bsq_seed_t *seeds, float frac_rep,
+                            uint64_t *srt, bsq_ksw_scratch_t &ksw, bsq_reg_t *regs) {
+  int n_regs = 0;
+  const int64_t l_pac = ix.l_pac;
+  for (int ci = 0; ci < n_chains; ++ci) {
+    const bsq_chain_t &c = chains[ci];
+    if (c.n_seeds == 0) continue;
+    const bsq_seed_t *cs = seeds + c.seed_off;
+    // mem_chain_reference_span
+    int64_t rmax0 = l_pac << 1, rmax1 = 0;
+    for (int i = 0; i < c.n_seeds; ++i) {
+      const bsq_seed_t &s = cs[i];
+      int64_t b = s.rbeg - (s.qbeg + bsq_cal_max_gap(opt, s.qbeg));
+      int64_t e = s.rbeg + s.len + ((l_query - s.qbeg - s.len) + bsq_cal_max_gap(opt, l_query - s.qbeg - s.len));
+      rmax0 = rmax0 < b ? rmax0 : b;
+      rmax1 = rmax1 > e ? rmax1 : e;
+    }
+    rmax0 = rmax0 > 0 ? rmax0 : 0;
+    rmax1 = rmax1 < l_pac << 1 ? rmax1 : l_pac << 1;
+    if (rmax0 < l_pac && l_pac < rmax1) {
+      if (cs[0].rbeg < l_pac) rmax1 = l_pac; else rmax0 = l_pac;
+    }
+    // bns_fetch_seq: clip to the contig (and strand) that holds the first seed
+    int is_rev;
+    const int rid = bsq_pos2rid(ix, bsq_depos(ix, cs[0].rbeg, &is_rev));
+    int64_t far_beg = ix.ann_offset[rid], far_end = far_beg + ix.ann_len[rid];
+    if (is_rev) {
+      int64_t t = far_beg;
+      far_beg = (l_pac << 1) - far_end;
+      far_end = (l_pac << 1) - t;
+    }
+    rmax0 = rmax0 > far_beg ? rmax0 : far_beg;
+    rmax1 = rmax1 < far_end ? rmax1 : far_end;
+    const int n0 = n_regs;
+    bsq_chain2region1(opt, ix, rmax0, rmax1, rid, l_query, query, cs, c.n_seeds, parent, frac_rep, srt, ksw, regs, &n_regs);
+    if (n_regs == n0 && c.n_extra > 0)
+      bsq_chain2region1(opt, ix, rmax0, rmax1, rid, l_query, query, cs + c.n_seeds, c.n_extra, parent, frac_rep, srt, ksw,
+                        regs, &n_regs);
+  }
+  return n_regs;
+}

@@ -1,0 +1,135 @@
+/* bsq.h -- C ABI of libbsq.so, the B200 (sm_100a) implementation of BISCUIT's two data-parallel
+ * hot paths (bisulfite seed-and-extend alignment, methylation pileup).
+ *
+ * Plain C: pointers and sizes only.  All buffers named `h_*` or documented as "host" are HOST
+ * memory owned by the caller; the library stages them to the GPU, runs the kernels and copies the
+ * results back.  Every function returns 0 on success or a negative BSQ_E* code; nothing in the
+ * library calls exit().  There is NO CPU implementation behind these entry points: if no CUDA
+ * device is usable they return BSQ_ENODEV.
+ *
+ * The entry points replace these interfaces of the reference (zhou-lab/biscuit @ b682768):
+ *   bsq_index_upload        <- bwa_idx_load_from_disk()            lib/aln/bwa.c:525-554 (device copy of bwaidx_t)
+ *   bsq_align_phase1        <- bis_worker1() body up to mem_merge_regions   lib/aln/bwamem.c:311-375
+ *                              (= mem_align1_core x2: mem_chain, mem_chain_flt, mem_chain2region)
+ *   bsq_collect_intv        <- mem_collect_intv()                  lib/aln/memchain.c:50-106
+ *                              (bwt_smem1a lib/aln/bwt.c:307, bwt_seed_strategy1 bwt.c:376)
+ *   bsq_occ4                <- bwt_occ4()                          lib/aln/bwt.c:173-200
+ *   bsq_sa_lookup           <- bwt_sa()                            lib/aln/bwt.c:87-97
+ *   bsq_extend_batch        <- ksw_extend2()                       lib/aln/ksw.c:380-479
+ *   bsq_plp_*               <- process_func() hot loop + plp_getcnts  src/pileup.c:707-831, :372-387
+ */
+#ifndef BSQ_H
+#define BSQ_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSQ_OK 0
+#define BSQ_ENODEV (-1)    /* no usable CUDA device / CUDA runtime error */
+#define BSQ_EINVAL (-2)    /* bad argument (e.g. read longer than BSQ_MAX_READ_LEN) */
+#define BSQ_EOVERFLOW (-3) /* a per-read capacity was exceeded; nothing was silently dropped */
+#define BSQ_ENOMEM (-4)
+
+#define BSQ_MAX_READ_LEN 256
+#define BSQ_MAX_INTV 160
+
+/* same layout as the reference's bwtintv_t (lib/aln/bwt.h:80-82) */
+typedef struct { uint64_t x[3], info; } bsq_intv;
+
+/* phase-1 alignment region: the fields of mem_alnreg_t (lib/aln/mem_alnreg.h:34-66) that are
+ * set by mem_chain2region1 (lib/aln/memchain.c:742-871) */
+typedef struct {
+  int64_t rb, re;
+  int32_t qb, qe;
+  int32_t rid, score, truesc, w;
+  int32_t seedcov, seedlen0;
+  float frac_rep;
+  uint8_t bss, parent, pad_[2];
+} bsq_reg;
+
+/* alignment options that reach the device: subset of mem_opt_t (lib/aln/bwamem.h:54-124),
+ * defaults from mem_opt_init (lib/aln/bwamem.c:77-128) via bsq_opt_default() */
+typedef struct {
+  int32_t a, b, o_del, e_del, o_ins, e_ins, pen_clip5, pen_clip3, w, zdrop;
+  int32_t min_seed_len, split_width, max_occ, max_chain_gap, min_chain_weight, max_chain_extend;
+  int32_t max_mem_intv, split_len, self_ovlp, bsstrand;
+  float mask_level, drop_ratio;
+  int8_t ctmat[25], gamat[25];
+  int8_t pad_[2];
+} bsq_opt;
+
+/* host view of a loaded index (bwaidx_t, lib/aln/bwa.h:42-50).  which: 0 = daughter (G>A,
+ * <prefix>.dau.*), 1 = parent (C>T, <prefix>.par.*) as in bwa.c:535-536 */
+typedef struct {
+  const uint32_t *bwt[2];  /* body of the .bwt file after the 40-byte header */
+  uint64_t bwt_words[2];   /* number of u32 words in bwt[] */
+  uint64_t primary[2];
+  uint64_t L2[2][5];       /* L2[.][0] = 0 */
+  uint64_t seq_len;        /* 2 * l_pac */
+  const uint64_t *sa[2];   /* n_sa entries, sa[0] = (uint64_t)-1 */
+  uint64_t n_sa[2];
+  int32_t sa_intv[2];
+  const uint8_t *pac;      /* .bis.pac body, (l_pac+3)/4 bytes */
+  int64_t l_pac;
+  int32_t n_seqs;
+  const int64_t *ann_offset;
+  const int32_t *ann_len;
+  const int32_t *ann_is_alt;
+} bsq_index_desc;
+
+typedef struct bsq_index bsq_index; /* device-resident index, opaque */
+
+void bsq_opt_default(bsq_opt *opt);
+const char *bsq_strerror(int code);
+const char *bsq_last_error(void); /* text of the last CUDA error seen by this thread */
+
+int bsq_index_upload(const bsq_index_desc *desc, int device, bsq_index **out);
+void bsq_index_free(bsq_index *idx);
+
+/* ---- kernel-level entry points (SoA, host buffers) ---- */
+
+/* cnt[4*i..4*i+3] = ranks of A,C,G,T up to BWT position k[i] in index `which` */
+int bsq_occ4(const bsq_index *idx, int which, int64_t n, const uint64_t *k, uint64_t *cnt);
+
+/* pos[i] = text position of BWT rank k[i] */
+int bsq_sa_lookup(const bsq_index *idx, int which, int64_t n, const uint64_t *k, uint64_t *pos);
+
+/* SMEM seeding of n_tasks (read, conversion) tasks.  seqs: UNCONVERTED nt4 reads, task t at
+ * seqs + t*stride, lens[t] bases; parent[t] selects the conversion (1: C>T vs parent index,
+ * 0: G>A vs daughter index).  out: n_tasks * BSQ_MAX_INTV intervals; n_out[t] = count. */
+int bsq_collect_intv(const bsq_index *idx, const bsq_opt *opt, int64_t n_tasks, const uint8_t *seqs, int32_t stride,
+                     const int32_t *lens, const uint8_t *parent, bsq_intv *out, int32_t *n_out);
+
+/* Batched ksw_extend2.  Job j: query = qbuf + qoff[j] (qlen[j] nt4 codes), target = tbuf + toff[j]
+ * (tlen[j] codes), matrix = is_parent[j] ? opt->ctmat : opt->gamat, band w[j], initial score h0[j],
+ * end bonus = opt->pen_clip5.  out[6*j..] = {score, qle, tle, gtle, gscore, max_off}. */
+int bsq_extend_batch(const bsq_opt *opt, int64_t n_jobs, const uint8_t *qbuf, const int64_t *qoff, const int32_t *qlen,
+                     const uint8_t *tbuf, const int64_t *toff, const int32_t *tlen, const uint8_t *is_parent,
+                     const int32_t *w, const int32_t *h0, int32_t *out);
+
+/* ---- phase 1 of the aligner for a batch of reads ---- */
+
+typedef struct bsq_aligner bsq_aligner; /* per-GPU context: streams + reusable device buffers */
+
+int bsq_aligner_create(const bsq_index *idx, const bsq_opt *opt, bsq_aligner **out);
+void bsq_aligner_destroy(bsq_aligner *al);
+
+/* Seed -> chain -> filter -> extend for n_tasks (read, conversion) tasks (same task layout as
+ * bsq_collect_intv).  Regions of task t are written to regs[reg_off[t] .. reg_off[t+1]) in the
+ * order mem_chain2region (lib/aln/memchain.c:873-904) produces them.  `regs` is malloc()ed by the
+ * library (caller frees with bsq_free); reg_off has n_tasks+1 entries (caller-allocated). */
+int bsq_align_phase1(bsq_aligner *al, int64_t n_tasks, const uint8_t *seqs, int32_t stride, const int32_t *lens,
+                     const uint8_t *parent, bsq_reg **regs, int64_t *reg_off);
+void bsq_free(void *p);
+
+/* counters of the last bsq_align_phase1 call (for the roofline arithmetic in bench.py):
+ * c[0]=tasks c[1]=intervals c[2]=seeds(SA lookups) c[3]=chains kept c[4]=regions
+ * c[5..8] = device ms of the seed / sa / chain / extend kernels  (as integer microseconds) */
+int bsq_aligner_counters(const bsq_aligner *al, int64_t *c, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,168 @@
+// TEST-ONLY host emulation of the bsq.h ABI.
+//
+// The per-task device code in biscuit_b200/csrc/bsq_*.h is plain C++ (BSQ_HD); this file compiles
+// it with g++ and drives it with sequential loops so the algorithmic logic can be checked against
+// the oracle on a machine without a GPU (`pytest -m "not gpu"`).  It is NOT part of the product:
+// nothing under biscuit_b200/ loads it, and libbsq.so has no host execution path.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "../../include/bsq.h"
+#include "../../biscuit_b200/csrc/bsq_task.h"
+
+static_assert(sizeof(bsq_intv) == sizeof(bsq_intv_t), "abi");
+static_assert(sizeof(bsq_reg) == sizeof(bsq_reg_t), "abi");
+static_assert(sizeof(bsq_opt) == sizeof(bsq_devopt_t), "abi");
+
+struct bsq_index { bsq_devidx_t d; };
+struct bsq_aligner { const bsq_index *idx; bsq_devopt_t opt; int64_t counters[16]; };
+
+#include "../../biscuit_b200/csrc/bsq_opt_default.h"
+
+extern "C" {
+const char *bsq_strerror(int code) {
+  switch (code) { case 0: return "ok"; case BSQ_ENODEV: return "no device"; case BSQ_EINVAL: return "invalid argument";
+    case BSQ_EOVERFLOW: return "capacity overflow"; case BSQ_ENOMEM: return "out of memory"; }
+  return "unknown";
+}
+const char *bsq_last_error(void) { return "hostemu"; }
+
+int bsq_index_upload(const bsq_index_desc *h, int device, bsq_index **out) {
+  (void)device;
+  bsq_index *ix = new bsq_index();
+  memset(&ix->d, 0, sizeof ix->d);
+  for (int w = 0; w < 2; ++w) {
+    bsq_fm_t &f = ix->d.fm[w];
+    f.blocks = h->bwt[w]; f.sa = h->sa[w]; f.primary = h->primary[w]; f.seq_len = h->seq_len; f.sa_intv = h->sa_intv[w];
+    for (int i = 0; i < 5; ++i) f.L2[i] = h->L2[w][i];
+  }
+  ix->d.pac = h->pac; ix->d.l_pac = h->l_pac; ix->d.n_seqs = h->n_seqs;
+  ix->d.ann_offset = h->ann_offset; ix->d.ann_len = h->ann_len; ix->d.ann_is_alt = h->ann_is_alt;
+  *out = ix;
+  return 0;
+}
+void bsq_index_free(bsq_index *ix) { delete ix; }
+
+int bsq_occ4(const bsq_index *ix, int which, int64_t n, const uint64_t *k, uint64_t *cnt) {
+  for (int64_t i = 0; i < n; ++i) bsq_occ4(ix->d.fm[which], k[i], cnt + 4 * i);
+  return 0;
+}
+int bsq_sa_lookup(const bsq_index *ix, int which, int64_t n, const uint64_t *k, uint64_t *pos) {
+  for (int64_t i = 0; i < n; ++i) pos[i] = bsq_sa(ix->d.fm[which], k[i]);
+  return 0;
+}
+int bsq_collect_intv(const bsq_index *ix, const bsq_opt *opt_, int64_t n_tasks, const uint8_t *seqs, int32_t stride,
+                     const int32_t *lens, const uint8_t *parent, bsq_intv *out, int32_t *n_out) {
+  bsq_devopt_t opt; memcpy(&opt, opt_, sizeof opt);
+  bsq_seed_scratch_t *scr = new bsq_seed_scratch_t();
+  int rc = 0;
+  for (int64_t t = 0; t < n_tasks; ++t) {
+    if (lens[t] > BSQ_MAX_READ_LEN) { rc = BSQ_EINVAL; break; }
+    int32_t n_sa;
+    int n = bsq_task_seed(opt, ix->d, seqs + t * stride, lens[t], parent[t], false, *scr, (bsq_intv_t *)out + t * BSQ_MAX_INTV, &n_sa);
+    if (n < 0) { rc = BSQ_EOVERFLOW; break; }
+    n_out[t] = n;
+  }
+  delete scr;
+  return rc;
+}
+int bsq_extend_batch(const bsq_opt *opt_, int64_t n_jobs, const uint8_t *qbuf, const int64_t *qoff, const int32_t *qlen,
+                     const uint8_t *tbuf, const int64_t *toff, const int32_t *tlen, const uint8_t *is_parent,
+                     const int32_t *w, const int32_t *h0, int32_t *out) {
+  bsq_devopt_t opt; memcpy(&opt, opt_, sizeof opt);
+  bsq_ksw_scratch_t scr;
+  for (int64_t j = 0; j < n_jobs; ++j) {
+    if (qlen[j] > BSQ_MAX_READ_LEN) return BSQ_EINVAL;
+    struct G { const uint8_t *p; int operator()(int i) const { return p[i]; } } qa{qbuf + qoff[j]}, ta{tbuf + toff[j]};
+    bsq_ext_result_t r = bsq_ksw_extend(qlen[j], qa, tlen[j], ta, is_parent[j] ? opt.ctmat : opt.gamat, opt.o_del, opt.e_del,
+                                        opt.o_ins, opt.e_ins, w[j], opt.pen_clip5, opt.zdrop, h0[j], scr);
+    memcpy(out + 6 * j, &r, 24);
+  }
+  return 0;
+}
+
+int bsq_aligner_create(const bsq_index *ix, const bsq_opt *opt, bsq_aligner **out) {
+  bsq_aligner *a = new bsq_aligner();
+  a->idx = ix; memcpy(&a->opt, opt, sizeof a->opt); memset(a->counters, 0, sizeof a->counters);
+  *out = a;
+  return 0;
+}
+void bsq_aligner_destroy(bsq_aligner *a) { delete a; }
+void bsq_free(void *p) { free(p); }
+int bsq_aligner_counters(const bsq_aligner *a, int64_t *c, int n) { for (int i = 0; i < n && i < 16; ++i) c[i] = a->counters[i]; return 0; }
+
+int bsq_align_phase1(bsq_aligner *al, int64_t n_tasks, const uint8_t *seqs, int32_t stride, const int32_t *lens,
+                     const uint8_t *parent, bsq_reg **regs_out, int64_t *reg_off) {
+  const bsq_devopt_t &opt = al->opt;
+  const bsq_devidx_t &ix = al->idx->d;
+  std::vector<bsq_reg_t> all;
+  bsq_seed_scratch_t *scr = new bsq_seed_scratch_t();
+  bsq_ksw_scratch_t *ksw = new bsq_ksw_scratch_t();
+  std::vector<bsq_intv_t> intv(BSQ_MAX_INTV);
+  int rc = 0;
+  memset(al->counters, 0, sizeof al->counters);
+  for (int64_t t = 0; t < n_tasks && rc == 0; ++t) {
+    reg_off[t] = (int64_t)all.size();
+    if (lens[t] > BSQ_MAX_READ_LEN) { rc = BSQ_EINVAL; break; }
+    const uint8_t *seq = seqs + t * stride;
+    int32_t n_sa;
+    int n = bsq_task_seed(opt, ix, seq, lens[t], parent[t], true, *scr, intv.data(), &n_sa);
+    if (n < 0) { rc = BSQ_EOVERFLOW; break; }
+    std::vector<uint64_t> ranks(n_sa + 1), pos(n_sa + 1);
+    bsq_task_expand(opt, intv.data(), n, ranks.data());
+    for (int i = 0; i < n_sa; ++i) pos[i] = bsq_sa(ix.fm[parent[t]], ranks[i]);
+    const int cap = n_sa + 64;
+    std::vector<bsq_snode_t> sn(cap); std::vector<bsq_wchain_t> wc(cap); std::vector<bsq_bnode_t> bn(cap + 2);
+    std::vector<int32_t> ord(cap); std::vector<bsq_chain_t> och(cap); std::vector<bsq_seed_t> osd(cap);
+    bsq_chain_ws_t ws; ws.cap = cap; ws.snodes = sn.data(); ws.chains = wc.data(); ws.bnodes = bn.data(); ws.order = ord.data();
+    bsq_chain_result_t cr = bsq_chain_task(opt, ix, parent[t], lens[t], intv.data(), n, pos.data(), ws, och.data(), osd.data());
+    if (cr.status) { rc = BSQ_EOVERFLOW; break; }
+    std::vector<uint64_t> srt(cap); std::vector<bsq_reg_t> rg(cap);
+    int nr = bsq_chain2region(opt, ix, parent[t], lens[t], seq, och.data(), cr.n_chains, osd.data(), cr.frac_rep, srt.data(), *ksw, rg.data());
+    all.insert(all.end(), rg.begin(), rg.begin() + nr);
+    al->counters[0]++; al->counters[1] += n; al->counters[2] += n_sa; al->counters[3] += cr.n_chains; al->counters[4] += nr;
+  }
+  reg_off[n_tasks] = (int64_t)all.size();
+  delete scr; delete ksw;
+  if (rc) return rc;
+  *regs_out = (bsq_reg *)malloc(all.size() * sizeof(bsq_reg) + 8);
+  memcpy(*regs_out, all.data(), all.size() * sizeof(bsq_reg));
+  return 0;
+}
+
+// test hook: chains after mem_chain + mem_chain_flt for one task, flattened like oracle's refp_chain
+int64_t hostemu_chain(const bsq_index *ixp, const bsq_opt *opt_, int parent, int len, const uint8_t *seq, int *n_chains,
+                      float *frac_rep, int64_t *out, int64_t cap_out) {
+  bsq_devopt_t opt; memcpy(&opt, opt_, sizeof opt);
+  const bsq_devidx_t &ix = ixp->d;
+  bsq_seed_scratch_t *scr = new bsq_seed_scratch_t();
+  std::vector<bsq_intv_t> intv(BSQ_MAX_INTV);
+  int32_t n_sa;
+  int n = bsq_task_seed(opt, ix, seq, len, parent, true, *scr, intv.data(), &n_sa);
+  delete scr;
+  if (n < 0) return -1;
+  std::vector<uint64_t> ranks(n_sa + 1), pos(n_sa + 1);
+  bsq_task_expand(opt, intv.data(), n, ranks.data());
+  for (int i = 0; i < n_sa; ++i) pos[i] = bsq_sa(ix.fm[parent], ranks[i]);
+  const int cap = n_sa + 64;
+  std::vector<bsq_snode_t> sn(cap); std::vector<bsq_wchain_t> wc(cap); std::vector<bsq_bnode_t> bn(cap + 2);
+  std::vector<int32_t> ord(cap); std::vector<bsq_chain_t> och(cap); std::vector<bsq_seed_t> osd(cap);
+  bsq_chain_ws_t ws; ws.cap = cap; ws.snodes = sn.data(); ws.chains = wc.data(); ws.bnodes = bn.data(); ws.order = ord.data();
+  bsq_chain_result_t cr = bsq_chain_task(opt, ix, parent, len, intv.data(), n, pos.data(), ws, och.data(), osd.data());
+  if (cr.status) return -1;
+  *n_chains = cr.n_chains; *frac_rep = cr.frac_rep;
+  int64_t o = 0;
+  for (int i = 0; i < cr.n_chains; ++i) {
+    const bsq_chain_t &c = och[i];
+    if (o + 8 + 4 * (int64_t)(c.n_seeds + c.n_extra) > cap_out) return -1;
+    out[o++] = c.pos; out[o++] = c.rid; out[o++] = c.w; out[o++] = c.kept; out[o++] = c.first; out[o++] = c.is_alt;
+    out[o++] = c.n_seeds; out[o++] = c.n_extra;
+    for (int j = 0; j < c.n_seeds + c.n_extra; ++j) {
+      const bsq_seed_t &s = osd[c.seed_off + j];
+      out[o++] = s.rbeg; out[o++] = s.qbeg; out[o++] = s.len; out[o++] = s.len;
+    }
+  }
+  return o;
+}
+}  // extern "C"
