@@ -1,0 +1,479 @@
+// libbsq.so -- aligner half: CUDA kernels (sm_100a) and the C ABI of include/bsq.h.
+//
+// Phase 1 of `biscuit align` for a batch of (read, conversion) tasks runs as five kernels:
+//   k_seed    one thread per task      SMEM seeding over the two FM-indices (random 64-B gathers)
+//   k_expand  one thread per task      BWT ranks of the occurrences chaining will visit
+//   k_sa      one thread per rank      sampled-SA lookup (LF walk, random 64-B gathers)
+//   k_chain   one thread per task      B-tree chaining + chain filter
+//   k_region  one thread per task      banded extension of the chained seeds -> regions
+// Buffers between the stages are sized exactly from device-side prefix sums, so nothing is
+// truncated; capacity violations raise BSQ_EOVERFLOW.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <cub/device/device_scan.cuh>
+
+#include "../../include/bsq.h"
+#include "bsq_task.h"
+#include "bsq_opt_default.h"
+
+static_assert(sizeof(bsq_intv) == sizeof(bsq_intv_t), "abi");
+static_assert(sizeof(bsq_reg) == sizeof(bsq_reg_t), "abi");
+static_assert(sizeof(bsq_opt) == sizeof(bsq_devopt_t), "abi");
+
+#define BSQ_TAIL_SLACK 64  // extra seed slots per task for the k >= max_occ tail (memchain.c:325-326)
+
+static thread_local char g_err[512] = "";
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      snprintf(g_err, sizeof g_err, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      return e_ == cudaErrorMemoryAllocation ? BSQ_ENOMEM : BSQ_ENODEV;                            \
+    }                                                                                              \
+  } while (0)
+
+struct bsq_index {
+  bsq_devidx_t d;  // device pointers
+  int device;
+  void *allocs[16];
+  int n_allocs;
+};
+
+// grow-only device buffer
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      snprintf(g_err, sizeof g_err, "cudaMalloc(%zu): %s", want, cudaGetErrorString(e));
+      return BSQ_ENOMEM;
+    }
+    cap = want;
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct bsq_aligner {
+  const bsq_index *idx;
+  bsq_devopt_t opt;
+  cudaStream_t stream;
+  cudaEvent_t ev[8];
+  DevBuf seqs, lens, parent, intv, n_intv, n_sa, sa_off, ranks, pos, status;
+  DevBuf snodes, wchains, bnodes, order, ochains, oseeds, n_chains, frac_rep, srt, regs_tmp, n_regs, reg_off, regs;
+  DevBuf cub_tmp, scalars;
+  int64_t counters[16];
+};
+
+// ------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(128) k_seed(bsq_devopt_t opt, bsq_devidx_t ix, int64_t n_tasks, const uint8_t *seqs, int stride,
+                                              const int32_t *lens, const uint8_t *parent, int pipeline, bsq_intv_t *intv,
+                                              int32_t *n_intv, int32_t *n_sa, int32_t *status) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tasks) return;
+  bsq_seed_scratch_t scr;
+  int32_t nsa = 0;
+  int n = bsq_task_seed(opt, ix, seqs + t * stride, lens[t], parent[t], pipeline != 0, scr, intv + t * BSQ_MAX_INTV, &nsa);
+  if (n < 0) { atomicOr(status, 1); n = 0; nsa = 0; }
+  n_intv[t] = n;
+  n_sa[t] = nsa;
+}
+
+__global__ void k_expand(bsq_devopt_t opt, int64_t n_tasks, const bsq_intv_t *intv, const int32_t *n_intv, const uint8_t *parent,
+                         const int64_t *sa_off, uint64_t *ranks) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tasks) return;
+  const bsq_intv_t *v = intv + t * BSQ_MAX_INTV;
+  const uint64_t tag = (uint64_t)(parent[t] != 0) << 63;
+  int64_t o = sa_off[t];
+  const int n = n_intv[t];
+  for (int i = 0; i < n; ++i) {
+    uint64_t m = v[i].x[2] < (uint64_t)(uint32_t)opt.max_occ ? v[i].x[2] : (uint64_t)(uint32_t)opt.max_occ;
+    for (uint64_t k = 0; k < m; ++k) ranks[o++] = (v[i].x[0] + k) | tag;
+  }
+}
+
+__global__ void k_sa(bsq_devidx_t ix, int64_t n, const uint64_t *ranks, uint64_t *pos) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t r = ranks[i];
+  pos[i] = bsq_sa(ix.fm[r >> 63], r & ~(1ull << 63));
+}
+
+__global__ void k_sa_plain(bsq_devidx_t ix, int which, int64_t n, const uint64_t *ranks, uint64_t *pos) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  pos[i] = bsq_sa(ix.fm[which], ranks[i]);
+}
+
+__global__ void k_occ4(bsq_devidx_t ix, int which, int64_t n, const uint64_t *k, uint64_t *cnt) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t c[4];
+  bsq_occ4(ix.fm[which], k[i], c);
+  cnt[4 * i] = c[0]; cnt[4 * i + 1] = c[1]; cnt[4 * i + 2] = c[2]; cnt[4 * i + 3] = c[3];
+}
+
+// per-task workspace offset: sa_off[t] + t * BSQ_TAIL_SLACK entries
+__device__ __forceinline__ int64_t ws_off(const int64_t *sa_off, int64_t t) { return sa_off[t] + t * BSQ_TAIL_SLACK; }
+
+__global__ void __launch_bounds__(128) k_chain(bsq_devopt_t opt, bsq_devidx_t ix, int64_t n_tasks, const int32_t *lens,
+                                               const uint8_t *parent, const bsq_intv_t *intv, const int32_t *n_intv,
+                                               const int64_t *sa_off, const uint64_t *pos, bsq_snode_t *snodes,
+                                               bsq_wchain_t *wchains, bsq_bnode_t *bnodes, int32_t *order, bsq_chain_t *ochains,
+                                               bsq_seed_t *oseeds, int32_t *n_chains, float *frac_rep, int32_t *status) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tasks) return;
+  const int64_t wo = ws_off(sa_off, t);
+  bsq_chain_ws_t ws;
+  ws.cap = (int32_t)(sa_off[t + 1] - sa_off[t]) + BSQ_TAIL_SLACK;
+  ws.snodes = snodes + wo; ws.chains = wchains + wo; ws.bnodes = bnodes + wo + 2 * t; ws.order = order + wo;
+  bsq_chain_result_t r = bsq_chain_task(opt, ix, parent[t], lens[t], intv + t * BSQ_MAX_INTV, n_intv[t], pos + sa_off[t], ws,
+                                        ochains + wo, oseeds + wo);
+  if (r.status) { atomicOr(status, 2); r.n_chains = 0; }
+  n_chains[t] = r.n_chains;
+  frac_rep[t] = r.frac_rep;
+}
+
+__global__ void __launch_bounds__(128) k_region(bsq_devopt_t opt, bsq_devidx_t ix, int64_t n_tasks, const uint8_t *seqs, int stride,
+                                                const int32_t *lens, const uint8_t *parent, const int64_t *sa_off,
+                                                const bsq_chain_t *ochains, const bsq_seed_t *oseeds, const int32_t *n_chains,
+                                                const float *frac_rep, uint64_t *srt, bsq_reg_t *regs_tmp, int32_t *n_regs) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tasks) return;
+  const int64_t wo = ws_off(sa_off, t);
+  bsq_ksw_scratch_t ksw;
+  n_regs[t] = bsq_chain2region(opt, ix, parent[t], lens[t], seqs + t * stride, ochains + wo, n_chains[t], oseeds + wo,
+                               frac_rep[t], srt + wo, ksw, regs_tmp + wo);
+}
+
+__global__ void k_compact_regs(int64_t n_tasks, const int64_t *sa_off, const int32_t *n_regs, const int64_t *reg_off,
+                               const bsq_reg_t *regs_tmp, bsq_reg_t *regs) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tasks) return;
+  const bsq_reg_t *src = regs_tmp + ws_off(sa_off, t);
+  bsq_reg_t *dst = regs + reg_off[t];
+  for (int i = 0; i < n_regs[t]; ++i) dst[i] = src[i];
+}
+
+struct PtrGet { const uint8_t *p; __device__ int operator()(int i) const { return p[i]; } };
+
+__global__ void __launch_bounds__(128) k_extend(bsq_devopt_t opt, int64_t n_jobs, const uint8_t *qbuf, const int64_t *qoff,
+                                                const int32_t *qlen, const uint8_t *tbuf, const int64_t *toff, const int32_t *tlen,
+                                                const uint8_t *is_parent, const int32_t *w, const int32_t *h0, int32_t *out) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_jobs) return;
+  bsq_ksw_scratch_t scr;
+  PtrGet qa{qbuf + qoff[j]}, ta{tbuf + toff[j]};
+  bsq_ext_result_t r = bsq_ksw_extend(qlen[j], qa, tlen[j], ta, is_parent[j] ? opt.ctmat : opt.gamat, opt.o_del, opt.e_del,
+                                      opt.o_ins, opt.e_ins, w[j], opt.pen_clip5, opt.zdrop, h0[j], scr);
+  int32_t *o = out + 6 * j;
+  o[0] = r.score; o[1] = r.qle; o[2] = r.tle; o[3] = r.gtle; o[4] = r.gscore; o[5] = r.max_off;
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+
+static inline unsigned nblk(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+extern "C" {
+
+const char *bsq_strerror(int code) {
+  switch (code) {
+    case BSQ_OK: return "ok";
+    case BSQ_ENODEV: return "CUDA device/runtime error";
+    case BSQ_EINVAL: return "invalid argument";
+    case BSQ_EOVERFLOW: return "per-read capacity exceeded";
+    case BSQ_ENOMEM: return "out of device memory";
+  }
+  return "unknown error";
+}
+
+const char *bsq_last_error(void) { return g_err; }
+
+static int upload_array(bsq_index *ix, const void *src, size_t bytes, const void **dst) {
+  void *p = nullptr;
+  CK(cudaMalloc(&p, bytes ? bytes : 16));
+  ix->allocs[ix->n_allocs++] = p;
+  if (bytes) CK(cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice));
+  *dst = p;
+  return 0;
+}
+
+int bsq_index_upload(const bsq_index_desc *h, int device, bsq_index **out) {
+  if (!h || !out) return BSQ_EINVAL;
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) { snprintf(g_err, sizeof g_err, "device %d of %d", device, ndev); return BSQ_ENODEV; }
+  CK(cudaSetDevice(device));
+  bsq_index *ix = (bsq_index *)calloc(1, sizeof(bsq_index));
+  ix->device = device;
+  int rc = 0;
+  for (int w = 0; w < 2 && !rc; ++w) {
+    bsq_fm_t &f = ix->d.fm[w];
+    f.primary = h->primary[w]; f.seq_len = h->seq_len; f.sa_intv = h->sa_intv[w];
+    for (int i = 0; i < 5; ++i) f.L2[i] = h->L2[w][i];
+    rc = upload_array(ix, h->bwt[w], h->bwt_words[w] * 4, (const void **)&f.blocks);
+    if (!rc) rc = upload_array(ix, h->sa[w], h->n_sa[w] * 8, (const void **)&f.sa);
+  }
+  if (!rc) rc = upload_array(ix, h->pac, (size_t)(h->l_pac / 4 + 1), (const void **)&ix->d.pac);
+  if (!rc) rc = upload_array(ix, h->ann_offset, (size_t)h->n_seqs * 8, (const void **)&ix->d.ann_offset);
+  if (!rc) rc = upload_array(ix, h->ann_len, (size_t)h->n_seqs * 4, (const void **)&ix->d.ann_len);
+  if (!rc) rc = upload_array(ix, h->ann_is_alt, (size_t)h->n_seqs * 4, (const void **)&ix->d.ann_is_alt);
+  ix->d.l_pac = h->l_pac; ix->d.n_seqs = h->n_seqs;
+  if (rc) { bsq_index_free(ix); return rc; }
+  *out = ix;
+  return 0;
+}
+
+void bsq_index_free(bsq_index *ix) {
+  if (!ix) return;
+  for (int i = 0; i < ix->n_allocs; ++i) cudaFree(ix->allocs[i]);
+  free(ix);
+}
+
+int bsq_occ4(const bsq_index *ix, int which, int64_t n, const uint64_t *k, uint64_t *cnt) {
+  if (!ix || which < 0 || which > 1 || n < 0) return BSQ_EINVAL;
+  if (n == 0) return 0;
+  CK(cudaSetDevice(ix->device));
+  uint64_t *dk = nullptr, *dc = nullptr;
+  CK(cudaMalloc(&dk, n * 8)); CK(cudaMalloc(&dc, n * 32));
+  CK(cudaMemcpy(dk, k, n * 8, cudaMemcpyHostToDevice));
+  k_occ4<<<nblk(n, 256), 256>>>(ix->d, which, n, dk, dc);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(cnt, dc, n * 32, cudaMemcpyDeviceToHost));
+  cudaFree(dk); cudaFree(dc);
+  return 0;
+}
+
+int bsq_sa_lookup(const bsq_index *ix, int which, int64_t n, const uint64_t *k, uint64_t *pos) {
+  if (!ix || which < 0 || which > 1 || n < 0) return BSQ_EINVAL;
+  if (n == 0) return 0;
+  CK(cudaSetDevice(ix->device));
+  uint64_t *dk = nullptr, *dp = nullptr;
+  CK(cudaMalloc(&dk, n * 8)); CK(cudaMalloc(&dp, n * 8));
+  CK(cudaMemcpy(dk, k, n * 8, cudaMemcpyHostToDevice));
+  k_sa_plain<<<nblk(n, 256), 256>>>(ix->d, which, n, dk, dp);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(pos, dp, n * 8, cudaMemcpyDeviceToHost));
+  cudaFree(dk); cudaFree(dp);
+  return 0;
+}
+
+static int check_lens(int64_t n, const int32_t *lens, int32_t stride) {
+  for (int64_t i = 0; i < n; ++i)
+    if (lens[i] < 0 || lens[i] > BSQ_MAX_READ_LEN || lens[i] > stride) {
+      snprintf(g_err, sizeof g_err, "read %lld has length %d (max %d, stride %d)", (long long)i, lens[i], BSQ_MAX_READ_LEN, stride);
+      return BSQ_EINVAL;
+    }
+  return 0;
+}
+
+int bsq_collect_intv(const bsq_index *ix, const bsq_opt *opt_, int64_t n, const uint8_t *seqs, int32_t stride,
+                     const int32_t *lens, const uint8_t *parent, bsq_intv *out, int32_t *n_out) {
+  if (!ix || !opt_ || n < 0) return BSQ_EINVAL;
+  if (n == 0) return 0;
+  int rc = check_lens(n, lens, stride);
+  if (rc) return rc;
+  CK(cudaSetDevice(ix->device));
+  bsq_devopt_t opt; memcpy(&opt, opt_, sizeof opt);
+  uint8_t *dseq = nullptr, *dpar = nullptr; int32_t *dlen = nullptr, *dn = nullptr, *dnsa = nullptr, *dst = nullptr; bsq_intv_t *dint = nullptr;
+  CK(cudaMalloc(&dseq, n * stride)); CK(cudaMalloc(&dpar, n)); CK(cudaMalloc(&dlen, n * 4)); CK(cudaMalloc(&dn, n * 4));
+  CK(cudaMalloc(&dnsa, n * 4)); CK(cudaMalloc(&dst, 4)); CK(cudaMalloc(&dint, n * BSQ_MAX_INTV * sizeof(bsq_intv_t)));
+  CK(cudaMemcpy(dseq, seqs, n * stride, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dpar, parent, n, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dlen, lens, n * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dst, 0, 4));
+  k_seed<<<nblk(n, 128), 128>>>(opt, ix->d, n, dseq, stride, dlen, dpar, 0, dint, dn, dnsa, dst);
+  CK(cudaGetLastError());
+  int32_t st = 0;
+  CK(cudaMemcpy(&st, dst, 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(n_out, dn, n * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(out, dint, n * BSQ_MAX_INTV * sizeof(bsq_intv_t), cudaMemcpyDeviceToHost));
+  cudaFree(dseq); cudaFree(dpar); cudaFree(dlen); cudaFree(dn); cudaFree(dnsa); cudaFree(dst); cudaFree(dint);
+  return st ? BSQ_EOVERFLOW : 0;
+}
+
+int bsq_extend_batch(const bsq_opt *opt_, int64_t n, const uint8_t *qbuf, const int64_t *qoff, const int32_t *qlen,
+                     const uint8_t *tbuf, const int64_t *toff, const int32_t *tlen, const uint8_t *is_parent,
+                     const int32_t *w, const int32_t *h0, int32_t *out) {
+  if (!opt_ || n < 0) return BSQ_EINVAL;
+  if (n == 0) return 0;
+  int64_t qtot = 0, ttot = 0;
+  for (int64_t j = 0; j < n; ++j) {
+    if (qlen[j] < 0 || qlen[j] > BSQ_MAX_READ_LEN || tlen[j] < 0 || h0[j] <= 0) return BSQ_EINVAL;
+    if (qoff[j] + qlen[j] > qtot) qtot = qoff[j] + qlen[j];
+    if (toff[j] + tlen[j] > ttot) ttot = toff[j] + tlen[j];
+  }
+  bsq_devopt_t opt; memcpy(&opt, opt_, sizeof opt);
+  uint8_t *dq, *dt, *dp; int64_t *dqo, *dto; int32_t *dql, *dtl, *dw, *dh, *dout;
+  CK(cudaMalloc(&dq, qtot + 1)); CK(cudaMalloc(&dt, ttot + 1)); CK(cudaMalloc(&dp, n));
+  CK(cudaMalloc(&dqo, n * 8)); CK(cudaMalloc(&dto, n * 8));
+  CK(cudaMalloc(&dql, n * 4)); CK(cudaMalloc(&dtl, n * 4)); CK(cudaMalloc(&dw, n * 4)); CK(cudaMalloc(&dh, n * 4));
+  CK(cudaMalloc(&dout, n * 24));
+  CK(cudaMemcpy(dq, qbuf, qtot, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dt, tbuf, ttot, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dp, is_parent, n, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dqo, qoff, n * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dto, toff, n * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dql, qlen, n * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dtl, tlen, n * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dw, w, n * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dh, h0, n * 4, cudaMemcpyHostToDevice));
+  k_extend<<<nblk(n, 128), 128>>>(opt, n, dq, dqo, dql, dt, dto, dtl, dp, dw, dh, dout);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(out, dout, n * 24, cudaMemcpyDeviceToHost));
+  cudaFree(dq); cudaFree(dt); cudaFree(dp); cudaFree(dqo); cudaFree(dto); cudaFree(dql); cudaFree(dtl); cudaFree(dw);
+  cudaFree(dh); cudaFree(dout);
+  return 0;
+}
+
+int bsq_aligner_create(const bsq_index *ix, const bsq_opt *opt, bsq_aligner **out) {
+  if (!ix || !opt || !out) return BSQ_EINVAL;
+  CK(cudaSetDevice(ix->device));
+  bsq_aligner *al = new bsq_aligner();
+  al->idx = ix;
+  memcpy(&al->opt, opt, sizeof al->opt);
+  memset(al->counters, 0, sizeof al->counters);
+  CK(cudaStreamCreateWithFlags(&al->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&al->ev[i]));
+  *out = al;
+  return 0;
+}
+
+void bsq_aligner_destroy(bsq_aligner *al) {
+  if (!al) return;
+  cudaSetDevice(al->idx->device);
+  DevBuf *bufs[] = {&al->seqs, &al->lens, &al->parent, &al->intv, &al->n_intv, &al->n_sa, &al->sa_off, &al->ranks, &al->pos,
+                    &al->status, &al->snodes, &al->wchains, &al->bnodes, &al->order, &al->ochains, &al->oseeds, &al->n_chains,
+                    &al->frac_rep, &al->srt, &al->regs_tmp, &al->n_regs, &al->reg_off, &al->regs, &al->cub_tmp, &al->scalars};
+  for (DevBuf *b : bufs) b->release();
+  for (int i = 0; i < 8; ++i) cudaEventDestroy(al->ev[i]);
+  cudaStreamDestroy(al->stream);
+  delete al;
+}
+
+void bsq_free(void *p) { free(p); }
+
+int bsq_aligner_counters(const bsq_aligner *al, int64_t *c, int n) {
+  if (!al || !c) return BSQ_EINVAL;
+  for (int i = 0; i < n && i < 16; ++i) c[i] = al->counters[i];
+  return 0;
+}
+
+// exclusive prefix sum of n int32 counts into n+1 int64 offsets (offsets[n] = total)
+static int scan_counts(bsq_aligner *al, const int32_t *d_counts, int64_t *d_off, int64_t n, int64_t *total) {
+  // shift-by-one trick: run an inclusive sum into d_off+1 and zero d_off[0]
+  size_t tmp = 0;
+  CK(cub::DeviceScan::InclusiveSum(nullptr, tmp, d_counts, d_off + 1, (int)n, al->stream));
+  int rc = al->cub_tmp.reserve(tmp);
+  if (rc) return rc;
+  CK(cudaMemsetAsync(d_off, 0, 8, al->stream));
+  CK(cub::DeviceScan::InclusiveSum(al->cub_tmp.p, tmp, d_counts, d_off + 1, (int)n, al->stream));
+  CK(cudaMemcpyAsync(total, d_off + n, 8, cudaMemcpyDeviceToHost, al->stream));
+  CK(cudaStreamSynchronize(al->stream));
+  return 0;
+}
+
+// Device-resident core of phase 1: inputs already in al->seqs / lens / parent.
+static int phase1_device(bsq_aligner *al, int64_t n, int32_t stride, int64_t *total_regs) {
+  const bsq_devidx_t &ix = al->idx->d;
+  const bsq_devopt_t &opt = al->opt;
+  cudaStream_t s = al->stream;
+  int rc;
+#define RES(buf, bytes) if ((rc = al->buf.reserve(bytes))) return rc
+  RES(intv, (size_t)n * BSQ_MAX_INTV * sizeof(bsq_intv_t));
+  RES(n_intv, n * 4); RES(n_sa, n * 4); RES(sa_off, (n + 1) * 8); RES(status, 4);
+  RES(n_chains, n * 4); RES(frac_rep, n * 4); RES(n_regs, n * 4); RES(reg_off, (n + 1) * 8);
+  CK(cudaMemsetAsync(al->status.p, 0, 4, s));
+  CK(cudaEventRecord(al->ev[0], s));
+  k_seed<<<nblk(n, 128), 128, 0, s>>>(opt, ix, n, al->seqs.as<uint8_t>(), stride, al->lens.as<int32_t>(), al->parent.as<uint8_t>(), 1,
+                                       al->intv.as<bsq_intv_t>(), al->n_intv.as<int32_t>(), al->n_sa.as<int32_t>(), al->status.as<int32_t>());
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(al->ev[1], s));
+  int64_t total_sa = 0;
+  if ((rc = scan_counts(al, al->n_sa.as<int32_t>(), al->sa_off.as<int64_t>(), n, &total_sa))) return rc;
+  const int64_t pool = total_sa + n * BSQ_TAIL_SLACK;
+  RES(ranks, (total_sa + 1) * 8); RES(pos, (total_sa + 1) * 8);
+  RES(snodes, pool * sizeof(bsq_snode_t)); RES(wchains, pool * sizeof(bsq_wchain_t));
+  RES(bnodes, (pool + 2 * n) * sizeof(bsq_bnode_t)); RES(order, pool * 4);
+  RES(ochains, pool * sizeof(bsq_chain_t)); RES(oseeds, pool * sizeof(bsq_seed_t));
+  RES(srt, pool * 8); RES(regs_tmp, pool * sizeof(bsq_reg_t));
+  CK(cudaEventRecord(al->ev[2], s));
+  k_expand<<<nblk(n, 128), 128, 0, s>>>(opt, n, al->intv.as<bsq_intv_t>(), al->n_intv.as<int32_t>(), al->parent.as<uint8_t>(),
+                                         al->sa_off.as<int64_t>(), al->ranks.as<uint64_t>());
+  CK(cudaGetLastError());
+  if (total_sa > 0) {
+    k_sa<<<nblk(total_sa, 256), 256, 0, s>>>(ix, total_sa, al->ranks.as<uint64_t>(), al->pos.as<uint64_t>());
+    CK(cudaGetLastError());
+  }
+  CK(cudaEventRecord(al->ev[3], s));
+  k_chain<<<nblk(n, 128), 128, 0, s>>>(opt, ix, n, al->lens.as<int32_t>(), al->parent.as<uint8_t>(), al->intv.as<bsq_intv_t>(),
+                                        al->n_intv.as<int32_t>(), al->sa_off.as<int64_t>(), al->pos.as<uint64_t>(),
+                                        al->snodes.as<bsq_snode_t>(), al->wchains.as<bsq_wchain_t>(), al->bnodes.as<bsq_bnode_t>(),
+                                        al->order.as<int32_t>(), al->ochains.as<bsq_chain_t>(), al->oseeds.as<bsq_seed_t>(),
+                                        al->n_chains.as<int32_t>(), al->frac_rep.as<float>(), al->status.as<int32_t>());
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(al->ev[4], s));
+  k_region<<<nblk(n, 128), 128, 0, s>>>(opt, ix, n, al->seqs.as<uint8_t>(), stride, al->lens.as<int32_t>(), al->parent.as<uint8_t>(),
+                                         al->sa_off.as<int64_t>(), al->ochains.as<bsq_chain_t>(), al->oseeds.as<bsq_seed_t>(),
+                                         al->n_chains.as<int32_t>(), al->frac_rep.as<float>(), al->srt.as<uint64_t>(),
+                                         al->regs_tmp.as<bsq_reg_t>(), al->n_regs.as<int32_t>());
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(al->ev[5], s));
+  if ((rc = scan_counts(al, al->n_regs.as<int32_t>(), al->reg_off.as<int64_t>(), n, total_regs))) return rc;
+  RES(regs, (*total_regs + 1) * sizeof(bsq_reg_t));
+  k_compact_regs<<<nblk(n, 128), 128, 0, s>>>(n, al->sa_off.as<int64_t>(), al->n_regs.as<int32_t>(), al->reg_off.as<int64_t>(),
+                                               al->regs_tmp.as<bsq_reg_t>(), al->regs.as<bsq_reg_t>());
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(al->ev[6], s));
+  int32_t st = 0;
+  CK(cudaMemcpyAsync(&st, al->status.p, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+#undef RES
+  if (st) { snprintf(g_err, sizeof g_err, "device status 0x%x (1: interval list, 2: chain workspace)", st); return BSQ_EOVERFLOW; }
+  float ms[6];
+  for (int i = 0; i < 6; ++i) cudaEventElapsedTime(&ms[i], al->ev[i], al->ev[i + 1]);
+  al->counters[0] = n; al->counters[2] = total_sa; al->counters[4] = *total_regs;
+  al->counters[5] = (int64_t)(ms[0] * 1000); al->counters[6] = (int64_t)(ms[2] * 1000);
+  al->counters[7] = (int64_t)(ms[3] * 1000); al->counters[8] = (int64_t)(ms[4] * 1000);
+  al->counters[9] = (int64_t)((ms[1] + ms[5]) * 1000);
+  return 0;
+}
+
+int bsq_align_phase1(bsq_aligner *al, int64_t n, const uint8_t *seqs, int32_t stride, const int32_t *lens, const uint8_t *parent,
+                     bsq_reg **regs_out, int64_t *reg_off) {
+  if (!al || n < 0 || !regs_out || !reg_off) return BSQ_EINVAL;
+  *regs_out = nullptr;
+  if (n == 0) { reg_off[0] = 0; return 0; }
+  int rc = check_lens(n, lens, stride);
+  if (rc) return rc;
+  CK(cudaSetDevice(al->idx->device));
+  if ((rc = al->seqs.reserve((size_t)n * stride))) return rc;
+  if ((rc = al->lens.reserve(n * 4))) return rc;
+  if ((rc = al->parent.reserve(n))) return rc;
+  cudaStream_t s = al->stream;
+  CK(cudaMemcpyAsync(al->seqs.p, seqs, (size_t)n * stride, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(al->lens.p, lens, n * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(al->parent.p, parent, n, cudaMemcpyHostToDevice, s));
+  int64_t total = 0;
+  if ((rc = phase1_device(al, n, stride, &total))) return rc;
+  bsq_reg *host = (bsq_reg *)malloc((size_t)(total + 1) * sizeof(bsq_reg));
+  if (!host) return BSQ_ENOMEM;
+  CK(cudaMemcpyAsync(host, al->regs.p, (size_t)total * sizeof(bsq_reg), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(reg_off, al->reg_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  *regs_out = host;
+  return 0;
+}
+
+}  // extern "C"
