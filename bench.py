@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the bisulfite aligner hot path on synthetic 2x150 bp reads.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--ref-mb MB] [--pairs P]
+
+One "step" = one batch of P read pairs (2P reads, 4P (read, conversion) tasks) through phase 1 of
+`biscuit align` (SMEM seeding over both converted FM-indices, SA lookup, chaining, chain filter,
+banded extension -> alignment regions; reference lib/aln/bwamem.c:311-375 up to mem_merge_regions).
+The reference index is synthetic (iid ACGT, --ref-mb megabases, GRCh38-like contig count) and is
+built on the GPU by bsq_index_build in the reference's own layout.
+
+  value : reads/s, kernels only, inputs resident in HBM (CUDA-event/sync bracketed, max over ranks)
+  e2e   : reads/s through the C ABI with pinned HOST buffers: H2D of the reads + kernels + D2H of
+          the regions inside the timed region
+  --impl reference : the UNMODIFIED reference (oracle/_ref, mem_process_seqs, all host threads) on a
+          bounded sample of the same workload.  NB it runs the reference's WHOLE batch API (phase 1 +
+          pairing + SAM text), i.e. more work per read than the GPU arm currently covers; stated in
+          config.reference_scope.
+Multi-GPU: one process per GPU (torchrun), reads shard by rank with a full index replica per GPU,
+no data-path collective; NCCL only for the barrier / max-over-ranks of the timing.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+METRIC = "bisulfite_2x150_reads_per_s_aligned"
+
+
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+def gen_reference(ref_mb: float, seed: int = 7):
+    import pack
+    L = int(ref_mb * 1_000_000)
+    n_contigs = max(1, min(24, L // 2_000_000))
+    rng = np.random.default_rng(seed)
+    nt4 = rng.integers(0, 4, size=L, dtype=np.uint8)
+    base = L // n_contigs
+    lens = np.full(n_contigs, base, np.int32)
+    lens[-1] = L - base * (n_contigs - 1)
+    offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
+    names = [f"chr{i + 1}" for i in range(n_contigs)]
+    pac = pack.pack_pac(nt4)
+    return nt4, pac, names, offs, lens
+
+
+def sim_batch(nt4, names, offs, lens, n_pairs, seed):
+    """(seqs (2P,150) interleaved r1,r2 ; truth) -- same generator as the tests (tools/synth.py)."""
+    import synth
+    contigs = [(names[i], nt4[offs[i]:offs[i] + lens[i]]) for i in range(len(names))]
+    out_r = []
+    chunk = 250_000
+    for c0 in range(0, n_pairs, chunk):
+        p = synth.simulate_pairs(contigs, min(chunk, n_pairs - c0), seed=seed + c0)
+        inter = np.empty((2 * len(p["r1"]), 150), np.uint8)
+        inter[0::2] = p["r1"]
+        inter[1::2] = p["r2"]
+        out_r.append(inter)
+    return np.concatenate(out_r)
+
+
+def tasks_from_reads(reads):
+    """bis_worker1 order (bwamem.c:350-372): read1 -> parent, daughter; read2 -> daughter, parent."""
+    n = len(reads)
+    seqs = np.repeat(reads, 2, axis=0)
+    par = np.empty(2 * n, np.uint8)
+    par[0::4] = 1
+    par[1::4] = 0
+    par[2::4] = 0
+    par[3::4] = 1
+    lens = np.full(2 * n, reads.shape[1], np.int32)
+    return seqs, lens, par
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, gpu: int):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.startswith("Active"):
+                    reasons.add(name)
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def write_index_files(dx, prefix, pac, l_pac, names, offs, lens):
+    """The GPU-built index in the reference's on-disk layout (so the unmodified reference can load it)."""
+    sz = dx.sizes()
+    for which, tag in ((0, "dau"), (1, "par")):
+        bwt, sa = dx.download(which)
+        hdr = np.zeros(5, np.uint64)
+        hdr[0] = sz["primary"][which]
+        hdr[1:] = sz["L2"][which][1:]
+        with open(f"{prefix}.{tag}.bwt", "wb") as fh:
+            fh.write(hdr.tobytes())
+            fh.write(bwt.tobytes())
+        with open(f"{prefix}.{tag}.sa", "wb") as fh:
+            fh.write(hdr.tobytes())
+            fh.write(np.array([32, 2 * l_pac], np.uint64).tobytes())
+            fh.write(sa[1:].tobytes())
+    with open(f"{prefix}.bis.pac", "wb") as fh:
+        body = pac[: (l_pac >> 2) + (1 if l_pac & 3 else 0)]
+        fh.write(body.tobytes())
+        if l_pac % 4 == 0:
+            fh.write(b"\0")
+        fh.write(bytes([l_pac % 4]))
+    with open(f"{prefix}.bis.ann", "w") as fh:
+        fh.write(f"{l_pac} {len(names)} 11\n")
+        for nm, o, ln in zip(names, offs, lens):
+            fh.write(f"0 {nm} (null)\n{int(o)} {int(ln)} 0\n")
+    with open(f"{prefix}.bis.amb", "w") as fh:
+        fh.write(f"{l_pac} {len(names)} 0\n")
+
+
+def reference_run(prefix, reads, n_threads, steps, warmup):
+    """mem_process_seqs of the unmodified reference on `reads` (2P,150), timed per step."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import refprobe
+    rp = refprobe.RefProbe(prefix)
+    rp.lib.refp_process_seqs.restype = C.c_int64
+    n = len(reads)
+    lens = np.full(n, reads.shape[1], np.int32)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        rp.lib.refp_process_seqs(rp.h, C.c_int(n_threads), C.c_int64(0), C.c_int(n), reads.ctypes.data_as(C.c_void_p),
+                                 C.c_int(reads.shape[1]), lens.ctypes.data_as(C.c_void_p), None, None, C.c_int64(0))
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    rp.close()
+    return times
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-mb", type=float, default=float(os.environ.get("BSQ_BENCH_REF_MB", "3100")))
+    ap.add_argument("--pairs", type=int, default=int(os.environ.get("BSQ_BENCH_PAIRS", "500000")))
+    ap.add_argument("--cpu-pairs", type=int, default=int(os.environ.get("BSQ_BENCH_CPU_PAIRS", "20000")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference" and rank != 0:
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from biscuit_b200 import capi
+
+    if world > 1 and args.impl == "ours":
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    peak, peak_src = load_peaks()
+    ncores = os.cpu_count() or 1
+
+    t0 = time.time()
+    nt4, pac, names, offs, lens = gen_reference(args.ref_mb)
+    L = len(nt4)
+    log(f"rank {rank}: reference {L / 1e6:.0f} Mb, {len(names)} contigs generated in {time.time() - t0:.1f}s")
+    bsq = capi.load()
+    t0 = time.time()
+    dx = bsq.build_index(pac, L, names, offs, lens, device=local_rank)
+    t_index = time.time() - t0
+    log(f"rank {rank}: FM-indices built on GPU in {t_index:.1f}s (stats {dx.sizes()['stats'].tolist()})")
+    workload = f"align 2x150bp synthetic bisulfite pairs vs {L / 1e6:.0f} Mb synthetic reference (GRCh38-sized = 3100 Mb)"
+
+    if args.impl == "reference":
+        import tempfile
+        reads = sim_batch(nt4, names, offs, lens, args.cpu_pairs, seed=2024)
+        with tempfile.TemporaryDirectory() as d:
+            prefix = os.path.join(d, "ref.fa")
+            t0 = time.time()
+            write_index_files(dx, prefix, pac, L, names, offs, lens)
+            dx.close()
+            log(f"index files written in {time.time() - t0:.1f}s")
+            times = reference_run(prefix, reads, ncores, args.steps, args.warmup)
+        ms = 1000 * float(np.mean(times))
+        v = len(reads) / (ms / 1000)
+        line = {"metric": METRIC, "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+                "data": "synthetic", "impl": "reference",
+                "config": {"workload": workload, "pairs_per_step": args.cpu_pairs, "read_len": 150,
+                           "reference_scope": "mem_process_seqs: phase 1 + pairing + SAM text (bwamem.c:432-476)"},
+                "cpu_baseline": {"value": v, "unit": "reads/s", "cores": ncores, "kind": "reference",
+                                 "sample": f"{args.cpu_pairs} pairs per step through oracle/_ref mem_process_seqs"},
+                "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    # ---------------- ours ----------------
+    opt = bsq.default_opt()
+    al = capi.Aligner(dx, opt)
+    t0 = time.time()
+    reads = sim_batch(nt4, names, offs, lens, args.pairs, seed=2024 + 1000 * rank)
+    seqs, tl, par = tasks_from_reads(reads)
+    n_tasks = len(seqs)
+    n_reads = len(reads)
+    log(f"rank {rank}: {args.pairs} pairs simulated in {time.time() - t0:.1f}s")
+    lib = bsq.lib
+
+    def pinned(arr):
+        p = C.c_void_p()
+        bsq.check(lib.bsq_host_alloc(C.byref(p), C.c_size_t(arr.nbytes)), "bsq_host_alloc")
+        buf = np.frombuffer((C.c_char * arr.nbytes).from_address(p.value), dtype=arr.dtype).reshape(arr.shape)
+        buf[...] = arr
+        return buf, p
+
+    h_seqs, p1 = pinned(seqs)
+    h_len, p2 = pinned(tl)
+    h_par, p3 = pinned(par)
+    h2d = h_seqs.nbytes + h_len.nbytes + h_par.nbytes
+
+    def stage():
+        bsq.check(lib.bsq_aligner_stage(al.h, C.c_int64(n_tasks), p1, C.c_int32(seqs.shape[1]), p2, p3), "stage")
+
+    n_regs = C.c_int64()
+
+    def run():
+        bsq.check(lib.bsq_aligner_run(al.h, C.byref(n_regs)), "run")
+
+    stage()
+    run()
+    reg_cap = int(n_regs.value * 1.2) + 1024
+    pr, po = C.c_void_p(), C.c_void_p()
+    bsq.check(lib.bsq_host_alloc(C.byref(pr), C.c_size_t(reg_cap * 56)), "alloc")
+    bsq.check(lib.bsq_host_alloc(C.byref(po), C.c_size_t((n_tasks + 1) * 8)), "alloc")
+
+    def fetch():
+        assert n_regs.value <= reg_cap
+        bsq.check(lib.bsq_aligner_fetch(al.h, pr, po), "fetch")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # --- kernel-only: inputs resident in HBM ---
+    for _ in range(args.warmup):
+        run()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    kern_us = np.zeros(6)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run()
+        c = al.counters()
+        kern_us += c[5:11]
+    barrier()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    # --- end to end: pinned host buffers, H2D + kernels + D2H every step ---
+    for _ in range(max(1, args.warmup // 2)):
+        stage(); run(); fetch()
+    barrier()
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        stage(); run(); fetch()
+    barrier()
+    dt_e2e = time.perf_counter() - t1
+    d2h = int(n_regs.value) * 56 + (n_tasks + 1) * 8
+    if world > 1:
+        t = torch.tensor([dt, dt_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt, dt_e2e = float(t[0]), float(t[1])
+    counters = al.counters()
+    kern_us /= args.steps
+    stage_names = ["k_seed", "k_expand+k_sa", "k_chain", "k_region", "scan+compact", "all"]
+    log("kernel us/step:", dict(zip(stage_names, [int(x) for x in kern_us])), "regions/step", n_regs.value, "sa lookups", int(counters[2]))
+
+    if rank == 0:
+        # ---- algorithmic work of one step, from the instrumented build (untimed) ----
+        work = None
+        try:
+            cb = capi.Bsq(os.path.join(capi.HERE, "csrc", "libbsq_count.so"))
+            # the instrumented library needs its own index copy: reuse by download->upload is too slow for
+            # GRCh38-sized; instead count on a bounded sub-batch against an index built by that library
+            if True:
+                dx2 = cb.build_index(pac, L, names, offs, lens, device=local_rank) if L <= 400_000_000 else None
+            if dx2 is not None:
+                al2 = capi.Aligner(dx2, cb.default_opt())
+                nsub = min(n_tasks, 200_000)
+                w0 = np.zeros(8, np.uint64)
+                cb.lib.bsq_work_counters(w0.ctypes.data_as(C.c_void_p), C.c_int(8), C.c_int(1))
+                al2.phase1(seqs[:nsub], tl[:nsub], par[:nsub])
+                cb.lib.bsq_work_counters(w0.ctypes.data_as(C.c_void_p), C.c_int(8), C.c_int(1))
+                work = {k: float(w0[i]) / nsub for i, k in enumerate(["blocks", "extends", "ksw_calls", "cells", "ref_bases"])}
+                c2 = al2.counters()
+                work["seed_blocks"] = float(c2[12] - c2[11]) / nsub
+                work["sa_blocks"] = float(c2[13] - c2[12]) / nsub
+                work["sa_lookups"] = float(c2[2]) / nsub
+                al2.close()
+                dx2.close()
+        except Exception as e:  # noqa: BLE001
+            log("work counters unavailable:", e)
+        # dominant kernel by device time
+        dom = int(np.argmax(kern_us[:4]))
+        dom_name = stage_names[dom]
+        if work:
+            sa_per_task = float(counters[2]) / n_tasks
+            per_task_bytes = {
+                "k_seed": None, "k_expand+k_sa": None, "k_chain": None, "k_region": None}
+            # blocks counted over the whole pipeline: seeding extends fetch 1-2 blocks each, every LF step 1 block
+            # (instrumented run reports totals; split: SA blocks = total - seed blocks is not separable here, so the
+            # roofline of the dominant kernel uses all FM-index block traffic when it is k_seed or k_sa)
+            per_task_bytes["k_seed"] = 64.0 * work["seed_blocks"] + 150 + 32 * 10
+            per_task_bytes["k_expand+k_sa"] = 64.0 * work["sa_blocks"] + 24 * sa_per_task
+            per_task_bytes["k_chain"] = 200.0 * sa_per_task
+            per_task_bytes["k_region"] = work["ref_bases"] / 4 + 150 + 56
+            alg_bytes = per_task_bytes[dom_name] * n_tasks
+        else:
+            alg_bytes = None
+        dom_s = kern_us[dom] * 1e-6
+        roof = {"bound": "hbm", "kernel": dom_name, "achieved": (alg_bytes / dom_s / 1e9) if alg_bytes else None, "peak": peak,
+                "unit": "GB/s", "frac": (alg_bytes / dom_s / 1e9 / peak) if alg_bytes else None, "traffic": None,
+                "peak_source": peak_src, "kernel_ms": kern_us[dom] / 1000, "share_of_step": float(kern_us[dom] / max(kern_us[5], 1)),
+                "work_per_task": work}
+        cpu = None
+        if not args.no_cpu_baseline:
+            try:
+                import tempfile
+                creads = reads[: 2 * args.cpu_pairs]
+                with tempfile.TemporaryDirectory() as d:
+                    prefix = os.path.join(d, "ref.fa")
+                    write_index_files(dx, prefix, pac, L, names, offs, lens)
+                    times = reference_run(prefix, creads, ncores, 1, 0)
+                v = len(creads) / times[0]
+                cpu = {"value": v, "unit": "reads/s", "cores": ncores, "kind": "reference",
+                       "sample": f"{len(creads) // 2} pairs, one mem_process_seqs call of oracle/_ref (phase 1 + pairing + SAM text)"}
+            except Exception as e:  # noqa: BLE001
+                log("cpu baseline failed:", e)
+                cpu = {"value": None, "unit": "reads/s", "cores": ncores, "kind": "reference", "sample": f"failed: {e}"}
+        value = world * n_reads * args.steps / dt
+        e2e = world * n_reads * args.steps / dt_e2e
+        line = {"metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "int32", "data": "synthetic",
+                "config": {"workload": workload, "pairs_per_step_per_gpu": args.pairs, "read_len": 150,
+                           "stage": "phase 1: seed + SA + chain + filter + extend -> regions (host phase 2 not included)",
+                           "l2": "inputs larger than L2 (FM-index gathers over the whole index)", "index_build_s": t_index,
+                           "parallelism": f"dp{world} (reads sharded, index replicated)"},
+                "clocks": clocks, "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": 6 * args.steps, "roofline": roof, "cpu_baseline": cpu,
+                "kernel_us_per_step": dict(zip(stage_names, [float(x) for x in kern_us]))}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -81,6 +81,18 @@ class Bsq:
         L.bsq_index_free.argtypes = [C.c_void_p]
         L.bsq_aligner_destroy.argtypes = [C.c_void_p]
 
+    def build_index(self, pac: np.ndarray, l_pac: int, names, ann_offset, ann_len, ann_is_alt=None, device: int = 0) -> "DevIndex":
+        """GPU `biscuit index`: both FM-indices from the forward 2-bit pac; the result stays on the device."""
+        pac = np.ascontiguousarray(pac, dtype=np.uint8)
+        ann_offset = np.ascontiguousarray(ann_offset, dtype=np.int64)
+        ann_len = np.ascontiguousarray(ann_len, dtype=np.int32)
+        alt = np.zeros(len(ann_len), np.int32) if ann_is_alt is None else np.ascontiguousarray(ann_is_alt, dtype=np.int32)
+        out = C.c_void_p()
+        rc = self.lib.bsq_index_build(_p(pac), C.c_int64(l_pac), C.c_int32(len(ann_len)), _p(ann_offset), _p(ann_len), _p(alt),
+                                      C.c_int(device), C.byref(out))
+        self.check(rc, "bsq_index_build")
+        return DevIndex(self, out, None)
+
     def check(self, rc: int, what: str) -> None:
         if rc != 0:
             raise BsqError(f"{what}: {self.lib.bsq_strerror(rc).decode()} ({self.lib.bsq_last_error().decode()})")
@@ -123,6 +135,20 @@ class DevIndex:
         if self.h:
             self.bsq.lib.bsq_index_free(self.h)
             self.h = None
+
+    def sizes(self):
+        bw = np.zeros(2, np.uint64); ns = np.zeros(2, np.uint64); pr = np.zeros(2, np.uint64)
+        L2 = np.zeros(10, np.uint64); st = np.zeros(3, np.int64)
+        self.bsq.check(self.bsq.lib.bsq_index_sizes(self.h, _p(bw), _p(ns), _p(pr), _p(L2), _p(st)), "bsq_index_sizes")
+        return dict(bwt_words=bw, n_sa=ns, primary=pr, L2=L2.reshape(2, 5), stats=st)
+
+    def download(self, which: int):
+        """(bwt u32 words, sa u64) of one half, exactly as the reference stores them on disk."""
+        sz = self.sizes()
+        bwt = np.zeros(int(sz["bwt_words"][which]), np.uint32)
+        sa = np.zeros(int(sz["n_sa"][which]), np.uint64)
+        self.bsq.check(self.bsq.lib.bsq_index_download(self.h, C.c_int(which), _p(bwt), _p(sa)), "bsq_index_download")
+        return bwt, sa
 
     def occ4(self, which: int, k: np.ndarray) -> np.ndarray:
         k = np.ascontiguousarray(k, dtype=np.uint64)

@@ -15,6 +15,10 @@
 #include <cub/device/device_scan.cuh>
 
 #include "../../include/bsq.h"
+#include "bsq_internal.h"
+#ifdef BSQ_INSTRUMENT
+static __device__ unsigned long long bsq_ctr[8];
+#endif
 #include "bsq_task.h"
 #include "bsq_opt_default.h"
 
@@ -35,12 +39,22 @@ static thread_local char g_err[512] = "";
     }                                                                                              \
   } while (0)
 
-struct bsq_index {
-  bsq_devidx_t d;  // device pointers
-  int device;
-  void *allocs[16];
-  int n_allocs;
-};
+void bsq_set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+
+bsq_index *bsq_index_alloc(int device) {
+  bsq_index *ix = (bsq_index *)calloc(1, sizeof(bsq_index));
+  ix->device = device;
+  return ix;
+}
+
+void bsq_index_adopt(bsq_index *ix, void *p) {
+  if (p && ix->n_allocs < 32) ix->allocs[ix->n_allocs++] = p;
+}
 
 // grow-only device buffer
 struct DevBuf {
@@ -72,6 +86,8 @@ struct bsq_aligner {
   DevBuf snodes, wchains, bnodes, order, ochains, oseeds, n_chains, frac_rep, srt, regs_tmp, n_regs, reg_off, regs;
   DevBuf cub_tmp, scalars;
   int64_t counters[16];
+  int64_t n_staged = 0, n_regs_total = -1;
+  int32_t stride = 0;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -219,9 +235,9 @@ int bsq_index_upload(const bsq_index_desc *h, int device, bsq_index **out) {
   CK(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) { snprintf(g_err, sizeof g_err, "device %d of %d", device, ndev); return BSQ_ENODEV; }
   CK(cudaSetDevice(device));
-  bsq_index *ix = (bsq_index *)calloc(1, sizeof(bsq_index));
-  ix->device = device;
+  bsq_index *ix = bsq_index_alloc(device);
   int rc = 0;
+  for (int w = 0; w < 2; ++w) { ix->bwt_words[w] = h->bwt_words[w]; ix->n_sa[w] = h->n_sa[w]; }
   for (int w = 0; w < 2 && !rc; ++w) {
     bsq_fm_t &f = ix->d.fm[w];
     f.primary = h->primary[w]; f.seq_len = h->seq_len; f.sa_intv = h->sa_intv[w];
@@ -384,6 +400,19 @@ static int scan_counts(bsq_aligner *al, const int32_t *d_counts, int64_t *d_off,
   return 0;
 }
 
+#ifdef BSQ_INSTRUMENT
+// blocks fetched so far (stream-synchronising; instrumented build only)
+static void snap_blocks(bsq_aligner *al, int slot) {
+  unsigned long long h[8];
+  cudaStreamSynchronize(al->stream);
+  cudaMemcpyFromSymbol(h, bsq_ctr, sizeof h);
+  al->counters[slot] = (int64_t)h[BSQ_CTR_BLOCKS];
+}
+#define SNAP(slot) snap_blocks(al, slot)
+#else
+#define SNAP(slot) ((void)0)
+#endif
+
 // Device-resident core of phase 1: inputs already in al->seqs / lens / parent.
 static int phase1_device(bsq_aligner *al, int64_t n, int32_t stride, int64_t *total_regs) {
   const bsq_devidx_t &ix = al->idx->d;
@@ -395,11 +424,13 @@ static int phase1_device(bsq_aligner *al, int64_t n, int32_t stride, int64_t *to
   RES(n_intv, n * 4); RES(n_sa, n * 4); RES(sa_off, (n + 1) * 8); RES(status, 4);
   RES(n_chains, n * 4); RES(frac_rep, n * 4); RES(n_regs, n * 4); RES(reg_off, (n + 1) * 8);
   CK(cudaMemsetAsync(al->status.p, 0, 4, s));
+  SNAP(11);
   CK(cudaEventRecord(al->ev[0], s));
   k_seed<<<nblk(n, 128), 128, 0, s>>>(opt, ix, n, al->seqs.as<uint8_t>(), stride, al->lens.as<int32_t>(), al->parent.as<uint8_t>(), 1,
                                        al->intv.as<bsq_intv_t>(), al->n_intv.as<int32_t>(), al->n_sa.as<int32_t>(), al->status.as<int32_t>());
   CK(cudaGetLastError());
   CK(cudaEventRecord(al->ev[1], s));
+  SNAP(12);
   int64_t total_sa = 0;
   if ((rc = scan_counts(al, al->n_sa.as<int32_t>(), al->sa_off.as<int64_t>(), n, &total_sa))) return rc;
   const int64_t pool = total_sa + n * BSQ_TAIL_SLACK;
@@ -417,6 +448,7 @@ static int phase1_device(bsq_aligner *al, int64_t n, int32_t stride, int64_t *to
     CK(cudaGetLastError());
   }
   CK(cudaEventRecord(al->ev[3], s));
+  SNAP(13);
   k_chain<<<nblk(n, 128), 128, 0, s>>>(opt, ix, n, al->lens.as<int32_t>(), al->parent.as<uint8_t>(), al->intv.as<bsq_intv_t>(),
                                         al->n_intv.as<int32_t>(), al->sa_off.as<int64_t>(), al->pos.as<uint64_t>(),
                                         al->snodes.as<bsq_snode_t>(), al->wchains.as<bsq_wchain_t>(), al->bnodes.as<bsq_bnode_t>(),
@@ -443,6 +475,7 @@ static int phase1_device(bsq_aligner *al, int64_t n, int32_t stride, int64_t *to
   if (st) { snprintf(g_err, sizeof g_err, "device status 0x%x (1: interval list, 2: chain workspace)", st); return BSQ_EOVERFLOW; }
   float ms[6];
   for (int i = 0; i < 6; ++i) cudaEventElapsedTime(&ms[i], al->ev[i], al->ev[i + 1]);
+  { float tot; cudaEventElapsedTime(&tot, al->ev[0], al->ev[6]); al->counters[10] = (int64_t)(tot * 1000); }
   al->counters[0] = n; al->counters[2] = total_sa; al->counters[4] = *total_regs;
   al->counters[5] = (int64_t)(ms[0] * 1000); al->counters[6] = (int64_t)(ms[2] * 1000);
   al->counters[7] = (int64_t)(ms[3] * 1000); al->counters[8] = (int64_t)(ms[4] * 1000);
@@ -450,11 +483,10 @@ static int phase1_device(bsq_aligner *al, int64_t n, int32_t stride, int64_t *to
   return 0;
 }
 
-int bsq_align_phase1(bsq_aligner *al, int64_t n, const uint8_t *seqs, int32_t stride, const int32_t *lens, const uint8_t *parent,
-                     bsq_reg **regs_out, int64_t *reg_off) {
-  if (!al || n < 0 || !regs_out || !reg_off) return BSQ_EINVAL;
-  *regs_out = nullptr;
-  if (n == 0) { reg_off[0] = 0; return 0; }
+int bsq_aligner_stage(bsq_aligner *al, int64_t n, const uint8_t *seqs, int32_t stride, const int32_t *lens, const uint8_t *parent) {
+  if (!al || n < 0) return BSQ_EINVAL;
+  al->n_staged = 0;
+  if (n == 0) return 0;
   int rc = check_lens(n, lens, stride);
   if (rc) return rc;
   CK(cudaSetDevice(al->idx->device));
@@ -465,15 +497,74 @@ int bsq_align_phase1(bsq_aligner *al, int64_t n, const uint8_t *seqs, int32_t st
   CK(cudaMemcpyAsync(al->seqs.p, seqs, (size_t)n * stride, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(al->lens.p, lens, n * 4, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(al->parent.p, parent, n, cudaMemcpyHostToDevice, s));
+  al->n_staged = n; al->stride = stride; al->n_regs_total = -1;
+  return 0;
+}
+
+int bsq_aligner_run(bsq_aligner *al, int64_t *n_regs) {
+  if (!al) return BSQ_EINVAL;
+  if (al->n_staged == 0) { if (n_regs) *n_regs = 0; al->n_regs_total = 0; return 0; }
+  CK(cudaSetDevice(al->idx->device));
   int64_t total = 0;
-  if ((rc = phase1_device(al, n, stride, &total))) return rc;
-  bsq_reg *host = (bsq_reg *)malloc((size_t)(total + 1) * sizeof(bsq_reg));
-  if (!host) return BSQ_ENOMEM;
-  CK(cudaMemcpyAsync(host, al->regs.p, (size_t)total * sizeof(bsq_reg), cudaMemcpyDeviceToHost, s));
+  int rc = phase1_device(al, al->n_staged, al->stride, &total);
+  if (rc) return rc;
+  al->n_regs_total = total;
+  if (n_regs) *n_regs = total;
+  return 0;
+}
+
+int bsq_aligner_fetch(bsq_aligner *al, bsq_reg *regs, int64_t *reg_off) {
+  if (!al || al->n_regs_total < 0 || !reg_off) return BSQ_EINVAL;
+  const int64_t n = al->n_staged;
+  if (n == 0) { reg_off[0] = 0; return 0; }
+  CK(cudaSetDevice(al->idx->device));
+  cudaStream_t s = al->stream;
+  if (al->n_regs_total > 0) {
+    if (!regs) return BSQ_EINVAL;
+    CK(cudaMemcpyAsync(regs, al->regs.p, (size_t)al->n_regs_total * sizeof(bsq_reg), cudaMemcpyDeviceToHost, s));
+  }
   CK(cudaMemcpyAsync(reg_off, al->reg_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int bsq_align_phase1(bsq_aligner *al, int64_t n, const uint8_t *seqs, int32_t stride, const int32_t *lens, const uint8_t *parent,
+                     bsq_reg **regs_out, int64_t *reg_off) {
+  if (!al || n < 0 || !regs_out || !reg_off) return BSQ_EINVAL;
+  *regs_out = nullptr;
+  if (n == 0) { reg_off[0] = 0; return 0; }
+  int rc = bsq_aligner_stage(al, n, seqs, stride, lens, parent);
+  if (rc) return rc;
+  int64_t total = 0;
+  if ((rc = bsq_aligner_run(al, &total))) return rc;
+  bsq_reg *host = (bsq_reg *)malloc((size_t)(total + 1) * sizeof(bsq_reg));
+  if (!host) return BSQ_ENOMEM;
+  if ((rc = bsq_aligner_fetch(al, host, reg_off))) { free(host); return rc; }
   *regs_out = host;
   return 0;
 }
+
+// Work counters (see BSQ_CTR in bsq_common.h).  The product build is not instrumented and says so.
+int bsq_work_counters(uint64_t *out, int n, int reset) {
+#ifdef BSQ_INSTRUMENT
+  unsigned long long h[8];
+  CK(cudaMemcpyFromSymbol(h, bsq_ctr, sizeof h));
+  for (int i = 0; i < n && i < 8; ++i) out[i] = h[i];
+  if (reset) { memset(h, 0, sizeof h); CK(cudaMemcpyToSymbol(bsq_ctr, h, sizeof h)); }
+  return 0;
+#else
+  (void)out; (void)n; (void)reset;
+  snprintf(g_err, sizeof g_err, "libbsq.so is not instrumented; use libbsq_count.so");
+  return BSQ_EINVAL;
+#endif
+}
+
+int bsq_host_alloc(void **p, size_t bytes) {
+  if (!p) return BSQ_EINVAL;
+  CK(cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocDefault));
+  return 0;
+}
+
+void bsq_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 }  // extern "C"

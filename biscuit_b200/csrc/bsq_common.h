@@ -17,6 +17,19 @@
 #define BSQ_HDN inline
 #endif
 
+// Work counters for the roofline arithmetic (bench.py).  Only the separately built
+// libbsq_count.so (-DBSQ_INSTRUMENT) carries them; in the product build the macro is empty.
+#if defined(BSQ_INSTRUMENT) && defined(__CUDA_ARCH__)
+#define BSQ_CTR(i, v) atomicAdd(&bsq_ctr[i], (unsigned long long)(v))
+#else
+#define BSQ_CTR(i, v) ((void)0)
+#endif
+#define BSQ_CTR_BLOCKS 0   // 64-byte FM-index blocks fetched
+#define BSQ_CTR_EXTENDS 1  // bwt_extend calls
+#define BSQ_CTR_KSW 2      // ksw_extend2 calls
+#define BSQ_CTR_CELLS 3    // DP cells
+#define BSQ_CTR_REFB 4     // reference bases decoded from the 2-bit pac
+
 #define BSQ_MAX_READ_LEN 256  // longest read the device seeding kernels accept
 #define BSQ_MAX_INTV 160      // per (read,conversion) capacity of the SMEM interval list
 

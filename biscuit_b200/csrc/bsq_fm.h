@@ -9,6 +9,7 @@ struct bsq_block_t {
 };
 
 BSQ_HD void bsq_load_block(const uint32_t *blocks, uint64_t blk, bsq_block_t &b) {
+  BSQ_CTR(BSQ_CTR_BLOCKS, 1);
 #if defined(__CUDA_ARCH__)
   const uint4 *p = reinterpret_cast<const uint4 *>(blocks) + blk * 4;
   uint4 a0 = __ldg(p), a1 = __ldg(p + 1), a2 = __ldg(p + 2), a3 = __ldg(p + 3);
@@ -87,6 +88,7 @@ template <int BACK>
 BSQ_HD void bsq_extend(const bsq_fm_t &fm, const bsq_intv_t &ik, bsq_intv_t ok[4]) {
   uint64_t tk[4], tl[4];
   const uint64_t beg = ik.x[!BACK];
+  BSQ_CTR(BSQ_CTR_EXTENDS, 1);
   bsq_2occ4(fm, beg - 1, beg - 1 + ik.x[2], tk, tl);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {

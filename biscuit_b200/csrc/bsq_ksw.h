@@ -25,6 +25,7 @@ BSQ_HD bsq_ext_result_t bsq_ksw_extend(int qlen, QGet qget, int tlen, TGet tget,
                                        int o_ins, int e_ins, int w, int end_bonus, int zdrop, int h0,
                                        bsq_ksw_scratch_t &scr) {
   bsq_eh_t *eh = scr.eh;
+  BSQ_CTR(BSQ_CTR_KSW, 1);
   const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
   int i, j;
   for (j = 0; j <= qlen; ++j) eh[j].h = eh[j].e = 0;
@@ -49,6 +50,7 @@ BSQ_HD bsq_ext_result_t bsq_ksw_extend(int qlen, QGet qget, int tlen, TGet tget,
     if (beg < i - w) beg = i - w;
     if (end > i + w + 1) end = i + w + 1;
     if (end > qlen) end = qlen;
+    BSQ_CTR(BSQ_CTR_CELLS, end > beg ? end - beg : 0);
     if (beg == 0) {
       h1 = h0 - (o_del + e_del * (i + 1));
       if (h1 < 0) h1 = 0;

@@ -14,6 +14,7 @@ BSQ_HD int bsq_pac_base(const uint8_t *pac, int64_t l) { return pac[l >> 2] >> (
 
 // base at forward-reverse coordinate pos in [0, 2*l_pac)
 BSQ_HD int bsq_ref_base(const bsq_devidx_t &ix, int64_t pos) {
+  BSQ_CTR(BSQ_CTR_REFB, 1);
   return pos < ix.l_pac ? bsq_pac_base(ix.pac, pos) : 3 - bsq_pac_base(ix.pac, (ix.l_pac << 1) - 1 - pos);
 }
 

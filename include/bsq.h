@@ -20,6 +20,7 @@
  */
 #ifndef BSQ_H
 #define BSQ_H
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -88,6 +89,17 @@ const char *bsq_last_error(void); /* text of the last CUDA error seen by this th
 int bsq_index_upload(const bsq_index_desc *desc, int device, bsq_index **out);
 void bsq_index_free(bsq_index *idx);
 
+/* `biscuit index` on the GPU (replaces bwt_bwtgen/bwt_pac2bwt + bwt_bwtupdate_core + bwt_cal_sa,
+ * lib/aln/bwtindex.c:258-344): builds both converted FM-indices from the forward 2-bit pac (host
+ * buffer, N already replaced, i.e. the content of <prefix>.bis.pac) and leaves them resident on
+ * `device`.  bsq_index_sizes/_download return the arrays exactly as the reference stores them in
+ * <prefix>.{par,dau}.{bwt,sa} (which: 0 = dau, 1 = par). */
+int bsq_index_build(const uint8_t *pac, int64_t l_pac, int32_t n_seqs, const int64_t *ann_offset, const int32_t *ann_len,
+                    const int32_t *ann_is_alt, int device, bsq_index **out);
+int bsq_index_sizes(const bsq_index *idx, uint64_t bwt_words[2], uint64_t n_sa[2], uint64_t primary[2], uint64_t L2[10],
+                    int64_t stats[3]);
+int bsq_index_download(const bsq_index *idx, int which, uint32_t *bwt, uint64_t *sa);
+
 /* ---- kernel-level entry points (SoA, host buffers) ---- */
 
 /* cnt[4*i..4*i+3] = ranks of A,C,G,T up to BWT position k[i] in index `which` */
@@ -124,9 +136,28 @@ int bsq_align_phase1(bsq_aligner *al, int64_t n_tasks, const uint8_t *seqs, int3
                      const uint8_t *parent, bsq_reg **regs, int64_t *reg_off);
 void bsq_free(void *p);
 
+/* The same call split in three so that a caller can pipeline batches (and so that bench.py can time the
+ * device part with inputs already resident in HBM): stage = host->device copy of the reads,
+ * run = the five kernels (returns the number of regions), fetch = device->host copy into caller
+ * buffers (regs: *n_regs entries, reg_off: n_tasks+1).  bsq_host_alloc returns page-locked host
+ * memory for these buffers. */
+int bsq_aligner_stage(bsq_aligner *al, int64_t n_tasks, const uint8_t *seqs, int32_t stride, const int32_t *lens,
+                      const uint8_t *parent);
+int bsq_aligner_run(bsq_aligner *al, int64_t *n_regs);
+int bsq_aligner_fetch(bsq_aligner *al, bsq_reg *regs, int64_t *reg_off);
+int bsq_host_alloc(void **p, size_t bytes);
+/* work counters for the roofline arithmetic: only the instrumented build (libbsq_count.so) has them,
+ * libbsq.so returns BSQ_EINVAL.  out[0]=64-B index blocks fetched, [1]=bwt_extend calls,
+ * [2]=ksw_extend2 calls, [3]=DP cells, [4]=reference bases decoded */
+int bsq_work_counters(uint64_t *out, int n, int reset);
+void bsq_host_free(void *p);
+
 /* counters of the last bsq_align_phase1 call (for the roofline arithmetic in bench.py):
  * c[0]=tasks c[1]=intervals c[2]=seeds(SA lookups) c[3]=chains kept c[4]=regions
- * c[5..8] = device ms of the seed / sa / chain / extend kernels  (as integer microseconds) */
+ * c[5..8] = device time of the seed / expand+sa / chain / extend kernels, c[9] = scans+compaction,
+ * c[10] = first kernel to last kernel, all in integer microseconds (CUDA events on the aligner's stream);
+ * instrumented build only: c[11..13] = running count of 64-B index blocks fetched before k_seed / after
+ * k_seed / after k_sa */
 int bsq_aligner_counters(const bsq_aligner *al, int64_t *c, int n);
 
 #ifdef __cplusplus

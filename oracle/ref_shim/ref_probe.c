@@ -222,3 +222,35 @@ int refp_worker1(refp_t *h, int which_read, int len, const uint8_t *seq, int64_t
   free(regs.a); free(buf); free(b.bisseq[0]); free(b.bisseq[1]);
   return n;
 }
+
+/* mem_process_seqs (bwamem.c:432-476), the reference's batch API, on n
+ * interleaved reads given as nt4 rows.  Returns total SAM bytes; if sam_out != NULL the SAM text
+ * of all reads is concatenated into it (cap bytes).  Timed by the caller. */
+int64_t refp_process_seqs(refp_t *h, int n_threads, int64_t n_processed, int n, const uint8_t *seqs, int stride,
+                          const int32_t *lens, const uint8_t *quals, char *sam_out, int64_t cap) {
+  bseq1_t *bs = calloc(n, sizeof(bseq1_t));
+  int i; int64_t tot = 0;
+  char nm[64];
+  for (i = 0; i < n; ++i) {
+    bs[i].l_seq = lens[i];
+    bs[i].seq = malloc(lens[i] + 1); memcpy(bs[i].seq, seqs + (int64_t)i * stride, lens[i]);
+    bs[i].qual = malloc(lens[i] + 1);
+    if (quals) memcpy(bs[i].qual, quals + (int64_t)i * stride, lens[i]); else memset(bs[i].qual, 'I', lens[i]);
+    bs[i].qual[lens[i]] = 0;
+    snprintf(nm, sizeof nm, "r%lld", (long long)((n_processed + i) >> 1));
+    bs[i].name = strdup(nm);
+    bs[i].id = i;
+  }
+  h->opt->n_threads = n_threads;
+  mem_process_seqs(h->opt, h->idx->bwt, h->idx->bns, h->idx->pac, n_processed, n, bs, 0);
+  for (i = 0; i < n; ++i) {
+    int64_t l = bs[i].sam ? (int64_t)strlen(bs[i].sam) : 0;
+    if (sam_out && tot + l < cap) memcpy(sam_out + tot, bs[i].sam, l);
+    tot += l;
+    free(bs[i].sam); free(bs[i].seq0 ? bs[i].seq0 : bs[i].seq); free(bs[i].qual); free(bs[i].name);
+    free(bs[i].bisseq[0]); free(bs[i].bisseq[1]);
+  }
+  if (sam_out && tot < cap) sam_out[tot] = 0;
+  free(bs);
+  return tot;
+}
