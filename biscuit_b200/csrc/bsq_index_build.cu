@@ -173,7 +173,8 @@ __global__ void k_write_blocks(const uint8_t *bwt_sym, uint64_t n, uint64_t prim
                                uint64_t out_words) {
   uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b > n_blocks) return;
-  uint32_t *o = out + b * 16;
+  // the trailing occ[4] sits right after the last symbol word (the last block may be partial)
+  uint32_t *o = b < n_blocks ? out + b * 16 : out + (out_words - 8);
   for (int s = 0; s < 4; ++s) {
     uint64_t v = occ4[(uint64_t)s * (n_blocks + 1) + b];
     o[2 * s] = (uint32_t)v; o[2 * s + 1] = (uint32_t)(v >> 32);

@@ -67,5 +67,5 @@ def ds_1m(tmp_path_factory):
 def ds_hard(tmp_path_factory):
     """Small reference (200 kb incl. N runs, 5 contigs) with noisy reads: substitutions 2 %, indels, N bases,
     mixed qualities -- exercises ties, re-seeding, band doubling and contig edges."""
-    return _make_dataset(tmp_path_factory, "dshard", 200_000, 5, 400, 3, sub_rate=0.02, indel_rate=0.004, n_rate=0.002,
+    return _make_dataset(tmp_path_factory, "dshard", 200_037, 5, 400, 3, sub_rate=0.02, indel_rate=0.004, n_rate=0.002,
                          qual="mixed", n_runs=3)
