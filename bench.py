@@ -185,8 +185,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-mb", type=float, default=float(os.environ.get("BSQ_BENCH_REF_MB", "3100")))
-    ap.add_argument("--pairs", type=int, default=int(os.environ.get("BSQ_BENCH_PAIRS", "500000")))
-    ap.add_argument("--cpu-pairs", type=int, default=int(os.environ.get("BSQ_BENCH_CPU_PAIRS", "20000")))
+    ap.add_argument("--pairs", type=int, default=int(os.environ.get("BSQ_BENCH_PAIRS", "100000")))
+    ap.add_argument("--cpu-pairs", type=int, default=int(os.environ.get("BSQ_BENCH_CPU_PAIRS", "10000")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -327,13 +327,12 @@ def main():
         work = None
         try:
             cb = capi.Bsq(os.path.join(capi.HERE, "csrc", "libbsq_count.so"))
-            # the instrumented library needs its own index copy: reuse by download->upload is too slow for
-            # GRCh38-sized; instead count on a bounded sub-batch against an index built by that library
-            if True:
-                dx2 = cb.build_index(pac, L, names, offs, lens, device=local_rank) if L <= 400_000_000 else None
+            # the instrumented library keeps its own index copy (built again, seconds) and counts the work of a
+            # bounded sub-batch of the same tasks
+            dx2 = cb.build_index(pac, L, names, offs, lens, device=local_rank)
             if dx2 is not None:
                 al2 = capi.Aligner(dx2, cb.default_opt())
-                nsub = min(n_tasks, 200_000)
+                nsub = min(n_tasks, 100_000)
                 w0 = np.zeros(8, np.uint64)
                 cb.lib.bsq_work_counters(w0.ctypes.data_as(C.c_void_p), C.c_int(8), C.c_int(1))
                 al2.phase1(seqs[:nsub], tl[:nsub], par[:nsub])
@@ -359,16 +358,21 @@ def main():
             # roofline of the dominant kernel uses all FM-index block traffic when it is k_seed or k_sa)
             per_task_bytes["k_seed"] = 64.0 * work["seed_blocks"] + 150 + 32 * 10
             per_task_bytes["k_expand+k_sa"] = 64.0 * work["sa_blocks"] + 24 * sa_per_task
-            per_task_bytes["k_chain"] = 200.0 * sa_per_task
+            per_task_bytes["k_chain"] = (8 + 16 + 40) * sa_per_task  # SA position in, seed + chain records out
             per_task_bytes["k_region"] = work["ref_bases"] / 4 + 150 + 56
             alg_bytes = per_task_bytes[dom_name] * n_tasks
         else:
             alg_bytes = None
         dom_s = kern_us[dom] * 1e-6
+        by_kernel = None
+        if work:
+            by_kernel = {k: {"ms": kern_us[i] / 1000, "alg_GBps": per_task_bytes[k] * n_tasks / (kern_us[i] * 1e-6) / 1e9,
+                             "frac": per_task_bytes[k] * n_tasks / (kern_us[i] * 1e-6) / 1e9 / peak}
+                         for i, k in enumerate(stage_names[:4])}
         roof = {"bound": "hbm", "kernel": dom_name, "achieved": (alg_bytes / dom_s / 1e9) if alg_bytes else None, "peak": peak,
                 "unit": "GB/s", "frac": (alg_bytes / dom_s / 1e9 / peak) if alg_bytes else None, "traffic": None,
                 "peak_source": peak_src, "kernel_ms": kern_us[dom] / 1000, "share_of_step": float(kern_us[dom] / max(kern_us[5], 1)),
-                "work_per_task": work}
+                "work_per_task": work, "by_kernel": by_kernel}
         cpu = None
         if not args.no_cpu_baseline:
             try:

@@ -14,7 +14,7 @@ import numpy as np
 from .indexio import HostIndex
 
 MAX_READ_LEN = 256
-MAX_INTV = 160
+MAX_INTV = 384
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libbsq.so")
 

@@ -20,6 +20,7 @@
 static __device__ unsigned long long bsq_ctr[8];
 #endif
 #include "bsq_task.h"
+#include "bsq_ksw_warp.cuh"
 #include "bsq_opt_default.h"
 
 static_assert(sizeof(bsq_intv) == sizeof(bsq_intv_t), "abi");
@@ -94,31 +95,63 @@ struct bsq_aligner {
 // kernels
 // ------------------------------------------------------------------------------------------
 
+// SMEM seeding.  Each lane owns one (read, conversion) task at a time and pulls the next one from a
+// global counter when it finishes; all lanes of the warp meet at the single bsq_extend1 site per
+// iteration so that their FM-index gathers are in flight together (see bsq_seed.h).
 __global__ void __launch_bounds__(128) k_seed(bsq_devopt_t opt, bsq_devidx_t ix, int64_t n_tasks, const uint8_t *seqs, int stride,
-                                              const int32_t *lens, const uint8_t *parent, int pipeline, bsq_intv_t *intv,
-                                              int32_t *n_intv, int32_t *n_sa, int32_t *status) {
-  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_tasks) return;
+                                              const int32_t *lens, const uint8_t *parent, int pipeline, bsq_pk_t *intv,
+                                              int32_t *n_intv, int32_t *n_sa, int32_t *status, unsigned long long *next_task) {
   bsq_seed_scratch_t scr;
-  int32_t nsa = 0;
-  int n = bsq_task_seed(opt, ix, seqs + t * stride, lens[t], parent[t], pipeline != 0, scr, intv + t * BSQ_MAX_INTV, &nsa);
-  if (n < 0) { atomicOr(status, 1); n = 0; nsa = 0; }
-  n_intv[t] = n;
-  n_sa[t] = nsa;
+  bsq_seed_machine_t m;
+  bsq_ext_req_t req;
+  int64_t t = -1;
+  int par = 0;
+  bool have = false, exhausted = false;
+  bsq_pk_t *out = nullptr;
+  for (;;) {
+    if (!have && !exhausted) {
+      t = (int64_t)atomicAdd(next_task, 1ull);
+      if (t >= n_tasks) exhausted = true;
+      else {
+        const int len = lens[t];
+        par = parent[t] != 0;
+        out = intv + t * BSQ_MAX_INTV;
+        if (pipeline && len < opt.min_seed_len) { n_intv[t] = 0; n_sa[t] = 0; }  // mem_chain returns before seeding
+        else {
+          bsq_bsconvert(seqs + t * stride, len, par, scr.q);
+          bsq_sm_init(m, opt, len, BSQ_MAX_INTV);
+          have = true;
+        }
+      }
+    }
+    bool need = false;
+    if (have) {
+      need = bsq_sm_next(m, ix.fm[par], ix.fm[!par], scr, out, req);
+      if (!need) {
+        if (m.overflow) { atomicOr(status, 1); n_intv[t] = 0; n_sa[t] = 0; }
+        else { n_sa[t] = bsq_sm_finalize(m, opt, out); n_intv[t] = m.n_out; }
+        have = false;
+      }
+    }
+    if (__all_sync(0xffffffffu, exhausted && !have)) break;
+    if (need) {
+      uint64_t o0, o1, o2;
+      bsq_extend1(ix.fm[par], ix.fm[!par], req, o0, o1, o2);
+      bsq_sm_consume(m, scr, out, o0, o1, o2);
+    }
+  }
 }
 
-__global__ void k_expand(bsq_devopt_t opt, int64_t n_tasks, const bsq_intv_t *intv, const int32_t *n_intv, const uint8_t *parent,
+__global__ void k_expand(bsq_devopt_t opt, int64_t n_tasks, const bsq_pk_t *intv, const int32_t *n_intv, const uint8_t *parent,
                          const int64_t *sa_off, uint64_t *ranks) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_tasks) return;
-  const bsq_intv_t *v = intv + t * BSQ_MAX_INTV;
-  const uint64_t tag = (uint64_t)(parent[t] != 0) << 63;
-  int64_t o = sa_off[t];
-  const int n = n_intv[t];
-  for (int i = 0; i < n; ++i) {
-    uint64_t m = v[i].x[2] < (uint64_t)(uint32_t)opt.max_occ ? v[i].x[2] : (uint64_t)(uint32_t)opt.max_occ;
-    for (uint64_t k = 0; k < m; ++k) ranks[o++] = (v[i].x[0] + k) | tag;
-  }
+  bsq_task_expand(opt, intv + t * BSQ_MAX_INTV, n_intv[t], (uint64_t)(parent[t] != 0) << 63, ranks + sa_off[t]);
+}
+
+__global__ void k_unpack_intv(int64_t n, const bsq_pk_t *in, bsq_intv_t *out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = bsq_pk_unpack(in[i]);
 }
 
 __global__ void k_sa(bsq_devidx_t ix, int64_t n, const uint64_t *ranks, uint64_t *pos) {
@@ -146,7 +179,7 @@ __global__ void k_occ4(bsq_devidx_t ix, int which, int64_t n, const uint64_t *k,
 __device__ __forceinline__ int64_t ws_off(const int64_t *sa_off, int64_t t) { return sa_off[t] + t * BSQ_TAIL_SLACK; }
 
 __global__ void __launch_bounds__(128) k_chain(bsq_devopt_t opt, bsq_devidx_t ix, int64_t n_tasks, const int32_t *lens,
-                                               const uint8_t *parent, const bsq_intv_t *intv, const int32_t *n_intv,
+                                               const uint8_t *parent, const bsq_pk_t *intv, const int32_t *n_intv,
                                                const int64_t *sa_off, const uint64_t *pos, bsq_snode_t *snodes,
                                                bsq_wchain_t *wchains, bsq_bnode_t *bnodes, int32_t *order, bsq_chain_t *ochains,
                                                bsq_seed_t *oseeds, int32_t *n_chains, float *frac_rep, int32_t *status) {
@@ -163,16 +196,18 @@ __global__ void __launch_bounds__(128) k_chain(bsq_devopt_t opt, bsq_devidx_t ix
   frac_rep[t] = r.frac_rep;
 }
 
-__global__ void __launch_bounds__(128) k_region(bsq_devopt_t opt, bsq_devidx_t ix, int64_t n_tasks, const uint8_t *seqs, int stride,
+// Chains -> regions, one WARP per task: the control flow of mem_chain2region runs uniformly in all
+// lanes, every banded extension is spread over the lanes (bsq_ksw_warp.cuh), lane 0 stores.
+__global__ void __launch_bounds__(128, 4) k_region(bsq_devopt_t opt, bsq_devidx_t ix, int64_t n_tasks, const uint8_t *seqs, int stride,
                                                 const int32_t *lens, const uint8_t *parent, const int64_t *sa_off,
                                                 const bsq_chain_t *ochains, const bsq_seed_t *oseeds, const int32_t *n_chains,
                                                 const float *frac_rep, uint64_t *srt, bsq_reg_t *regs_tmp, int32_t *n_regs) {
-  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_tasks) return;
+  const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (t >= n_tasks) return;  // whole warps leave together
   const int64_t wo = ws_off(sa_off, t);
-  bsq_ksw_scratch_t ksw;
-  n_regs[t] = bsq_chain2region(opt, ix, parent[t], lens[t], seqs + t * stride, ochains + wo, n_chains[t], oseeds + wo,
-                               frac_rep[t], srt + wo, ksw, regs_tmp + wo);
+  const int n = bsq_chain2region<bsq_warp_policy>(opt, ix, parent[t], lens[t], seqs + t * stride, ochains + wo, n_chains[t], oseeds + wo,
+                                                  frac_rep[t], srt + wo, nullptr, regs_tmp + wo);
+  if ((threadIdx.x & 31) == 0) n_regs[t] = n;
 }
 
 __global__ void k_compact_regs(int64_t n_tasks, const int64_t *sa_off, const int32_t *n_regs, const int64_t *reg_off,
@@ -184,17 +219,18 @@ __global__ void k_compact_regs(int64_t n_tasks, const int64_t *sa_off, const int
   for (int i = 0; i < n_regs[t]; ++i) dst[i] = src[i];
 }
 
-struct PtrGet { const uint8_t *p; __device__ int operator()(int i) const { return p[i]; } };
 
-__global__ void __launch_bounds__(128) k_extend(bsq_devopt_t opt, int64_t n_jobs, const uint8_t *qbuf, const int64_t *qoff,
-                                                const int32_t *qlen, const uint8_t *tbuf, const int64_t *toff, const int32_t *tlen,
-                                                const uint8_t *is_parent, const int32_t *w, const int32_t *h0, int32_t *out) {
-  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// batched ksw_extend2 jobs through the warp-cooperative kernel that k_region uses (one warp per job)
+__global__ void __launch_bounds__(128) k_extend_warp(bsq_devopt_t opt, int64_t n_jobs, const uint8_t *qbuf, const int64_t *qoff,
+                                                     const int32_t *qlen, const uint8_t *tbuf, const int64_t *toff, const int32_t *tlen,
+                                                     const uint8_t *is_parent, const int32_t *w, const int32_t *h0, int32_t *out) {
+  const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (j >= n_jobs) return;
-  bsq_ksw_scratch_t scr;
-  PtrGet qa{qbuf + qoff[j]}, ta{tbuf + toff[j]};
-  bsq_ext_result_t r = bsq_ksw_extend(qlen[j], qa, tlen[j], ta, is_parent[j] ? opt.ctmat : opt.gamat, opt.o_del, opt.e_del,
-                                      opt.o_ins, opt.e_ins, w[j], opt.pen_clip5, opt.zdrop, h0[j], scr);
+  bsq_qacc_t qa; qa.q = qbuf + qoff[j]; qa.step = 1;
+  bsq_tacc_t ta; ta.ix = nullptr; ta.buf = tbuf + toff[j]; ta.p0 = 0; ta.step = 1;
+  bsq_ext_result_t r = bsq_ksw_extend_warp(qlen[j], qa, tlen[j], ta, is_parent[j] ? opt.ctmat : opt.gamat, opt.o_del, opt.e_del,
+                                           opt.o_ins, opt.e_ins, w[j], opt.pen_clip5, opt.zdrop, h0[j]);
+  if ((threadIdx.x & 31) != 0) return;
   int32_t *o = out + 6 * j;
   o[0] = r.score; o[1] = r.qle; o[2] = r.tle; o[3] = r.gtle; o[4] = r.gscore; o[5] = r.max_off;
 }
@@ -204,6 +240,12 @@ __global__ void __launch_bounds__(128) k_extend(bsq_devopt_t opt, int64_t n_jobs
 // ------------------------------------------------------------------------------------------
 
 static inline unsigned nblk(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+// k_seed is persistent (lanes pull tasks from a counter): one wave of 148 SMs x 8 resident CTAs of 128
+static inline unsigned seed_grid(int64_t n) {
+  int64_t want = (n + 127) / 128;
+  return (unsigned)(want < 148 * 8 ? want : 148 * 8);
+}
 
 extern "C" {
 
@@ -306,20 +348,25 @@ int bsq_collect_intv(const bsq_index *ix, const bsq_opt *opt_, int64_t n, const 
   if (rc) return rc;
   CK(cudaSetDevice(ix->device));
   bsq_devopt_t opt; memcpy(&opt, opt_, sizeof opt);
-  uint8_t *dseq = nullptr, *dpar = nullptr; int32_t *dlen = nullptr, *dn = nullptr, *dnsa = nullptr, *dst = nullptr; bsq_intv_t *dint = nullptr;
+  uint8_t *dseq = nullptr, *dpar = nullptr; int32_t *dlen = nullptr, *dn = nullptr, *dnsa = nullptr, *dst = nullptr;
+  bsq_pk_t *dpk = nullptr; bsq_intv_t *dint = nullptr; unsigned long long *dnext = nullptr;
   CK(cudaMalloc(&dseq, n * stride)); CK(cudaMalloc(&dpar, n)); CK(cudaMalloc(&dlen, n * 4)); CK(cudaMalloc(&dn, n * 4));
-  CK(cudaMalloc(&dnsa, n * 4)); CK(cudaMalloc(&dst, 4)); CK(cudaMalloc(&dint, n * BSQ_MAX_INTV * sizeof(bsq_intv_t)));
+  CK(cudaMalloc(&dnsa, n * 4)); CK(cudaMalloc(&dst, 4)); CK(cudaMalloc(&dnext, 8));
+  CK(cudaMalloc(&dpk, n * BSQ_MAX_INTV * sizeof(bsq_pk_t))); CK(cudaMalloc(&dint, n * BSQ_MAX_INTV * sizeof(bsq_intv_t)));
   CK(cudaMemcpy(dseq, seqs, n * stride, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dpar, parent, n, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dlen, lens, n * 4, cudaMemcpyHostToDevice));
-  CK(cudaMemset(dst, 0, 4));
-  k_seed<<<nblk(n, 128), 128>>>(opt, ix->d, n, dseq, stride, dlen, dpar, 0, dint, dn, dnsa, dst);
+  CK(cudaMemset(dst, 0, 4)); CK(cudaMemset(dnext, 0, 8));
+  CK(cudaMemset(dpk, 0, n * BSQ_MAX_INTV * sizeof(bsq_pk_t)));
+  k_seed<<<seed_grid(n), 128>>>(opt, ix->d, n, dseq, stride, dlen, dpar, 0, dpk, dn, dnsa, dst, dnext);
+  CK(cudaGetLastError());
+  k_unpack_intv<<<nblk(n * BSQ_MAX_INTV, 256), 256>>>(n * BSQ_MAX_INTV, dpk, dint);
   CK(cudaGetLastError());
   int32_t st = 0;
   CK(cudaMemcpy(&st, dst, 4, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(n_out, dn, n * 4, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(out, dint, n * BSQ_MAX_INTV * sizeof(bsq_intv_t), cudaMemcpyDeviceToHost));
-  cudaFree(dseq); cudaFree(dpar); cudaFree(dlen); cudaFree(dn); cudaFree(dnsa); cudaFree(dst); cudaFree(dint);
+  cudaFree(dseq); cudaFree(dpar); cudaFree(dlen); cudaFree(dn); cudaFree(dnsa); cudaFree(dst); cudaFree(dpk); cudaFree(dint); cudaFree(dnext);
   return st ? BSQ_EOVERFLOW : 0;
 }
 
@@ -345,7 +392,7 @@ int bsq_extend_batch(const bsq_opt *opt_, int64_t n, const uint8_t *qbuf, const 
   CK(cudaMemcpy(dqo, qoff, n * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dto, toff, n * 8, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dql, qlen, n * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dtl, tlen, n * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dw, w, n * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dh, h0, n * 4, cudaMemcpyHostToDevice));
-  k_extend<<<nblk(n, 128), 128>>>(opt, n, dq, dqo, dql, dt, dto, dtl, dp, dw, dh, dout);
+  k_extend_warp<<<nblk(n * 32, 128), 128>>>(opt, n, dq, dqo, dql, dt, dto, dtl, dp, dw, dh, dout);
   CK(cudaGetLastError());
   CK(cudaMemcpy(out, dout, n * 24, cudaMemcpyDeviceToHost));
   cudaFree(dq); cudaFree(dt); cudaFree(dp); cudaFree(dqo); cudaFree(dto); cudaFree(dql); cudaFree(dtl); cudaFree(dw);
@@ -420,14 +467,16 @@ static int phase1_device(bsq_aligner *al, int64_t n, int32_t stride, int64_t *to
   cudaStream_t s = al->stream;
   int rc;
 #define RES(buf, bytes) if ((rc = al->buf.reserve(bytes))) return rc
-  RES(intv, (size_t)n * BSQ_MAX_INTV * sizeof(bsq_intv_t));
+  RES(intv, (size_t)n * BSQ_MAX_INTV * sizeof(bsq_pk_t)); RES(scalars, 64);
   RES(n_intv, n * 4); RES(n_sa, n * 4); RES(sa_off, (n + 1) * 8); RES(status, 4);
   RES(n_chains, n * 4); RES(frac_rep, n * 4); RES(n_regs, n * 4); RES(reg_off, (n + 1) * 8);
   CK(cudaMemsetAsync(al->status.p, 0, 4, s));
+  CK(cudaMemsetAsync(al->scalars.p, 0, 64, s));
   SNAP(11);
   CK(cudaEventRecord(al->ev[0], s));
-  k_seed<<<nblk(n, 128), 128, 0, s>>>(opt, ix, n, al->seqs.as<uint8_t>(), stride, al->lens.as<int32_t>(), al->parent.as<uint8_t>(), 1,
-                                       al->intv.as<bsq_intv_t>(), al->n_intv.as<int32_t>(), al->n_sa.as<int32_t>(), al->status.as<int32_t>());
+  k_seed<<<seed_grid(n), 128, 0, s>>>(opt, ix, n, al->seqs.as<uint8_t>(), stride, al->lens.as<int32_t>(), al->parent.as<uint8_t>(), 1,
+                                      al->intv.as<bsq_pk_t>(), al->n_intv.as<int32_t>(), al->n_sa.as<int32_t>(), al->status.as<int32_t>(),
+                                      al->scalars.as<unsigned long long>());
   CK(cudaGetLastError());
   CK(cudaEventRecord(al->ev[1], s));
   SNAP(12);
@@ -440,7 +489,7 @@ static int phase1_device(bsq_aligner *al, int64_t n, int32_t stride, int64_t *to
   RES(ochains, pool * sizeof(bsq_chain_t)); RES(oseeds, pool * sizeof(bsq_seed_t));
   RES(srt, pool * 8); RES(regs_tmp, pool * sizeof(bsq_reg_t));
   CK(cudaEventRecord(al->ev[2], s));
-  k_expand<<<nblk(n, 128), 128, 0, s>>>(opt, n, al->intv.as<bsq_intv_t>(), al->n_intv.as<int32_t>(), al->parent.as<uint8_t>(),
+  k_expand<<<nblk(n, 128), 128, 0, s>>>(opt, n, al->intv.as<bsq_pk_t>(), al->n_intv.as<int32_t>(), al->parent.as<uint8_t>(),
                                          al->sa_off.as<int64_t>(), al->ranks.as<uint64_t>());
   CK(cudaGetLastError());
   if (total_sa > 0) {
@@ -449,14 +498,14 @@ static int phase1_device(bsq_aligner *al, int64_t n, int32_t stride, int64_t *to
   }
   CK(cudaEventRecord(al->ev[3], s));
   SNAP(13);
-  k_chain<<<nblk(n, 128), 128, 0, s>>>(opt, ix, n, al->lens.as<int32_t>(), al->parent.as<uint8_t>(), al->intv.as<bsq_intv_t>(),
+  k_chain<<<nblk(n, 128), 128, 0, s>>>(opt, ix, n, al->lens.as<int32_t>(), al->parent.as<uint8_t>(), al->intv.as<bsq_pk_t>(),
                                         al->n_intv.as<int32_t>(), al->sa_off.as<int64_t>(), al->pos.as<uint64_t>(),
                                         al->snodes.as<bsq_snode_t>(), al->wchains.as<bsq_wchain_t>(), al->bnodes.as<bsq_bnode_t>(),
                                         al->order.as<int32_t>(), al->ochains.as<bsq_chain_t>(), al->oseeds.as<bsq_seed_t>(),
                                         al->n_chains.as<int32_t>(), al->frac_rep.as<float>(), al->status.as<int32_t>());
   CK(cudaGetLastError());
   CK(cudaEventRecord(al->ev[4], s));
-  k_region<<<nblk(n, 128), 128, 0, s>>>(opt, ix, n, al->seqs.as<uint8_t>(), stride, al->lens.as<int32_t>(), al->parent.as<uint8_t>(),
+  k_region<<<nblk(n * 32, 128), 128, 0, s>>>(opt, ix, n, al->seqs.as<uint8_t>(), stride, al->lens.as<int32_t>(), al->parent.as<uint8_t>(),
                                          al->sa_off.as<int64_t>(), al->ochains.as<bsq_chain_t>(), al->oseeds.as<bsq_seed_t>(),
                                          al->n_chains.as<int32_t>(), al->frac_rep.as<float>(), al->srt.as<uint64_t>(),
                                          al->regs_tmp.as<bsq_reg_t>(), al->n_regs.as<int32_t>());

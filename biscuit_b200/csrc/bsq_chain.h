@@ -10,6 +10,7 @@
 #pragma once
 #include "bsq_common.h"
 #include "bsq_fm.h"
+#include "bsq_seed.h"
 #include "bsq_sort.h"
 
 #define BSQ_BT_T 3
@@ -262,7 +263,7 @@ struct bsq_chain_result_t {
 // interval (computed by the SA-lookup kernel).  Results go to out_chains / out_seeds (both with
 // room for ws.cap entries).
 BSQ_HD bsq_chain_result_t bsq_chain_task(const bsq_devopt_t &opt, const bsq_devidx_t &ix, int parent, int l_seq,
-                                         const bsq_intv_t *intv, int n_intv, const uint64_t *sa_pos, bsq_chain_ws_t &ws,
+                                         const bsq_pk_t *intv, int n_intv, const uint64_t *sa_pos, bsq_chain_ws_t &ws,
                                          bsq_chain_t *out_chains, bsq_seed_t *out_seeds) {
   bsq_chain_result_t res;
   res.n_chains = 0; res.n_seeds = 0; res.status = 0; res.frac_rep = 0.f;
@@ -272,8 +273,8 @@ BSQ_HD bsq_chain_result_t bsq_chain_task(const bsq_devopt_t &opt, const bsq_devi
   // length of the read covered by repetitive seeds (memchain.c:294-301)
   int b = 0, e = 0, l_rep = 0;
   for (int i = 0; i < n_intv; ++i) {
-    if (intv[i].x[2] <= (uint64_t)(uint32_t)opt.max_occ) continue;
-    int sb = (int)(intv[i].info >> 32), se = (int)(uint32_t)intv[i].info;
+    if (bsq_pk_x2(intv[i]) <= (uint64_t)(uint32_t)opt.max_occ) continue;
+    int sb = bsq_pk_beg(intv[i]), se = bsq_pk_end(intv[i]);
     if (sb > e) { l_rep += e - b; b = sb; e = se; }
     else e = e > se ? e : se;
   }
@@ -285,20 +286,22 @@ BSQ_HD bsq_chain_result_t bsq_chain_task(const bsq_devopt_t &opt, const bsq_devi
   int n_sn = 0, n_ch = 0;
   int64_t sa_i = 0;
   for (int i = 0; i < n_intv; ++i) {
-    const bsq_intv_t &v = intv[i];
-    const int slen = (int)((uint32_t)v.info - (uint32_t)(v.info >> 32));
-    const uint64_t n_pre = v.x[2] < (uint64_t)(uint32_t)opt.max_occ ? v.x[2] : (uint64_t)(uint32_t)opt.max_occ;
+    const bsq_pk_t pk = intv[i];
+    const uint64_t v_x0 = bsq_pk_x0(pk), v_x2 = bsq_pk_x2(pk);
+    const int v_beg = bsq_pk_beg(pk);
+    const int slen = bsq_pk_end(pk) - v_beg;
+    const uint64_t n_pre = v_x2 < (uint64_t)(uint32_t)opt.max_occ ? v_x2 : (uint64_t)(uint32_t)opt.max_occ;
     uint32_t count = 0;
     uint64_t k;
-    for (k = 0; k < v.x[2] && count < (uint32_t)opt.max_occ && ((count > 5 && k < (uint64_t)(uint32_t)opt.max_occ) || count <= 5); ++k) {
-      const int64_t rbeg = (int64_t)(k < n_pre ? sa_pos[sa_i + (int64_t)k] : bsq_sa(fm, v.x[0] + k));
+    for (k = 0; k < v_x2 && count < (uint32_t)opt.max_occ && ((count > 5 && k < (uint64_t)(uint32_t)opt.max_occ) || count <= 5); ++k) {
+      const int64_t rbeg = (int64_t)(k < n_pre ? sa_pos[sa_i + (int64_t)k] : bsq_sa(fm, v_x0 + k));
       const int rid = bsq_intv2rid(ix, rbeg, rbeg + slen);
       if (rid < 0) continue;
       if ((opt.bsstrand & 1) && bsq_getbss(ix, parent, rbeg) != (opt.bsstrand >> 1)) continue;
       if (n_sn >= ws.cap) { res.status = 1; return res; }
       const int si = n_sn++;
       bsq_snode_t &s = ws.snodes[si];
-      s.rbeg = rbeg; s.qbeg = (int)(v.info >> 32); s.len = slen; s.next = -1; s.pad_ = 0;
+      s.rbeg = rbeg; s.qbeg = v_beg; s.len = slen; s.next = -1; s.pad_ = 0;
       bool to_add = true;
       if (tree.n_keys > 0) {
         int lower = bsq_bt_lower(tree, rbeg);

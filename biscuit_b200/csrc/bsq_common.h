@@ -31,7 +31,7 @@
 #define BSQ_CTR_REFB 4     // reference bases decoded from the 2-bit pac
 
 #define BSQ_MAX_READ_LEN 256  // longest read the device seeding kernels accept
-#define BSQ_MAX_INTV 160      // per (read,conversion) capacity of the SMEM interval list
+#define BSQ_MAX_INTV 384      // per (read,conversion) capacity of the SMEM interval list (a GRCh38-sized 3-letter index yields >100 SMEMs per read)
 
 // Same fields and meaning as the reference's bwtintv_t (lib/aln/bwt.h:80-82):
 // x[0] = interval start in the searched index, x[1] = start in the complementary index,

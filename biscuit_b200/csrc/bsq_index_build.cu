@@ -40,9 +40,12 @@
 
 __device__ __forceinline__ int txt_sym(const uint32_t *T, uint64_t i) { return (T[i >> 4] >> ((~i & 15) << 1)) & 3; }
 
-// 31 symbols starting at i as a 62-bit number, zero padded past n; low 2 bits: 1 if i < n else the whole key is 0
+// Sort key of the suffix starting at i, 31 symbols at a time.  Bit 63 = 1 while the suffix still has
+// symbols (i < n), followed by 31 symbols (bits 62..1, zero padded past the end of the text).  A suffix
+// that is exhausted (i >= n) sorts before every live one ('$' is the smallest symbol) and, among
+// exhausted suffixes of one tie group, the shorter one first: key = 64 - (i - n).
 __device__ __forceinline__ uint64_t txt_key31(const uint32_t *T, uint64_t n, uint64_t i) {
-  if (i >= n) return 0;
+  if (i >= n) { uint64_t e = i - n; return 64 - (e < 63 ? e : 63); }
   const uint64_t w = i >> 4;
   const int sh = (int)(i & 15) << 1;  // bits to drop from the first word
   uint64_t hi = ((uint64_t)T[w] << 32) | T[w + 1];
@@ -50,11 +53,11 @@ __device__ __forceinline__ uint64_t txt_key31(const uint32_t *T, uint64_t n, uin
   uint64_t v = sh ? (hi << sh) | (lo >> (64 - sh)) : hi;  // 32 symbols starting at i (words past the end are zero)
   uint64_t rem = n - i;                                    // real symbols available
   if (rem < 31) v &= ~((1ull << ((32 - rem) << 1)) - 1);
-  return (v & ~3ull) | 1ull;
+  return (1ull << 63) | ((v >> 2) << 1);
 }
 
 __device__ __forceinline__ uint32_t txt_prefix(const uint32_t *T, uint64_t n, uint64_t i) {
-  return (uint32_t)(txt_key31(T, n, i) >> (64 - 2 * PFX_SYMS));
+  return (uint32_t)(txt_key31(T, n, i) >> (63 - 2 * PFX_SYMS)) & (PFX_BUCKETS - 1);
 }
 
 // ---- kernels ----
@@ -441,7 +444,8 @@ extern "C" int bsq_index_build(const uint8_t *pac, int64_t l_pac, int32_t n_seqs
   }
   for (int parent = 1; parent >= 0; --parent) {
     void *a = nullptr, *b = nullptr;
-    const uint64_t chunk_max = 1ull << 29;
+    uint64_t chunk_max = 1ull << 29;  // suffixes sorted per pass (4 x 8 bytes each); BSQ_INDEX_CHUNK overrides (tests)
+    if (const char *e = getenv("BSQ_INDEX_CHUNK")) { long long v = atoll(e); if (v > 0) chunk_max = (uint64_t)v; }
     rc = build_half(ix->d.pac, l_pac, parent, 32, chunk_max, &ix->d.fm[parent], &a, &b, &ix->bwt_words[parent], &ix->n_sa[parent], stats);
     if (rc) goto done;
     bsq_index_adopt(ix, a); bsq_index_adopt(ix, b);

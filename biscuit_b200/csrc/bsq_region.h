@@ -26,30 +26,59 @@ BSQ_HD int bsq_cal_max_gap(const bsq_devopt_t &opt, int qlen) {
   return l < opt.w << 1 ? l : opt.w << 1;
 }
 
-struct bsq_q_fwd { const uint8_t *q; BSQ_HD int operator()(int j) const { return q[j]; } };
-struct bsq_q_rev { const uint8_t *q; int last; BSQ_HD int operator()(int j) const { return q[last - j]; } };
-struct bsq_t_fwd { const bsq_devidx_t *ix; int64_t p0; BSQ_HD int operator()(int i) const { return bsq_ref_base(*ix, p0 + i); } };
-struct bsq_t_rev { const bsq_devidx_t *ix; int64_t p0; BSQ_HD int operator()(int i) const { return bsq_ref_base(*ix, p0 - i); } };
+// Query / target accessors shared by left (step = -1) and right (step = +1) extensions, so that the
+// DP code is instantiated once.  The target comes either from the packed reference (ix != 0) or from
+// a plain nt4 buffer (kernel-level test entry point).
+struct bsq_qacc_t {
+  const uint8_t *q;
+  int step;
+  BSQ_HD int operator()(int j) const { return q[j * step]; }
+};
+struct bsq_tacc_t {
+  const bsq_devidx_t *ix;
+  const uint8_t *buf;
+  int64_t p0;
+  int step;
+  BSQ_HD int operator()(int i) const { return ix ? bsq_ref_base(*ix, p0 + (int64_t)i * step) : buf[i]; }
+};
+
+// Execution policy of the region builder.  The scalar policy runs everything in the calling thread
+// (host emulation, k_extend).  The CUDA warp policy (bsq_ksw_warp.cuh) runs the control flow
+// redundantly and uniformly in all 32 lanes, lets lane 0 do the stores, and spreads each DP row
+// over the lanes.
+struct bsq_scalar_policy {
+  BSQ_HD static bool leader() { return true; }
+  BSQ_HD static void sync() {}
+  // asymmetric_flt_seed (memchain.c:138-149): ref T under read C, or ref A under read G, inside the seed
+  BSQ_HD static bool asym_conflict(const bsq_devidx_t &ix, const bsq_seed_t &s, const uint8_t *query) {
+    for (int i = 0; i < s.len; ++i) {
+      const int r = bsq_ref_base(ix, s.rbeg + i), qv = query[s.qbeg + i];
+      if ((r == 3 && qv == 1) || (r == 0 && qv == 2)) return true;
+    }
+    return false;
+  }
+  BSQ_HD static bsq_ext_result_t extend(int qlen, bsq_qacc_t qget, int tlen, bsq_tacc_t tget, const int8_t *mat, int o_del, int e_del, int o_ins,
+                                        int e_ins, int w, int end_bonus, int zdrop, int h0, bsq_ksw_scratch_t *scr) {
+    return bsq_ksw_extend(qlen, qget, tlen, tget, mat, o_del, e_del, o_ins, e_ins, w, end_bonus, zdrop, h0, *scr);
+  }
+};
 
 // mem_chain2region1 for one seed list.  regs[reg0..*n_regs) are the regions of this task so far.
+template <typename X>
 BSQ_HD void bsq_chain2region1(const bsq_devopt_t &opt, const bsq_devidx_t &ix, int64_t rmax0, int64_t rmax1, int rid,
                               int l_query, const uint8_t *query, const bsq_seed_t *seeds, int n_seeds, int parent,
-                              float frac_rep, uint64_t *srt, bsq_ksw_scratch_t &ksw, bsq_reg_t *regs, int *n_regs) {
+                              float frac_rep, uint64_t *srt, bsq_ksw_scratch_t *ksw, bsq_reg_t *regs, int *n_regs) {
   const int8_t *mat = parent ? opt.ctmat : opt.gamat;
-  for (int i = 0; i < n_seeds; ++i) srt[i] = (uint64_t)(uint32_t)seeds[i].len << 32 | (uint32_t)i;  // score == len
   struct u64_less { BSQ_HD bool operator()(uint64_t a, uint64_t b) const { return a < b; } };
-  bsq_introsort(srt, (int64_t)n_seeds, u64_less());
+  if (X::leader()) {
+    for (int i = 0; i < n_seeds; ++i) srt[i] = (uint64_t)(uint32_t)seeds[i].len << 32 | (uint32_t)i;  // score == len
+    bsq_introsort(srt, (int64_t)n_seeds, u64_less());
+  }
+  X::sync();
   for (int k = n_seeds - 1; k >= 0; --k) {
     const bsq_seed_t &s = seeds[(uint32_t)srt[k]];
     // asymmetric_flt_seed: reject ref T/read C and ref A/read G inside the seed
-    {
-      bool bad = false;
-      for (int i = 0; i < s.len; ++i) {
-        const int r = bsq_ref_base(ix, s.rbeg + i), qv = query[s.qbeg + i];
-        if ((r == 3 && qv == 1) || (r == 0 && qv == 2)) { bad = true; break; }
-      }
-      if (bad) continue;
-    }
+    if (X::asym_conflict(ix, s, query)) continue;
     // was this seed already covered by an earlier extension?
     int u;
     for (u = 0; u < *n_regs; ++u) {
@@ -77,26 +106,31 @@ BSQ_HD void bsq_chain2region1(const bsq_devopt_t &opt, const bsq_devidx_t &ix, i
         if (s.qbeg <= t.qbeg && s.qbeg + s.len - t.qbeg >= s.len >> 2 && t.qbeg - s.qbeg != t.rbeg - s.rbeg) break;
         if (t.qbeg <= s.qbeg && t.qbeg + t.len - s.qbeg >= s.len >> 2 && s.qbeg - t.qbeg != s.rbeg - t.rbeg) break;
       }
-      if (i == n_seeds) { srt[k] = 0; continue; }
+      if (i == n_seeds) {
+        X::sync();  // every lane has finished reading srt[]
+        if (X::leader()) srt[k] = 0;
+        X::sync();
+        continue;
+      }
     }
     // ---- extension ----
-    bsq_reg_t &reg = regs[(*n_regs)++];
+    bsq_reg_t reg;
     int aw0 = opt.w, aw1 = opt.w;
     reg.rb = reg.re = 0; reg.qb = reg.qe = 0; reg.w = opt.w; reg.score = reg.truesc = -1; reg.rid = rid;
     reg.seedcov = 0; reg.seedlen0 = 0; reg.frac_rep = 0.f; reg.bss = reg.parent = 0; reg.pad_[0] = reg.pad_[1] = 0;
     if (s.qbeg == 0) {
       reg.score = reg.truesc = s.len * opt.a; reg.qb = 0; reg.rb = s.rbeg;
     } else {
-      bsq_q_rev qa; qa.q = query; qa.last = s.qbeg - 1;
-      bsq_t_rev ta; ta.ix = &ix; ta.p0 = s.rbeg - 1;
+      bsq_qacc_t qa; qa.q = query + s.qbeg - 1; qa.step = -1;
+      bsq_tacc_t ta; ta.ix = &ix; ta.buf = nullptr; ta.p0 = s.rbeg - 1; ta.step = -1;
       const int tlen = (int)(s.rbeg - rmax0);
       bsq_ext_result_t r;
       r.score = 0; r.qle = r.tle = r.gtle = 0; r.gscore = -1; r.max_off = 0;
       for (int i = 0; i < 2; ++i) {
         const int prev = reg.score;
         aw0 = opt.w << i;
-        r = bsq_ksw_extend(s.qbeg, qa, tlen, ta, mat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, aw0, opt.pen_clip5,
-                           opt.zdrop, s.len * opt.a, ksw);
+        r = X::extend(s.qbeg, qa, tlen, ta, mat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, aw0, opt.pen_clip5,
+                      opt.zdrop, s.len * opt.a, ksw);
         reg.score = r.score;
         if (reg.score == prev || r.max_off < (aw0 >> 1) + (aw0 >> 2)) break;
       }
@@ -110,16 +144,16 @@ BSQ_HD void bsq_chain2region1(const bsq_devopt_t &opt, const bsq_devidx_t &ix, i
       reg.qe = l_query; reg.re = s.rbeg + s.len;
     } else {
       const int sc0 = reg.score, qe = s.qbeg + s.len;
-      bsq_q_fwd qa; qa.q = query + qe;
-      bsq_t_fwd ta; ta.ix = &ix; ta.p0 = s.rbeg + s.len;
+      bsq_qacc_t qa; qa.q = query + qe; qa.step = 1;
+      bsq_tacc_t ta; ta.ix = &ix; ta.buf = nullptr; ta.p0 = s.rbeg + s.len; ta.step = 1;
       const int tlen = (int)(rmax1 - (s.rbeg + s.len));
       bsq_ext_result_t r;
       r.score = 0; r.qle = r.tle = r.gtle = 0; r.gscore = -1; r.max_off = 0;
       for (int i = 0; i < 2; ++i) {
         const int prev = reg.score;
         aw1 = opt.w << i;
-        r = bsq_ksw_extend(l_query - qe, qa, tlen, ta, mat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, aw1,
-                           opt.pen_clip3, opt.zdrop, sc0, ksw);
+        r = X::extend(l_query - qe, qa, tlen, ta, mat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, aw1,
+                      opt.pen_clip3, opt.zdrop, sc0, ksw);
         reg.score = r.score;
         if (reg.score == prev || r.max_off < (aw1 >> 1) + (aw1 >> 2)) break;
       }
@@ -131,7 +165,7 @@ BSQ_HD void bsq_chain2region1(const bsq_devopt_t &opt, const bsq_devidx_t &ix, i
     }
     reg.bss = (uint8_t)bsq_getbss(ix, parent, reg.rb);
     reg.parent = (uint8_t)parent;
-    if (bsq_getbss(ix, parent, reg.re) != reg.bss) { --(*n_regs); continue; }  // crosses the strand boundary
+    if (bsq_getbss(ix, parent, reg.re) != reg.bss) continue;  // crosses the strand boundary: dropped
     int cov = 0;
     for (int i = 0; i < n_seeds; ++i) {
       const bsq_seed_t &t = seeds[i];
@@ -141,13 +175,17 @@ BSQ_HD void bsq_chain2region1(const bsq_devopt_t &opt, const bsq_devidx_t &ix, i
     reg.w = aw0 > aw1 ? aw0 : aw1;
     reg.seedlen0 = s.len;
     reg.frac_rep = frac_rep;
+    if (X::leader()) regs[*n_regs] = reg;
+    ++(*n_regs);
+    X::sync();
   }
 }
 
 // mem_chain2region for one task.  Returns the number of regions written to regs[].
+template <typename X>
 BSQ_HD int bsq_chain2region(const bsq_devopt_t &opt, const bsq_devidx_t &ix, int parent, int l_query, const uint8_t *query,
                             const bsq_chain_t *chains, int n_chains, const bsq_seed_t *seeds, float frac_rep,
-                            uint64_t *srt, bsq_ksw_scratch_t &ksw, bsq_reg_t *regs) {
+                            uint64_t *srt, bsq_ksw_scratch_t *ksw, bsq_reg_t *regs) {
   int n_regs = 0;
   const int64_t l_pac = ix.l_pac;
   for (int ci = 0; ci < n_chains; ++ci) {
@@ -180,9 +218,9 @@ BSQ_HD int bsq_chain2region(const bsq_devopt_t &opt, const bsq_devidx_t &ix, int
     rmax0 = rmax0 > far_beg ? rmax0 : far_beg;
     rmax1 = rmax1 < far_end ? rmax1 : far_end;
     const int n0 = n_regs;
-    bsq_chain2region1(opt, ix, rmax0, rmax1, rid, l_query, query, cs, c.n_seeds, parent, frac_rep, srt, ksw, regs, &n_regs);
+    bsq_chain2region1<X>(opt, ix, rmax0, rmax1, rid, l_query, query, cs, c.n_seeds, parent, frac_rep, srt, ksw, regs, &n_regs);
     if (n_regs == n0 && c.n_extra > 0)
-      bsq_chain2region1(opt, ix, rmax0, rmax1, rid, l_query, query, cs + c.n_seeds, c.n_extra, parent, frac_rep, srt, ksw,
+      bsq_chain2region1<X>(opt, ix, rmax0, rmax1, rid, l_query, query, cs + c.n_seeds, c.n_extra, parent, frac_rep, srt, ksw,
                         regs, &n_regs);
   }
   return n_regs;

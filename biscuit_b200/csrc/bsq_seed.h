@@ -1,174 +1,249 @@
 // SMEM seeding for one (read, conversion) task: the three passes of mem_collect_intv
-// (lib/aln/memchain.c:50-106) over bwt_smem1a (lib/aln/bwt.c:307-370) and
-// bwt_seed_strategy1 (lib/aln/bwt.c:376-396).  Per-task scratch lives in thread-local arrays
-// (interleaved local memory on the GPU), the result list goes to the caller's buffer.
+// (lib/aln/memchain.c:50-106) over bwt_smem1a (lib/aln/bwt.c:307-370) and bwt_seed_strategy1
+// (lib/aln/bwt.c:376-396), re-organised for SIMT execution.
+//
+// The reference's loops are turned inside out into a resumable state machine whose only
+// suspension point is "I need one bwt_extend": next() runs the cheap control logic up to the
+// next extension request, the caller performs the extension (the random 64-byte FM-index
+// gathers -- the one long-latency operation) and hands the result to consume().  In the CUDA
+// kernel all 32 lanes of a warp therefore meet at a single extend site every iteration and
+// their DRAM round trips overlap, instead of each lane serialising its own (v1 measured 4 of
+// 32 lanes active, profiles/README.md).  Candidate intervals are kept as 16-byte packed
+// records (3 x 34-bit positions + 2 x 9-bit read coordinates) to keep the thread-local scratch
+// that spills through L2 small.
 #pragma once
 #include "bsq_fm.h"
 #include "bsq_sort.h"
 
-// Scratch entry for the forward/backward sweeps: interval + end coordinate on the read.
-struct bsq_cand_t {
-  uint64_t x0, x1, x2;
-  int32_t end, pad_;
+// ---- packed bi-interval: x0,x1,x2 < 2^34, beg,end < 2^9 ----
+struct bsq_pk_t {
+  uint64_t w0, w1;
 };
+BSQ_HD bsq_pk_t bsq_pk_make(uint64_t x0, uint64_t x1, uint64_t x2, int beg, int end) {
+  bsq_pk_t p;
+  p.w0 = x0 | (x1 << 34);
+  p.w1 = (x1 >> 30) | (x2 << 4) | ((uint64_t)(uint32_t)beg << 38) | ((uint64_t)(uint32_t)end << 47);
+  return p;
+}
+BSQ_HD uint64_t bsq_pk_x0(const bsq_pk_t &p) { return p.w0 & 0x3FFFFFFFFull; }
+BSQ_HD uint64_t bsq_pk_x1(const bsq_pk_t &p) { return (p.w0 >> 34) | ((p.w1 & 0xF) << 30); }
+BSQ_HD uint64_t bsq_pk_x2(const bsq_pk_t &p) { return (p.w1 >> 4) & 0x3FFFFFFFFull; }
+BSQ_HD int bsq_pk_beg(const bsq_pk_t &p) { return (int)((p.w1 >> 38) & 0x1FF); }
+BSQ_HD int bsq_pk_end(const bsq_pk_t &p) { return (int)((p.w1 >> 47) & 0x1FF); }
+BSQ_HD uint64_t bsq_pk_info(const bsq_pk_t &p) { return (uint64_t)bsq_pk_beg(p) << 32 | (uint32_t)bsq_pk_end(p); }
+BSQ_HD bsq_intv_t bsq_pk_unpack(const bsq_pk_t &p) {
+  bsq_intv_t v;
+  v.x[0] = bsq_pk_x0(p); v.x[1] = bsq_pk_x1(p); v.x[2] = bsq_pk_x2(p); v.info = bsq_pk_info(p);
+  return v;
+}
 
 struct bsq_seed_scratch_t {
-  bsq_cand_t a[2][BSQ_MAX_READ_LEN + 1];
-  bsq_intv_t one[BSQ_MAX_READ_LEN + 1];  // SMEMs of a single bwt_smem1a call (the reference's `_mem`)
+  bsq_pk_t a[2][BSQ_MAX_READ_LEN + 1];  // the reference's tmpvec[0..1] (curr / prev candidate lists)
+  uint8_t q[BSQ_MAX_READ_LEN];          // converted read
 };
 
-BSQ_HD bsq_intv_t bsq_cand2intv(const bsq_cand_t &c) {
-  bsq_intv_t r;
-  r.x[0] = c.x0; r.x[1] = c.x1; r.x[2] = c.x2; r.info = (uint64_t)(uint32_t)c.end;
-  return r;
-}
-BSQ_HD bsq_cand_t bsq_intv2cand(const bsq_intv_t &v, int end) {
-  bsq_cand_t c;
-  c.x0 = v.x[0]; c.x1 = v.x[1]; c.x2 = v.x[2]; c.end = end; c.pad_ = 0;
-  return c;
+// one pending bwt_extend: interval (x0,x1,x2), direction, and the symbol whose child is wanted
+struct bsq_ext_req_t {
+  uint64_t x0, x1, x2;
+  int back, c;
+};
+
+// bwt_extend (bwt.c:278-293) restricted to the one child that is used.  back=1 extends to the
+// left in `fm`; back=0 is the forward extension = a backward step in the complementary index.
+BSQ_HD void bsq_extend1(const bsq_fm_t &fm, const bsq_fm_t &fmc, const bsq_ext_req_t &r, uint64_t &o0, uint64_t &o1, uint64_t &o2) {
+  const bsq_fm_t &f = r.back ? fm : fmc;
+  const uint64_t xa = r.back ? r.x0 : r.x1;  // coordinate in the index being stepped
+  const uint64_t xb = r.back ? r.x1 : r.x0;  // coordinate in the other index
+  uint64_t tk[4], tl[4];
+  BSQ_CTR(BSQ_CTR_EXTENDS, 1);
+  bsq_2occ4(f, xa - 1, xa - 1 + r.x2, tk, tl);
+  const uint64_t na = f.L2[r.c] + 1 + tk[r.c];
+  uint64_t nb = xb + (xa <= f.primary && xa + r.x2 - 1 >= f.primary);
+#pragma unroll
+  for (int s = 3; s > 0; --s)
+    if (s > r.c) nb += tl[s] - tk[s];
+  o2 = tl[r.c] - tk[r.c];
+  if (r.back) { o0 = na; o1 = nb; } else { o1 = na; o0 = nb; }
 }
 
-// All SMEMs through query position x whose interval size is >= min_intv (bwt.c:307-370 with
-// max_intv == 0, the only way the reference calls it).  q is the converted read.  Returns the
-// next x; the SMEMs, sorted by start, are left in scr.one[0..*n_out).
-BSQ_HD int bsq_smem1(const bsq_fm_t &fm, const bsq_fm_t &fmc, int len, const uint8_t *q, int x, int min_intv,
-                     bsq_seed_scratch_t &scr, int *n_out) {
-  *n_out = 0;
-  if (q[x] > 3) return x + 1;
-  if (min_intv < 1) min_intv = 1;
-  bsq_cand_t *curr = scr.a[0], *prev = scr.a[1];
-  int n_curr = 0, n_prev;
-  bsq_intv_t ik, ok[4];
-  bsq_set_intv(fm, fmc, q[x], ik);
-  int ik_end = x + 1, i;
-  // forward sweep: remember the interval every time its size changes
-  for (i = x + 1; i < len; ++i) {
-    if (q[i] < 4) {
-      int c = 3 - q[i];
-      bsq_extend<0>(fmc, ik, ok);
-      if (ok[c].x[2] != ik.x[2]) {
-        curr[n_curr++] = bsq_intv2cand(ik, ik_end);
-        if (ok[c].x[2] < (uint64_t)min_intv) break;
-      }
-      ik = ok[c];
-      ik_end = i + 1;
-    } else {
-      curr[n_curr++] = bsq_intv2cand(ik, ik_end);
-      break;
-    }
+enum { BSQ_ST_NEXT = 0, BSQ_ST_FWD, BSQ_ST_BWD, BSQ_ST_S1, BSQ_ST_DONE };
+
+struct bsq_seed_machine_t {
+  // immutable per task
+  int len, cap;
+  int min_seed_len, split_len, split_width, start_width, max_mem_intv;
+  // state
+  int st, pass, x, i, j, k2, old_n;
+  int n_curr, n_prev, n_tmp, n_out, cur, min_intv, ret, overflow;
+  uint64_t ik0, ik1, ik2;
+  int ik_end;
+};
+
+BSQ_HD void bsq_sm_init(bsq_seed_machine_t &m, const bsq_devopt_t &opt, int len, int cap) {
+  m.len = len; m.cap = cap;
+  m.min_seed_len = opt.min_seed_len; m.split_len = opt.split_len; m.split_width = opt.split_width;
+  m.start_width = opt.self_ovlp ? 2 : 1; m.max_mem_intv = opt.max_mem_intv;
+  m.st = BSQ_ST_NEXT; m.pass = 1; m.x = 0; m.i = m.j = m.k2 = m.old_n = 0;
+  m.n_curr = m.n_prev = m.n_tmp = m.n_out = 0; m.cur = 0; m.min_intv = 1; m.ret = 0; m.overflow = 0;
+  m.ik0 = m.ik1 = m.ik2 = 0; m.ik_end = 0;
+}
+
+// begin bwt_smem1a at query position x (bwt.c:313-322)
+BSQ_HD void bsq_sm_start_smem(bsq_seed_machine_t &m, const bsq_fm_t &fm, const bsq_fm_t &fmc, const uint8_t *q, int x, int min_intv) {
+  m.n_tmp = 0; m.n_curr = 0;
+  m.x = x;
+  if (q[x] > 3) { m.ret = x + 1; m.st = BSQ_ST_NEXT; return; }
+  m.min_intv = min_intv < 1 ? 1 : min_intv;
+  const int c = q[x];
+  m.ik0 = fm.L2[c] + 1; m.ik2 = fm.L2[c + 1] - fm.L2[c]; m.ik1 = fmc.L2[3 - c] + 1;
+  m.ik_end = x + 1; m.i = x + 1;
+  m.st = BSQ_ST_FWD;
+}
+
+// end of the forward sweep: longest matches first, then walk left (bwt.c:340-345)
+BSQ_HD void bsq_sm_finish_fwd(bsq_seed_machine_t &m, bsq_seed_scratch_t &scr) {
+  bsq_pk_t *curr = scr.a[m.cur];
+  for (int a = 0, b = m.n_curr - 1; a < b; ++a, --b) { bsq_pk_t t = curr[a]; curr[a] = curr[b]; curr[b] = t; }
+  m.ret = bsq_pk_end(curr[0]);
+  m.cur ^= 1;  // the sweep result becomes `prev`
+  m.n_prev = m.n_curr; m.n_curr = 0;
+  m.i = m.x - 1; m.j = 0; m.n_tmp = 0;
+  m.st = BSQ_ST_BWD;
+}
+
+// a candidate cannot be extended further to the left (bwt.c:350-356)
+BSQ_HD void bsq_sm_bwd_stop(bsq_seed_machine_t &m, const bsq_pk_t &p, bsq_pk_t *out) {
+  if (m.n_curr != 0) return;  // contained in a longer match kept in this round
+  if (m.n_tmp == 0 || m.i + 1 < bsq_pk_beg(out[m.n_out + m.n_tmp - 1])) {
+    if (m.n_out + m.n_tmp >= m.cap) { m.overflow = 1; return; }
+    out[m.n_out + m.n_tmp] = bsq_pk_make(bsq_pk_x0(p), bsq_pk_x1(p), bsq_pk_x2(p), m.i + 1, bsq_pk_end(p));
+    ++m.n_tmp;
   }
-  if (i == len) curr[n_curr++] = bsq_intv2cand(ik, ik_end);
-  // longest matches first
-  for (int a = 0, b = n_curr - 1; a < b; ++a, --b) { bsq_cand_t t = curr[a]; curr[a] = curr[b]; curr[b] = t; }
-  const int ret = curr[0].end;
-  { bsq_cand_t *t = curr; curr = prev; prev = t; }
-  n_prev = n_curr;
-  // backward sweep
-  int n_mem = 0;
-  for (i = x - 1; i >= -1; --i) {
-    const int c = i < 0 ? -1 : (q[i] < 4 ? q[i] : -1);
-    n_curr = 0;
-    for (int j = 0; j < n_prev; ++j) {
-      const bsq_cand_t &p = prev[j];
-      bool stop = c < 0;
-      if (!stop) {
-        bsq_extend<1>(fm, bsq_cand2intv(p), ok);
-        stop = ok[c].x[2] < (uint64_t)min_intv;
-      }
-      if (stop) {
-        // cannot be extended further to the left: a MEM unless a longer one was kept in this round
-        if (n_curr == 0) {
-          if (n_mem == 0 || (uint32_t)(i + 1) < (uint32_t)(scr.one[n_mem - 1].info >> 32)) {
-            bsq_intv_t m = bsq_cand2intv(p);
-            m.info |= (uint64_t)(i + 1) << 32;
-            scr.one[n_mem++] = m;
+}
+
+// end of one bwt_smem1a call: order by start, keep seeds of at least min_seed_len (memchain.c:69-71)
+BSQ_HD void bsq_sm_finish_bwd(bsq_seed_machine_t &m, bsq_pk_t *out) {
+  bsq_pk_t *t = out + m.n_out;
+  for (int a = 0, b = m.n_tmp - 1; a < b; ++a, --b) { bsq_pk_t s = t[a]; t[a] = t[b]; t[b] = s; }
+  int kept = 0;
+  for (int a = 0; a < m.n_tmp; ++a)
+    if (bsq_pk_end(t[a]) - bsq_pk_beg(t[a]) >= m.min_seed_len) t[kept++] = t[a];
+  m.n_out += kept;
+  m.n_tmp = 0;
+  if (m.pass == 1) m.x = m.ret;
+  m.st = BSQ_ST_NEXT;
+}
+
+// Run the control logic up to the next extension.  Returns false when the task is finished
+// (out[0..n_out) then holds the unsorted interval list).
+BSQ_HD bool bsq_sm_next(bsq_seed_machine_t &m, const bsq_fm_t &fm, const bsq_fm_t &fmc, bsq_seed_scratch_t &scr, bsq_pk_t *out,
+                        bsq_ext_req_t &req) {
+  const uint8_t *q = scr.q;
+  for (;;) {
+    if (m.overflow) { m.st = BSQ_ST_DONE; return false; }
+    switch (m.st) {
+      case BSQ_ST_NEXT: {
+        if (m.pass == 1) {  // every SMEM (memchain.c:65-73)
+          while (m.x < m.len && q[m.x] > 3) ++m.x;
+          if (m.x >= m.len) { m.pass = 2; m.old_n = m.n_out; m.k2 = 0; break; }
+          bsq_sm_start_smem(m, fm, fmc, q, m.x, m.start_width);
+          if (m.st == BSQ_ST_NEXT) m.x = m.ret;
+        } else if (m.pass == 2) {  // re-seed from the middle of long, rare SMEMs (memchain.c:76-85)
+          int found = 0;
+          while (m.k2 < m.old_n) {
+            const bsq_pk_t p = out[m.k2++];
+            const int start = bsq_pk_beg(p), end = bsq_pk_end(p);
+            if (end - start < m.split_len || bsq_pk_x2(p) > (uint64_t)m.split_width) continue;
+            bsq_sm_start_smem(m, fm, fmc, q, (start + end) >> 1, (int)(bsq_pk_x2(p) + 1));
+            found = 1;
+            break;
           }
+          if (!found) { m.pass = 3; m.x = 0; }
+        } else {  // greedy forward seeds (memchain.c:88-103)
+          if (m.max_mem_intv <= 0) { m.st = BSQ_ST_DONE; return false; }
+          while (m.x < m.len && q[m.x] > 3) ++m.x;
+          if (m.x >= m.len) { m.st = BSQ_ST_DONE; return false; }
+          const int c = q[m.x];
+          m.ik0 = fm.L2[c] + 1; m.ik2 = fm.L2[c + 1] - fm.L2[c]; m.ik1 = fmc.L2[3 - c] + 1;
+          m.i = m.x + 1;
+          m.st = BSQ_ST_S1;
         }
-      } else if (n_curr == 0 || ok[c].x[2] != curr[n_curr - 1].x2) {
-        curr[n_curr++] = bsq_intv2cand(ok[c], p.end);
+        break;
       }
+      case BSQ_ST_FWD: {
+        if (m.i == m.len || q[m.i] > 3) {  // read end or ambiguous base closes the sweep (bwt.c:335-340)
+          scr.a[m.cur][m.n_curr++] = bsq_pk_make(m.ik0, m.ik1, m.ik2, 0, m.ik_end);
+          bsq_sm_finish_fwd(m, scr);
+          break;
+        }
+        req.x0 = m.ik0; req.x1 = m.ik1; req.x2 = m.ik2; req.back = 0; req.c = 3 - q[m.i];
+        return true;
+      }
+      case BSQ_ST_BWD: {
+        if (m.j == m.n_prev) {  // one column to the left done (bwt.c:362-363)
+          if (m.n_curr == 0) { bsq_sm_finish_bwd(m, out); break; }
+          m.cur ^= 1; m.n_prev = m.n_curr; m.n_curr = 0; --m.i; m.j = 0;
+          if (m.i < -1) bsq_sm_finish_bwd(m, out);
+          break;
+        }
+        const int c = m.i < 0 ? -1 : (q[m.i] < 4 ? q[m.i] : -1);
+        const bsq_pk_t p = scr.a[m.cur ^ 1][m.j];
+        if (c < 0) { bsq_sm_bwd_stop(m, p, out); ++m.j; break; }
+        req.x0 = bsq_pk_x0(p); req.x1 = bsq_pk_x1(p); req.x2 = bsq_pk_x2(p); req.back = 1; req.c = c;
+        return true;
+      }
+      case BSQ_ST_S1: {
+        if (m.i == m.len) { m.x = m.len; m.st = BSQ_ST_NEXT; break; }
+        if (q[m.i] > 3) { m.x = m.i + 1; m.st = BSQ_ST_NEXT; break; }
+        req.x0 = m.ik0; req.x1 = m.ik1; req.x2 = m.ik2; req.back = 0; req.c = 3 - q[m.i];
+        return true;
+      }
+      default:
+        return false;
     }
-    if (n_curr == 0) break;
-    { bsq_cand_t *t = curr; curr = prev; prev = t; }
-    n_prev = n_curr;
   }
-  for (int a = 0, b = n_mem - 1; a < b; ++a, --b) { bsq_intv_t t = scr.one[a]; scr.one[a] = scr.one[b]; scr.one[b] = t; }
-  *n_out = n_mem;
-  return ret;
 }
 
-// bwt_seed_strategy1 (bwt.c:376-396).  m.x[2] == 0 when nothing was found.
-BSQ_HD int bsq_seed_strategy1(const bsq_fm_t &fm, const bsq_fm_t &fmc, int len, const uint8_t *q, int x, int min_len,
-                              int max_intv, bsq_intv_t &m) {
-  m.x[0] = m.x[1] = m.x[2] = m.info = 0;
-  if (q[x] > 3) return x + 1;
-  bsq_intv_t ik, ok[4];
-  bsq_set_intv(fm, fmc, q[x], ik);
-  for (int i = x + 1; i < len; ++i) {
-    if (q[i] >= 4) return i + 1;
-    int c = 3 - q[i];
-    bsq_extend<0>(fmc, ik, ok);
-    if (ok[c].x[2] < (uint64_t)max_intv && i - x >= min_len) {
-      m = ok[c];
-      m.info = (uint64_t)x << 32 | (uint32_t)(i + 1);
-      return i + 1;
+// Hand the result of the requested extension back to the machine.
+BSQ_HD void bsq_sm_consume(bsq_seed_machine_t &m, bsq_seed_scratch_t &scr, bsq_pk_t *out, uint64_t o0, uint64_t o1, uint64_t o2) {
+  if (m.st == BSQ_ST_FWD) {  // bwt.c:326-334
+    if (o2 != m.ik2) {
+      scr.a[m.cur][m.n_curr++] = bsq_pk_make(m.ik0, m.ik1, m.ik2, 0, m.ik_end);
+      if (o2 < (uint64_t)m.min_intv) { bsq_sm_finish_fwd(m, scr); return; }
     }
-    ik = ok[c];
+    m.ik0 = o0; m.ik1 = o1; m.ik2 = o2; m.ik_end = m.i + 1; ++m.i;
+  } else if (m.st == BSQ_ST_BWD) {  // bwt.c:349-360
+    const bsq_pk_t p = scr.a[m.cur ^ 1][m.j];
+    if (o2 < (uint64_t)m.min_intv) bsq_sm_bwd_stop(m, p, out);
+    else if (m.n_curr == 0 || o2 != bsq_pk_x2(scr.a[m.cur][m.n_curr - 1]))
+      scr.a[m.cur][m.n_curr++] = bsq_pk_make(o0, o1, o2, 0, bsq_pk_end(p));
+    ++m.j;
+  } else {  // BSQ_ST_S1, bwt.c:387-392
+    if (o2 < (uint64_t)m.max_mem_intv && m.i - m.x >= m.min_seed_len) {
+      if (o2 > 0) {  // memchain.c:95
+        if (m.n_out >= m.cap) { m.overflow = 1; return; }
+        out[m.n_out++] = bsq_pk_make(o0, o1, o2, m.x, m.i + 1);
+      }
+      m.x = m.i + 1;
+      m.st = BSQ_ST_NEXT;
+    } else {
+      m.ik0 = o0; m.ik1 = o1; m.ik2 = o2; ++m.i;
+    }
   }
-  return len;
 }
 
-struct bsq_intv_less {
-  BSQ_HD bool operator()(const bsq_intv_t &a, const bsq_intv_t &b) const { return a.info < b.info; }
+struct bsq_pk_less {
+  BSQ_HD bool operator()(const bsq_pk_t &a, const bsq_pk_t &b) const { return bsq_pk_info(a) < bsq_pk_info(b); }
 };
 
-// mem_collect_intv (memchain.c:50-106).  `out` has room for `cap` intervals; returns the number
-// found, or -1 when `cap` is too small.  On return out[] is sorted the way ks_introsort leaves it.
-BSQ_HD int bsq_collect_intv(const bsq_devopt_t &opt, const bsq_fm_t &fm, const bsq_fm_t &fmc, int len, const uint8_t *q,
-                            bsq_seed_scratch_t &scr, bsq_intv_t *out, int cap) {
-  int n = 0, x = 0, n1;
-  const int start_width = opt.self_ovlp ? 2 : 1;
-  // pass 1: every SMEM of at least min_seed_len
-  while (x < len) {
-    if (q[x] < 4) {
-      x = bsq_smem1(fm, fmc, len, q, x, start_width, scr, &n1);
-      for (int i = 0; i < n1; ++i) {
-        const bsq_intv_t &m = scr.one[i];
-        if ((uint32_t)m.info - (uint32_t)(m.info >> 32) >= (uint32_t)opt.min_seed_len) {
-          if (n == cap) return -1;
-          out[n++] = m;
-        }
-      }
-    } else ++x;
+// Sort the finished list the way ks_introsort(mem_intv) does (memchain.c:105) and count the
+// SA lookups chaining will need up front: min(x[2], max_occ) per interval (memchain.c:325-326).
+BSQ_HD int32_t bsq_sm_finalize(const bsq_seed_machine_t &m, const bsq_devopt_t &opt, bsq_pk_t *out) {
+  bsq_introsort(out, (int64_t)m.n_out, bsq_pk_less());
+  int64_t tot = 0;
+  for (int i = 0; i < m.n_out; ++i) {
+    uint64_t x2 = bsq_pk_x2(out[i]);
+    tot += (int64_t)(x2 < (uint64_t)(uint32_t)opt.max_occ ? x2 : (uint64_t)(uint32_t)opt.max_occ);
   }
-  // pass 2: re-seed from the middle of long, rare SMEMs
-  const int old_n = n;
-  for (int k = 0; k < old_n; ++k) {
-    const int start = (int)(out[k].info >> 32), end = (int32_t)out[k].info;
-    if (end - start < opt.split_len || out[k].x[2] > (uint64_t)opt.split_width) continue;
-    bsq_smem1(fm, fmc, len, q, (start + end) >> 1, (int)(out[k].x[2] + 1), scr, &n1);
-    for (int i = 0; i < n1; ++i) {
-      const bsq_intv_t &m = scr.one[i];
-      if ((uint32_t)m.info - (uint32_t)(m.info >> 32) >= (uint32_t)opt.min_seed_len) {
-        if (n == cap) return -1;
-        out[n++] = m;
-      }
-    }
-  }
-  // pass 3: greedy forward seeds with fewer than max_mem_intv occurrences
-  if (opt.max_mem_intv > 0) {
-    x = 0;
-    while (x < len) {
-      if (q[x] < 4) {
-        bsq_intv_t m;
-        x = bsq_seed_strategy1(fm, fmc, len, q, x, opt.min_seed_len, opt.max_mem_intv, m);
-        if (m.x[2] > 0) {
-          if (n == cap) return -1;
-          out[n++] = m;
-        }
-      } else ++x;
-    }
-  }
-  bsq_introsort(out, n, bsq_intv_less());
-  return n;
+  return (int32_t)tot;
 }

@@ -14,28 +14,34 @@ BSQ_HD void bsq_bsconvert(const uint8_t *seq, int len, int parent, uint8_t *out)
   }
 }
 
-// Seeding of one task.  Returns the interval count (or -1 on overflow) and, in *n_sa, how many
-// suffix-array lookups the chaining stage will need up front: min(x[2], max_occ) per interval
-// (the occurrences mem_chain always visits, memchain.c:325-326).
+// Seeding of one task, driven sequentially (host emulation; the CUDA kernel k_seed drives the same
+// machine with all lanes of a warp meeting at the extend).  Returns the interval count (or -1 on
+// overflow); out[] is packed and sorted; *n_sa = SA lookups chaining will need up front.
 BSQ_HD int bsq_task_seed(const bsq_devopt_t &opt, const bsq_devidx_t &ix, const uint8_t *seq, int len, int parent,
-                         bool pipeline, bsq_seed_scratch_t &scr, bsq_intv_t *out, int32_t *n_sa) {
-  uint8_t q[BSQ_MAX_READ_LEN];
+                         bool pipeline, bsq_seed_scratch_t &scr, bsq_pk_t *out, int32_t *n_sa) {
   *n_sa = 0;
   if (pipeline && len < opt.min_seed_len) return 0;  // mem_chain returns before seeding (memchain.c:280)
-  bsq_bsconvert(seq, len, parent, q);
-  int n = bsq_collect_intv(opt, ix.fm[parent], ix.fm[!parent], len, q, scr, out, BSQ_MAX_INTV);
-  if (n < 0) return -1;
-  int64_t tot = 0;
-  for (int i = 0; i < n; ++i) tot += (int64_t)(out[i].x[2] < (uint64_t)(uint32_t)opt.max_occ ? out[i].x[2] : (uint64_t)(uint32_t)opt.max_occ);
-  *n_sa = (int32_t)tot;
-  return n;
+  bsq_bsconvert(seq, len, parent, scr.q);
+  bsq_seed_machine_t m;
+  bsq_sm_init(m, opt, len, BSQ_MAX_INTV);
+  bsq_ext_req_t req;
+  const bsq_fm_t &fm = ix.fm[parent], &fmc = ix.fm[!parent];
+  while (bsq_sm_next(m, fm, fmc, scr, out, req)) {
+    uint64_t o0, o1, o2;
+    bsq_extend1(fm, fmc, req, o0, o1, o2);
+    bsq_sm_consume(m, scr, out, o0, o1, o2);
+  }
+  if (m.overflow) return -1;
+  *n_sa = bsq_sm_finalize(m, opt, out);
+  return m.n_out;
 }
 
 // BWT ranks whose text positions the chaining stage needs, in visiting order.
-BSQ_HD void bsq_task_expand(const bsq_devopt_t &opt, const bsq_intv_t *intv, int n, uint64_t *ranks) {
+BSQ_HD void bsq_task_expand(const bsq_devopt_t &opt, const bsq_pk_t *intv, int n, uint64_t tag, uint64_t *ranks) {
   int64_t o = 0;
   for (int i = 0; i < n; ++i) {
-    uint64_t m = intv[i].x[2] < (uint64_t)(uint32_t)opt.max_occ ? intv[i].x[2] : (uint64_t)(uint32_t)opt.max_occ;
-    for (uint64_t k = 0; k < m; ++k) ranks[o++] = intv[i].x[0] + k;
+    const uint64_t x2 = bsq_pk_x2(intv[i]), x0 = bsq_pk_x0(intv[i]);
+    const uint64_t m = x2 < (uint64_t)(uint32_t)opt.max_occ ? x2 : (uint64_t)(uint32_t)opt.max_occ;
+    for (uint64_t k = 0; k < m; ++k) ranks[o++] = (x0 + k) | tag;
   }
 }

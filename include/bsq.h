@@ -34,7 +34,7 @@ extern "C" {
 #define BSQ_ENOMEM (-4)
 
 #define BSQ_MAX_READ_LEN 256
-#define BSQ_MAX_INTV 160
+#define BSQ_MAX_INTV 384
 
 /* same layout as the reference's bwtintv_t (lib/aln/bwt.h:80-82) */
 typedef struct { uint64_t x[3], info; } bsq_intv;

@@ -60,8 +60,10 @@ int bsq_collect_intv(const bsq_index *ix, const bsq_opt *opt_, int64_t n_tasks, 
   for (int64_t t = 0; t < n_tasks; ++t) {
     if (lens[t] > BSQ_MAX_READ_LEN) { rc = BSQ_EINVAL; break; }
     int32_t n_sa;
-    int n = bsq_task_seed(opt, ix->d, seqs + t * stride, lens[t], parent[t], false, *scr, (bsq_intv_t *)out + t * BSQ_MAX_INTV, &n_sa);
+    bsq_pk_t pk[BSQ_MAX_INTV];
+    int n = bsq_task_seed(opt, ix->d, seqs + t * stride, lens[t], parent[t], false, *scr, pk, &n_sa);
     if (n < 0) { rc = BSQ_EOVERFLOW; break; }
+    for (int i = 0; i < n; ++i) ((bsq_intv_t *)out)[t * BSQ_MAX_INTV + i] = bsq_pk_unpack(pk[i]);
     n_out[t] = n;
   }
   delete scr;
@@ -74,7 +76,8 @@ int bsq_extend_batch(const bsq_opt *opt_, int64_t n_jobs, const uint8_t *qbuf, c
   bsq_ksw_scratch_t scr;
   for (int64_t j = 0; j < n_jobs; ++j) {
     if (qlen[j] > BSQ_MAX_READ_LEN) return BSQ_EINVAL;
-    struct G { const uint8_t *p; int operator()(int i) const { return p[i]; } } qa{qbuf + qoff[j]}, ta{tbuf + toff[j]};
+    bsq_qacc_t qa; qa.q = qbuf + qoff[j]; qa.step = 1;
+    bsq_tacc_t ta; ta.ix = nullptr; ta.buf = tbuf + toff[j]; ta.p0 = 0; ta.step = 1;
     bsq_ext_result_t r = bsq_ksw_extend(qlen[j], qa, tlen[j], ta, is_parent[j] ? opt.ctmat : opt.gamat, opt.o_del, opt.e_del,
                                         opt.o_ins, opt.e_ins, w[j], opt.pen_clip5, opt.zdrop, h0[j], scr);
     memcpy(out + 6 * j, &r, 24);
@@ -99,7 +102,7 @@ int bsq_align_phase1(bsq_aligner *al, int64_t n_tasks, const uint8_t *seqs, int3
   std::vector<bsq_reg_t> all;
   bsq_seed_scratch_t *scr = new bsq_seed_scratch_t();
   bsq_ksw_scratch_t *ksw = new bsq_ksw_scratch_t();
-  std::vector<bsq_intv_t> intv(BSQ_MAX_INTV);
+  std::vector<bsq_pk_t> intv(BSQ_MAX_INTV);
   int rc = 0;
   memset(al->counters, 0, sizeof al->counters);
   for (int64_t t = 0; t < n_tasks && rc == 0; ++t) {
@@ -110,7 +113,7 @@ int bsq_align_phase1(bsq_aligner *al, int64_t n_tasks, const uint8_t *seqs, int3
     int n = bsq_task_seed(opt, ix, seq, lens[t], parent[t], true, *scr, intv.data(), &n_sa);
     if (n < 0) { rc = BSQ_EOVERFLOW; break; }
     std::vector<uint64_t> ranks(n_sa + 1), pos(n_sa + 1);
-    bsq_task_expand(opt, intv.data(), n, ranks.data());
+    bsq_task_expand(opt, intv.data(), n, 0, ranks.data());
     for (int i = 0; i < n_sa; ++i) pos[i] = bsq_sa(ix.fm[parent[t]], ranks[i]);
     const int cap = n_sa + 64;
     std::vector<bsq_snode_t> sn(cap); std::vector<bsq_wchain_t> wc(cap); std::vector<bsq_bnode_t> bn(cap + 2);
@@ -119,7 +122,7 @@ int bsq_align_phase1(bsq_aligner *al, int64_t n_tasks, const uint8_t *seqs, int3
     bsq_chain_result_t cr = bsq_chain_task(opt, ix, parent[t], lens[t], intv.data(), n, pos.data(), ws, och.data(), osd.data());
     if (cr.status) { rc = BSQ_EOVERFLOW; break; }
     std::vector<uint64_t> srt(cap); std::vector<bsq_reg_t> rg(cap);
-    int nr = bsq_chain2region(opt, ix, parent[t], lens[t], seq, och.data(), cr.n_chains, osd.data(), cr.frac_rep, srt.data(), *ksw, rg.data());
+    int nr = bsq_chain2region<bsq_scalar_policy>(opt, ix, parent[t], lens[t], seq, och.data(), cr.n_chains, osd.data(), cr.frac_rep, srt.data(), ksw, rg.data());
     all.insert(all.end(), rg.begin(), rg.begin() + nr);
     al->counters[0]++; al->counters[1] += n; al->counters[2] += n_sa; al->counters[3] += cr.n_chains; al->counters[4] += nr;
   }
@@ -137,13 +140,13 @@ int64_t hostemu_chain(const bsq_index *ixp, const bsq_opt *opt_, int parent, int
   bsq_devopt_t opt; memcpy(&opt, opt_, sizeof opt);
   const bsq_devidx_t &ix = ixp->d;
   bsq_seed_scratch_t *scr = new bsq_seed_scratch_t();
-  std::vector<bsq_intv_t> intv(BSQ_MAX_INTV);
+  std::vector<bsq_pk_t> intv(BSQ_MAX_INTV);
   int32_t n_sa;
   int n = bsq_task_seed(opt, ix, seq, len, parent, true, *scr, intv.data(), &n_sa);
   delete scr;
   if (n < 0) return -1;
   std::vector<uint64_t> ranks(n_sa + 1), pos(n_sa + 1);
-  bsq_task_expand(opt, intv.data(), n, ranks.data());
+  bsq_task_expand(opt, intv.data(), n, 0, ranks.data());
   for (int i = 0; i < n_sa; ++i) pos[i] = bsq_sa(ix.fm[parent], ranks[i]);
   const int cap = n_sa + 64;
   std::vector<bsq_snode_t> sn(cap); std::vector<bsq_wchain_t> wc(cap); std::vector<bsq_bnode_t> bn(cap + 2);

@@ -27,6 +27,19 @@ def test_index_matches_reference(cuda, ds_name, request):
 
 
 @pytest.mark.gpu
+def test_index_many_chunks(cuda, ds_1m, monkeypatch):
+    """Force the bucketed multi-pass path (as used for GRCh38-sized references) on a small reference."""
+    monkeypatch.setenv("BSQ_INDEX_CHUNK", "150000")
+    hi = indexio.load_index(ds_1m["fa"])
+    dx = cuda.build_index(hi.pac, hi.l_pac, hi.names, hi.ann_offset, hi.ann_len)
+    assert dx.sizes()["stats"][0] > 10
+    for which in (0, 1):
+        bwt, sa = dx.download(which)
+        assert (bwt == hi.fm[which].bwt).all() and (sa == hi.fm[which].sa).all()
+    dx.close()
+
+
+@pytest.mark.gpu
 def test_index_low_complexity(cuda, tmp_path):
     """Tandem repeats and homopolymer runs force many tie-refinement passes."""
     import subprocess
@@ -34,6 +47,8 @@ def test_index_low_complexity(cuda, tmp_path):
     unit = rng.integers(0, 4, size=37).astype(np.uint8)
     seq = np.concatenate([rng.integers(0, 4, size=5000).astype(np.uint8), np.tile(unit, 200), np.zeros(3000, np.uint8),
                           rng.integers(0, 4, size=5000).astype(np.uint8), np.tile(unit, 100), np.full(2000, 3, np.uint8)])
+    # the doubled text then ends in a run of A (revcomp of the leading T run): exhausted-suffix ties
+    seq = np.concatenate([np.full(40, 3, np.uint8), seq])
     fa = str(tmp_path / "rep.fa")
     synth.write_fasta(fa, [("rep", seq)])
     if not refprobe.available():
