@@ -160,6 +160,73 @@ void bsq_host_free(void *p);
  * k_seed / after k_sa */
 int bsq_aligner_counters(const bsq_aligner *al, int64_t *c, int n);
 
+/* ================= pileup (methylation caller) =================
+ * Replaces the per-window hot loop of process_func (src/pileup.c:707-831: read filters, bisulfite-strand
+ * inference, mate-overlap skip, per-base retention/conversion events), plp_getcnts (src/pileup.c:372-387)
+ * and the integer part of plp_format (src/pileup.c:415-485: ambiguity redistribution, top mutant, emit
+ * rule, methcallable, 5-mer cytosine context of src/bisc_utils.c:33-74).  Genotype likelihoods (double,
+ * utils/stats.h) and VCF/BED text stay on the host (biscuit_b200/host).
+ *
+ * Input = the BAM records of one contig as structure-of-arrays, i.e. exactly the fields of bam1_core_t
+ * plus CIGAR / 4-bit SEQ / QUAL / the tags the reference reads (NM AS MC YD ZS XG), coordinate sorted. */
+typedef struct {
+  int64_t n_reads;
+  const int32_t *pos;        /* 0-based leftmost reference position */
+  const int32_t *mpos;       /* mate position, 0-based */
+  const int32_t *mate_rlen;  /* reference length of the mate from the MC tag, -1 if absent */
+  const int32_t *l_qseq;
+  const int32_t *nm;         /* NM tag, INT32_MIN if absent */
+  const int32_t *as;         /* AS tag, INT32_MIN if absent */
+  const uint16_t *flag;
+  const uint8_t *mapq;
+  const int8_t *bss_tag;     /* 0: YD:f / ZS:+ / XG:CT, 1: YD:r / ZS:- / XG:GA, -1: none (infer from the read) */
+  const uint8_t *sid;        /* sample (BAM file) index, < n_bams */
+  const int32_t *n_cigar;
+  const int64_t *cigar_off;
+  const uint32_t *cigar;     /* BAM encoding: len<<4 | op */
+  const int64_t *seq_off;    /* byte offset into seq[]; 4-bit packed as in BAM */
+  const uint8_t *seq;
+  const int64_t *qual_off;
+  const uint8_t *qual;
+} bsq_plp_reads;
+
+/* meth_filter_t + the pileup_conf_t switches that affect counting (src/bisc_utils.h:95-113, pileup.h:49-63) */
+typedef struct {
+  int32_t min_base_qual, min_read_len, min_dist_end_5p, min_dist_end_3p, min_mapq, min_score, max_nm, max_retention;
+  int32_t filter_ppair, filter_secondary, filter_duplicate, filter_qcfail, filter_doublecnt;
+  int32_t ambi_redist, verbose, is_nome;
+} bsq_plp_conf;
+
+/* one emitted locus x one sample (n_bams consecutive records per locus) */
+typedef struct {
+  int32_t pos, dp;           /* 1-based position; DP = all events of the sample (pileup.c:572) */
+  int32_t meth[3];           /* retention, conversion, NA (after base filters) */
+  int32_t base[7];           /* A C G T N Y R (after base filters) */
+  int32_t base_redist[7];    /* after redistribute_cnts */
+  uint8_t rb_code;           /* reference base 0..3 */
+  int8_t cm1;                /* top mutant base code or -1 */
+  uint8_t ctx, methcallable; /* cytosine_context_t (6 = NA); methcallable of this sample */
+  char n5[5];
+  uint8_t any_callable, pad_[2];
+} bsq_plp_rec;
+
+typedef struct bsq_plp bsq_plp;
+
+void bsq_plp_conf_default(bsq_plp_conf *c);
+int bsq_plp_create(int device, int n_bams, bsq_plp **out);
+void bsq_plp_destroy(bsq_plp *p);
+/* upload one contig: nt4 codes (A0 C1 G2 T3 N4), ref_len bases */
+int bsq_plp_set_contig(bsq_plp *p, const uint8_t *ref_nt4, int32_t ref_len);
+/* host->device copy of the reads; run = kernels over loci [beg,end) (1-based, end exclusive, clipped so that
+ * the last base of the contig is never piled, pileup.c:1191-1196), returns the number of emitted loci;
+ * fetch = device->host copy of n_loci*n_bams records */
+int bsq_plp_stage(bsq_plp *p, const bsq_plp_reads *reads);
+int bsq_plp_run(bsq_plp *p, const bsq_plp_conf *conf, int32_t beg, int32_t end, int64_t *n_loci);
+int bsq_plp_fetch(bsq_plp *p, bsq_plp_rec *out);
+/* c[0] = reads staged, c[1] = loci scanned, c[2] = loci emitted, c[3] = base events (after read filters),
+ * c[4..5] = device microseconds of the event kernel / the per-locus kernel of the last run */
+int bsq_plp_counters(const bsq_plp *p, int64_t *c, int n);
+
 #ifdef __cplusplus
 }
 #endif
