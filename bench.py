@@ -178,8 +178,116 @@ def reference_run(prefix, reads, n_threads, steps, warmup):
     return times
 
 
+def plp_make_reads(nt4, n_pairs, seed):
+    """Vectorised coordinate-sorted alignments (150M CIGARs, YD/NM/AS/MC tags present) for the pileup path."""
+    import synth
+    out = []
+    chunk = 250_000
+    for c0 in range(0, n_pairs, chunk):
+        p = synth.simulate_pairs([("c", nt4)], min(chunk, n_pairs - c0), seed=seed + c0, qual="mixed")
+        _, pos, bsc, flen = p["truth"]
+        rc = lambda a: np.where(a[:, ::-1] < 4, 3 - a[:, ::-1], 4).astype(np.uint8)  # noqa: E731
+        left, right = pos.astype(np.int64), (pos + flen - 150).astype(np.int64)
+        b = bsc[:, None]
+        seq_a = np.where(b, rc(p["r1"]), p["r1"]); qual_a = np.where(b, p["q1"][:, ::-1], p["q1"])
+        seq_b = np.where(b, p["r2"], rc(p["r2"])); qual_b = np.where(b, p["q2"], p["q2"][:, ::-1])
+        pos_a = np.where(bsc, right, left); pos_b = np.where(bsc, left, right)
+        flag_a = np.where(bsc, 83, 99); flag_b = np.where(bsc, 163, 147)
+        out.append((np.concatenate([pos_a, pos_b]), np.concatenate([pos_b, pos_a]), np.concatenate([flag_a, flag_b]),
+                    np.concatenate([bsc, bsc]).astype(np.int8), np.concatenate([seq_a, seq_b]), np.concatenate([qual_a, qual_b])))
+    pos = np.concatenate([o[0] for o in out]); mpos = np.concatenate([o[1] for o in out]); flag = np.concatenate([o[2] for o in out])
+    bss = np.concatenate([o[3] for o in out]); seq = np.concatenate([o[4] for o in out]); qual = np.concatenate([o[5] for o in out])
+    order = np.argsort(pos, kind="stable")
+    pos, mpos, flag, bss, seq, qual = pos[order], mpos[order], flag[order], bss[order], seq[order], qual[order]
+    n = len(pos)
+    nt16 = np.array([1, 2, 4, 8, 15], np.uint8)[np.minimum(seq, 4)]
+    return dict(n_reads=n, pos=pos.astype(np.int32), mpos=mpos.astype(np.int32), mate_rlen=np.full(n, 150, np.int32),
+                l_qseq=np.full(n, 150, np.int32), nm=np.full(n, 1, np.int32), as_=np.full(n, 140, np.int32), flag=flag.astype(np.uint16),
+                mapq=np.full(n, 60, np.uint8), bss_tag=bss, sid=np.zeros(n, np.uint8), n_cigar=np.ones(n, np.int32),
+                cigar_off=np.arange(n, dtype=np.int64), cigar=np.full(n, (150 << 4), np.uint32),
+                seq=((nt16[:, 0::2] << 4) | nt16[:, 1::2]).astype(np.uint8).reshape(-1), seq_off=np.arange(n, dtype=np.int64) * 75,
+                qual=(qual.astype(np.int16) - 33).astype(np.uint8).reshape(-1), qual_off=np.arange(n, dtype=np.int64) * 150)
+
+
+def bench_pileup(args):
+    """`--path pileup`: loci/s of the methylation caller over a 30x synthetic WGBS contig."""
+    import torch
+    from biscuit_b200 import capi, plp
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    torch.cuda.set_device(0)
+    peak, peak_src = load_peaks()
+    L = int(args.plp_mb * 1_000_000)
+    rng = np.random.default_rng(7)
+    nt4 = rng.integers(0, 4, size=L, dtype=np.uint8)
+    n_pairs = int(L * args.plp_depth / 300)
+    t0 = time.time()
+    rd = plp_make_reads(nt4, n_pairs, 31)
+    log(f"pileup: {rd['n_reads']} reads over {L / 1e6:.0f} Mb ({args.plp_depth}x) simulated in {time.time() - t0:.1f}s")
+    bsq = capi.load()
+    pl = plp.Pileup(bsq, 1)
+    conf = pl.default_conf()
+    pl.set_contig(nt4)
+    pl.stage(rd)
+    n_loci = pl.run(conf, 1, L)
+    for _ in range(args.warmup):
+        pl.run(conf, 1, L)
+    sampler = ClockSampler(0)
+    sampler.start()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    kus = np.zeros(2)
+    for _ in range(args.steps):
+        pl.run(conf, 1, L)
+        kus += pl.counters()[4:6]
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    c = pl.counters()
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        pl.stage(rd)
+        recs = pl.fetch(pl.run(conf, 1, L))
+    dt_e2e = time.perf_counter() - t1
+    kus /= args.steps
+    h2d = sum(int(np.asarray(v).nbytes) for k, v in rd.items() if k != "n_reads")
+    alg = rd["n_reads"] * (75 + 150 + 48) + (L - 1) * (1 + 48) + n_loci * 88
+    cpu = None
+    if not args.no_cpu_baseline:
+        import oracle_plp
+        sub = min(L, 2_000_000)
+        keep = rd["pos"] < sub
+        rs = {k: (v[keep] if isinstance(v, np.ndarray) and len(v) == rd["n_reads"] else v) for k, v in rd.items()}
+        rs["n_reads"] = int(keep.sum())
+        t2 = time.perf_counter()
+        exp = oracle_plp.region(conf, nt4, rs, 1, sub - 200)
+        dtc = time.perf_counter() - t2
+        got = recs[recs["pos"] < sub - 200]
+        ok = got.tobytes() == exp.tobytes()
+        cpu = {"value": (sub - 200) / dtc, "unit": "loci/s", "cores": 1, "kind": "port",
+               "sample": f"first {sub / 1e6:.0f} Mb through oracle/bsq_oracle_pileup.c (single thread); identical to GPU output: {ok}"}
+    line = {"metric": "wgbs_pileup_loci_per_s", "value": (L - 1) * args.steps / dt, "unit": "loci/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic",
+            "config": {"workload": f"pileup {args.plp_depth}x synthetic WGBS, coordinate-sorted decoded BAM records, {L / 1e6:.0f} Mb contig, "
+                                   "CpG/CHG/CHH extraction", "reads": int(rd["n_reads"]), "emitted_loci": int(n_loci),
+                       "l2": "inputs larger than L2 (reads + counters)"},
+            "clocks": clocks, "e2e": {"value": (L - 1) * args.steps / dt_e2e, "unit": "loci/s", "h2d_bytes_per_step": h2d,
+                                      "d2h_bytes_per_step": int(n_loci) * 88},
+            "gpu_launches": 3 * args.steps * ((L + (8 << 20) - 1) // (8 << 20)),
+            "roofline": {"bound": "hbm", "kernel": "k_plp_pile", "achieved": alg / (kus[0] * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (kus[0] * 1e-6) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel_ms": kus[0] / 1000, "locus_kernels_ms": kus[1] / 1000, "events": int(c[3])},
+            "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    pl.close()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--path", default="align", choices=["align", "pileup"])
+    ap.add_argument("--plp-mb", type=float, default=20.0)
+    ap.add_argument("--plp-depth", type=int, default=30)
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
@@ -189,6 +297,8 @@ def main():
     ap.add_argument("--cpu-pairs", type=int, default=int(os.environ.get("BSQ_BENCH_CPU_PAIRS", "10000")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.path == "pileup":
+        return bench_pileup(args)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
