@@ -1,0 +1,186 @@
+/* bq.h -- host side (C) of the B200 BISCUIT hot paths.
+ *
+ * The GPU does phase 1 of `biscuit align` (seeding, chaining, extension: libbsq.so, include/bsq.h).
+ * Everything here is the host shell around it, restated from the reference's lib/aln in this project's
+ * own code: reference sequence access, region merging, insert-size statistics, mate rescue, primary
+ * marking, pairing, mapQ, CIGAR/MD generation and SAM text -- the parts of mem_process_seqs
+ * (lib/aln/bwamem.c:432-476) that involve libm or text formatting -- plus the
+ * `biscuit index|align` command lines and the on-disk index format.
+ */
+#ifndef BQ_H
+#define BQ_H
+#include <stddef.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/bsq.h"
+
+#define BQ_VERSION "1.6.1-dev-b200"
+
+/* ---- options: mem_opt_t (lib/aln/bwamem.h:54-124), defaults mem_opt_init (bwamem.c:77-128) ---- */
+#define BQ_F_PE 0x2
+#define BQ_F_NOPAIRING 0x4
+#define BQ_F_ALL 0x8
+#define BQ_F_NO_MULTI 0x10
+#define BQ_F_NO_RESCUE 0x20
+#define BQ_F_SELF_OVLP 0x40
+#define BQ_F_REF_HDR 0x100
+#define BQ_F_SOFTCLIP 0x200
+#define BQ_F_KEEP_SUPP_MAPQ 0x1000
+
+typedef struct {
+  int a, b, o_del, e_del, o_ins, e_ins, pen_unpaired, pen_clip5, pen_clip3, w, zdrop;
+  uint64_t max_mem_intv;
+  int T, flag, min_seed_len, min_chain_weight;
+  uint32_t max_chain_extend;
+  float split_factor;
+  int split_width;
+  uint32_t max_occ;
+  int max_chain_gap, n_threads, chunk_size;
+  float mask_level, drop_ratio, XA_drop_ratio, mask_level_redun, mapQ_coef_len;
+  int mapQ_coef_fac, max_ins, max_matesw, max_XA_hits, max_XA_hits_alt;
+  int8_t mat[25], ctmat[25], gamat[25];
+  uint8_t parent, bsstrand;
+  uint8_t *adaptor1, *adaptor2;
+  int l_adaptor1, l_adaptor2, clip5, clip3, min_base_qual;
+  uint8_t has_bc;
+} bq_opt_t;
+
+typedef struct {
+  int low, high, set, failed;
+  double avg, std;
+} bq_pestat_t;
+
+/* ---- reference meta data: bntseq_t / bntann1_t (lib/aln/bntseq.h:41-64) ---- */
+typedef struct {
+  int64_t offset;
+  int32_t len, n_ambs;
+  uint32_t gi;
+  int32_t is_alt;
+  char *name, *anno;
+} bq_ann_t;
+
+typedef struct {
+  int64_t offset;
+  int32_t len;
+  char amb;
+} bq_amb_t;
+
+typedef struct {
+  int64_t l_pac;
+  int32_t n_seqs;
+  uint32_t seed;
+  bq_ann_t *anns;
+  int32_t n_holes;
+  bq_amb_t *ambs;
+  uint8_t *pac; /* forward-only 2-bit packed reference */
+} bq_ref_t;
+
+/* host copy of one FM-index half as stored on disk */
+typedef struct {
+  uint64_t primary, L2[5], seq_len, bwt_words, n_sa;
+  int sa_intv;
+  uint32_t *bwt;
+  uint64_t *sa;
+} bq_fm_t;
+
+typedef struct {
+  bq_fm_t fm[2]; /* [0] daughter, [1] parent */
+  bq_ref_t ref;
+} bq_index_t;
+
+/* ---- reads: bseq1_t (lib/aln/bwa.h:52-61) ---- */
+typedef struct {
+  int l_seq, id;
+  char *name, *comment, *barcode, *umi, *qual, *sam;
+  uint8_t *seq;  /* nt4, after clipping */
+  uint8_t *seq0; /* nt4, as read */
+  int l_seq0, l_adaptor, clip5, clip3;
+} bq_read_t;
+
+/* ---- alignment region: mem_alnreg_t (lib/aln/mem_alnreg.h:34-66) ---- */
+typedef struct {
+  int64_t rb, re;
+  int qb, qe, rid, score, truesc, sub, alt_sc, csub, sub_n, w, seedcov, secondary, secondary_all, seedlen0;
+  int n_comp, is_alt;
+  float frac_rep;
+  uint64_t hash;
+  uint8_t bss, parent, read_in_pair;
+  int pos, flag, NM, n_cigar;
+  int is_rev, sam_set;
+  unsigned mapq;
+  uint32_t ZC, ZR;
+  int bss_u;
+  uint32_t *cigar; /* n_cigar words followed by the NUL-terminated MD string */
+} bq_reg_t;
+
+typedef struct {
+  size_t n, m, n_pri;
+  bq_reg_t *a;
+} bq_regv_t;
+
+typedef struct {
+  size_t l, m;
+  char *s;
+} bq_str_t;
+
+/* bq_core.c */
+void bq_opt_init(bq_opt_t *o);
+void bq_fill_scmat(int a, int b, int8_t mat[25]);
+void bq_fill_scmat_bis(int a, int b, int ct, int8_t mat[25]);
+void bq_opt_to_dev(const bq_opt_t *o, bsq_opt *d);
+uint64_t bq_hash64(uint64_t key);
+void bq_introsort(void *base, size_t n, size_t sz, int (*lt)(const void *, const void *));
+int bq_pos2rid(const bq_ref_t *r, int64_t pos_f);
+int64_t bq_depos(const bq_ref_t *r, int64_t pos, int *is_rev);
+uint8_t *bq_get_seq(int64_t l_pac, const uint8_t *pac, int64_t beg, int64_t end, int64_t *len);
+uint8_t *bq_fetch_seq(const bq_ref_t *r, int64_t *beg, int64_t mid, int64_t *end, int *rid);
+int bq_global_align(int qlen, const uint8_t *query, int tlen, const uint8_t *target, const int8_t *mat, int o_del, int e_del, int o_ins,
+                    int e_ins, int w, int *n_cigar, uint32_t **cigar);
+typedef struct { int score, te, qe, score2, te2, tb, qb; } bq_swr_t;
+#define BQ_XBYTE 0x10000
+#define BQ_XSTOP 0x20000
+#define BQ_XSUBO 0x40000
+#define BQ_XSTART 0x80000
+bq_swr_t bq_local_align(int qlen, uint8_t *query, int tlen, uint8_t *target, const int8_t *mat, int o_del, int e_del, int o_ins, int e_ins,
+                        int xtra);
+uint32_t *bq_gen_cigar(const int8_t mat[25], int o_del, int e_del, int o_ins, int e_ins, int w_, int64_t l_pac, const uint8_t *pac,
+                       int l_query, uint8_t *query, int64_t rb, int64_t re, int *score, int *n_cigar, int *NM, uint32_t *ZC, uint32_t *ZR,
+                       int *bss_u, uint8_t parent);
+void bq_kputs(bq_str_t *s, const char *p);
+void bq_kputsn(bq_str_t *s, const char *p, size_t n);
+void bq_kputc(bq_str_t *s, int c);
+void bq_kputw(bq_str_t *s, int v);
+void bq_kputl(bq_str_t *s, long v);
+void bq_str_reserve(bq_str_t *s, size_t extra);
+
+/* bq_phase2.c */
+void bq_merge_regions(const bq_opt_t *opt, const bq_ref_t *ref, const uint8_t *query, int l_query, bq_regv_t *regs);
+bq_pestat_t bq_pestat(const bq_opt_t *opt, const bq_ref_t *ref, int n, const bq_regv_t *regs);
+void bq_matesw(const bq_opt_t *opt, const bq_ref_t *ref, bq_pestat_t pes, bq_read_t s[2], bq_regv_t regs[2]);
+void bq_mark_primary(const bq_opt_t *opt, bq_regv_t *regs, int64_t id);
+int bq_approx_mapq_se(const bq_opt_t *opt, const bq_reg_t *a);
+void bq_reg2sam_se(const bq_opt_t *opt, const bq_ref_t *ref, bq_read_t *s, bq_regv_t *regs, const char *rg_id);
+void bq_reg2sam_pe(const bq_opt_t *opt, const bq_ref_t *ref, uint64_t id, bq_read_t s[2], bq_regv_t regs[2], bq_pestat_t pes,
+                   const char *rg_id);
+void bq_read_clipping(bq_read_t *s, const uint8_t *adaptor, int l_adaptor, const bq_opt_t *opt);
+/* mem_process_seqs (lib/aln/bwamem.c:432-476) on top of the GPU aligner: fills seqs[i].sam */
+int bq_process_seqs(const bq_opt_t *opt, bsq_aligner *al, const bq_ref_t *ref, int64_t n_processed, int n, bq_read_t *seqs,
+                    const bq_pestat_t *pes0, const char *rg_id);
+
+/* bq_io.c */
+int bq_index_load(const char *prefix, bq_index_t *idx);
+void bq_index_free(bq_index_t *idx);
+int bq_index_to_device(const bq_index_t *idx, int device, bsq_index **out);
+int bq_main_index(int argc, char **argv);
+typedef struct bq_fastq bq_fastq_t;
+bq_fastq_t *bq_fastq_open(const char *fn);
+void bq_fastq_close(bq_fastq_t *f);
+bq_read_t *bq_read_batch(int chunk_size, int has_bc, int keep_comment, int *n, bq_fastq_t *f1, bq_fastq_t *f2);
+void bq_print_sam_hdr(const bq_ref_t *ref, const char *hdr_line, const char *pg_line);
+void bq_fatal(const char *fmt, ...);
+
+/* bq_main.c */
+int bq_main_align(int argc, char **argv);
+
+extern int bq_verbose;
+#endif

@@ -1,0 +1,886 @@
+/* bq_phase2.c -- what happens to the alignment regions after the GPU: region merging, insert-size
+ * statistics, mate rescue, primary marking, pairing, mapQ, SAM records.  Restated from
+ * lib/aln/mem_alnreg.c, mem_pair.c, mem_alnreg_format.c and bwamem.c (line references at each function);
+ * all libm use of the aligner lives here. */
+#include <limits.h>
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+#include "bq.h"
+
+#define MINV(a, b) ((a) < (b) ? (a) : (b))
+#define MAXV(a, b) ((a) > (b) ? (a) : (b))
+
+static void regv_push(bq_regv_t *v, const bq_reg_t *r) {
+  if (v->n == v->m) { v->m = v->m ? v->m << 1 : 4; v->a = realloc(v->a, v->m * sizeof(bq_reg_t)); }
+  v->a[v->n++] = *r;
+}
+
+/* mem_alnreg_isize / mem_infer_isize (mem_alnreg.h:74-93): "insert" measured between the two rb of the
+ * forward-reverse coordinates -- includes the aligned length of the reverse read */
+static int infer_isize(int64_t pos1, int64_t pos2, int isrev1, int isrev2, int64_t len1, int64_t len2, int64_t *isize) {
+  if (isrev1 && !isrev2) { *isize = pos1 - pos2 + len1; return 1; }
+  if (isrev2 && !isrev1) { *isize = pos2 - pos1 + len2; return 1; }
+  return 0;
+}
+static int reg_isize(const bq_ref_t *ref, const bq_reg_t *r1, const bq_reg_t *r2, int64_t *isize) {
+  if (r1->rid != r2->rid) return 0;
+  const int isrev1 = r1->rb > ref->l_pac, isrev2 = r2->rb > ref->l_pac;
+  const int64_t pos1 = isrev1 ? (ref->l_pac << 1) - 1 - r1->rb : r1->rb, pos2 = isrev2 ? (ref->l_pac << 1) - 1 - r2->rb : r2->rb;
+  return infer_isize(pos1, pos2, isrev1, isrev2, r1->qe - r1->qb, r2->qe - r2->qb, isize);
+}
+static int is_proper_pair(const bq_ref_t *ref, const bq_reg_t *r1, const bq_reg_t *r2, bq_pestat_t pes) {
+  int64_t is;
+  if (!reg_isize(ref, r1, r2, &is)) return 0;
+  return is >= pes.low && is <= pes.high;
+}
+static int region_depos(const bq_ref_t *ref, const bq_reg_t *reg, int *is_rev) {
+  int tmp;
+  int64_t rpos = bq_depos(ref, reg->rb < ref->l_pac ? reg->rb : reg->re - 1, is_rev ? is_rev : &tmp);
+  return (int)(rpos - ref->anns[reg->rid].offset);
+}
+
+/* ---------------- region merging: mem_alnreg.c:63-227 ---------------- */
+
+static int lt_re(const void *a, const void *b) { return ((const bq_reg_t *)a)->re < ((const bq_reg_t *)b)->re; }
+static int lt_score_rb_qb(const void *a_, const void *b_) {
+  const bq_reg_t *a = a_, *b = b_;
+  return a->score > b->score || (a->score == b->score && (a->rb < b->rb || (a->rb == b->rb && a->qb < b->qb)));
+}
+
+/* score of joining two colinear regions through a global alignment, 0 when they should stay apart */
+static int test_concatenation(const bq_opt_t *opt, const bq_ref_t *ref, uint8_t *query, const bq_reg_t *a, const bq_reg_t *b, int *w_out) {
+  if (ref == 0 || query == 0) return 0;
+  if (a->rb < ref->l_pac && b->rb >= ref->l_pac) return 0;
+  if (a->qb >= b->qb || a->qe >= b->qe || a->re >= b->re) return 0;
+  int w = (int)((a->re - b->rb) - (a->qe - b->qb));
+  w = w > 0 ? w : -w;
+  double r = (double)(a->re - b->rb) / (b->re - a->rb) - (double)(a->qe - b->qb) / (b->qe - a->qb);
+  r = r > 0. ? r : -r;
+  if (a->re < b->rb || a->qe < b->qb) { if (w > opt->w << 1 || r >= 0.05f) return 0; }
+  else if (w > opt->w << 2 || r >= 0.05f * 2) return 0;
+  w += a->w + b->w;
+  w = MINV(w, opt->w << 2);
+  int score;
+  bq_gen_cigar(a->parent ? opt->ctmat : opt->gamat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, w, ref->l_pac, ref->pac, b->qe - a->qb,
+               query + a->qb, a->rb, b->re, &score, 0, 0, 0, 0, 0, a->parent);
+  int q_s = (int)((double)(b->qe - a->qb) / ((b->qe - b->qb) + (a->qe - a->qb)) * (b->score + a->score) + .499);
+  int r_s = (int)((double)(b->re - a->rb) / ((b->re - b->rb) + (a->re - a->rb)) * (b->score + a->score) + .499);
+  if ((double)score / MAXV(q_s, r_s) < 0.90f) return 0;
+  *w_out = w;
+  return score;
+}
+
+static void sort_dedup(const bq_opt_t *opt, const bq_ref_t *ref, uint8_t *query, bq_regv_t *regs) {
+  if (regs->n <= 1) return;
+  bq_introsort(regs->a, regs->n, sizeof(bq_reg_t), lt_re);
+  int i, m;
+  for (i = 0; (size_t)i < regs->n; ++i) regs->a[i].n_comp = 1;
+  for (i = 1; (size_t)i < regs->n; ++i) {
+    bq_reg_t *p = regs->a + i;
+    for (int j = i - 1; j >= 0 && p->rid == regs->a[j].rid && p->rb < regs->a[j].re + opt->max_chain_gap; --j) {
+      bq_reg_t *q = regs->a + j;
+      if (q->qe == q->qb) continue;
+      int64_t orr = q->re - p->rb, oq = q->qb < p->qb ? q->qe - p->qb : p->qe - q->qb;
+      int64_t mr = MINV(q->re - q->rb, p->re - p->rb), mq = MINV(q->qe - q->qb, p->qe - p->qb);
+      int score, w;
+      if (orr > opt->mask_level_redun * mr && oq > opt->mask_level_redun * mq) {
+        if (p->score < q->score) { p->qe = p->qb; break; }
+        else q->qe = q->qb;
+      } else if (q->rb < p->rb && (score = test_concatenation(opt, ref, query, q, p, &w)) > 0) {
+        p->n_comp += q->n_comp + 1;
+        p->seedcov = p->seedcov > q->seedcov ? p->seedcov : q->seedcov;
+        p->sub = MAXV(p->sub, q->sub);
+        p->csub = MAXV(p->csub, q->csub);
+        p->truesc = p->score = score;
+        p->qb = q->qb; p->rb = q->rb; p->w = w;
+        q->qb = q->qe;
+      }
+    }
+  }
+  for (i = 0, m = 0; (size_t)i < regs->n; ++i)
+    if (regs->a[i].qe > regs->a[i].qb) { if (m != i) regs->a[m++] = regs->a[i]; else ++m; }
+  regs->n = (size_t)m;
+  bq_introsort(regs->a, regs->n, sizeof(bq_reg_t), lt_score_rb_qb);
+  for (i = 1; (size_t)i < regs->n; ++i)
+    if (regs->a[i].score == regs->a[i - 1].score && regs->a[i].rb == regs->a[i - 1].rb && regs->a[i].qb == regs->a[i - 1].qb)
+      regs->a[i].qe = regs->a[i].qb;
+  for (i = 1, m = 1; (size_t)i < regs->n; ++i)
+    if (regs->a[i].qe > regs->a[i].qb) { if (m != i) regs->a[m++] = regs->a[i]; else ++m; }
+  regs->n = (size_t)m;
+}
+
+void bq_merge_regions(const bq_opt_t *opt, const bq_ref_t *ref, const uint8_t *query, int l_query, bq_regv_t *regs) {
+  sort_dedup(opt, ref, (uint8_t *)query, regs);
+  if ((opt->flag & BQ_F_SELF_OVLP) && regs->n && regs->a[0].truesc == l_query * opt->a) { /* mem_test_and_remove_exact */
+    memmove(regs->a, regs->a + 1, (regs->n - 1) * sizeof(bq_reg_t));
+    regs->n--;
+  }
+  for (size_t i = 0; i < regs->n; ++i)
+    if (regs->a[i].rid >= 0 && ref->anns[regs->a[i].rid].is_alt) regs->a[i].is_alt = 1;
+}
+
+/* ---------------- insert size statistics: mem_pair.c:42-144 ---------------- */
+
+static int cal_sub(const bq_opt_t *opt, const bq_regv_t *regs) {
+  const bq_reg_t *best = &regs->a[0], *p = 0;
+  size_t j;
+  for (j = 1; j < regs->n; ++j) {
+    p = &regs->a[j];
+    int b_max = MAXV(p->qb, best->qb), e_min = MINV(p->qe, best->qe);
+    if (e_min > b_max) {
+      int min_l = MINV(p->qe - p->qb, best->qe - best->qb);
+      if (e_min - b_max >= min_l * opt->mask_level) break;
+    }
+  }
+  return j < regs->n ? p->score : opt->min_seed_len * opt->a;
+}
+
+static int lt_i64(const void *a, const void *b) { return *(const int64_t *)a < *(const int64_t *)b; }
+
+bq_pestat_t bq_pestat(const bq_opt_t *opt, const bq_ref_t *ref, int n, const bq_regv_t *regs) {
+  int64_t *isz = malloc(sizeof(int64_t) * (size_t)(n / 2 + 1));
+  size_t n_is = 0;
+  bq_pestat_t pes;
+  memset(&pes, 0, sizeof pes);
+  for (int i = 0; i < n >> 1; ++i) {
+    const bq_regv_t *r0 = &regs[i << 1], *r1 = &regs[i << 1 | 1];
+    int64_t is;
+    if (r0->n == 0 || r1->n == 0) continue;
+    if (cal_sub(opt, r0) > 0.8 * r0->a[0].score) continue; /* MIN_RATIO, mem_pair.c:35 */
+    if (cal_sub(opt, r1) > 0.8 * r1->a[0].score) continue;
+    if (r0->a[0].rid != r1->a[0].rid) continue;
+    if (r0->a[0].bss != r1->a[0].bss) continue;
+    if (reg_isize(ref, &r0->a[0], &r1->a[0], &is))
+      if (is <= opt->max_ins && is >= -opt->max_ins) isz[n_is++] = is;
+  }
+  if (bq_verbose >= 3) fprintf(stderr, "[M::mem_pestat] # candidate unique pairs: %ld\n", (long)n_is);
+  if (n_is < 10) {
+    fprintf(stderr, "[M:mem_pestat] There are not enough pairs for insert size inference\n");
+    free(isz);
+    pes.failed = 1;
+    return pes;
+  }
+  bq_introsort(isz, n_is, sizeof(int64_t), lt_i64);
+  int p25 = (int)isz[(int)(.25 * n_is + .499)], p50 = (int)isz[(int)(.50 * n_is + .499)], p75 = (int)isz[(int)(.75 * n_is + .499)];
+  pes.low = (int)(p25 - 2.0 * (p75 - p25) + .499);
+  pes.high = (int)(p75 + 2.0 * (p75 - p25) + .499);
+  fprintf(stderr, "[M::mem_pestat] (25, 50, 75) percentile: (%d, %d, %d)\n", p25, p50, p75);
+  fprintf(stderr, "[M::mem_pestat] low and high boundaries for computing mean and std.dev: (%d, %d)\n", pes.low, pes.high);
+  int x = 0;
+  size_t i;
+  for (i = 0, pes.avg = 0; i < n_is; ++i)
+    if (isz[i] >= pes.low && isz[i] <= pes.high) { pes.avg += isz[i]; ++x; }
+  pes.avg /= x;
+  for (i = 0, pes.std = 0; i < n_is; ++i)
+    if (isz[i] >= pes.low && isz[i] <= pes.high) pes.std += (isz[i] - pes.avg) * (isz[i] - pes.avg);
+  pes.std = sqrt(pes.std / x);
+  fprintf(stderr, "[M::mem_pestat] mean and std.dev: (%.2f, %.2f)\n", pes.avg, pes.std);
+  pes.low = (int)(p25 - 3.0 * (p75 - p25) + .499);
+  pes.high = (int)(p75 + 3.0 * (p75 - p25) + .499);
+  if (pes.low > pes.avg - 4.0 * pes.std) pes.low = (int)(pes.avg - 4.0 * pes.std + .499);
+  if (pes.high < pes.avg + 4.0 * pes.std) pes.high = (int)(pes.avg + 4.0 * pes.std + .499);
+  fprintf(stderr, "[M::mem_pestat] low and high boundaries for proper pairs: (%d, %d)\n", pes.low, pes.high);
+  free(isz);
+  return pes;
+}
+
+/* ---------------- mate rescue: mem_alnreg.c:395-513 ---------------- */
+
+static void matesw_core(const bq_opt_t *opt, const bq_ref_t *ref, bq_pestat_t pes, const bq_reg_t *reg, int l_ms, const uint8_t *ms,
+                        bq_regv_t *mregs) {
+  const int64_t l_pac = ref->l_pac;
+  int i;
+  for (i = 0; (size_t)i < mregs->n; ++i) {
+    int64_t is;
+    if (reg_isize(ref, reg, &mregs->a[i], &is) && is >= pes.low && is <= pes.high) return;
+  }
+  uint8_t *rev = malloc((size_t)l_ms + 1);
+  for (i = 0; i < l_ms; ++i) rev[l_ms - 1 - i] = ms[i] < 4 ? 3 - ms[i] : 4;
+  int64_t rb = MAXV(0, reg->rb + pes.low - l_ms), re = MINV(l_pac << 1, reg->rb + pes.high);
+  uint8_t *rseq = 0;
+  int rid = -1;
+  if (rb < re) rseq = bq_fetch_seq(ref, &rb, (rb + re) >> 1, &re, &rid);
+  if (reg->rid != rid || re - rb < opt->min_seed_len) { free(rev); free(rseq); return; }
+  const uint8_t parent = reg->bss ^ (reg->rb < l_pac);
+  const int xtra = BQ_XSUBO | BQ_XSTART | (l_ms * opt->a < 250 ? BQ_XBYTE : 0) | (opt->min_seed_len * opt->a);
+  bq_swr_t aln = bq_local_align(l_ms, rev, (int)(re - rb), rseq, parent ? opt->gamat : opt->ctmat, opt->o_del, opt->e_del, opt->o_ins,
+                                opt->e_ins, xtra);
+  if (aln.score >= opt->min_seed_len && aln.qb >= 0) {
+    bq_reg_t b;
+    memset(&b, 0, sizeof b);
+    b.rid = reg->rid; b.is_alt = reg->is_alt;
+    b.qb = l_ms - (aln.qe + 1); b.qe = l_ms - aln.qb;
+    b.rb = (l_pac << 1) - (rb + aln.te + 1); b.re = (l_pac << 1) - (rb + aln.tb);
+    b.score = aln.score; b.csub = aln.score2; b.secondary = -1;
+    b.seedcov = (int)(MINV(b.re - b.rb, (int64_t)(b.qe - b.qb)) >> 1);
+    b.bss = reg->bss; b.parent = 1 - parent;
+    regv_push(mregs, &b);
+    for (i = 0; (size_t)i < mregs->n - 1; ++i)
+      if (mregs->a[i].score < b.score) break;
+    int at = i;
+    for (i = (int)mregs->n - 1; i > at; --i) mregs->a[i] = mregs->a[i - 1];
+    mregs->a[i] = b;
+    sort_dedup(opt, 0, 0, mregs);
+  }
+  free(rev); free(rseq);
+}
+
+void bq_matesw(const bq_opt_t *opt, const bq_ref_t *ref, bq_pestat_t pes, bq_read_t s[2], bq_regv_t regs[2]) {
+  bq_regv_t good[2] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+  int i;
+  size_t j;
+  for (i = 0; i < 2; ++i)
+    for (j = 0; j < regs[i].n; ++j)
+      if (regs[i].a[j].score >= regs[i].a[0].score - opt->pen_unpaired) regv_push(&good[i], &regs[i].a[j]);
+  for (i = 0; i < 2; ++i)
+    for (j = 0; j < good[i].n && (int)j < opt->max_matesw; ++j)
+      matesw_core(opt, ref, pes, &good[i].a[j], s[!i].l_seq, s[!i].seq, &regs[!i]);
+  free(good[0].a); free(good[1].a);
+}
+
+/* ---------------- primary marking: mem_alnreg.c:242-380 ---------------- */
+
+static int lt_hash(const void *a_, const void *b_) {
+  const bq_reg_t *a = a_, *b = b_;
+  return a->score > b->score || (a->score == b->score && (a->is_alt < b->is_alt || (a->is_alt == b->is_alt && a->hash < b->hash)));
+}
+static int lt_hash2(const void *a_, const void *b_) {
+  const bq_reg_t *a = a_, *b = b_;
+  return a->is_alt < b->is_alt || (a->is_alt == b->is_alt && (a->score > b->score || (a->score == b->score && a->hash < b->hash)));
+}
+
+static void mark_core(const bq_opt_t *opt, int n_mark, bq_regv_t *regs, int *z, int *nz) {
+  int tmp = opt->a + opt->b;
+  tmp = MAXV(opt->o_del + opt->e_del, tmp);
+  tmp = MAXV(opt->o_ins + opt->e_ins, tmp);
+  *nz = 0;
+  z[(*nz)++] = 0;
+  for (int i = 1; i < n_mark; ++i) {
+    bq_reg_t *a = regs->a + i;
+    int k;
+    for (k = 0; k < *nz; ++k) {
+      bq_reg_t *b = regs->a + z[k];
+      int b_max = MAXV(a->qb, b->qb), e_min = MINV(a->qe, b->qe);
+      if (e_min > b_max) {
+        int min_l = MINV(a->qe - a->qb, b->qe - b->qb);
+        if (e_min - b_max >= min_l * opt->mask_level) {
+          if (b->sub == 0) b->sub = a->score;
+          if (b->score - a->score <= tmp && (b->is_alt || !a->is_alt)) ++b->sub_n;
+          break;
+        }
+      }
+    }
+    if (k == *nz) z[(*nz)++] = i;
+    else a->secondary = z[k];
+  }
+}
+
+void bq_mark_primary(const bq_opt_t *opt, bq_regv_t *regs, int64_t id) {
+  regs->n_pri = 0;
+  if (regs->n == 0) return;
+  int i, nz;
+  for (i = 0; (size_t)i < regs->n; ++i) {
+    bq_reg_t *p = regs->a + i;
+    p->sub = p->alt_sc = 0;
+    p->secondary = p->secondary_all = -1;
+    p->hash = bq_hash64((uint64_t)(id + i));
+    if (!p->is_alt) ++regs->n_pri;
+  }
+  bq_introsort(regs->a, regs->n, sizeof(bq_reg_t), lt_hash);
+  int *z = malloc(sizeof(int) * (regs->n + 1));
+  mark_core(opt, (int)regs->n, regs, z, &nz);
+  for (i = 0; (size_t)i < regs->n; ++i) {
+    bq_reg_t *p = regs->a + i;
+    p->secondary_all = i;
+    if (!p->is_alt && p->secondary >= 0 && regs->a[p->secondary].is_alt) p->alt_sc = regs->a[p->secondary].score;
+  }
+  if (regs->n_pri > 0 && regs->n_pri < regs->n) {
+    bq_introsort(regs->a, regs->n, sizeof(bq_reg_t), lt_hash2);
+    for (i = 0; (size_t)i < regs->n; ++i) z[regs->a[i].secondary_all] = i;
+    for (i = 0; (size_t)i < regs->n; ++i) {
+      if (regs->a[i].secondary >= 0) {
+        regs->a[i].secondary_all = z[regs->a[i].secondary];
+        if (regs->a[i].is_alt) regs->a[i].secondary = INT_MAX;
+      } else regs->a[i].secondary_all = -1;
+    }
+    for (i = 0; (size_t)i < regs->n_pri; ++i) { regs->a[i].sub = 0; regs->a[i].secondary = -1; }
+    mark_core(opt, (int)regs->n_pri, regs, z, &nz);
+  } else
+    for (i = 0; (size_t)i < regs->n; ++i) regs->a[i].secondary_all = regs->a[i].secondary;
+  free(z);
+}
+
+/* ---------------- mapQ: bwamem.c:134-157 ---------------- */
+
+int bq_approx_mapq_se(const bq_opt_t *opt, const bq_reg_t *a) {
+  int mapq, l, sub = a->sub ? a->sub : opt->min_seed_len * opt->a;
+  double identity;
+  sub = a->csub > sub ? a->csub : sub;
+  if (sub >= a->score) return 0;
+  l = a->qe - a->qb > a->re - a->rb ? a->qe - a->qb : (int)(a->re - a->rb);
+  identity = 1. - (double)(l * opt->a - a->score) / (opt->a + opt->b) / l;
+  if (a->score == 0) mapq = 0;
+  else if (opt->mapQ_coef_len > 0) {
+    double tmp = l < opt->mapQ_coef_len ? 1. : opt->mapQ_coef_fac / log(l);
+    tmp *= identity * identity;
+    mapq = (int)(6.02 * (a->score - sub) / opt->a * tmp * tmp + .499);
+  } else {
+    mapq = (int)(30.0 * (1. - (double)sub / a->score) * log(a->seedcov) + .499);
+    mapq = identity < 0.95 ? (int)(mapq * identity * identity + .499) : mapq;
+  }
+  if (a->sub_n > 0) mapq -= (int)(4.343 * log(a->sub_n + 1) + .499);
+  if (mapq > 60) mapq = 60;
+  if (mapq < 0) mapq = 0;
+  mapq = (int)(mapq * (1. - a->frac_rep) + .499);
+  return mapq;
+}
+
+/* ---------------- pairing: mem_pair.c:147-270 ---------------- */
+
+typedef struct { uint64_t x, y, z; } trio_t;
+typedef struct { uint64_t x, y; } pair_t;
+static int lt_xy3(const void *a_, const void *b_) { const trio_t *a = a_, *b = b_; return a->x < b->x || (a->x == b->x && a->y < b->y); }
+static int lt_xy2(const void *a_, const void *b_) { const pair_t *a = a_, *b = b_; return a->x < b->x || (a->x == b->x && a->y < b->y); }
+
+static void pair_regs(const bq_opt_t *opt, const bq_ref_t *ref, bq_pestat_t pes, bq_regv_t regs[2], int id, int *score, int *sub, int *n_sub,
+                      int z[2]) {
+  const int64_t l_pac = ref->l_pac;
+  size_t nv = regs[0].n_pri + regs[1].n_pri, n = 0, np = 0, mp = 0;
+  trio_t *v = malloc(sizeof(trio_t) * (nv + 1));
+  pair_t *pp = 0;
+  int i, k, r;
+  for (r = 0; r < 2; ++r)
+    for (i = 0; (size_t)i < regs[r].n_pri; ++i) {
+      const bq_reg_t *p = &regs[r].a[i];
+      v[n].x = (uint64_t)p->bss << 63 | (uint64_t)p->rid << 32 | (uint64_t)(int64_t)region_depos(ref, p, 0);
+      v[n].y = (uint64_t)p->score << 32 | (uint64_t)(int64_t)(i << 2 | (p->rb >= l_pac) << 1 | r);
+      v[n].z = (uint64_t)(p->qe - p->qb);
+      ++n;
+    }
+  bq_introsort(v, n, sizeof(trio_t), lt_xy3);
+  for (i = 0; (size_t)i < n; ++i)
+    for (k = i - 1; k >= 0; --k) {
+      if (v[i].x >> 32 != v[k].x >> 32) break;
+      if (v[i].x >> 63 != v[k].x >> 63) break;
+      if ((int64_t)(v[i].x & 0xffffffffU) - (int64_t)(v[k].x & 0xffffffffU) > MAXV(pes.low, pes.high)) break;
+      if ((v[i].y & 1) == (v[k].y & 1)) break;
+      int64_t is = 0;
+      if (infer_isize((int64_t)v[k].x, (int64_t)v[i].x, (v[k].y >> 1) & 1, (v[i].y >> 1) & 1, (int64_t)v[k].z, (int64_t)v[i].z, &is) &&
+          is >= pes.low && is <= pes.high) {
+        double zscore = (is - pes.avg) / pes.std;
+        int sc = (int)((v[i].y >> 32) + (v[k].y >> 32) + .721 * log(2. * erfc(fabs(zscore) * M_SQRT1_2)) * opt->a + .499);
+        sc = MAXV(0, sc);
+        if (np == mp) { mp = mp ? mp << 1 : 8; pp = realloc(pp, mp * sizeof(pair_t)); }
+        pp[np].y = (uint64_t)k << 32 | (uint64_t)i;
+        pp[np].x = (uint64_t)sc << 32 | (bq_hash64(pp[np].y ^ (uint64_t)(int64_t)(id << 8)) & 0xffffffffU);
+        ++np;
+      }
+    }
+  if (np) {
+    bq_introsort(pp, np, sizeof(pair_t), lt_xy2);
+    i = (int)(pp[np - 1].y >> 32);
+    k = (int)(pp[np - 1].y << 32 >> 32);
+    z[v[i].y & 1] = (int)(v[i].y << 32 >> 34);
+    z[v[k].y & 1] = (int)(v[k].y << 32 >> 34);
+    *score = (int)(pp[np - 1].x >> 32);
+    *sub = np > 1 ? (int)(pp[np - 2].x >> 32) : 0;
+    int tmp = opt->a + opt->b;
+    tmp = MAXV(tmp, opt->o_del + opt->e_del);
+    tmp = MAXV(tmp, opt->o_ins + opt->e_ins);
+    *n_sub = 0;
+    for (long u = (long)np - 2; u >= 0; --u)
+      if (*sub - (int)(pp[u].x >> 32) <= tmp) ++*n_sub;
+  } else { *score = 0; *sub = 0; *n_sub = 0; z[0] = z[1] = -1; }
+  free(pp); free(v);
+}
+
+/* ---------------- SAM: mem_alnreg_format.c ---------------- */
+
+static int infer_bw(int l1, int l2, int score, int a, int q, int r) { /* bwamem.h:192 */
+  int w;
+  if (l1 == l2 && l1 * a - score < (q + r - a) << 1) return 0;
+  w = (int)((double)((l1 < l2 ? l1 : l2) * a - score - q) / r + 2.);
+  if (w < abs(l1 - l2)) w = abs(l1 - l2);
+  return w;
+}
+static int get_rlen(int n_cigar, const uint32_t *cigar) {
+  int l = 0;
+  for (int k = 0; k < n_cigar; ++k) { int op = cigar[k] & 0xf; if (op == 0 || op == 2) l += (int)(cigar[k] >> 4); }
+  return l;
+}
+
+/* mem_alnreg_setSAM (:40-123): final CIGAR with band doubling, position, clipping */
+static void set_sam(const bq_opt_t *opt, const bq_ref_t *ref, bq_read_t *s, bq_reg_t *reg) {
+  if (reg->n_cigar > 0) return;
+  uint8_t *query = malloc((size_t)s->l_seq + 1);
+  int i;
+  for (i = 0; i < s->l_seq; ++i) query[i] = s->seq[i] < 5 ? s->seq[i] : 4;
+  int w1 = infer_bw(reg->qe - reg->qb, (int)(reg->re - reg->rb), reg->truesc, opt->a, opt->o_del, opt->e_del);
+  int w2 = infer_bw(reg->qe - reg->qb, (int)(reg->re - reg->rb), reg->truesc, opt->a, opt->o_ins, opt->e_ins);
+  int w = MAXV(w1, w2);
+  if (w > opt->w) w = MINV(w, reg->w);
+  uint32_t *cigar = 0;
+  int n_cigar = 0, score = 0, last_sc = -(1 << 30);
+  for (i = 0; i < 3; ++i, w <<= 1, last_sc = score) {
+    free(cigar);
+    w = MINV(w, opt->w << 2);
+    cigar = bq_gen_cigar(reg->parent ? opt->ctmat : opt->gamat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, w, ref->l_pac, ref->pac,
+                         reg->qe - reg->qb, &query[reg->qb], reg->rb, reg->re, &score, &n_cigar, &reg->NM, &reg->ZC, &reg->ZR, &reg->bss_u,
+                         reg->parent);
+    if (score == last_sc) break;
+    if (w == opt->w << 2) break;
+    if (score >= reg->truesc - opt->a) break;
+  }
+  int l_MD = cigar ? (int)strlen((char *)(cigar + n_cigar)) + 1 : 0;
+  int is_rev;
+  int64_t rpos = bq_depos(ref, reg->rb < ref->l_pac ? reg->rb : reg->re - 1, &is_rev);
+  reg->is_rev = is_rev;
+  reg->flag |= reg->is_rev ? 0x10 : 0;
+  if (n_cigar > 0) {
+    if ((cigar[0] & 0xf) == 2) {
+      rpos += cigar[0] >> 4;
+      --n_cigar;
+      memmove(cigar, cigar + 1, (size_t)n_cigar * 4 + l_MD);
+    } else if ((cigar[n_cigar - 1] & 0xf) == 2) {
+      --n_cigar;
+      memmove(cigar + n_cigar, cigar + n_cigar + 1, (size_t)l_MD);
+    }
+  }
+  if (reg->qb != 0 || reg->qe != s->l_seq || s->clip5 || s->clip3) {
+    int clip5 = reg->is_rev ? s->l_seq - reg->qe + s->clip3 : reg->qb + s->clip5;
+    int clip3 = reg->is_rev ? reg->qb + s->clip5 : s->l_seq - reg->qe + s->clip3;
+    cigar = realloc(cigar, 4 * (size_t)(n_cigar + 2) + l_MD);
+    if (clip5) { memmove(cigar + 1, cigar, (size_t)n_cigar * 4 + l_MD); cigar[0] = (uint32_t)clip5 << 4 | 3; ++n_cigar; }
+    if (clip3) { memmove(cigar + n_cigar + 1, cigar + n_cigar, (size_t)l_MD); cigar[n_cigar++] = (uint32_t)clip3 << 4 | 3; }
+  }
+  free(query);
+  reg->n_cigar = n_cigar;
+  if (reg->n_cigar > 0) reg->cigar = cigar; else free(cigar);
+  reg->pos = (int)(rpos - ref->anns[reg->rid].offset);
+}
+
+static int get_pri_idx(double XA_drop_ratio, const bq_reg_t *a, int i) { /* mem_alnreg.h:127-131 */
+  int k = a[i].secondary_all;
+  if (k >= 0 && a[i].score >= a[k].score * XA_drop_ratio) return k;
+  return -1;
+}
+
+static void tag_xaxb(const bq_opt_t *opt, const bq_ref_t *ref, bq_read_t *s, const bq_reg_t *p0, const bq_regv_t *regs0, bq_str_t *out) {
+  if (!regs0 || (opt->flag & BQ_F_ALL)) return;
+  int cnt_pri = 0, cnt_alt = 0;
+  size_t i;
+  for (i = 0; i < regs0->n; ++i) {
+    int r = get_pri_idx(opt->XA_drop_ratio, regs0->a, (int)i);
+    if (r >= 0 && regs0->a + r == p0) { if (regs0->a[i].is_alt) ++cnt_alt; else ++cnt_pri; }
+  }
+  if (cnt_pri <= opt->max_XA_hits && cnt_alt <= opt->max_XA_hits_alt) {
+    bq_str_t str = {0, 0, 0};
+    int n = 0;
+    for (i = 0; i < regs0->n; ++i) {
+      bq_reg_t *q = regs0->a + i;
+      int r = get_pri_idx(opt->XA_drop_ratio, regs0->a, (int)i);
+      if (r < 0 || regs0->a + r != p0) continue;
+      if (q->n_cigar == 0) { set_sam(opt, ref, s, q); if (q->n_cigar == 0) continue; }
+      if (n) bq_kputc(&str, ';');
+      bq_kputs(&str, ref->anns[q->rid].name); bq_kputc(&str, ','); bq_kputc(&str, "+-"[q->is_rev]); bq_kputl(&str, q->pos + 1);
+      bq_kputc(&str, ',');
+      for (int k = 0; k < q->n_cigar; ++k) { bq_kputw(&str, (int)(q->cigar[k] >> 4)); bq_kputc(&str, "MIDSHN"[q->cigar[k] & 0xf]); }
+      bq_kputc(&str, ','); bq_kputw(&str, q->NM);
+      ++n;
+    }
+    if (str.l) { bq_kputsn(out, "\tXA:Z:", 6); bq_kputs(out, str.s); }
+    free(str.s);
+  }
+  if (cnt_pri > 0 || cnt_alt > 0) { bq_kputsn(out, "\tXB:Z:", 6); bq_kputw(out, cnt_pri); bq_kputc(out, ','); bq_kputw(out, cnt_alt); }
+}
+
+static void tag_sa(const bq_ref_t *ref, const bq_reg_t *p0, const bq_regv_t *regs0, bq_str_t *out) {
+  if (!regs0 || (p0->flag & 0x100)) return;
+  bq_str_t str = {0, 0, 0};
+  for (size_t i = 0; i < regs0->n; ++i) {
+    const bq_reg_t *q = regs0->a + i;
+    if (q == p0 || q->n_cigar == 0 || (q->flag & 0x100)) continue;
+    bq_kputs(&str, ref->anns[q->rid].name); bq_kputc(&str, ','); bq_kputl(&str, q->pos + 1); bq_kputc(&str, ',');
+    bq_kputc(&str, "+-"[q->is_rev]); bq_kputc(&str, ',');
+    for (int k = 0; k < q->n_cigar; ++k) { bq_kputw(&str, (int)(q->cigar[k] >> 4)); bq_kputc(&str, "MIDSH"[q->cigar[k] & 0xf]); }
+    bq_kputc(&str, ','); bq_kputw(&str, (int)q->mapq); bq_kputc(&str, ','); bq_kputw(&str, q->NM); bq_kputc(&str, ';');
+  }
+  if (str.l) { bq_kputsn(out, "\tSA:Z:", 6); bq_kputs(out, str.s); }
+  free(str.s);
+}
+
+static void put_cigar(const bq_opt_t *opt, const bq_reg_t *r, int is_primary, bq_str_t *str) {
+  for (int i = 0; i < r->n_cigar; ++i) {
+    int c = r->cigar[i] & 0xf;
+    if (!(opt->flag & BQ_F_SOFTCLIP) && !r->is_alt && (c == 3 || c == 4)) c = is_primary ? 3 : 4;
+    bq_kputw(str, (int)(r->cigar[i] >> 4)); bq_kputc(str, "MIDSH"[c]);
+  }
+}
+
+/* mem_alnreg_formatSAM (:237-436) */
+static void format_sam(const bq_opt_t *opt, const bq_ref_t *ref, bq_str_t *str, bq_read_t *s, const bq_reg_t *p0, const bq_reg_t *m0,
+                       const bq_regv_t *regs0, int is_primary, const bq_pestat_t *pes, const char *rg_id) {
+  bq_reg_t p = *p0, m;
+  memset(&m, 0, sizeof m);
+  if (m0) m = *m0;
+  p.flag |= m0 ? 0x1 : 0;
+  p.flag |= m0 && m.rid < 0 ? 0x8 : 0;
+  if (m0 && m0->bss_u == 0) p.bss_u = 0;
+  if (p.rid >= 0 && m0 && m.rid >= 0 && pes && is_proper_pair(ref, &p, &m, *pes)) { p.flag |= 2; m.flag |= 2; }
+  if (p.rid < 0 && m0 && m.rid >= 0) { p.rid = m.rid; p.pos = m.pos; p.is_rev = m.is_rev; p.n_cigar = 0; }
+  if (m0 && m.rid < 0 && p.rid >= 0) { m.rid = p.rid; m.pos = p.pos; m.is_rev = p.is_rev; m.n_cigar = 0; }
+  p.flag |= m0 && m.is_rev ? 0x20 : 0;
+  bq_kputs(str, s->name);
+  if (s->comment) { bq_kputc(str, '_'); bq_kputs(str, s->comment); }
+  bq_kputc(str, '\t');
+  bq_kputw(str, (p.flag & 0xffff) | (p.flag & 0x10000 ? 0x100 : 0)); bq_kputc(str, '\t');
+  if (p.rid >= 0) {
+    bq_kputs(str, ref->anns[p.rid].name); bq_kputc(str, '\t');
+    bq_kputl(str, p.pos + 1); bq_kputc(str, '\t');
+    bq_kputw(str, (int)p.mapq); bq_kputc(str, '\t');
+    if (p.n_cigar) put_cigar(opt, &p, is_primary, str);
+    else bq_kputc(str, '*');
+  } else bq_kputsn(str, "*\t0\t0\t*", 7);
+  bq_kputc(str, '\t');
+  if (m0 && m.rid >= 0) {
+    if (p.rid == m.rid) bq_kputc(str, '='); else bq_kputs(str, ref->anns[m.rid].name);
+    bq_kputc(str, '\t'); bq_kputl(str, m.pos + 1); bq_kputc(str, '\t');
+    if (p.rid == m.rid) { /* biscuit-specific TLEN (:304-311) */
+      int64_t q0 = -1, q1 = -1;
+      if (p.is_rev) q1 = p.pos + get_rlen(p.n_cigar, p.cigar) - 1; else q0 = p.pos;
+      if (m.is_rev) q1 = m.pos + get_rlen(m.n_cigar, m.cigar) - 1; else q0 = m.pos;
+      if (p.n_cigar > 0 && m.n_cigar > 0 && q0 >= 0 && q1 >= 0) bq_kputl(str, (long)(q1 - q0 + 1));
+      else bq_kputc(str, '0');
+    } else bq_kputc(str, '0');
+  } else bq_kputsn(str, "*\t0\t0", 5);
+  bq_kputc(str, '\t');
+  if (p.flag & 0x100) bq_kputsn(str, "*\t*", 3);
+  else {
+    int i, qb = 0, qe = s->l_seq0;
+    const int hard = p.n_cigar && !is_primary && !(opt->flag & BQ_F_SOFTCLIP) && !p.is_alt;
+    if (p.is_rev) {
+      if (hard) {
+        if ((p.cigar[0] & 0xf) == 4 || (p.cigar[0] & 0xf) == 3) qe -= (int)(p.cigar[0] >> 4);
+        if ((p.cigar[p.n_cigar - 1] & 0xf) == 4 || (p.cigar[p.n_cigar - 1] & 0xf) == 3) qb += (int)(p.cigar[p.n_cigar - 1] >> 4);
+      }
+      bq_str_reserve(str, (size_t)(qe - qb) * 2 + 4);
+      for (i = qe - 1; i >= qb; --i) str->s[str->l++] = "TGCAN"[(int)s->seq0[i]];
+      str->s[str->l] = 0;
+      bq_kputc(str, '\t');
+      if (s->qual) { for (i = qe - 1; i >= qb; --i) str->s[str->l++] = s->qual[i]; str->s[str->l] = 0; }
+      else bq_kputc(str, '*');
+    } else {
+      if (hard) {
+        if ((p.cigar[0] & 0xf) == 4 || (p.cigar[0] & 0xf) == 3) qb += (int)(p.cigar[0] >> 4);
+        if ((p.cigar[p.n_cigar - 1] & 0xf) == 4 || (p.cigar[p.n_cigar - 1] & 0xf) == 3) qe -= (int)(p.cigar[p.n_cigar - 1] >> 4);
+      }
+      bq_str_reserve(str, (size_t)(qe - qb) * 2 + 4);
+      for (i = qb; i < qe; ++i) str->s[str->l++] = "ACGTN"[(int)s->seq0[i]];
+      str->s[str->l] = 0;
+      bq_kputc(str, '\t');
+      if (s->qual) { for (i = qb; i < qe; ++i) str->s[str->l++] = s->qual[i]; str->s[str->l] = 0; }
+      else bq_kputc(str, '*');
+    }
+  }
+  if (p.n_cigar) {
+    bq_kputsn(str, "\tNM:i:", 6); bq_kputw(str, p.NM);
+    bq_kputsn(str, "\tMD:Z:", 6); bq_kputs(str, (char *)(p.cigar + p.n_cigar));
+    bq_kputsn(str, "\tZC:i:", 6); bq_kputw(str, (int)p.ZC);
+    bq_kputsn(str, "\tZR:i:", 6); bq_kputw(str, (int)p.ZR);
+  }
+  if (p.score >= 0) { bq_kputsn(str, "\tAS:i:", 6); bq_kputw(str, p.score); }
+  if (p.sub >= 0) { bq_kputsn(str, "\tXS:i:", 6); bq_kputw(str, MAXV(p.sub, p.csub)); }
+  if (rg_id && rg_id[0]) { bq_kputsn(str, "\tRG:Z:", 6); bq_kputs(str, rg_id); }
+  if (regs0) tag_sa(ref, p0, regs0, str);
+  if (is_primary && p.alt_sc > 0) { char b[64]; snprintf(b, sizeof b, "\tPA:f:%.3f", (double)p.score / p.alt_sc); bq_kputs(str, b); }
+  bq_kputsn(str, "\tXL:i:", 6); bq_kputw(str, s->l_seq);
+  if (regs0) tag_xaxb(opt, ref, s, p0, regs0, str);
+  if ((opt->flag & BQ_F_REF_HDR) && p.rid >= 0 && ref->anns[p.rid].anno != 0 && ref->anns[p.rid].anno[0] != 0) {
+    bq_kputsn(str, "\tXR:Z:", 6);
+    size_t t0 = str->l;
+    bq_kputs(str, ref->anns[p.rid].anno);
+    for (size_t i = t0; i < str->l; ++i) if (str->s[i] == '\t') str->s[i] = ' ';
+  }
+  if (s->barcode) { bq_kputsn(str, "\tCB:Z:", 6); bq_kputs(str, s->barcode); }
+  if (s->umi) { bq_kputsn(str, "\tRX:Z:", 6); bq_kputs(str, s->umi); }
+  bq_kputsn(str, "\tMC:Z:", 6);
+  if (m.n_cigar) put_cigar(opt, &m, is_primary, str); else bq_kputc(str, '*');
+  bq_kputsn(str, "\tMQ:i:", 6); bq_kputw(str, (int)m.mapq);
+  bq_kputsn(str, "\tYD:A:", 6);
+  if (p.bss_u) bq_kputc(str, 'u'); else bq_kputc(str, "fr"[p.bss]);
+  bq_kputc(str, '\n');
+}
+
+/* mem_alnreg_select_format (:445-488) */
+static int *select_format(const bq_opt_t *opt, const bq_ref_t *ref, bq_read_t *s, bq_regv_t *regs, int *n_out) {
+  int *out = malloc(sizeof(int) * (regs->n + 1)), l = 0;
+  for (size_t k = 0; k < regs->n; ++k) {
+    bq_reg_t *p = regs->a + k;
+    if (p->rb < 0 || p->re < 0) continue;
+    if (p->score < opt->T) continue;
+    if (p->secondary >= 0 && (p->is_alt || !(opt->flag & BQ_F_ALL))) continue;
+    if (p->secondary >= 0 && p->secondary < INT_MAX && p->score < regs->a[p->secondary].score * opt->drop_ratio) continue;
+    if (l && p->secondary < 0) p->flag |= (opt->flag & BQ_F_NO_MULTI) ? 0x10000 : 0x800;
+    if (p->secondary >= 0) p->flag |= 0x100;
+    p->mapq = p->secondary < 0 ? (unsigned)bq_approx_mapq_se(opt, p) : 0;
+    if (!(opt->flag & BQ_F_KEEP_SUPP_MAPQ) && l && !p->is_alt) p->mapq = MINV(p->mapq, regs->a[0].mapq);
+    set_sam(opt, ref, s, p);
+    out[l++] = (int)k;
+  }
+  *n_out = l;
+  return out;
+}
+
+void bq_reg2sam_se(const bq_opt_t *opt, const bq_ref_t *ref, bq_read_t *s, bq_regv_t *regs, const char *rg_id) {
+  bq_str_t str = {0, 0, 0};
+  int n, *to = select_format(opt, ref, s, regs, &n);
+  if (n > 0) for (int i = 0; i < n; ++i) format_sam(opt, ref, &str, s, &regs->a[to[i]], 0, regs, !i, 0, rg_id);
+  else {
+    bq_reg_t reg;
+    memset(&reg, 0, sizeof reg);
+    reg.rid = -1; reg.flag = 0x4;
+    format_sam(opt, ref, &str, s, &reg, 0, regs, 1, 0, rg_id);
+  }
+  s->sam = str.s;
+  free(to);
+}
+
+static void reg2sam_pe_nopairing(const bq_opt_t *opt, const bq_ref_t *ref, bq_read_t s[2], bq_regv_t regs[2], bq_pestat_t pes,
+                                 const char *rg_id) {
+  bq_reg_t *best[2] = {0, 0}, unmapped[2];
+  int *to[2], n_to[2], i;
+  for (i = 0; i < 2; ++i) {
+    to[i] = select_format(opt, ref, &s[i], &regs[i], &n_to[i]);
+    if (n_to[i] > 0) best[i] = &regs[i].a[to[i][0]];
+    else {
+      memset(&unmapped[i], 0, sizeof(bq_reg_t));
+      unmapped[i].rid = -1; unmapped[i].flag = 0x40 << i | 0x1 | 0x4;
+      best[i] = &unmapped[i];
+    }
+  }
+  for (i = 0; i < 2; ++i) {
+    bq_str_t str = {0, 0, 0};
+    if (n_to[i]) {
+      for (int j = 0; j < n_to[i]; ++j) format_sam(opt, ref, &str, &s[i], &regs[i].a[to[i][j]], best[!i], &regs[i], !j, &pes, rg_id);
+    } else format_sam(opt, ref, &str, &s[i], best[i], best[!i], 0, 1, &pes, rg_id);
+    s[i].sam = str.s;
+  }
+  free(to[0]); free(to[1]);
+}
+
+#define RAW_MAPQ(diff, a) ((int)(6.02 * (diff) / (a) + .499))
+
+/* mem_reg2sam_pe (:562-696) */
+void bq_reg2sam_pe(const bq_opt_t *opt, const bq_ref_t *ref, uint64_t id, bq_read_t s[2], bq_regv_t regs[2], bq_pestat_t pes,
+                   const char *rg_id) {
+  int i;
+  size_t k, j;
+  for (i = 0; i < 2; ++i)
+    for (k = 0; k < regs[i].n; ++k) regs[i].a[k].flag |= (0x40 << i) | 1;
+  if ((opt->flag & BQ_F_NOPAIRING) || regs[0].n_pri == 0 || regs[1].n_pri == 0) { reg2sam_pe_nopairing(opt, ref, s, regs, pes, rg_id); return; }
+  int is_multi[2];
+  for (i = 0; i < 2; ++i) {
+    for (j = 1; j < regs[i].n_pri; ++j)
+      if (regs[i].a[j].secondary < 0 && regs[i].a[j].score >= opt->T) break;
+    is_multi[i] = j < regs[i].n_pri ? 1 : 0;
+  }
+  if (is_multi[0] || is_multi[1]) { reg2sam_pe_nopairing(opt, ref, s, regs, pes, rg_id); return; }
+  int pscore, sub_pscore, n_sub, z[2] = {0, 0};
+  pair_regs(opt, ref, pes, regs, (int)id, &pscore, &sub_pscore, &n_sub, z);
+  if (pscore <= 0) { reg2sam_pe_nopairing(opt, ref, s, regs, pes, rg_id); return; }
+  int score_unpaired = regs[0].a[0].score + regs[1].a[0].score - opt->pen_unpaired;
+  if (pscore > score_unpaired) {
+    sub_pscore = MAXV(sub_pscore, score_unpaired);
+    int q_pe = RAW_MAPQ(pscore - sub_pscore, opt->a);
+    if (n_sub > 0) q_pe -= (int)(4.343 * log(n_sub + 1) + .499);
+    q_pe = MAXV(0, MINV(60, q_pe));
+    q_pe = (int)(q_pe * (1. - .5 * (regs[0].a[0].frac_rep + regs[1].a[0].frac_rep)) + .499);
+    int q_se[2];
+    bq_reg_t *c[2] = {&regs[0].a[z[0]], &regs[1].a[z[1]]};
+    for (i = 0; i < 2; ++i) {
+      if (c[i]->secondary >= 0) { c[i]->sub = regs[i].a[c[i]->secondary].score; c[i]->secondary = -2; }
+      q_se[i] = bq_approx_mapq_se(opt, c[i]);
+    }
+    q_se[0] = MAXV(q_se[0], MINV(q_pe, q_se[0] + 40));
+    q_se[1] = MAXV(q_se[1], MINV(q_pe, q_se[1] + 40));
+    c[0]->mapq = (unsigned)MINV(q_se[0], RAW_MAPQ(c[0]->score - c[0]->csub, opt->a));
+    c[1]->mapq = (unsigned)MINV(q_se[1], RAW_MAPQ(c[1]->score - c[1]->csub, opt->a));
+  } else {
+    z[0] = z[1] = 0;
+    regs[0].a[0].mapq = (unsigned)bq_approx_mapq_se(opt, &regs[0].a[0]);
+    regs[1].a[0].mapq = (unsigned)bq_approx_mapq_se(opt, &regs[1].a[0]);
+  }
+  for (i = 0; i < 2; ++i) { /* a chosen secondary swaps roles with its primary */
+    bq_regv_t *r = &regs[i];
+    int kk = r->a[z[i]].secondary_all;
+    if (kk >= 0 && (size_t)kk < r->n_pri) {
+      for (j = 0; j < r->n; ++j)
+        if (r->a[j].secondary_all == kk || j == (size_t)kk) r->a[j].secondary_all = z[i];
+      r->a[z[i]].secondary_all = -1;
+    }
+  }
+  for (i = 0; i < 2; ++i) set_sam(opt, ref, &s[i], &regs[i].a[z[i]]);
+  for (i = 0; i < 2; ++i) {
+    bq_str_t str = {0, 0, 0};
+    bq_regv_t *r = &regs[i];
+    format_sam(opt, ref, &str, &s[i], r->a + z[i], regs[!i].a + z[!i], r, 1, &pes, rg_id);
+    if (r->n_pri < r->n) {
+      bq_reg_t *p = &r->a[r->n_pri];
+      if (p->score >= opt->T && p->secondary < 0) {
+        p->flag |= 0x800;
+        set_sam(opt, ref, &s[i], p);
+        format_sam(opt, ref, &str, &s[i], p, 0, r, 0, &pes, rg_id);
+      }
+    }
+    s[i].sam = str.s;
+  }
+}
+
+/* ---------------- read clipping: bwamem.c:238-303 ---------------- */
+
+static const uint8_t *find_sub(const uint8_t *hay, size_t hlen, const uint8_t *needle, size_t nlen) {
+  if (!nlen) return 0;
+  for (size_t i = 0; i + nlen <= hlen; ++i)
+    if (hay[i] == needle[0] && memcmp(hay + i, needle, nlen) == 0) return hay + i;
+  return 0;
+}
+
+void bq_read_clipping(bq_read_t *s, const uint8_t *adaptor, int l_adaptor, const bq_opt_t *opt) {
+  if (adaptor == 0) s->l_adaptor = 0;
+  else {
+    const uint8_t *hit = find_sub(s->seq, (size_t)s->l_seq, adaptor, (size_t)l_adaptor);
+    if (hit) s->l_adaptor = s->l_seq - (int)(hit - s->seq);
+    else {
+      int i;
+      for (i = l_adaptor - 1; i; --i)
+        if (memcmp(s->seq + s->l_seq - i, adaptor, (size_t)i) == 0) break;
+      s->l_adaptor = i;
+    }
+  }
+  s->clip5 = opt->clip5;
+  s->clip3 = opt->clip3 + s->l_adaptor;
+  if (s->qual) {
+    for (; s->clip5 < s->l_seq - s->clip3; s->clip5++)
+      if (s->qual[s->clip5] >= opt->min_base_qual + 33) break;
+    for (; s->l_seq - s->clip3 >= s->clip5; s->clip3++)
+      if (s->qual[s->l_seq - s->clip3 - 1] >= opt->min_base_qual + 33) break;
+  }
+  s->seq0 = s->seq; s->l_seq0 = s->l_seq;
+  s->seq += s->clip5;
+  s->l_seq = s->l_seq - s->clip3 - s->clip5;
+  if (s->l_seq < 0) s->l_seq = 0;
+}
+
+/* ---------------- the batch driver: mem_process_seqs (bwamem.c:432-476) ---------------- */
+
+typedef struct {
+  const bq_opt_t *opt; const bq_ref_t *ref; bq_read_t *seqs; bq_regv_t *regs; bq_pestat_t pes; int64_t n_processed;
+  const char *rg_id; int n_items, n_threads, pe, stage;
+  const bsq_reg *dev_regs; const int64_t *reg_off; const int64_t *task_of_read; /* first task of each read */
+  const uint8_t *n_task_of_read;
+} work_t;
+
+static void reg_from_dev(const bsq_reg *d, bq_reg_t *r) {
+  memset(r, 0, sizeof *r);
+  r->rb = d->rb; r->re = d->re; r->qb = d->qb; r->qe = d->qe; r->rid = d->rid; r->score = d->score; r->truesc = d->truesc; r->w = d->w;
+  r->seedcov = d->seedcov; r->seedlen0 = d->seedlen0; r->frac_rep = d->frac_rep; r->bss = d->bss; r->parent = d->parent;
+}
+
+static void work_item(work_t *w, long i) {
+  if (w->stage == 1) { /* gather the regions of read i in the reference's order and merge them */
+    bq_regv_t *rv = &w->regs[i];
+    rv->n = rv->m = rv->n_pri = 0; rv->a = 0;
+    for (int t = 0; t < w->n_task_of_read[i]; ++t) {
+      const int64_t task = w->task_of_read[i] + t;
+      for (int64_t k = w->reg_off[task]; k < w->reg_off[task + 1]; ++k) { bq_reg_t r; reg_from_dev(&w->dev_regs[k], &r); regv_push(rv, &r); }
+    }
+    bq_merge_regions(w->opt, w->ref, w->seqs[i].seq, w->seqs[i].l_seq, rv);
+  } else if (!w->pe) {
+    bq_mark_primary(w->opt, &w->regs[i], w->n_processed + i);
+    for (size_t k = 0; k < w->regs[i].n; ++k) w->regs[i].a[k].flag = 0;
+    bq_reg2sam_se(w->opt, w->ref, &w->seqs[i], &w->regs[i], w->rg_id);
+  } else {
+    if (!(w->opt->flag & BQ_F_NO_RESCUE)) bq_matesw(w->opt, w->ref, w->pes, &w->seqs[i << 1], &w->regs[i << 1]);
+    bq_mark_primary(w->opt, &w->regs[i << 1 | 0], i << 1 | 0); /* PE ids lack n_processed (bwamem.c:408,413) */
+    bq_mark_primary(w->opt, &w->regs[i << 1 | 1], i << 1 | 1);
+    for (int e = 0; e < 2; ++e)
+      for (size_t k = 0; k < w->regs[i << 1 | e].n; ++k) w->regs[i << 1 | e].a[k].flag = 0;
+    bq_reg2sam_pe(w->opt, w->ref, (uint64_t)((w->n_processed >> 1) + i), &w->seqs[i << 1], &w->regs[i << 1], w->pes, w->rg_id);
+  }
+}
+
+typedef struct { work_t *w; int tid; } thr_t;
+static void *thr_main(void *a) {
+  thr_t *t = a;
+  for (long i = t->tid; i < t->w->n_items; i += t->w->n_threads) work_item(t->w, i);
+  return 0;
+}
+static void run_threads(work_t *w, int n_items) {
+  w->n_items = n_items;
+  int nt = w->n_threads < 1 ? 1 : w->n_threads;
+  if (nt == 1) { for (long i = 0; i < n_items; ++i) work_item(w, i); return; }
+  pthread_t *th = malloc(sizeof(pthread_t) * (size_t)nt);
+  thr_t *ta = malloc(sizeof(thr_t) * (size_t)nt);
+  for (int t = 0; t < nt; ++t) { ta[t].w = w; ta[t].tid = t; pthread_create(&th[t], 0, thr_main, &ta[t]); }
+  for (int t = 0; t < nt; ++t) pthread_join(th[t], 0);
+  free(th); free(ta);
+}
+
+int bq_process_seqs(const bq_opt_t *opt, bsq_aligner *al, const bq_ref_t *ref, int64_t n_processed, int n, bq_read_t *seqs,
+                    const bq_pestat_t *pes0, const char *rg_id) {
+  const int pe = (opt->flag & BQ_F_PE) != 0;
+  int i, max_len = 1;
+  /* clipping (bwamem.c:322,343-344) */
+  for (i = 0; i < n; ++i) {
+    const int second = pe && (i & 1);
+    bq_read_clipping(&seqs[i], second ? opt->adaptor2 : opt->adaptor1, second ? opt->l_adaptor2 : opt->l_adaptor1, opt);
+    if (seqs[i].l_seq > max_len) max_len = seqs[i].l_seq;
+  }
+  /* (read, conversion) tasks in the order bis_worker1 runs them (bwamem.c:325-372) */
+  int64_t *task_of_read = malloc(sizeof(int64_t) * (size_t)(n + 1));
+  uint8_t *n_task = malloc((size_t)n + 1), *par = malloc((size_t)n * 2 + 2);
+  int64_t nt = 0;
+  for (i = 0; i < n; ++i) {
+    task_of_read[i] = nt;
+    int k0 = (int)nt;
+    if (!pe) {
+      if (!(opt->parent & 1) || opt->parent >> 1) par[nt++] = 0;
+      if (!(opt->parent & 1) || !(opt->parent >> 1)) par[nt++] = 1;
+    } else if (!(i & 1)) { par[nt++] = 1; if (!opt->parent) par[nt++] = 0; }
+    else { par[nt++] = 0; if (!opt->parent) par[nt++] = 1; }
+    n_task[i] = (uint8_t)(nt - k0);
+  }
+  const int stride = (max_len + 15) & ~15;
+  uint8_t *tseq = calloc((size_t)nt * stride + 16, 1);
+  int32_t *tlen = malloc(sizeof(int32_t) * (size_t)(nt + 1));
+  for (i = 0; i < n; ++i)
+    for (int t = 0; t < n_task[i]; ++t) {
+      memcpy(tseq + (size_t)(task_of_read[i] + t) * stride, seqs[i].seq, (size_t)seqs[i].l_seq);
+      tlen[task_of_read[i] + t] = seqs[i].l_seq;
+    }
+  bsq_reg *dregs = 0;
+  int64_t *reg_off = malloc(sizeof(int64_t) * (size_t)(nt + 1));
+  int rc = bsq_align_phase1(al, nt, tseq, stride, tlen, par, &dregs, reg_off);
+  free(tseq); free(tlen); free(par);
+  if (rc) { free(task_of_read); free(n_task); free(reg_off); return rc; }
+  work_t w;
+  memset(&w, 0, sizeof w);
+  w.opt = opt; w.ref = ref; w.seqs = seqs; w.n_processed = n_processed; w.rg_id = rg_id; w.n_threads = opt->n_threads; w.pe = pe;
+  w.regs = calloc((size_t)n + 1, sizeof(bq_regv_t));
+  w.dev_regs = dregs; w.reg_off = reg_off; w.task_of_read = task_of_read; w.n_task_of_read = n_task;
+  w.stage = 1;
+  run_threads(&w, n);
+  bsq_free(dregs);
+  free(task_of_read); free(n_task); free(reg_off);
+  if (pe) { if (pes0) w.pes = *pes0; else w.pes = bq_pestat(opt, ref, n, w.regs); }
+  w.stage = 2;
+  run_threads(&w, pe ? n >> 1 : n);
+  for (i = 0; i < n; ++i) {
+    for (size_t k = 0; k < w.regs[i].n; ++k) if (w.regs[i].a[k].n_cigar > 0) free(w.regs[i].a[k].cigar);
+    free(w.regs[i].a);
+  }
+  free(w.regs);
+  return 0;
+}

@@ -38,11 +38,21 @@ int bsq_index_upload(const bsq_index_desc *h, int device, bsq_index **out) {
     for (int i = 0; i < 5; ++i) f.L2[i] = h->L2[w][i];
   }
   ix->d.pac = h->pac; ix->d.l_pac = h->l_pac; ix->d.n_seqs = h->n_seqs;
-  ix->d.ann_offset = h->ann_offset; ix->d.ann_len = h->ann_len; ix->d.ann_is_alt = h->ann_is_alt;
+  // the caller may free its contig tables after the call (the CUDA library copies them to the device)
+  int64_t *off = (int64_t *)malloc(sizeof(int64_t) * h->n_seqs);
+  int32_t *len = (int32_t *)malloc(sizeof(int32_t) * h->n_seqs), *alt = (int32_t *)malloc(sizeof(int32_t) * h->n_seqs);
+  memcpy(off, h->ann_offset, sizeof(int64_t) * h->n_seqs);
+  memcpy(len, h->ann_len, sizeof(int32_t) * h->n_seqs);
+  memcpy(alt, h->ann_is_alt, sizeof(int32_t) * h->n_seqs);
+  ix->d.ann_offset = off; ix->d.ann_len = len; ix->d.ann_is_alt = alt;
   *out = ix;
   return 0;
 }
-void bsq_index_free(bsq_index *ix) { delete ix; }
+void bsq_index_free(bsq_index *ix) {
+  if (!ix) return;
+  free((void *)ix->d.ann_offset); free((void *)ix->d.ann_len); free((void *)ix->d.ann_is_alt);
+  delete ix;
+}
 
 int bsq_occ4(const bsq_index *ix, int which, int64_t n, const uint64_t *k, uint64_t *cnt) {
   for (int64_t i = 0; i < n; ++i) bsq_occ4(ix->d.fm[which], k[i], cnt + 4 * i);
@@ -169,3 +179,11 @@ int64_t hostemu_chain(const bsq_index *ixp, const bsq_opt *opt_, int parent, int
   return o;
 }
 }  // extern "C"
+
+// Entry points that only exist on the GPU (index construction, pinned memory, staged execution, pileup):
+// the host emulation says so instead of pretending.
+extern "C" {
+int bsq_index_build(const uint8_t *, int64_t, int32_t, const int64_t *, const int32_t *, const int32_t *, int, bsq_index **) { return BSQ_ENODEV; }
+int bsq_index_sizes(const bsq_index *, uint64_t *, uint64_t *, uint64_t *, uint64_t *, int64_t *) { return BSQ_ENODEV; }
+int bsq_index_download(const bsq_index *, int, uint32_t *, uint64_t *) { return BSQ_ENODEV; }
+}

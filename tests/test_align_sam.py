@@ -1,0 +1,107 @@
+"""End-to-end `biscuit align` parity: SAM byte-identical to the unmodified reference (oracle/_ref/biscuit_ref)
+modulo the @PG line, over the reference's own command-line boundary (B3).
+
+* not-gpu: host code (biscuit_b200/host/*.c) linked against the test-only host emulation of libbsq
+* gpu:     the product binary biscuit_b200/host/biscuit (links libbsq.so, CUDA)
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import refprobe
+import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "biscuit_b200", "host")
+EMU_BIN = os.path.join(ROOT, "tests", "hostemu", "biscuit_hostemu")
+GPU_BIN = os.path.join(HOST, "biscuit")
+
+
+def build_emu_bin():
+    import conftest
+    conftest.build_hostemu()
+    srcs = [os.path.join(HOST, f) for f in ("bq_core.c", "bq_phase2.c", "bq_io.c", "bq_main.c")]
+    deps = srcs + [os.path.join(HOST, "bq.h"), os.path.join(ROOT, "tests", "hostemu", "libbsq_hostemu.so")]
+    if not os.path.exists(EMU_BIN) or any(os.path.getmtime(d) > os.path.getmtime(EMU_BIN) for d in deps):
+        subprocess.check_call(["gcc", "-O2", "-g", "-std=gnu11", "-o", EMU_BIN] + srcs +
+                              ["-L" + os.path.dirname(EMU_BIN), "-lbsq_hostemu", "-Wl,-rpath,$ORIGIN", "-lz", "-lpthread", "-lm"])
+    return EMU_BIN
+
+
+@pytest.fixture(scope="module")
+def hard_set(tmp_path_factory):
+    if not refprobe.available():
+        pytest.skip("oracle/_ref not built")
+    d = str(tmp_path_factory.mktemp("sam"))
+    ref = synth.make_reference(300_037, 5, seed=9, n_runs=3)
+    fa = os.path.join(d, "hard.fa")
+    synth.write_fasta(fa, ref)
+    subprocess.check_call([refprobe.REF_BIN, "index", fa], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    p = synth.simulate_pairs(ref, 3000, seed=3, sub_rate=0.03, indel_rate=0.006, n_rate=0.002, qual="mixed")
+    rng = np.random.default_rng(1)
+    r1, r2 = p["r1"].copy(), p["r2"].copy()
+    k = rng.random(len(r2)) < 0.10  # unrelated mates: mate rescue, unpaired output
+    r2[k] = rng.integers(0, 4, size=(int(k.sum()), 150))
+    k = rng.random(len(r2)) < 0.05
+    r1[k] = rng.integers(0, 4, size=(int(k.sum()), 150))
+    r1[:20, :] = 0  # low-complexity reads
+    r2[20:40, 30:120] = 3
+    f1, f2 = os.path.join(d, "h1.fq"), os.path.join(d, "h2.fq")
+    synth.write_fastq(f1, r1, p["q1"], suffix="/1")
+    synth.write_fastq(f2, r2, p["q2"], suffix="/2")
+    return fa, f1, f2
+
+
+def _sam(binary, args):
+    out = subprocess.run([binary, "align"] + args, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout
+    return b"\n".join(ln for ln in out.split(b"\n") if not ln.startswith(b"@PG"))
+
+
+CASES = [[], ["-b", "1"], ["-a"], ["-5", "4", "-3", "7", "-z", "15"], ["-A", "2"], ["-I", "450,40"], ["-S"], ["-P"], ["-M", "-Y"],
+         ["-R", "@RG\\tID:x\\tSM:y"]]
+
+
+@pytest.mark.parametrize("extra", CASES, ids=[" ".join(c) or "default" for c in CASES])
+def test_sam_identical_hostemu(hard_set, extra):
+    fa, f1, f2 = hard_set
+    args = ["-@", "4"] + extra + [fa, f1, f2]
+    assert _sam(build_emu_bin(), args) == _sam(refprobe.REF_BIN, args)
+
+
+def test_sam_identical_single_end_hostemu(hard_set):
+    fa, f1, _ = hard_set
+    args = ["-@", "4", fa, f1]
+    assert _sam(build_emu_bin(), args) == _sam(refprobe.REF_BIN, args)
+
+
+def test_sam_clean_1m_hostemu(ds_1m, tmp_path):
+    """BASELINE.json configs[0] shape: clean 2x150 pairs vs a 1 Mb reference."""
+    p = ds_1m["pairs"]
+    f1, f2 = str(tmp_path / "r1.fq"), str(tmp_path / "r2.fq")
+    synth.write_fastq(f1, p["r1"], p["q1"])
+    synth.write_fastq(f2, p["r2"], p["q2"])
+    args = ["-@", "4", ds_1m["fa"], f1, f2]
+    assert _sam(build_emu_bin(), args) == _sam(refprobe.REF_BIN, args)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("extra", [[], ["-b", "1"], ["-5", "4", "-3", "7", "-z", "15"]], ids=["default", "-b 1", "clip"])
+def test_sam_identical_gpu(hard_set, extra):
+    if not os.path.exists(GPU_BIN):
+        pytest.fail("biscuit_b200/host/biscuit not built: run __graft_entry__.build()")
+    fa, f1, f2 = hard_set
+    args = ["-@", "4"] + extra + [fa, f1, f2]
+    assert _sam(GPU_BIN, args) == _sam(refprobe.REF_BIN, args)
+
+
+@pytest.mark.gpu
+def test_index_cli_gpu(hard_set, tmp_path):
+    """`biscuit index` (GPU suffix sorting) writes the same seven files as the reference, byte for byte."""
+    fa, _, _ = hard_set
+    mine = str(tmp_path / "mine.fa")
+    subprocess.check_call(["cp", fa, mine])
+    subprocess.check_call([GPU_BIN, "index", mine], stderr=subprocess.DEVNULL)
+    for ext in (".par.bwt", ".dau.bwt", ".par.sa", ".dau.sa", ".bis.pac", ".bis.ann", ".bis.amb"):
+        assert open(mine + ext, "rb").read() == open(fa + ext, "rb").read(), ext
