@@ -1,0 +1,70 @@
+/* bq_api.c -- the batch boundary B1 (mem_process_seqs, lib/aln/bwamem.c:432-476) as a flat C entry point of
+ * libbiscuit_host.so, for callers that already hold reads in memory (bench.py, tests): nt4 read rows in, SAM
+ * text out.  GPU phase 1 through libbsq.so, phase 2 on host threads. */
+#include <stdlib.h>
+#include <string.h>
+#include "bq.h"
+
+typedef struct {
+  bq_opt_t opt;
+  bq_ref_t ref;
+  bsq_aligner *al;
+} bq_session;
+
+bq_session *bq_session_create(bsq_index *dx, const uint8_t *pac, int64_t l_pac, int n_seqs, const char *const *names, const int64_t *offs,
+                              const int32_t *lens, int n_threads, int paired) {
+  bq_session *s = calloc(1, sizeof *s);
+  bq_opt_init(&s->opt);
+  s->opt.flag |= BQ_F_NO_MULTI;
+  if (paired) s->opt.flag |= BQ_F_PE;
+  s->opt.n_threads = n_threads > 0 ? n_threads : 1;
+  s->ref.l_pac = l_pac; s->ref.n_seqs = n_seqs; s->ref.seed = 11;
+  s->ref.anns = calloc((size_t)n_seqs, sizeof(bq_ann_t));
+  for (int i = 0; i < n_seqs; ++i) {
+    s->ref.anns[i].name = strdup(names[i]); s->ref.anns[i].anno = strdup("");
+    s->ref.anns[i].offset = offs[i]; s->ref.anns[i].len = lens[i];
+  }
+  s->ref.pac = (uint8_t *)pac; /* borrowed */
+  bsq_opt d;
+  bq_opt_to_dev(&s->opt, &d);
+  if (bsq_aligner_create(dx, &d, &s->al)) { free(s->ref.anns); free(s); return 0; }
+  return s;
+}
+
+void bq_session_destroy(bq_session *s) {
+  if (!s) return;
+  bsq_aligner_destroy(s->al);
+  for (int i = 0; i < s->ref.n_seqs; ++i) { free(s->ref.anns[i].name); free(s->ref.anns[i].anno); }
+  free(s->ref.anns);
+  free(s);
+}
+
+/* Align n reads (interleaved pairs when the session is paired).  Returns the total number of SAM bytes, or a
+ * negative BSQ_E* code; the SAM text is copied to sam_out when it is non-NULL and fits in cap. */
+int64_t bq_session_align(bq_session *s, int64_t n_processed, int n, const uint8_t *seqs, int stride, const int32_t *lens, const uint8_t *quals,
+                         char *sam_out, int64_t cap) {
+  bq_read_t *rd = calloc((size_t)n + 1, sizeof(bq_read_t));
+  char nm[64];
+  for (int i = 0; i < n; ++i) {
+    rd[i].l_seq = rd[i].l_seq0 = lens[i];
+    rd[i].seq = rd[i].seq0 = malloc((size_t)lens[i] + 1);
+    memcpy(rd[i].seq, seqs + (size_t)i * stride, (size_t)lens[i]);
+    rd[i].qual = malloc((size_t)lens[i] + 1);
+    if (quals) memcpy(rd[i].qual, quals + (size_t)i * stride, (size_t)lens[i]); else memset(rd[i].qual, 'I', (size_t)lens[i]);
+    rd[i].qual[lens[i]] = 0;
+    snprintf(nm, sizeof nm, "r%lld", (long long)((n_processed + i) >> 1));
+    rd[i].name = strdup(nm);
+    rd[i].id = i;
+  }
+  int rc = bq_process_seqs(&s->opt, s->al, &s->ref, n_processed, n, rd, 0, "");
+  int64_t tot = 0;
+  for (int i = 0; i < n; ++i) {
+    int64_t l = rd[i].sam ? (int64_t)strlen(rd[i].sam) : 0;
+    if (sam_out && tot + l < cap) memcpy(sam_out + tot, rd[i].sam, (size_t)l);
+    tot += l;
+    free(rd[i].sam); free(rd[i].seq0); free(rd[i].qual); free(rd[i].name);
+  }
+  if (sam_out && tot < cap) sam_out[tot] = 0;
+  free(rd);
+  return rc ? rc : tot;
+}
