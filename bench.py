@@ -443,12 +443,15 @@ def main():
             raise RuntimeError(f"bq_session_align: {r}")
         return r
 
-    full_step()
+    hostlib.bq_session_align_stream.restype = C.c_int64
+    sam_bytes = full_step()  # warm-up (single batch, unpipelined)
     barrier()
     t2 = time.perf_counter()
-    sam_bytes = 0
-    for _ in range(args.steps):
-        sam_bytes = full_step()
+    # K batches through the two-stage pipeline the CLI uses (GPU half of batch i+1 overlaps the host half of batch i)
+    r = hostlib.bq_session_align_stream(sess, C.c_int(args.steps), C.c_int(n_reads), reads_c.ctypes.data_as(C.c_void_p),
+                                        C.c_int(reads.shape[1]), rlens.ctypes.data_as(C.c_void_p), None)
+    if r < 0:
+        raise RuntimeError(f"bq_session_align_stream: {r}")
     barrier()
     dt_full = time.perf_counter() - t2
     hostlib.bq_session_destroy(sess)

@@ -167,6 +167,11 @@ void bq_read_clipping(bq_read_t *s, const uint8_t *adaptor, int l_adaptor, const
 int bq_process_seqs(const bq_opt_t *opt, bsq_aligner *al, const bq_ref_t *ref, int64_t n_processed, int n, bq_read_t *seqs,
                     const bq_pestat_t *pes0, const char *rg_id);
 
+typedef struct bq_batch bq_batch_t;
+/* GPU half (clipping, task list, bsq_align_phase1) and host half (merge, pestat, phase 2, SAM) of one batch */
+bq_batch_t *bq_batch_gpu(const bq_opt_t *opt, bsq_aligner *al, int64_t n_processed, int n, bq_read_t *seqs, int *rc);
+void bq_batch_finish(const bq_opt_t *opt, const bq_ref_t *ref, bq_batch_t *b, const bq_pestat_t *pes0, const char *rg_id);
+
 /* bq_io.c */
 int bq_index_load(const char *prefix, bq_index_t *idx);
 void bq_index_free(bq_index_t *idx);

@@ -1,6 +1,7 @@
 /* bq_api.c -- the batch boundary B1 (mem_process_seqs, lib/aln/bwamem.c:432-476) as a flat C entry point of
  * libbiscuit_host.so, for callers that already hold reads in memory (bench.py, tests): nt4 read rows in, SAM
  * text out.  GPU phase 1 through libbsq.so, phase 2 on host threads. */
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
 #include "bq.h"
@@ -66,5 +67,72 @@ int64_t bq_session_align(bq_session *s, int64_t n_processed, int n, const uint8_
   }
   if (sam_out && tot < cap) sam_out[tot] = 0;
   free(rd);
+  return rc ? rc : tot;
+}
+
+/* n_batches batches of the same n reads, pipelined: the GPU half of batch i+1 overlaps the host half of batch i.
+ * Returns the SAM bytes of the last batch (negative BSQ_E* on error). */
+typedef struct { bq_session *s; int n_batches, n, stride; const uint8_t *seqs, *quals; const int32_t *lens;
+                 pthread_mutex_t mu; pthread_cond_t cv; bq_batch_t *slot; bq_read_t *slot_reads; int full, rc; } stream_t;
+
+static bq_read_t *make_reads(int64_t n_processed, int n, const uint8_t *seqs, int stride, const int32_t *lens, const uint8_t *quals) {
+  bq_read_t *rd = calloc((size_t)n + 1, sizeof(bq_read_t));
+  char nm[64];
+  for (int i = 0; i < n; ++i) {
+    rd[i].l_seq = rd[i].l_seq0 = lens[i];
+    rd[i].seq = rd[i].seq0 = malloc((size_t)lens[i] + 1);
+    memcpy(rd[i].seq, seqs + (size_t)i * stride, (size_t)lens[i]);
+    rd[i].qual = malloc((size_t)lens[i] + 1);
+    if (quals) memcpy(rd[i].qual, quals + (size_t)i * stride, (size_t)lens[i]); else memset(rd[i].qual, 'I', (size_t)lens[i]);
+    rd[i].qual[lens[i]] = 0;
+    snprintf(nm, sizeof nm, "r%lld", (long long)((n_processed + i) >> 1));
+    rd[i].name = strdup(nm);
+    rd[i].id = i;
+  }
+  return rd;
+}
+
+static void *stream_producer(void *arg) {
+  stream_t *st = arg;
+  for (int b = 0; b < st->n_batches; ++b) {
+    int rc = 0;
+    bq_read_t *rd = make_reads((int64_t)b * st->n, st->n, st->seqs, st->stride, st->lens, st->quals);
+    bq_batch_t *bt = bq_batch_gpu(&st->s->opt, st->s->al, (int64_t)b * st->n, st->n, rd, &rc);
+    pthread_mutex_lock(&st->mu);
+    while (st->full) pthread_cond_wait(&st->cv, &st->mu);
+    st->slot = bt; st->slot_reads = rd; st->rc = rc; st->full = 1;
+    pthread_cond_broadcast(&st->cv);
+    pthread_mutex_unlock(&st->mu);
+    if (!bt) return 0;
+  }
+  return 0;
+}
+
+int64_t bq_session_align_stream(bq_session *s, int n_batches, int n, const uint8_t *seqs, int stride, const int32_t *lens, const uint8_t *quals) {
+  stream_t st;
+  memset(&st, 0, sizeof st);
+  st.s = s; st.n_batches = n_batches; st.n = n; st.stride = stride; st.seqs = seqs; st.quals = quals; st.lens = lens;
+  pthread_mutex_init(&st.mu, 0); pthread_cond_init(&st.cv, 0);
+  pthread_t prod;
+  pthread_create(&prod, 0, stream_producer, &st);
+  int64_t tot = 0;
+  int rc = 0;
+  for (int b = 0; b < n_batches; ++b) {
+    pthread_mutex_lock(&st.mu);
+    while (!st.full) pthread_cond_wait(&st.cv, &st.mu);
+    bq_batch_t *bt = st.slot; bq_read_t *rd = st.slot_reads; rc = st.rc;
+    st.full = 0;
+    pthread_cond_broadcast(&st.cv);
+    pthread_mutex_unlock(&st.mu);
+    if (!bt) { for (int i = 0; i < n; ++i) { free(rd[i].seq0); free(rd[i].qual); free(rd[i].name); } free(rd); break; }
+    bq_batch_finish(&s->opt, &s->ref, bt, 0, "");
+    tot = 0;
+    for (int i = 0; i < n; ++i) {
+      tot += rd[i].sam ? (int64_t)strlen(rd[i].sam) : 0;
+      free(rd[i].sam); free(rd[i].seq0); free(rd[i].qual); free(rd[i].name);
+    }
+    free(rd);
+  }
+  pthread_join(prod, 0);
   return rc ? rc : tot;
 }

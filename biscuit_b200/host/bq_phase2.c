@@ -828,8 +828,18 @@ static void run_threads(work_t *w, int n_items) {
   free(th); free(ta);
 }
 
-int bq_process_seqs(const bq_opt_t *opt, bsq_aligner *al, const bq_ref_t *ref, int64_t n_processed, int n, bq_read_t *seqs,
-                    const bq_pestat_t *pes0, const char *rg_id) {
+/* The batch in two halves so that callers can overlap the GPU half of batch i+1 with the host half of batch i
+ * (the reference overlaps I/O and compute the same way with kt_pipeline, align.c:577). */
+struct bq_batch {
+  int n;
+  int64_t n_processed;
+  bq_read_t *seqs;
+  bsq_reg *dregs;
+  int64_t *reg_off, *task_of_read;
+  uint8_t *n_task;
+};
+
+bq_batch_t *bq_batch_gpu(const bq_opt_t *opt, bsq_aligner *al, int64_t n_processed, int n, bq_read_t *seqs, int *rc_out) {
   const int pe = (opt->flag & BQ_F_PE) != 0;
   int i, max_len = 1;
   /* clipping (bwamem.c:322,343-344) */
@@ -839,48 +849,65 @@ int bq_process_seqs(const bq_opt_t *opt, bsq_aligner *al, const bq_ref_t *ref, i
     if (seqs[i].l_seq > max_len) max_len = seqs[i].l_seq;
   }
   /* (read, conversion) tasks in the order bis_worker1 runs them (bwamem.c:325-372) */
-  int64_t *task_of_read = malloc(sizeof(int64_t) * (size_t)(n + 1));
-  uint8_t *n_task = malloc((size_t)n + 1), *par = malloc((size_t)n * 2 + 2);
+  bq_batch_t *b = calloc(1, sizeof *b);
+  b->n = n; b->n_processed = n_processed; b->seqs = seqs;
+  b->task_of_read = malloc(sizeof(int64_t) * (size_t)(n + 1));
+  b->n_task = malloc((size_t)n + 1);
+  uint8_t *par = malloc((size_t)n * 2 + 2);
   int64_t nt = 0;
   for (i = 0; i < n; ++i) {
-    task_of_read[i] = nt;
+    b->task_of_read[i] = nt;
     int k0 = (int)nt;
     if (!pe) {
       if (!(opt->parent & 1) || opt->parent >> 1) par[nt++] = 0;
       if (!(opt->parent & 1) || !(opt->parent >> 1)) par[nt++] = 1;
     } else if (!(i & 1)) { par[nt++] = 1; if (!opt->parent) par[nt++] = 0; }
     else { par[nt++] = 0; if (!opt->parent) par[nt++] = 1; }
-    n_task[i] = (uint8_t)(nt - k0);
+    b->n_task[i] = (uint8_t)(nt - k0);
   }
   const int stride = (max_len + 15) & ~15;
   uint8_t *tseq = calloc((size_t)nt * stride + 16, 1);
   int32_t *tlen = malloc(sizeof(int32_t) * (size_t)(nt + 1));
   for (i = 0; i < n; ++i)
-    for (int t = 0; t < n_task[i]; ++t) {
-      memcpy(tseq + (size_t)(task_of_read[i] + t) * stride, seqs[i].seq, (size_t)seqs[i].l_seq);
-      tlen[task_of_read[i] + t] = seqs[i].l_seq;
+    for (int t = 0; t < b->n_task[i]; ++t) {
+      memcpy(tseq + (size_t)(b->task_of_read[i] + t) * stride, seqs[i].seq, (size_t)seqs[i].l_seq);
+      tlen[b->task_of_read[i] + t] = seqs[i].l_seq;
     }
-  bsq_reg *dregs = 0;
-  int64_t *reg_off = malloc(sizeof(int64_t) * (size_t)(nt + 1));
-  int rc = bsq_align_phase1(al, nt, tseq, stride, tlen, par, &dregs, reg_off);
+  b->reg_off = malloc(sizeof(int64_t) * (size_t)(nt + 1));
+  int rc = bsq_align_phase1(al, nt, tseq, stride, tlen, par, &b->dregs, b->reg_off);
   free(tseq); free(tlen); free(par);
-  if (rc) { free(task_of_read); free(n_task); free(reg_off); return rc; }
+  if (rc_out) *rc_out = rc;
+  if (rc) { free(b->task_of_read); free(b->n_task); free(b->reg_off); free(b); return 0; }
+  return b;
+}
+
+void bq_batch_finish(const bq_opt_t *opt, const bq_ref_t *ref, bq_batch_t *b, const bq_pestat_t *pes0, const char *rg_id) {
+  const int pe = (opt->flag & BQ_F_PE) != 0, n = b->n;
   work_t w;
   memset(&w, 0, sizeof w);
-  w.opt = opt; w.ref = ref; w.seqs = seqs; w.n_processed = n_processed; w.rg_id = rg_id; w.n_threads = opt->n_threads; w.pe = pe;
+  w.opt = opt; w.ref = ref; w.seqs = b->seqs; w.n_processed = b->n_processed; w.rg_id = rg_id; w.n_threads = opt->n_threads; w.pe = pe;
   w.regs = calloc((size_t)n + 1, sizeof(bq_regv_t));
-  w.dev_regs = dregs; w.reg_off = reg_off; w.task_of_read = task_of_read; w.n_task_of_read = n_task;
+  w.dev_regs = b->dregs; w.reg_off = b->reg_off; w.task_of_read = b->task_of_read; w.n_task_of_read = b->n_task;
   w.stage = 1;
   run_threads(&w, n);
-  bsq_free(dregs);
-  free(task_of_read); free(n_task); free(reg_off);
+  bsq_free(b->dregs);
+  free(b->task_of_read); free(b->n_task); free(b->reg_off);
   if (pe) { if (pes0) w.pes = *pes0; else w.pes = bq_pestat(opt, ref, n, w.regs); }
   w.stage = 2;
   run_threads(&w, pe ? n >> 1 : n);
-  for (i = 0; i < n; ++i) {
+  for (int i = 0; i < n; ++i) {
     for (size_t k = 0; k < w.regs[i].n; ++k) if (w.regs[i].a[k].n_cigar > 0) free(w.regs[i].a[k].cigar);
     free(w.regs[i].a);
   }
   free(w.regs);
+  free(b);
+}
+
+int bq_process_seqs(const bq_opt_t *opt, bsq_aligner *al, const bq_ref_t *ref, int64_t n_processed, int n, bq_read_t *seqs,
+                    const bq_pestat_t *pes0, const char *rg_id) {
+  int rc = 0;
+  bq_batch_t *b = bq_batch_gpu(opt, al, n_processed, n, seqs, &rc);
+  if (!b) return rc ? rc : BSQ_ENOMEM;
+  bq_batch_finish(opt, ref, b, pes0, rg_id);
   return 0;
 }
