@@ -462,7 +462,8 @@ def main():
     counters = al.counters()
     kern_us /= args.steps
     stage_names = ["k_seed", "k_expand+k_sa", "k_chain", "k_region", "scan+compact", "all"]
-    log("kernel us/step:", dict(zip(stage_names, [int(x) for x in kern_us])), "regions/step", n_regs.value, "sa lookups", int(counters[2]))
+    log("kernel us/step:", dict(zip(stage_names, [int(x) for x in kern_us])), "regions/step", n_regs.value, "sa lookups", int(counters[2]),
+        "chain fallback tasks", int(counters[14]), "k_chain_warp us", int(counters[15]))
 
     if rank == 0:
         # ---- algorithmic work of one step, from the instrumented build (untimed) ----

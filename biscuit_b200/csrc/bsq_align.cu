@@ -21,6 +21,7 @@ static __device__ unsigned long long bsq_ctr[8];
 #endif
 #include "bsq_task.h"
 #include "bsq_ksw_warp.cuh"
+#include "bsq_chain_warp.h"
 #include "bsq_opt_default.h"
 
 static_assert(sizeof(bsq_intv) == sizeof(bsq_intv_t), "abi");
@@ -85,7 +86,7 @@ struct bsq_aligner {
   cudaEvent_t ev[8];
   DevBuf seqs, lens, parent, intv, n_intv, n_sa, sa_off, ranks, pos, status;
   DevBuf snodes, wchains, bnodes, order, ochains, oseeds, n_chains, frac_rep, srt, regs_tmp, n_regs, reg_off, regs;
-  DevBuf cub_tmp, scalars;
+  DevBuf cub_tmp, scalars, fb_flag;
   int64_t counters[16];
   int64_t n_staged = 0, n_regs_total = -1;
   int32_t stride = 0;
@@ -182,9 +183,11 @@ __global__ void __launch_bounds__(128) k_chain(bsq_devopt_t opt, bsq_devidx_t ix
                                                const uint8_t *parent, const bsq_pk_t *intv, const int32_t *n_intv,
                                                const int64_t *sa_off, const uint64_t *pos, bsq_snode_t *snodes,
                                                bsq_wchain_t *wchains, bsq_bnode_t *bnodes, int32_t *order, bsq_chain_t *ochains,
-                                               bsq_seed_t *oseeds, int32_t *n_chains, float *frac_rep, int32_t *status) {
+                                               bsq_seed_t *oseeds, int32_t *n_chains, float *frac_rep, int32_t *status,
+                                               const uint8_t *only_flagged) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_tasks) return;
+  if (only_flagged && !only_flagged[t]) return;  // already done by k_chain_warp
   const int64_t wo = ws_off(sa_off, t);
   bsq_chain_ws_t ws;
   ws.cap = (int32_t)(sa_off[t + 1] - sa_off[t]) + BSQ_TAIL_SLACK;
@@ -196,9 +199,57 @@ __global__ void __launch_bounds__(128) k_chain(bsq_devopt_t opt, bsq_devidx_t ix
   frac_rep[t] = r.frac_rep;
 }
 
+// warp policy of bsq_chain_warp
+struct bsq_cw_warp {
+  __device__ static int lane() { return threadIdx.x & 31; }
+  __device__ static int nl() { return 32; }
+  __device__ static void sync() { __syncwarp(); }
+  __device__ static int first_true(bool p) { unsigned b = __ballot_sync(0xffffffffu, p); return b ? __ffs(b) - 1 : -1; }
+  __device__ static bool any(bool p) { return __any_sync(0xffffffffu, p); }
+  // bitonic sort of n <= BSQ_CW_CAP keys in shared memory (keys are unique, so the result is the total order)
+  __device__ static void sort_keys(uint64_t *k, int n) {
+    const int lane = threadIdx.x & 31;
+    int P = 32;
+    while (P < n) P <<= 1;
+    for (int i = n + lane; i < P; i += 32) k[i] = ~0ull;
+    __syncwarp();
+    for (int kk = 2; kk <= P; kk <<= 1)
+      for (int j = kk >> 1; j > 0; j >>= 1) {
+        for (int i = lane; i < P; i += 32) {
+          const int x = i ^ j;
+          if (x > i) {
+            const uint64_t a = k[i], b = k[x];
+            if ((a > b) == ((i & kk) == 0)) { k[i] = b; k[x] = a; }
+          }
+        }
+        __syncwarp();
+      }
+  }
+};
+
+// Chaining + chain filter, one WARP per task, state in shared memory (bsq_chain_warp.h).  Tasks the decomposition
+// cannot take exactly are flagged for k_chain (thread-per-task, exact B-tree replay).
+__global__ void __launch_bounds__(128) k_chain_warp(bsq_devopt_t opt, bsq_devidx_t ix, int64_t n_tasks, const int32_t *lens, const uint8_t *parent,
+                                                    const bsq_pk_t *intv, const int32_t *n_intv, const int32_t *n_sa, const int64_t *sa_off,
+                                                    const uint64_t *pos, bsq_chain_t *ochains, bsq_seed_t *oseeds, int32_t *n_chains,
+                                                    float *frac_rep, uint8_t *fb_flag, unsigned long long *n_fallback) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  bsq_cw_smem_t *sm = reinterpret_cast<bsq_cw_smem_t *>(smem_raw) + (threadIdx.x >> 5);
+  const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (t >= n_tasks) return;
+  const int64_t wo = ws_off(sa_off, t);
+  bsq_chain_result_t r;
+  const int rc = bsq_chain_warp<bsq_cw_warp>(opt, ix, parent[t], lens[t], intv + t * BSQ_MAX_INTV, n_intv[t], pos + sa_off[t], n_sa[t], *sm,
+                                             ochains + wo, oseeds + wo, r);
+  if ((threadIdx.x & 31) == 0) {
+    if (rc == BSQ_CW_OK) { n_chains[t] = r.n_chains; frac_rep[t] = r.frac_rep; fb_flag[t] = 0; }
+    else { fb_flag[t] = 1; atomicAdd(n_fallback, 1ull); }
+  }
+}
+
 // Chains -> regions, one WARP per task: the control flow of mem_chain2region runs uniformly in all
 // lanes, every banded extension is spread over the lanes (bsq_ksw_warp.cuh), lane 0 stores.
-__global__ void __launch_bounds__(128, 4) k_region(bsq_devopt_t opt, bsq_devidx_t ix, int64_t n_tasks, const uint8_t *seqs, int stride,
+__global__ void __launch_bounds__(128, 8) k_region(bsq_devopt_t opt, bsq_devidx_t ix, int64_t n_tasks, const uint8_t *seqs, int stride,
                                                 const int32_t *lens, const uint8_t *parent, const int64_t *sa_off,
                                                 const bsq_chain_t *ochains, const bsq_seed_t *oseeds, const int32_t *n_chains,
                                                 const float *frac_rep, uint64_t *srt, bsq_reg_t *regs_tmp, int32_t *n_regs) {
@@ -418,7 +469,7 @@ void bsq_aligner_destroy(bsq_aligner *al) {
   cudaSetDevice(al->idx->device);
   DevBuf *bufs[] = {&al->seqs, &al->lens, &al->parent, &al->intv, &al->n_intv, &al->n_sa, &al->sa_off, &al->ranks, &al->pos,
                     &al->status, &al->snodes, &al->wchains, &al->bnodes, &al->order, &al->ochains, &al->oseeds, &al->n_chains,
-                    &al->frac_rep, &al->srt, &al->regs_tmp, &al->n_regs, &al->reg_off, &al->regs, &al->cub_tmp, &al->scalars};
+                    &al->frac_rep, &al->srt, &al->regs_tmp, &al->n_regs, &al->reg_off, &al->regs, &al->cub_tmp, &al->scalars, &al->fb_flag};
   for (DevBuf *b : bufs) b->release();
   for (int i = 0; i < 8; ++i) cudaEventDestroy(al->ev[i]);
   cudaStreamDestroy(al->stream);
@@ -498,11 +549,25 @@ static int phase1_device(bsq_aligner *al, int64_t n, int32_t stride, int64_t *to
   }
   CK(cudaEventRecord(al->ev[3], s));
   SNAP(13);
+  RES(fb_flag, n);
+  {
+    static bool attr_set = false;
+    const size_t smem = 4 * sizeof(bsq_cw_smem_t);
+    if (!attr_set) { CK(cudaFuncSetAttribute(k_chain_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+    k_chain_warp<<<nblk(n * 32, 128), 128, smem, s>>>(opt, ix, n, al->lens.as<int32_t>(), al->parent.as<uint8_t>(), al->intv.as<bsq_pk_t>(),
+                                                      al->n_intv.as<int32_t>(), al->n_sa.as<int32_t>(), al->sa_off.as<int64_t>(),
+                                                      al->pos.as<uint64_t>(), al->ochains.as<bsq_chain_t>(), al->oseeds.as<bsq_seed_t>(),
+                                                      al->n_chains.as<int32_t>(), al->frac_rep.as<float>(), al->fb_flag.as<uint8_t>(),
+                                                      al->scalars.as<unsigned long long>() + 1);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(al->ev[7], s));
+  }
   k_chain<<<nblk(n, 128), 128, 0, s>>>(opt, ix, n, al->lens.as<int32_t>(), al->parent.as<uint8_t>(), al->intv.as<bsq_pk_t>(),
                                         al->n_intv.as<int32_t>(), al->sa_off.as<int64_t>(), al->pos.as<uint64_t>(),
                                         al->snodes.as<bsq_snode_t>(), al->wchains.as<bsq_wchain_t>(), al->bnodes.as<bsq_bnode_t>(),
                                         al->order.as<int32_t>(), al->ochains.as<bsq_chain_t>(), al->oseeds.as<bsq_seed_t>(),
-                                        al->n_chains.as<int32_t>(), al->frac_rep.as<float>(), al->status.as<int32_t>());
+                                        al->n_chains.as<int32_t>(), al->frac_rep.as<float>(), al->status.as<int32_t>(),
+                                        al->fb_flag.as<uint8_t>());
   CK(cudaGetLastError());
   CK(cudaEventRecord(al->ev[4], s));
   k_region<<<nblk(n * 32, 128), 128, 0, s>>>(opt, ix, n, al->seqs.as<uint8_t>(), stride, al->lens.as<int32_t>(), al->parent.as<uint8_t>(),
@@ -518,8 +583,12 @@ static int phase1_device(bsq_aligner *al, int64_t n, int32_t stride, int64_t *to
   CK(cudaGetLastError());
   CK(cudaEventRecord(al->ev[6], s));
   int32_t st = 0;
+  unsigned long long n_fb = 0;
   CK(cudaMemcpyAsync(&st, al->status.p, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&n_fb, al->scalars.as<unsigned long long>() + 1, 8, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  al->counters[14] = (int64_t)n_fb;  // tasks chained by the exact fallback kernel
+  { float w_ms = 0; cudaEventElapsedTime(&w_ms, al->ev[3], al->ev[7]); al->counters[15] = (int64_t)(w_ms * 1000); }
 #undef RES
   if (st) { snprintf(g_err, sizeof g_err, "device status 0x%x (1: interval list, 2: chain workspace)", st); return BSQ_EOVERFLOW; }
   float ms[6];

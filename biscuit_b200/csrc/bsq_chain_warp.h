@@ -1,0 +1,278 @@
+// Warp-per-task chaining + chain filter with all per-task state in shared memory (k_chain v2).
+//
+// Same results as bsq_chain_task (= mem_chain + mem_chain_flt, lib/aln/memchain.c:268-488); different
+// organisation.  v1 ran one task per thread with its B-tree, seed lists and chain records in global memory:
+// every step was a dependent DRAM access, serialised across the diverged lanes of a warp (40 % of the
+// GRCh38-sized step, profiles/README.md).  Here one warp owns a task and keeps everything in shared memory:
+//
+//  1. all lanes load the occurrences of the task (coalesced) and resolve contig ids;
+//  2. the seeds are sorted by reference position (bitonic, in shared memory) and cut into clusters wherever two
+//     neighbours are at least G = BSQ_MAX_READ_LEN + w + 1 apart.  A seed can only ever join the chain that
+//     precedes it in reference order (merge_seed_to_chain needs |qdist - rdist| <= w and containment needs
+//     overlap), so clusters cannot interact and their chains simply concatenate in position order -- the
+//     order the reference reads out of its B-tree;
+//  3. inside a cluster the reference's sequential rule is replayed in arrival order against a small sorted
+//     list of the cluster's chains (lane 0; the list is a handful of entries);
+//  4. weights, the introsort by weight (exact comparison sequence, lane 0) and the greedy overlap filter, whose
+//     inner loop over the kept chains is spread over the lanes (first "drop" position by ballot).
+//
+// Exactness guard: the decomposition is only equivalent when (F1) no interval has more than max_occ occurrences
+// (otherwise the reference's `count` cap couples clusters, memchain.c:325-326), (F2) the task fits the
+// shared-memory capacity and (F3) no two chains get the same position (the B-tree's equal-key behaviour is
+// shape dependent).  Any violation returns BSQ_CW_FALLBACK and the task is redone by bsq_chain_task.
+#pragma once
+#include "bsq_chain.h"
+
+#define BSQ_CW_CAP 256
+#define BSQ_CW_OK 0
+#define BSQ_CW_FALLBACK 1
+#define BSQ_CW_NONE 0xFFFFu
+
+struct bsq_cw_smem_t {
+  int64_t rbeg[BSQ_CW_CAP];       // seed reference position, arrival order
+  uint64_t key[BSQ_CW_CAP];       // sort keys: rbeg << 8 | arrival index
+  int64_t c_last_rbeg[BSQ_CW_CAP];  // chain state, indexed by the arrival index of the chain's first seed
+  int32_t c_w[BSQ_CW_CAP];
+  uint16_t qbeg[BSQ_CW_CAP], slen[BSQ_CW_CAP];
+  int16_t rid[BSQ_CW_CAP];        // < 0: seed dropped (bridges contigs / strands, memchain.c:339-346)
+  uint16_t next[BSQ_CW_CAP];      // seed lists
+  uint16_t c_last_q[BSQ_CW_CAP], c_last_len[BSQ_CW_CAP], c_tail[BSQ_CW_CAP], c_n[BSQ_CW_CAP];
+  uint16_t c_xhead[BSQ_CW_CAP], c_xtail[BSQ_CW_CAP], c_xn[BSQ_CW_CAP];
+  int16_t c_first[BSQ_CW_CAP];
+  uint16_t clist[BSQ_CW_CAP];     // chains in position order
+  uint16_t ord[BSQ_CW_CAP];       // chains in filter order
+  uint16_t keep[BSQ_CW_CAP];
+  uint8_t c_kept[BSQ_CW_CAP];
+  uint8_t c_alt[BSQ_CW_CAP];       // is_alt of the seed's contig
+  uint16_t iv_off[BSQ_MAX_INTV + 1];  // first seed of every interval (prefix sums of the occurrence counts)
+  int32_t pub[4];                 // lane 0 -> all lanes: number of chains / fallback request
+};
+
+// scalar policy (host emulation): one "lane"
+struct bsq_cw_scalar {
+  BSQ_HD static int lane() { return 0; }
+  BSQ_HD static int nl() { return 1; }
+  BSQ_HD static void sync() {}
+  BSQ_HD static int first_true(bool p) { return p ? 0 : -1; }
+  BSQ_HD static bool any(bool p) { return p; }
+  BSQ_HD static void sort_keys(uint64_t *k, int n) {
+    for (int i = 1; i < n; ++i) { uint64_t v = k[i]; int j = i; while (j > 0 && k[j - 1] > v) { k[j] = k[j - 1]; --j; } k[j] = v; }
+  }
+};
+
+// filter order: sort (weight << 16 | chain) by weight only, descending -- the chain id rides along but takes no part
+// in the comparison, so the comparison/swap sequence is the reference's (flt_lt, memchain.c:402)
+struct bsq_cw_by_weight {
+  BSQ_HD bool operator()(uint64_t a, uint64_t b) const { return (a >> 16) > (b >> 16); }
+};
+
+// merge_seed_to_chain (memchain.c:227-256) against chain L (created by seed L)
+BSQ_HD int bsq_cw_merge(const bsq_devopt_t &opt, int64_t l_pac, bsq_cw_smem_t &s, int L, int a) {
+  if (s.rid[a] != s.rid[L]) return 0;
+  const int64_t f_rbeg = s.rbeg[L], l_rbeg = s.c_last_rbeg[L], rb = s.rbeg[a];
+  const int f_q = s.qbeg[L], l_q = s.c_last_q[L], l_len = s.c_last_len[L], qb = s.qbeg[a], ln = s.slen[a];
+  if (qb >= f_q && qb + ln <= l_q + l_len && rb >= f_rbeg && rb + ln <= l_rbeg + l_len) {
+    if (s.c_xn[L] == 0) s.c_xhead[L] = (uint16_t)a; else s.next[s.c_xtail[L]] = (uint16_t)a;
+    s.c_xtail[L] = (uint16_t)a; ++s.c_xn[L];
+    return 1;
+  }
+  if ((l_rbeg < l_pac || f_rbeg < l_pac) && rb >= l_pac) return 0;
+  const int64_t qdist = qb - l_q, rdist = rb - l_rbeg;
+  if (rdist >= 0 && qdist - rdist <= opt.w && rdist - qdist <= opt.w && qdist - l_len < opt.max_chain_gap && rdist - l_len < opt.max_chain_gap) {
+    s.next[s.c_tail[L]] = (uint16_t)a;
+    s.c_tail[L] = (uint16_t)a; ++s.c_n[L];
+    s.c_last_rbeg[L] = rb; s.c_last_q[L] = (uint16_t)qb; s.c_last_len[L] = (uint16_t)ln;
+    return 1;
+  }
+  return 0;
+}
+
+BSQ_HD int bsq_cw_weight(const bsq_cw_smem_t &s, int c) {  // mem_chain_weight (memchain.c:158-180)
+  int64_t end = 0;
+  int w = 0, tmp, j;
+  for (j = c; j != (int)BSQ_CW_NONE; j = s.next[j]) {
+    const int q = s.qbeg[j], l = s.slen[j];
+    if (q >= end) w += l; else if (q + l > end) w += (int)(q + l - end);
+    end = end > q + l ? end : q + l;
+  }
+  tmp = w; w = 0; end = 0;
+  for (j = c; j != (int)BSQ_CW_NONE; j = s.next[j]) {
+    const int64_t r = s.rbeg[j]; const int l = s.slen[j];
+    if (r >= end) w += l; else if (r + l > end) w += (int)(r + l - end);
+    end = end > r + l ? end : r + l;
+  }
+  w = w < tmp ? w : tmp;
+  return w < 1 << 30 ? w : (1 << 30) - 1;
+}
+
+// Returns BSQ_CW_OK (res filled, outputs written) or BSQ_CW_FALLBACK (nothing written that matters).
+template <typename W>
+BSQ_HD int bsq_chain_warp(const bsq_devopt_t &opt, const bsq_devidx_t &ix, int parent, int l_seq, const bsq_pk_t *intv, int n_intv,
+                          const uint64_t *sa_pos, int n_sa, bsq_cw_smem_t &s, bsq_chain_t *out_chains, bsq_seed_t *out_seeds,
+                          bsq_chain_result_t &res) {
+  const int lane = W::lane(), NL = W::nl();
+  res.n_chains = 0; res.n_seeds = 0; res.status = 0; res.frac_rep = 0.f;
+  if (l_seq < opt.min_seed_len) return BSQ_CW_OK;
+  if (n_sa > BSQ_CW_CAP || ix.n_seqs > 32767) return BSQ_CW_FALLBACK;  // (F2)
+  const uint64_t max_occ = (uint64_t)(uint32_t)opt.max_occ;
+  // ---- 1. seeds of the task (arrival order = interval order, then occurrence order) ----
+  // 1a. occurrence counts of all intervals, lanes in parallel; prefix sums by lane 0
+  {
+    bool big = false;
+    for (int i = lane; i < n_intv; i += NL) {
+      const uint64_t x2 = bsq_pk_x2(intv[i]);
+      if (x2 > max_occ) big = true;
+      s.iv_off[i + 1] = (uint16_t)(x2 > max_occ ? 0 : x2);
+    }
+    if (W::any(big)) return BSQ_CW_FALLBACK;  // (F1)
+    W::sync();
+    if (lane == 0) {
+      int o = 0;
+      s.iv_off[0] = 0;
+      for (int i = 0; i < n_intv; ++i) { o += s.iv_off[i + 1]; s.iv_off[i + 1] = (uint16_t)o; }
+    }
+    W::sync();
+  }
+  // 1b. one seed per lane step: interval by binary search in the prefix sums, position from the SA-lookup kernel
+  for (int a = lane; a < n_sa; a += NL) {
+    int lo = 0, hi = n_intv;  // last interval with iv_off[i] <= a
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s.iv_off[mid] <= a) lo = mid; else hi = mid; }
+    const bsq_pk_t pk = intv[lo];
+    const int qb = bsq_pk_beg(pk), ln = bsq_pk_end(pk) - qb;
+    const int64_t rb = (int64_t)sa_pos[a];
+    int rid = bsq_intv2rid(ix, rb, rb + ln);
+    if (rid >= 0 && (opt.bsstrand & 1) && bsq_getbss(ix, parent, rb) != (opt.bsstrand >> 1)) rid = -1;
+    s.rbeg[a] = rb; s.qbeg[a] = (uint16_t)qb; s.slen[a] = (uint16_t)ln; s.rid[a] = (int16_t)(rid < 0 ? -1 : rid);
+    s.c_alt[a] = (uint8_t)(rid >= 0 && ix.ann_is_alt[rid] != 0);
+    s.next[a] = (uint16_t)BSQ_CW_NONE;
+    s.key[a] = rid < 0 ? ~0ull : ((uint64_t)rb << 8 | (uint64_t)a);
+  }
+  W::sync();
+  // ---- 2. order by reference position ----
+  W::sort_keys(s.key, n_sa);
+  W::sync();
+  // ---- 3. clusters, replay of the merge rule (lane 0) ----
+  const int64_t G = (int64_t)BSQ_MAX_READ_LEN + opt.w + 1;
+  int n_ch = 0, dup = 0;
+  if (lane == 0) {
+    int n_valid = n_sa;
+    while (n_valid > 0 && s.key[n_valid - 1] == ~0ull) --n_valid;
+    int i = 0;
+    while (i < n_valid && !dup) {
+      int j = i + 1;
+      while (j < n_valid && (int64_t)(s.key[j] >> 8) - (int64_t)(s.key[j - 1] >> 8) < G) ++j;
+      const int cl0 = n_ch;
+      // members in arrival order: insertion sort of the arrival indices of key[i..j)
+      for (int u = i; u < j; ++u) s.ord[u] = (uint16_t)(s.key[u] & 255);
+      for (int u = i + 1; u < j; ++u) { uint16_t v = s.ord[u]; int t = u; while (t > i && s.ord[t - 1] > v) { s.ord[t] = s.ord[t - 1]; --t; } s.ord[t] = v; }
+      for (int u = i; u < j; ++u) {
+        const int a = s.ord[u];
+        int p = cl0 - 1;  // predecessor inside the cluster (cl0 - 1: none)
+        for (int c = cl0; c < n_ch; ++c) { if (s.rbeg[s.clist[c]] <= s.rbeg[a]) p = c; else break; }
+        if (p >= cl0 && bsq_cw_merge(opt, ix.l_pac, s, s.clist[p], a)) continue;
+        if (p >= cl0 && s.rbeg[s.clist[p]] == s.rbeg[a]) { dup = 1; break; }  // (F3)
+        for (int c = n_ch; c > p + 1; --c) s.clist[c] = s.clist[c - 1];
+        s.clist[p + 1] = (uint16_t)a;
+        ++n_ch;
+        s.c_last_rbeg[a] = s.rbeg[a]; s.c_last_q[a] = s.qbeg[a]; s.c_last_len[a] = s.slen[a];
+        s.c_tail[a] = (uint16_t)a; s.c_n[a] = 1; s.c_xhead[a] = s.c_xtail[a] = (uint16_t)BSQ_CW_NONE; s.c_xn[a] = 0;
+      }
+      i = j;
+    }
+    // ---- 4a. weights + order for the filter ----
+    if (!dup) {
+      int k = 0;
+      for (int c = 0; c < n_ch; ++c) {
+        const int a = s.clist[c];
+        s.c_first[a] = -1; s.c_kept[a] = 0;
+        s.c_w[a] = bsq_cw_weight(s, a);
+        if (s.c_w[a] >= opt.min_chain_weight) s.key[k++] = (uint64_t)(uint32_t)s.c_w[a] << 16 | (uint64_t)a;
+      }
+      n_ch = k;
+      bsq_introsort(s.key, (int64_t)n_ch, bsq_cw_by_weight());
+      for (int c = 0; c < n_ch; ++c) s.ord[c] = (uint16_t)(s.key[c] & 0xffff);
+      if (n_ch > 0) { s.c_kept[s.ord[0]] = 3; s.keep[0] = 0; }
+    }
+    s.pub[0] = dup ? -1 : n_ch;
+  }
+  W::sync();
+  {
+    const int v = s.pub[0];
+    if (v < 0) return BSQ_CW_FALLBACK;
+    n_ch = v;
+  }
+  if (n_ch == 0) return BSQ_CW_OK;
+  // ---- 4b. greedy overlap filter (memchain.c:427-457); inner loop over the kept chains spread over the lanes ----
+  int n_keep = 1;
+  for (int i = 1; i < n_ch; ++i) {
+    const int ci = s.ord[i];
+    const int ci_beg = s.qbeg[ci], ci_end = s.c_last_q[ci] + s.c_last_len[ci], ci_w = s.c_w[ci];
+    const bool ci_alt = s.c_alt[ci] != 0;
+    bool large_overlap = false;
+    int K = n_keep;
+    for (int base = 0; base < n_keep && K == n_keep; base += NL) {
+      const int k = base + lane;
+      bool large = false, drop = false;
+      int ck = 0;
+      if (k < n_keep) {
+        ck = s.ord[s.keep[k]];
+        const int ck_beg = s.qbeg[ck], ck_end = s.c_last_q[ck] + s.c_last_len[ck];
+        const int b_max = ck_beg > ci_beg ? ck_beg : ci_beg, e_min = ck_end < ci_end ? ck_end : ci_end;
+        const bool ck_alt = s.c_alt[ck] != 0;
+        if (e_min > b_max && (!ck_alt || ci_alt)) {
+          const int li = ci_end - ci_beg, lj = ck_end - ck_beg, min_l = li < lj ? li : lj;
+          const float thr = (float)min_l * opt.mask_level;
+          if ((float)(e_min - b_max) >= thr && min_l < opt.max_chain_gap) {
+            large = true;
+            const float wk = (float)s.c_w[ck] * opt.drop_ratio;
+            drop = (float)ci_w < wk && s.c_w[ck] - ci_w >= (opt.min_seed_len << 1);
+          }
+        }
+      }
+      const int fl = W::first_true(drop);
+      const int last = fl >= 0 ? base + fl : base + NL - 1;  // side effects up to and including the dropping chain
+      const bool eff = k < n_keep && k <= last && large;
+      if (eff && s.c_first[ck] < 0) s.c_first[ck] = (int16_t)i;
+      large_overlap = W::any(eff) || large_overlap;
+      if (fl >= 0) K = base + fl;
+    }
+    W::sync();
+    if (K == n_keep) {
+      if (lane == 0) { s.keep[n_keep] = (uint16_t)i; s.c_kept[ci] = large_overlap ? 2 : 3; }
+      ++n_keep;
+      W::sync();
+    }
+  }
+  // ---- 4c. kept = 1 for shadowed firsts, max_chain_extend, emit (lane 0) ----
+  if (lane == 0) {
+    for (int i = 0; i < n_keep; ++i) {
+      const int c = s.ord[s.keep[i]];
+      if (s.c_first[c] >= 0) s.c_kept[s.ord[s.c_first[c]]] = 1;
+    }
+    {
+      int i; uint32_t kk = 0;
+      for (i = 0; i < n_ch; ++i) {
+        const int kept = s.c_kept[s.ord[i]];
+        if (kept == 0 || kept == 3) continue;
+        if (++kk >= (uint32_t)opt.max_chain_extend) break;
+      }
+      for (; i < n_ch; ++i) if (s.c_kept[s.ord[i]] < 3) s.c_kept[s.ord[i]] = 0;
+    }
+    int n_out = 0, s_out = 0;
+    for (int i = 0; i < n_ch; ++i) {
+      const int c = s.ord[i];
+      if (s.c_kept[c] == 0) continue;
+      bsq_chain_t &o = out_chains[n_out++];
+      o.pos = s.rbeg[c]; o.rid = s.rid[c]; o.w = s.c_w[c]; o.first = s.c_first[c]; o.kept = s.c_kept[c];
+      o.is_alt = s.c_alt[c];
+      o.seed_off = s_out; o.n_seeds = s.c_n[c]; o.n_extra = s.c_xn[c];
+      for (int q = 0; q < 6; ++q) o.pad_[q] = 0;
+      for (int j = c; j != (int)BSQ_CW_NONE; j = s.next[j]) { bsq_seed_t &d = out_seeds[s_out++]; d.rbeg = s.rbeg[j]; d.qbeg = s.qbeg[j]; d.len = s.slen[j]; }
+      for (int j = s.c_xn[c] ? s.c_xhead[c] : (int)BSQ_CW_NONE; j != (int)BSQ_CW_NONE; j = s.next[j]) {
+        bsq_seed_t &d = out_seeds[s_out++]; d.rbeg = s.rbeg[j]; d.qbeg = s.qbeg[j]; d.len = s.slen[j];
+      }
+    }
+    res.n_chains = n_out; res.n_seeds = s_out;
+  }
+  return BSQ_CW_OK;
+}

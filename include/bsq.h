@@ -157,7 +157,8 @@ void bsq_host_free(void *p);
  * c[5..8] = device time of the seed / expand+sa / chain / extend kernels, c[9] = scans+compaction,
  * c[10] = first kernel to last kernel, all in integer microseconds (CUDA events on the aligner's stream);
  * instrumented build only: c[11..13] = running count of 64-B index blocks fetched before k_seed / after
- * k_seed / after k_sa */
+ * k_seed / after k_sa; c[14] = tasks whose chaining went through the exact fallback kernel,
+ * c[15] = microseconds of k_chain_warp alone (c[7] = both chaining kernels) */
 int bsq_aligner_counters(const bsq_aligner *al, int64_t *c, int n);
 
 /* ================= pileup (methylation caller) =================

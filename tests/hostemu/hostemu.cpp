@@ -10,6 +10,7 @@
 #include <vector>
 #include "../../include/bsq.h"
 #include "../../biscuit_b200/csrc/bsq_task.h"
+#include "../../biscuit_b200/csrc/bsq_chain_warp.h"
 
 static_assert(sizeof(bsq_intv) == sizeof(bsq_intv_t), "abi");
 static_assert(sizeof(bsq_reg) == sizeof(bsq_reg_t), "abi");
@@ -129,7 +130,13 @@ int bsq_align_phase1(bsq_aligner *al, int64_t n_tasks, const uint8_t *seqs, int3
     std::vector<bsq_snode_t> sn(cap); std::vector<bsq_wchain_t> wc(cap); std::vector<bsq_bnode_t> bn(cap + 2);
     std::vector<int32_t> ord(cap); std::vector<bsq_chain_t> och(cap); std::vector<bsq_seed_t> osd(cap);
     bsq_chain_ws_t ws; ws.cap = cap; ws.snodes = sn.data(); ws.chains = wc.data(); ws.bnodes = bn.data(); ws.order = ord.data();
-    bsq_chain_result_t cr = bsq_chain_task(opt, ix, parent[t], lens[t], intv.data(), n, pos.data(), ws, och.data(), osd.data());
+    // same order of attempts as the CUDA path: shared-memory decomposition first, exact B-tree replay as fallback
+    bsq_chain_result_t cr;
+    static bsq_cw_smem_t cw;
+    if (getenv("BSQ_EMU_NO_CW") || bsq_chain_warp<bsq_cw_scalar>(opt, ix, parent[t], lens[t], intv.data(), n, pos.data(), n_sa, cw, och.data(), osd.data(), cr) != BSQ_CW_OK) {
+      cr = bsq_chain_task(opt, ix, parent[t], lens[t], intv.data(), n, pos.data(), ws, och.data(), osd.data());
+      al->counters[11]++;
+    }
     if (cr.status) { rc = BSQ_EOVERFLOW; break; }
     std::vector<uint64_t> srt(cap); std::vector<bsq_reg_t> rg(cap);
     int nr = bsq_chain2region<bsq_scalar_policy>(opt, ix, parent[t], lens[t], seq, och.data(), cr.n_chains, osd.data(), cr.frac_rep, srt.data(), ksw, rg.data());
@@ -162,7 +169,10 @@ int64_t hostemu_chain(const bsq_index *ixp, const bsq_opt *opt_, int parent, int
   std::vector<bsq_snode_t> sn(cap); std::vector<bsq_wchain_t> wc(cap); std::vector<bsq_bnode_t> bn(cap + 2);
   std::vector<int32_t> ord(cap); std::vector<bsq_chain_t> och(cap); std::vector<bsq_seed_t> osd(cap);
   bsq_chain_ws_t ws; ws.cap = cap; ws.snodes = sn.data(); ws.chains = wc.data(); ws.bnodes = bn.data(); ws.order = ord.data();
-  bsq_chain_result_t cr = bsq_chain_task(opt, ix, parent, len, intv.data(), n, pos.data(), ws, och.data(), osd.data());
+  bsq_chain_result_t cr;
+  static bsq_cw_smem_t cw;
+  if (getenv("BSQ_EMU_NO_CW") || bsq_chain_warp<bsq_cw_scalar>(opt, ix, parent, len, intv.data(), n, pos.data(), n_sa, cw, och.data(), osd.data(), cr) != BSQ_CW_OK)
+    cr = bsq_chain_task(opt, ix, parent, len, intv.data(), n, pos.data(), ws, och.data(), osd.data());
   if (cr.status) return -1;
   *n_chains = cr.n_chains; *frac_rep = cr.frac_rep;
   int64_t o = 0;
