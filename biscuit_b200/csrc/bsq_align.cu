@@ -54,6 +54,25 @@ bsq_index *bsq_index_alloc(int device) {
   return ix;
 }
 
+bool bsq_want_full_sa(uint64_t n, int halves_left) {
+  const char *e = getenv("BSQ_FULL_SA");
+  if (e) return atoi(e) != 0;
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return false;
+  const double need = (double)halves_left * (double)(n + 1) * 8.0 + 40e9;
+  return (double)free_b > need;
+}
+
+// SA of every rank by walking LF from each rank (for indices loaded from the reference's files, which only
+// hold every 32nd entry): one thread per rank, same arithmetic as bwt_sa.
+__global__ void k_derive_full_sa(bsq_fm_t fm, uint64_t n_ranks, uint64_t *full) {
+  uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_ranks) return;
+  bsq_fm_t f = fm;
+  f.full_sa = nullptr;
+  full[k] = bsq_sa(f, k);
+}
+
 void bsq_index_adopt(bsq_index *ix, void *p) {
   if (p && ix->n_allocs < 32) ix->allocs[ix->n_allocs++] = p;
 }
@@ -344,6 +363,16 @@ int bsq_index_upload(const bsq_index_desc *h, int device, bsq_index **out) {
   if (!rc) rc = upload_array(ix, h->ann_is_alt, (size_t)h->n_seqs * 4, (const void **)&ix->d.ann_is_alt);
   ix->d.l_pac = h->l_pac; ix->d.n_seqs = h->n_seqs;
   if (rc) { bsq_index_free(ix); return rc; }
+  for (int w = 1; w >= 0; --w) {  // optional full SA (see bsq_want_full_sa)
+    ix->d.fm[w].full_sa = nullptr;
+    if (!bsq_want_full_sa(h->seq_len, w + 1)) continue;
+    uint64_t *full = nullptr;
+    if (cudaMalloc(&full, (h->seq_len + 1) * 8) != cudaSuccess) { cudaGetLastError(); continue; }
+    k_derive_full_sa<<<(unsigned)((h->seq_len + 1 + 255) / 256), 256>>>(ix->d.fm[w], h->seq_len + 1, full);
+    if (cudaDeviceSynchronize() != cudaSuccess) { cudaGetLastError(); cudaFree(full); continue; }
+    ix->allocs[ix->n_allocs++] = full;
+    ix->d.fm[w].full_sa = full;
+  }
   *out = ix;
   return 0;
 }

@@ -136,6 +136,7 @@ BSQ_HD uint64_t bsq_inv_psi(const bsq_fm_t &fm, uint64_t k) {
 
 // bwt_sa (bwt.c:87-97): walk LF until a sampled rank is reached.
 BSQ_HD uint64_t bsq_sa(const bsq_fm_t &fm, uint64_t k) {
+  if (fm.full_sa) return fm.full_sa[k];
   uint64_t steps = 0, mask = (uint64_t)fm.sa_intv - 1;
   while (k & mask) {
     ++steps;

@@ -293,7 +293,7 @@ done:
 
 // Build one FM-index half on the current device.  d_pac: forward pac on the device.
 static int build_half(const uint8_t *d_pac, int64_t l_pac, int parent, int sa_intv, uint64_t chunk_max, bsq_fm_t *fm, void **alloc_bwt, void **alloc_sa,
-                      uint64_t *bwt_words_out, uint64_t *n_sa_out, int64_t *stats) {
+                      uint64_t *bwt_words_out, uint64_t *n_sa_out, int64_t *stats, uint64_t *full_sa) {
   int rc = 0;
   const uint64_t n = (uint64_t)l_pac * 2;
   const uint64_t n_words = (n + 15) / 16;
@@ -366,7 +366,7 @@ static int build_half(const uint8_t *d_pac, int64_t l_pac, int parent, int sa_in
         int np = 0;
         if ((rc = refine_ties(T, n, pos2, keys2, m, tmp, &np))) goto done;
         tot_pass += np;
-        k_emit<<<nb(m, 256), 256>>>(T, pos2, m, rank0, bwt_sym, sa, sa_intv, d_small + 4, nullptr);
+        k_emit<<<nb(m, 256), 256>>>(T, pos2, m, rank0, bwt_sym, sa, sa_intv, d_small + 4, full_sa);
         CKB(cudaGetLastError());
         rank0 += m;
       }
@@ -382,6 +382,7 @@ static int build_half(const uint8_t *d_pac, int64_t l_pac, int parent, int sa_in
     CKB(cudaMemcpy(bwt_sym, &s, 1, cudaMemcpyHostToDevice));
     uint64_t m1 = ~0ull;
     CKB(cudaMemcpy(sa, &m1, 8, cudaMemcpyHostToDevice));
+    if (full_sa) CKB(cudaMemcpy(full_sa, &m1, 8, cudaMemcpyHostToDevice));
   }
   CKB(cudaMemcpy(h_small, d_small, 5 * 8, cudaMemcpyDeviceToHost));
   cudaFree(pos); pos = nullptr; cudaFree(pos2); pos2 = nullptr; cudaFree(keys); keys = nullptr; cudaFree(keys2); keys2 = nullptr;
@@ -402,7 +403,7 @@ static int build_half(const uint8_t *d_pac, int64_t l_pac, int parent, int sa_in
   k_write_blocks<<<nb(n_blocks + 1, 128), 128>>>(bwt_sym, n, h_small[4], n_blocks, cnt4, blocks, out_words);
   CKB(cudaGetLastError());
   CKB(cudaDeviceSynchronize());
-  fm->blocks = blocks; fm->sa = sa; fm->primary = h_small[4]; fm->seq_len = n; fm->sa_intv = sa_intv;
+  fm->blocks = blocks; fm->sa = sa; fm->full_sa = full_sa; fm->primary = h_small[4]; fm->seq_len = n; fm->sa_intv = sa_intv;
   fm->L2[0] = 0;
   for (int s = 0; s < 4; ++s) fm->L2[s + 1] = fm->L2[s] + h_small[s];
   *alloc_bwt = blocks; *alloc_sa = sa; *bwt_words_out = out_words; *n_sa_out = n_sa;
@@ -446,9 +447,13 @@ extern "C" int bsq_index_build(const uint8_t *pac, int64_t l_pac, int32_t n_seqs
     void *a = nullptr, *b = nullptr;
     uint64_t chunk_max = 1ull << 29;  // suffixes sorted per pass (4 x 8 bytes each); BSQ_INDEX_CHUNK overrides (tests)
     if (const char *e = getenv("BSQ_INDEX_CHUNK")) { long long v = atoll(e); if (v > 0) chunk_max = (uint64_t)v; }
-    rc = build_half(ix->d.pac, l_pac, parent, 32, chunk_max, &ix->d.fm[parent], &a, &b, &ix->bwt_words[parent], &ix->n_sa[parent], stats);
-    if (rc) goto done;
-    bsq_index_adopt(ix, a); bsq_index_adopt(ix, b);
+    uint64_t *full = nullptr;
+    if (bsq_want_full_sa((uint64_t)l_pac * 2, parent == 1 ? 2 : 1)) {
+      if (cudaMalloc(&full, ((uint64_t)l_pac * 2 + 1) * 8) != cudaSuccess) { full = nullptr; cudaGetLastError(); }
+    }
+    rc = build_half(ix->d.pac, l_pac, parent, 32, chunk_max, &ix->d.fm[parent], &a, &b, &ix->bwt_words[parent], &ix->n_sa[parent], stats, full);
+    if (rc) { cudaFree(full); goto done; }
+    bsq_index_adopt(ix, a); bsq_index_adopt(ix, b); bsq_index_adopt(ix, full);
   }
   ix->build_stats[0] = stats[0]; ix->build_stats[1] = stats[1]; ix->build_stats[2] = stats[2];
   *out = ix; ix = nullptr;

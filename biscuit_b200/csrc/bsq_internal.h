@@ -16,3 +16,5 @@ struct bsq_index {
 void bsq_set_error(const char *fmt, ...);
 bsq_index *bsq_index_alloc(int device);
 void bsq_index_adopt(bsq_index *ix, void *dev_ptr);  // freed by bsq_index_free
+// full suffix array in HBM?  BSQ_FULL_SA=0/1 forces it; default: when `halves_left` arrays of (n+1) x 8 B fit with 40 GB to spare
+bool bsq_want_full_sa(uint64_t n, int halves_left);

@@ -35,7 +35,7 @@ int bsq_index_upload(const bsq_index_desc *h, int device, bsq_index **out) {
   memset(&ix->d, 0, sizeof ix->d);
   for (int w = 0; w < 2; ++w) {
     bsq_fm_t &f = ix->d.fm[w];
-    f.blocks = h->bwt[w]; f.sa = h->sa[w]; f.primary = h->primary[w]; f.seq_len = h->seq_len; f.sa_intv = h->sa_intv[w];
+    f.blocks = h->bwt[w]; f.sa = h->sa[w]; f.full_sa = nullptr; f.primary = h->primary[w]; f.seq_len = h->seq_len; f.sa_intv = h->sa_intv[w];
     for (int i = 0; i < 5; ++i) f.L2[i] = h->L2[w][i];
   }
   ix->d.pac = h->pac; ix->d.l_pac = h->l_pac; ix->d.n_seqs = h->n_seqs;

@@ -10,12 +10,22 @@ from biscuit_b200 import indexio
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("full_sa", ["0", "1"])
 @pytest.mark.parametrize("ds_name", ["ds_1m", "ds_hard"])
-def test_index_matches_reference(cuda, ds_name, request):
+def test_index_matches_reference(cuda, ds_name, full_sa, request, monkeypatch):
     ds = request.getfixturevalue(ds_name)
     hi = indexio.load_index(ds["fa"])
+    monkeypatch.setenv("BSQ_FULL_SA", full_sa)
     dx = cuda.build_index(hi.pac, hi.l_pac, hi.names, hi.ann_offset, hi.ann_len)
     sz = dx.sizes()
+    if refprobe.available():  # every rank's SA value (the builder's full SA, or the LF walk) against bwt_sa of the reference
+        rp = refprobe.RefProbe(ds["fa"])
+        rng = np.random.default_rng(5)
+        for which in (0, 1):
+            k = rng.integers(1, hi.fm[which].seq_len + 1, size=20000).astype(np.uint64)
+            k[:3] = [0, hi.fm[which].primary, hi.fm[which].seq_len]
+            assert (dx.sa_lookup(which, k) == rp.sa(which, k)).all()
+        rp.close()
     for which in (0, 1):
         f = hi.fm[which]
         assert int(sz["primary"][which]) == f.primary

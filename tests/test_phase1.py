@@ -34,9 +34,11 @@ def ctx(request):
     rp.close()
 
 
+@pytest.mark.parametrize("full_sa", ["0", "1"])  # LF walk over the sampled SA vs. the full SA derived in HBM
 @pytest.mark.parametrize("backend", BACKENDS)
-def test_occ4_and_sa(ctx, backend, request):
+def test_occ4_and_sa(ctx, backend, full_sa, request, monkeypatch):
     ds, hi, rp = ctx
+    monkeypatch.setenv("BSQ_FULL_SA", full_sa)
     bsq = request.getfixturevalue(backend)
     dx = bsq.upload(hi)
     rng = np.random.default_rng(0)
