@@ -115,13 +115,53 @@ struct bsq_aligner {
 // kernels
 // ------------------------------------------------------------------------------------------
 
+// Scratch of the seeding state machine on the device (interface: bsq_seed.h).  The first CAP candidates
+// of each lane live in shared memory, [entry][lane] with 16-byte elements: whatever entries the 32 lanes
+// address, every quarter-warp touches 8 distinct 16-byte bank groups, so accesses are conflict-free.
+// Longer lists (rare: a list has one entry per distinct interval size along the sweep) continue in local
+// memory.  The read is not copied: q() converts on the fly from an 8-byte register window over the batch
+// buffer (the enclosing aligned word always lies inside the 256-byte-granular device allocation).
+template <int CAP>
+struct bsq_seed_scratch_dev {
+  uint4 *sm;  // this lane's column; entry e at sm[e * 32]
+  bsq_pk_t spill[BSQ_MAX_READ_LEN + 1 - CAP];
+  const uint8_t *seq;
+  uint64_t qwin;
+  uintptr_t qaddr;
+  int parent;
+  __device__ __forceinline__ void bind(const uint8_t *s, int par) { seq = s; parent = par; qaddr = ~(uintptr_t)0; }
+  __device__ __forceinline__ bsq_pk_t get(int i) const {
+    if (i >= CAP) return spill[i - CAP];
+    const uint4 v = sm[i * 32];
+    bsq_pk_t p;
+    p.w0 = (uint64_t)v.x | (uint64_t)v.y << 32; p.w1 = (uint64_t)v.z | (uint64_t)v.w << 32;
+    return p;
+  }
+  __device__ __forceinline__ void set(int i, const bsq_pk_t &p) {
+    if (i >= CAP) { spill[i - CAP] = p; return; }
+    sm[i * 32] = make_uint4((uint32_t)p.w0, (uint32_t)(p.w0 >> 32), (uint32_t)p.w1, (uint32_t)(p.w1 >> 32));
+  }
+  __device__ __forceinline__ int q(int i) {
+    const uintptr_t a = (uintptr_t)(seq + i), w = a & ~(uintptr_t)7;
+    if (w != qaddr) { qaddr = w; qwin = __ldg(reinterpret_cast<const uint64_t *>(w)); }
+    const int c = (int)(qwin >> ((a & 7) * 8)) & 0xff;
+    return parent ? (c == 1 ? 3 : c) : (c == 2 ? 0 : c);
+  }
+};
+
+#define BSQ_SEED_CAP 32  // shared-memory candidates per lane: 64 KB per 128-thread CTA, 3 CTAs (12 warps) per SM
+
 // SMEM seeding.  Each lane owns one (read, conversion) task at a time and pulls the next one from a
 // global counter when it finishes; all lanes of the warp meet at the single bsq_extend1 site per
-// iteration so that their FM-index gathers are in flight together (see bsq_seed.h).
+// iteration so that their FM-index gathers are in flight together (see bsq_seed.h).  Starting and
+// finishing a task cost a handful of instructions (no read conversion pass, no sort: k_seed_sort), so a
+// lane that switches tasks does not hold up the other 31.
 __global__ void __launch_bounds__(128) k_seed(bsq_devopt_t opt, bsq_devidx_t ix, int64_t n_tasks, const uint8_t *seqs, int stride,
                                               const int32_t *lens, const uint8_t *parent, int pipeline, bsq_pk_t *intv,
-                                              int32_t *n_intv, int32_t *n_sa, int32_t *status, unsigned long long *next_task) {
-  bsq_seed_scratch_t scr;
+                                              int32_t *n_intv, int32_t *status, unsigned long long *next_task) {
+  extern __shared__ uint4 seed_smem[];
+  bsq_seed_scratch_dev<BSQ_SEED_CAP> scr;
+  scr.sm = seed_smem + (threadIdx.x >> 5) * (BSQ_SEED_CAP * 32) + (threadIdx.x & 31);
   bsq_seed_machine_t m;
   bsq_ext_req_t req;
   int64_t t = -1;
@@ -136,9 +176,9 @@ __global__ void __launch_bounds__(128) k_seed(bsq_devopt_t opt, bsq_devidx_t ix,
         const int len = lens[t];
         par = parent[t] != 0;
         out = intv + t * BSQ_MAX_INTV;
-        if (pipeline && len < opt.min_seed_len) { n_intv[t] = 0; n_sa[t] = 0; }  // mem_chain returns before seeding
+        if (pipeline && len < opt.min_seed_len) n_intv[t] = 0;  // mem_chain returns before seeding
         else {
-          bsq_bsconvert(seqs + t * stride, len, par, scr.q);
+          scr.bind(seqs + t * stride, par);
           bsq_sm_init(m, opt, len, BSQ_MAX_INTV);
           have = true;
         }
@@ -148,8 +188,8 @@ __global__ void __launch_bounds__(128) k_seed(bsq_devopt_t opt, bsq_devidx_t ix,
     if (have) {
       need = bsq_sm_next(m, ix.fm[par], ix.fm[!par], scr, out, req);
       if (!need) {
-        if (m.overflow) { atomicOr(status, 1); n_intv[t] = 0; n_sa[t] = 0; }
-        else { n_sa[t] = bsq_sm_finalize(m, opt, out); n_intv[t] = m.n_out; }
+        if (m.overflow) { atomicOr(status, 1); n_intv[t] = 0; }
+        else n_intv[t] = m.n_out;
         have = false;
       }
     }
@@ -157,9 +197,19 @@ __global__ void __launch_bounds__(128) k_seed(bsq_devopt_t opt, bsq_devidx_t ix,
     if (need) {
       uint64_t o0, o1, o2;
       bsq_extend1(ix.fm[par], ix.fm[!par], req, o0, o1, o2);
-      bsq_sm_consume(m, scr, out, o0, o1, o2);
+      bsq_sm_consume(m, scr, out, req, o0, o1, o2);
     }
   }
+}
+
+// Order each task's interval list (memchain.c:105) and count its SA lookups; one thread per task, all
+// lanes busy (inside k_seed a finishing lane would sort while 31 lanes wait).
+__global__ void __launch_bounds__(128) k_seed_sort(bsq_devopt_t opt, int64_t n_tasks, bsq_pk_t *intv, const int32_t *n_intv, int32_t *n_sa) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tasks) return;
+  uint32_t keys[BSQ_MAX_INTV];
+  const int n = n_intv[t];
+  n_sa[t] = n > 0 ? bsq_seed_sort(opt, intv + t * BSQ_MAX_INTV, n, keys) : 0;
 }
 
 __global__ void k_expand(bsq_devopt_t opt, int64_t n_tasks, const bsq_pk_t *intv, const int32_t *n_intv, const uint8_t *parent,
@@ -311,10 +361,13 @@ __global__ void __launch_bounds__(128) k_extend_warp(bsq_devopt_t opt, int64_t n
 
 static inline unsigned nblk(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
-// k_seed is persistent (lanes pull tasks from a counter): one wave of 148 SMs x 8 resident CTAs of 128
+// k_seed is persistent (lanes pull tasks from a counter): one wave of 148 SMs x 3 resident CTAs of 128
+static const size_t kSeedSmem = (size_t)128 * BSQ_SEED_CAP * 16;
 static inline unsigned seed_grid(int64_t n) {
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(k_seed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSeedSmem); attr_set = true; }
   int64_t want = (n + 127) / 128;
-  return (unsigned)(want < 148 * 8 ? want : 148 * 8);
+  return (unsigned)(want < 148 * 3 ? want : 148 * 3);
 }
 
 extern "C" {
@@ -438,7 +491,9 @@ int bsq_collect_intv(const bsq_index *ix, const bsq_opt *opt_, int64_t n, const 
   CK(cudaMemcpy(dlen, lens, n * 4, cudaMemcpyHostToDevice));
   CK(cudaMemset(dst, 0, 4)); CK(cudaMemset(dnext, 0, 8));
   CK(cudaMemset(dpk, 0, n * BSQ_MAX_INTV * sizeof(bsq_pk_t)));
-  k_seed<<<seed_grid(n), 128>>>(opt, ix->d, n, dseq, stride, dlen, dpar, 0, dpk, dn, dnsa, dst, dnext);
+  k_seed<<<seed_grid(n), 128, kSeedSmem>>>(opt, ix->d, n, dseq, stride, dlen, dpar, 0, dpk, dn, dst, dnext);
+  CK(cudaGetLastError());
+  k_seed_sort<<<nblk(n, 128), 128>>>(opt, n, dpk, dn, dnsa);
   CK(cudaGetLastError());
   k_unpack_intv<<<nblk(n * BSQ_MAX_INTV, 256), 256>>>(n * BSQ_MAX_INTV, dpk, dint);
   CK(cudaGetLastError());
@@ -554,9 +609,11 @@ static int phase1_device(bsq_aligner *al, int64_t n, int32_t stride, int64_t *to
   CK(cudaMemsetAsync(al->scalars.p, 0, 64, s));
   SNAP(11);
   CK(cudaEventRecord(al->ev[0], s));
-  k_seed<<<seed_grid(n), 128, 0, s>>>(opt, ix, n, al->seqs.as<uint8_t>(), stride, al->lens.as<int32_t>(), al->parent.as<uint8_t>(), 1,
-                                      al->intv.as<bsq_pk_t>(), al->n_intv.as<int32_t>(), al->n_sa.as<int32_t>(), al->status.as<int32_t>(),
-                                      al->scalars.as<unsigned long long>());
+  k_seed<<<seed_grid(n), 128, kSeedSmem, s>>>(opt, ix, n, al->seqs.as<uint8_t>(), stride, al->lens.as<int32_t>(), al->parent.as<uint8_t>(), 1,
+                                              al->intv.as<bsq_pk_t>(), al->n_intv.as<int32_t>(), al->status.as<int32_t>(),
+                                              al->scalars.as<unsigned long long>());
+  CK(cudaGetLastError());
+  k_seed_sort<<<nblk(n, 128), 128, 0, s>>>(opt, n, al->intv.as<bsq_pk_t>(), al->n_intv.as<int32_t>(), al->n_sa.as<int32_t>());
   CK(cudaGetLastError());
   CK(cudaEventRecord(al->ev[1], s));
   SNAP(12);

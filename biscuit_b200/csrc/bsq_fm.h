@@ -82,6 +82,26 @@ BSQ_HD void bsq_2occ4(const bsq_fm_t &fm, uint64_t k, uint64_t l, uint64_t ck[4]
   }
 }
 
+// bwt_2occ4 for k, l != -1 with one control path: both block fetches are issued back to back (the second is
+// skipped, not branched around, when l falls in k's block), so lanes of a warp whose intervals are wide and
+// lanes whose intervals are narrow wait for DRAM together instead of one group after the other.
+BSQ_HD void bsq_2occ4_flat(const bsq_fm_t &fm, uint64_t k, uint64_t l, uint64_t ck[4], uint64_t cl[4]) {
+  const uint64_t k2 = k - (k >= fm.primary), l2 = l - (l >= fm.primary);
+  const uint64_t kb = k2 >> 7, lb = l2 >> 7;
+  bsq_block_t bk, bl;
+  bsq_load_block(fm.blocks, kb, bk);
+  if (lb != kb) bsq_load_block(fm.blocks, lb, bl);
+  else bl = bk;
+  uint32_t a[4], c[4];
+  bsq_block_count4(bk, (int)(k2 & 127) + 1, a);
+  bsq_block_count4(bl, (int)(l2 & 127) + 1, c);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    ck[i] = bsq_block_occ(bk, i) + a[i];
+    cl[i] = bsq_block_occ(bl, i) + c[i];
+  }
+}
+
 // bwt_extend (bwt.c:278-293).  BACK=1 extends to the left in `fm`; BACK=0 is the forward
 // extension, performed as a backward step in the complementary index.
 template <int BACK>

@@ -21,7 +21,7 @@ BSQ_HD int bsq_task_seed(const bsq_devopt_t &opt, const bsq_devidx_t &ix, const 
                          bool pipeline, bsq_seed_scratch_t &scr, bsq_pk_t *out, int32_t *n_sa) {
   *n_sa = 0;
   if (pipeline && len < opt.min_seed_len) return 0;  // mem_chain returns before seeding (memchain.c:280)
-  bsq_bsconvert(seq, len, parent, scr.q);
+  scr.bind(seq, parent);
   bsq_seed_machine_t m;
   bsq_sm_init(m, opt, len, BSQ_MAX_INTV);
   bsq_ext_req_t req;
@@ -29,10 +29,11 @@ BSQ_HD int bsq_task_seed(const bsq_devopt_t &opt, const bsq_devidx_t &ix, const 
   while (bsq_sm_next(m, fm, fmc, scr, out, req)) {
     uint64_t o0, o1, o2;
     bsq_extend1(fm, fmc, req, o0, o1, o2);
-    bsq_sm_consume(m, scr, out, o0, o1, o2);
+    bsq_sm_consume(m, scr, out, req, o0, o1, o2);
   }
   if (m.overflow) return -1;
-  *n_sa = bsq_sm_finalize(m, opt, out);
+  uint32_t keys[BSQ_MAX_INTV];
+  *n_sa = bsq_seed_sort(opt, out, m.n_out, keys);
   return m.n_out;
 }
 
