@@ -67,6 +67,19 @@ void bsqo_plp_conf_default(bsqo_plp_conf *c);
 int64_t bsqo_plp_region(const bsqo_plp_conf *conf, const uint8_t *ref, int32_t ref_len, int32_t beg, int32_t end,
                         const bsqo_plp_reads *reads, int n_bams, bsqo_plp_rec *out, int64_t cap_loci);
 
+/* genotyping / text options of plp_format (pileup_conf_t, src/pileup.h:49-63; defaults src/pileup.c:944-963) */
+typedef struct {
+  double error, contam, prior0, prior1, prior2;
+  int32_t is_nome, pad_;
+} bsqo_vcf_conf;
+
+/* VCF lines (src/pileup.c:521-636) of n_loci emitted loci of contig chrm; betasum/cnt[sid*6+ctx] accumulate the
+ * methylation statistics of these loci in order (src/pileup.c:610-616).  malloc()ed text, free with bsqo_free.
+ * QUAL/FILTER/GT/GL1/GQ: parity unpinned (see the header of bsq_oracle_vcf.c). */
+char *bsqo_plp_vcf(const bsqo_vcf_conf *conf, const char *chrm, const bsqo_plp_rec *recs, int64_t n_loci, int n_bams, double *betasum,
+                   int64_t *cnt);
+void bsqo_free(void *p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,248 @@
+"""Minimal BGZF / BAM / BAI writer (and SAM -> sorted BAM converter) in pure Python + zlib.
+
+The real workflow uses samtools for this step (reference README.md:33-38); samtools/htslib are not in the image,
+so tests and the end-to-end bench build their BAM inputs here, from the SAM/BAM v1 specification.
+Test/bench tooling only -- the product reads BAM through biscuit_b200/host/bq_bam.c.
+"""
+from __future__ import annotations
+
+import struct
+import zlib
+
+import numpy as np
+
+BGZF_EOF = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+NT16 = {c: i for i, c in enumerate("=ACMGRSVTWYHKDBN")}
+CIG_OPS = "MIDNSHP=XB"
+
+
+def bgzf_block(data: bytes, level: int = 1) -> bytes:
+    co = zlib.compressobj(level, zlib.DEFLATED, -15)
+    comp = co.compress(data) + co.flush()
+    bsize = len(comp) + 25
+    assert bsize < 65536
+    return (b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", bsize) + comp +
+            struct.pack("<II", zlib.crc32(data) & 0xffffffff, len(data)))
+
+
+class BgzfWriter:
+    """Tracks virtual offsets (coffset << 16 | uoffset) so that a BAI can be written alongside."""
+
+    def __init__(self, path: str, block: int = 0xff00):
+        self.fh = open(path, "wb")
+        self.buf = bytearray()
+        self.coff = 0
+        self.block = block
+
+    def tell(self) -> int:
+        return (self.coff << 16) | len(self.buf)
+
+    def write(self, data: bytes):
+        self.buf += data
+        while len(self.buf) >= self.block:
+            self._flush(self.block)
+
+    def _flush(self, n: int):
+        blk = bgzf_block(bytes(self.buf[:n]))
+        self.fh.write(blk)
+        self.coff += len(blk)
+        del self.buf[:n]
+
+    def flush_block(self):
+        if self.buf:
+            self._flush(len(self.buf))
+
+    def close(self):
+        self.flush_block()
+        self.fh.write(BGZF_EOF)
+        self.fh.close()
+
+
+def reg2bin(beg: int, end: int) -> int:
+    end -= 1
+    if beg >> 14 == end >> 14:
+        return ((1 << 15) - 1) // 7 + (beg >> 14)
+    if beg >> 17 == end >> 17:
+        return ((1 << 12) - 1) // 7 + (beg >> 17)
+    if beg >> 20 == end >> 20:
+        return ((1 << 9) - 1) // 7 + (beg >> 20)
+    if beg >> 23 == end >> 23:
+        return ((1 << 6) - 1) // 7 + (beg >> 23)
+    if beg >> 26 == end >> 26:
+        return ((1 << 3) - 1) // 7 + (beg >> 26)
+    return 0
+
+
+def encode_record(tid, pos, mapq, flag, cigar, seq_nt16, qual, mtid, mpos, tlen, name: bytes, tags: bytes) -> bytes:
+    """cigar: list of (len, op); seq_nt16: sequence of 4-bit codes; qual: bytes of phred values."""
+    l_seq = len(seq_nt16)
+    rlen = sum(ln for ln, op in cigar if op in (0, 2, 3, 7, 8))
+    end = pos + (rlen if rlen > 0 else 1)
+    s = list(seq_nt16) + [0]
+    packed = bytes((s[i] << 4) | s[i + 1] for i in range(0, l_seq, 2))
+    body = struct.pack("<iiBBHHHiiii", tid, pos, len(name) + 1, mapq, reg2bin(pos, end), len(cigar), flag, l_seq, mtid, mpos, tlen)
+    body += name + b"\0" + b"".join(struct.pack("<I", (ln << 4) | op) for ln, op in cigar) + packed + bytes(qual) + tags
+    return struct.pack("<I", len(body)) + body, end
+
+
+def tag_i(tag: str, v: int) -> bytes:
+    return tag.encode() + b"i" + struct.pack("<i", v)
+
+
+def tag_z(tag: str, v: str) -> bytes:
+    return tag.encode() + b"Z" + v.encode() + b"\0"
+
+
+def tag_a(tag: str, v: str) -> bytes:
+    return tag.encode() + b"A" + v.encode()
+
+
+class BamWriter:
+    def __init__(self, path: str, contigs, header_text: str | None = None, block: int = 0xff00):
+        """contigs: list of (name, length)."""
+        self.path, self.contigs = path, list(contigs)
+        self.w = BgzfWriter(path, block)
+        if header_text is None:
+            header_text = "@HD\tVN:1.6\tSO:coordinate\n" + "".join(f"@SQ\tSN:{n}\tLN:{ln}\n" for n, ln in self.contigs)
+        t = header_text.encode()
+        self.w.write(b"BAM\1" + struct.pack("<i", len(t)) + t + struct.pack("<i", len(self.contigs)))
+        for n, ln in self.contigs:
+            self.w.write(struct.pack("<i", len(n) + 1) + n.encode() + b"\0" + struct.pack("<i", ln))
+        self.w.flush_block()
+        self.bins = [dict() for _ in self.contigs]      # bin -> list of [beg, end] chunks
+        self.lin = [dict() for _ in self.contigs]       # 16 kb window -> min voffset
+        self.n_rec = 0
+
+    def add(self, tid, pos, end, rec: bytes):
+        v0 = self.w.tell()
+        self.w.write(rec)
+        v1 = self.w.tell()
+        self.n_rec += 1
+        if tid < 0:
+            return
+        b = reg2bin(pos, end)
+        ch = self.bins[tid].setdefault(b, [])
+        if ch and ch[-1][1] == v0:
+            ch[-1][1] = v1
+        else:
+            ch.append([v0, v1])
+        for w in range(pos >> 14, ((end - 1) >> 14) + 1):
+            if w not in self.lin[tid] or v0 < self.lin[tid][w]:
+                self.lin[tid][w] = v0
+
+    def close(self, write_bai: bool = True):
+        self.w.close()
+        if not write_bai:
+            return
+        with open(self.path + ".bai", "wb") as fh:
+            fh.write(b"BAI\1" + struct.pack("<i", len(self.contigs)))
+            for tid in range(len(self.contigs)):
+                bins = self.bins[tid]
+                fh.write(struct.pack("<i", len(bins)))
+                for b, chunks in bins.items():
+                    fh.write(struct.pack("<Ii", b, len(chunks)))
+                    for c0, c1 in chunks:
+                        fh.write(struct.pack("<QQ", c0, c1))
+                lin = self.lin[tid]
+                n_intv = (max(lin) + 1) if lin else 0
+                fh.write(struct.pack("<i", n_intv))
+                last = 0
+                for w in range(n_intv):
+                    last = lin.get(w, last)
+                    fh.write(struct.pack("<Q", last))
+            fh.write(struct.pack("<Q", 0))
+
+
+def write_bam_from_soa(path: str, contigs, per_contig_reads, sid: int | None = None, block: int = 0xff00, tag_style: str = "YD"):
+    """per_contig_reads: list (one per contig, None allowed) of dicts as produced by tools/synth_plp.make_reads.
+    Only reads of sample `sid` are written when sid is not None.  Returns the number of records."""
+    w = BamWriter(path, contigs, block=block)
+    I32MIN = np.iinfo(np.int32).min
+    for tid, rd in enumerate(per_contig_reads):
+        if rd is None:
+            continue
+        for i in range(int(rd["n_reads"])):
+            if sid is not None and int(rd["sid"][i]) != sid:
+                continue
+            nc, co = int(rd["n_cigar"][i]), int(rd["cigar_off"][i])
+            cigar = [(int(c) >> 4, int(c) & 0xf) for c in rd["cigar"][co:co + nc]]
+            lq = int(rd["l_qseq"][i])
+            so, qo = int(rd["seq_off"][i]), int(rd["qual_off"][i])
+            packed = rd["seq"][so:so + (lq + 1) // 2]
+            nt16 = np.empty(len(packed) * 2, np.uint8)
+            nt16[0::2] = packed >> 4
+            nt16[1::2] = packed & 0xf
+            tags = b""
+            if int(rd["nm"][i]) != I32MIN:
+                tags += tag_i("NM", int(rd["nm"][i]))
+            if int(rd["as_"][i]) != I32MIN:
+                tags += tag_i("AS", int(rd["as_"][i]))
+            if int(rd["mate_rlen"][i]) >= 0:
+                tags += tag_z("MC", f"{int(rd['mate_rlen'][i])}M")
+            b = int(rd["bss_tag"][i])
+            if b >= 0:
+                if tag_style == "YD":
+                    tags += tag_a("YD", "fr"[b])
+                elif tag_style == "ZS":
+                    tags += tag_z("ZS", "+-"[b] + "+")
+                else:
+                    tags += tag_z("XG", ("CT", "GA")[b])
+            rec, end = encode_record(tid, int(rd["pos"][i]), int(rd["mapq"][i]), int(rd["flag"][i]), cigar, nt16[:lq].tolist(),
+                                     bytes(rd["qual"][qo:qo + lq]), tid, int(rd["mpos"][i]), 0, f"r{i}".encode(), tags)
+            w.add(tid, int(rd["pos"][i]), end, rec)
+    n = w.n_rec
+    w.close()
+    return n
+
+
+def sam_to_sorted_bam(sam_path: str, bam_path: str) -> int:
+    """Coordinate-sort a SAM file (header @SQ order) and write BAM + BAI.  Small inputs only (in-memory sort)."""
+    contigs, hdr, recs = [], [], []
+    with open(sam_path) as fh:
+        for line in fh:
+            if line.startswith("@"):
+                hdr.append(line)
+                if line.startswith("@SQ"):
+                    f = dict(x.split(":", 1) for x in line.rstrip("\n").split("\t")[1:])
+                    contigs.append((f["SN"], int(f["LN"])))
+                continue
+            recs.append(line.rstrip("\n").split("\t"))
+    tid_of = {n: i for i, (n, _) in enumerate(contigs)}
+
+    def key(f):
+        t = tid_of.get(f[2], -1)
+        return (t if t >= 0 else 1 << 30, int(f[3]))
+
+    recs.sort(key=key)
+    w = BamWriter(bam_path, contigs, header_text="".join(hdr))
+    for f in recs:
+        tid = tid_of.get(f[2], -1)
+        pos = int(f[3]) - 1
+        cigar = []
+        if f[5] != "*":
+            num = ""
+            for ch in f[5]:
+                if ch.isdigit():
+                    num += ch
+                else:
+                    cigar.append((int(num), CIG_OPS.index(ch)))
+                    num = ""
+        seq = [] if f[9] == "*" else [NT16.get(c, 15) for c in f[9].upper()]
+        qual = bytes([0xff] * len(seq)) if f[10] == "*" else bytes(ord(c) - 33 for c in f[10])
+        mtid = tid if f[6] == "=" else tid_of.get(f[6], -1)
+        tags = b""
+        for t in f[11:]:
+            tg, ty, val = t.split(":", 2)
+            if ty == "i":
+                tags += tag_i(tg, int(val))
+            elif ty == "A":
+                tags += tag_a(tg, val)
+            elif ty == "f":
+                tags += tg.encode() + b"f" + struct.pack("<f", float(val))
+            else:
+                tags += tag_z(tg, val)
+        rec, end = encode_record(tid, pos, int(f[4]), int(f[1]), cigar, seq, qual, mtid, int(f[7]) - 1, int(f[8]), f[0].encode(), tags)
+        w.add(tid, pos, end, rec)
+    n = w.n_rec
+    w.close()
+    return n
