@@ -156,7 +156,7 @@ struct bsq_seed_scratch_dev {
 // iteration so that their FM-index gathers are in flight together (see bsq_seed.h).  Starting and
 // finishing a task cost a handful of instructions (no read conversion pass, no sort: k_seed_sort), so a
 // lane that switches tasks does not hold up the other 31.
-__global__ void __launch_bounds__(128) k_seed(bsq_devopt_t opt, bsq_devidx_t ix, int64_t n_tasks, const uint8_t *seqs, int stride,
+__global__ void __launch_bounds__(128) k_seed(const __grid_constant__ bsq_devopt_t opt, const __grid_constant__ bsq_devidx_t ix, int64_t n_tasks, const uint8_t *seqs, int stride,
                                               const int32_t *lens, const uint8_t *parent, int pipeline, bsq_pk_t *intv,
                                               int32_t *n_intv, int32_t *status, unsigned long long *next_task) {
   extern __shared__ uint4 seed_smem[];
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(128) k_seed(bsq_devopt_t opt, bsq_devidx_t ix,
 
 // Order each task's interval list (memchain.c:105) and count its SA lookups; one thread per task, all
 // lanes busy (inside k_seed a finishing lane would sort while 31 lanes wait).
-__global__ void __launch_bounds__(128) k_seed_sort(bsq_devopt_t opt, int64_t n_tasks, bsq_pk_t *intv, const int32_t *n_intv, int32_t *n_sa) {
+__global__ void __launch_bounds__(128) k_seed_sort(const __grid_constant__ bsq_devopt_t opt, int64_t n_tasks, bsq_pk_t *intv, const int32_t *n_intv, int32_t *n_sa) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_tasks) return;
   uint32_t keys[BSQ_MAX_INTV];
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(128) k_seed_sort(bsq_devopt_t opt, int64_t n_t
   n_sa[t] = n > 0 ? bsq_seed_sort(opt, intv + t * BSQ_MAX_INTV, n, keys) : 0;
 }
 
-__global__ void k_expand(bsq_devopt_t opt, int64_t n_tasks, const bsq_pk_t *intv, const int32_t *n_intv, const uint8_t *parent,
+__global__ void k_expand(const __grid_constant__ bsq_devopt_t opt, int64_t n_tasks, const bsq_pk_t *intv, const int32_t *n_intv, const uint8_t *parent,
                          const int64_t *sa_off, uint64_t *ranks) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_tasks) return;
@@ -248,7 +248,7 @@ __global__ void k_occ4(bsq_devidx_t ix, int which, int64_t n, const uint64_t *k,
 // per-task workspace offset: sa_off[t] + t * BSQ_TAIL_SLACK entries
 __device__ __forceinline__ int64_t ws_off(const int64_t *sa_off, int64_t t) { return sa_off[t] + t * BSQ_TAIL_SLACK; }
 
-__global__ void __launch_bounds__(128) k_chain(bsq_devopt_t opt, bsq_devidx_t ix, int64_t n_tasks, const int32_t *lens,
+__global__ void __launch_bounds__(128) k_chain(const __grid_constant__ bsq_devopt_t opt, const __grid_constant__ bsq_devidx_t ix, int64_t n_tasks, const int32_t *lens,
                                                const uint8_t *parent, const bsq_pk_t *intv, const int32_t *n_intv,
                                                const int64_t *sa_off, const uint64_t *pos, bsq_snode_t *snodes,
                                                bsq_wchain_t *wchains, bsq_bnode_t *bnodes, int32_t *order, bsq_chain_t *ochains,
@@ -298,7 +298,7 @@ struct bsq_cw_warp {
 
 // Chaining + chain filter, one WARP per task, state in shared memory (bsq_chain_warp.h).  Tasks the decomposition
 // cannot take exactly are flagged for k_chain (thread-per-task, exact B-tree replay).
-__global__ void __launch_bounds__(128) k_chain_warp(bsq_devopt_t opt, bsq_devidx_t ix, int64_t n_tasks, const int32_t *lens, const uint8_t *parent,
+__global__ void __launch_bounds__(128) k_chain_warp(const __grid_constant__ bsq_devopt_t opt, const __grid_constant__ bsq_devidx_t ix, int64_t n_tasks, const int32_t *lens, const uint8_t *parent,
                                                     const bsq_pk_t *intv, const int32_t *n_intv, const int32_t *n_sa, const int64_t *sa_off,
                                                     const uint64_t *pos, bsq_chain_t *ochains, bsq_seed_t *oseeds, int32_t *n_chains,
                                                     float *frac_rep, uint8_t *fb_flag, unsigned long long *n_fallback) {
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(128) k_chain_warp(bsq_devopt_t opt, bsq_devidx
 
 // Chains -> regions, one WARP per task: the control flow of mem_chain2region runs uniformly in all
 // lanes, every banded extension is spread over the lanes (bsq_ksw_warp.cuh), lane 0 stores.
-__global__ void __launch_bounds__(128, 8) k_region(bsq_devopt_t opt, bsq_devidx_t ix, int64_t n_tasks, const uint8_t *seqs, int stride,
+__global__ void __launch_bounds__(128, 8) k_region(const __grid_constant__ bsq_devopt_t opt, const __grid_constant__ bsq_devidx_t ix, int64_t n_tasks, const uint8_t *seqs, int stride,
                                                 const int32_t *lens, const uint8_t *parent, const int64_t *sa_off,
                                                 const bsq_chain_t *ochains, const bsq_seed_t *oseeds, const int32_t *n_chains,
                                                 const float *frac_rep, uint64_t *srt, bsq_reg_t *regs_tmp, int32_t *n_regs) {
@@ -341,7 +341,7 @@ __global__ void k_compact_regs(int64_t n_tasks, const int64_t *sa_off, const int
 
 
 // batched ksw_extend2 jobs through the warp-cooperative kernel that k_region uses (one warp per job)
-__global__ void __launch_bounds__(128) k_extend_warp(bsq_devopt_t opt, int64_t n_jobs, const uint8_t *qbuf, const int64_t *qoff,
+__global__ void __launch_bounds__(128) k_extend_warp(const __grid_constant__ bsq_devopt_t opt, int64_t n_jobs, const uint8_t *qbuf, const int64_t *qoff,
                                                      const int32_t *qlen, const uint8_t *tbuf, const int64_t *toff, const int32_t *tlen,
                                                      const uint8_t *is_parent, const int32_t *w, const int32_t *h0, int32_t *out) {
   const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;

@@ -3,55 +3,63 @@
 //
 // The reference's band is adaptive: after every row it is trimmed to the non-zero extent of that row
 // (ksw.c:466-469), and the trimming is not value-neutral, so rows must be finished one at a time
-// (SURVEY.md §7 item 7) -- an anti-diagonal wavefront inside one extension would read cells the
-// reference never computes.  Rows are therefore processed synchronously:
-//   * lane L owns the C = ceil((qlen+1)/32) consecutive query columns [L*C, L*C+C); their eh[] state
-//     (H of the previous row shifted by one, E of this row) lives in registers, including stale cells
-//     outside the current band exactly as the reference's eh[] array keeps them;
+// (SURVEY.md section 7 item 7) -- an anti-diagonal wavefront inside one extension would read cells the
+// reference never computes.  Rows are therefore processed synchronously, and the lanes stripe the
+// CURRENT band (typically 20-40 columns), not the whole query:
+//   * the reference's eh[] array (H of the previous row shifted by one, E of this row, stale cells
+//     outside the band included) lives in shared memory, one slice per warp; in row i lane L owns
+//     columns beg + L, beg + L + 32, ...  Each lane reads and writes only its own index, so the row is
+//     updated in place like the reference does;
 //   * the horizontal gap state F(i,j+1) = max(F(i,j) - e_ins, max(M(i,j) - oe_ins, 0)) is a max-plus
-//     prefix scan over the columns: A_k = t_k + k*e_ins, F_j = max_{k<j} A_k - (j-1)*e_ins, done with a
-//     per-lane serial pass and a 5-step shuffle scan across lanes;
-//   * row maximum (last column wins ties), band trimming (first / last non-zero cell) and the
-//     to-end score are warp reductions.
+//     prefix scan over the columns: A_k = t_k + k*e_ins, F_j = max_{k<j} A_k - (j-1)*e_ins, a 5-step
+//     shuffle scan per 32 columns with a carry between chunks;
+//   * row maximum (last column wins ties) is a REDUX over packed keys, band trimming (first / last
+//     non-zero cell) comes from ballots;
+//   * the 32 target bases of a block of rows are decoded by 32 lanes at once and broadcast row by row.
 // All control decisions are warp-uniform, all arithmetic is the reference's int32 arithmetic.
 #pragma once
 #include "bsq_region.h"
 
 #define BSQ_NEG_INF (-0x40000000)
+#define BSQ_KSW_WARPS 4  // warps per CTA of every kernel that calls bsq_ksw_extend_warp
 
 // single-instruction warp reductions (REDUX)
 __device__ __forceinline__ int bsq_warp_max(int v) { return __reduce_max_sync(0xffffffffu, v); }
 __device__ __forceinline__ int bsq_warp_min(int v) { return __reduce_min_sync(0xffffffffu, v); }
 
-// One instantiation per column count, never inlined: the DP body is large and is reached from four
-// call sites (left/right extension of seeds and of backup seeds); keeping one copy keeps the
-// instruction cache warm (the first version stalled mostly on instruction fetch, profiles/README.md).
-template <int CMAX>
-__device__ __noinline__ bsq_ext_result_t bsq_ksw_extend_warp_c(int qlen, bsq_qacc_t qget, int tlen, bsq_tacc_t tget, const int8_t *mat, int o_del,
-                                                               int e_del, int o_ins, int e_ins, int w, int end_bonus, int zdrop, int h0) {
-  const int lane = threadIdx.x & 31;
-  const int C = (qlen + 1 + 31) >> 5;  // columns 0..qlen
-  const int j0 = lane * C;
+// Never inlined: the DP body is reached from four call sites (left/right extension of seeds and of
+// backup seeds); one copy keeps the instruction cache warm.
+__device__ __noinline__ bsq_ext_result_t bsq_ksw_extend_warp(int qlen, bsq_qacc_t qget, int tlen, bsq_tacc_t tget, const int8_t *mat, int o_del,
+                                                             int e_del, int o_ins, int e_ins, int w, int end_bonus, int zdrop, int h0) {
+  __shared__ int2 s_eh[BSQ_KSW_WARPS][BSQ_MAX_READ_LEN + 2];
+  __shared__ uint8_t s_q[BSQ_KSW_WARPS][BSQ_MAX_READ_LEN + 8];
+  __shared__ int8_t s_mat[BSQ_KSW_WARPS][32];
+  const int lane = threadIdx.x & 31, wid = (threadIdx.x >> 5) & (BSQ_KSW_WARPS - 1);
+  int2 *eh = s_eh[wid];
+  uint8_t *qs = s_q[wid];
+  int8_t *sm = s_mat[wid];
   const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
-  int H[CMAX], E[CMAX], Q[CMAX];
   BSQ_CTR(BSQ_CTR_KSW, lane == 0);
-  // first row (ksw.c:395-397)
+  __syncwarp();  // the previous extension of this warp is done with the slices
+  // first row (ksw.c:395-397), query codes, scoring matrix
   const int h_1 = h0 > oe_ins ? h0 - oe_ins : 0;
-#pragma unroll
-  for (int k = 0; k < CMAX; ++k) {
-    const int j = j0 + k;
-    int v = 0;
-    if (k < C && j <= qlen) {
-      if (j == 0) v = h0;
-      else if (j == 1) v = h_1;
-      else v = (h_1 - (j - 2) * e_ins > e_ins) ? h_1 - (j - 1) * e_ins : 0;
-    }
-    H[k] = v; E[k] = 0;
-    Q[k] = (k < C && j < qlen) ? qget(j) : 4;
+  for (int j = lane; j <= qlen; j += 32) {
+    int v;
+    if (j == 0) v = h0;
+    else if (j == 1) v = h_1;
+    else v = (h_1 - (j - 2) * e_ins > e_ins) ? h_1 - (j - 1) * e_ins : 0;
+    eh[j] = make_int2(v, 0);
+    if (j < qlen) qs[j] = (uint8_t)qget(j);
   }
-  // band cap (ksw.c:399-407)
   int mx = 0;
-  for (int i = 0; i < 25; ++i) mx = mx > mat[i] ? mx : mat[i];
+  {
+    const int v = lane < 25 ? mat[lane] : 0;
+    if (lane < 25) sm[lane] = (int8_t)v;
+    mx = bsq_warp_max(v);
+    mx = mx > 0 ? mx : 0;
+  }
+  __syncwarp();
+  // band cap (ksw.c:399-407)
   int max_ins = (int)((double)(qlen * mx + end_bonus - o_ins) / e_ins + 1.);
   max_ins = max_ins > 1 ? max_ins : 1;
   w = w < max_ins ? w : max_ins;
@@ -60,9 +68,10 @@ __device__ __noinline__ bsq_ext_result_t bsq_ksw_extend_warp_c(int qlen, bsq_qac
   w = w < max_del ? w : max_del;
   int max = h0, max_i = -1, max_j = -1, max_ie = -1, gscore = -1, max_off = 0;
   int beg = 0, end = qlen;
+  int tblk = 0;  // target bases of rows [i & ~31, +32), one per lane
   for (int i = 0; i < tlen; ++i) {
-    const int8_t *row = mat + 5 * tget(i);
-    const int r0 = row[0], r1 = row[1], r2 = row[2], r3 = row[3], r4 = row[4];  // uniform loads; picked per column below
+    if ((i & 31) == 0) tblk = i + lane < tlen ? tget(i + lane) : 4;
+    const int8_t *row = sm + 5 * __shfl_sync(0xffffffffu, tblk, i & 31);
     if (beg < i - w) beg = i - w;
     if (end > i + w + 1) end = i + w + 1;
     if (end > qlen) end = qlen;
@@ -70,85 +79,56 @@ __device__ __noinline__ bsq_ext_result_t bsq_ksw_extend_warp_c(int qlen, bsq_qac
     int h1_first;
     if (beg == 0) { h1_first = h0 - (o_del + e_del * (i + 1)); if (h1_first < 0) h1_first = 0; }
     else h1_first = 0;
-    // ---- M, E', and the scan operand A ----
-    int M[CMAX], A[CMAX];
-    int run = BSQ_NEG_INF;  // serial prefix max of A inside the lane (exclusive)
-    int Pk[CMAX];
+    int key = 0;               // (row max << 10) | (column + 1): ties go to the last column (ksw.c:437)
+    int carry = BSQ_NEG_INF;   // max of A over the chunks already done
+    int prevh = h1_first;      // H(i, j-1) for the first column of the chunk; eh[beg].h = h1_first
+    int nz_first = end, nz_last = -1;
+    for (int jb = beg; jb < end; jb += 32) {
+      const int j = jb + lane;
+      const bool act = j < end;
+      int2 cur = make_int2(0, 0);
+      int sc = 0;
+      if (act) { cur = eh[j]; sc = row[qs[j]]; }
+      const int M = cur.x ? cur.x + sc : 0;  // no restart from 0 (ksw.c:433)
+      int t = M - oe_ins; t = t > 0 ? t : 0;
+      int incl = act ? t + j * e_ins : BSQ_NEG_INF;
 #pragma unroll
-    for (int k = 0; k < CMAX; ++k) {
-      const int j = j0 + k;
-      const bool act = k < C && j >= beg && j < end;
-      int m_ = 0;
-      if (act) {
-        const int q = Q[k];
-        const int sc = q == 0 ? r0 : q == 1 ? r1 : q == 2 ? r2 : q == 3 ? r3 : r4;
-        m_ = H[k]; m_ = m_ ? m_ + sc : 0;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl = incl > v ? incl : v;
       }
-      M[k] = m_;
-      int t = m_ - oe_ins; t = t > 0 ? t : 0;
-      A[k] = act ? t + j * e_ins : BSQ_NEG_INF;
-      Pk[k] = run;
-      run = run > A[k] ? run : A[k];
-    }
-    // exclusive prefix max of the lane totals across lanes
-    int incl = run;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl = incl > v ? incl : v;
-    }
-    int excl = __shfl_up_sync(0xffffffffu, incl, 1);
-    if (lane == 0) excl = BSQ_NEG_INF;
-    // ---- H(i,j), row max, new E ----
-    int hrow[CMAX];
-    int m = 0, mj = -1;
-#pragma unroll
-    for (int k = 0; k < CMAX; ++k) {
-      const int j = j0 + k;
-      const bool act = k < C && j >= beg && j < end;
-      int h = 0;
-      if (act) {
-        int p = Pk[k] > excl ? Pk[k] : excl;
-        int f = p - (j - 1) * e_ins; f = f > 0 ? f : 0;  // F(i,beg) = 0; t >= 0 keeps F >= 0
-        int e = E[k];
-        h = M[k] > e ? M[k] : e;
-        h = h > f ? h : f;
-        if (h >= m) { m = h; mj = j; }
-        int t = M[k] - oe_del; t = t > 0 ? t : 0;
-        e -= e_del; e = e > t ? e : t;
-        E[k] = e;
+      int p = __shfl_up_sync(0xffffffffu, incl, 1);
+      if (lane == 0) p = BSQ_NEG_INF;
+      p = p > carry ? p : carry;
+      int f = p - (j - 1) * e_ins; f = f > 0 ? f : 0;  // F(i,beg) = 0; t >= 0 keeps F >= 0
+      int h = M > cur.y ? M : cur.y;
+      h = h > f ? h : f;
+      h = act ? h : 0;
+      const int k2 = act ? (h << 10) | (j + 1) : 0;
+      key = key > k2 ? key : k2;
+      int e = M - oe_del; e = e > 0 ? e : 0;
+      { const int e2 = cur.y - e_del; e = e > e2 ? e : e2; }
+      int left = __shfl_up_sync(0xffffffffu, h, 1);
+      if (lane == 0) left = prevh;
+      if (act) eh[j] = make_int2(left, e);  // eh[j].h = H(i,j-1), eh[j].e = E(i+1,j)
+      const unsigned nzb = __ballot_sync(0xffffffffu, act && (left != 0 || e != 0));
+      if (nzb) {
+        if (nz_last < 0) nz_first = jb + __ffs(nzb) - 1;
+        nz_last = jb + 31 - __clz(nzb);
       }
-      hrow[k] = h;
+      const int nact = end - jb < 32 ? end - jb : 32;
+      prevh = __shfl_sync(0xffffffffu, h, nact - 1);
+      const int ctot = __shfl_sync(0xffffffffu, incl, 31);
+      carry = carry > ctot ? carry : ctot;
     }
-    // warp row max; ties: the last column wins (ksw.c:437).  h < 2^15 and j < 2^9 pack into one key.
-    {
-      const int key = bsq_warp_max((m << 10) | (mj + 1));
-      m = key >> 10;
-      mj = (key & 1023) - 1;
-    }
-    // ---- shift: eh[j].h = H(i,j-1) for j in (beg,end], eh[beg].h = h1_first, eh[end].e = 0 ----
-    int lastv = 0;
-#pragma unroll
-    for (int k = 0; k < CMAX; ++k) if (k == C - 1) lastv = hrow[k];
-    const int prev_last = __shfl_up_sync(0xffffffffu, lastv, 1);  // H(i, j0-1) from the lane to the left
-    const bool nonempty = beg < end;
-    int h_end1 = 0;  // H(i,end-1), needed by the to-end score
-#pragma unroll
-    for (int k = 0; k < CMAX; ++k) {
-      const int j = j0 + k;
-      if (k < C) {
-        const int left = k == 0 ? prev_last : hrow[k - 1];
-        if (nonempty) {
-          if (j == beg) H[k] = h1_first;
-          else if (j > beg && j <= end) H[k] = left;
-          if (j == end - 1) h_end1 = hrow[k];
-        } else if (j == end) H[k] = h1_first;  // empty band: only eh[end] is touched (ksw.c:449)
-        if (j == end) E[k] = 0;
-      }
-    }
-    if (nonempty) h_end1 = bsq_warp_max(h_end1);  // scores are >= 0 and exactly one lane holds the value
-    else h_end1 = h1_first;
-    if ((nonempty ? end : beg) == qlen) {  // the column loop stopped at the query end (ksw.c:450-453)
+    // eh[end].h = H(i,end-1) (or h1_first for an empty band), eh[end].e = 0 (ksw.c:449)
+    const int h_end1 = prevh;
+    if (lane == 0) eh[end] = make_int2(h_end1, 0);
+    if (h_end1 != 0) nz_last = end;  // index end counts for the last, never for the first non-zero cell
+    __syncwarp();
+    key = bsq_warp_max(key);
+    const int m = key >> 10, mj = (key & 1023) - 1;
+    if ((beg < end ? end : beg) == qlen) {  // the column loop stopped at the query end (ksw.c:450-453)
       max_ie = gscore > h_end1 ? max_ie : i;
       gscore = gscore > h_end1 ? gscore : h_end1;
     }
@@ -164,33 +144,15 @@ __device__ __noinline__ bsq_ext_result_t bsq_ksw_extend_warp_c(int qlen, bsq_qac
       }
     }
     // ---- trim the band to the non-zero extent (ksw.c:466-469) ----
-    int first_nz = end, last_nz = -1;
-#pragma unroll
-    for (int k = 0; k < CMAX; ++k) {
-      const int j = j0 + k;
-      if (k < C && j >= beg && j <= end && (H[k] != 0 || E[k] != 0)) {
-        if (j < end && j < first_nz) first_nz = j;
-        if (j > last_nz) last_nz = j;
-      }
-    }
-    first_nz = bsq_warp_min(first_nz);
-    last_nz = bsq_warp_max(last_nz);
-    beg = first_nz;                                   // first non-zero cell in [beg,end), else end
-    const int jj = last_nz >= beg ? last_nz : beg - 1;  // last non-zero cell in [beg,end], else beg-1
+    // first non-zero cell in [beg,end) else end; last non-zero cell in [beg,end] else beg-1
+    const int nbeg = nz_first < end ? nz_first : end;
+    const int jj = nz_last >= nbeg ? nz_last : nbeg - 1;
+    beg = nbeg;
     end = jj + 2 < qlen ? jj + 2 : qlen;
   }
   bsq_ext_result_t r;
   r.score = max; r.qle = max_j + 1; r.tle = max_i + 1; r.gtle = max_ie + 1; r.gscore = gscore; r.max_off = max_off;
   return r;
-}
-
-// dispatch on the number of columns per lane
-__device__ __forceinline__ bsq_ext_result_t bsq_ksw_extend_warp(int qlen, bsq_qacc_t qget, int tlen, bsq_tacc_t tget, const int8_t *mat, int o_del,
-                                                                int e_del, int o_ins, int e_ins, int w, int end_bonus, int zdrop, int h0) {
-  const int C = (qlen + 1 + 31) >> 5;
-  if (C <= 2) return bsq_ksw_extend_warp_c<2>(qlen, qget, tlen, tget, mat, o_del, e_del, o_ins, e_ins, w, end_bonus, zdrop, h0);
-  if (C <= 5) return bsq_ksw_extend_warp_c<5>(qlen, qget, tlen, tget, mat, o_del, e_del, o_ins, e_ins, w, end_bonus, zdrop, h0);
-  return bsq_ksw_extend_warp_c<9>(qlen, qget, tlen, tget, mat, o_del, e_del, o_ins, e_ins, w, end_bonus, zdrop, h0);
 }
 
 struct bsq_warp_policy {

@@ -19,8 +19,11 @@ BSQ_HD int bsq_ref_base(const bsq_devidx_t &ix, int64_t pos) {
 }
 
 BSQ_HD int bsq_cal_max_gap(const bsq_devopt_t &opt, int qlen) {
-  int l_del = (int)((double)(qlen * opt.a - opt.o_del) / opt.e_del + 1.);
-  int l_ins = (int)((double)(qlen * opt.a - opt.o_ins) / opt.e_ins + 1.);
+  // (int)((double)x / e + 1.) of memchain.c:577-578 in integer arithmetic: x and e are small integers, e > 0, so
+  // the double quotient is never within rounding distance of an integer it does not equal, and truncating
+  // x/e + 1 toward zero is the C division (x + e) / e
+  int l_del = opt.e_del > 0 ? (qlen * opt.a - opt.o_del + opt.e_del) / opt.e_del : (int)((double)(qlen * opt.a - opt.o_del) / opt.e_del + 1.);
+  int l_ins = opt.e_ins > 0 ? (qlen * opt.a - opt.o_ins + opt.e_ins) / opt.e_ins : (int)((double)(qlen * opt.a - opt.o_ins) / opt.e_ins + 1.);
   int l = l_del > l_ins ? l_del : l_ins;
   l = l > 1 ? l : 1;
   return l < opt.w << 1 ? l : opt.w << 1;

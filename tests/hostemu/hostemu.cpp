@@ -196,4 +196,13 @@ extern "C" {
 int bsq_index_build(const uint8_t *, int64_t, int32_t, const int64_t *, const int32_t *, const int32_t *, int, bsq_index **) { return BSQ_ENODEV; }
 int bsq_index_sizes(const bsq_index *, uint64_t *, uint64_t *, uint64_t *, uint64_t *, int64_t *) { return BSQ_ENODEV; }
 int bsq_index_download(const bsq_index *, int, uint32_t *, uint64_t *) { return BSQ_ENODEV; }
+// pileup has no host emulation: the kernels are checked on the GPU box against oracle/bsq_oracle_pileup.c
+void bsq_plp_conf_default(bsq_plp_conf *c) { memset(c, 0, sizeof *c); }
+int bsq_plp_create(int, int, bsq_plp **) { return BSQ_ENODEV; }
+void bsq_plp_destroy(bsq_plp *) {}
+int bsq_plp_set_contig(bsq_plp *, const uint8_t *, int32_t) { return BSQ_ENODEV; }
+int bsq_plp_stage(bsq_plp *, const bsq_plp_reads *) { return BSQ_ENODEV; }
+int bsq_plp_run(bsq_plp *, const bsq_plp_conf *, int32_t, int32_t, int64_t *) { return BSQ_ENODEV; }
+int bsq_plp_fetch(bsq_plp *, bsq_plp_rec *) { return BSQ_ENODEV; }
+int bsq_plp_counters(const bsq_plp *, int64_t *, int) { return BSQ_ENODEV; }
 }
