@@ -101,11 +101,11 @@ struct DevBuf {
 struct bsq_aligner {
   const bsq_index *idx;
   bsq_devopt_t opt;
-  cudaStream_t stream;
-  cudaEvent_t ev[8];
+  cudaStream_t stream, stream2;  // stream2: the large-task chaining tier, concurrent with the small tiers
+  cudaEvent_t ev[8], ev_fork, ev_join;
   DevBuf seqs, lens, parent, intv, n_intv, n_sa, sa_off, ranks, pos, status;
   DevBuf snodes, wchains, bnodes, order, ochains, oseeds, n_chains, frac_rep, srt, regs_tmp, n_regs, reg_off, regs;
-  DevBuf cub_tmp, scalars, fb_flag;
+  DevBuf cub_tmp, scalars, fb_flag, tiers;
   int64_t counters[16];
   int64_t n_staged = 0, n_regs_total = -1;
   int32_t stride = 0;
@@ -296,24 +296,66 @@ struct bsq_cw_warp {
   }
 };
 
-// Chaining + chain filter, one WARP per task, state in shared memory (bsq_chain_warp.h).  Tasks the decomposition
-// cannot take exactly are flagged for k_chain (thread-per-task, exact B-tree replay).
-__global__ void __launch_bounds__(128) k_chain_warp(const __grid_constant__ bsq_devopt_t opt, const __grid_constant__ bsq_devidx_t ix, int64_t n_tasks, const int32_t *lens, const uint8_t *parent,
-                                                    const bsq_pk_t *intv, const int32_t *n_intv, const int32_t *n_sa, const int64_t *sa_off,
-                                                    const uint64_t *pos, bsq_chain_t *ochains, bsq_seed_t *oseeds, int32_t *n_chains,
-                                                    float *frac_rep, uint8_t *fb_flag, unsigned long long *n_fallback) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  bsq_cw_smem_t *sm = reinterpret_cast<bsq_cw_smem_t *>(smem_raw) + (threadIdx.x >> 5);
-  const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+// Tasks binned by their number of seeds: tier 0: n_sa <= 64, 1: <= 128, 2: <= 256, 3: the rest.  Order inside a
+// tier is arbitrary (every task writes to its own slots).
+__global__ void k_chain_tiers(int64_t n_tasks, const int32_t *n_sa, int32_t *tier_list, unsigned long long *tier_cnt) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_tasks) return;
+  const int ns = n_sa[t];
+  const int tier = ns <= 64 ? 0 : ns <= 128 ? 1 : ns <= 256 ? 2 : 3;
+  // one atomic per (warp, tier)
+  for (int q = 0; q < 4; ++q) {
+    const unsigned m = __ballot_sync(__activemask(), tier == q);
+    if (tier == q) {
+      const int leader = __ffs(m) - 1, lane = threadIdx.x & 31;
+      unsigned long long base = 0;
+      if (lane == leader) base = atomicAdd(&tier_cnt[q], (unsigned long long)__popc(m));
+      base = __shfl_sync(m, base, leader);
+      tier_list[q * n_tasks + base + __popc(m & ((1u << lane) - 1))] = (int32_t)t;
+    }
+  }
+}
+
+// Chaining + chain filter, one WARP per task, state in shared memory (bsq_chain_warp.h).  Instantiated for several
+// slice capacities (one launch per tier of k_chain_tiers), so small tasks run at high occupancy.  Tasks the decomposition cannot take exactly are
+// flagged for k_chain (thread-per-task, exact B-tree replay).
+template <int CAP, int WPB>
+__global__ void __launch_bounds__(32 * WPB) k_chain_warp(const __grid_constant__ bsq_devopt_t opt, const __grid_constant__ bsq_devidx_t ix, int64_t n_tasks,
+                                                    const int32_t *tier_list, const unsigned long long *tier_cnt, const int32_t *lens,
+                                                    const uint8_t *parent, const bsq_pk_t *intv, const int32_t *n_intv,
+                                                    const int32_t *n_sa, const int64_t *sa_off, const uint64_t *pos, bsq_chain_t *ochains,
+                                                    bsq_seed_t *oseeds, int32_t *n_chains, float *frac_rep, uint8_t *fb_flag,
+                                                    unsigned long long *n_fallback) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  typedef bsq_cw_smem_tt<CAP> S;
+  const int64_t wi = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (wi >= (int64_t)*tier_cnt) return;  // whole warps leave together
+  const int64_t t = tier_list[wi];
+  const int ns = n_sa[t];
+  S *sm = reinterpret_cast<S *>(smem_raw) + (threadIdx.x >> 5);
   const int64_t wo = ws_off(sa_off, t);
   bsq_chain_result_t r;
-  const int rc = bsq_chain_warp<bsq_cw_warp>(opt, ix, parent[t], lens[t], intv + t * BSQ_MAX_INTV, n_intv[t], pos + sa_off[t], n_sa[t], *sm,
+  const int rc = bsq_chain_warp<bsq_cw_warp>(opt, ix, parent[t], lens[t], intv + t * BSQ_MAX_INTV, n_intv[t], pos + sa_off[t], ns, *sm,
                                              ochains + wo, oseeds + wo, r);
   if ((threadIdx.x & 31) == 0) {
     if (rc == BSQ_CW_OK) { n_chains[t] = r.n_chains; frac_rep[t] = r.frac_rep; fb_flag[t] = 0; }
     else { fb_flag[t] = 1; atomicAdd(n_fallback, 1ull); }
   }
+}
+
+template <int CAP, int WPB>
+static int launch_chain_warp(cudaStream_t s, const bsq_devopt_t &opt, const bsq_devidx_t &ix, int64_t n, const int32_t *tier_list,
+                             const unsigned long long *tier_cnt, const int32_t *lens,
+                             const uint8_t *parent, const bsq_pk_t *intv, const int32_t *n_intv, const int32_t *n_sa, const int64_t *sa_off,
+                             const uint64_t *pos, bsq_chain_t *ochains, bsq_seed_t *oseeds, int32_t *n_chains, float *frac_rep, uint8_t *fb_flag,
+                             unsigned long long *n_fallback) {
+  static bool attr_set = false;
+  const size_t smem = WPB * sizeof(bsq_cw_smem_tt<CAP>);
+  if (!attr_set) { CK(cudaFuncSetAttribute(k_chain_warp<CAP, WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+  k_chain_warp<CAP, WPB><<<(unsigned)((n + WPB - 1) / WPB), 32 * WPB, smem, s>>>(opt, ix, n, tier_list, tier_cnt, lens, parent, intv, n_intv, n_sa, sa_off, pos, ochains,
+                                                                              oseeds, n_chains, frac_rep, fb_flag, n_fallback);
+  CK(cudaGetLastError());
+  return 0;
 }
 
 // Chains -> regions, one WARP per task: the control flow of mem_chain2region runs uniformly in all
@@ -543,6 +585,8 @@ int bsq_aligner_create(const bsq_index *ix, const bsq_opt *opt, bsq_aligner **ou
   memcpy(&al->opt, opt, sizeof al->opt);
   memset(al->counters, 0, sizeof al->counters);
   CK(cudaStreamCreateWithFlags(&al->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&al->stream2, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&al->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&al->ev_join, cudaEventDisableTiming));
   for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&al->ev[i]));
   *out = al;
   return 0;
@@ -553,10 +597,11 @@ void bsq_aligner_destroy(bsq_aligner *al) {
   cudaSetDevice(al->idx->device);
   DevBuf *bufs[] = {&al->seqs, &al->lens, &al->parent, &al->intv, &al->n_intv, &al->n_sa, &al->sa_off, &al->ranks, &al->pos,
                     &al->status, &al->snodes, &al->wchains, &al->bnodes, &al->order, &al->ochains, &al->oseeds, &al->n_chains,
-                    &al->frac_rep, &al->srt, &al->regs_tmp, &al->n_regs, &al->reg_off, &al->regs, &al->cub_tmp, &al->scalars, &al->fb_flag};
+                    &al->frac_rep, &al->srt, &al->regs_tmp, &al->n_regs, &al->reg_off, &al->regs, &al->cub_tmp, &al->scalars, &al->fb_flag, &al->tiers};
   for (DevBuf *b : bufs) b->release();
   for (int i = 0; i < 8; ++i) cudaEventDestroy(al->ev[i]);
   cudaStreamDestroy(al->stream);
+  cudaStreamDestroy(al->stream2); cudaEventDestroy(al->ev_fork); cudaEventDestroy(al->ev_join);
   delete al;
 }
 
@@ -637,15 +682,23 @@ static int phase1_device(bsq_aligner *al, int64_t n, int32_t stride, int64_t *to
   SNAP(13);
   RES(fb_flag, n);
   {
-    static bool attr_set = false;
-    const size_t smem = 4 * sizeof(bsq_cw_smem_t);
-    if (!attr_set) { CK(cudaFuncSetAttribute(k_chain_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
-    k_chain_warp<<<nblk(n * 32, 128), 128, smem, s>>>(opt, ix, n, al->lens.as<int32_t>(), al->parent.as<uint8_t>(), al->intv.as<bsq_pk_t>(),
-                                                      al->n_intv.as<int32_t>(), al->n_sa.as<int32_t>(), al->sa_off.as<int64_t>(),
-                                                      al->pos.as<uint64_t>(), al->ochains.as<bsq_chain_t>(), al->oseeds.as<bsq_seed_t>(),
-                                                      al->n_chains.as<int32_t>(), al->frac_rep.as<float>(), al->fb_flag.as<uint8_t>(),
-                                                      al->scalars.as<unsigned long long>() + 1);
+    RES(tiers, (size_t)n * 4 * 4);
+    unsigned long long *tcnt = al->scalars.as<unsigned long long>() + 2;
+    k_chain_tiers<<<nblk(n, 256), 256, 0, s>>>(n, al->n_sa.as<int32_t>(), al->tiers.as<int32_t>(), tcnt);
     CK(cudaGetLastError());
+#define CW_LAUNCH(CAP, WPB, Q, STREAM) if ((rc = launch_chain_warp<CAP, WPB>(STREAM, opt, ix, n, al->tiers.as<int32_t>() + (size_t)(Q) * n, tcnt + (Q), al->lens.as<int32_t>(), al->parent.as<uint8_t>(),  \
+                al->intv.as<bsq_pk_t>(), al->n_intv.as<int32_t>(), al->n_sa.as<int32_t>(), al->sa_off.as<int64_t>(), al->pos.as<uint64_t>(), \
+                al->ochains.as<bsq_chain_t>(), al->oseeds.as<bsq_seed_t>(), al->n_chains.as<int32_t>(), al->frac_rep.as<float>(),           \
+                al->fb_flag.as<uint8_t>(), al->scalars.as<unsigned long long>() + 1))) return rc
+    CK(cudaEventRecord(al->ev_fork, s));
+    CK(cudaStreamWaitEvent(al->stream2, al->ev_fork, 0));
+    CW_LAUNCH(1024, 2, 3, al->stream2);  // the few large tasks run beside the small tiers: their long tail is hidden
+    CK(cudaEventRecord(al->ev_join, al->stream2));
+    CW_LAUNCH(256, 4, 2, s);
+    CW_LAUNCH(128, 4, 1, s);
+    CW_LAUNCH(64, 4, 0, s);
+    CK(cudaStreamWaitEvent(s, al->ev_join, 0));
+#undef CW_LAUNCH
     CK(cudaEventRecord(al->ev[7], s));
   }
   k_chain<<<nblk(n, 128), 128, 0, s>>>(opt, ix, n, al->lens.as<int32_t>(), al->parent.as<uint8_t>(), al->intv.as<bsq_pk_t>(),

@@ -23,30 +23,35 @@
 #pragma once
 #include "bsq_chain.h"
 
-#define BSQ_CW_CAP 256
+#define BSQ_CW_CAP 256   // default capacity (host emulation); the CUDA kernels use 64 / 128 / 256 / 512
 #define BSQ_CW_OK 0
 #define BSQ_CW_FALLBACK 1
 #define BSQ_CW_NONE 0xFFFFu
 
-struct bsq_cw_smem_t {
-  int64_t rbeg[BSQ_CW_CAP];       // seed reference position, arrival order
-  uint64_t key[BSQ_CW_CAP];       // sort keys: rbeg << 8 | arrival index
-  int64_t c_last_rbeg[BSQ_CW_CAP];  // chain state, indexed by the arrival index of the chain's first seed
-  int32_t c_w[BSQ_CW_CAP];
-  uint16_t qbeg[BSQ_CW_CAP], slen[BSQ_CW_CAP];
-  int16_t rid[BSQ_CW_CAP];        // < 0: seed dropped (bridges contigs / strands, memchain.c:339-346)
-  uint16_t next[BSQ_CW_CAP];      // seed lists
-  uint16_t c_last_q[BSQ_CW_CAP], c_last_len[BSQ_CW_CAP], c_tail[BSQ_CW_CAP], c_n[BSQ_CW_CAP];
-  uint16_t c_xhead[BSQ_CW_CAP], c_xtail[BSQ_CW_CAP], c_xn[BSQ_CW_CAP];
-  int16_t c_first[BSQ_CW_CAP];
-  uint16_t clist[BSQ_CW_CAP];     // chains in position order
-  uint16_t ord[BSQ_CW_CAP];       // chains in filter order
-  uint16_t keep[BSQ_CW_CAP];
-  uint8_t c_kept[BSQ_CW_CAP];
-  uint8_t c_alt[BSQ_CW_CAP];       // is_alt of the seed's contig
-  uint16_t iv_off[BSQ_MAX_INTV + 1];  // first seed of every interval (prefix sums of the occurrence counts)
+// CAP = capacity in seeds (= SA lookups of the task); the kernel is instantiated for several capacities so that
+// small tasks (the majority) run at high occupancy and only the few large ones pay for a large slice
+template <int CAP_>
+struct bsq_cw_smem_tt {
+  static const int CAP = CAP_;
+  int64_t rbeg[CAP_];       // seed reference position, arrival order
+  uint64_t key[CAP_];       // sort keys: rbeg << 10 | arrival index
+  int64_t c_last_rbeg[CAP_];  // chain state, indexed by the arrival index of the chain's first seed
+  int32_t c_w[CAP_];
+  uint16_t qbeg[CAP_], slen[CAP_];
+  int16_t rid[CAP_];        // < 0: seed dropped (bridges contigs / strands, memchain.c:339-346)
+  uint16_t next[CAP_];      // seed lists
+  uint16_t c_last_q[CAP_], c_last_len[CAP_], c_tail[CAP_], c_n[CAP_];
+  uint16_t c_xhead[CAP_], c_xtail[CAP_], c_xn[CAP_];
+  int16_t c_first[CAP_];
+  uint16_t clist[CAP_];     // chains in position order
+  uint16_t ord[CAP_];       // chains in filter order
+  uint16_t keep[CAP_];
+  uint8_t c_kept[CAP_];
+  uint8_t c_alt[CAP_];       // is_alt of the seed's contig
+  uint16_t iv_off[CAP_ + 2];  // first seed of every interval (prefix sums of the occurrence counts; n_intv <= n_sa)
   int32_t pub[4];                 // lane 0 -> all lanes: number of chains / fallback request
 };
+typedef bsq_cw_smem_tt<BSQ_CW_CAP> bsq_cw_smem_t;
 
 // scalar policy (host emulation): one "lane"
 struct bsq_cw_scalar {
@@ -67,7 +72,8 @@ struct bsq_cw_by_weight {
 };
 
 // merge_seed_to_chain (memchain.c:227-256) against chain L (created by seed L)
-BSQ_HD int bsq_cw_merge(const bsq_devopt_t &opt, int64_t l_pac, bsq_cw_smem_t &s, int L, int a) {
+template <typename S>
+BSQ_HD int bsq_cw_merge(const bsq_devopt_t &opt, int64_t l_pac, S &s, int L, int a) {
   if (s.rid[a] != s.rid[L]) return 0;
   const int64_t f_rbeg = s.rbeg[L], l_rbeg = s.c_last_rbeg[L], rb = s.rbeg[a];
   const int f_q = s.qbeg[L], l_q = s.c_last_q[L], l_len = s.c_last_len[L], qb = s.qbeg[a], ln = s.slen[a];
@@ -87,7 +93,8 @@ BSQ_HD int bsq_cw_merge(const bsq_devopt_t &opt, int64_t l_pac, bsq_cw_smem_t &s
   return 0;
 }
 
-BSQ_HD int bsq_cw_weight(const bsq_cw_smem_t &s, int c) {  // mem_chain_weight (memchain.c:158-180)
+template <typename S>
+BSQ_HD int bsq_cw_weight(const S &s, int c) {  // mem_chain_weight (memchain.c:158-180)
   int64_t end = 0;
   int w = 0, tmp, j;
   for (j = c; j != (int)BSQ_CW_NONE; j = s.next[j]) {
@@ -106,14 +113,14 @@ BSQ_HD int bsq_cw_weight(const bsq_cw_smem_t &s, int c) {  // mem_chain_weight (
 }
 
 // Returns BSQ_CW_OK (res filled, outputs written) or BSQ_CW_FALLBACK (nothing written that matters).
-template <typename W>
+template <typename W, typename S>
 BSQ_HD int bsq_chain_warp(const bsq_devopt_t &opt, const bsq_devidx_t &ix, int parent, int l_seq, const bsq_pk_t *intv, int n_intv,
-                          const uint64_t *sa_pos, int n_sa, bsq_cw_smem_t &s, bsq_chain_t *out_chains, bsq_seed_t *out_seeds,
+                          const uint64_t *sa_pos, int n_sa, S &s, bsq_chain_t *out_chains, bsq_seed_t *out_seeds,
                           bsq_chain_result_t &res) {
   const int lane = W::lane(), NL = W::nl();
   res.n_chains = 0; res.n_seeds = 0; res.status = 0; res.frac_rep = 0.f;
   if (l_seq < opt.min_seed_len) return BSQ_CW_OK;
-  if (n_sa > BSQ_CW_CAP || ix.n_seqs > 32767) return BSQ_CW_FALLBACK;  // (F2)
+  if (n_sa > S::CAP || n_intv > S::CAP || ix.n_seqs > 32767) return BSQ_CW_FALLBACK;  // (F2)
   const uint64_t max_occ = (uint64_t)(uint32_t)opt.max_occ;
   // ---- 1. seeds of the task (arrival order = interval order, then occurrence order) ----
   // 1a. occurrence counts of all intervals, lanes in parallel; prefix sums by lane 0
@@ -145,7 +152,7 @@ BSQ_HD int bsq_chain_warp(const bsq_devopt_t &opt, const bsq_devidx_t &ix, int p
     s.rbeg[a] = rb; s.qbeg[a] = (uint16_t)qb; s.slen[a] = (uint16_t)ln; s.rid[a] = (int16_t)(rid < 0 ? -1 : rid);
     s.c_alt[a] = (uint8_t)(rid >= 0 && ix.ann_is_alt[rid] != 0);
     s.next[a] = (uint16_t)BSQ_CW_NONE;
-    s.key[a] = rid < 0 ? ~0ull : ((uint64_t)rb << 8 | (uint64_t)a);
+    s.key[a] = rid < 0 ? ~0ull : ((uint64_t)rb << 10 | (uint64_t)a);
   }
   W::sync();
   // ---- 2. order by reference position ----
@@ -160,10 +167,10 @@ BSQ_HD int bsq_chain_warp(const bsq_devopt_t &opt, const bsq_devidx_t &ix, int p
     int i = 0;
     while (i < n_valid && !dup) {
       int j = i + 1;
-      while (j < n_valid && (int64_t)(s.key[j] >> 8) - (int64_t)(s.key[j - 1] >> 8) < G) ++j;
+      while (j < n_valid && (int64_t)(s.key[j] >> 10) - (int64_t)(s.key[j - 1] >> 10) < G) ++j;
       const int cl0 = n_ch;
       // members in arrival order: insertion sort of the arrival indices of key[i..j)
-      for (int u = i; u < j; ++u) s.ord[u] = (uint16_t)(s.key[u] & 255);
+      for (int u = i; u < j; ++u) s.ord[u] = (uint16_t)(s.key[u] & 1023);
       for (int u = i + 1; u < j; ++u) { uint16_t v = s.ord[u]; int t = u; while (t > i && s.ord[t - 1] > v) { s.ord[t] = s.ord[t - 1]; --t; } s.ord[t] = v; }
       for (int u = i; u < j; ++u) {
         const int a = s.ord[u];

@@ -169,8 +169,18 @@ int bq_process_seqs(const bq_opt_t *opt, bsq_aligner *al, const bq_ref_t *ref, i
 
 typedef struct bq_batch bq_batch_t;
 /* GPU half (clipping, task list, bsq_align_phase1) and host half (merge, pestat, phase 2, SAM) of one batch */
+bq_batch_t *bq_batch_prep(const bq_opt_t *opt, int64_t n_processed, int n, bq_read_t *seqs, int *rc);
+int bq_batch_run(bsq_aligner *al, bq_batch_t *b);
+void bq_batch_discard(bq_batch_t *b);
 bq_batch_t *bq_batch_gpu(const bq_opt_t *opt, bsq_aligner *al, int64_t n_processed, int n, bq_read_t *seqs, int *rc);
 void bq_batch_finish(const bq_opt_t *opt, const bq_ref_t *ref, bq_batch_t *b, const bq_pestat_t *pes0, const char *rg_id);
+
+/* bq_pipe.c: source -> prep | GPU | phase 2 -> sink, batches in order.  src returns the next batch (NULL / n <= 0 at the end);
+ * sink receives the reads with .sam filled and frees them (n < 0: the batch failed, free only). */
+typedef bq_read_t *(*bq_source_fn)(void *ctx, int *n);
+typedef void (*bq_sink_fn)(void *ctx, bq_read_t *seqs, int n);
+int bq_pipeline_run(const bq_opt_t *opt, const bq_ref_t *ref, bsq_aligner *al, bq_source_fn src, void *src_ctx, bq_sink_fn sink, void *sink_ctx,
+                    const bq_pestat_t *pes0, const char *rg_id);
 
 /* bq_io.c */
 int bq_index_load(const char *prefix, bq_index_t *idx);

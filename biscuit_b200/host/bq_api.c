@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "bq.h"
+#include <stdio.h>
 
 typedef struct {
   bq_opt_t opt;
@@ -70,10 +71,9 @@ int64_t bq_session_align(bq_session *s, int64_t n_processed, int n, const uint8_
   return rc ? rc : tot;
 }
 
-/* n_batches batches of the same n reads, pipelined: the GPU half of batch i+1 overlaps the host half of batch i.
+/* n_batches batches of the same n reads through the three-stage pipeline of the CLI (bq_pipe.c).
  * Returns the SAM bytes of the last batch (negative BSQ_E* on error). */
-typedef struct { bq_session *s; int n_batches, n, stride; const uint8_t *seqs, *quals; const int32_t *lens;
-                 pthread_mutex_t mu; pthread_cond_t cv; bq_batch_t *slot; bq_read_t *slot_reads; int full, rc; } stream_t;
+typedef struct { int n_batches, b, n, stride; const uint8_t *seqs, *quals; const int32_t *lens; int64_t sam_bytes; } stream_t;
 
 static bq_read_t *make_reads(int64_t n_processed, int n, const uint8_t *seqs, int stride, const int32_t *lens, const uint8_t *quals) {
   bq_read_t *rd = calloc((size_t)n + 1, sizeof(bq_read_t));
@@ -92,47 +92,32 @@ static bq_read_t *make_reads(int64_t n_processed, int n, const uint8_t *seqs, in
   return rd;
 }
 
-static void *stream_producer(void *arg) {
-  stream_t *st = arg;
-  for (int b = 0; b < st->n_batches; ++b) {
-    int rc = 0;
-    bq_read_t *rd = make_reads((int64_t)b * st->n, st->n, st->seqs, st->stride, st->lens, st->quals);
-    bq_batch_t *bt = bq_batch_gpu(&st->s->opt, st->s->al, (int64_t)b * st->n, st->n, rd, &rc);
-    pthread_mutex_lock(&st->mu);
-    while (st->full) pthread_cond_wait(&st->cv, &st->mu);
-    st->slot = bt; st->slot_reads = rd; st->rc = rc; st->full = 1;
-    pthread_cond_broadcast(&st->cv);
-    pthread_mutex_unlock(&st->mu);
-    if (!bt) return 0;
+static bq_read_t *stream_source(void *ctx, int *n) {
+  stream_t *st = ctx;
+  if (st->b >= st->n_batches) { *n = 0; return 0; }
+  bq_read_t *rd = make_reads((int64_t)st->b * st->n, st->n, st->seqs, st->stride, st->lens, st->quals);
+  st->b++;
+  *n = st->n;
+  return rd;
+}
+
+static void stream_sink(void *ctx, bq_read_t *rd, int n) {
+  stream_t *st = ctx;
+  const int ok = n >= 0;
+  if (n < 0) n = -n;
+  int64_t tot = 0;
+  for (int i = 0; i < n; ++i) {
+    tot += rd[i].sam ? (int64_t)strlen(rd[i].sam) : 0;
+    free(rd[i].sam); free(rd[i].seq0); free(rd[i].qual); free(rd[i].name);
   }
-  return 0;
+  free(rd);
+  if (ok) st->sam_bytes = tot;
 }
 
 int64_t bq_session_align_stream(bq_session *s, int n_batches, int n, const uint8_t *seqs, int stride, const int32_t *lens, const uint8_t *quals) {
   stream_t st;
   memset(&st, 0, sizeof st);
-  st.s = s; st.n_batches = n_batches; st.n = n; st.stride = stride; st.seqs = seqs; st.quals = quals; st.lens = lens;
-  pthread_mutex_init(&st.mu, 0); pthread_cond_init(&st.cv, 0);
-  pthread_t prod;
-  pthread_create(&prod, 0, stream_producer, &st);
-  int64_t tot = 0;
-  int rc = 0;
-  for (int b = 0; b < n_batches; ++b) {
-    pthread_mutex_lock(&st.mu);
-    while (!st.full) pthread_cond_wait(&st.cv, &st.mu);
-    bq_batch_t *bt = st.slot; bq_read_t *rd = st.slot_reads; rc = st.rc;
-    st.full = 0;
-    pthread_cond_broadcast(&st.cv);
-    pthread_mutex_unlock(&st.mu);
-    if (!bt) { for (int i = 0; i < n; ++i) { free(rd[i].seq0); free(rd[i].qual); free(rd[i].name); } free(rd); break; }
-    bq_batch_finish(&s->opt, &s->ref, bt, 0, "");
-    tot = 0;
-    for (int i = 0; i < n; ++i) {
-      tot += rd[i].sam ? (int64_t)strlen(rd[i].sam) : 0;
-      free(rd[i].sam); free(rd[i].seq0); free(rd[i].qual); free(rd[i].name);
-    }
-    free(rd);
-  }
-  pthread_join(prod, 0);
-  return rc ? rc : tot;
+  st.n_batches = n_batches; st.n = n; st.stride = stride; st.seqs = seqs; st.quals = quals; st.lens = lens;
+  const int rc = bq_pipeline_run(&s->opt, &s->ref, s->al, stream_source, &st, stream_sink, &st, 0, "");
+  return rc ? rc : st.sam_bytes;
 }

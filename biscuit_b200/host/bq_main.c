@@ -12,40 +12,31 @@
 
 #include <pthread.h>
 
-/* two-stage pipeline: a producer thread reads a batch and runs its GPU half while the main thread runs the
- * host half of the previous batch and writes its SAM (cf. kt_pipeline in the reference, align.c:577) */
-typedef struct {
-  pthread_mutex_t mu;
-  pthread_cond_t cv;
-  bq_batch_t *batch; /* slot of capacity 1 */
-  bq_read_t *seqs;
-  int n, full, done, rc;
-  /* producer context */
-  bq_opt_t *opt; bsq_aligner *al; bq_fastq_t *f1, *f2; int chunk, copy_comment;
-  int64_t n_processed;
-} pipe_t;
+/* source and sink of the batch pipeline (bq_pipe.c): FASTQ batches in, SAM text out (cf. process() steps 0 and 2,
+ * lib/aln/align.c:70-167) */
+typedef struct { bq_opt_t *opt; bq_fastq_t *f1, *f2; int chunk, copy_comment; } src_ctx_t;
 
-static void *producer_main(void *arg) {
-  pipe_t *p = arg;
-  for (;;) {
-    int n = 0, rc = 0;
-    bq_read_t *seqs = bq_read_batch(p->chunk, p->opt->has_bc, p->copy_comment, &n, p->f1, p->f2);
-    bq_batch_t *b = 0;
-    if (seqs && n > 0) {
-      int64_t size = 0;
-      for (int i = 0; i < n; ++i) size += seqs[i].l_seq;
-      if (bq_verbose >= 3) fprintf(stderr, "[M::process] read %d sequences (%ld bp)...\n", n, (long)size);
-      b = bq_batch_gpu(p->opt, p->al, p->n_processed, n, seqs, &rc);
-      p->n_processed += n;
-    } else { free(seqs); seqs = 0; }
-    pthread_mutex_lock(&p->mu);
-    while (p->full) pthread_cond_wait(&p->cv, &p->mu);
-    p->batch = b; p->seqs = seqs; p->n = n; p->rc = rc; p->full = 1;
-    if (!b) p->done = 1;
-    pthread_cond_broadcast(&p->cv);
-    pthread_mutex_unlock(&p->mu);
-    if (!b) return 0;
+static bq_read_t *fastq_source(void *ctx, int *n) {
+  src_ctx_t *p = ctx;
+  bq_read_t *seqs = bq_read_batch(p->chunk, p->opt->has_bc, p->copy_comment, n, p->f1, p->f2);
+  if (seqs && *n > 0 && bq_verbose >= 3) {
+    int64_t size = 0;
+    for (int i = 0; i < *n; ++i) size += seqs[i].l_seq;
+    fprintf(stderr, "[M::process] read %d sequences (%ld bp)...\n", *n, (long)size);
   }
+  return seqs;
+}
+
+static void sam_sink(void *ctx, bq_read_t *seqs, int n) {
+  const int ok = n >= 0;
+  if (n < 0) n = -n;
+  for (int i = 0; i < n; ++i) {
+    if (ok && seqs[i].sam) fputs(seqs[i].sam, stdout);
+    free(seqs[i].name); free(seqs[i].comment); free(seqs[i].barcode); free(seqs[i].umi); free(seqs[i].seq0); free(seqs[i].qual);
+    free(seqs[i].sam);
+  }
+  free(seqs);
+  if (ok && bq_verbose >= 3) fprintf(stderr, "[M::mem_process_seqs] Processed %d reads\n", n);
 }
 
 static double now(void) { struct timeval tv; gettimeofday(&tv, 0); return tv.tv_sec + tv.tv_usec * 1e-6; }
@@ -267,31 +258,9 @@ int bq_main_align(int argc, char **argv) {
     for (i = 0; i < n; ++i) { if (seqs[i].sam) fputs(seqs[i].sam, stdout); free(seqs[i].name); free(seqs[i].seq0); free(seqs[i].sam); }
     free(seqs);
   } else {
-    pipe_t pp;
-    memset(&pp, 0, sizeof pp);
-    pthread_mutex_init(&pp.mu, 0); pthread_cond_init(&pp.cv, 0);
-    pp.opt = &opt; pp.al = al; pp.f1 = f1; pp.f2 = f2; pp.chunk = chunk; pp.copy_comment = copy_comment;
-    pthread_t prod;
-    pthread_create(&prod, 0, producer_main, &pp);
-    for (;;) {
-      pthread_mutex_lock(&pp.mu);
-      while (!pp.full) pthread_cond_wait(&pp.cv, &pp.mu);
-      bq_batch_t *b = pp.batch; bq_read_t *seqs = pp.seqs; int n = pp.n; rc = pp.rc;
-      pp.full = 0;
-      pthread_cond_broadcast(&pp.cv);
-      pthread_mutex_unlock(&pp.mu);
-      if (!b) { if (rc) bq_fatal("alignment batch failed: %s (%s)", bsq_strerror(rc), bsq_last_error()); break; }
-      double t1 = now();
-      bq_batch_finish(&opt, &idx.ref, b, pes0, rg_id);
-      if (bq_verbose >= 3) fprintf(stderr, "[M::mem_process_seqs] Processed %d reads; host phase %.3f real sec\n", n, now() - t1);
-      for (i = 0; i < n; ++i) {
-        if (seqs[i].sam) fputs(seqs[i].sam, stdout);
-        free(seqs[i].name); free(seqs[i].comment); free(seqs[i].barcode); free(seqs[i].umi); free(seqs[i].seq0); free(seqs[i].qual);
-        free(seqs[i].sam);
-      }
-      free(seqs);
-    }
-    pthread_join(prod, 0);
+    src_ctx_t sc = {&opt, f1, f2, chunk, copy_comment};
+    if ((rc = bq_pipeline_run(&opt, &idx.ref, al, fastq_source, &sc, sam_sink, 0, pes0, rg_id)))
+      bq_fatal("alignment batch failed: %s (%s)", bsq_strerror(rc), bsq_last_error());
   }
   bsq_aligner_destroy(al);
   bsq_index_free(dx);

@@ -774,6 +774,9 @@ void bq_read_clipping(bq_read_t *s, const uint8_t *adaptor, int l_adaptor, const
 }
 
 /* ---------------- the batch driver: mem_process_seqs (bwamem.c:432-476) ---------------- */
+#include <time.h>
+static double bq_now(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + ts.tv_nsec * 1e-9; }
+
 
 typedef struct {
   const bq_opt_t *opt; const bq_ref_t *ref; bq_read_t *seqs; bq_regv_t *regs; bq_pestat_t pes; int64_t n_processed;
@@ -828,8 +831,42 @@ static void run_threads(work_t *w, int n_items) {
   free(th); free(ta);
 }
 
-/* The batch in two halves so that callers can overlap the GPU half of batch i+1 with the host half of batch i
- * (the reference overlaps I/O and compute the same way with kt_pipeline, align.c:577). */
+/* The batch in three parts so that callers can pipeline them (bq_pipeline_run): host preparation (clipping, task
+ * list), the GPU part (stage / run / fetch through page-locked buffers) and the host phase 2.  (The reference
+ * overlaps I/O and compute the same way with kt_pipeline, align.c:577.) */
+typedef struct bq_slot {
+  void *tseq; size_t tseq_cap;   /* page-locked task rows */
+  void *regs; size_t regs_cap;   /* page-locked regions */
+  struct bq_slot *next;
+} bq_slot_t;
+static pthread_mutex_t slot_mu = PTHREAD_MUTEX_INITIALIZER;
+static bq_slot_t *slot_free_list;
+
+static bq_slot_t *slot_get(void) {
+  pthread_mutex_lock(&slot_mu);
+  bq_slot_t *s = slot_free_list;
+  if (s) slot_free_list = s->next;
+  pthread_mutex_unlock(&slot_mu);
+  if (!s) s = calloc(1, sizeof *s);
+  return s;
+}
+static void slot_put(bq_slot_t *s) {
+  if (!s) return;
+  pthread_mutex_lock(&slot_mu);
+  s->next = slot_free_list; slot_free_list = s;
+  pthread_mutex_unlock(&slot_mu);
+}
+static int slot_reserve(void **p, size_t *cap, size_t need) {
+  if (need <= *cap) return 0;
+  if (*p) bsq_host_free(*p);
+  *p = 0; *cap = 0;
+  const size_t want = need + need / 4 + 4096;
+  const int rc = bsq_host_alloc(p, want);
+  if (rc) return rc;
+  *cap = want;
+  return 0;
+}
+
 struct bq_batch {
   int n;
   int64_t n_processed;
@@ -837,11 +874,18 @@ struct bq_batch {
   bsq_reg *dregs;
   int64_t *reg_off, *task_of_read;
   uint8_t *n_task;
+  /* prepared for the GPU */
+  int64_t nt;
+  int stride;
+  int32_t *tlen;
+  uint8_t *par;
+  bq_slot_t *slot;
 };
 
-bq_batch_t *bq_batch_gpu(const bq_opt_t *opt, bsq_aligner *al, int64_t n_processed, int n, bq_read_t *seqs, int *rc_out) {
+bq_batch_t *bq_batch_prep(const bq_opt_t *opt, int64_t n_processed, int n, bq_read_t *seqs, int *rc_out) {
   const int pe = (opt->flag & BQ_F_PE) != 0;
   int i, max_len = 1;
+  if (rc_out) *rc_out = 0;
   /* clipping (bwamem.c:322,343-344) */
   for (i = 0; i < n; ++i) {
     const int second = pe && (i & 1);
@@ -866,18 +910,49 @@ bq_batch_t *bq_batch_gpu(const bq_opt_t *opt, bsq_aligner *al, int64_t n_process
     b->n_task[i] = (uint8_t)(nt - k0);
   }
   const int stride = (max_len + 15) & ~15;
-  uint8_t *tseq = calloc((size_t)nt * stride + 16, 1);
+  b->slot = slot_get();
+  const int rc = slot_reserve(&b->slot->tseq, &b->slot->tseq_cap, (size_t)nt * stride + 16);
+  if (rc) { if (rc_out) *rc_out = rc; slot_put(b->slot); free(par); free(b->task_of_read); free(b->n_task); free(b); return 0; }
+  uint8_t *tseq = b->slot->tseq;
   int32_t *tlen = malloc(sizeof(int32_t) * (size_t)(nt + 1));
   for (i = 0; i < n; ++i)
     for (int t = 0; t < b->n_task[i]; ++t) {
-      memcpy(tseq + (size_t)(b->task_of_read[i] + t) * stride, seqs[i].seq, (size_t)seqs[i].l_seq);
+      uint8_t *row = tseq + (size_t)(b->task_of_read[i] + t) * stride;
+      memcpy(row, seqs[i].seq, (size_t)seqs[i].l_seq);
+      memset(row + seqs[i].l_seq, 0, (size_t)(stride - seqs[i].l_seq));
       tlen[b->task_of_read[i] + t] = seqs[i].l_seq;
     }
   b->reg_off = malloc(sizeof(int64_t) * (size_t)(nt + 1));
-  int rc = bsq_align_phase1(al, nt, tseq, stride, tlen, par, &b->dregs, b->reg_off);
-  free(tseq); free(tlen); free(par);
+  b->nt = nt; b->stride = stride; b->tlen = tlen; b->par = par;
+  return b;
+}
+
+/* GPU part: H2D of the task rows, the phase-1 kernels, D2H of the regions (all through page-locked memory) */
+int bq_batch_run(bsq_aligner *al, bq_batch_t *b) {
+  int rc;
+  int64_t n_regs = 0;
+  if (b->nt == 0) { b->reg_off[0] = 0; return 0; }
+  if ((rc = bsq_aligner_stage(al, b->nt, b->slot->tseq, b->stride, b->tlen, b->par))) return rc;
+  if ((rc = bsq_aligner_run(al, &n_regs))) return rc;
+  if ((rc = slot_reserve(&b->slot->regs, &b->slot->regs_cap, (size_t)(n_regs + 1) * sizeof(bsq_reg)))) return rc;
+  if ((rc = bsq_aligner_fetch(al, b->slot->regs, b->reg_off))) return rc;
+  b->dregs = b->slot->regs;
+  return 0;
+}
+
+static void batch_free(bq_batch_t *b) {
+  slot_put(b->slot);
+  free(b->task_of_read); free(b->n_task); free(b->reg_off); free(b->tlen); free(b->par);
+  free(b);
+}
+
+void bq_batch_discard(bq_batch_t *b) { if (b) batch_free(b); }
+
+bq_batch_t *bq_batch_gpu(const bq_opt_t *opt, bsq_aligner *al, int64_t n_processed, int n, bq_read_t *seqs, int *rc_out) {
+  int rc = 0;
+  bq_batch_t *b = bq_batch_prep(opt, n_processed, n, seqs, &rc);
+  if (b && (rc = bq_batch_run(al, b))) { batch_free(b); b = 0; }
   if (rc_out) *rc_out = rc;
-  if (rc) { free(b->task_of_read); free(b->n_task); free(b->reg_off); free(b); return 0; }
   return b;
 }
 
@@ -889,18 +964,22 @@ void bq_batch_finish(const bq_opt_t *opt, const bq_ref_t *ref, bq_batch_t *b, co
   w.regs = calloc((size_t)n + 1, sizeof(bq_regv_t));
   w.dev_regs = b->dregs; w.reg_off = b->reg_off; w.task_of_read = b->task_of_read; w.n_task_of_read = b->n_task;
   w.stage = 1;
+  double t0_ = getenv("BQ_TIMING") ? bq_now() : 0;
   run_threads(&w, n);
-  bsq_free(b->dregs);
-  free(b->task_of_read); free(b->n_task); free(b->reg_off);
+  const double tm_ = t0_ > 0 ? bq_now() : 0;
+  if (t0_ > 0) fprintf(stderr, "[bq_finish] merge %.3f", tm_ - t0_);
+  slot_put(b->slot); b->slot = 0; b->dregs = 0;  /* the regions now live in w.regs */
   if (pe) { if (pes0) w.pes = *pes0; else w.pes = bq_pestat(opt, ref, n, w.regs); }
   w.stage = 2;
+  double t1_ = t0_ > 0 ? bq_now() : 0;
   run_threads(&w, pe ? n >> 1 : n);
+  if (t0_ > 0) fprintf(stderr, " pestat %.3f phase2 %.3f s\n", t1_ - tm_, bq_now() - t1_);
   for (int i = 0; i < n; ++i) {
     for (size_t k = 0; k < w.regs[i].n; ++k) if (w.regs[i].a[k].n_cigar > 0) free(w.regs[i].a[k].cigar);
     free(w.regs[i].a);
   }
   free(w.regs);
-  free(b);
+  batch_free(b);
 }
 
 int bq_process_seqs(const bq_opt_t *opt, bsq_aligner *al, const bq_ref_t *ref, int64_t n_processed, int n, bq_read_t *seqs,

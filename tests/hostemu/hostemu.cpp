@@ -17,7 +17,12 @@ static_assert(sizeof(bsq_reg) == sizeof(bsq_reg_t), "abi");
 static_assert(sizeof(bsq_opt) == sizeof(bsq_devopt_t), "abi");
 
 struct bsq_index { bsq_devidx_t d; };
-struct bsq_aligner { const bsq_index *idx; bsq_devopt_t opt; int64_t counters[16]; };
+struct bsq_aligner {
+  const bsq_index *idx; bsq_devopt_t opt; int64_t counters[16];
+  // staged execution (bsq_aligner_stage / _run / _fetch): copies of the inputs and the results of the last run
+  std::vector<uint8_t> st_seqs, st_par; std::vector<int32_t> st_lens; int32_t st_stride = 0; int64_t st_n = 0;
+  bsq_reg *res_regs = nullptr; std::vector<int64_t> res_off; int64_t res_n = -1;
+};
 
 #include "../../biscuit_b200/csrc/bsq_opt_default.h"
 
@@ -102,7 +107,7 @@ int bsq_aligner_create(const bsq_index *ix, const bsq_opt *opt, bsq_aligner **ou
   *out = a;
   return 0;
 }
-void bsq_aligner_destroy(bsq_aligner *a) { delete a; }
+void bsq_aligner_destroy(bsq_aligner *a) { if (a) free(a->res_regs); delete a; }
 void bsq_free(void *p) { free(p); }
 int bsq_aligner_counters(const bsq_aligner *a, int64_t *c, int n) { for (int i = 0; i < n && i < 16; ++i) c[i] = a->counters[i]; return 0; }
 
@@ -189,6 +194,33 @@ int64_t hostemu_chain(const bsq_index *ixp, const bsq_opt *opt_, int parent, int
   return o;
 }
 }  // extern "C"
+
+// staged execution on top of bsq_align_phase1 (plain host memory stands in for page-locked memory)
+extern "C" {
+int bsq_aligner_stage(bsq_aligner *al, int64_t n, const uint8_t *seqs, int32_t stride, const int32_t *lens, const uint8_t *parent) {
+  al->st_seqs.assign(seqs, seqs + n * stride); al->st_lens.assign(lens, lens + n); al->st_par.assign(parent, parent + n);
+  al->st_stride = stride; al->st_n = n; al->res_n = -1;
+  return 0;
+}
+int bsq_aligner_run(bsq_aligner *al, int64_t *n_regs) {
+  free(al->res_regs); al->res_regs = nullptr;
+  al->res_off.assign(al->st_n + 1, 0);
+  if (al->st_n == 0) { al->res_n = 0; if (n_regs) *n_regs = 0; return 0; }
+  int rc = bsq_align_phase1(al, al->st_n, al->st_seqs.data(), al->st_stride, al->st_lens.data(), al->st_par.data(), &al->res_regs, al->res_off.data());
+  if (rc) return rc;
+  al->res_n = al->res_off[al->st_n];
+  if (n_regs) *n_regs = al->res_n;
+  return 0;
+}
+int bsq_aligner_fetch(bsq_aligner *al, bsq_reg *regs, int64_t *reg_off) {
+  if (al->res_n < 0) return BSQ_EINVAL;
+  if (al->res_n > 0) memcpy(regs, al->res_regs, (size_t)al->res_n * sizeof(bsq_reg));
+  memcpy(reg_off, al->res_off.data(), (size_t)(al->st_n + 1) * 8);
+  return 0;
+}
+int bsq_host_alloc(void **p, size_t bytes) { *p = malloc(bytes ? bytes : 1); return *p ? 0 : BSQ_ENOMEM; }
+void bsq_host_free(void *p) { free(p); }
+}
 
 // Entry points that only exist on the GPU (index construction, pinned memory, staged execution, pileup):
 // the host emulation says so instead of pretending.
