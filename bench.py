@@ -249,6 +249,52 @@ def bench_pileup(args):
         recs = pl.fetch(pl.run(conf, 1, L))
     dt_e2e = time.perf_counter() - t1
     kus /= args.steps
+    # --- the command line itself: coordinate-sorted BAM + FASTA in, VCF text out (BGZF inflate, BAM decode, GPU, text) ---
+    cli = None
+    try:
+        import bamio
+        import tempfile
+        with tempfile.TemporaryDirectory() as d:
+            t3 = time.perf_counter()
+            with open(os.path.join(d, "ref.fa"), "w") as fh:
+                fh.write(">chrS\n")
+                txt = np.frombuffer(b"ACGT", np.uint8)[nt4].tobytes().decode()
+                fh.write("\n".join(txt[i:i + 100] for i in range(0, L, 100)) + "\n")
+            bamio.write_bam_fixed(os.path.join(d, "in.bam"), "chrS", L, rd)
+            bam_bytes = os.path.getsize(os.path.join(d, "in.bam"))
+            log(f"pileup: FASTA + BAM ({bam_bytes / 1e6:.0f} MB) written in {time.perf_counter() - t3:.1f}s")
+            exe = os.path.join(ROOT, "biscuit_b200", "host", "biscuit")
+            ncores = os.cpu_count() or 1
+            t4 = time.perf_counter()
+            subprocess.run([exe, "pileup", "-@", str(ncores), "-o", os.path.join(d, "out.vcf"), os.path.join(d, "ref.fa"),
+                            os.path.join(d, "in.bam")], check=True, env=dict(os.environ, BSQ_PLP_TIMING="1"))
+            dt_cli = time.perf_counter() - t4
+            vcf_bytes = os.path.getsize(os.path.join(d, "out.vcf"))
+            cli = {"value": (L - 1) / dt_cli, "unit": "loci/s", "seconds": dt_cli, "bam_bytes": bam_bytes, "vcf_bytes": vcf_bytes,
+                   "host_threads": ncores, "note": "biscuit pileup: process start, FASTA load, BGZF inflate + BAM decode, GPU, VCF text, file write"}
+            if not args.no_cpu_baseline:
+                import oracle_plp
+                sys.path.insert(0, os.path.join(ROOT, "tests"))
+                from test_pileup_cli import oracle_vcf
+                sub = min(L, 2_000_000)
+                keep = rd["pos"] < sub
+                rs = {k: (v[keep] if isinstance(v, np.ndarray) and len(v) == rd["n_reads"] else v) for k, v in rd.items()}
+                rs["n_reads"] = int(keep.sum())
+                t5 = time.perf_counter()
+                exp_txt = oracle_vcf(oracle_plp.region(conf, nt4, rs, 1, sub - 200), "chrS", 1)[0]
+                dt_oracle_cli = time.perf_counter() - t5
+                got_lines = []
+                with open(os.path.join(d, "out.vcf"), "rb") as fh:
+                    for line in fh:
+                        if line[:1] == b"#":
+                            continue
+                        if int(line.split(b"\t", 2)[1]) >= sub - 200:
+                            break
+                        got_lines.append(line)
+                cli["identical_to_oracle_text"] = b"".join(got_lines) == exp_txt
+                cli["oracle_loci_per_s"] = (sub - 200) / dt_oracle_cli
+    except Exception as e:  # noqa: BLE001
+        log("pileup CLI leg failed:", e)
     h2d = sum(int(np.asarray(v).nbytes) for k, v in rd.items() if k != "n_reads")
     alg = rd["n_reads"] * (75 + 150 + 48) + (L - 1) * (1 + 48) + n_loci * 88
     cpu = None
@@ -272,7 +318,9 @@ def bench_pileup(args):
                                    "CpG/CHG/CHH extraction", "reads": int(rd["n_reads"]), "emitted_loci": int(n_loci),
                        "l2": "inputs larger than L2 (reads + counters)"},
             "clocks": clocks, "e2e": {"value": (L - 1) * args.steps / dt_e2e, "unit": "loci/s", "h2d_bytes_per_step": h2d,
-                                      "d2h_bytes_per_step": int(n_loci) * 88},
+                                      "d2h_bytes_per_step": int(n_loci) * 88,
+                                      "note": "C ABI with host buffers: stage (H2D) + kernels + fetch (D2H) per pass"},
+            "e2e_cli": cli,
             "gpu_launches": 3 * args.steps * ((L + (8 << 20) - 1) // (8 << 20)),
             "roofline": {"bound": "hbm", "kernel": "k_plp_pile", "achieved": alg / (kus[0] * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": alg / (kus[0] * 1e-6) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
@@ -289,7 +337,7 @@ def main():
     ap.add_argument("--plp-mb", type=float, default=20.0)
     ap.add_argument("--plp-depth", type=int, default=30)
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-mb", type=float, default=float(os.environ.get("BSQ_BENCH_REF_MB", "3100")))
@@ -503,7 +551,10 @@ def main():
             # (instrumented run reports totals; split: SA blocks = total - seed blocks is not separable here, so the
             # roofline of the dominant kernel uses all FM-index block traffic when it is k_seed or k_sa)
             per_task_bytes["k_seed"] = 64.0 * work["seed_blocks"] + 150 + 32 * 10
-            per_task_bytes["k_expand+k_sa"] = 64.0 * work["sa_blocks"] + 24 * sa_per_task
+            # with the full suffix array resident (counters[1] == 2) a lookup is rank in, one 8-byte SA entry, position out:
+            # no credit for the LF-walk blocks that are no longer fetched
+            full_sa = int(counters[1]) == 2
+            per_task_bytes["k_expand+k_sa"] = 24 * sa_per_task + (0.0 if full_sa else 64.0 * work["sa_blocks"])
             per_task_bytes["k_chain"] = (8 + 16 + 40) * sa_per_task  # SA position in, seed + chain records out
             per_task_bytes["k_region"] = work["ref_bases"] / 4 + 150 + 56
             alg_bytes = per_task_bytes[dom_name] * n_tasks
@@ -518,7 +569,7 @@ def main():
         roof = {"bound": "hbm", "kernel": dom_name, "achieved": (alg_bytes / dom_s / 1e9) if alg_bytes else None, "peak": peak,
                 "unit": "GB/s", "frac": (alg_bytes / dom_s / 1e9 / peak) if alg_bytes else None, "traffic": None,
                 "peak_source": peak_src, "kernel_ms": kern_us[dom] / 1000, "share_of_step": float(kern_us[dom] / max(kern_us[5], 1)),
-                "work_per_task": work, "by_kernel": by_kernel}
+                "work_per_task": work, "by_kernel": by_kernel, "full_sa_resident": int(counters[1]) == 2 if work else None}
         cpu = None
         if not args.no_cpu_baseline:
             try:
@@ -549,7 +600,7 @@ def main():
                 "clocks": clocks, "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                                           "sam_bytes_per_step": int(sam_bytes), "host_threads": ncores},
                 "e2e_phase1": {"value": e2e_phase1, "unit": "reads/s", "note": "C ABI with pinned host buffers: H2D + kernels + D2H of regions"},
-                "gpu_launches": 6 * args.steps, "roofline": roof, "cpu_baseline": cpu,
+                "gpu_launches": 12 * args.steps, "roofline": roof, "cpu_baseline": cpu,
                 "kernel_us_per_step": dict(zip(stage_names, [float(x) for x in kern_us]))}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -149,14 +149,19 @@ struct bsq_seed_scratch_dev {
   }
 };
 
-#define BSQ_SEED_CAP 32  // shared-memory candidates per lane: 64 KB per 128-thread CTA, 3 CTAs (12 warps) per SM
+#ifndef BSQ_SEED_CAP
+#define BSQ_SEED_CAP 16  // shared-memory candidates per lane: 32 KB per 128-thread CTA
+#endif
+#ifndef BSQ_SEED_CTAS
+#define BSQ_SEED_CTAS 5   // resident CTAs per SM (registers: 96 per thread)
+#endif
 
 // SMEM seeding.  Each lane owns one (read, conversion) task at a time and pulls the next one from a
 // global counter when it finishes; all lanes of the warp meet at the single bsq_extend1 site per
 // iteration so that their FM-index gathers are in flight together (see bsq_seed.h).  Starting and
 // finishing a task cost a handful of instructions (no read conversion pass, no sort: k_seed_sort), so a
 // lane that switches tasks does not hold up the other 31.
-__global__ void __launch_bounds__(128) k_seed(const __grid_constant__ bsq_devopt_t opt, const __grid_constant__ bsq_devidx_t ix, int64_t n_tasks, const uint8_t *seqs, int stride,
+__global__ void __launch_bounds__(128, BSQ_SEED_CTAS) k_seed(const __grid_constant__ bsq_devopt_t opt, const __grid_constant__ bsq_devidx_t ix, int64_t n_tasks, const uint8_t *seqs, int stride,
                                               const int32_t *lens, const uint8_t *parent, int pipeline, bsq_pk_t *intv,
                                               int32_t *n_intv, int32_t *status, unsigned long long *next_task) {
   extern __shared__ uint4 seed_smem[];
@@ -409,7 +414,7 @@ static inline unsigned seed_grid(int64_t n) {
   static bool attr_set = false;
   if (!attr_set) { cudaFuncSetAttribute(k_seed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSeedSmem); attr_set = true; }
   int64_t want = (n + 127) / 128;
-  return (unsigned)(want < 148 * 3 ? want : 148 * 3);
+  return (unsigned)(want < 148 * BSQ_SEED_CTAS ? want : 148 * BSQ_SEED_CTAS);
 }
 
 extern "C" {
@@ -734,6 +739,7 @@ static int phase1_device(bsq_aligner *al, int64_t n, int32_t stride, int64_t *to
   for (int i = 0; i < 6; ++i) cudaEventElapsedTime(&ms[i], al->ev[i], al->ev[i + 1]);
   { float tot; cudaEventElapsedTime(&tot, al->ev[0], al->ev[6]); al->counters[10] = (int64_t)(tot * 1000); }
   al->counters[0] = n; al->counters[2] = total_sa; al->counters[4] = *total_regs;
+  al->counters[1] = (ix.fm[0].full_sa != nullptr) + (ix.fm[1].full_sa != nullptr);
   al->counters[5] = (int64_t)(ms[0] * 1000); al->counters[6] = (int64_t)(ms[2] * 1000);
   al->counters[7] = (int64_t)(ms[3] * 1000); al->counters[8] = (int64_t)(ms[4] * 1000);
   al->counters[9] = (int64_t)((ms[1] + ms[5]) * 1000);

@@ -812,6 +812,14 @@ static void work_item(work_t *w, long i) {
       for (size_t k = 0; k < w->regs[i << 1 | e].n; ++k) w->regs[i << 1 | e].a[k].flag = 0;
     bq_reg2sam_pe(w->opt, w->ref, (uint64_t)((w->n_processed >> 1) + i), &w->seqs[i << 1], &w->regs[i << 1], w->pes, w->rg_id);
   }
+  if (w->stage == 2) { /* the regions of this item are done with: release them here, on the worker */
+    const long lo = w->pe ? i << 1 : i, hi = w->pe ? (i << 1) + 2 : i + 1;
+    for (long r = lo; r < hi; ++r) {
+      for (size_t k = 0; k < w->regs[r].n; ++k) if (w->regs[r].a[k].n_cigar > 0) free(w->regs[r].a[k].cigar);
+      free(w->regs[r].a);
+      w->regs[r].a = 0; w->regs[r].n = 0;
+    }
+  }
 }
 
 typedef struct { work_t *w; int tid; } thr_t;
@@ -974,10 +982,6 @@ void bq_batch_finish(const bq_opt_t *opt, const bq_ref_t *ref, bq_batch_t *b, co
   double t1_ = t0_ > 0 ? bq_now() : 0;
   run_threads(&w, pe ? n >> 1 : n);
   if (t0_ > 0) fprintf(stderr, " pestat %.3f phase2 %.3f s\n", t1_ - tm_, bq_now() - t1_);
-  for (int i = 0; i < n; ++i) {
-    for (size_t k = 0; k < w.regs[i].n; ++k) if (w.regs[i].a[k].n_cigar > 0) free(w.regs[i].a[k].cigar);
-    free(w.regs[i].a);
-  }
   free(w.regs);
   batch_free(b);
 }

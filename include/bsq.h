@@ -153,7 +153,8 @@ int bsq_work_counters(uint64_t *out, int n, int reset);
 void bsq_host_free(void *p);
 
 /* counters of the last bsq_align_phase1 call (for the roofline arithmetic in bench.py):
- * c[0]=tasks c[1]=intervals c[2]=seeds(SA lookups) c[3]=chains kept c[4]=regions
+ * c[0]=tasks c[1]=index halves with a resident full suffix array (0..2: SA lookups are then one 8-byte read,
+ * no LF walk) c[2]=seeds(SA lookups) c[3]=unused c[4]=regions
  * c[5..8] = device time of the seed / expand+sa / chain / extend kernels, c[9] = scans+compaction,
  * c[10] = first kernel to last kernel, all in integer microseconds (CUDA events on the aligner's stream);
  * instrumented build only: c[11..13] = running count of 64-B index blocks fetched before k_seed / after

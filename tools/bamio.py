@@ -246,3 +246,95 @@ def sam_to_sorted_bam(sam_path: str, bam_path: str) -> int:
     n = w.n_rec
     w.close()
     return n
+
+
+def write_bam_fixed(path: str, contig: str, contig_len: int, rd: dict, level: int = 1) -> int:
+    """Vectorised writer for the bench: every read has one M operation of its full length and the same tag set
+    (NM:i AS:i MC:Z:<len>M YD:A:f|r), so all records have the same size and are laid out with numpy.  Records
+    never straddle BGZF blocks.  Writes <path> and <path>.bai; returns the number of records."""
+    n = int(rd["n_reads"])
+    L = int(rd["l_qseq"][0])
+    assert (rd["l_qseq"] == L).all() and (rd["n_cigar"] == 1).all()
+    name_w = 10
+    mc = f"{L}M".encode()
+    tags_len = 7 + 7 + (3 + len(mc) + 1) + 4
+    body = 32 + name_w + 4 + (L + 1) // 2 + L + tags_len
+    rec = np.zeros((n, 4 + body), np.uint8)
+
+    def put32(col, v):
+        rec[:, col:col + 4] = np.ascontiguousarray(v.astype("<i4")).view(np.uint8).reshape(n, 4)
+
+    def put16(col, v):
+        rec[:, col:col + 2] = np.ascontiguousarray(v.astype("<u2")).view(np.uint8).reshape(n, 2)
+
+    pos = rd["pos"].astype(np.int64)
+    put32(0, np.full(n, body))
+    put32(4, np.zeros(n))                       # refID
+    put32(8, pos)
+    rec[:, 12] = name_w
+    rec[:, 13] = rd["mapq"]
+    put16(14, np.full(n, 4680))                 # bin: not used by the reader
+    put16(16, np.ones(n))                       # n_cigar_op
+    put16(18, rd["flag"])
+    put32(20, np.full(n, L))
+    put32(24, np.zeros(n))                      # next refID
+    put32(28, rd["mpos"])
+    put32(32, np.zeros(n))                      # tlen
+    o = 36
+    ids = np.arange(n)
+    digits = np.zeros((n, name_w - 1), np.uint8)
+    for k in range(name_w - 2, 0, -1):
+        digits[:, k] = 48 + ids % 10
+        ids = ids // 10
+    digits[:, 0] = ord("r")
+    rec[:, o:o + name_w - 1] = digits
+    o += name_w
+    put32(o, np.full(n, (L << 4)))
+    o += 4
+    nb = (L + 1) // 2
+    rec[:, o:o + nb] = rd["seq"].reshape(n, nb)
+    o += nb
+    rec[:, o:o + L] = rd["qual"].reshape(n, L)
+    o += L
+    rec[:, o:o + 3] = np.frombuffer(b"NMi", np.uint8); put32(o + 3, rd["nm"]); o += 7
+    rec[:, o:o + 3] = np.frombuffer(b"ASi", np.uint8); put32(o + 3, rd["as_"]); o += 7
+    t = b"MCZ" + mc + b"\0"
+    rec[:, o:o + len(t)] = np.frombuffer(t, np.uint8); o += len(t)
+    rec[:, o:o + 3] = np.frombuffer(b"YDA", np.uint8)
+    rec[:, o + 3] = np.where(rd["bss_tag"] > 0, ord("r"), ord("f"))
+    o += 4
+    assert o == 4 + body
+    per_block = max(1, 0xff00 // (4 + body))
+    hdr_text = f"@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:{contig}\tLN:{contig_len}\n".encode()
+    hdr = (b"BAM\1" + struct.pack("<i", len(hdr_text)) + hdr_text + struct.pack("<i", 1) + struct.pack("<i", len(contig) + 1) +
+           contig.encode() + b"\0" + struct.pack("<i", contig_len))
+    flat = rec.reshape(-1)
+    n_blocks = (n + per_block - 1) // per_block
+    coffs = np.zeros(n_blocks + 1, np.int64)
+    with open(path, "wb") as fh:
+        blk = bgzf_block(hdr, level)
+        fh.write(blk)
+        off = len(blk)
+        step = per_block * (4 + body)
+        for b in range(n_blocks):
+            coffs[b] = off
+            blk = bgzf_block(flat[b * step:(b + 1) * step].tobytes(), level)
+            fh.write(blk)
+            off += len(blk)
+        coffs[n_blocks] = off
+        fh.write(BGZF_EOF)
+    rec_idx = np.arange(n)
+    voff = (coffs[rec_idx // per_block] << 16) | ((rec_idx % per_block) * (4 + body))
+    end_v = int(coffs[n_blocks]) << 16
+    n_intv = int((pos[-1] + L - 1) >> 14) + 1 if n else 0
+    first_rec = np.searchsorted(pos + L, np.arange(n_intv, dtype=np.int64) << 14, side="right") if n else np.zeros(0, np.int64)
+    with open(path + ".bai", "wb") as fh:
+        fh.write(b"BAI\1" + struct.pack("<i", 1))
+        if n:
+            fh.write(struct.pack("<i", 1) + struct.pack("<Ii", 0, 1) + struct.pack("<QQ", int(voff[0]), end_v))
+        else:
+            fh.write(struct.pack("<i", 0))
+        fh.write(struct.pack("<i", n_intv))
+        fh.write(np.ascontiguousarray(voff[np.minimum(first_rec, n - 1)].astype("<u8")).tobytes() if n else b"")
+        fh.write(struct.pack("<Q", 0))
+    return n
