@@ -212,46 +212,83 @@ def plp_make_reads(nt4, n_pairs, seed):
 def bench_pileup(args):
     """`--path pileup`: loci/s of the methylation caller over a 30x synthetic WGBS contig."""
     import torch
+    import torch.distributed as dist
     from biscuit_b200 import capi, plp
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    torch.cuda.set_device(0)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
     peak, peak_src = load_peaks()
     L = int(args.plp_mb * 1_000_000)
-    rng = np.random.default_rng(7)
+    # one contig per rank (pileup shards by contig / window, SURVEY.md section 8e); weak scaling
+    rng = np.random.default_rng(7 + rank)
     nt4 = rng.integers(0, 4, size=L, dtype=np.uint8)
     n_pairs = int(L * args.plp_depth / 300)
     t0 = time.time()
-    rd = plp_make_reads(nt4, n_pairs, 31)
-    log(f"pileup: {rd['n_reads']} reads over {L / 1e6:.0f} Mb ({args.plp_depth}x) simulated in {time.time() - t0:.1f}s")
+    rd = plp_make_reads(nt4, n_pairs, 31 + 1000 * rank)
+    log(f"pileup rank {rank}: {rd['n_reads']} reads over {L / 1e6:.0f} Mb ({args.plp_depth}x) simulated in {time.time() - t0:.1f}s")
     bsq = capi.load()
-    pl = plp.Pileup(bsq, 1)
+    pl = plp.Pileup(bsq, 1, device=local_rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
     conf = pl.default_conf()
     pl.set_contig(nt4)
     pl.stage(rd)
     n_loci = pl.run(conf, 1, L)
     for _ in range(args.warmup):
         pl.run(conf, 1, L)
-    sampler = ClockSampler(0)
+    sampler = ClockSampler(local_rank)
     sampler.start()
-    torch.cuda.synchronize()
+    barrier()
     t0 = time.perf_counter()
     kus = np.zeros(2)
     for _ in range(args.steps):
         pl.run(conf, 1, L)
         kus += pl.counters()[4:6]
-    torch.cuda.synchronize()
+    barrier()
     dt = time.perf_counter() - t0
     clocks = sampler.stop()
     c = pl.counters()
+    barrier()
     t1 = time.perf_counter()
     for _ in range(args.steps):
         pl.stage(rd)
         recs = pl.fetch(pl.run(conf, 1, L))
+    barrier()
     dt_e2e = time.perf_counter() - t1
     kus /= args.steps
+    # the one collective of the path: per-contig methylation statistics -> every rank (NCCL over NVLink)
+    reduce_ms = None
+    if world > 1:
+        cnt_all = np.zeros((world, 1, 6), np.int64)
+        beta_all = np.zeros((world, 1, 6))
+        cnt_all[rank], beta_all[rank] = plp.context_stats(recs[recs["pos"] <= 2_000_000], 1)
+        barrier()
+        t6 = time.perf_counter()
+        cnt_m, beta_m = plp.merge_stats(cnt_all, beta_all, device=f"cuda:{local_rank}")
+        barrier()
+        reduce_ms = 1000 * (time.perf_counter() - t6)
+        assert (cnt_m[rank] == cnt_all[rank]).all() and int((cnt_m.sum(axis=(1, 2)) > 0).sum()) == world
+        tt = torch.tensor([dt, dt_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt, dt_e2e = float(tt[0]), float(tt[1])
+    if rank != 0:
+        pl.close()
+        dist.barrier()
+        dist.destroy_process_group()
+        return 0
     # --- the command line itself: coordinate-sorted BAM + FASTA in, VCF text out (BGZF inflate, BAM decode, GPU, text) ---
     cli = None
     try:
+        if world > 1:
+            raise RuntimeError("CLI leg runs at N=1 only")
         import bamio
         import tempfile
         with tempfile.TemporaryDirectory() as d:
@@ -298,7 +335,7 @@ def bench_pileup(args):
     h2d = sum(int(np.asarray(v).nbytes) for k, v in rd.items() if k != "n_reads")
     alg = rd["n_reads"] * (75 + 150 + 48) + (L - 1) * (1 + 48) + n_loci * 88
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         import oracle_plp
         sub = min(L, 2_000_000)
         keep = rd["pos"] < sub
@@ -311,13 +348,14 @@ def bench_pileup(args):
         ok = got.tobytes() == exp.tobytes()
         cpu = {"value": (sub - 200) / dtc, "unit": "loci/s", "cores": 1, "kind": "port",
                "sample": f"first {sub / 1e6:.0f} Mb through oracle/bsq_oracle_pileup.c (single thread); identical to GPU output: {ok}"}
-    line = {"metric": "wgbs_pileup_loci_per_s", "value": (L - 1) * args.steps / dt, "unit": "loci/s", "n_gpus": 1, "steps": args.steps,
+    line = {"metric": "wgbs_pileup_loci_per_s", "value": world * (L - 1) * args.steps / dt, "unit": "loci/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
             "config": {"workload": f"pileup {args.plp_depth}x synthetic WGBS, coordinate-sorted decoded BAM records, {L / 1e6:.0f} Mb contig, "
                                    "CpG/CHG/CHH extraction", "reads": int(rd["n_reads"]), "emitted_loci": int(n_loci),
                        "l2": "inputs larger than L2 (reads + counters)"},
-            "clocks": clocks, "e2e": {"value": (L - 1) * args.steps / dt_e2e, "unit": "loci/s", "h2d_bytes_per_step": h2d,
+            "clocks": clocks, "stats_reduce_ms": reduce_ms,
+            "e2e": {"value": world * (L - 1) * args.steps / dt_e2e, "unit": "loci/s", "h2d_bytes_per_step": h2d,
                                       "d2h_bytes_per_step": int(n_loci) * 88,
                                       "note": "C ABI with host buffers: stage (H2D) + kernels + fetch (D2H) per pass"},
             "e2e_cli": cli,
@@ -328,6 +366,9 @@ def bench_pileup(args):
             "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     pl.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     return 0
 
 

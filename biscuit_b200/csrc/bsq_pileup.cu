@@ -415,7 +415,7 @@ int bsq_plp_run(bsq_plp *p, const bsq_plp_conf *cf, int32_t beg, int32_t end, in
   if ((rc = p->scal.need(64))) return rc;
   CKP(cudaMemsetAsync(p->scal.p, 0, 64, s));
   // worst case output: every locus emitted; grow lazily per tile instead
-  int64_t out_cap = 0, n_out = 0;
+  int64_t out_cap = (int64_t)(p->out.cap / ((size_t)nb * sizeof(bsq_plp_rec))), n_out = 0;  // the output buffer is kept between runs
   for (int64_t tb = beg; tb < end; tb += PLP_TILE) {
     const int64_t te = tb + PLP_TILE < end ? tb + PLP_TILE : end;
     const int64_t nl = te - tb;

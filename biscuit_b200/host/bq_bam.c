@@ -276,30 +276,43 @@ static int32_t mc_rlen(const char *mc) {
 
 /* ------------------------------------------------------------------ SoA batch ---- */
 
-#define GROW(ptr, n, cap, extra)                                           \
-  do {                                                                     \
-    if ((n) + (extra) > (cap)) {                                           \
-      (cap) = ((n) + (extra)) * 3 / 2 + 1024;                              \
-      (ptr) = realloc((ptr), (size_t)(cap) * sizeof *(ptr));               \
-    }                                                                      \
+/* The batch arrays are page-locked (bsq_host_alloc) so that bsq_plp_stage copies them at full PCIe speed; they only
+ * ever grow and batches are reused, so the (slow) pinned allocations amortise. */
+static int g_pinned = 1; /* bamdump (no device involved) switches to plain memory */
+static void batch_mem_free(void *p) { if (!p) return; if (g_pinned) bsq_host_free(p); else free(p); }
+static void *pinned_grow(void *old, size_t old_bytes, size_t new_bytes) {
+  void *p = 0;
+  if (!g_pinned) { p = malloc(new_bytes); if (!p) bq_fatal("[pileup] out of memory\n"); }
+  else if (bsq_host_alloc(&p, new_bytes) != 0) bq_fatal("[pileup] cannot allocate %zu bytes of page-locked memory: %s\n", new_bytes, bsq_last_error());
+  if (old) { memcpy(p, old, old_bytes); batch_mem_free(old); }
+  return p;
+}
+#define GROW(ptr, n, cap, extra)                                                                              \
+  do {                                                                                                        \
+    if ((n) + (extra) > (cap)) {                                                                              \
+      const int64_t ncap_ = ((n) + (extra)) * 2 + (1 << 16);                                                   \
+      (ptr) = pinned_grow((ptr), (size_t)(n) * sizeof *(ptr), (size_t)ncap_ * sizeof *(ptr));                 \
+      (cap) = ncap_;                                                                                          \
+    }                                                                                                         \
   } while (0)
 
 void bq_plp_batch_reset(bq_plp_batch_t *B) { B->n = 0; B->n_cig = 0; B->n_seq = 0; B->n_qual = 0; }
 
 void bq_plp_batch_free(bq_plp_batch_t *B) {
-  free(B->pos); free(B->mpos); free(B->mate_rlen); free(B->l_qseq); free(B->nm); free(B->as); free(B->flag); free(B->mapq);
-  free(B->bss_tag); free(B->sid); free(B->n_cigar); free(B->cigar_off); free(B->cigar); free(B->seq_off); free(B->seq);
-  free(B->qual_off); free(B->qual); free(B->end);
+  void *ps[] = {B->pos, B->mpos, B->mate_rlen, B->l_qseq, B->nm, B->as, B->flag, B->mapq, B->bss_tag, B->sid, B->n_cigar, B->cigar_off, B->cigar,
+                B->seq_off, B->seq, B->qual_off, B->qual, B->end};
+  for (size_t i = 0; i < sizeof ps / sizeof ps[0]; ++i) batch_mem_free(ps[i]);
   memset(B, 0, sizeof *B);
 }
 
 static void batch_room(bq_plp_batch_t *B, int64_t n_cig, int64_t n_seq, int64_t n_qual) {
   if (B->n + 1 > B->cap) {
-    B->cap = (B->n + 1) * 3 / 2 + 1024;
-#define R(f) B->f = realloc(B->f, (size_t)B->cap * sizeof *B->f)
+    const int64_t ncap = (B->n + 1) * 2 + (1 << 14);
+#define R(f) B->f = pinned_grow(B->f, (size_t)B->n * sizeof *B->f, (size_t)ncap * sizeof *B->f)
     R(pos); R(mpos); R(mate_rlen); R(l_qseq); R(nm); R(as); R(flag); R(mapq); R(bss_tag); R(sid); R(n_cigar); R(cigar_off); R(seq_off);
     R(qual_off); R(end);
 #undef R
+    B->cap = ncap;
   }
   GROW(B->cigar, B->n_cig, B->cap_cig, n_cig);
   GROW(B->seq, B->n_seq, B->cap_seq, n_seq);
@@ -545,6 +558,7 @@ uint64_t bq_bai_start(const bq_bai_t *bai, int tid, int64_t beg0) {
  * one line per record: tid pos mpos flag mapq l_qseq NM AS mate_rlen bss n_cigar cigar... */
 int bq_main_bamdump(int argc, char **argv) {
   if (argc < 2) { fprintf(stderr, "Usage: biscuit bamdump <in.bam> [tid [beg0]]\n"); return 1; }
+  g_pinned = 0;
   bq_bgzf_t *fp = bq_bgzf_open(argv[1], 2);
   if (!fp) bq_fatal("Cannot open %s\n", argv[1]);
   bq_bam_hdr_t h;

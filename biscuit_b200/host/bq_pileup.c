@@ -474,6 +474,129 @@ typedef struct {
   int cur_tid_done; /* reader has run past the current contig */
 } bam_in_t;
 
+/* ---- small blocking queue of pointers (pipeline plumbing) ---- */
+#define PQ_CAP 8
+typedef struct { pthread_mutex_t mu; pthread_cond_t cv; void *a[PQ_CAP]; int head, n; } pq_t;
+static void pq_init(pq_t *q) { memset(q, 0, sizeof *q); pthread_mutex_init(&q->mu, 0); pthread_cond_init(&q->cv, 0); }
+static void pq_put(pq_t *q, void *p) {
+  pthread_mutex_lock(&q->mu);
+  while (q->n == PQ_CAP) pthread_cond_wait(&q->cv, &q->mu);
+  q->a[(q->head + q->n++) % PQ_CAP] = p;
+  pthread_cond_broadcast(&q->cv);
+  pthread_mutex_unlock(&q->mu);
+}
+static void *pq_get(pq_t *q) {
+  pthread_mutex_lock(&q->mu);
+  while (q->n == 0) pthread_cond_wait(&q->cv, &q->mu);
+  void *p = q->a[q->head];
+  q->head = (q->head + 1) % PQ_CAP; --q->n;
+  pthread_cond_broadcast(&q->cv);
+  pthread_mutex_unlock(&q->mu);
+  return p;
+}
+
+/* one chunk of windows on its way from the BAM decoder to the GPU stage */
+typedef struct {
+  int end, tid;
+  int64_t cb, ce;
+  bq_plp_batch_t *bt;
+  uint8_t *ref; /* nt4 codes of the contig, set on its first chunk (ownership passes to the consumer) */
+  int64_t ref_len;
+} chunk_msg_t;
+
+typedef struct { bq_str_t text; int end; } text_msg_t;
+
+typedef struct {
+  /* decoder */
+  int nb, n_work;
+  bam_in_t *in;
+  const bq_bam_hdr_t *hdr;
+  const bq_fasta_t *fa;
+  const char *reffn;
+  struct work_item { int tid; int64_t beg, end; } *work;
+  int64_t chunk;
+  pq_t q_chunks, q_free_batches;
+  double t_dec;
+  /* writer */
+  FILE *out;
+  pq_t q_text, q_free_text;
+  double t_wr;
+} plp_pipe_t;
+
+static double now_s(void);
+
+/* stage 1: stream the BAMs contig by contig and cut them into chunks of decoded records */
+static void *decoder_main(void *arg) {
+  plp_pipe_t *P = arg;
+  const int nb = P->nb;
+  for (int wi = 0; wi < P->n_work; ++wi) {
+    const int tid = P->work[wi].tid;
+    const int64_t beg = P->work[wi].beg, end = P->work[wi].end;
+    if (beg >= end) continue;
+    int any = 0;
+    for (int s = 0; s < nb; ++s) {
+      const uint64_t v = bq_bai_start(&P->in[s].bai, tid, beg - 1);
+      P->in[s].cur_tid_done = v == UINT64_MAX;
+      if (!P->in[s].cur_tid_done) { bq_bgzf_seek(P->in[s].fp, v); any = 1; }
+    }
+    if (!any) continue; /* no reads on this contig: the reference emits nothing for it */
+    uint8_t *ref = 0;
+    const int64_t ref_len = bq_fasta_fetch_nt4(P->fa, P->hdr->name[tid], &ref);
+    if (ref_len < 0) bq_fatal("[pileup] contig %s is not in %s\n", P->hdr->name[tid], P->reffn);
+    if (ref_len < end) bq_fatal("[pileup] contig %s: reference has %ld bases, BAM header says %d\n", P->hdr->name[tid], (long)ref_len, P->hdr->len[tid]);
+    bq_plp_batch_t *bt = pq_get(&P->q_free_batches);
+    bq_plp_batch_reset(bt);
+    for (int64_t cb = beg; cb < end; cb += P->chunk) {
+      const int64_t ce = cb + P->chunk < end ? cb + P->chunk : end;
+      const double t0 = now_s();
+      /* reads of this contig starting before the chunk end (0-based pos < ce - 1) */
+      for (int s = 0; s < nb; ++s) {
+        while (!P->in[s].cur_tid_done) {
+          uint32_t len;
+          const uint8_t *r = bq_bam_peek(P->in[s].fp, &len);
+          if (!r) { P->in[s].cur_tid_done = 1; break; }
+          const int32_t rtid = (int32_t)(r[0] | r[1] << 8 | r[2] << 16 | (uint32_t)r[3] << 24);
+          const int32_t pos = (int32_t)(r[4] | r[5] << 8 | r[6] << 16 | (uint32_t)r[7] << 24);
+          if (rtid != tid) { P->in[s].cur_tid_done = 1; break; }
+          if (pos >= ce - 1) break;
+          bq_plp_batch_push(bt, r, len, s);
+          bq_bam_skip(P->in[s].fp, len);
+        }
+      }
+      /* the reads that reach into the next chunk are carried over */
+      bq_plp_batch_t *nx = pq_get(&P->q_free_batches);
+      bq_plp_batch_reset(nx);
+      for (int64_t i = 0; i < bt->n; ++i)
+        if (bt->end[i] >= ce) bq_plp_batch_copy1(nx, bt, i);
+      P->t_dec += now_s() - t0;
+      chunk_msg_t *m = calloc(1, sizeof *m);
+      m->tid = tid; m->cb = cb; m->ce = ce; m->bt = bt; m->ref = ref; m->ref_len = ref_len;
+      ref = 0;
+      pq_put(&P->q_chunks, m);
+      bt = nx;
+    }
+    pq_put(&P->q_free_batches, bt);
+    free(ref);
+  }
+  chunk_msg_t *m = calloc(1, sizeof *m);
+  m->end = 1;
+  pq_put(&P->q_chunks, m);
+  return 0;
+}
+
+/* stage 3: ordered output */
+static void *writer_main(void *arg) {
+  plp_pipe_t *P = arg;
+  for (;;) {
+    text_msg_t *t = pq_get(&P->q_text);
+    if (t->end) { free(t); return 0; }
+    const double t0 = now_s();
+    if (t->text.l && fwrite(t->text.s, 1, t->text.l, P->out) != t->text.l && errno == EPIPE) exit(1);
+    P->t_wr += now_s() - t0;
+    pq_put(&P->q_free_text, t);
+  }
+}
+
 static double now_s(void) {
   struct timespec ts;
   clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -578,7 +701,7 @@ int bq_main_pileup(int argc, char **argv) {
 
   /* work list: (target index, beg, end) with 1-based beg, exclusive end (src/pileup.c:1171-1200) */
   int n_work = 0;
-  struct { int tid; int64_t beg, end; } *work = calloc((size_t)hdr.n_targets + 1, sizeof *work);
+  struct work_item *work = calloc((size_t)hdr.n_targets + 1, sizeof *work);
   if (reg) {
     int tid = -1; int64_t beg, end;
     if (parse_region(reg, &hdr, &tid, &beg, &end) != 0) bq_fatal("[pileup] cannot parse region %s\n", reg);
@@ -600,94 +723,88 @@ int bq_main_pileup(int argc, char **argv) {
   fcf.prior0 = conf.prior0 = 1.0 - conf.prior1 - conf.prior2; fcf.prior1 = conf.prior1; fcf.prior2 = conf.prior2;
   if (fcf.prior0 < 0 || fcf.prior1 < 0 || fcf.prior2 < 0) bq_fatal("[Error] genotype priors must be from 0 to 1.\n");
 
-  /* chunk = a whole number of windows, at most 8 M loci (one device tile) */
-  int64_t win_per_chunk = 8000000 / conf.step;
+  /* chunk = a whole number of windows */
+  /* about a million loci per chunk: small enough that decode, GPU and text overlap well and that the page-locked
+   * staging stays small, large enough that the per-chunk launches do not matter */
+  int64_t win_per_chunk = 1000000 / conf.step;
   if (win_per_chunk < 1) win_per_chunk = 1;
   const int64_t chunk = win_per_chunk * conf.step;
-  bq_plp_batch_t B[2];
+  /* pipeline: BAM decode (thread) | GPU + VCF text (this thread, text on conf.n_threads threads) | output (thread) */
+  plp_pipe_t P;
+  memset(&P, 0, sizeof P);
+  P.nb = nb; P.n_work = n_work; P.in = in; P.hdr = &hdr; P.fa = &fa; P.reffn = reffn; P.work = work; P.chunk = chunk; P.out = out;
+  pq_init(&P.q_chunks); pq_init(&P.q_free_batches); pq_init(&P.q_text); pq_init(&P.q_free_text);
+  bq_plp_batch_t B[4];
   memset(B, 0, sizeof B);
-  bsq_plp_rec *recs = 0;
+  for (int i = 0; i < 4; ++i) pq_put(&P.q_free_batches, &B[i]);
+  text_msg_t *texts[3];
+  for (int i = 0; i < 3; ++i) { texts[i] = calloc(1, sizeof(text_msg_t)); pq_put(&P.q_free_text, texts[i]); }
+  pthread_t th_dec, th_wr;
+  pthread_create(&th_dec, 0, decoder_main, &P);
+  pthread_create(&th_wr, 0, writer_main, &P);
+  bsq_plp_rec *recs = 0; /* page-locked */
   int64_t recs_cap = 0;
   double *wbeta = calloc((size_t)win_per_chunk * nb * BQ_NCTX, sizeof(double));
   int64_t *wcnt = calloc((size_t)win_per_chunk * nb * BQ_NCTX, sizeof(int64_t));
-  bq_str_t text = {0, 0, 0};
-  double t_dec = 0, t_gpu = 0, t_fmt = 0, t_wr = 0;
+  double t_gpu = 0, t_fmt = 0, t_wait = 0;
   int64_t tot_reads = 0, tot_loci = 0, tot_emit = 0;
-
-  for (int wi = 0; wi < n_work; ++wi) {
-    const int tid = work[wi].tid;
-    const int64_t beg = work[wi].beg, end = work[wi].end;
-    if (beg >= end) continue;
-    int any = 0;
-    for (int s = 0; s < nb; ++s) {
-      const uint64_t v = bq_bai_start(&in[s].bai, tid, beg - 1);
-      in[s].cur_tid_done = v == UINT64_MAX;
-      if (!in[s].cur_tid_done) { bq_bgzf_seek(in[s].fp, v); any = 1; }
+  for (;;) {
+    double t0 = now_s();
+    chunk_msg_t *m = pq_get(&P.q_chunks);
+    t_wait += now_s() - t0; t0 = now_s();
+    if (m->end) { free(m); break; }
+    const int tid = m->tid;
+    const int64_t cb = m->cb, ce = m->ce;
+    bq_plp_batch_t *bt = m->bt;
+    if (m->ref) {
+      if ((rc = bsq_plp_set_contig(plp, m->ref, (int32_t)m->ref_len))) bq_fatal("[pileup] bsq_plp_set_contig: %s (%s)\n", bsq_strerror(rc), bsq_last_error());
+      free(m->ref);
     }
-    if (!any) continue; /* no reads on this contig: the reference emits nothing for it */
-    uint8_t *ref = 0;
-    const int64_t ref_len = bq_fasta_fetch_nt4(&fa, hdr.name[tid], &ref);
-    if (ref_len < 0) bq_fatal("[pileup] contig %s is not in %s\n", hdr.name[tid], reffn);
-    if (ref_len < end) bq_fatal("[pileup] contig %s: reference has %ld bases, BAM header says %d\n", hdr.name[tid], (long)ref_len, hdr.len[tid]);
-    if ((rc = bsq_plp_set_contig(plp, ref, (int32_t)ref_len))) bq_fatal("[pileup] bsq_plp_set_contig: %s (%s)\n", bsq_strerror(rc), bsq_last_error());
-    free(ref);
-    int cur = 0;
-    bq_plp_batch_reset(&B[0]); bq_plp_batch_reset(&B[1]);
-    for (int64_t cb = beg; cb < end; cb += chunk) {
-      const int64_t ce = cb + chunk < end ? cb + chunk : end;
-      bq_plp_batch_t *bt = &B[cur];
-      double t0 = now_s();
-      /* reads of this contig starting before the chunk end (0-based pos < ce - 1) */
-      for (int s = 0; s < nb; ++s) {
-        while (!in[s].cur_tid_done) {
-          uint32_t len;
-          const uint8_t *r = bq_bam_peek(in[s].fp, &len);
-          if (!r) { in[s].cur_tid_done = 1; break; }
-          const int32_t rtid = (int32_t)(r[0] | r[1] << 8 | r[2] << 16 | (uint32_t)r[3] << 24);
-          const int32_t pos = (int32_t)(r[4] | r[5] << 8 | r[6] << 16 | (uint32_t)r[7] << 24);
-          if (rtid != tid) { in[s].cur_tid_done = 1; break; }
-          if (pos >= ce - 1) break;
-          bq_plp_batch_push(bt, r, len, s);
-          bq_bam_skip(in[s].fp, len);
-        }
-      }
-      t_dec += now_s() - t0; t0 = now_s();
-      int64_t n_loci = 0;
-      if (bt->n > 0) {
-        bsq_plp_reads view;
-        bq_plp_batch_view(bt, &view);
-        if ((rc = bsq_plp_stage(plp, &view))) bq_fatal("[pileup] bsq_plp_stage: %s (%s)\n", bsq_strerror(rc), bsq_last_error());
-        if ((rc = bsq_plp_run(plp, &conf.filt, (int32_t)cb, (int32_t)ce, &n_loci))) bq_fatal("[pileup] bsq_plp_run: %s (%s)\n", bsq_strerror(rc), bsq_last_error());
-        if (n_loci > recs_cap) { recs_cap = n_loci * 5 / 4 + 1024; free(recs); recs = malloc((size_t)recs_cap * nb * sizeof *recs); }
-        if (n_loci > 0 && (rc = bsq_plp_fetch(plp, recs))) bq_fatal("[pileup] bsq_plp_fetch: %s (%s)\n", bsq_strerror(rc), bsq_last_error());
-      }
-      t_gpu += now_s() - t0; t0 = now_s();
-      tot_reads += bt->n; tot_loci += ce - cb; tot_emit += n_loci;
-      const int n_win = (int)((ce - cb + conf.step - 1) / conf.step);
-      if (n_loci > 0) {
-        memset(wbeta, 0, (size_t)n_win * nb * BQ_NCTX * sizeof(double));
-        memset(wcnt, 0, (size_t)n_win * nb * BQ_NCTX * sizeof(int64_t));
-        text.l = 0;
-        bq_plp_format(&fcf, hdr.name[tid], recs, n_loci, cb, conf.step, n_win, &text, wbeta, wcnt);
-        t_fmt += now_s() - t0; t0 = now_s();
-        if (text.l && fwrite(text.s, 1, text.l, out) != text.l && errno == EPIPE) exit(1);
-        for (int w = 0; w < n_win; ++w) /* one record per window, added in block order */
-          for (int s = 0; s < nb; ++s)
-            for (int i = 0; i < BQ_NCTX; ++i) {
-              betasum[s * smpl_block + tid * BQ_NCTX + i] += wbeta[((size_t)w * nb + s) * BQ_NCTX + i];
-              cnt[s * smpl_block + tid * BQ_NCTX + i] += wcnt[((size_t)w * nb + s) * BQ_NCTX + i];
-            }
-        t_wr += now_s() - t0;
-      }
-      /* carry the reads that reach into the next chunk */
-      bq_plp_batch_t *nx = &B[cur ^ 1];
-      bq_plp_batch_reset(nx);
-      for (int64_t i = 0; i < bt->n; ++i)
-        if (bt->end[i] >= ce) bq_plp_batch_copy1(nx, bt, i);
-      cur ^= 1;
-      if (progress) fprintf(stderr, "[pileup] %s:%ld-%ld reads %ld emitted %ld\n", hdr.name[tid], (long)cb, (long)ce, (long)bt->n, (long)n_loci);
+    int64_t n_loci = 0;
+    const int64_t n_reads_chunk = bt->n;
+    if (bt->n > 0) {
+      bsq_plp_reads view;
+      bq_plp_batch_view(bt, &view);
+      if ((rc = bsq_plp_stage(plp, &view))) bq_fatal("[pileup] bsq_plp_stage: %s (%s)\n", bsq_strerror(rc), bsq_last_error());
+      if ((rc = bsq_plp_run(plp, &conf.filt, (int32_t)cb, (int32_t)ce, &n_loci))) bq_fatal("[pileup] bsq_plp_run: %s (%s)\n", bsq_strerror(rc), bsq_last_error());
     }
+    pq_put(&P.q_free_batches, bt); /* bsq_plp_run has synchronised: the staged copies are complete */
+    if (n_loci > recs_cap) {
+      if (recs) bsq_host_free(recs);
+      recs_cap = n_loci * 5 / 4 + 1024;
+      void *pp_ = 0;
+      if (bsq_host_alloc(&pp_, (size_t)recs_cap * nb * sizeof *recs)) bq_fatal("[pileup] out of page-locked memory\n");
+      recs = pp_;
+    }
+    if (n_loci > 0 && (rc = bsq_plp_fetch(plp, recs))) bq_fatal("[pileup] bsq_plp_fetch: %s (%s)\n", bsq_strerror(rc), bsq_last_error());
+    t_gpu += now_s() - t0; t0 = now_s();
+    tot_reads += n_reads_chunk; tot_loci += ce - cb; tot_emit += n_loci;
+    const int n_win = (int)((ce - cb + conf.step - 1) / conf.step);
+    if (n_loci > 0) {
+      memset(wbeta, 0, (size_t)n_win * nb * BQ_NCTX * sizeof(double));
+      memset(wcnt, 0, (size_t)n_win * nb * BQ_NCTX * sizeof(int64_t));
+      text_msg_t *tm = pq_get(&P.q_free_text);
+      tm->text.l = 0;
+      bq_plp_format(&fcf, hdr.name[tid], recs, n_loci, cb, conf.step, n_win, &tm->text, wbeta, wcnt);
+      pq_put(&P.q_text, tm);
+      for (int w = 0; w < n_win; ++w) /* one record per window, added in block order (write_func) */
+        for (int s = 0; s < nb; ++s)
+          for (int i = 0; i < BQ_NCTX; ++i) {
+            betasum[s * smpl_block + tid * BQ_NCTX + i] += wbeta[((size_t)w * nb + s) * BQ_NCTX + i];
+            cnt[s * smpl_block + tid * BQ_NCTX + i] += wcnt[((size_t)w * nb + s) * BQ_NCTX + i];
+          }
+      t_fmt += now_s() - t0;
+    }
+    if (progress) fprintf(stderr, "[pileup] %s:%ld-%ld reads %ld emitted %ld\n", hdr.name[tid], (long)cb, (long)ce, (long)n_reads_chunk, (long)n_loci);
+    free(m);
   }
+  {
+    text_msg_t *e = calloc(1, sizeof *e);
+    e->end = 1;
+    pq_put(&P.q_text, e);
+  }
+  pthread_join(th_dec, 0); pthread_join(th_wr, 0);
+  const double t_dec = P.t_dec, t_wr = P.t_wr;
 
   if (!statsfn && outfn) statsfn = strdup(outfn);
   if (statsfn) { /* src/pileup.c:201-222 */
@@ -713,13 +830,15 @@ int bq_main_pileup(int argc, char **argv) {
     free(fn);
   }
   if (progress || getenv("BSQ_PLP_TIMING"))
-    fprintf(stderr, "[pileup] reads %ld loci %ld emitted %ld | decode %.2fs gpu %.2fs format %.2fs write %.2fs\n", (long)tot_reads, (long)tot_loci,
-            (long)tot_emit, t_dec, t_gpu, t_fmt, t_wr);
+    fprintf(stderr, "[pileup] reads %ld loci %ld emitted %ld | decode %.2fs (thread) | wait %.2fs gpu %.2fs format %.2fs | write %.2fs (thread)\n",
+            (long)tot_reads, (long)tot_loci, (long)tot_emit, t_dec, t_wait, t_gpu, t_fmt, t_wr);
   if (outfn) fclose(out); else fflush(out);
   bsq_plp_destroy(plp);
   for (int s = 0; s < nb; ++s) { bq_bgzf_close(in[s].fp); bq_bai_free(&in[s].bai); }
-  bq_plp_batch_free(&B[0]); bq_plp_batch_free(&B[1]);
-  free(recs); free(wbeta); free(wcnt); free(text.s); free(betasum); free(cnt); free(work); free(targets); free(statsfn);
+  for (int i = 0; i < 4; ++i) bq_plp_batch_free(&B[i]);
+  for (int i = 0; i < 3; ++i) { free(texts[i]->text.s); free(texts[i]); }
+  if (recs) bsq_host_free(recs);
+  free(wbeta); free(wcnt); free(betasum); free(cnt); free(work); free(targets); free(statsfn);
   bq_fasta_free(&fa);
   bq_bam_hdr_free(&hdr);
   return 0;

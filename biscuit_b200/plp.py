@@ -84,3 +84,54 @@ class Pileup:
     def region(self, conf: Conf, rd: dict, beg: int, end: int) -> np.ndarray:
         self.stage(rd)
         return self.fetch(self.run(conf, beg, end))
+
+
+# ---- multi-GPU: the only cross-rank state of the pileup path -------------------------------
+def context_stats(recs: np.ndarray, n_bams: int, pos0: int = 1, step: int = 100000):
+    """Per-sample methylation statistics of emitted records, as write_func accumulates them (src/pileup.c:178-185):
+    cnt[sid, ctx] (int64) and betasum[sid, ctx] (float64) over the 6 cytosine contexts.  betasum is summed per
+    window of `step` loci in locus order and the windows are then added in order, like the reference's records."""
+    cnt = np.zeros((n_bams, 6), np.int64)
+    beta = np.zeros((n_bams, 6), np.float64)
+    if len(recs) == 0:
+        return cnt, beta
+    r = recs.reshape(-1, n_bams)
+    win = (r["pos"][:, 0].astype(np.int64) - pos0) // step
+    for s in range(n_bams):
+        q = r[:, s]
+        ok = (q["methcallable"] != 0) & (q["ctx"] < 6)
+        ret = q["meth"][:, 0].astype(np.float64)
+        tot = (q["meth"][:, 0] + q["meth"][:, 1]).astype(np.float64)
+        b = np.divide(ret, tot, out=np.zeros_like(ret), where=ok)
+        for ctx in range(6):
+            m = ok & (q["ctx"] == ctx)
+            cnt[s, ctx] = int(m.sum())
+            acc = 0.0
+            for w in np.unique(win[m]):
+                part = 0.0
+                for v in b[m & (win == w)]:  # locus order inside the window
+                    part += float(v)
+                acc += part
+            beta[s, ctx] = acc
+    return cnt, beta
+
+
+def merge_stats(cnt: np.ndarray, beta: np.ndarray, device=None):
+    """Final reduce across ranks (torch.distributed; NCCL over NVLink when `device` is a CUDA device, gloo on CPU).
+    cnt / beta: [n_contigs_total, n_bams, 6] with zeros for the contigs this rank did not process.
+    Integer counts: one all_reduce(SUM).  The double sums are all-gathered and added in rank order on every rank, so
+    the `%1.3f` figures of <out>_meth_average.tsv do not depend on the reduction tree."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return cnt.copy(), beta.copy()
+    dev = torch.device(device) if device is not None else torch.device("cpu")
+    c = torch.from_numpy(np.ascontiguousarray(cnt)).to(dev)
+    dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    b = torch.from_numpy(np.ascontiguousarray(beta)).to(dev)
+    parts = [torch.empty_like(b) for _ in range(dist.get_world_size())]
+    dist.all_gather(parts, b)
+    tot = torch.zeros_like(b)
+    for p in parts:  # fixed order
+        tot += p
+    return c.cpu().numpy(), tot.cpu().numpy()

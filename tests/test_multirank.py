@@ -64,3 +64,46 @@ def test_two_ranks_gloo(tmp_path):
     import conftest
     lib = conftest.build_hostemu()
     mp.spawn(_worker, args=(2, _free_port(), lib, str(tmp_path)), nprocs=2, join=True)
+
+
+def _plp_worker(rank, world, port, out_dir):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools")]
+    import torch.distributed as dist
+    import oracle_plp
+    import synth
+    import synth_plp
+    from biscuit_b200 import plp
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # two contigs, one per rank (pileup shards by contig / window; records are per-rank, only the statistics meet)
+    contigs = [synth.make_reference(60_000, 1, seed=11 + i)[0][1] for i in range(world)]
+    reads = [synth_plp.make_reads(c, 1200, seed=21 + i, noise=True) for i, c in enumerate(contigs)]
+    conf = oracle_plp.conf_default()
+    cnt = np.zeros((world, 1, 6), np.int64)
+    beta = np.zeros((world, 1, 6))
+    recs = oracle_plp.region(conf, contigs[rank], reads[rank], 1, len(contigs[rank]), 1)  # stands in for the GPU records (same layout)
+    cnt[rank], beta[rank] = plp.context_stats(recs, 1)
+    mc, mb = plp.merge_stats(cnt, beta)
+    if rank == 0:
+        exp_c = np.zeros_like(cnt)
+        exp_b = np.zeros_like(beta)
+        for i in range(world):
+            r = oracle_plp.region(conf, contigs[i], reads[i], 1, len(contigs[i]), 1)
+            exp_c[i], exp_b[i] = plp.context_stats(r, 1)
+        assert (mc == exp_c).all() and mc.sum() > 1000
+        assert mb.tobytes() == exp_b.tobytes()
+        # and context_stats agrees with the reference-order accumulation of the oracle's text restatement
+        import test_pileup_cli
+        _, ob, oc = test_pileup_cli.oracle_vcf(oracle_plp.region(conf, contigs[0], reads[0], 1, len(contigs[0]), 1), "c", 1)
+        assert oc.tolist() == exp_c[0, 0].tolist() and ob.tobytes() == exp_b[0, 0].tobytes()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_pileup_stats_reduce_two_ranks_gloo(tmp_path):
+    import torch.multiprocessing as mp
+    import oracle_plp
+    if not oracle_plp.available():
+        pytest.skip("oracle not built")
+    mp.spawn(_plp_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
