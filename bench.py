@@ -38,6 +38,17 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 METRIC = "bisulfite_2x150_reads_per_s_aligned"
+_JSON_FD = None
+
+
+def emit(line: dict):
+    """The one JSON line of the bench contract, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def log(*a):
@@ -364,7 +375,7 @@ def bench_pileup(args):
                          "frac": alg / (kus[0] * 1e-6) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                          "kernel_ms": kus[0] / 1000, "locus_kernels_ms": kus[1] / 1000, "events": int(c[3])},
             "cpu_baseline": cpu}
-    print(json.dumps(line), flush=True)
+    emit(line)
     pl.close()
     if world > 1:
         dist.barrier()
@@ -373,6 +384,11 @@ def bench_pileup(args):
 
 
 def main():
+    # stdout carries exactly one JSON line: libraries that print banners (e.g. NCCL with NCCL_DEBUG set) go to stderr
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--path", default="align", choices=["align", "pileup"])
     ap.add_argument("--plp-mb", type=float, default=20.0)
@@ -404,6 +420,8 @@ def main():
     torch.cuda.set_device(local_rank)
     peak, peak_src = load_peaks()
     ncores = os.cpu_count() or 1
+    if args.impl == "ours":
+        ncores = max(1, ncores // world)  # the host cores are shared by the ranks of the node
 
     t0 = time.time()
     nt4, pac, names, offs, lens = gen_reference(args.ref_mb)
@@ -436,7 +454,7 @@ def main():
                 "cpu_baseline": {"value": v, "unit": "reads/s", "cores": ncores, "kind": "reference",
                                  "sample": f"{args.cpu_pairs} pairs per step through oracle/_ref mem_process_seqs"},
                 "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return 0
 
     # ---------------- ours ----------------
@@ -643,7 +661,7 @@ def main():
                 "e2e_phase1": {"value": e2e_phase1, "unit": "reads/s", "note": "C ABI with pinned host buffers: H2D + kernels + D2H of regions"},
                 "gpu_launches": 12 * args.steps, "roofline": roof, "cpu_baseline": cpu,
                 "kernel_us_per_step": dict(zip(stage_names, [float(x) for x in kern_us]))}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

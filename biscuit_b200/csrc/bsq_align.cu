@@ -280,6 +280,7 @@ struct bsq_cw_warp {
   __device__ static void sync() { __syncwarp(); }
   __device__ static int first_true(bool p) { unsigned b = __ballot_sync(0xffffffffu, p); return b ? __ffs(b) - 1 : -1; }
   __device__ static bool any(bool p) { return __any_sync(0xffffffffu, p); }
+  __device__ static int sum(int v) { return __reduce_add_sync(0xffffffffu, v); }
   // bitonic sort of n <= BSQ_CW_CAP keys in shared memory (keys are unique, so the result is the total order)
   __device__ static void sort_keys(uint64_t *k, int n) {
     const int lane = threadIdx.x & 31;
@@ -369,6 +370,7 @@ __global__ void __launch_bounds__(128, 8) k_region(const __grid_constant__ bsq_d
                                                 const int32_t *lens, const uint8_t *parent, const int64_t *sa_off,
                                                 const bsq_chain_t *ochains, const bsq_seed_t *oseeds, const int32_t *n_chains,
                                                 const float *frac_rep, uint64_t *srt, bsq_reg_t *regs_tmp, int32_t *n_regs) {
+  bsq_gap_tab_init(opt);
   const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (t >= n_tasks) return;  // whole warps leave together
   const int64_t wo = ws_off(sa_off, t);

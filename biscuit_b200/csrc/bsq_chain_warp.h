@@ -60,6 +60,7 @@ struct bsq_cw_scalar {
   BSQ_HD static void sync() {}
   BSQ_HD static int first_true(bool p) { return p ? 0 : -1; }
   BSQ_HD static bool any(bool p) { return p; }
+  BSQ_HD static int sum(int v) { return v; }
   BSQ_HD static void sort_keys(uint64_t *k, int n) {
     for (int i = 1; i < n; ++i) { uint64_t v = k[i]; int j = i; while (j > 0 && k[j - 1] > v) { k[j] = k[j - 1]; --j; } k[j] = v; }
   }
@@ -158,56 +159,76 @@ BSQ_HD int bsq_chain_warp(const bsq_devopt_t &opt, const bsq_devidx_t &ix, int p
   // ---- 2. order by reference position ----
   W::sort_keys(s.key, n_sa);
   W::sync();
-  // ---- 3. clusters, replay of the merge rule (lane 0) ----
+  // ---- 3. clusters, replay of the merge rule: one cluster per lane at a time ----
+  // Cluster [u, j) of the sorted keys keeps its chains (in position order) in clist[u, u + nc) and its arrival-order
+  // scratch in ord[u, j): private ranges, and all chain state is indexed by seed, so clusters never touch the same
+  // entry.  keep[u] = nc at cluster starts, 0 elsewhere; lane 0 then compacts clist left to right.
   const int64_t G = (int64_t)BSQ_MAX_READ_LEN + opt.w + 1;
-  int n_ch = 0, dup = 0;
-  if (lane == 0) {
-    int n_valid = n_sa;
-    while (n_valid > 0 && s.key[n_valid - 1] == ~0ull) --n_valid;
-    int i = 0;
-    while (i < n_valid && !dup) {
-      int j = i + 1;
-      while (j < n_valid && (int64_t)(s.key[j] >> 10) - (int64_t)(s.key[j - 1] >> 10) < G) ++j;
-      const int cl0 = n_ch;
-      // members in arrival order: insertion sort of the arrival indices of key[i..j)
-      for (int u = i; u < j; ++u) s.ord[u] = (uint16_t)(s.key[u] & 1023);
-      for (int u = i + 1; u < j; ++u) { uint16_t v = s.ord[u]; int t = u; while (t > i && s.ord[t - 1] > v) { s.ord[t] = s.ord[t - 1]; --t; } s.ord[t] = v; }
-      for (int u = i; u < j; ++u) {
-        const int a = s.ord[u];
-        int p = cl0 - 1;  // predecessor inside the cluster (cl0 - 1: none)
-        for (int c = cl0; c < n_ch; ++c) { if (s.rbeg[s.clist[c]] <= s.rbeg[a]) p = c; else break; }
-        if (p >= cl0 && bsq_cw_merge(opt, ix.l_pac, s, s.clist[p], a)) continue;
-        if (p >= cl0 && s.rbeg[s.clist[p]] == s.rbeg[a]) { dup = 1; break; }  // (F3)
-        for (int c = n_ch; c > p + 1; --c) s.clist[c] = s.clist[c - 1];
-        s.clist[p + 1] = (uint16_t)a;
-        ++n_ch;
-        s.c_last_rbeg[a] = s.rbeg[a]; s.c_last_q[a] = s.qbeg[a]; s.c_last_len[a] = s.slen[a];
-        s.c_tail[a] = (uint16_t)a; s.c_n[a] = 1; s.c_xhead[a] = s.c_xtail[a] = (uint16_t)BSQ_CW_NONE; s.c_xn[a] = 0;
-      }
-      i = j;
-    }
-    // ---- 4a. weights + order for the filter ----
-    if (!dup) {
-      int k = 0;
-      for (int c = 0; c < n_ch; ++c) {
-        const int a = s.clist[c];
-        s.c_first[a] = -1; s.c_kept[a] = 0;
-        s.c_w[a] = bsq_cw_weight(s, a);
-        if (s.c_w[a] >= opt.min_chain_weight) s.key[k++] = (uint64_t)(uint32_t)s.c_w[a] << 16 | (uint64_t)a;
-      }
-      n_ch = k;
-      bsq_introsort(s.key, (int64_t)n_ch, bsq_cw_by_weight());
-      for (int c = 0; c < n_ch; ++c) s.ord[c] = (uint16_t)(s.key[c] & 0xffff);
-      if (n_ch > 0) { s.c_kept[s.ord[0]] = 3; s.keep[0] = 0; }
-    }
-    s.pub[0] = dup ? -1 : n_ch;
+  int n_ch = 0;
+  int n_valid;
+  {
+    int nv = 0;
+    for (int u = lane; u < n_sa; u += NL) { nv += s.key[u] != ~0ull; s.keep[u] = 0; }
+    n_valid = W::sum(nv);  // dropped seeds sort to the end
   }
   W::sync();
-  {
-    const int v = s.pub[0];
-    if (v < 0) return BSQ_CW_FALLBACK;
-    n_ch = v;
+  bool dup = false;
+  for (int u = lane; u < n_valid; u += NL) {
+    if (u > 0 && (int64_t)(s.key[u] >> 10) - (int64_t)(s.key[u - 1] >> 10) < G) continue;  // not a cluster start
+    int j = u + 1;
+    while (j < n_valid && (int64_t)(s.key[j] >> 10) - (int64_t)(s.key[j - 1] >> 10) < G) ++j;
+    const int cl0 = u;
+    int nc = cl0;  // end of this cluster's chain list
+    // members in arrival order: insertion sort of the arrival indices of key[u..j)
+    for (int v = u; v < j; ++v) s.ord[v] = (uint16_t)(s.key[v] & 1023);
+    for (int v = u + 1; v < j; ++v) { uint16_t x = s.ord[v]; int t = v; while (t > u && s.ord[t - 1] > x) { s.ord[t] = s.ord[t - 1]; --t; } s.ord[t] = x; }
+    for (int v = u; v < j && !dup; ++v) {
+      const int a = s.ord[v];
+      int p = cl0 - 1;  // predecessor inside the cluster (cl0 - 1: none)
+      for (int c = cl0; c < nc; ++c) { if (s.rbeg[s.clist[c]] <= s.rbeg[a]) p = c; else break; }
+      if (p >= cl0 && bsq_cw_merge(opt, ix.l_pac, s, s.clist[p], a)) continue;
+      if (p >= cl0 && s.rbeg[s.clist[p]] == s.rbeg[a]) { dup = true; break; }  // (F3)
+      for (int c = nc; c > p + 1; --c) s.clist[c] = s.clist[c - 1];
+      s.clist[p + 1] = (uint16_t)a;
+      ++nc;
+      s.c_last_rbeg[a] = s.rbeg[a]; s.c_last_q[a] = s.qbeg[a]; s.c_last_len[a] = s.slen[a];
+      s.c_tail[a] = (uint16_t)a; s.c_n[a] = 1; s.c_xhead[a] = s.c_xtail[a] = (uint16_t)BSQ_CW_NONE; s.c_xn[a] = 0;
+    }
+    s.keep[u] = (uint16_t)(nc - cl0);
   }
+  if (W::any(dup)) return BSQ_CW_FALLBACK;
+  W::sync();
+  if (lane == 0) {  // compaction (destination never passes the source)
+    int k = 0;
+    for (int u = 0; u < n_valid; ++u) {
+      const int nc = s.keep[u];
+      for (int c = 0; c < nc; ++c) s.clist[k++] = s.clist[u + c];
+    }
+    s.pub[0] = k;
+  }
+  W::sync();
+  n_ch = s.pub[0];
+  // ---- 4a. weights (one chain per lane), then the order for the filter (lane 0: exact introsort) ----
+  for (int c = lane; c < n_ch; c += NL) {
+    const int a = s.clist[c];
+    s.c_first[a] = -1; s.c_kept[a] = 0;
+    s.c_w[a] = bsq_cw_weight(s, a);
+  }
+  W::sync();
+  if (lane == 0) {
+    int k = 0;
+    for (int c = 0; c < n_ch; ++c) {
+      const int a = s.clist[c];
+      if (s.c_w[a] >= opt.min_chain_weight) s.key[k++] = (uint64_t)(uint32_t)s.c_w[a] << 16 | (uint64_t)a;
+    }
+    n_ch = k;
+    bsq_introsort(s.key, (int64_t)n_ch, bsq_cw_by_weight());
+    for (int c = 0; c < n_ch; ++c) s.ord[c] = (uint16_t)(s.key[c] & 0xffff);
+    if (n_ch > 0) { s.c_kept[s.ord[0]] = 3; s.keep[0] = 0; }
+    s.pub[0] = n_ch;
+  }
+  W::sync();
+  n_ch = s.pub[0];
   if (n_ch == 0) return BSQ_CW_OK;
   // ---- 4b. greedy overlap filter (memchain.c:427-457); inner loop over the kept chains spread over the lanes ----
   int n_keep = 1;
@@ -265,21 +286,31 @@ BSQ_HD int bsq_chain_warp(const bsq_devopt_t &opt, const bsq_devidx_t &ix, int p
       }
       for (; i < n_ch; ++i) if (s.c_kept[s.ord[i]] < 3) s.c_kept[s.ord[i]] = 0;
     }
+    // output slots: keep[o] = chain, iv_off[o] = first seed slot of output chain o
     int n_out = 0, s_out = 0;
     for (int i = 0; i < n_ch; ++i) {
       const int c = s.ord[i];
       if (s.c_kept[c] == 0) continue;
-      bsq_chain_t &o = out_chains[n_out++];
-      o.pos = s.rbeg[c]; o.rid = s.rid[c]; o.w = s.c_w[c]; o.first = s.c_first[c]; o.kept = s.c_kept[c];
-      o.is_alt = s.c_alt[c];
-      o.seed_off = s_out; o.n_seeds = s.c_n[c]; o.n_extra = s.c_xn[c];
-      for (int q = 0; q < 6; ++q) o.pad_[q] = 0;
-      for (int j = c; j != (int)BSQ_CW_NONE; j = s.next[j]) { bsq_seed_t &d = out_seeds[s_out++]; d.rbeg = s.rbeg[j]; d.qbeg = s.qbeg[j]; d.len = s.slen[j]; }
-      for (int j = s.c_xn[c] ? s.c_xhead[c] : (int)BSQ_CW_NONE; j != (int)BSQ_CW_NONE; j = s.next[j]) {
-        bsq_seed_t &d = out_seeds[s_out++]; d.rbeg = s.rbeg[j]; d.qbeg = s.qbeg[j]; d.len = s.slen[j];
-      }
+      s.keep[n_out] = (uint16_t)c; s.iv_off[n_out] = (uint16_t)s_out;
+      ++n_out; s_out += s.c_n[c] + s.c_xn[c];
     }
-    res.n_chains = n_out; res.n_seeds = s_out;
+    s.pub[1] = n_out; s.pub[2] = s_out;
   }
+  W::sync();
+  const int n_out = s.pub[1];
+  for (int o_ = lane; o_ < n_out; o_ += NL) {  // emit, one chain per lane
+    const int c = s.keep[o_];
+    int s_out = s.iv_off[o_];
+    bsq_chain_t &o = out_chains[o_];
+    o.pos = s.rbeg[c]; o.rid = s.rid[c]; o.w = s.c_w[c]; o.first = s.c_first[c]; o.kept = s.c_kept[c];
+    o.is_alt = s.c_alt[c];
+    o.seed_off = s_out; o.n_seeds = s.c_n[c]; o.n_extra = s.c_xn[c];
+    for (int q = 0; q < 6; ++q) o.pad_[q] = 0;
+    for (int j = c; j != (int)BSQ_CW_NONE; j = s.next[j]) { bsq_seed_t &d = out_seeds[s_out++]; d.rbeg = s.rbeg[j]; d.qbeg = s.qbeg[j]; d.len = s.slen[j]; }
+    for (int j = s.c_xn[c] ? s.c_xhead[c] : (int)BSQ_CW_NONE; j != (int)BSQ_CW_NONE; j = s.next[j]) {
+      bsq_seed_t &d = out_seeds[s_out++]; d.rbeg = s.rbeg[j]; d.qbeg = s.qbeg[j]; d.len = s.slen[j];
+    }
+  }
+  res.n_chains = n_out; res.n_seeds = s.pub[2];
   return BSQ_CW_OK;
 }

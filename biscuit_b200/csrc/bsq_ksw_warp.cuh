@@ -155,8 +155,23 @@ __device__ __noinline__ bsq_ext_result_t bsq_ksw_extend_warp(int qlen, bsq_qacc_
   return r;
 }
 
+// cal_max_gap (memchain.c:576-582) depends on the query length only: one table per CTA instead of two integer
+// divisions per call (it is evaluated for every seed of every chain)
+__device__ __forceinline__ int32_t *bsq_gap_tab() {
+  __shared__ int32_t tab[BSQ_MAX_READ_LEN + 2];
+  return tab;
+}
+__device__ __forceinline__ void bsq_gap_tab_init(const bsq_devopt_t &opt) {  // all threads of the CTA
+  int32_t *t = bsq_gap_tab();
+  for (int q = threadIdx.x; q <= BSQ_MAX_READ_LEN; q += blockDim.x) t[q] = bsq_cal_max_gap(opt, q);
+  __syncthreads();
+}
+
 struct bsq_warp_policy {
   __device__ static bool leader() { return (threadIdx.x & 31) == 0; }
+  __device__ static int max_gap(const bsq_devopt_t &opt, int qlen) {
+    return (unsigned)qlen <= (unsigned)BSQ_MAX_READ_LEN ? bsq_gap_tab()[qlen] : bsq_cal_max_gap(opt, qlen);
+  }
   __device__ static void sync() { __syncwarp(); }
   // asymmetric_flt_seed (memchain.c:138-149), 32 seed positions per step
   __device__ static bool asym_conflict(const bsq_devidx_t &ix, const bsq_seed_t &s, const uint8_t *query) {

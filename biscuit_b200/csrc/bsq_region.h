@@ -51,6 +51,7 @@ struct bsq_tacc_t {
 // over the lanes.
 struct bsq_scalar_policy {
   BSQ_HD static bool leader() { return true; }
+  BSQ_HD static int max_gap(const bsq_devopt_t &opt, int qlen) { return bsq_cal_max_gap(opt, qlen); }
   BSQ_HD static void sync() {}
   // asymmetric_flt_seed (memchain.c:138-149): ref T under read C, or ref A under read G, inside the seed
   BSQ_HD static bool asym_conflict(const bsq_devidx_t &ix, const bsq_seed_t &s, const uint8_t *query) {
@@ -90,12 +91,12 @@ BSQ_HD void bsq_chain2region1(const bsq_devopt_t &opt, const bsq_devidx_t &ix, i
       if ((double)(s.len - reg.seedlen0) > .1 * l_query) continue;
       int qd = s.qbeg - reg.qb;
       int64_t rd = s.rbeg - reg.rb;
-      int max_gap = bsq_cal_max_gap(opt, (int)(qd < rd ? qd : rd));
+      int max_gap = X::max_gap(opt, (int)(qd < rd ? qd : rd));
       int w = max_gap < reg.w ? max_gap : reg.w;
       if (qd - rd < w && rd - qd < w) break;
       qd = reg.qe - (s.qbeg + s.len);
       rd = reg.re - (s.rbeg + s.len);
-      max_gap = bsq_cal_max_gap(opt, (int)(qd < rd ? qd : rd));
+      max_gap = X::max_gap(opt, (int)(qd < rd ? qd : rd));
       w = max_gap < reg.w ? max_gap : reg.w;
       if (qd - rd < w && rd - qd < w) break;
     }
@@ -199,8 +200,8 @@ BSQ_HD int bsq_chain2region(const bsq_devopt_t &opt, const bsq_devidx_t &ix, int
     int64_t rmax0 = l_pac << 1, rmax1 = 0;
     for (int i = 0; i < c.n_seeds; ++i) {
       const bsq_seed_t &s = cs[i];
-      int64_t b = s.rbeg - (s.qbeg + bsq_cal_max_gap(opt, s.qbeg));
-      int64_t e = s.rbeg + s.len + ((l_query - s.qbeg - s.len) + bsq_cal_max_gap(opt, l_query - s.qbeg - s.len));
+      int64_t b = s.rbeg - (s.qbeg + X::max_gap(opt, s.qbeg));
+      int64_t e = s.rbeg + s.len + ((l_query - s.qbeg - s.len) + X::max_gap(opt, l_query - s.qbeg - s.len));
       rmax0 = rmax0 < b ? rmax0 : b;
       rmax1 = rmax1 > e ? rmax1 : e;
     }
@@ -210,8 +211,9 @@ BSQ_HD int bsq_chain2region(const bsq_devopt_t &opt, const bsq_devidx_t &ix, int
       if (cs[0].rbeg < l_pac) rmax1 = l_pac; else rmax0 = l_pac;
     }
     // bns_fetch_seq: clip to the contig (and strand) that holds the first seed
-    int is_rev;
-    const int rid = bsq_pos2rid(ix, bsq_depos(ix, cs[0].rbeg, &is_rev));
+    // contig of the first seed: the chain record carries it (set from the same seed by the chaining kernels)
+    const int is_rev = cs[0].rbeg >= l_pac;
+    const int rid = c.rid;
     int64_t far_beg = ix.ann_offset[rid], far_end = far_beg + ix.ann_len[rid];
     if (is_rev) {
       int64_t t = far_beg;
