@@ -59,7 +59,7 @@ bool bsq_want_full_sa(uint64_t n, int halves_left) {
   if (e) return atoi(e) != 0;
   size_t free_b = 0, total_b = 0;
   if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return false;
-  const double need = (double)halves_left * (double)(n + 1) * 8.0 + 40e9;
+  const double need = (double)halves_left * (double)(n + 1) * 8.0 + 40e9;  // leaves room for two aligner contexts
   return (double)free_b > need;
 }
 
@@ -108,6 +108,7 @@ struct bsq_aligner {
   DevBuf cub_tmp, scalars, fb_flag, tiers;
   int64_t counters[16];
   int64_t n_staged = 0, n_regs_total = -1;
+  int64_t fb_cap = 0;  // entries of the fallback-chaining workspace pools
   int32_t stride = 0;
 };
 
@@ -253,24 +254,31 @@ __global__ void k_occ4(bsq_devidx_t ix, int which, int64_t n, const uint64_t *k,
 // per-task workspace offset: sa_off[t] + t * BSQ_TAIL_SLACK entries
 __device__ __forceinline__ int64_t ws_off(const int64_t *sa_off, int64_t t) { return sa_off[t] + t * BSQ_TAIL_SLACK; }
 
-__global__ void __launch_bounds__(128) k_chain(const __grid_constant__ bsq_devopt_t opt, const __grid_constant__ bsq_devidx_t ix, int64_t n_tasks, const int32_t *lens,
-                                               const uint8_t *parent, const bsq_pk_t *intv, const int32_t *n_intv,
+// Exact chaining (B-tree replay), one thread per task, only for the tasks k_chain_warp flagged (fb_flag == 1).  Their
+// workspaces come from a small pool by bump allocation (the flagged tasks are a handful per batch); if the pool is
+// too small the task stays flagged and status bit 4 asks the host to retry with a larger pool -- nothing is dropped.
+__global__ void __launch_bounds__(128) k_chain(const __grid_constant__ bsq_devopt_t opt, const __grid_constant__ bsq_devidx_t ix, int64_t n_tasks,
+                                               const int32_t *lens, const uint8_t *parent, const bsq_pk_t *intv, const int32_t *n_intv,
                                                const int64_t *sa_off, const uint64_t *pos, bsq_snode_t *snodes,
-                                               bsq_wchain_t *wchains, bsq_bnode_t *bnodes, int32_t *order, bsq_chain_t *ochains,
+                                               bsq_wchain_t *wchains, bsq_bnode_t *bnodes, int32_t *order, int64_t fb_cap,
+                                               unsigned long long *fb_cursor, bsq_chain_t *ochains,
                                                bsq_seed_t *oseeds, int32_t *n_chains, float *frac_rep, int32_t *status,
-                                               const uint8_t *only_flagged) {
+                                               uint8_t *fb_flag) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_tasks) return;
-  if (only_flagged && !only_flagged[t]) return;  // already done by k_chain_warp
+  if (fb_flag[t] != 1) return;  // done by k_chain_warp (0) or by an earlier pass of this kernel (2)
   const int64_t wo = ws_off(sa_off, t);
   bsq_chain_ws_t ws;
   ws.cap = (int32_t)(sa_off[t + 1] - sa_off[t]) + BSQ_TAIL_SLACK;
-  ws.snodes = snodes + wo; ws.chains = wchains + wo; ws.bnodes = bnodes + wo + 2 * t; ws.order = order + wo;
+  const int64_t fo = (int64_t)atomicAdd(fb_cursor, (unsigned long long)(ws.cap + 2));
+  if (fo + ws.cap + 2 > fb_cap) { atomicOr(status, 4); return; }
+  ws.snodes = snodes + fo; ws.chains = wchains + fo; ws.bnodes = bnodes + fo; ws.order = order + fo;
   bsq_chain_result_t r = bsq_chain_task(opt, ix, parent[t], lens[t], intv + t * BSQ_MAX_INTV, n_intv[t], pos + sa_off[t], ws,
                                         ochains + wo, oseeds + wo);
   if (r.status) { atomicOr(status, 2); r.n_chains = 0; }
   n_chains[t] = r.n_chains;
   frac_rep[t] = r.frac_rep;
+  fb_flag[t] = 2;
 }
 
 // warp policy of bsq_chain_warp
@@ -673,8 +681,12 @@ static int phase1_device(bsq_aligner *al, int64_t n, int32_t stride, int64_t *to
   if ((rc = scan_counts(al, al->n_sa.as<int32_t>(), al->sa_off.as<int64_t>(), n, &total_sa))) return rc;
   const int64_t pool = total_sa + n * BSQ_TAIL_SLACK;
   RES(ranks, (total_sa + 1) * 8); RES(pos, (total_sa + 1) * 8);
-  RES(snodes, pool * sizeof(bsq_snode_t)); RES(wchains, pool * sizeof(bsq_wchain_t));
-  RES(bnodes, (pool + 2 * n) * sizeof(bsq_bnode_t)); RES(order, pool * 4);
+  // workspace of the exact fallback chaining: small by default (bump-allocated to the few flagged tasks)
+  int64_t fb_cap = pool / 16 + 65536;
+  if (al->fb_cap > fb_cap) fb_cap = al->fb_cap;  // keep a pool that was grown earlier
+  al->fb_cap = fb_cap;
+  RES(snodes, fb_cap * sizeof(bsq_snode_t)); RES(wchains, fb_cap * sizeof(bsq_wchain_t));
+  RES(bnodes, fb_cap * sizeof(bsq_bnode_t)); RES(order, fb_cap * 4);
   RES(ochains, pool * sizeof(bsq_chain_t)); RES(oseeds, pool * sizeof(bsq_seed_t));
   RES(srt, pool * 8); RES(regs_tmp, pool * sizeof(bsq_reg_t));
   CK(cudaEventRecord(al->ev[2], s));
@@ -708,13 +720,29 @@ static int phase1_device(bsq_aligner *al, int64_t n, int32_t stride, int64_t *to
 #undef CW_LAUNCH
     CK(cudaEventRecord(al->ev[7], s));
   }
-  k_chain<<<nblk(n, 128), 128, 0, s>>>(opt, ix, n, al->lens.as<int32_t>(), al->parent.as<uint8_t>(), al->intv.as<bsq_pk_t>(),
-                                        al->n_intv.as<int32_t>(), al->sa_off.as<int64_t>(), al->pos.as<uint64_t>(),
-                                        al->snodes.as<bsq_snode_t>(), al->wchains.as<bsq_wchain_t>(), al->bnodes.as<bsq_bnode_t>(),
-                                        al->order.as<int32_t>(), al->ochains.as<bsq_chain_t>(), al->oseeds.as<bsq_seed_t>(),
-                                        al->n_chains.as<int32_t>(), al->frac_rep.as<float>(), al->status.as<int32_t>(),
-                                        al->fb_flag.as<uint8_t>());
-  CK(cudaGetLastError());
+  for (int pass = 0; pass < 2; ++pass) {
+    unsigned long long *fb_cursor = al->scalars.as<unsigned long long>() + 6;
+    k_chain<<<nblk(n, 128), 128, 0, s>>>(opt, ix, n, al->lens.as<int32_t>(), al->parent.as<uint8_t>(), al->intv.as<bsq_pk_t>(),
+                                          al->n_intv.as<int32_t>(), al->sa_off.as<int64_t>(), al->pos.as<uint64_t>(),
+                                          al->snodes.as<bsq_snode_t>(), al->wchains.as<bsq_wchain_t>(), al->bnodes.as<bsq_bnode_t>(),
+                                          al->order.as<int32_t>(), fb_cap, fb_cursor, al->ochains.as<bsq_chain_t>(),
+                                          al->oseeds.as<bsq_seed_t>(), al->n_chains.as<int32_t>(), al->frac_rep.as<float>(),
+                                          al->status.as<int32_t>(), al->fb_flag.as<uint8_t>());
+    CK(cudaGetLastError());
+    int32_t st_now = 0;
+    CK(cudaMemcpyAsync(&st_now, al->status.p, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (!(st_now & 4)) break;
+    if (pass == 1) { snprintf(g_err, sizeof g_err, "fallback chaining workspace exhausted twice"); return BSQ_EOVERFLOW; }
+    // many flagged tasks (e.g. repeats with more than max_occ occurrences): give the fallback the full-size pool and redo the rest
+    fb_cap = al->fb_cap = pool + 2 * n;
+    RES(snodes, fb_cap * sizeof(bsq_snode_t)); RES(wchains, fb_cap * sizeof(bsq_wchain_t));
+    RES(bnodes, fb_cap * sizeof(bsq_bnode_t)); RES(order, fb_cap * 4);
+    st_now &= ~4;
+    CK(cudaMemcpyAsync(al->status.p, &st_now, 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(fb_cursor, 0, 8, s));
+    CK(cudaStreamSynchronize(s));
+  }
   CK(cudaEventRecord(al->ev[4], s));
   k_region<<<nblk(n * 32, 128), 128, 0, s>>>(opt, ix, n, al->seqs.as<uint8_t>(), stride, al->lens.as<int32_t>(), al->parent.as<uint8_t>(),
                                          al->sa_off.as<int64_t>(), al->ochains.as<bsq_chain_t>(), al->oseeds.as<bsq_seed_t>(),
@@ -736,7 +764,7 @@ static int phase1_device(bsq_aligner *al, int64_t n, int32_t stride, int64_t *to
   al->counters[14] = (int64_t)n_fb;  // tasks chained by the exact fallback kernel
   { float w_ms = 0; cudaEventElapsedTime(&w_ms, al->ev[3], al->ev[7]); al->counters[15] = (int64_t)(w_ms * 1000); }
 #undef RES
-  if (st) { snprintf(g_err, sizeof g_err, "device status 0x%x (1: interval list, 2: chain workspace)", st); return BSQ_EOVERFLOW; }
+  if (st) { snprintf(g_err, sizeof g_err, "device status 0x%x (1: interval list, 2: chain workspace, 4: fallback pool)", st); return BSQ_EOVERFLOW; }
   float ms[6];
   for (int i = 0; i < 6; ++i) cudaEventElapsedTime(&ms[i], al->ev[i], al->ev[i + 1]);
   { float tot; cudaEventElapsedTime(&tot, al->ev[0], al->ev[6]); al->counters[10] = (int64_t)(tot * 1000); }

@@ -10,7 +10,7 @@
 typedef struct {
   bq_opt_t opt;
   bq_ref_t ref;
-  bsq_aligner *al;
+  bsq_aligner *al, *al2;
 } bq_session;
 
 bq_session *bq_session_create(bsq_index *dx, const uint8_t *pac, int64_t l_pac, int n_seqs, const char *const *names, const int64_t *offs,
@@ -30,12 +30,14 @@ bq_session *bq_session_create(bsq_index *dx, const uint8_t *pac, int64_t l_pac, 
   bsq_opt d;
   bq_opt_to_dev(&s->opt, &d);
   if (bsq_aligner_create(dx, &d, &s->al)) { free(s->ref.anns); free(s); return 0; }
+  if (!getenv("BQ_TWO_CONTEXTS") || bsq_aligner_create(dx, &d, &s->al2)) s->al2 = 0; /* measured: no gain from a second context */
   return s;
 }
 
 void bq_session_destroy(bq_session *s) {
   if (!s) return;
   bsq_aligner_destroy(s->al);
+  if (s->al2) bsq_aligner_destroy(s->al2);
   for (int i = 0; i < s->ref.n_seqs; ++i) { free(s->ref.anns[i].name); free(s->ref.anns[i].anno); }
   free(s->ref.anns);
   free(s);
@@ -118,6 +120,6 @@ int64_t bq_session_align_stream(bq_session *s, int n_batches, int n, const uint8
   stream_t st;
   memset(&st, 0, sizeof st);
   st.n_batches = n_batches; st.n = n; st.stride = stride; st.seqs = seqs; st.quals = quals; st.lens = lens;
-  const int rc = bq_pipeline_run(&s->opt, &s->ref, s->al, stream_source, &st, stream_sink, &st, 0, "");
+  const int rc = bq_pipeline_run(&s->opt, &s->ref, s->al, s->al2, stream_source, &st, stream_sink, &st, 0, "");
   return rc ? rc : st.sam_bytes;
 }

@@ -231,6 +231,8 @@ int bq_main_align(int argc, char **argv) {
   bq_opt_to_dev(&opt, &dopt);
   bsq_aligner *al = 0;
   if ((rc = bsq_aligner_create(dx, &dopt, &al))) bq_fatal("bsq_aligner_create: %s", bsq_strerror(rc));
+  bsq_aligner *al2 = 0; /* second GPU context of the batch pipeline (bq_pipe.c) */
+  if (!getenv("BQ_TWO_CONTEXTS") || bsq_aligner_create(dx, &dopt, &al2)) al2 = 0; /* off by default: measured no gain */
   if (bq_verbose >= 3) fprintf(stderr, "[M::main_align] index loaded and staged on GPU %d in %.3f sec\n", device, now() - t0);
 
   bq_fastq_t *f1 = 0, *f2 = 0;
@@ -259,10 +261,11 @@ int bq_main_align(int argc, char **argv) {
     free(seqs);
   } else {
     src_ctx_t sc = {&opt, f1, f2, chunk, copy_comment};
-    if ((rc = bq_pipeline_run(&opt, &idx.ref, al, fastq_source, &sc, sam_sink, 0, pes0, rg_id)))
+    if ((rc = bq_pipeline_run(&opt, &idx.ref, al, al2, fastq_source, &sc, sam_sink, 0, pes0, rg_id)))
       bq_fatal("alignment batch failed: %s (%s)", bsq_strerror(rc), bsq_last_error());
   }
   bsq_aligner_destroy(al);
+  if (al2) bsq_aligner_destroy(al2);
   bsq_index_free(dx);
   bq_index_free(&idx);
   bq_fastq_close(f1); bq_fastq_close(f2);

@@ -940,10 +940,18 @@ int bq_batch_run(bsq_aligner *al, bq_batch_t *b) {
   int rc;
   int64_t n_regs = 0;
   if (b->nt == 0) { b->reg_off[0] = 0; return 0; }
+  const double t0 = getenv("BQ_TIMING") ? bq_now() : 0;
   if ((rc = bsq_aligner_stage(al, b->nt, b->slot->tseq, b->stride, b->tlen, b->par))) return rc;
+  const double t1 = t0 > 0 ? bq_now() : 0;
   if ((rc = bsq_aligner_run(al, &n_regs))) return rc;
+  const double t2 = t0 > 0 ? bq_now() : 0;
   if ((rc = slot_reserve(&b->slot->regs, &b->slot->regs_cap, (size_t)(n_regs + 1) * sizeof(bsq_reg)))) return rc;
   if ((rc = bsq_aligner_fetch(al, b->slot->regs, b->reg_off))) return rc;
+  if (t0 > 0) {
+    int64_t c[16];
+    bsq_aligner_counters(al, c, 16);
+    fprintf(stderr, "[bq_batch_run] stage %.4f run %.4f (kernels %.4f) fetch %.4f s\n", t1 - t0, t2 - t1, c[10] * 1e-6, bq_now() - t2);
+  }
   b->dregs = b->slot->regs;
   return 0;
 }

@@ -1,7 +1,8 @@
 /* bq_pipe.c -- three-stage batch pipeline of `biscuit align` on one GPU:
  *
  *   stage A (thread)  next batch of reads from the source + host preparation (clipping, task rows in page-locked memory)
- *   stage B (thread)  GPU: H2D, phase-1 kernels, D2H                                              (bq_batch_run)
+ *   stage B (1-2 threads, one GPU context each, batches alternate) GPU: H2D, phase-1 kernels, D2H  (bq_batch_run);
+ *                     with two contexts the copies and kernel tails of one batch overlap the kernels of the next
  *   stage C (caller)  host phase 2 on opt->n_threads threads
  *   stage D (thread)  the sink (SAM output, freeing the reads), batches in order
  *
@@ -42,10 +43,11 @@ static void q_get(q1_t *q, bq_batch_t **b, bq_read_t **seqs, int *n, int *rc, in
 
 typedef struct {
   const bq_opt_t *opt;
-  bsq_aligner *al;
+  bsq_aligner *al[2]; /* two GPU contexts: the copies of one batch overlap the kernels of the other */
+  int n_al;
   bq_source_fn src;
   void *src_ctx;
-  q1_t qa, qb, qc;
+  q1_t qa[2], qb[2], qc;
   int64_t n_processed;
   double t_src, t_prep, t_gpu, t_sink;
   bq_sink_fn sink;
@@ -56,33 +58,45 @@ static double pnow(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &t
 
 static void *stage_a(void *arg) {
   pipe_ctx_t *p = arg;
-  for (;;) {
+  for (int seq = 0;; ++seq) {
+    q1_t *qa = &p->qa[seq % p->n_al];
     int n = 0, rc = 0;
     double t0 = pnow();
     bq_read_t *seqs = p->src(p->src_ctx, &n);
     p->t_src += pnow() - t0; t0 = pnow();
-    if (!seqs || n <= 0) { free(seqs); q_put(&p->qa, 0, 0, 0, 0, 1); return 0; }
+    if (!seqs || n <= 0) { /* end marker to every GPU lane, in sequence order */
+      free(seqs);
+      for (int k = 0; k < p->n_al; ++k) q_put(&p->qa[(seq + k) % p->n_al], 0, 0, 0, 0, 1);
+      return 0;
+    }
     bq_batch_t *b = bq_batch_prep(p->opt, p->n_processed, n, seqs, &rc);
     p->t_prep += pnow() - t0;
     p->n_processed += n;
-    q_put(&p->qa, b, seqs, n, rc, b == 0);
-    if (!b) return 0;
+    if (!b) { /* preparation failed: report it on this lane, end the others */
+      q_put(qa, 0, seqs, n, rc, 1);
+      for (int k = 1; k < p->n_al; ++k) q_put(&p->qa[(seq + k) % p->n_al], 0, 0, 0, 0, 1);
+      return 0;
+    }
+    q_put(qa, b, seqs, n, rc, 0);
   }
 }
 
+typedef struct { pipe_ctx_t *p; int lane; double t_gpu; } lane_t;
+
 static void *stage_b(void *arg) {
-  pipe_ctx_t *p = arg;
+  lane_t *L = arg;
+  pipe_ctx_t *p = L->p;
   int failed = 0;
   for (;;) {
     bq_batch_t *b; bq_read_t *seqs; int n, rc, end;
-    q_get(&p->qa, &b, &seqs, &n, &rc, &end);
+    q_get(&p->qa[L->lane], &b, &seqs, &n, &rc, &end);
     if (b && !failed) {
       const double t0 = pnow();
-      rc = bq_batch_run(p->al, b);
-      p->t_gpu += pnow() - t0;
+      rc = bq_batch_run(p->al[L->lane], b);
+      L->t_gpu += pnow() - t0;
       if (rc) failed = rc;
     } else if (b) rc = failed;  /* after a failure the remaining batches are only drained */
-    q_put(&p->qb, b, seqs, n, rc, end);
+    q_put(&p->qb[L->lane], b, seqs, n, rc, end);
     if (end) return 0;
   }
 }
@@ -102,23 +116,25 @@ static void *stage_d(void *arg) {
   }
 }
 
-int bq_pipeline_run(const bq_opt_t *opt, const bq_ref_t *ref, bsq_aligner *al, bq_source_fn src, void *src_ctx, bq_sink_fn sink, void *sink_ctx,
-                    const bq_pestat_t *pes0, const char *rg_id) {
+int bq_pipeline_run(const bq_opt_t *opt, const bq_ref_t *ref, bsq_aligner *al, bsq_aligner *al2, bq_source_fn src, void *src_ctx, bq_sink_fn sink,
+                    void *sink_ctx, const bq_pestat_t *pes0, const char *rg_id) {
   pipe_ctx_t p;
   memset(&p, 0, sizeof p);
-  p.opt = opt; p.al = al; p.src = src; p.src_ctx = src_ctx;
+  p.opt = opt; p.al[0] = al; p.al[1] = al2; p.n_al = al2 ? 2 : 1; p.src = src; p.src_ctx = src_ctx;
   p.sink = sink; p.sink_ctx = sink_ctx;
-  q_init(&p.qa); q_init(&p.qb); q_init(&p.qc);
-  pthread_t ta, tb, td;
+  for (int k = 0; k < 2; ++k) { q_init(&p.qa[k]); q_init(&p.qb[k]); }
+  q_init(&p.qc);
+  pthread_t ta, tb[2], td;
+  lane_t lanes[2] = {{&p, 0, 0}, {&p, 1, 0}};
   pthread_create(&ta, 0, stage_a, &p);
-  pthread_create(&tb, 0, stage_b, &p);
+  for (int k = 0; k < p.n_al; ++k) pthread_create(&tb[k], 0, stage_b, &lanes[k]);
   pthread_create(&td, 0, stage_d, &p);
   int ret = 0;
   double t_wait = 0, t_fin = 0;
-  for (;;) {
+  for (int seq = 0;; ++seq) { /* batches come back in sequence order: lane seq % n_al */
     bq_batch_t *b; bq_read_t *seqs; int n, rc, end;
     double t0 = pnow();
-    q_get(&p.qb, &b, &seqs, &n, &rc, &end);
+    q_get(&p.qb[seq % p.n_al], &b, &seqs, &n, &rc, &end);
     t_wait += pnow() - t0; t0 = pnow();
     if (b && rc == 0) {
       bq_batch_finish(opt, ref, b, pes0, rg_id);
@@ -129,9 +145,18 @@ int bq_pipeline_run(const bq_opt_t *opt, const bq_ref_t *ref, bsq_aligner *al, b
       if (b) bq_batch_discard(b);
       q_put(&p.qc, 0, seqs, n, rc ? rc : -1, end); /* failed batch: the sink only frees */
     }
-    if (end) break;
+    if (end) { /* drain the end markers of the other lanes */
+      for (int k = 1; k < p.n_al; ++k) {
+        bq_batch_t *b2; bq_read_t *s2; int n2, rc2, e2;
+        q_get(&p.qb[(seq + k) % p.n_al], &b2, &s2, &n2, &rc2, &e2);
+      }
+      break;
+    }
   }
-  pthread_join(ta, 0); pthread_join(tb, 0); pthread_join(td, 0);
+  pthread_join(ta, 0);
+  for (int k = 0; k < p.n_al; ++k) pthread_join(tb[k], 0);
+  pthread_join(td, 0);
+  p.t_gpu = lanes[0].t_gpu + lanes[1].t_gpu;
   if (getenv("BQ_TIMING"))
     fprintf(stderr, "[bq_pipeline] source %.3f prep %.3f | gpu %.3f | wait %.3f phase2 %.3f sink %.3f s\n", p.t_src, p.t_prep, p.t_gpu, t_wait, t_fin,
             p.t_sink);

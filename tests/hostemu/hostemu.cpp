@@ -137,7 +137,7 @@ int bsq_align_phase1(bsq_aligner *al, int64_t n_tasks, const uint8_t *seqs, int3
     bsq_chain_ws_t ws; ws.cap = cap; ws.snodes = sn.data(); ws.chains = wc.data(); ws.bnodes = bn.data(); ws.order = ord.data();
     // same order of attempts as the CUDA path: shared-memory decomposition first, exact B-tree replay as fallback
     bsq_chain_result_t cr;
-    static bsq_cw_smem_t cw;
+    static thread_local bsq_cw_smem_t cw;
     if (getenv("BSQ_EMU_NO_CW") || bsq_chain_warp<bsq_cw_scalar>(opt, ix, parent[t], lens[t], intv.data(), n, pos.data(), n_sa, cw, och.data(), osd.data(), cr) != BSQ_CW_OK) {
       cr = bsq_chain_task(opt, ix, parent[t], lens[t], intv.data(), n, pos.data(), ws, och.data(), osd.data());
       al->counters[11]++;
@@ -175,7 +175,7 @@ int64_t hostemu_chain(const bsq_index *ixp, const bsq_opt *opt_, int parent, int
   std::vector<int32_t> ord(cap); std::vector<bsq_chain_t> och(cap); std::vector<bsq_seed_t> osd(cap);
   bsq_chain_ws_t ws; ws.cap = cap; ws.snodes = sn.data(); ws.chains = wc.data(); ws.bnodes = bn.data(); ws.order = ord.data();
   bsq_chain_result_t cr;
-  static bsq_cw_smem_t cw;
+  static thread_local bsq_cw_smem_t cw;
   if (getenv("BSQ_EMU_NO_CW") || bsq_chain_warp<bsq_cw_scalar>(opt, ix, parent, len, intv.data(), n, pos.data(), n_sa, cw, och.data(), osd.data(), cr) != BSQ_CW_OK)
     cr = bsq_chain_task(opt, ix, parent, len, intv.data(), n, pos.data(), ws, och.data(), osd.data());
   if (cr.status) return -1;
