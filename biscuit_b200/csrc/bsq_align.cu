@@ -310,15 +310,18 @@ struct bsq_cw_warp {
   }
 };
 
-// Tasks binned by their number of seeds: tier 0: n_sa <= 64, 1: <= 128, 2: <= 256, 3: the rest.  Order inside a
-// tier is arbitrary (every task writes to its own slots).
+// Tasks binned by their number of seeds into BSQ_N_TIERS capacity classes (k_chain_warp is instantiated once per
+// class).  Order inside a tier is arbitrary (every task writes to its own slots).
+#define BSQ_N_TIERS 7
+__constant__ int c_tier_cap[BSQ_N_TIERS] = {64, 96, 128, 160, 192, 256, 1 << 30};
 __global__ void k_chain_tiers(int64_t n_tasks, const int32_t *n_sa, int32_t *tier_list, unsigned long long *tier_cnt) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_tasks) return;
   const int ns = n_sa[t];
-  const int tier = ns <= 64 ? 0 : ns <= 128 ? 1 : ns <= 256 ? 2 : 3;
+  int tier = 0;
+  while (ns > c_tier_cap[tier]) ++tier;
   // one atomic per (warp, tier)
-  for (int q = 0; q < 4; ++q) {
+  for (int q = 0; q < BSQ_N_TIERS; ++q) {
     const unsigned m = __ballot_sync(__activemask(), tier == q);
     if (tier == q) {
       const int leader = __ffs(m) - 1, lane = threadIdx.x & 31;
@@ -662,11 +665,11 @@ static int phase1_device(bsq_aligner *al, int64_t n, int32_t stride, int64_t *to
   cudaStream_t s = al->stream;
   int rc;
 #define RES(buf, bytes) if ((rc = al->buf.reserve(bytes))) return rc
-  RES(intv, (size_t)n * BSQ_MAX_INTV * sizeof(bsq_pk_t)); RES(scalars, 64);
+  RES(intv, (size_t)n * BSQ_MAX_INTV * sizeof(bsq_pk_t)); RES(scalars, 128);
   RES(n_intv, n * 4); RES(n_sa, n * 4); RES(sa_off, (n + 1) * 8); RES(status, 4);
   RES(n_chains, n * 4); RES(frac_rep, n * 4); RES(n_regs, n * 4); RES(reg_off, (n + 1) * 8);
   CK(cudaMemsetAsync(al->status.p, 0, 4, s));
-  CK(cudaMemsetAsync(al->scalars.p, 0, 64, s));
+  CK(cudaMemsetAsync(al->scalars.p, 0, 128, s));
   SNAP(11);
   CK(cudaEventRecord(al->ev[0], s));
   k_seed<<<seed_grid(n), 128, kSeedSmem, s>>>(opt, ix, n, al->seqs.as<uint8_t>(), stride, al->lens.as<int32_t>(), al->parent.as<uint8_t>(), 1,
@@ -701,8 +704,8 @@ static int phase1_device(bsq_aligner *al, int64_t n, int32_t stride, int64_t *to
   SNAP(13);
   RES(fb_flag, n);
   {
-    RES(tiers, (size_t)n * 4 * 4);
-    unsigned long long *tcnt = al->scalars.as<unsigned long long>() + 2;
+    RES(tiers, (size_t)n * 4 * BSQ_N_TIERS);
+    unsigned long long *tcnt = al->scalars.as<unsigned long long>() + 8;
     k_chain_tiers<<<nblk(n, 256), 256, 0, s>>>(n, al->n_sa.as<int32_t>(), al->tiers.as<int32_t>(), tcnt);
     CK(cudaGetLastError());
 #define CW_LAUNCH(CAP, WPB, Q, STREAM) if ((rc = launch_chain_warp<CAP, WPB>(STREAM, opt, ix, n, al->tiers.as<int32_t>() + (size_t)(Q) * n, tcnt + (Q), al->lens.as<int32_t>(), al->parent.as<uint8_t>(),  \
@@ -711,10 +714,13 @@ static int phase1_device(bsq_aligner *al, int64_t n, int32_t stride, int64_t *to
                 al->fb_flag.as<uint8_t>(), al->scalars.as<unsigned long long>() + 1))) return rc
     CK(cudaEventRecord(al->ev_fork, s));
     CK(cudaStreamWaitEvent(al->stream2, al->ev_fork, 0));
-    CW_LAUNCH(1024, 2, 3, al->stream2);  // the few large tasks run beside the small tiers: their long tail is hidden
+    CW_LAUNCH(1024, 2, 6, al->stream2);  // the few large tasks run beside the small tiers: their long tail is hidden
     CK(cudaEventRecord(al->ev_join, al->stream2));
-    CW_LAUNCH(256, 4, 2, s);
-    CW_LAUNCH(128, 4, 1, s);
+    CW_LAUNCH(256, 4, 5, s);
+    CW_LAUNCH(192, 4, 4, s);
+    CW_LAUNCH(160, 4, 3, s);
+    CW_LAUNCH(128, 4, 2, s);
+    CW_LAUNCH(96, 4, 1, s);
     CW_LAUNCH(64, 4, 0, s);
     CK(cudaStreamWaitEvent(s, al->ev_join, 0));
 #undef CW_LAUNCH

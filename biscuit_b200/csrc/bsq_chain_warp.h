@@ -34,7 +34,8 @@ template <int CAP_>
 struct bsq_cw_smem_tt {
   static const int CAP = CAP_;
   int64_t rbeg[CAP_];       // seed reference position, arrival order
-  uint64_t key[CAP_];       // sort keys: rbeg << 10 | arrival index
+  static const int KEYS = CAP_ <= 64 ? 64 : CAP_ <= 128 ? 128 : CAP_ <= 256 ? 256 : CAP_ <= 512 ? 512 : 1024;  // bitonic sort pads to a power of two
+  uint64_t key[KEYS];       // sort keys: rbeg << 10 | arrival index
   int64_t c_last_rbeg[CAP_];  // chain state, indexed by the arrival index of the chain's first seed
   int32_t c_w[CAP_];
   uint16_t qbeg[CAP_], slen[CAP_];
