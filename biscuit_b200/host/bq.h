@@ -95,6 +95,10 @@ typedef struct {
   uint8_t *seq;  /* nt4, after clipping */
   uint8_t *seq0; /* nt4, as read */
   int l_seq0, l_adaptor, clip5, clip3;
+  /* batch readers place name / seq0 / qual of all reads of a batch in one slab (owned by the first read of the
+   * batch) instead of three allocations per read; bq_reads_free knows both conventions */
+  char *slab;
+  uint8_t in_slab;
 } bq_read_t;
 
 /* ---- alignment region: mem_alnreg_t (lib/aln/mem_alnreg.h:34-66) ---- */
@@ -191,6 +195,7 @@ typedef struct bq_fastq bq_fastq_t;
 bq_fastq_t *bq_fastq_open(const char *fn);
 void bq_fastq_close(bq_fastq_t *f);
 bq_read_t *bq_read_batch(int chunk_size, int has_bc, int keep_comment, int *n, bq_fastq_t *f1, bq_fastq_t *f2);
+void bq_reads_free(bq_read_t *seqs, int n); /* reads of one batch incl. their .sam strings and the array itself */
 void bq_print_sam_hdr(const bq_ref_t *ref, const char *hdr_line, const char *pg_line);
 void bq_fatal(const char *fmt, ...);
 

@@ -78,19 +78,21 @@ int64_t bq_session_align(bq_session *s, int64_t n_processed, int n, const uint8_
 typedef struct { int n_batches, b, n, stride; const uint8_t *seqs, *quals; const int32_t *lens; int64_t sam_bytes; } stream_t;
 
 static bq_read_t *make_reads(int64_t n_processed, int n, const uint8_t *seqs, int stride, const int32_t *lens, const uint8_t *quals) {
+  /* what bq_read_batch produces for a FASTQ batch: one slab with name, nt4 sequence and quality of every read */
   bq_read_t *rd = calloc((size_t)n + 1, sizeof(bq_read_t));
-  char nm[64];
+  size_t tot = 0;
+  for (int i = 0; i < n; ++i) tot += 24 + 2 * ((size_t)lens[i] + 1);
+  char *slab = malloc(tot + 16), *p = slab;
   for (int i = 0; i < n; ++i) {
+    rd[i].name = p; p += 1 + sprintf(p, "r%lld", (long long)((n_processed + i) >> 1));
     rd[i].l_seq = rd[i].l_seq0 = lens[i];
-    rd[i].seq = rd[i].seq0 = malloc((size_t)lens[i] + 1);
-    memcpy(rd[i].seq, seqs + (size_t)i * stride, (size_t)lens[i]);
-    rd[i].qual = malloc((size_t)lens[i] + 1);
-    if (quals) memcpy(rd[i].qual, quals + (size_t)i * stride, (size_t)lens[i]); else memset(rd[i].qual, 'I', (size_t)lens[i]);
-    rd[i].qual[lens[i]] = 0;
-    snprintf(nm, sizeof nm, "r%lld", (long long)((n_processed + i) >> 1));
-    rd[i].name = strdup(nm);
-    rd[i].id = i;
+    rd[i].seq = rd[i].seq0 = (uint8_t *)p; memcpy(p, seqs + (size_t)i * stride, (size_t)lens[i]); p += lens[i] + 1;
+    rd[i].qual = p;
+    if (quals) memcpy(p, quals + (size_t)i * stride, (size_t)lens[i]); else memset(p, 'I', (size_t)lens[i]);
+    p[lens[i]] = 0; p += lens[i] + 1;
+    rd[i].id = i; rd[i].in_slab = 1;
   }
+  if (n > 0) rd[0].slab = slab; else free(slab);
   return rd;
 }
 
@@ -108,11 +110,8 @@ static void stream_sink(void *ctx, bq_read_t *rd, int n) {
   const int ok = n >= 0;
   if (n < 0) n = -n;
   int64_t tot = 0;
-  for (int i = 0; i < n; ++i) {
-    tot += rd[i].sam ? (int64_t)strlen(rd[i].sam) : 0;
-    free(rd[i].sam); free(rd[i].seq0); free(rd[i].qual); free(rd[i].name);
-  }
-  free(rd);
+  for (int i = 0; i < n; ++i) tot += rd[i].sam ? (int64_t)strlen(rd[i].sam) : 0;
+  bq_reads_free(rd, n);
   if (ok) st->sam_bytes = tot;
 }
 

@@ -141,27 +141,71 @@ static void to_read(bq_fastq_t *f, bq_read_t *s, int has_bc, int keep_comment) {
   s->qual = f->qual.l ? strdup(f->qual.s) : 0;
 }
 
+/* slab variant of to_read for the common case (no barcode extraction, no comments): offsets first, pointers once
+ * the slab has stopped growing */
+static void to_read_slab(bq_fastq_t *f, bq_read_t *s, bq_str_t *slab, size_t off[3]) {
+  const uint8_t *t = nt4_table();
+  memset(s, 0, sizeof *s);
+  bq_str_reserve(slab, f->name.l + 1 + 2 * (f->seq.l + 1) + 16);
+  off[0] = slab->l; memcpy(slab->s + slab->l, f->name.s, f->name.l + 1); slab->l += f->name.l + 1;
+  off[1] = slab->l;
+  for (size_t i = 0; i < f->seq.l; ++i) slab->s[slab->l + i] = (char)t[(unsigned char)f->seq.s[i]];
+  slab->l += f->seq.l + 1;
+  off[2] = (size_t)-1;
+  if (f->qual.l) { off[2] = slab->l; memcpy(slab->s + slab->l, f->qual.s, f->qual.l + 1); slab->l += f->qual.l + 1; }
+  s->l_seq = s->l_seq0 = (int)f->seq.l;
+  s->in_slab = 1;
+}
+
 bq_read_t *bq_read_batch(int chunk_size, int has_bc, int keep_comment, int *n_, bq_fastq_t *f1, bq_fastq_t *f2) { /* bis_bseq_read, bwa.c:817-850 */
   int size = 0, m = 0, n = 0;
   bq_read_t *seqs = 0;
+  const int use_slab = !has_bc && !keep_comment;
+  bq_str_t slab = {0, 0, 0};
+  size_t *offs = 0;
   while (fq_read(f1) >= 0) {
     if (f2 && fq_read(f2) < 0) { fprintf(stderr, "[W::bis_bseq_read] the 2nd file has fewer sequences.\n"); break; }
-    if (n + 2 > m) { m = m ? m << 1 : 256; seqs = realloc(seqs, (size_t)m * sizeof(bq_read_t)); }
+    if (n + 2 > m) {
+      m = m ? m << 1 : 256;
+      seqs = realloc(seqs, (size_t)m * sizeof(bq_read_t));
+      if (use_slab) offs = realloc(offs, (size_t)m * 3 * sizeof(size_t));
+    }
     trim_readno(&f1->name);
-    to_read(f1, &seqs[n], has_bc, keep_comment);
+    if (use_slab) to_read_slab(f1, &seqs[n], &slab, offs + 3 * (size_t)n); else to_read(f1, &seqs[n], has_bc, keep_comment);
     seqs[n].id = n;
     size += seqs[n++].l_seq;
     if (f2) {
       trim_readno(&f2->name);
-      to_read(f2, &seqs[n], has_bc, keep_comment);
+      if (use_slab) to_read_slab(f2, &seqs[n], &slab, offs + 3 * (size_t)n); else to_read(f2, &seqs[n], has_bc, keep_comment);
       seqs[n].id = n;
       size += seqs[n++].l_seq;
     }
     if (size >= chunk_size && (n & 1) == 0) break;
   }
   if (size == 0 && f2 && fq_read(f2) >= 0) fprintf(stderr, "[W::bis_bseq_read] the 1st file has fewer sequences.\n");
+  if (use_slab && n > 0) {
+    for (int i = 0; i < n; ++i) {
+      seqs[i].name = slab.s + offs[3 * (size_t)i];
+      seqs[i].seq = seqs[i].seq0 = (uint8_t *)slab.s + offs[3 * (size_t)i + 1];
+      seqs[i].qual = offs[3 * (size_t)i + 2] == (size_t)-1 ? 0 : slab.s + offs[3 * (size_t)i + 2];
+    }
+    seqs[0].slab = slab.s;
+  } else free(slab.s);
+  free(offs);
   *n_ = n;
   return seqs;
+}
+
+void bq_reads_free(bq_read_t *seqs, int n) {
+  if (!seqs) return;
+  char *slab = n > 0 ? seqs[0].slab : 0;
+  for (int i = 0; i < n; ++i) {
+    if (!seqs[i].in_slab) { free(seqs[i].name); free(seqs[i].seq0); free(seqs[i].qual); }
+    free(seqs[i].comment); free(seqs[i].barcode); free(seqs[i].umi);
+    free(seqs[i].sam);
+  }
+  free(slab);
+  free(seqs);
 }
 
 /* ---------------- index files ---------------- */

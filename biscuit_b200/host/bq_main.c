@@ -30,12 +30,10 @@ static bq_read_t *fastq_source(void *ctx, int *n) {
 static void sam_sink(void *ctx, bq_read_t *seqs, int n) {
   const int ok = n >= 0;
   if (n < 0) n = -n;
-  for (int i = 0; i < n; ++i) {
-    if (ok && seqs[i].sam) fputs(seqs[i].sam, stdout);
-    free(seqs[i].name); free(seqs[i].comment); free(seqs[i].barcode); free(seqs[i].umi); free(seqs[i].seq0); free(seqs[i].qual);
-    free(seqs[i].sam);
-  }
-  free(seqs);
+  if (ok)
+    for (int i = 0; i < n; ++i)
+      if (seqs[i].sam) fputs(seqs[i].sam, stdout);
+  bq_reads_free(seqs, n);
   if (ok && bq_verbose >= 3) fprintf(stderr, "[M::mem_process_seqs] Processed %d reads\n", n);
 }
 
