@@ -126,11 +126,28 @@ template <int CAP>
 struct bsq_seed_scratch_dev {
   uint4 *sm;  // this lane's column; entry e at sm[e * 32]
   bsq_pk_t spill[BSQ_MAX_READ_LEN + 1 - CAP];
-  const uint8_t *seq;
-  uint64_t qwin;
-  uintptr_t qaddr;
-  int parent;
-  __device__ __forceinline__ void bind(const uint8_t *s, int par) { seq = s; parent = par; qaddr = ~(uintptr_t)0; }
+  const uint32_t *rd;  // this lane's converted read, 4 bits per base, word w at rd[w * 128] (shared memory)
+  // Copy the read of the task into shared memory, converted for the index it is searched in (C>T parent, G>A daughter;
+  // bseq_bsconvert, bwamem.c:161-178).  q() is on the critical path of every extension step: from here it is one
+  // shared-memory word instead of a global load.
+  __device__ __forceinline__ void bind(uint32_t *rd_sm, const uint8_t *s, int len, int par) {
+    rd = rd_sm;
+    const int nw = (len + 7) >> 3;
+    const bool al8 = ((uintptr_t)s & 7) == 0;
+    for (int w = 0; w < nw; ++w) {
+      uint64_t v;
+      if (al8) v = __ldg(reinterpret_cast<const uint64_t *>(s) + w);  // the row is padded to its stride
+      else { v = 0; for (int k = 0; k < 8; ++k) if (8 * w + k < len) v |= (uint64_t)s[8 * w + k] << (8 * k); }
+      uint32_t pk = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        int c = (int)(v >> (8 * k)) & 0xf;
+        c = par ? (c == 1 ? 3 : c) : (c == 2 ? 0 : c);
+        pk |= (uint32_t)c << (4 * k);
+      }
+      rd_sm[w * 128] = pk;
+    }
+  }
   __device__ __forceinline__ bsq_pk_t get(int i) const {
     if (i >= CAP) return spill[i - CAP];
     const uint4 v = sm[i * 32];
@@ -142,12 +159,7 @@ struct bsq_seed_scratch_dev {
     if (i >= CAP) { spill[i - CAP] = p; return; }
     sm[i * 32] = make_uint4((uint32_t)p.w0, (uint32_t)(p.w0 >> 32), (uint32_t)p.w1, (uint32_t)(p.w1 >> 32));
   }
-  __device__ __forceinline__ int q(int i) {
-    const uintptr_t a = (uintptr_t)(seq + i), w = a & ~(uintptr_t)7;
-    if (w != qaddr) { qaddr = w; qwin = __ldg(reinterpret_cast<const uint64_t *>(w)); }
-    const int c = (int)(qwin >> ((a & 7) * 8)) & 0xff;
-    return parent ? (c == 1 ? 3 : c) : (c == 2 ? 0 : c);
-  }
+  __device__ __forceinline__ int q(int i) const { return (int)(rd[(i >> 3) * 128] >> ((i & 7) * 4)) & 0xf; }
 };
 
 #ifndef BSQ_SEED_CAP
@@ -168,6 +180,7 @@ __global__ void __launch_bounds__(128, BSQ_SEED_CTAS) k_seed(const __grid_consta
   extern __shared__ uint4 seed_smem[];
   bsq_seed_scratch_dev<BSQ_SEED_CAP> scr;
   scr.sm = seed_smem + (threadIdx.x >> 5) * (BSQ_SEED_CAP * 32) + (threadIdx.x & 31);
+  uint32_t *rd_sm = reinterpret_cast<uint32_t *>(seed_smem + 128 * BSQ_SEED_CAP) + threadIdx.x;  // [word][thread]
   bsq_seed_machine_t m;
   bsq_ext_req_t req;
   int64_t t = -1;
@@ -184,7 +197,7 @@ __global__ void __launch_bounds__(128, BSQ_SEED_CTAS) k_seed(const __grid_consta
         out = intv + t * BSQ_MAX_INTV;
         if (pipeline && len < opt.min_seed_len) n_intv[t] = 0;  // mem_chain returns before seeding
         else {
-          scr.bind(seqs + t * stride, par);
+          scr.bind(rd_sm, seqs + t * stride, len, par);
           bsq_sm_init(m, opt, len, BSQ_MAX_INTV);
           have = true;
         }
@@ -422,10 +435,11 @@ __global__ void __launch_bounds__(128) k_extend_warp(const __grid_constant__ bsq
 static inline unsigned nblk(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
 // k_seed is persistent (lanes pull tasks from a counter): one wave of 148 SMs x 3 resident CTAs of 128
-static const size_t kSeedSmem = (size_t)128 * BSQ_SEED_CAP * 16;
+// shared memory of k_seed: candidate lists + the converted reads (4 bits per base, as many words as the longest row needs)
+static inline size_t seed_smem_bytes(int stride) { return (size_t)128 * BSQ_SEED_CAP * 16 + (size_t)((stride + 7) >> 3) * 128 * 4; }
 static inline unsigned seed_grid(int64_t n) {
   static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(k_seed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSeedSmem); attr_set = true; }
+  if (!attr_set) { cudaFuncSetAttribute(k_seed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seed_smem_bytes(BSQ_MAX_READ_LEN + 8)); attr_set = true; }
   int64_t want = (n + 127) / 128;
   return (unsigned)(want < 148 * BSQ_SEED_CTAS ? want : 148 * BSQ_SEED_CTAS);
 }
@@ -551,7 +565,7 @@ int bsq_collect_intv(const bsq_index *ix, const bsq_opt *opt_, int64_t n, const 
   CK(cudaMemcpy(dlen, lens, n * 4, cudaMemcpyHostToDevice));
   CK(cudaMemset(dst, 0, 4)); CK(cudaMemset(dnext, 0, 8));
   CK(cudaMemset(dpk, 0, n * BSQ_MAX_INTV * sizeof(bsq_pk_t)));
-  k_seed<<<seed_grid(n), 128, kSeedSmem>>>(opt, ix->d, n, dseq, stride, dlen, dpar, 0, dpk, dn, dst, dnext);
+  k_seed<<<seed_grid(n), 128, seed_smem_bytes(stride)>>>(opt, ix->d, n, dseq, stride, dlen, dpar, 0, dpk, dn, dst, dnext);
   CK(cudaGetLastError());
   k_seed_sort<<<nblk(n, 128), 128>>>(opt, n, dpk, dn, dnsa);
   CK(cudaGetLastError());
@@ -672,7 +686,7 @@ static int phase1_device(bsq_aligner *al, int64_t n, int32_t stride, int64_t *to
   CK(cudaMemsetAsync(al->scalars.p, 0, 128, s));
   SNAP(11);
   CK(cudaEventRecord(al->ev[0], s));
-  k_seed<<<seed_grid(n), 128, kSeedSmem, s>>>(opt, ix, n, al->seqs.as<uint8_t>(), stride, al->lens.as<int32_t>(), al->parent.as<uint8_t>(), 1,
+  k_seed<<<seed_grid(n), 128, seed_smem_bytes(stride), s>>>(opt, ix, n, al->seqs.as<uint8_t>(), stride, al->lens.as<int32_t>(), al->parent.as<uint8_t>(), 1,
                                               al->intv.as<bsq_pk_t>(), al->n_intv.as<int32_t>(), al->status.as<int32_t>(),
                                               al->scalars.as<unsigned long long>());
   CK(cudaGetLastError());
