@@ -169,7 +169,10 @@ struct bsq_seed_scratch_dev {
 #define BSQ_SEED_CTAS 5   // resident CTAs per SM (registers: 96 per thread)
 #endif
 
-// SMEM seeding.  Each lane owns one (read, conversion) task at a time and pulls the next one from a
+#include "bsq_seed_dev.cuh"
+
+// First organisation of the seeding kernel (kept for comparison: BSQ_SEED_V1=1 in the environment selects it).
+// Each lane owns one (read, conversion) task at a time and pulls the next one from a
 // global counter when it finishes; all lanes of the warp meet at the single bsq_extend1 site per
 // iteration so that their FM-index gathers are in flight together (see bsq_seed.h).  Starting and
 // finishing a task cost a handful of instructions (no read conversion pass, no sort: k_seed_sort), so a
@@ -437,9 +440,14 @@ static inline unsigned nblk(int64_t n, int bs) { return (unsigned)((n + bs - 1) 
 // k_seed is persistent (lanes pull tasks from a counter): one wave of 148 SMs x 3 resident CTAs of 128
 // shared memory of k_seed: candidate lists + the converted reads (4 bits per base, as many words as the longest row needs)
 static inline size_t seed_smem_bytes(int stride) { return (size_t)128 * BSQ_SEED_CAP * 16 + (size_t)((stride + 7) >> 3) * 128 * 4; }
+static inline bool seed_v1() { static int v = -1; if (v < 0) { const char *e = getenv("BSQ_SEED_V1"); v = e && atoi(e) != 0; } return v != 0; }
 static inline unsigned seed_grid(int64_t n) {
   static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(k_seed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seed_smem_bytes(BSQ_MAX_READ_LEN + 8)); attr_set = true; }
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_seed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seed_smem_bytes(BSQ_MAX_READ_LEN + 8));
+    cudaFuncSetAttribute(k_seed2<BSQ_SEED_CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seed_smem_bytes(BSQ_MAX_READ_LEN + 8));
+    attr_set = true;
+  }
   int64_t want = (n + 127) / 128;
   return (unsigned)(want < 148 * BSQ_SEED_CTAS ? want : 148 * BSQ_SEED_CTAS);
 }
@@ -565,7 +573,8 @@ int bsq_collect_intv(const bsq_index *ix, const bsq_opt *opt_, int64_t n, const 
   CK(cudaMemcpy(dlen, lens, n * 4, cudaMemcpyHostToDevice));
   CK(cudaMemset(dst, 0, 4)); CK(cudaMemset(dnext, 0, 8));
   CK(cudaMemset(dpk, 0, n * BSQ_MAX_INTV * sizeof(bsq_pk_t)));
-  k_seed<<<seed_grid(n), 128, seed_smem_bytes(stride)>>>(opt, ix->d, n, dseq, stride, dlen, dpar, 0, dpk, dn, dst, dnext);
+  if (seed_v1()) k_seed<<<seed_grid(n), 128, seed_smem_bytes(stride)>>>(opt, ix->d, n, dseq, stride, dlen, dpar, 0, dpk, dn, dst, dnext);
+  else k_seed2<BSQ_SEED_CAP><<<seed_grid(n), 128, seed_smem_bytes(stride)>>>(opt, ix->d, n, dseq, stride, dlen, dpar, 0, dpk, dn, dst, dnext);
   CK(cudaGetLastError());
   k_seed_sort<<<nblk(n, 128), 128>>>(opt, n, dpk, dn, dnsa);
   CK(cudaGetLastError());
@@ -686,9 +695,14 @@ static int phase1_device(bsq_aligner *al, int64_t n, int32_t stride, int64_t *to
   CK(cudaMemsetAsync(al->scalars.p, 0, 128, s));
   SNAP(11);
   CK(cudaEventRecord(al->ev[0], s));
-  k_seed<<<seed_grid(n), 128, seed_smem_bytes(stride), s>>>(opt, ix, n, al->seqs.as<uint8_t>(), stride, al->lens.as<int32_t>(), al->parent.as<uint8_t>(), 1,
-                                              al->intv.as<bsq_pk_t>(), al->n_intv.as<int32_t>(), al->status.as<int32_t>(),
-                                              al->scalars.as<unsigned long long>());
+  if (seed_v1())
+    k_seed<<<seed_grid(n), 128, seed_smem_bytes(stride), s>>>(opt, ix, n, al->seqs.as<uint8_t>(), stride, al->lens.as<int32_t>(), al->parent.as<uint8_t>(), 1,
+                                                              al->intv.as<bsq_pk_t>(), al->n_intv.as<int32_t>(), al->status.as<int32_t>(),
+                                                              al->scalars.as<unsigned long long>());
+  else
+    k_seed2<BSQ_SEED_CAP><<<seed_grid(n), 128, seed_smem_bytes(stride), s>>>(opt, ix, n, al->seqs.as<uint8_t>(), stride, al->lens.as<int32_t>(),
+                                                                             al->parent.as<uint8_t>(), 1, al->intv.as<bsq_pk_t>(), al->n_intv.as<int32_t>(),
+                                                                             al->status.as<int32_t>(), al->scalars.as<unsigned long long>());
   CK(cudaGetLastError());
   k_seed_sort<<<nblk(n, 128), 128, 0, s>>>(opt, n, al->intv.as<bsq_pk_t>(), al->n_intv.as<int32_t>(), al->n_sa.as<int32_t>());
   CK(cudaGetLastError());

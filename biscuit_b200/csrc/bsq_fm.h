@@ -35,12 +35,16 @@ BSQ_HD uint64_t bsq_block_occ(const bsq_block_t &b, int c) { return (uint64_t)b.
 // Number of A,C,G,T among the first `n` (0..128) symbols of the block, packed as four counts.
 BSQ_HD void bsq_block_count4(const bsq_block_t &b, int n, uint32_t c[4]) {
   uint32_t c1 = 0, c2 = 0, c3 = 0;
+  // All four words, no early exit: the lanes of a warp count different prefixes, a data-dependent trip count would
+  // serialise them.  Word i contributes its first clamp(n - 32 i, 0, 32) symbols; masked-out symbols read as A and are
+  // not counted in c1..c3 (c[0] follows from n).
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     int m = n - 32 * i;
-    if (m <= 0) break;
+    m = m < 0 ? 0 : (m > 32 ? 32 : m);
     uint64_t v = (uint64_t)b.w[8 + 2 * i] << 32 | b.w[9 + 2 * i];  // 32 symbols, first symbol in the top bits
-    if (m < 32) v &= ~((1ull << ((32 - m) << 1)) - 1);
+    const uint64_t keep = m == 0 ? 0ull : ~0ull << ((32 - m) << 1);  // top 2m bits
+    v &= keep;
     uint64_t lo = v & 0x5555555555555555ull, hi = (v >> 1) & 0x5555555555555555ull;
     c3 += bsq_popc64(hi & lo);
     c2 += bsq_popc64(hi & ~lo);

@@ -64,6 +64,11 @@ struct bsq_ext_req_t {
 
 // bwt_extend (bwt.c:278-293) restricted to the one child that is used.  back=1 extends to the
 // left in `fm`; back=0 is the forward extension = a backward step in the complementary index.
+BSQ_HD uint64_t bsq_sel4(int c, uint64_t a0, uint64_t a1, uint64_t a2, uint64_t a3) {  // a[c] without indexing (keeps a[] in registers)
+  const uint64_t lo = (c & 1) ? a1 : a0, hi = (c & 1) ? a3 : a2;
+  return (c & 2) ? hi : lo;
+}
+
 BSQ_HD void bsq_extend1(const bsq_fm_t &fm, const bsq_fm_t &fmc, const bsq_ext_req_t &r, uint64_t &o0, uint64_t &o1, uint64_t &o2) {
   const bsq_fm_t &f = r.back ? fm : fmc;
   const uint64_t xa = r.back ? r.x0 : r.x1;  // coordinate in the index being stepped
@@ -71,12 +76,14 @@ BSQ_HD void bsq_extend1(const bsq_fm_t &fm, const bsq_fm_t &fmc, const bsq_ext_r
   uint64_t tk[4], tl[4];
   BSQ_CTR(BSQ_CTR_EXTENDS, 1);
   bsq_2occ4_flat(f, xa - 1, xa - 1 + r.x2, tk, tl);
-  const uint64_t na = f.L2[r.c] + 1 + tk[r.c];
+  const int c = r.c;
+  const uint64_t tkc = bsq_sel4(c, tk[0], tk[1], tk[2], tk[3]), tlc = bsq_sel4(c, tl[0], tl[1], tl[2], tl[3]);
+  const uint64_t na = bsq_sel4(c, f.L2[0], f.L2[1], f.L2[2], f.L2[3]) + 1 + tkc;
   uint64_t nb = xb + (xa <= f.primary && xa + r.x2 - 1 >= f.primary);
 #pragma unroll
   for (int s = 3; s > 0; --s)
-    if (s > r.c) nb += tl[s] - tk[s];
-  o2 = tl[r.c] - tk[r.c];
+    if (s > c) nb += tl[s] - tk[s];
+  o2 = tlc - tkc;
   if (r.back) { o0 = na; o1 = nb; } else { o1 = na; o0 = nb; }
 }
 
