@@ -552,8 +552,9 @@ def main():
 
     hostlib.bq_session_align_stream.restype = C.c_int64
     sam_bytes = full_step()  # warm-up (single batch, unpipelined)
-    # warm-up of the pipeline itself (page-locked staging slots are allocated on first use)
-    hostlib.bq_session_align_stream(sess, C.c_int(max(3, args.warmup)), C.c_int(n_reads), reads_c.ctypes.data_as(C.c_void_p),
+    # warm-up of the pipeline itself: page-locked staging slots are allocated on first use (~50-90 ms each) and up to
+    # five batches are in flight, so six warm-up batches bring the slot pool to its steady state
+    hostlib.bq_session_align_stream(sess, C.c_int(max(6, args.warmup)), C.c_int(n_reads), reads_c.ctypes.data_as(C.c_void_p),
                                     C.c_int(reads.shape[1]), rlens.ctypes.data_as(C.c_void_p), None)
     barrier()
     t2 = time.perf_counter()

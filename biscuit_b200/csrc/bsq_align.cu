@@ -393,7 +393,10 @@ static int launch_chain_warp(cudaStream_t s, const bsq_devopt_t &opt, const bsq_
 
 // Chains -> regions, one WARP per task: the control flow of mem_chain2region runs uniformly in all
 // lanes, every banded extension is spread over the lanes (bsq_ksw_warp.cuh), lane 0 stores.
-__global__ void __launch_bounds__(128, 8) k_region(const __grid_constant__ bsq_devopt_t opt, const __grid_constant__ bsq_devidx_t ix, int64_t n_tasks, const uint8_t *seqs, int stride,
+#ifndef BSQ_REGION_CTAS
+#define BSQ_REGION_CTAS 8
+#endif
+__global__ void __launch_bounds__(128, BSQ_REGION_CTAS) k_region(const __grid_constant__ bsq_devopt_t opt, const __grid_constant__ bsq_devidx_t ix, int64_t n_tasks, const uint8_t *seqs, int stride,
                                                 const int32_t *lens, const uint8_t *parent, const int64_t *sa_off,
                                                 const bsq_chain_t *ochains, const bsq_seed_t *oseeds, const int32_t *n_chains,
                                                 const float *frac_rep, uint64_t *srt, bsq_reg_t *regs_tmp, int32_t *n_regs) {

@@ -635,6 +635,7 @@ static int *select_format(const bq_opt_t *opt, const bq_ref_t *ref, bq_read_t *s
 
 void bq_reg2sam_se(const bq_opt_t *opt, const bq_ref_t *ref, bq_read_t *s, bq_regv_t *regs, const char *rg_id) {
   bq_str_t str = {0, 0, 0};
+  bq_str_reserve(&str, 2 * (size_t)s->l_seq0 + 400);
   int n, *to = select_format(opt, ref, s, regs, &n);
   if (n > 0) for (int i = 0; i < n; ++i) format_sam(opt, ref, &str, s, &regs->a[to[i]], 0, regs, !i, 0, rg_id);
   else {
@@ -662,6 +663,7 @@ static void reg2sam_pe_nopairing(const bq_opt_t *opt, const bq_ref_t *ref, bq_re
   }
   for (i = 0; i < 2; ++i) {
     bq_str_t str = {0, 0, 0};
+    bq_str_reserve(&str, 2 * (size_t)s[i].l_seq0 + 400);
     if (n_to[i]) {
       for (int j = 0; j < n_to[i]; ++j) format_sam(opt, ref, &str, &s[i], &regs[i].a[to[i][j]], best[!i], &regs[i], !j, &pes, rg_id);
     } else format_sam(opt, ref, &str, &s[i], best[i], best[!i], 0, 1, &pes, rg_id);
@@ -725,6 +727,7 @@ void bq_reg2sam_pe(const bq_opt_t *opt, const bq_ref_t *ref, uint64_t id, bq_rea
   for (i = 0; i < 2; ++i) {
     bq_str_t str = {0, 0, 0};
     bq_regv_t *r = &regs[i];
+    bq_str_reserve(&str, 2 * (size_t)s[i].l_seq0 + 400);  /* one allocation for the usual single-line record */
     format_sam(opt, ref, &str, &s[i], r->a + z[i], regs[!i].a + z[!i], r, 1, &pes, rg_id);
     if (r->n_pri < r->n) {
       bq_reg_t *p = &r->a[r->n_pri];
