@@ -99,6 +99,11 @@ typedef struct {
    * batch) instead of three allocations per read; bq_reads_free knows both conventions */
   char *slab;
   uint8_t in_slab;
+  /* phase 2 writes the SAM text of a batch into one buffer per worker thread; .sam then points into it
+   * (sam_in_slab) and the buffers hang off the first read of the batch */
+  uint8_t sam_in_slab;
+  int n_sam_slabs;
+  char **sam_slabs;
 } bq_read_t;
 
 /* ---- alignment region: mem_alnreg_t (lib/aln/mem_alnreg.h:34-66) ---- */
@@ -150,12 +155,31 @@ bq_swr_t bq_local_align(int qlen, uint8_t *query, int tlen, uint8_t *target, con
 uint32_t *bq_gen_cigar(const int8_t mat[25], int o_del, int e_del, int o_ins, int e_ins, int w_, int64_t l_pac, const uint8_t *pac,
                        int l_query, uint8_t *query, int64_t rb, int64_t re, int *score, int *n_cigar, int *NM, uint32_t *ZC, uint32_t *ZR,
                        int *bss_u, uint8_t parent);
-void bq_kputs(bq_str_t *s, const char *p);
-void bq_kputsn(bq_str_t *s, const char *p, size_t n);
-void bq_kputc(bq_str_t *s, int c);
-void bq_kputw(bq_str_t *s, int v);
-void bq_kputl(bq_str_t *s, long v);
-void bq_str_reserve(bq_str_t *s, size_t extra);
+/* string buffer (kstring-like); inline: SAM formatting calls these ~100 times per record */
+#include <stdlib.h>
+#include <string.h>
+static inline void bq_str_reserve(bq_str_t *s, size_t extra) {
+  if (s->l + extra + 1 > s->m) {
+    size_t m = s->m ? s->m : 64;
+    while (m < s->l + extra + 1) m <<= 1;
+    s->s = (char *)realloc(s->s, m);
+    s->m = m;
+  }
+}
+static inline void bq_kputsn(bq_str_t *s, const char *p, size_t n) { bq_str_reserve(s, n); memcpy(s->s + s->l, p, n); s->l += n; s->s[s->l] = 0; }
+static inline void bq_kputs(bq_str_t *s, const char *p) { bq_kputsn(s, p, strlen(p)); }
+static inline void bq_kputc(bq_str_t *s, int c) { bq_str_reserve(s, 1); s->s[s->l++] = (char)c; s->s[s->l] = 0; }
+static inline void bq_kputl(bq_str_t *s, long v) { /* decimal without printf: numbers are a large share of the SAM text */
+  char b[24];
+  int n = 0;
+  unsigned long u = v < 0 ? 0ul - (unsigned long)v : (unsigned long)v;
+  do { b[n++] = (char)('0' + u % 10); u /= 10; } while (u);
+  if (v < 0) b[n++] = '-';
+  bq_str_reserve(s, (size_t)n);
+  while (n) s->s[s->l++] = b[--n];
+  s->s[s->l] = 0;
+}
+static inline void bq_kputw(bq_str_t *s, int v) { bq_kputl(s, v); }
 
 /* bq_phase2.c */
 void bq_merge_regions(const bq_opt_t *opt, const bq_ref_t *ref, const uint8_t *query, int l_query, bq_regv_t *regs);

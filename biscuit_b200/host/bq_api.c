@@ -66,10 +66,9 @@ int64_t bq_session_align(bq_session *s, int64_t n_processed, int n, const uint8_
     int64_t l = rd[i].sam ? (int64_t)strlen(rd[i].sam) : 0;
     if (sam_out && tot + l < cap) memcpy(sam_out + tot, rd[i].sam, (size_t)l);
     tot += l;
-    free(rd[i].sam); free(rd[i].seq0); free(rd[i].qual); free(rd[i].name);
   }
   if (sam_out && tot < cap) sam_out[tot] = 0;
-  free(rd);
+  bq_reads_free(rd, n);
   return rc ? rc : tot;
 }
 

@@ -65,28 +65,7 @@ uint64_t bq_hash64(uint64_t key) { /* utils.h:107 */
 
 /* ---------------- string buffer ---------------- */
 
-void bq_str_reserve(bq_str_t *s, size_t extra) {
-  if (s->l + extra + 1 > s->m) {
-    size_t m = s->m ? s->m : 64;
-    while (m < s->l + extra + 1) m <<= 1;
-    s->s = realloc(s->s, m);
-    s->m = m;
-  }
-}
-void bq_kputsn(bq_str_t *s, const char *p, size_t n) { bq_str_reserve(s, n); memcpy(s->s + s->l, p, n); s->l += n; s->s[s->l] = 0; }
-void bq_kputs(bq_str_t *s, const char *p) { bq_kputsn(s, p, strlen(p)); }
-void bq_kputc(bq_str_t *s, int c) { bq_str_reserve(s, 1); s->s[s->l++] = (char)c; s->s[s->l] = 0; }
-void bq_kputl(bq_str_t *s, long v) { /* decimal without printf: numbers are a large share of the SAM text */
-  char b[24];
-  int n = 0;
-  unsigned long u = v < 0 ? 0ul - (unsigned long)v : (unsigned long)v;
-  do { b[n++] = (char)('0' + u % 10); u /= 10; } while (u);
-  if (v < 0) b[n++] = '-';
-  bq_str_reserve(s, (size_t)n);
-  while (n) s->s[s->l++] = b[--n];
-  s->s[s->l] = 0;
-}
-void bq_kputw(bq_str_t *s, int v) { bq_kputl(s, v); }
+/* bq_str_reserve / bq_kput*: static inline in bq.h */
 
 /* ---------------- introsort with klib's exact comparison/swap sequence (ksort.h:150-233) ---------------- */
 

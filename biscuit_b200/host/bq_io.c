@@ -199,11 +199,15 @@ bq_read_t *bq_read_batch(int chunk_size, int has_bc, int keep_comment, int *n_, 
 void bq_reads_free(bq_read_t *seqs, int n) {
   if (!seqs) return;
   char *slab = n > 0 ? seqs[0].slab : 0;
+  char **sam_slabs = n > 0 ? seqs[0].sam_slabs : 0;
+  const int n_sam_slabs = n > 0 ? seqs[0].n_sam_slabs : 0;
   for (int i = 0; i < n; ++i) {
     if (!seqs[i].in_slab) { free(seqs[i].name); free(seqs[i].seq0); free(seqs[i].qual); }
     free(seqs[i].comment); free(seqs[i].barcode); free(seqs[i].umi);
-    free(seqs[i].sam);
+    if (!seqs[i].sam_in_slab) free(seqs[i].sam);
   }
+  for (int k = 0; k < n_sam_slabs; ++k) free(sam_slabs[k]);
+  free(sam_slabs);
   free(slab);
   free(seqs);
 }

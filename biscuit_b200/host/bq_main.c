@@ -255,8 +255,8 @@ int bq_main_align(int argc, char **argv) {
     }
     if (seq2) opt.flag |= BQ_F_PE;
     if ((rc = bq_process_seqs(&opt, al, &idx.ref, 0, n, seqs, pes0, rg_id))) bq_fatal("alignment failed: %s (%s)", bsq_strerror(rc), bsq_last_error());
-    for (i = 0; i < n; ++i) { if (seqs[i].sam) fputs(seqs[i].sam, stdout); free(seqs[i].name); free(seqs[i].seq0); free(seqs[i].sam); }
-    free(seqs);
+    for (i = 0; i < n; ++i) if (seqs[i].sam) fputs(seqs[i].sam, stdout);
+    bq_reads_free(seqs, n);
   } else {
     src_ctx_t sc = {&opt, f1, f2, chunk, copy_comment};
     if ((rc = bq_pipeline_run(&opt, &idx.ref, al, al2, fastq_source, &sc, sam_sink, 0, pes0, rg_id)))

@@ -8,6 +8,13 @@
 #include <stdlib.h>
 #include <string.h>
 #include "bq.h"
+#include <pthread.h>
+#include <time.h>
+/* BQ_PROF=1: thread-seconds per part of phase 2, printed per batch (diagnostics) */
+static int g_prof = -1;
+static double g_t_mate, g_t_mark, g_t_sam, g_t_pair, g_t_setsam, g_t_fmt;
+static pthread_mutex_t g_prof_mu = PTHREAD_MUTEX_INITIALIZER;
+static double bq_now(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + ts.tv_nsec * 1e-9; }
 
 #define MINV(a, b) ((a) < (b) ? (a) : (b))
 #define MAXV(a, b) ((a) > (b) ? (a) : (b))
@@ -162,7 +169,17 @@ bq_pestat_t bq_pestat(const bq_opt_t *opt, const bq_ref_t *ref, int n, const bq_
     pes.failed = 1;
     return pes;
   }
-  bq_introsort(isz, n_is, sizeof(int64_t), lt_i64);
+  /* ascending order (ks_introsort_64, mem_pair.c:104).  The keys are plain integers in [-max_ins, max_ins], so any
+   * correct sort gives the same array; a counting sort replaces ~1.7 M comparator calls per batch on this serial path */
+  if (opt->max_ins > 0 && opt->max_ins <= (1 << 22)) {
+    const int64_t lo = -(int64_t)opt->max_ins, range = 2 * (int64_t)opt->max_ins + 1;
+    uint32_t *cnt = calloc((size_t)range, sizeof(uint32_t));
+    for (size_t k = 0; k < n_is; ++k) ++cnt[isz[k] - lo];
+    size_t o = 0;
+    for (int64_t v = 0; v < range; ++v)
+      for (uint32_t c = cnt[v]; c > 0; --c) isz[o++] = v + lo;
+    free(cnt);
+  } else bq_introsort(isz, n_is, sizeof(int64_t), lt_i64);
   int p25 = (int)isz[(int)(.25 * n_is + .499)], p50 = (int)isz[(int)(.50 * n_is + .499)], p75 = (int)isz[(int)(.75 * n_is + .499)];
   pes.low = (int)(p25 - 2.0 * (p75 - p25) + .499);
   pes.high = (int)(p75 + 2.0 * (p75 - p25) + .499);
@@ -690,7 +707,9 @@ void bq_reg2sam_pe(const bq_opt_t *opt, const bq_ref_t *ref, uint64_t id, bq_rea
   }
   if (is_multi[0] || is_multi[1]) { reg2sam_pe_nopairing(opt, ref, s, regs, pes, rg_id); return; }
   int pscore, sub_pscore, n_sub, z[2] = {0, 0};
+  const double q0 = g_prof > 0 ? bq_now() : 0;
   pair_regs(opt, ref, pes, regs, (int)id, &pscore, &sub_pscore, &n_sub, z);
+  if (g_prof > 0) { const double q1 = bq_now(); pthread_mutex_lock(&g_prof_mu); g_t_pair += q1 - q0; pthread_mutex_unlock(&g_prof_mu); }
   if (pscore <= 0) { reg2sam_pe_nopairing(opt, ref, s, regs, pes, rg_id); return; }
   int score_unpaired = regs[0].a[0].score + regs[1].a[0].score - opt->pen_unpaired;
   if (pscore > score_unpaired) {
@@ -723,7 +742,9 @@ void bq_reg2sam_pe(const bq_opt_t *opt, const bq_ref_t *ref, uint64_t id, bq_rea
       r->a[z[i]].secondary_all = -1;
     }
   }
+  const double q2 = g_prof > 0 ? bq_now() : 0;
   for (i = 0; i < 2; ++i) set_sam(opt, ref, &s[i], &regs[i].a[z[i]]);
+  if (g_prof > 0) { const double q3 = bq_now(); pthread_mutex_lock(&g_prof_mu); g_t_setsam += q3 - q2; pthread_mutex_unlock(&g_prof_mu); }
   for (i = 0; i < 2; ++i) {
     bq_str_t str = {0, 0, 0};
     bq_regv_t *r = &regs[i];
@@ -777,8 +798,6 @@ void bq_read_clipping(bq_read_t *s, const uint8_t *adaptor, int l_adaptor, const
 }
 
 /* ---------------- the batch driver: mem_process_seqs (bwamem.c:432-476) ---------------- */
-#include <time.h>
-static double bq_now(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + ts.tv_nsec * 1e-9; }
 
 
 typedef struct {
@@ -786,6 +805,9 @@ typedef struct {
   const char *rg_id; int n_items, n_threads, pe, stage;
   const bsq_reg *dev_regs; const int64_t *reg_off; const int64_t *task_of_read; /* first task of each read */
   const uint8_t *n_task_of_read;
+  bq_str_t *sam_slab;   /* per worker thread: SAM text of the reads it formatted */
+  size_t *sam_off;      /* per read: offset of its text in its thread's slab */
+  uint8_t *sam_thr;     /* per read: which thread's slab */
 } work_t;
 
 static void reg_from_dev(const bsq_reg *d, bq_reg_t *r) {
@@ -794,10 +816,15 @@ static void reg_from_dev(const bsq_reg *d, bq_reg_t *r) {
   r->seedcov = d->seedcov; r->seedlen0 = d->seedlen0; r->frac_rep = d->frac_rep; r->bss = d->bss; r->parent = d->parent;
 }
 
-static void work_item(work_t *w, long i) {
+static void work_item(work_t *w, long i, int tid) {
   if (w->stage == 1) { /* gather the regions of read i in the reference's order and merge them */
     bq_regv_t *rv = &w->regs[i];
     rv->n = rv->m = rv->n_pri = 0; rv->a = 0;
+    {
+      size_t tot = 0;
+      for (int t = 0; t < w->n_task_of_read[i]; ++t) tot += (size_t)(w->reg_off[w->task_of_read[i] + t + 1] - w->reg_off[w->task_of_read[i] + t]);
+      if (tot) { rv->m = tot + 2; rv->a = malloc(rv->m * sizeof(bq_reg_t)); }  /* one allocation (+2: mate rescue may add hits) */
+    }
     for (int t = 0; t < w->n_task_of_read[i]; ++t) {
       const int64_t task = w->task_of_read[i] + t;
       for (int64_t k = w->reg_off[task]; k < w->reg_off[task + 1]; ++k) { bq_reg_t r; reg_from_dev(&w->dev_regs[k], &r); regv_push(rv, &r); }
@@ -808,15 +835,35 @@ static void work_item(work_t *w, long i) {
     for (size_t k = 0; k < w->regs[i].n; ++k) w->regs[i].a[k].flag = 0;
     bq_reg2sam_se(w->opt, w->ref, &w->seqs[i], &w->regs[i], w->rg_id);
   } else {
+    const double p0 = g_prof > 0 ? bq_now() : 0;
     if (!(w->opt->flag & BQ_F_NO_RESCUE)) bq_matesw(w->opt, w->ref, w->pes, &w->seqs[i << 1], &w->regs[i << 1]);
+    const double p1 = g_prof > 0 ? bq_now() : 0;
     bq_mark_primary(w->opt, &w->regs[i << 1 | 0], i << 1 | 0); /* PE ids lack n_processed (bwamem.c:408,413) */
     bq_mark_primary(w->opt, &w->regs[i << 1 | 1], i << 1 | 1);
     for (int e = 0; e < 2; ++e)
       for (size_t k = 0; k < w->regs[i << 1 | e].n; ++k) w->regs[i << 1 | e].a[k].flag = 0;
+    const double p2 = g_prof > 0 ? bq_now() : 0;
     bq_reg2sam_pe(w->opt, w->ref, (uint64_t)((w->n_processed >> 1) + i), &w->seqs[i << 1], &w->regs[i << 1], w->pes, w->rg_id);
+    if (g_prof > 0) {
+      const double p3 = bq_now();
+      pthread_mutex_lock(&g_prof_mu);
+      g_t_mate += p1 - p0; g_t_mark += p2 - p1; g_t_sam += p3 - p2;
+      pthread_mutex_unlock(&g_prof_mu);
+    }
   }
   if (w->stage == 2) { /* the regions of this item are done with: release them here, on the worker */
     const long lo = w->pe ? i << 1 : i, hi = w->pe ? (i << 1) + 2 : i + 1;
+    for (long r = lo; r < hi; ++r) { /* move the text into this thread's slab (allocated and freed by the same thread) */
+      bq_read_t *rd = &w->seqs[r];
+      if (!rd->sam) continue;
+      bq_str_t *sl = &w->sam_slab[tid];
+      const size_t l = strlen(rd->sam);
+      if (sl->m == 0) bq_str_reserve(sl, (size_t)(w->n_items / w->n_threads + 1) * (w->pe ? 2 : 1) * (l + 64));
+      w->sam_off[r] = sl->l; w->sam_thr[r] = (uint8_t)tid;
+      bq_kputsn(sl, rd->sam, l + 1); /* with the terminating NUL */
+      free(rd->sam);
+      rd->sam = 0; rd->sam_in_slab = 1;
+    }
     for (long r = lo; r < hi; ++r) {
       for (size_t k = 0; k < w->regs[r].n; ++k) if (w->regs[r].a[k].n_cigar > 0) free(w->regs[r].a[k].cigar);
       free(w->regs[r].a);
@@ -828,13 +875,15 @@ static void work_item(work_t *w, long i) {
 typedef struct { work_t *w; int tid; } thr_t;
 static void *thr_main(void *a) {
   thr_t *t = a;
-  for (long i = t->tid; i < t->w->n_items; i += t->w->n_threads) work_item(t->w, i);
+  for (long i = t->tid; i < t->w->n_items; i += t->w->n_threads) work_item(t->w, i, t->tid);
   return 0;
 }
 static void run_threads(work_t *w, int n_items) {
   w->n_items = n_items;
   int nt = w->n_threads < 1 ? 1 : w->n_threads;
-  if (nt == 1) { for (long i = 0; i < n_items; ++i) work_item(w, i); return; }
+  if (nt > 255) nt = 255;
+  w->n_threads = nt;
+  if (nt == 1) { for (long i = 0; i < n_items; ++i) work_item(w, i, 0); return; }
   pthread_t *th = malloc(sizeof(pthread_t) * (size_t)nt);
   thr_t *ta = malloc(sizeof(thr_t) * (size_t)nt);
   for (int t = 0; t < nt; ++t) { ta[t].w = w; ta[t].tid = t; pthread_create(&th[t], 0, thr_main, &ta[t]); }
@@ -991,8 +1040,27 @@ void bq_batch_finish(const bq_opt_t *opt, const bq_ref_t *ref, bq_batch_t *b, co
   if (pe) { if (pes0) w.pes = *pes0; else w.pes = bq_pestat(opt, ref, n, w.regs); }
   w.stage = 2;
   double t1_ = t0_ > 0 ? bq_now() : 0;
+  if (g_prof < 0) g_prof = getenv("BQ_PROF") != 0;
+  g_t_mate = g_t_mark = g_t_sam = g_t_pair = g_t_setsam = g_t_fmt = 0;
+  {
+    const int nt = opt->n_threads < 1 ? 1 : (opt->n_threads > 255 ? 255 : opt->n_threads);
+    w.sam_slab = calloc((size_t)nt, sizeof(bq_str_t));
+    w.sam_off = malloc(sizeof(size_t) * (size_t)(n + 1));
+    w.sam_thr = malloc((size_t)n + 1);
+  }
   run_threads(&w, pe ? n >> 1 : n);
+  if (n > 0) { /* .sam pointers into the (now final) slabs; the slabs belong to the first read of the batch */
+    const int nt = w.n_threads;
+    for (int i = 0; i < n; ++i)
+      if (b->seqs[i].sam_in_slab) b->seqs[i].sam = w.sam_slab[w.sam_thr[i]].s + w.sam_off[i];
+    b->seqs[0].sam_slabs = malloc(sizeof(char *) * (size_t)nt);
+    b->seqs[0].n_sam_slabs = nt;
+    for (int k = 0; k < nt; ++k) b->seqs[0].sam_slabs[k] = w.sam_slab[k].s;
+  }
+  free(w.sam_slab); free(w.sam_off); free(w.sam_thr);
   if (t0_ > 0) fprintf(stderr, " pestat %.3f phase2 %.3f s\n", t1_ - tm_, bq_now() - t1_);
+  if (g_prof > 0) fprintf(stderr, "[bq_prof] thread-seconds: matesw %.3f mark_primary %.3f reg2sam %.3f (pair %.3f set_sam %.3f format %.3f)\n",
+                          g_t_mate, g_t_mark, g_t_sam, g_t_pair, g_t_setsam, g_t_fmt);
   free(w.regs);
   batch_free(b);
 }
