@@ -69,8 +69,8 @@ struct bsq_cw_scalar {
 
 // filter order: sort (weight << 16 | chain) by weight only, descending -- the chain id rides along but takes no part
 // in the comparison, so the comparison/swap sequence is the reference's (flt_lt, memchain.c:402)
-struct bsq_cw_by_weight {
-  BSQ_HD bool operator()(uint64_t a, uint64_t b) const { return (a >> 16) > (b >> 16); }
+struct bsq_cw_by_weight {  // 32-bit keys: weight (at most the read length) << 16 | chain
+  BSQ_HD bool operator()(uint32_t a, uint32_t b) const { return (a >> 16) > (b >> 16); }
 };
 
 // merge_seed_to_chain (memchain.c:227-256) against chain L (created by seed L)
@@ -216,15 +216,21 @@ BSQ_HD int bsq_chain_warp(const bsq_devopt_t &opt, const bsq_devidx_t &ix, int p
     s.c_w[a] = bsq_cw_weight(s, a);
   }
   W::sync();
+  {  // a weight that does not fit the 16-bit key field cannot occur for reads of at most BSQ_MAX_READ_LEN bases
+    bool big = false;
+    for (int c = lane; c < n_ch; c += NL) big |= s.c_w[s.clist[c]] >= 65536;
+    if (W::any(big)) return BSQ_CW_FALLBACK;
+  }
   if (lane == 0) {
+    uint32_t *k32 = reinterpret_cast<uint32_t *>(s.key);  // the position keys are no longer needed
     int k = 0;
     for (int c = 0; c < n_ch; ++c) {
       const int a = s.clist[c];
-      if (s.c_w[a] >= opt.min_chain_weight) s.key[k++] = (uint64_t)(uint32_t)s.c_w[a] << 16 | (uint64_t)a;
+      if (s.c_w[a] >= opt.min_chain_weight) k32[k++] = (uint32_t)s.c_w[a] << 16 | (uint32_t)a;
     }
     n_ch = k;
-    bsq_introsort(s.key, (int64_t)n_ch, bsq_cw_by_weight());
-    for (int c = 0; c < n_ch; ++c) s.ord[c] = (uint16_t)(s.key[c] & 0xffff);
+    bsq_introsort(k32, (int64_t)n_ch, bsq_cw_by_weight());
+    for (int c = 0; c < n_ch; ++c) s.ord[c] = (uint16_t)(k32[c] & 0xffff);
     if (n_ch > 0) { s.c_kept[s.ord[0]] = 3; s.keep[0] = 0; }
     s.pub[0] = n_ch;
   }
