@@ -11,6 +11,7 @@
 #include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <zlib.h>
 #include "bq_plp.h"
 
@@ -76,9 +77,13 @@ static void *inflate_worker(void *arg) {
   return 0;
 }
 
+double bq_bgzf_t_read, bq_bgzf_t_inflate, bq_plp_t_fill; /* diagnostics (BSQ_PLP_TIMING) */
+static double bam_now(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + ts.tv_nsec * 1e-9; }
+
 /* read and inflate the next batch of blocks behind the unread bytes; returns bytes added (0 at EOF) */
 static size_t bgzf_refill(bq_bgzf_t *b) {
   if (b->eof) return 0;
+  const double t0_ = bam_now();
   if (b->ubeg > 0) { /* keep the unread tail at the front */
     memmove(b->u, b->u + b->ubeg, b->uend - b->ubeg);
     b->uend -= b->ubeg; b->ubeg = 0;
@@ -116,6 +121,8 @@ static size_t bgzf_refill(bq_bgzf_t *b) {
     coff += clen; uoff += ulen;
   }
   if (b->n_blk == 0) return 0;
+  const double t1_ = bam_now();
+  bq_bgzf_t_read += t1_ - t0_;
   int nt = b->n_threads < b->n_blk ? b->n_threads : b->n_blk;
   inflate_job_t jobs[64];
   pthread_t th[64];
@@ -130,6 +137,7 @@ static size_t bgzf_refill(bq_bgzf_t *b) {
   for (int t = 0; t < nt; ++t) if (jobs[t].err) bq_fatal("[bgzf] %s: inflate/CRC error\n", b->fn);
   const size_t added = uoff - b->uend;
   b->uend = uoff;
+  bq_bgzf_t_inflate += bam_now() - t1_;
   return added;
 }
 
@@ -279,19 +287,21 @@ static int32_t mc_rlen(const char *mc) {
 /* The batch arrays are page-locked (bsq_host_alloc) so that bsq_plp_stage copies them at full PCIe speed; they only
  * ever grow and batches are reused, so the (slow) pinned allocations amortise. */
 static int g_pinned = 1; /* bamdump (no device involved) switches to plain memory */
-static void batch_mem_free(void *p) { if (!p) return; if (g_pinned) bsq_host_free(p); else free(p); }
-static void *pinned_grow(void *old, size_t old_bytes, size_t new_bytes) {
+static void batch_mem_free(void *p, int pinned) { if (!p) return; if (pinned) bsq_host_free(p); else free(p); }
+#define BATCH_PINNED(B) (g_pinned && !(B)->plain)
+static void *pinned_grow(void *old, size_t old_bytes, size_t new_bytes, int pinned) {
   void *p = 0;
-  if (!g_pinned) { p = malloc(new_bytes); if (!p) bq_fatal("[pileup] out of memory\n"); }
+  if (!pinned) { p = malloc(new_bytes); if (!p) bq_fatal("[pileup] out of memory\n"); }
   else if (bsq_host_alloc(&p, new_bytes) != 0) bq_fatal("[pileup] cannot allocate %zu bytes of page-locked memory: %s\n", new_bytes, bsq_last_error());
-  if (old) { memcpy(p, old, old_bytes); batch_mem_free(old); }
+  if (old) { memcpy(p, old, old_bytes); batch_mem_free(old, pinned); }
   return p;
 }
 #define GROW(ptr, n, cap, extra)                                                                              \
   do {                                                                                                        \
     if ((n) + (extra) > (cap)) {                                                                              \
-      const int64_t ncap_ = ((n) + (extra)) * 2 + (1 << 16);                                                   \
-      (ptr) = pinned_grow((ptr), (size_t)(n) * sizeof *(ptr), (size_t)ncap_ * sizeof *(ptr));                 \
+      int64_t ncap_ = ((n) + (extra)) * 5 / 4 + (1 << 16);                                                     \
+      if (pin_ && ncap_ < (int64_t)(1 << 20)) ncap_ = (int64_t)(1 << 20); /* page-locking is slow: few, large steps */ \
+      (ptr) = pinned_grow((ptr), (size_t)(n) * sizeof *(ptr), (size_t)ncap_ * sizeof *(ptr), pin_);                 \
       (cap) = ncap_;                                                                                          \
     }                                                                                                         \
   } while (0)
@@ -301,14 +311,16 @@ void bq_plp_batch_reset(bq_plp_batch_t *B) { B->n = 0; B->n_cig = 0; B->n_seq = 
 void bq_plp_batch_free(bq_plp_batch_t *B) {
   void *ps[] = {B->pos, B->mpos, B->mate_rlen, B->l_qseq, B->nm, B->as, B->flag, B->mapq, B->bss_tag, B->sid, B->n_cigar, B->cigar_off, B->cigar,
                 B->seq_off, B->seq, B->qual_off, B->qual, B->end};
-  for (size_t i = 0; i < sizeof ps / sizeof ps[0]; ++i) batch_mem_free(ps[i]);
+  for (size_t i = 0; i < sizeof ps / sizeof ps[0]; ++i) batch_mem_free(ps[i], BATCH_PINNED(B));
   memset(B, 0, sizeof *B);
 }
 
 static void batch_room(bq_plp_batch_t *B, int64_t n_cig, int64_t n_seq, int64_t n_qual) {
+  const int pin_ = BATCH_PINNED(B);
   if (B->n + 1 > B->cap) {
-    const int64_t ncap = (B->n + 1) * 2 + (1 << 14);
-#define R(f) B->f = pinned_grow(B->f, (size_t)B->n * sizeof *B->f, (size_t)ncap * sizeof *B->f)
+    int64_t ncap = (B->n + 1) * 2 + (1 << 14);
+    if (pin_ && ncap < 262144) ncap = 262144;
+#define R(f) B->f = pinned_grow(B->f, (size_t)B->n * sizeof *B->f, (size_t)ncap * sizeof *B->f, pin_)
     R(pos); R(mpos); R(mate_rlen); R(l_qseq); R(nm); R(as); R(flag); R(mapq); R(bss_tag); R(sid); R(n_cigar); R(cigar_off); R(seq_off);
     R(qual_off); R(end);
 #undef R
@@ -319,9 +331,9 @@ static void batch_room(bq_plp_batch_t *B, int64_t n_cig, int64_t n_seq, int64_t 
   GROW(B->qual, B->n_qual, B->cap_qual, n_qual);
 }
 
-/* Append BAM record `r` (after block_size) of sample `sid`.  Returns 0, or -1 if the record was dropped
- * because it can never produce an event (unmapped / no CIGAR). */
-int bq_plp_batch_push(bq_plp_batch_t *B, const uint8_t *r, uint32_t len, int sid) {
+/* Fill slot i of the batch from BAM record `r` (after block_size); the variable-length parts go to the given offsets
+ * (the caller has made room). */
+static void batch_fill1(bq_plp_batch_t *B, int64_t i, int64_t cig_off, int64_t seq_off, int64_t qual_off, const uint8_t *r, uint32_t len, int sid) {
   const int32_t pos = (int32_t)le32(r + 4);
   const uint32_t l_read_name = r[8], mapq = r[9], n_cig = le16(r + 12), flag = le16(r + 14);
   const int32_t l_seq = (int32_t)le32(r + 16), mpos = (int32_t)le32(r + 24);
@@ -330,21 +342,17 @@ int bq_plp_batch_push(bq_plp_batch_t *B, const uint8_t *r, uint32_t len, int sid
   const uint8_t *qual = seq + ((size_t)l_seq + 1) / 2;
   const uint8_t *aux = qual + l_seq, *end = r + len;
   if (aux > end) bq_fatal("[bam] corrupt record\n");
-  if (n_cig == 0) return -1;
-  batch_room(B, n_cig, ((int64_t)l_seq + 1) / 2, l_seq);
-  const int64_t i = B->n;
   B->pos[i] = pos; B->mpos[i] = mpos; B->l_qseq[i] = l_seq; B->flag[i] = (uint16_t)flag; B->mapq[i] = (uint8_t)mapq; B->sid[i] = (uint8_t)sid;
-  B->n_cigar[i] = (int32_t)n_cig; B->cigar_off[i] = B->n_cig; B->seq_off[i] = B->n_seq; B->qual_off[i] = B->n_qual;
+  B->n_cigar[i] = (int32_t)n_cig; B->cigar_off[i] = cig_off; B->seq_off[i] = seq_off; B->qual_off[i] = qual_off;
   int64_t rlen = 0;
   for (uint32_t k = 0; k < n_cig; ++k) {
     const uint32_t c = le32(cig + 4 * k), op = c & 0xf;
-    B->cigar[B->n_cig + k] = c;
+    B->cigar[cig_off + k] = c;
     if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rlen += c >> 4;
   }
   B->end[i] = (int64_t)pos + (rlen > 0 ? rlen : 1);
-  memcpy(B->seq + B->n_seq, seq, ((size_t)l_seq + 1) / 2);
-  memcpy(B->qual + B->n_qual, qual, (size_t)l_seq);
-  B->n_cig += n_cig; B->n_seq += ((int64_t)l_seq + 1) / 2; B->n_qual += l_seq;
+  memcpy(B->seq + seq_off, seq, ((size_t)l_seq + 1) / 2);
+  memcpy(B->qual + qual_off, qual, (size_t)l_seq);
   /* tags read by process_func (src/pileup.c:709-746) */
   const uint8_t *t;
   t = aux_get(aux, end, "NM"); B->nm[i] = t ? (int32_t)aux2i(t) : INT32_MIN;
@@ -360,8 +368,91 @@ int bq_plp_batch_push(bq_plp_batch_t *B, const uint8_t *r, uint32_t len, int sid
     if (t && *t == 'Z') { if (strcmp((const char *)t + 1, "CT") == 0) bss = 0; else if (strcmp((const char *)t + 1, "GA") == 0) bss = 1; }
   }
   B->bss_tag[i] = (int8_t)bss;
+}
+
+/* Append BAM record `r` (after block_size) of sample `sid`.  Returns 0, or -1 if the record was dropped
+ * because it can never produce an event (unmapped / no CIGAR). */
+int bq_plp_batch_push(bq_plp_batch_t *B, const uint8_t *r, uint32_t len, int sid) {
+  const uint32_t n_cig = le16(r + 12);
+  const int32_t l_seq = (int32_t)le32(r + 16);
+  if (n_cig == 0) return -1;
+  batch_room(B, n_cig, ((int64_t)l_seq + 1) / 2, l_seq);
+  batch_fill1(B, B->n, B->n_cig, B->n_seq, B->n_qual, r, len, sid);
+  B->n_cig += n_cig; B->n_seq += ((int64_t)l_seq + 1) / 2; B->n_qual += l_seq;
   B->n++;
   return 0;
+}
+
+/* ---- bulk append: every following record of reference `tid` that starts before pos_lt ----
+ * The record headers of the inflated window are walked serially (a few nanoseconds each: sizes and offsets), the
+ * records are then decoded into the batch by n_threads threads.  Returns 1 when the stream has moved past the range
+ * (next record belongs to another reference / starts at or after pos_lt / end of file), 0 never. */
+typedef struct { const uint8_t *r; uint32_t len; int64_t cig_off, seq_off, qual_off; } rec_ref_t;
+typedef struct { bq_plp_batch_t *B; const rec_ref_t *recs; int64_t base, lo, hi; int sid; } fill_job_t;
+static void *fill_worker(void *arg) {
+  fill_job_t *j = arg;
+  for (int64_t k = j->lo; k < j->hi; ++k)
+    batch_fill1(j->B, j->base + k, j->recs[k].cig_off, j->recs[k].seq_off, j->recs[k].qual_off, j->recs[k].r, j->recs[k].len, j->sid);
+  return 0;
+}
+
+int bq_plp_batch_fill(bq_plp_batch_t *B, bq_bgzf_t *b, int sid, int tid, int64_t pos_lt, int n_threads) {
+  const int pin_ = BATCH_PINNED(B);
+  rec_ref_t *recs = 0;
+  int64_t cap = 0;
+  for (;;) {
+    uint32_t len0;
+    if (!bq_bam_peek(b, &len0)) return 1; /* end of file */
+    /* walk the complete records that are in the inflated window now */
+    int64_t n = 0, n_cig = 0, n_seq = 0, n_qual = 0;
+    size_t off = b->ubeg;
+    int past = 0;
+    while (off + 4 <= b->uend) {
+      const uint8_t *p = b->u + off;
+      const uint32_t bs = le32(p);
+      if (bs < 32) bq_fatal("[bam] %s: bad record size %u\n", b->fn, bs);
+      if (off + 4 + (size_t)bs > b->uend) break; /* continues in the next window */
+      const uint8_t *r = p + 4;
+      if ((int32_t)le32(r) != tid || (int32_t)le32(r + 4) >= pos_lt) { past = 1; break; }
+      const uint32_t nc = le16(r + 12);
+      const int32_t l_seq = (int32_t)le32(r + 16);
+      if (nc > 0) {
+        if (n == cap) { cap = cap ? cap * 2 : 1 << 16; recs = realloc(recs, (size_t)cap * sizeof *recs); }
+        recs[n].r = r; recs[n].len = bs; recs[n].cig_off = B->n_cig + n_cig; recs[n].seq_off = B->n_seq + n_seq; recs[n].qual_off = B->n_qual + n_qual;
+        ++n; n_cig += nc; n_seq += ((int64_t)l_seq + 1) / 2; n_qual += l_seq;
+      }
+      off += 4 + (size_t)bs;
+    }
+    if (n > 0) {
+      /* room for all of them, then decode in parallel */
+      if (B->n + n > B->cap) {
+        int64_t ncap = (B->n + n) * 5 / 4 + (1 << 14);
+        if (pin_ && ncap < 262144) ncap = 262144;
+#define R(f) B->f = pinned_grow(B->f, (size_t)B->n * sizeof *B->f, (size_t)ncap * sizeof *B->f, pin_)
+        R(pos); R(mpos); R(mate_rlen); R(l_qseq); R(nm); R(as); R(flag); R(mapq); R(bss_tag); R(sid); R(n_cigar); R(cigar_off); R(seq_off);
+        R(qual_off); R(end);
+#undef R
+        B->cap = ncap;
+      }
+      GROW(B->cigar, B->n_cig, B->cap_cig, n_cig);
+      GROW(B->seq, B->n_seq, B->cap_seq, n_seq);
+      GROW(B->qual, B->n_qual, B->cap_qual, n_qual);
+      int nt = n_threads < 1 ? 1 : (n_threads > 32 ? 32 : n_threads);
+      if (n < 4096) nt = 1;
+      const double tf_ = bam_now();
+      fill_job_t jobs[32];
+      pthread_t th[32];
+      for (int t = 0; t < nt; ++t) { jobs[t].B = B; jobs[t].recs = recs; jobs[t].base = B->n; jobs[t].lo = n * t / nt; jobs[t].hi = n * (t + 1) / nt; jobs[t].sid = sid; }
+      for (int t = 1; t < nt; ++t) pthread_create(&th[t], 0, fill_worker, &jobs[t]);
+      fill_worker(&jobs[0]);
+      for (int t = 1; t < nt; ++t) pthread_join(th[t], 0);
+      bq_plp_t_fill += bam_now() - tf_;
+      B->n += n; B->n_cig += n_cig; B->n_seq += n_seq; B->n_qual += n_qual;
+    }
+    b->ubeg = off; /* consumed */
+    if (past) { free(recs); return 1; }
+    /* window exhausted (possibly in the middle of a record): the next peek refills */
+  }
 }
 
 void bq_plp_batch_view(const bq_plp_batch_t *B, bsq_plp_reads *v) {

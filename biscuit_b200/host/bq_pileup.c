@@ -22,6 +22,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <unistd.h>
 #include "bq_plp.h"
 
 enum { B_A = 0, B_C, B_G, B_T, B_N, B_Y, B_R };
@@ -508,7 +509,7 @@ typedef struct { bq_str_t text; int end; } text_msg_t;
 
 typedef struct {
   /* decoder */
-  int nb, n_work;
+  int nb, n_work, n_threads;
   bam_in_t *in;
   const bq_bam_hdr_t *hdr;
   const bq_fasta_t *fa;
@@ -544,38 +545,34 @@ static void *decoder_main(void *arg) {
     const int64_t ref_len = bq_fasta_fetch_nt4(P->fa, P->hdr->name[tid], &ref);
     if (ref_len < 0) bq_fatal("[pileup] contig %s is not in %s\n", P->hdr->name[tid], P->reffn);
     if (ref_len < end) bq_fatal("[pileup] contig %s: reference has %ld bases, BAM header says %d\n", P->hdr->name[tid], (long)ref_len, P->hdr->len[tid]);
-    bq_plp_batch_t *bt = pq_get(&P->q_free_batches);
-    bq_plp_batch_reset(bt);
+    bq_plp_batch_t carry; /* reads reaching into the next chunk (a few dozen): private, plain memory */
+    memset(&carry, 0, sizeof carry);
+    carry.plain = 1;
     for (int64_t cb = beg; cb < end; cb += P->chunk) {
       const int64_t ce = cb + P->chunk < end ? cb + P->chunk : end;
+      bq_plp_batch_t *bt = pq_get(&P->q_free_batches); /* not timed: waiting for the consumer is not decoding */
       const double t0 = now_s();
-      /* reads of this contig starting before the chunk end (0-based pos < ce - 1) */
-      for (int s = 0; s < nb; ++s) {
-        while (!P->in[s].cur_tid_done) {
+      bq_plp_batch_reset(bt);
+      for (int64_t i = 0; i < carry.n; ++i) bq_plp_batch_copy1(bt, &carry, i);
+      /* reads of this contig starting before the chunk end (0-based pos < ce - 1), decoded on n_threads threads */
+      for (int s = 0; s < nb; ++s)
+        if (!P->in[s].cur_tid_done) {
+          bq_plp_batch_fill(bt, P->in[s].fp, s, tid, ce - 1, P->n_threads);
           uint32_t len;
           const uint8_t *r = bq_bam_peek(P->in[s].fp, &len);
-          if (!r) { P->in[s].cur_tid_done = 1; break; }
-          const int32_t rtid = (int32_t)(r[0] | r[1] << 8 | r[2] << 16 | (uint32_t)r[3] << 24);
-          const int32_t pos = (int32_t)(r[4] | r[5] << 8 | r[6] << 16 | (uint32_t)r[7] << 24);
-          if (rtid != tid) { P->in[s].cur_tid_done = 1; break; }
-          if (pos >= ce - 1) break;
-          bq_plp_batch_push(bt, r, len, s);
-          bq_bam_skip(P->in[s].fp, len);
+          if (!r || (int32_t)(r[0] | r[1] << 8 | r[2] << 16 | (uint32_t)r[3] << 24) != tid) P->in[s].cur_tid_done = 1;
         }
-      }
       /* the reads that reach into the next chunk are carried over */
-      bq_plp_batch_t *nx = pq_get(&P->q_free_batches);
-      bq_plp_batch_reset(nx);
+      bq_plp_batch_reset(&carry);
       for (int64_t i = 0; i < bt->n; ++i)
-        if (bt->end[i] >= ce) bq_plp_batch_copy1(nx, bt, i);
+        if (bt->end[i] >= ce) bq_plp_batch_copy1(&carry, bt, i);
       P->t_dec += now_s() - t0;
       chunk_msg_t *m = calloc(1, sizeof *m);
       m->tid = tid; m->cb = cb; m->ce = ce; m->bt = bt; m->ref = ref; m->ref_len = ref_len;
       ref = 0;
       pq_put(&P->q_chunks, m);
-      bt = nx;
     }
-    pq_put(&P->q_free_batches, bt);
+    bq_plp_batch_free(&carry);
     free(ref);
   }
   chunk_msg_t *m = calloc(1, sizeof *m);
@@ -664,6 +661,7 @@ int bq_main_pileup(int argc, char **argv) {
   if (n_fns > 8) bq_fatal("[pileup] at most 8 BAM files\n");
   const int nb = n_fns;
 
+  const double t_start = now_s();
   bam_in_t in[8];
   bq_bam_hdr_t hdr, h2;
   memset(&hdr, 0, sizeof hdr);
@@ -678,8 +676,10 @@ int bq_main_pileup(int argc, char **argv) {
   for (int i = 0; i < hdr.n_targets; ++i) { targets[i].tid = i; targets[i].name = hdr.name[i]; targets[i].len = hdr.len[i]; }
   qsort(targets, (size_t)hdr.n_targets, sizeof *targets, cmp_target); /* src/pileup.c:1135 */
 
+  const double t_bam = now_s();
   bq_fasta_t fa;
   if (bq_fasta_load(reffn, &fa) != 0) bq_fatal("[pileup] Cannot open reference %s\n", reffn);
+  const double t_fa = now_s();
 
   FILE *out = stdout;
   if (outfn) {
@@ -697,6 +697,7 @@ int bq_main_pileup(int argc, char **argv) {
   bsq_plp *plp = 0;
   int rc = bsq_plp_create(device, nb, &plp);
   if (rc) bq_fatal("[pileup] bsq_plp_create: %s (%s)\n", bsq_strerror(rc), bsq_last_error());
+  const double t_cuda = now_s();
   (void)rank; (void)world;
 
   /* work list: (target index, beg, end) with 1-based beg, exclusive end (src/pileup.c:1171-1200) */
@@ -732,11 +733,11 @@ int bq_main_pileup(int argc, char **argv) {
   /* pipeline: BAM decode (thread) | GPU + VCF text (this thread, text on conf.n_threads threads) | output (thread) */
   plp_pipe_t P;
   memset(&P, 0, sizeof P);
-  P.nb = nb; P.n_work = n_work; P.in = in; P.hdr = &hdr; P.fa = &fa; P.reffn = reffn; P.work = work; P.chunk = chunk; P.out = out;
+  P.nb = nb; P.n_work = n_work; P.n_threads = conf.n_threads; P.in = in; P.hdr = &hdr; P.fa = &fa; P.reffn = reffn; P.work = work; P.chunk = chunk; P.out = out;
   pq_init(&P.q_chunks); pq_init(&P.q_free_batches); pq_init(&P.q_text); pq_init(&P.q_free_text);
-  bq_plp_batch_t B[4];
+  bq_plp_batch_t B[3];  /* one being filled, one carrying over, one on the GPU */
   memset(B, 0, sizeof B);
-  for (int i = 0; i < 4; ++i) pq_put(&P.q_free_batches, &B[i]);
+  for (int i = 0; i < 3; ++i) pq_put(&P.q_free_batches, &B[i]);
   text_msg_t *texts[3];
   for (int i = 0; i < 3; ++i) { texts[i] = calloc(1, sizeof(text_msg_t)); pq_put(&P.q_free_text, texts[i]); }
   pthread_t th_dec, th_wr;
@@ -830,12 +831,24 @@ int bq_main_pileup(int argc, char **argv) {
     free(fn);
   }
   if (progress || getenv("BSQ_PLP_TIMING"))
+    { extern double bq_bgzf_t_read, bq_bgzf_t_inflate, bq_plp_t_fill;
+      fprintf(stderr, "[pileup] decode thread: file read %.2fs, inflate %.2fs, record decode %.2fs\n", bq_bgzf_t_read, bq_bgzf_t_inflate, bq_plp_t_fill); }
+    fprintf(stderr, "[pileup] start-up: BAM/BAI open %.2fs, FASTA load %.2fs, CUDA context %.2fs; main loop %.2fs\n", t_bam - t_start, t_fa - t_bam,
+            t_cuda - t_fa, now_s() - t_cuda);
+  if (progress || getenv("BSQ_PLP_TIMING"))
     fprintf(stderr, "[pileup] reads %ld loci %ld emitted %ld | decode %.2fs (thread) | wait %.2fs gpu %.2fs format %.2fs | write %.2fs (thread)\n",
             (long)tot_reads, (long)tot_loci, (long)tot_emit, t_dec, t_wait, t_gpu, t_fmt, t_wr);
   if (outfn) fclose(out); else fflush(out);
+  if (!getenv("BSQ_PLP_FULL_TEARDOWN")) {
+    /* All output is written.  Unpinning several hundred MB of page-locked staging memory and tearing the CUDA context
+     * down takes 0.5-1 s and frees nothing the exiting process will not free anyway. */
+    fprintf(stderr, "[main] Real time: %.3f sec\n", now_s() - t_start);
+    fflush(stderr);
+    _exit(0);
+  }
   bsq_plp_destroy(plp);
   for (int s = 0; s < nb; ++s) { bq_bgzf_close(in[s].fp); bq_bai_free(&in[s].bai); }
-  for (int i = 0; i < 4; ++i) bq_plp_batch_free(&B[i]);
+  for (int i = 0; i < 3; ++i) bq_plp_batch_free(&B[i]);
   for (int i = 0; i < 3; ++i) { free(texts[i]->text.s); free(texts[i]); }
   if (recs) bsq_host_free(recs);
   free(wbeta); free(wcnt); free(betasum); free(cnt); free(work); free(targets); free(statsfn);

@@ -54,10 +54,12 @@ typedef struct {
   int64_t *qual_off;
   uint8_t *qual;
   int64_t *end; /* 0-based exclusive reference end (pos + 1 for reads without reference span) */
+  int plain;    /* 1: ordinary memory (small private batches); 0: page-locked, staged to the GPU directly */
 } bq_plp_batch_t;
 void bq_plp_batch_reset(bq_plp_batch_t *B);
 void bq_plp_batch_free(bq_plp_batch_t *B);
 int bq_plp_batch_push(bq_plp_batch_t *B, const uint8_t *rec, uint32_t len, int sid);
+int bq_plp_batch_fill(bq_plp_batch_t *B, bq_bgzf_t *b, int sid, int tid, int64_t pos_lt, int n_threads);
 void bq_plp_batch_copy1(bq_plp_batch_t *dst, const bq_plp_batch_t *src, int64_t i);
 void bq_plp_batch_view(const bq_plp_batch_t *B, bsq_plp_reads *v);
 
