@@ -627,11 +627,11 @@ def main():
                              "frac": per_task_bytes[k] * n_tasks / (kern_us[i] * 1e-6) / 1e9 / peak}
                          for i, k in enumerate(stage_names[:4])}
         # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu capture of
-        # this same command (profiles/ncu_summary_r01_v5.json); null when the workload differs from the captured one
+        # this same command (profiles/ncu_summary_r01_v6.json); null when the workload differs from the captured one
         traffic = None
         try:
             if args.ref_mb == 3100 and args.pairs == 100000:
-                with open(os.path.join(ROOT, "profiles", "ncu_summary_r01_v5.json")) as fh:
+                with open(os.path.join(ROOT, "profiles", "ncu_summary_r01_v6.json")) as fh:
                     kk = json.load(fh)["kernels"].get(dom_name)
                 if kk:
                     traffic = kk["dram_read_bytes"] + kk["dram_write_bytes"]
