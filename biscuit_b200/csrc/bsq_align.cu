@@ -442,7 +442,10 @@ static inline unsigned nblk(int64_t n, int bs) { return (unsigned)((n + bs - 1) 
 
 // k_seed is persistent (lanes pull tasks from a counter): one wave of 148 SMs x 3 resident CTAs of 128
 // shared memory of k_seed: candidate lists + the converted reads (4 bits per base, as many words as the longest row needs)
-static inline size_t seed_smem_bytes(int stride) { return (size_t)128 * BSQ_SEED_CAP * 16 + (size_t)((stride + 7) >> 3) * 128 * 4; }
+static inline size_t seed_smem_bytes(int stride) {  // reads are at most BSQ_MAX_READ_LEN long whatever the row stride
+  const int len = stride < BSQ_MAX_READ_LEN ? stride : BSQ_MAX_READ_LEN;
+  return (size_t)128 * BSQ_SEED_CAP * 16 + (size_t)((len + 7) >> 3) * 128 * 4;
+}
 static inline bool seed_v1() { static int v = -1; if (v < 0) { const char *e = getenv("BSQ_SEED_V1"); v = e && atoi(e) != 0; } return v != 0; }
 static inline unsigned seed_grid(int64_t n) {
   static bool attr_set = false;
