@@ -720,6 +720,7 @@ static int phase1_device(bsq_aligner *al, int64_t n, int32_t stride, int64_t *to
   RES(ranks, (total_sa + 1) * 8); RES(pos, (total_sa + 1) * 8);
   // workspace of the exact fallback chaining: small by default (bump-allocated to the few flagged tasks)
   int64_t fb_cap = pool / 16 + 65536;
+  { const char *e = getenv("BSQ_FB_POOL"); if (e && atoll(e) > 0) fb_cap = atoll(e); }  // test hook: force the retry path
   if (al->fb_cap > fb_cap) fb_cap = al->fb_cap;  // keep a pool that was grown earlier
   al->fb_cap = fb_cap;
   RES(snodes, fb_cap * sizeof(bsq_snode_t)); RES(wchains, fb_cap * sizeof(bsq_wchain_t));

@@ -69,3 +69,59 @@ def test_overlong_read_rejected_and_empty_batch(long_case, backend, request):
     assert (refprobe.regs_from_bsq(regs) == exp).all()
     al.close()
     dx.close()
+
+
+@pytest.fixture(scope="module")
+def repeat_case(tmp_path_factory):
+    """A reference with a 900-copy tandem repeat: SMEM intervals with more than max_occ (500) occurrences, chains
+    with equal positions, tasks with thousands of seeds -- everything the shared-memory chaining declines and hands
+    to the exact fallback."""
+    import os
+    import subprocess
+    if not refprobe.available():
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    rng = np.random.default_rng(99)
+    unit = rng.integers(0, 4, size=700, dtype=np.uint8)
+    rep = np.tile(unit, 900)
+    mut = rng.random(len(rep)) < 0.002  # a few differences between copies
+    rep[mut] = (rep[mut] + 1 + rng.integers(0, 3, size=int(mut.sum()))) % 4
+    uniq = rng.integers(0, 4, size=120_000, dtype=np.uint8)
+    ref = [("chrU", uniq), ("chrR", rep.astype(np.uint8))]
+    d = tmp_path_factory.mktemp("repeat")
+    fa = os.path.join(str(d), "ref.fa")
+    synth.write_fasta(fa, ref)
+    subprocess.check_call([refprobe.REF_BIN, "index", fa], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    p = synth.simulate_pairs(ref, 40, seed=5, sub_rate=0.01)
+    reads = [np.asarray(r, dtype=np.uint8) for r in list(p["r1"]) + list(p["r2"])]
+    hi = indexio.load_index(fa)
+    rp = refprobe.RefProbe(fa)
+    yield hi, rp, reads
+    rp.close()
+
+
+@pytest.mark.parametrize("fb_pool", [None, "2000"])  # "2000": the fallback workspace is too small at first -> grow and retry
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_repeats_take_the_exact_fallback(repeat_case, backend, fb_pool, request, monkeypatch):
+    hi, rp, reads = repeat_case
+    if fb_pool:
+        monkeypatch.setenv("BSQ_FB_POOL", fb_pool)
+    bsq = request.getfixturevalue(backend)
+    dx = bsq.upload(hi)
+    al = capi.Aligner(dx, bsq.default_opt())
+    n = len(reads)
+    mat = np.stack(reads)
+    lens = np.full(n, mat.shape[1], np.int32)
+    tasks = np.concatenate([mat, mat])
+    tl = np.concatenate([lens, lens])
+    par = np.concatenate([np.zeros(n, np.uint8), np.ones(n, np.uint8)])
+    regs, off = al.phase1(tasks, tl, par)
+    mine = refprobe.regs_from_bsq(regs)
+    for t in range(2 * n):
+        exp = refprobe.regs_from_ref(rp.align1(int(par[t]), reads[t % n]))
+        got = mine[off[t]:off[t + 1]]
+        assert got.shape == exp.shape and (got == exp).all(), (t, got, exp)
+    c = al.counters()
+    if backend == "cuda":
+        assert c[14] > 0  # some tasks really went through k_chain
+    al.close()
+    dx.close()
