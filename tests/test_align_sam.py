@@ -105,3 +105,53 @@ def test_index_cli_gpu(hard_set, tmp_path):
     subprocess.check_call([GPU_BIN, "index", mine], stderr=subprocess.DEVNULL)
     for ext in (".par.bwt", ".dau.bwt", ".par.sa", ".dau.sa", ".bis.pac", ".bis.ann", ".bis.amb"):
         assert open(mine + ext, "rb").read() == open(fa + ext, "rb").read(), ext
+
+
+@pytest.fixture(scope="module")
+def repeat_set(tmp_path_factory):
+    """Tandem and dispersed repeats: many equally good hits (XA/XB tags, mapQ 0, secondary marking), mate rescue
+    among copies, SMEM intervals above max_occ."""
+    if not refprobe.available():
+        pytest.skip("oracle/_ref not built")
+    d = str(tmp_path_factory.mktemp("samrep"))
+    rng = np.random.default_rng(4)
+    unit = rng.integers(0, 4, size=400, dtype=np.uint8)
+    tandem = np.tile(unit, 30)
+    bg = rng.integers(0, 4, size=150_000, dtype=np.uint8)
+    elem = rng.integers(0, 4, size=600, dtype=np.uint8)
+    for k in range(12):  # a dispersed element with small differences between copies
+        p0 = 5000 + k * 11000
+        cp = elem.copy()
+        m = rng.random(len(cp)) < 0.01
+        cp[m] = (cp[m] + 1) % 4
+        bg[p0:p0 + len(cp)] = cp
+    ref = [("chrBg", bg), ("chrTandem", np.concatenate([rng.integers(0, 4, size=3000, dtype=np.uint8), tandem,
+                                                        rng.integers(0, 4, size=3000, dtype=np.uint8)]).astype(np.uint8))]
+    fa = os.path.join(d, "rep.fa")
+    synth.write_fasta(fa, ref)
+    subprocess.check_call([refprobe.REF_BIN, "index", fa], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    p = synth.simulate_pairs(ref, 1500, seed=8, sub_rate=0.01, indel_rate=0.002, qual="mixed")
+    f1, f2 = os.path.join(d, "r1.fq"), os.path.join(d, "r2.fq")
+    synth.write_fastq(f1, p["r1"], p["q1"], suffix="/1")
+    synth.write_fastq(f2, p["r2"], p["q2"], suffix="/2")
+    return fa, f1, f2
+
+
+@pytest.mark.parametrize("extra", [[], ["-a"], ["-K", "60000"]], ids=["default", "-a", "small batches"])
+def test_sam_identical_repeats_hostemu(repeat_set, extra):
+    fa, f1, f2 = repeat_set
+    args = ["-@", "3"] + extra + [fa, f1, f2]
+    a, b = _sam(build_emu_bin(), args), _sam(refprobe.REF_BIN, args)
+    assert a == b
+    if "-a" not in extra:  # with -a the alternative hits are separate records instead of XA tags
+        assert b"XA:Z:" in b and b"XB:Z:" in b  # the data set really has multi-hit reads
+    else:
+        assert sum(1 for ln in b.split(b"\n") if ln and not ln.startswith(b"@") and int(ln.split(b"\t")[1]) & 0x100) > 50
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("extra", [[], ["-K", "60000"]], ids=["default", "small batches"])
+def test_sam_identical_repeats_gpu(repeat_set, extra):
+    fa, f1, f2 = repeat_set
+    args = ["-@", "3"] + extra + [fa, f1, f2]
+    assert _sam(GPU_BIN, args) == _sam(refprobe.REF_BIN, args)
