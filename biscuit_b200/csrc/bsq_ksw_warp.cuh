@@ -94,8 +94,8 @@ __device__ __noinline__ bsq_ext_result_t bsq_ksw_extend_warp(int qlen, bsq_qacc_
       int incl = act ? t + j * e_ins : BSQ_NEG_INF;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl = incl > v ? incl : v;
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);  // lanes below o get their own value back: max is a no-op
+        incl = incl > v ? incl : v;
       }
       int p = __shfl_up_sync(0xffffffffu, incl, 1);
       if (lane == 0) p = BSQ_NEG_INF;
