@@ -315,3 +315,45 @@ def test_pileup_cli_matches_oracle(tmp_path, n_bams):
     rbody = b"\n".join(l for l in reg.split(b"\n") if not l.startswith(b"#"))
     recs = oracle_plp.region(oracle_plp.conf_default(), ref_b, rd_b, 100001, 150000, n_bams)
     assert rbody == oracle_vcf(recs, "chr2", n_bams, w0=100001)[0]
+
+
+@pytest.mark.gpu
+def test_align_to_pileup_end_to_end(tmp_path):
+    """BASELINE.json configs[4] in miniature: `biscuit index` -> `biscuit align` (GPU) -> coordinate-sorted BAM ->
+    `biscuit pileup` (GPU) -> `vcf2bed`.  The SAM must equal the reference's, and the VCF must equal what the oracle
+    derives from that SAM (tags YD / NM / AS / MC as the aligner wrote them)."""
+    import refprobe
+    _need(oracle_plp.SO, BISCUIT)
+    if not refprobe.available():
+        pytest.skip("oracle/_ref not built")
+    ref = synth.make_reference(150_000, 2, seed=21)
+    fa = str(tmp_path / "ref.fa")
+    synth.write_fasta(fa, ref)
+    subprocess.run([BISCUIT, "index", fa], check=True, capture_output=True)
+    p = synth.simulate_pairs(ref, 12000, seed=31, sub_rate=0.01, indel_rate=0.001, qual="mixed")  # about 24x
+    f1, f2 = str(tmp_path / "r1.fq"), str(tmp_path / "r2.fq")
+    synth.write_fastq(f1, p["r1"], p["q1"], suffix="/1")
+    synth.write_fastq(f2, p["r2"], p["q2"], suffix="/2")
+    sam = str(tmp_path / "out.sam")
+    with open(sam, "wb") as fh:
+        subprocess.run([BISCUIT, "align", "-@", "4", fa, f1, f2], check=True, stdout=fh, stderr=subprocess.DEVNULL)
+    ref_sam = subprocess.run([refprobe.REF_BIN, "align", "-@", "4", fa, f1, f2], check=True, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout
+    strip = lambda b: b"\n".join(ln for ln in b.split(b"\n") if not ln.startswith(b"@PG"))  # noqa: E731
+    assert strip(open(sam, "rb").read()) == strip(ref_sam)
+    bam = str(tmp_path / "out.bam")
+    assert bamio.sam_to_sorted_bam(sam, bam) == 24000
+    vcf = str(tmp_path / "out.vcf")
+    subprocess.run([BISCUIT, "pileup", "-@", "4", "-o", vcf, fa, bam], check=True)
+    body = b"\n".join(ln for ln in open(vcf, "rb").read().split(b"\n") if not ln.startswith(b"#"))
+    contigs, soa = bamio.sam_to_soa(sam)
+    nt4 = dict(ref)
+    exp = []
+    for name, _ in sorted(contigs):
+        if name not in soa:
+            continue
+        recs = oracle_plp.region(oracle_plp.conf_default(), nt4[name], soa[name], 1, len(nt4[name]), 1)
+        exp.append(oracle_vcf(recs, name, 1)[0])
+    assert body == b"".join(exp)
+    assert body.count(b"\n") > 20000  # most cytosines of 150 kb are covered
+    bed = subprocess.run([BISCUIT, "vcf2bed", "-t", "cg", vcf], check=True, capture_output=True).stdout.decode()
+    assert bed == _py_vcf2bed(open(vcf).read(), "CG", 1) and bed.count("\n") > 1000

@@ -338,3 +338,81 @@ def write_bam_fixed(path: str, contig: str, contig_len: int, rd: dict, level: in
         fh.write(np.ascontiguousarray(voff[np.minimum(first_rec, n - 1)].astype("<u8")).tobytes() if n else b"")
         fh.write(struct.pack("<Q", 0))
     return n
+
+
+def sam_to_soa(sam_path: str):
+    """Parse a SAM file into the per-contig structure-of-arrays the pileup oracle takes (same field meanings as
+    bsq_plp_reads), records in coordinate order (stable).  Returns (contigs [(name, len)], {name: dict})."""
+    contigs, recs = [], {}
+    with open(sam_path) as fh:
+        for line in fh:
+            if line.startswith("@"):
+                if line.startswith("@SQ"):
+                    f = dict(x.split(":", 1) for x in line.rstrip("\n").split("\t")[1:])
+                    contigs.append((f["SN"], int(f["LN"])))
+                continue
+            f = line.rstrip("\n").split("\t")
+            if f[2] == "*" or f[5] == "*":
+                continue
+            recs.setdefault(f[2], []).append(f)
+    I32MIN = np.iinfo(np.int32).min
+    out = {}
+    for name, rows in recs.items():
+        rows.sort(key=lambda f: int(f[3]))
+        n = len(rows)
+        d = dict(n_reads=n, pos=np.zeros(n, np.int32), mpos=np.zeros(n, np.int32), mate_rlen=np.full(n, -1, np.int32), l_qseq=np.zeros(n, np.int32),
+                 nm=np.full(n, I32MIN, np.int32), as_=np.full(n, I32MIN, np.int32), flag=np.zeros(n, np.uint16), mapq=np.zeros(n, np.uint8),
+                 bss_tag=np.full(n, -1, np.int8), sid=np.zeros(n, np.uint8), n_cigar=np.zeros(n, np.int32), cigar_off=np.zeros(n, np.int64),
+                 seq_off=np.zeros(n, np.int64), qual_off=np.zeros(n, np.int64))
+        cig, seq, qual = [], [], []
+        so = qo = 0
+        for i, f in enumerate(rows):
+            d["pos"][i] = int(f[3]) - 1
+            d["mpos"][i] = int(f[7]) - 1
+            d["flag"][i] = int(f[1])
+            d["mapq"][i] = int(f[4])
+            ops, num = [], ""
+            for ch in f[5]:
+                if ch.isdigit():
+                    num += ch
+                else:
+                    ops.append((int(num) << 4) | CIG_OPS.index(ch))
+                    num = ""
+            d["n_cigar"][i] = len(ops)
+            d["cigar_off"][i] = len(cig)
+            cig += ops
+            s = [] if f[9] == "*" else [NT16.get(c, 15) for c in f[9].upper()] 
+            d["l_qseq"][i] = len(s)
+            s2 = s + [0]
+            packed = [(s2[k] << 4) | s2[k + 1] for k in range(0, len(s), 2)]
+            d["seq_off"][i] = so
+            seq += packed
+            so += len(packed)
+            q = [0xff] * len(s) if f[10] == "*" else [ord(c) - 33 for c in f[10]]
+            d["qual_off"][i] = qo
+            qual += q
+            qo += len(q)
+            for t in f[11:]:
+                tg, ty, val = t.split(":", 2)
+                if tg == "NM":
+                    d["nm"][i] = int(val)
+                elif tg == "AS":
+                    d["as_"][i] = int(val)
+                elif tg == "MC":
+                    rl, num = 0, ""
+                    if val != "*":
+                        for ch in val:
+                            if ch.isdigit():
+                                num += ch
+                            else:
+                                if ch in "MDN=X":
+                                    rl += int(num)
+                                num = ""
+                    d["mate_rlen"][i] = rl
+                elif tg == "YD" and d["bss_tag"][i] < 0:
+                    d["bss_tag"][i] = 0 if val == "f" else 1 if val == "r" else -1
+        d["cigar"] = np.array(cig, np.uint32)
+        d["seq"] = np.array(seq, np.uint8)
+        d["qual"] = np.array(qual, np.uint8)
+        out[name] = d
+    return contigs, out
