@@ -275,7 +275,7 @@ int bq_main_pileup(int argc, char **argv);
 
 int main(int argc, char **argv) {
   if (argc < 2) {
-    fprintf(stderr, "\nProgram: biscuit (B200 build of the index/align/pileup hot paths)\nVersion: %s\n\nUsage: biscuit <index|align|pileup|vcf2bed|mergecg|version> [options]\n\n", BQ_VERSION);
+    fprintf(stderr, "\nProgram: biscuit (B200 build of the index/align/pileup hot paths)\nVersion: %s\n\nUsage: biscuit <index|align|sortbam|pileup|vcf2bed|mergecg|version> [options]\n\n", BQ_VERSION);
     return 1;
   }
   int ret;
@@ -283,6 +283,7 @@ int main(int argc, char **argv) {
   if (strcmp(argv[1], "index") == 0) ret = bq_main_index(argc - 1, argv + 1);
   else if (strcmp(argv[1], "align") == 0) ret = bq_main_align(argc - 1, argv + 1);
   else if (strcmp(argv[1], "pileup") == 0) ret = bq_main_pileup(argc - 1, argv + 1);
+  else if (strcmp(argv[1], "sortbam") == 0) ret = bq_main_sortbam(argc - 1, argv + 1);
   else if (strcmp(argv[1], "bamdump") == 0) ret = bq_main_bamdump(argc - 1, argv + 1);
   else if (strcmp(argv[1], "vcf2bed") == 0) ret = bq_main_vcf2bed(argc - 1, argv + 1);
   else if (strcmp(argv[1], "mergecg") == 0) ret = bq_main_mergecg(argc - 1, argv + 1);

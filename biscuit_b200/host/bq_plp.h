@@ -92,4 +92,6 @@ int bq_main_pileup(int argc, char **argv);
 /* ---- bq_vcf2bed.c ---- */
 int bq_main_vcf2bed(int argc, char **argv);
 int bq_main_mergecg(int argc, char **argv);
+/* ---- bq_sortbam.c ---- */
+int bq_main_sortbam(int argc, char **argv);
 #endif

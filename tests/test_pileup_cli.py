@@ -319,7 +319,7 @@ def test_pileup_cli_matches_oracle(tmp_path, n_bams):
 
 @pytest.mark.gpu
 def test_align_to_pileup_end_to_end(tmp_path):
-    """BASELINE.json configs[4] in miniature: `biscuit index` -> `biscuit align` (GPU) -> coordinate-sorted BAM ->
+    """BASELINE.json configs[4] in miniature: `biscuit index` -> `biscuit align` (GPU) -> `biscuit sortbam` ->
     `biscuit pileup` (GPU) -> `vcf2bed`.  The SAM must equal the reference's, and the VCF must equal what the oracle
     derives from that SAM (tags YD / NM / AS / MC as the aligner wrote them)."""
     import refprobe
@@ -341,7 +341,7 @@ def test_align_to_pileup_end_to_end(tmp_path):
     strip = lambda b: b"\n".join(ln for ln in b.split(b"\n") if not ln.startswith(b"@PG"))  # noqa: E731
     assert strip(open(sam, "rb").read()) == strip(ref_sam)
     bam = str(tmp_path / "out.bam")
-    assert bamio.sam_to_sorted_bam(sam, bam) == 24000
+    subprocess.run([BISCUIT, "sortbam", "-@", "4", "-o", bam, sam], check=True, capture_output=True)
     vcf = str(tmp_path / "out.vcf")
     subprocess.run([BISCUIT, "pileup", "-@", "4", "-o", vcf, fa, bam], check=True)
     body = b"\n".join(ln for ln in open(vcf, "rb").read().split(b"\n") if not ln.startswith(b"#"))
@@ -357,3 +357,37 @@ def test_align_to_pileup_end_to_end(tmp_path):
     assert body.count(b"\n") > 20000  # most cytosines of 150 kb are covered
     bed = subprocess.run([BISCUIT, "vcf2bed", "-t", "cg", vcf], check=True, capture_output=True).stdout.decode()
     assert bed == _py_vcf2bed(open(vcf).read(), "CG", 1) and bed.count("\n") > 1000
+
+
+def test_sortbam_matches_python_writer(tmp_path):
+    """`biscuit sortbam` (C: SAM -> coordinate-sorted BAM + BAI) against tools/bamio.py on the reference aligner's own
+    SAM: same decoded records in the same order, and the BAI lands a reader on the same records."""
+    import refprobe
+    _need(BISCUIT)
+    if not refprobe.available():
+        pytest.skip("oracle/_ref not built")
+    ref = synth.make_reference(90_000, 3, seed=12, n_runs=1)
+    fa = str(tmp_path / "ref.fa")
+    synth.write_fasta(fa, ref)
+    subprocess.check_call([refprobe.REF_BIN, "index", fa], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    p = synth.simulate_pairs(ref, 1500, seed=2, sub_rate=0.02, indel_rate=0.004, qual="mixed")
+    r2 = p["r2"].copy()
+    r2[:40] = np.random.default_rng(0).integers(0, 4, size=(40, 150))  # some unmapped mates
+    f1, f2 = str(tmp_path / "r1.fq"), str(tmp_path / "r2.fq")
+    synth.write_fastq(f1, p["r1"], p["q1"], suffix="/1")
+    synth.write_fastq(f2, r2, p["q2"], suffix="/2")
+    sam = str(tmp_path / "a.sam")
+    with open(sam, "wb") as fh:
+        subprocess.run([refprobe.REF_BIN, "align", "-@", "2", fa, f1, f2], check=True, stdout=fh, stderr=subprocess.DEVNULL)
+    py_bam, c_bam = str(tmp_path / "py.bam"), str(tmp_path / "c.bam")
+    n = bamio.sam_to_sorted_bam(sam, py_bam)
+    subprocess.run([BISCUIT, "sortbam", "-@", "3", "-o", c_bam, sam], check=True, capture_output=True)
+    dump = lambda *a: subprocess.run([BISCUIT, "bamdump", *a], capture_output=True, check=True).stdout  # noqa: E731
+    a, b = dump(py_bam), dump(c_bam)
+    assert a == b and a.count(b"\n") > n * 0.9
+    for args in (("1",), ("2", "20000"), ("0", "5000")):
+        assert dump(py_bam, *args) == dump(c_bam, *args)
+    # the file is a valid multi-member gzip stream holding a BAM
+    import gzip
+    raw = gzip.open(c_bam, "rb").read()
+    assert raw[:4] == b"BAM\x01"
