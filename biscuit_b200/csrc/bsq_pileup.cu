@@ -1,11 +1,16 @@
 // libbsq.so -- pileup half: methylation counting over coordinate-sorted reads (sm_100a).
 //
-//   k_plp_pile    one WARP per read: bisulfite-strand inference, read filters and cnt_retention as warp
-//                 reductions over the read's aligned bases (lanes stride the bases, coalesced SEQ/QUAL/REF
-//                 loads), then one retention/conversion/base event per aligned base, accumulated with
-//                 integer atomics into the per-locus counter tile  [locus][sample][12].
-//   k_plp_locus   one thread per locus: ambiguity redistribution, top mutant, emit rule, methcallable,
-//                 5-mer cytosine context -> flags + dense records.
+//   k_plp_win     coordinate-sorted reads (the normal case): one CTA per window of 1024 loci whose counters
+//                 [locus][sample][12] live in SHARED memory.  The warps of the CTA walk the reads that can touch the
+//                 window (k_plp_ranges: binary search on the sorted positions); per read one WARP does
+//                 bisulfite-strand inference, read filters and cnt_retention as warp reductions over the aligned
+//                 bases (lanes stride the bases, coalesced SEQ/QUAL/REF loads), then one retention/conversion/base
+//                 event per aligned base as shared-memory atomics; finally one thread per locus takes the
+//                 per-locus decisions (ambiguity redistribution, top mutant, emit rule, methcallable, 5-mer
+//                 cytosine context) straight from shared memory -> flags + dense records.  The counters never
+//                 travel through HBM.
+//   k_plp_pile, k_plp_locus   the same two steps over a counter tile in global memory, for reads that are not
+//                 coordinate-sorted (several BAMs concatenated).
 //   k_plp_compact emitted loci -> contiguous output (order = position), via a device prefix sum.
 // Reference: src/pileup.c:707-831 (events), :372-387 (plp_getcnts), :312-370 and :415-485 (per locus),
 // src/bisc_utils.c:33-122,163-238.  Integer work only; bit-exact against oracle/bsq_oracle_pileup.c.
@@ -72,7 +77,7 @@ struct bsq_plp {
   cudaStream_t stream;
   cudaEvent_t ev[4];
   DBuf ref, b_pos, b_mpos, b_mrl, b_lq, b_nm, b_as, b_flag, b_mapq, b_bss, b_sid, b_nc, b_coff, b_cig, b_soff, b_seq, b_qoff, b_qual;
-  DBuf cnt, flags, dense, offs, out, cub_tmp, scal;
+  DBuf cnt, flags, dense, offs, out, cub_tmp, scal, wr0, wr1;
   int32_t ref_len;
   DevReads dr;
   int32_t *h_pos;  // host copy of pos[] (tile -> read range by binary search)
@@ -89,11 +94,11 @@ __device__ __forceinline__ int rd_base(const uint8_t *seq, int q) {
   return c_nt16_to_nt4[(q & 1) ? (b & 0xf) : (b >> 4)];
 }
 
-// one warp per read
-__global__ void __launch_bounds__(256) k_plp_pile(DevReads rd, int64_t r0, int64_t r1, bsq_plp_conf cf, const uint8_t *ref, int32_t ref_len,
-                                                  int32_t beg, int32_t end, int n_bams, int *cnt, unsigned long long *n_events) {
-  const int64_t i = r0 + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  if (i >= r1) return;
+// One warp, one read: bisulfite-strand inference, read filters, then one event per aligned base inside [beg, end),
+// accumulated with integer atomics into cnt[((p - beg) * n_bams + sid) * PLP_NCNT + k] (global tile or a shared-memory
+// window).  Returns the number of events of this lane.
+__device__ __forceinline__ unsigned long long plp_read_events(const DevReads &rd, int64_t i, const bsq_plp_conf &cf, const uint8_t *ref, int32_t ref_len,
+                                                              int32_t beg, int32_t end, int n_bams, int *cnt) {
   const int lane = threadIdx.x & 31;
   const uint32_t *cig = rd.cigar + rd.cigar_off[i];
   const uint8_t *seq = rd.seq + rd.seq_off[i];
@@ -132,20 +137,20 @@ __global__ void __launch_bounds__(256) k_plp_pile(DevReads rd, int64_t r0, int64
     bsstrand = nC2T >= nG2A ? 0 : 1;
   }
   // ---- read-level filters (pileup.c:713-729) ----
-  if (rd.mapq[i] < cf.min_mapq) return;
+  if (rd.mapq[i] < cf.min_mapq) return 0;
   const int lq = rd.l_qseq[i];
-  if (lq < 0 || lq < cf.min_read_len) return;
+  if (lq < 0 || lq < cf.min_read_len) return 0;
   if (flag > 0) {
-    if (cf.filter_secondary && (flag & 0x100)) return;
-    if (cf.filter_duplicate && (flag & 0x400)) return;
-    if (cf.filter_ppair && (flag & 0x1) && !(flag & 0x2)) return;
-    if (cf.filter_qcfail && (flag & 0x200)) return;
+    if (cf.filter_secondary && (flag & 0x100)) return 0;
+    if (cf.filter_duplicate && (flag & 0x400)) return 0;
+    if (cf.filter_ppair && (flag & 0x1) && !(flag & 0x2)) return 0;
+    if (cf.filter_qcfail && (flag & 0x200)) return 0;
   }
-  if (rd.nm[i] != INT_MIN && rd.nm[i] > cf.max_nm) return;
-  if (rd.as[i] != INT_MIN && rd.as[i] < cf.min_score) return;
+  if (rd.nm[i] != INT_MIN && rd.nm[i] > cf.max_nm) return 0;
+  if (rd.as[i] != INT_MIN && rd.as[i] < cf.min_score) return 0;
   {
     const uint32_t c = (uint32_t)__reduce_add_sync(0xffffffffu, bsstrand ? nCC : nGG);  // cnt_retention quirk: C/C on BSC
-    if (c > (uint32_t)cf.max_retention) return;
+    if (c > (uint32_t)cf.max_retention) return 0;
   }
   // ---- pass B: events ----
   const uint32_t rmpos = (uint32_t)rd.mpos[i] + 1;
@@ -180,23 +185,29 @@ __global__ void __launch_bounds__(256) k_plp_pile(DevReads rd, int64_t r0, int64
     } else if (op == 1 || op == 4 || op == 5) qpos += ol;
     else if (op == 2) rpos += ol;
   }
+  return ev;
+}
+
+// one warp per read, counters in a global tile (used when the reads are not coordinate-sorted)
+__global__ void __launch_bounds__(256) k_plp_pile(DevReads rd, int64_t r0, int64_t r1, bsq_plp_conf cf, const uint8_t *ref, int32_t ref_len,
+                                                  int32_t beg, int32_t end, int n_bams, int *cnt, unsigned long long *n_events) {
+  const int64_t i = r0 + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (i >= r1) return;
+  unsigned long long ev = plp_read_events(rd, i, cf, ref, ref_len, beg, end, n_bams, cnt);
   ev = __reduce_add_sync(0xffffffffu, (unsigned)ev);
-  if (lane == 0 && ev) atomicAdd(n_events, ev);
+  if ((threadIdx.x & 31) == 0 && ev) atomicAdd(n_events, ev);
 }
 
 __device__ __forceinline__ char nt4_char(int c) { return c == 0 ? 'A' : c == 1 ? 'C' : c == 2 ? 'G' : c == 3 ? 'T' : 'N'; }
 
-// one thread per locus of the tile
-__global__ void k_plp_locus(const int *cnt, bsq_plp_conf cf, const uint8_t *ref, int32_t ref_len, int32_t beg, int64_t nl, int n_bams,
-                            int32_t *flags, bsq_plp_rec *dense) {
-  const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= nl) return;
-  const int *lc0 = cnt + l * n_bams * PLP_NCNT;
+// One locus: ambiguity redistribution, top mutant, emit rule, methcallable, cytosine context (plp_format, pileup.c:415-485)
+// from its counters lc0[n_bams][PLP_NCNT]; writes flags[l] and, when the locus is emitted, dense[l * n_bams + s].
+__device__ __forceinline__ void plp_locus(const int *lc0, const bsq_plp_conf &cf, const uint8_t *ref, int32_t ref_len, int32_t rpos, int64_t l, int n_bams,
+                                          int32_t *flags, bsq_plp_rec *dense) {
   int touched = 0;
   for (int s = 0; s < n_bams; ++s) touched |= lc0[s * PLP_NCNT + 10];
   flags[l] = 0;
   if (!touched) return;
-  const int32_t rpos = beg + (int32_t)l;
   const int rb = ref[rpos - 1];
   if (rb > 3) return;
   int raw_all[7], all_base[7], all_meth[3] = {0, 0, 0};
@@ -284,6 +295,51 @@ __global__ void k_plp_locus(const int *cnt, bsq_plp_conf cf, const uint8_t *ref,
   flags[l] = 1;
 }
 
+// one thread per locus of the tile, counters in the global tile
+__global__ void k_plp_locus(const int *cnt, bsq_plp_conf cf, const uint8_t *ref, int32_t ref_len, int32_t beg, int64_t nl, int n_bams,
+                            int32_t *flags, bsq_plp_rec *dense) {
+  const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= nl) return;
+  plp_locus(cnt + l * n_bams * PLP_NCNT, cf, ref, ref_len, beg + (int32_t)l, l, n_bams, flags, dense);
+}
+
+// Coordinate-sorted reads: one CTA per window of W loci.  The window's counters live in shared memory, the warps of the
+// CTA walk the reads that can touch the window (range from k_plp_ranges), events are shared-memory atomics, and the
+// per-locus decisions are taken straight from shared memory -- the counters never travel through HBM.
+__global__ void k_plp_ranges(const int32_t *pos, int64_t n_reads, int32_t tb, int32_t te, int W, int32_t max_span, int64_t *r0, int64_t *r1) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t wb = (int64_t)tb + w * W;
+  if (wb >= te) return;
+  const int64_t we = wb + W < te ? wb + W : te;
+  // reads with pos in [wb - 1 - max_span, we - 1) can touch [wb, we)
+  const int64_t lo_v = wb - 1 - (int64_t)max_span, hi_v = we - 1;
+  int64_t lo = 0, hi = n_reads;
+  while (lo < hi) { const int64_t m = (lo + hi) >> 1; if (pos[m] < lo_v) lo = m + 1; else hi = m; }
+  r0[w] = lo;
+  hi = n_reads;
+  while (lo < hi) { const int64_t m = (lo + hi) >> 1; if (pos[m] < hi_v) lo = m + 1; else hi = m; }
+  r1[w] = lo;
+}
+
+__global__ void __launch_bounds__(256) k_plp_win(DevReads rd, const int64_t *r0s, const int64_t *r1s, bsq_plp_conf cf, const uint8_t *ref, int32_t ref_len,
+                                                 int32_t tb, int32_t te, int W, int n_bams, int32_t *flags, bsq_plp_rec *dense,
+                                                 unsigned long long *n_events) {
+  extern __shared__ int s_cnt[];  // [W][n_bams][PLP_NCNT]
+  const int32_t wb = tb + (int32_t)blockIdx.x * W;
+  const int32_t we = wb + W < te ? wb + W : te;
+  const int n_cnt = (we - wb) * n_bams * PLP_NCNT;
+  for (int k = threadIdx.x; k < n_cnt; k += blockDim.x) s_cnt[k] = 0;
+  __syncthreads();
+  const int64_t r0 = r0s[blockIdx.x], r1 = r1s[blockIdx.x];
+  unsigned long long ev = 0;
+  for (int64_t i = r0 + (threadIdx.x >> 5); i < r1; i += blockDim.x >> 5) ev += plp_read_events(rd, i, cf, ref, ref_len, wb, we, n_bams, s_cnt);
+  ev = __reduce_add_sync(0xffffffffu, (unsigned)ev);
+  if ((threadIdx.x & 31) == 0 && ev) atomicAdd(n_events, ev);
+  __syncthreads();
+  for (int l = threadIdx.x; l < we - wb; l += blockDim.x)
+    plp_locus(s_cnt + l * n_bams * PLP_NCNT, cf, ref, ref_len, wb + l, (int64_t)(wb - tb) + l, n_bams, flags, dense);
+}
+
 __global__ void k_plp_compact(const int32_t *flags, const int64_t *offs, const bsq_plp_rec *dense, int64_t nl, int n_bams, int64_t out_base,
                               bsq_plp_rec *out) {
   const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -323,7 +379,7 @@ void bsq_plp_destroy(bsq_plp *p) {
   cudaSetDevice(p->device);
   DBuf *bufs[] = {&p->ref, &p->b_pos, &p->b_mpos, &p->b_mrl, &p->b_lq, &p->b_nm, &p->b_as, &p->b_flag, &p->b_mapq, &p->b_bss, &p->b_sid,
                   &p->b_nc, &p->b_coff, &p->b_cig, &p->b_soff, &p->b_seq, &p->b_qoff, &p->b_qual, &p->cnt, &p->flags, &p->dense, &p->offs,
-                  &p->out, &p->cub_tmp, &p->scal};
+                  &p->out, &p->cub_tmp, &p->scal, &p->wr0, &p->wr1};
   for (DBuf *b : bufs) b->release();
   for (int i = 0; i < 4; ++i) cudaEventDestroy(p->ev[i]);
   cudaStreamDestroy(p->stream);
@@ -395,12 +451,6 @@ int bsq_plp_stage(bsq_plp *p, const bsq_plp_reads *r) {
   return 0;
 }
 
-static int64_t lower_bound_pos(const int32_t *a, int64_t n, int64_t v) {
-  int64_t lo = 0, hi = n;
-  while (lo < hi) { int64_t m = (lo + hi) >> 1; if (a[m] < v) lo = m + 1; else hi = m; }
-  return lo;
-}
-
 int bsq_plp_run(bsq_plp *p, const bsq_plp_conf *cf, int32_t beg, int32_t end, int64_t *n_loci) {
   if (!p || !cf || !n_loci || p->ref_len <= 0) return BSQ_EINVAL;
   CKP(cudaSetDevice(p->device));
@@ -419,26 +469,43 @@ int bsq_plp_run(bsq_plp *p, const bsq_plp_conf *cf, int32_t beg, int32_t end, in
   for (int64_t tb = beg; tb < end; tb += PLP_TILE) {
     const int64_t te = tb + PLP_TILE < end ? tb + PLP_TILE : end;
     const int64_t nl = te - tb;
-    if ((rc = p->cnt.need((size_t)nl * nb * PLP_NCNT * 4))) return rc;
     if ((rc = p->flags.need((size_t)nl * 4))) return rc;
     if ((rc = p->offs.need((size_t)(nl + 1) * 8))) return rc;
     if ((rc = p->dense.need((size_t)nl * nb * sizeof(bsq_plp_rec)))) return rc;
-    CKP(cudaMemsetAsync(p->cnt.p, 0, (size_t)nl * nb * PLP_NCNT * 4, s));
-    int64_t r0 = 0, r1 = p->n_reads;
-    if (p->h_pos) {  // reads with pos in [tb-1-max_span, te-1) can touch the tile
-      r0 = lower_bound_pos(p->h_pos, p->n_reads, tb - 1 - (int64_t)p->max_span);
-      r1 = lower_bound_pos(p->h_pos, p->n_reads, te - 1);
-    }
     CKP(cudaEventRecord(p->ev[0], s));
-    if (r1 > r0) {
-      k_plp_pile<<<nbk((r1 - r0) * 32, 256), 256, 0, s>>>(p->dr, r0, r1, *cf, p->ref.as<uint8_t>(), p->ref_len, (int32_t)tb, (int32_t)te, nb,
-                                                           p->cnt.as<int>(), p->scal.as<unsigned long long>());
+    if (p->h_pos) {
+      // coordinate-sorted reads: windows of W loci with their counters in shared memory (k_plp_win)
+      int W = 1024 / nb;
+      if (W < 128) W = 128;
+      const int64_t n_win = (nl + W - 1) / W;
+      if ((rc = p->wr0.need((size_t)n_win * 8))) return rc;
+      if ((rc = p->wr1.need((size_t)n_win * 8))) return rc;
+      k_plp_ranges<<<nbk(n_win, 256), 256, 0, s>>>(p->dr.pos, p->n_reads, (int32_t)tb, (int32_t)te, W, p->max_span, p->wr0.as<int64_t>(),
+                                                    p->wr1.as<int64_t>());
+      CKP(cudaGetLastError());
+      const size_t smem = (size_t)W * nb * PLP_NCNT * sizeof(int);
+      static bool attr_set = false;
+      if (!attr_set) { CKP(cudaFuncSetAttribute(k_plp_win, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr_set = true; }
+      k_plp_win<<<(unsigned)n_win, 256, smem, s>>>(p->dr, p->wr0.as<int64_t>(), p->wr1.as<int64_t>(), *cf, p->ref.as<uint8_t>(), p->ref_len, (int32_t)tb,
+                                                    (int32_t)te, W, nb, p->flags.as<int32_t>(), p->dense.as<bsq_plp_rec>(),
+                                                    p->scal.as<unsigned long long>());
+      CKP(cudaGetLastError());
+      CKP(cudaEventRecord(p->ev[1], s));
+    } else {
+      // unsorted reads: every read is tried against the tile, counters in a global tile
+      if ((rc = p->cnt.need((size_t)nl * nb * PLP_NCNT * 4))) return rc;
+      CKP(cudaMemsetAsync(p->cnt.p, 0, (size_t)nl * nb * PLP_NCNT * 4, s));
+      const int64_t r0 = 0, r1 = p->n_reads;
+      if (r1 > r0) {
+        k_plp_pile<<<nbk((r1 - r0) * 32, 256), 256, 0, s>>>(p->dr, r0, r1, *cf, p->ref.as<uint8_t>(), p->ref_len, (int32_t)tb, (int32_t)te, nb,
+                                                             p->cnt.as<int>(), p->scal.as<unsigned long long>());
+        CKP(cudaGetLastError());
+      }
+      CKP(cudaEventRecord(p->ev[1], s));
+      k_plp_locus<<<nbk(nl, 256), 256, 0, s>>>(p->cnt.as<int>(), *cf, p->ref.as<uint8_t>(), p->ref_len, (int32_t)tb, nl, nb, p->flags.as<int32_t>(),
+                                                p->dense.as<bsq_plp_rec>());
       CKP(cudaGetLastError());
     }
-    CKP(cudaEventRecord(p->ev[1], s));
-    k_plp_locus<<<nbk(nl, 256), 256, 0, s>>>(p->cnt.as<int>(), *cf, p->ref.as<uint8_t>(), p->ref_len, (int32_t)tb, nl, nb, p->flags.as<int32_t>(),
-                                              p->dense.as<bsq_plp_rec>());
-    CKP(cudaGetLastError());
     size_t tmpb = 0;
     CKP(cub::DeviceScan::ExclusiveSum(nullptr, tmpb, p->flags.as<int32_t>(), p->offs.as<int64_t>(), (int)nl, s));
     if ((rc = p->cub_tmp.need(tmpb))) return rc;
