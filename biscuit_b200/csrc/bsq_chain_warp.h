@@ -13,7 +13,8 @@
 //     order the reference reads out of its B-tree;
 //  3. inside a cluster the reference's sequential rule is replayed in arrival order against a small sorted
 //     list of the cluster's chains (lane 0; the list is a handful of entries);
-//  4. weights, the introsort by weight (exact comparison sequence, lane 0) and the greedy overlap filter, whose
+//  4. weights, the introsort by weight (partitions: exact comparison sequence on lane 0; final insertion sort: a
+//     parallel stable sort) and the greedy overlap filter, whose
 //     inner loop over the kept chains is spread over the lanes (first "drop" position by ballot).
 //
 // Exactness guard: the decomposition is only equivalent when (F1) no interval has more than max_occ occurrences
@@ -209,7 +210,7 @@ BSQ_HD int bsq_chain_warp(const bsq_devopt_t &opt, const bsq_devidx_t &ix, int p
   }
   W::sync();
   n_ch = s.pub[0];
-  // ---- 4a. weights (one chain per lane), then the order for the filter (lane 0: exact introsort) ----
+  // ---- 4a. weights (one chain per lane), then the order for the filter ----
   for (int c = lane; c < n_ch; c += NL) {
     const int a = s.clist[c];
     s.c_first[a] = -1; s.c_kept[a] = 0;
@@ -221,21 +222,32 @@ BSQ_HD int bsq_chain_warp(const bsq_devopt_t &opt, const bsq_devidx_t &ix, int p
     for (int c = lane; c < n_ch; c += NL) big |= s.c_w[s.clist[c]] >= 65536;
     if (W::any(big)) return BSQ_CW_FALLBACK;
   }
+  // ks_introsort = quicksort partitions that leave ranges of <= 16 elements, then ONE insertion sort over the whole
+  // array (ksort.h:150-157,184-233).  An insertion sort is stable, so the second part is "the stable sort by weight of
+  // whatever the partition phase left": lane 0 replays only the partitions (exact comparison/swap sequence), all
+  // lanes then sort (weight descending, slot after partitioning) keys, which are unique.
+  uint32_t *k32 = reinterpret_cast<uint32_t *>(s.c_last_rbeg);  // free since step 3; s.key takes the 64-bit keys
   if (lane == 0) {
-    uint32_t *k32 = reinterpret_cast<uint32_t *>(s.key);  // the position keys are no longer needed
     int k = 0;
     for (int c = 0; c < n_ch; ++c) {
       const int a = s.clist[c];
       if (s.c_w[a] >= opt.min_chain_weight) k32[k++] = (uint32_t)s.c_w[a] << 16 | (uint32_t)a;
     }
-    n_ch = k;
-    bsq_introsort(k32, (int64_t)n_ch, bsq_cw_by_weight());
-    for (int c = 0; c < n_ch; ++c) s.ord[c] = (uint16_t)(k32[c] & 0xffff);
-    if (n_ch > 0) { s.c_kept[s.ord[0]] = 3; s.keep[0] = 0; }
-    s.pub[0] = n_ch;
+    bsq_introsort<false>(k32, (int64_t)k, bsq_cw_by_weight());
+    s.pub[0] = k;
   }
   W::sync();
   n_ch = s.pub[0];
+  for (int c = lane; c < n_ch; c += NL) {
+    const uint32_t v = k32[c];
+    s.key[c] = (uint64_t)(0xffffu - (v >> 16)) << 32 | (uint64_t)c << 16 | (uint64_t)(v & 0xffffu);
+  }
+  W::sync();
+  W::sort_keys(s.key, n_ch);
+  W::sync();
+  for (int c = lane; c < n_ch; c += NL) s.ord[c] = (uint16_t)(s.key[c] & 0xffffu);
+  if (lane == 0 && n_ch > 0) { s.c_kept[(uint16_t)(s.key[0] & 0xffffu)] = 3; s.keep[0] = 0; }
+  W::sync();
   if (n_ch == 0) return BSQ_CW_OK;
   // ---- 4b. greedy overlap filter (memchain.c:427-457); inner loop over the kept chains spread over the lanes ----
   int n_keep = 1;

@@ -35,7 +35,9 @@ BSQ_HD void bsq_combsort(T *a, int64_t n, LT lt) {
   if (gap != 1) bsq_insertion_sort(a, n, lt);
 }
 
-template <typename T, typename LT>
+// FINAL = false stops before the final insertion sort: what remains is a *stable* sort of
+// the array as the partition phase left it, which the caller may do in any way it likes (bsq_chain_warp: in parallel).
+template <bool FINAL = true, typename T, typename LT>
 BSQ_HD void bsq_introsort(T *a, int64_t n, LT lt) {
   if (n < 1) return;
   if (n == 2) {
@@ -79,7 +81,7 @@ BSQ_HD void bsq_introsort(T *a, int64_t n, LT lt) {
       }
     } else {
       if (top == 0) {
-        bsq_insertion_sort(a, n, lt);
+        if (FINAL) bsq_insertion_sort(a, n, lt);
         return;
       }
       --top;

@@ -37,12 +37,61 @@ static void sam_sink(void *ctx, bq_read_t *seqs, int n) {
   if (ok && bq_verbose >= 3) fprintf(stderr, "[M::mem_process_seqs] Processed %d reads\n", n);
 }
 
+/* -p: interleaved input whose neighbours with equal names are pairs, everything else single-end (bseq_classify,
+ * bwa.c:119-138, and the MEM_F_SMARTPE branch of process(), align.c:109-143).  Each batch becomes up to two
+ * mem_process_seqs-style calls: the single-end reads first (no insert-size prior), then the pairs with
+ * n_processed advanced by the number of single-end reads; SAM lines leave in input order.  The sub-batches are
+ * shallow copies of the batch's reads (names / sequences stay owned by the batch, the SAM text by the copies). */
+static void free_sub_sam(bq_read_t *sub, int n) {
+  if (n <= 0) return;
+  for (int i = 0; i < n; ++i) if (!sub[i].sam_in_slab) free(sub[i].sam);
+  for (int k = 0; k < sub[0].n_sam_slabs; ++k) free(sub[0].sam_slabs[k]);
+  free(sub[0].sam_slabs);
+}
+
+static int align_smart_pairing(const bq_opt_t *opt, const bq_ref_t *ref, bsq_aligner *al, src_ctx_t *sc, const bq_pestat_t *pes0, const char *rg_id) {
+  int64_t n_processed = 0;
+  for (;;) {
+    int n = 0, i, has_last, m[2] = {0, 0};
+    bq_read_t *seqs = fastq_source(sc, &n);
+    if (!seqs || n <= 0) { free(seqs); break; }
+    bq_read_t *sep[2];
+    sep[0] = calloc((size_t)n + 1, sizeof(bq_read_t)); sep[1] = calloc((size_t)n + 1, sizeof(bq_read_t));
+    for (i = 1, has_last = 1; i < n; ++i) {
+      if (has_last) {
+        if (strcmp(seqs[i].name, seqs[i - 1].name) == 0) { sep[1][m[1]++] = seqs[i - 1]; sep[1][m[1]++] = seqs[i]; has_last = 0; }
+        else sep[0][m[0]++] = seqs[i - 1];
+      } else has_last = 1;
+    }
+    if (has_last) sep[0][m[0]++] = seqs[i - 1];
+    if (bq_verbose >= 3) fprintf(stderr, "[bseq_classify] %d SE sequences; %d PE sequences\n", m[0], m[1]);
+    const char **sam = calloc((size_t)n, sizeof(char *));
+    for (int k = 0; k < 2; ++k) {
+      if (!m[k]) continue;
+      bq_opt_t tmp = *opt;
+      if (k) tmp.flag |= BQ_F_PE; else tmp.flag &= ~BQ_F_PE;
+      for (i = 0; i < m[k]; ++i) { sep[k][i].slab = 0; sep[k][i].sam = 0; sep[k][i].sam_slabs = 0; sep[k][i].n_sam_slabs = 0; sep[k][i].sam_in_slab = 0; }
+      const int rc = bq_process_seqs(&tmp, al, ref, n_processed + (k ? m[0] : 0), m[k], sep[k], k ? pes0 : 0, rg_id);
+      if (rc) return rc;
+      for (i = 0; i < m[k]; ++i) sam[sep[k][i].id] = sep[k][i].sam;
+    }
+    for (i = 0; i < n; ++i) if (sam[i]) fputs(sam[i], stdout);
+    if (bq_verbose >= 3) fprintf(stderr, "[M::mem_process_seqs] Processed %d reads\n", n);
+    free(sam);
+    free_sub_sam(sep[0], m[0]); free_sub_sam(sep[1], m[1]);
+    free(sep[0]); free(sep[1]);
+    n_processed += n;
+    bq_reads_free(seqs, n);
+  }
+  return 0;
+}
+
 static double now(void) { struct timeval tv; gettimeofday(&tv, 0); return tv.tv_sec + tv.tv_usec * 1e-6; }
 
 static int align_usage(void) {
   fprintf(stderr, "\nUsage: biscuit align [options] <fai-index base> <in1.fq> [in2.fq]\n\n"
                   "Options follow `biscuit align` of BISCUIT %s: -@ -b -f -k -w -d -r -y -c -D -W -m -S -P -e -9 -A -B -O -E -L -U\n"
-                  "    -1 -2 -i -R -H -j -q -T -g -a -C -V -Y -M -I -v -J -K -z -5 -3, plus\n    -G INT   CUDA device [0]\n\n", BQ_VERSION);
+                  "    -1 -2 -i -R -H -j -q -T -g -a -C -V -Y -M -I -v -J -K -z -5 -3 -p, plus\n    -G INT   CUDA device [0]\n\n", BQ_VERSION);
   return 1;
 }
 
@@ -96,7 +145,7 @@ int bq_main_align(int argc, char **argv) {
   bq_opt_init(&opt);
   opt.flag |= BQ_F_NO_MULTI; /* align.c:334 */
   memset(&set, 0, sizeof set);
-  int c, i, ignore_alt = 0, auto_alt = 1, copy_comment = 0, no_hdr = 0, device = 0;
+  int c, i, ignore_alt = 0, auto_alt = 1, copy_comment = 0, no_hdr = 0, device = 0, smart_pe = 0;
   char *p, *rg_line = 0, *hdr_line = 0, *seq1 = 0, *seq2 = 0, rg_id[256] = "";
   bq_pestat_t *pes0 = 0;
   const uint8_t *t4 = 0;
@@ -194,7 +243,7 @@ int bq_main_align(int argc, char **argv) {
       if (*p != 0 && ispunct((unsigned char)*p) && isdigit((unsigned char)p[1])) pes0->low = (int)(strtod(p + 1, &p) + .499);
       if (bq_verbose >= 3)
         fprintf(stderr, "[M::main_align] mean insert size: %.3f, stddev: %.3f, max: %d, min: %d\n", pes0->avg, pes0->std, pes0->high, pes0->low);
-    } else if (c == 'p') bq_fatal("-p (smart pairing) is not supported by this build");
+    } else if (c == 'p') { opt.flag |= BQ_F_PE; smart_pe = 1; }
     else if (c == ':') { align_usage(); bq_fatal("Option needs an argument: -%c", optopt); }
     else if (c == '?') { align_usage(); bq_fatal("Unrecognized option: -%c", optopt); }
     else return align_usage();
@@ -237,7 +286,9 @@ int bq_main_align(int argc, char **argv) {
   if (!seq1) {
     if (!(f1 = bq_fastq_open(argv[optind + 1]))) { fprintf(stderr, "[E::main_align] fail to open file `%s'.\n", argv[optind + 1]); return 1; }
     if (optind + 2 < argc) {
-      if (!(f2 = bq_fastq_open(argv[optind + 2]))) { fprintf(stderr, "[E::main_align] fail to open file `%s'.\n", argv[optind + 2]); return 1; }
+      if (smart_pe) {
+        if (bq_verbose >= 2) fprintf(stderr, "[W::main_align] when '-p' is in use, the second query file is ignored.\n");
+      } else if (!(f2 = bq_fastq_open(argv[optind + 2]))) { fprintf(stderr, "[E::main_align] fail to open file `%s'.\n", argv[optind + 2]); return 1; }
       opt.flag |= BQ_F_PE;
     }
   }
@@ -259,7 +310,9 @@ int bq_main_align(int argc, char **argv) {
     bq_reads_free(seqs, n);
   } else {
     src_ctx_t sc = {&opt, f1, f2, chunk, copy_comment};
-    if ((rc = bq_pipeline_run(&opt, &idx.ref, al, al2, fastq_source, &sc, sam_sink, 0, pes0, rg_id)))
+    if (smart_pe) {
+      if ((rc = align_smart_pairing(&opt, &idx.ref, al, &sc, pes0, rg_id))) bq_fatal("alignment batch failed: %s (%s)", bsq_strerror(rc), bsq_last_error());
+    } else if ((rc = bq_pipeline_run(&opt, &idx.ref, al, al2, fastq_source, &sc, sam_sink, 0, pes0, rg_id)))
       bq_fatal("alignment batch failed: %s (%s)", bsq_strerror(rc), bsq_last_error());
   }
   bsq_aligner_destroy(al);

@@ -76,6 +76,30 @@ def test_sam_identical_single_end_hostemu(hard_set):
     assert _sam(build_emu_bin(), args) == _sam(refprobe.REF_BIN, args)
 
 
+def _interleave(f1, f2, out):
+    """Interleaved FASTQ for -p: most pairs complete, some reads without their mate (single-end)."""
+    a, b = open(f1).read().split("\n"), open(f2).read().split("\n")
+    with open(out, "w") as fo:
+        for i in range(len(a) // 4):
+            ra, rb = a[4 * i:4 * i + 4], b[4 * i:4 * i + 4]
+            if i % 7 != 3:
+                fo.write("\n".join(ra) + "\n")
+            if i % 11 != 5:
+                fo.write("\n".join(rb) + "\n")
+    return out
+
+
+@pytest.mark.parametrize("extra", [[], ["-K", "70000"], ["-I", "450,40"]], ids=["default", "small batches", "-I"])
+def test_sam_identical_smart_pairing_hostemu(hard_set, tmp_path, extra):
+    """-p (MEM_F_SMARTPE, align.c:109-143): interleaved input, pairs by equal neighbouring names, the rest single-end."""
+    fa, f1, f2 = hard_set
+    fq = _interleave(f1, f2, str(tmp_path / "il.fq"))
+    args = ["-@", "4", "-p"] + extra + [fa, fq]
+    mine = _sam(build_emu_bin(), args)
+    assert mine == _sam(refprobe.REF_BIN, args)
+    assert mine.count(b"\n") > 5000
+
+
 def test_sam_clean_1m_hostemu(ds_1m, tmp_path):
     """BASELINE.json configs[0] shape: clean 2x150 pairs vs a 1 Mb reference."""
     p = ds_1m["pairs"]
