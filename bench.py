@@ -300,6 +300,8 @@ def bench_pileup(args):
     try:
         if world > 1:
             raise RuntimeError("CLI leg runs at N=1 only")
+        if args.no_cli:
+            raise RuntimeError("skipped (--no-cli)")
         import bamio
         import tempfile
         with tempfile.TemporaryDirectory() as d:
@@ -403,6 +405,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=int(os.environ.get("BSQ_BENCH_PAIRS", "100000")))
     ap.add_argument("--cpu-pairs", type=int, default=int(os.environ.get("BSQ_BENCH_CPU_PAIRS", "10000")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cli", action="store_true", help="pileup: skip the command-line leg (profiling runs)")
     args = ap.parse_args()
     if args.path == "pileup":
         return bench_pileup(args)

@@ -446,7 +446,9 @@ static inline size_t seed_smem_bytes(int stride) {  // reads are at most BSQ_MAX
   const int len = stride < BSQ_MAX_READ_LEN ? stride : BSQ_MAX_READ_LEN;
   return (size_t)128 * BSQ_SEED_CAP * 16 + (size_t)((len + 7) >> 3) * 128 * 4;
 }
-static inline bool seed_pf() { static int v = -1; if (v < 0) { const char *e = getenv("BSQ_SEED_PREFETCH"); v = !e || atoi(e) != 0; } return v != 0; }
+// BSQ_SEED_PREFETCH=0 launches the k_seed2 build without the L2 prefetches (read at every launch: tools/ab_seed.py
+// toggles it inside one process)
+static inline bool seed_pf() { const char *e = getenv("BSQ_SEED_PREFETCH"); return !e || atoi(e) != 0; }
 static inline bool seed_v1() { static int v = -1; if (v < 0) { const char *e = getenv("BSQ_SEED_V1"); v = e && atoi(e) != 0; } return v != 0; }
 static inline unsigned seed_grid(int64_t n) {
   static bool attr_set = false;

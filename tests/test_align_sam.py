@@ -100,6 +100,14 @@ def test_sam_identical_smart_pairing_hostemu(hard_set, tmp_path, extra):
     assert mine.count(b"\n") > 5000
 
 
+@pytest.mark.gpu
+def test_sam_identical_smart_pairing_gpu(hard_set, tmp_path):
+    fa, f1, f2 = hard_set
+    fq = _interleave(f1, f2, str(tmp_path / "il.fq"))
+    args = ["-@", "4", "-p", "-K", "200000", fa, fq]
+    assert _sam(GPU_BIN, args) == _sam(refprobe.REF_BIN, args)
+
+
 def test_sam_clean_1m_hostemu(ds_1m, tmp_path):
     """BASELINE.json configs[0] shape: clean 2x150 pairs vs a 1 Mb reference."""
     p = ds_1m["pairs"]
