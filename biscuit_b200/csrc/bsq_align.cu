@@ -446,16 +446,23 @@ static inline size_t seed_smem_bytes(int stride) {  // reads are at most BSQ_MAX
   const int len = stride < BSQ_MAX_READ_LEN ? stride : BSQ_MAX_READ_LEN;
   return (size_t)128 * BSQ_SEED_CAP * 16 + (size_t)((len + 7) >> 3) * 128 * 4;
 }
-// BSQ_SEED_PREFETCH=0 launches the k_seed2 build without the L2 prefetches (read at every launch: tools/ab_seed.py
-// toggles it inside one process)
-static inline bool seed_pf() { const char *e = getenv("BSQ_SEED_PREFETCH"); return !e || atoi(e) != 0; }
+// BSQ_SEED_VARIANT=0 launches k_seed2 without the round-1 v7 changes (bsq_seed_dev.cuh).  Read at every launch:
+// tools/ab_seed.py toggles it inside one process.
+static inline int seed_variant() { const char *e = getenv("BSQ_SEED_VARIANT"); return e ? atoi(e) != 0 : 1; }
+static void launch_seed2(int variant, unsigned grid, cudaStream_t s, const bsq_devopt_t &opt, const bsq_devidx_t &ix, int64_t n, const uint8_t *seqs, int stride,
+                         const int32_t *lens, const uint8_t *parent, int pipeline, bsq_pk_t *intv, int32_t *n_intv, int32_t *status,
+                         unsigned long long *next_task) {
+  const size_t smem = seed_smem_bytes(stride);
+  if (variant) k_seed2<BSQ_SEED_CAP, 1><<<grid, 128, smem, s>>>(opt, ix, n, seqs, stride, lens, parent, pipeline, intv, n_intv, status, next_task);
+  else k_seed2<BSQ_SEED_CAP, 0><<<grid, 128, smem, s>>>(opt, ix, n, seqs, stride, lens, parent, pipeline, intv, n_intv, status, next_task);
+}
 static inline bool seed_v1() { static int v = -1; if (v < 0) { const char *e = getenv("BSQ_SEED_V1"); v = e && atoi(e) != 0; } return v != 0; }
 static inline unsigned seed_grid(int64_t n) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(k_seed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seed_smem_bytes(BSQ_MAX_READ_LEN + 8));
-    cudaFuncSetAttribute(k_seed2<BSQ_SEED_CAP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seed_smem_bytes(BSQ_MAX_READ_LEN + 8));
-    cudaFuncSetAttribute(k_seed2<BSQ_SEED_CAP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seed_smem_bytes(BSQ_MAX_READ_LEN + 8));
+    cudaFuncSetAttribute(k_seed2<BSQ_SEED_CAP, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seed_smem_bytes(BSQ_MAX_READ_LEN + 8));
+    cudaFuncSetAttribute(k_seed2<BSQ_SEED_CAP, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seed_smem_bytes(BSQ_MAX_READ_LEN + 8));
     attr_set = true;
   }
   int64_t want = (n + 127) / 128;
@@ -584,8 +591,7 @@ int bsq_collect_intv(const bsq_index *ix, const bsq_opt *opt_, int64_t n, const 
   CK(cudaMemset(dst, 0, 4)); CK(cudaMemset(dnext, 0, 8));
   CK(cudaMemset(dpk, 0, n * BSQ_MAX_INTV * sizeof(bsq_pk_t)));
   if (seed_v1()) k_seed<<<seed_grid(n), 128, seed_smem_bytes(stride)>>>(opt, ix->d, n, dseq, stride, dlen, dpar, 0, dpk, dn, dst, dnext);
-  else if (seed_pf()) k_seed2<BSQ_SEED_CAP, true><<<seed_grid(n), 128, seed_smem_bytes(stride)>>>(opt, ix->d, n, dseq, stride, dlen, dpar, 0, dpk, dn, dst, dnext);
-  else k_seed2<BSQ_SEED_CAP, false><<<seed_grid(n), 128, seed_smem_bytes(stride)>>>(opt, ix->d, n, dseq, stride, dlen, dpar, 0, dpk, dn, dst, dnext);
+  else launch_seed2(seed_variant(), seed_grid(n), 0, opt, ix->d, n, dseq, stride, dlen, dpar, 0, dpk, dn, dst, dnext);
   CK(cudaGetLastError());
   k_seed_sort<<<nblk(n, 128), 128>>>(opt, n, dpk, dn, dnsa);
   CK(cudaGetLastError());
@@ -710,14 +716,9 @@ static int phase1_device(bsq_aligner *al, int64_t n, int32_t stride, int64_t *to
     k_seed<<<seed_grid(n), 128, seed_smem_bytes(stride), s>>>(opt, ix, n, al->seqs.as<uint8_t>(), stride, al->lens.as<int32_t>(), al->parent.as<uint8_t>(), 1,
                                                               al->intv.as<bsq_pk_t>(), al->n_intv.as<int32_t>(), al->status.as<int32_t>(),
                                                               al->scalars.as<unsigned long long>());
-  else if (seed_pf())
-    k_seed2<BSQ_SEED_CAP, true><<<seed_grid(n), 128, seed_smem_bytes(stride), s>>>(opt, ix, n, al->seqs.as<uint8_t>(), stride, al->lens.as<int32_t>(),
-                                                                                   al->parent.as<uint8_t>(), 1, al->intv.as<bsq_pk_t>(), al->n_intv.as<int32_t>(),
-                                                                                   al->status.as<int32_t>(), al->scalars.as<unsigned long long>());
   else
-    k_seed2<BSQ_SEED_CAP, false><<<seed_grid(n), 128, seed_smem_bytes(stride), s>>>(opt, ix, n, al->seqs.as<uint8_t>(), stride, al->lens.as<int32_t>(),
-                                                                                    al->parent.as<uint8_t>(), 1, al->intv.as<bsq_pk_t>(), al->n_intv.as<int32_t>(),
-                                                                                    al->status.as<int32_t>(), al->scalars.as<unsigned long long>());
+    launch_seed2(seed_variant(), seed_grid(n), s, opt, ix, n, al->seqs.as<uint8_t>(), stride, al->lens.as<int32_t>(), al->parent.as<uint8_t>(), 1,
+                 al->intv.as<bsq_pk_t>(), al->n_intv.as<int32_t>(), al->status.as<int32_t>(), al->scalars.as<unsigned long long>());
   CK(cudaGetLastError());
   k_seed_sort<<<nblk(n, 128), 128, 0, s>>>(opt, n, al->intv.as<bsq_pk_t>(), al->n_intv.as<int32_t>(), al->n_sa.as<int32_t>());
   CK(cudaGetLastError());

@@ -106,28 +106,6 @@ BSQ_HD void bsq_2occ4_flat(const bsq_fm_t &fm, uint64_t k, uint64_t l, uint64_t 
   }
 }
 
-// L2 prefetch of the block(s) a later bsq_2occ4_flat(fm, xa - 1, xa - 1 + x2) will read.  The candidates of one
-// column of the backward sweep are independent of each other (bwt.c:347-361), so their blocks can be requested
-// one step ahead of the dependent chain; no effect on results.
-BSQ_HD void bsq_prefetch_2occ(const bsq_fm_t &fm, uint64_t xa, uint64_t x2) {
-#if defined(__CUDA_ARCH__)
-  if (xa == 0) return;
-  const uint64_t k = xa - 1, l = k + x2;
-  const uint64_t kb = (k - (k >= fm.primary)) >> 7, lb = (l - (l >= fm.primary)) >> 7;
-  const uint64_t g = (uint64_t)__cvta_generic_to_global(fm.blocks);
-  // per-thread prefetch (CCTL), one per 32-byte sector; the bulk form (UBLKPF) takes a warp-uniform address and would
-  // be issued once per lane in a loop
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(g + kb * 64));
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(g + kb * 64 + 32));
-  if (lb != kb) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(g + lb * 64));
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(g + lb * 64 + 32));
-  }
-#else
-  (void)fm; (void)xa; (void)x2;
-#endif
-}
-
 // bwt_extend (bwt.c:278-293).  BACK=1 extends to the left in `fm`; BACK=0 is the forward
 // extension, performed as a backward step in the complementary index.
 template <int BACK>

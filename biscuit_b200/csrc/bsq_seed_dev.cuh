@@ -48,11 +48,21 @@ struct seed2_list_t {
   }
 };
 
-// PF: request the blocks of independent backward-sweep candidates ahead of their use (bsq_prefetch_2occ): the next
-// candidate of the current column while this one is extended, and the first candidate of the next column as soon as
-// it is known.  About 60 % of all extension steps are backward steps with another candidate behind them (measured
-// with the host emulation), so most gathers of the dependent chain become L2 hits.
-template <int CAP, bool PF>
+// V = 1 (default) adds four things the source-level profile of V = 0 asked for (profiles/README.md, r01 v7: only a
+// fifth of the stall samples sat on the FM-index gathers, a third on candidate-list / interval-array accesses in
+// code executed by one to three lanes):
+//   * the SMEMs of one bwt_smem1a call are left in emission order -- k_seed_sort orders the whole list by (start, end)
+//     afterwards and records with equal keys are identical (same substring, same bi-interval), so the reversal of
+//     bwt.c:365 (a single-lane loop over global memory) changes nothing;
+//   * pass 2 (memchain.c:76-85) takes its re-seeding positions from a four-entry queue filled when pass 1 stores a
+//     long, rare SMEM, instead of re-reading every pass-1 interval from global memory (falls back to the scan when
+//     more than four qualify);
+//   * the next candidate of a backward column is loaded one step ahead (entries beyond the shared-memory ring
+//     live in local memory, and its address feeds the next gather);
+//   * reads whose row is not 8-byte aligned are converted from aligned 8-byte words (funnel shift), not bytewise.
+// (L2 prefetches of the next candidate's blocks were tried -- prefetch.global.L2 and LDGSTS into a scratch slot --
+// and measured slower: 67.5 / 56 ms against 47.5 ms.)
+template <int CAP, int V>
 __global__ void __launch_bounds__(128, BSQ_SEED_CTAS) k_seed2(const __grid_constant__ bsq_devopt_t opt, const __grid_constant__ bsq_devidx_t ix, int64_t n_tasks,
                                                               const uint8_t *seqs, int stride, const int32_t *lens, const uint8_t *parent, int pipeline,
                                                               bsq_pk_t *intv, int32_t *n_intv, int32_t *status, unsigned long long *next_task) {
@@ -72,6 +82,11 @@ __global__ void __launch_bounds__(128, BSQ_SEED_CTAS) k_seed2(const __grid_const
   int64_t t = -1;
   bool exhausted = false;
   bsq_pk_t *out = nullptr;
+  // V = 1: pass-2 queue (16 bits per entry: position << 7 | min_intv), preloaded candidate j + 1
+  uint64_t q2 = 0;
+  int q2n = 0;      // entries queued; -1: more than four qualified (or do not fit), pass 2 scans the list
+  bsq_pk_t nxt; nxt.w0 = nxt.w1 = 0;
+  bool nxt_ok = false;  // nxt holds entry j of the current column (loaded while entry j - 1 was extended)
 
 #define S2_Q(pos) ((int)(rd[((pos) >> 3) * 128] >> (((pos) & 7) * 4)) & 0xf)
   // a candidate cannot be extended further to the left (bwt.c:350-356).  n_tmp counts every SMEM of this call like the
@@ -82,6 +97,10 @@ __global__ void __launch_bounds__(128, BSQ_SEED_CTAS) k_seed2(const __grid_const
       if (n_out + n_tmp >= BSQ_MAX_INTV) overflow = 1;                                      \
       else {                                                                                \
         if ((END) - (i + 1) >= min_seed_len) out[n_out + n_keep++] = bsq_pk_make((X0), (X1), (X2), i + 1, (END)); \
+        if (V && pass == 1 && (END) - (i + 1) >= min_seed_len && (END) - (i + 1) >= split_len && (X2) <= (uint64_t)split_width) { \
+          if (q2n >= 0 && q2n < 4 && (X2) < 127) { q2 |= (uint64_t)(((i + 1 + (END)) >> 1) << 7 | (int)((X2) + 1)) << (16 * q2n); ++q2n; } \
+          else q2n = -1;                                                                    \
+        }                                                                                   \
         last_beg = i + 1;                                                                   \
         ++n_tmp;                                                                            \
       }                                                                                     \
@@ -104,10 +123,13 @@ __global__ void __launch_bounds__(128, BSQ_SEED_CTAS) k_seed2(const __grid_const
         ret = ik_end;  // read end of the last candidate pushed
         top = n_curr; n_prev = n_curr; n_curr = 0;
         i = x - 1; j = 0; n_tmp = 0; n_keep = 0;
+        nxt_ok = false;
         st = S2_BWD;
       } else if (st == S2_FINBWD) {  // end of one bwt_smem1a call: the kept SMEMs ordered by start (memchain.c:69-71)
-        bsq_pk_t *tt = out + n_out;
-        for (int a = 0, b = n_keep - 1; a < b; ++a, --b) { const bsq_pk_t s_ = tt[a]; tt[a] = tt[b]; tt[b] = s_; }
+        if (!V) {
+          bsq_pk_t *tt = out + n_out;
+          for (int a = 0, b = n_keep - 1; a < b; ++a, --b) { const bsq_pk_t s_ = tt[a]; tt[a] = tt[b]; tt[b] = s_; }
+        }
         n_out += n_keep; n_tmp = 0; n_keep = 0;
         if (pass == 1) x = ret;
         st = S2_NEXT;
@@ -125,10 +147,16 @@ __global__ void __launch_bounds__(128, BSQ_SEED_CTAS) k_seed2(const __grid_const
             const uint8_t *s = seqs + t * stride;
             const int nw = (len + 7) >> 3;
             const bool al8 = ((uintptr_t)s & 7) == 0;
+            const uint64_t *s8 = reinterpret_cast<const uint64_t *>((uintptr_t)s & ~(uintptr_t)7);
+            const int sh = (int)((uintptr_t)s & 7);  // bytes of the first aligned word that precede the row
+            q2 = 0; q2n = 0; nxt_ok = false;
             for (int w = 0; w < nw; ++w) {
               uint64_t v;
               if (al8) v = __ldg(reinterpret_cast<const uint64_t *>(s) + w);
-              else { v = 0; for (int k = 0; k < 8; ++k) if (8 * w + k < len) v |= (uint64_t)s[8 * w + k] << (8 * k); }
+              else if (V) {  // bases 8w .. 8w+7 from two aligned words; the second only if it holds a base of this row
+                v = __ldg(s8 + w) >> (8 * sh);
+                if (8 * w + 8 - sh < len) v |= __ldg(s8 + w + 1) << (64 - 8 * sh);
+              } else { v = 0; for (int k = 0; k < 8; ++k) if (8 * w + k < len) v |= (uint64_t)s[8 * w + k] << (8 * k); }
               uint32_t pk = 0;
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
@@ -153,7 +181,13 @@ __global__ void __launch_bounds__(128, BSQ_SEED_CTAS) k_seed2(const __grid_const
           if (x >= len) { pass = 2; old_n = n_out; k2 = 0; }
           else { sx = x; smin = start_width; }
         }
-        if (!done && pass == 2 && sx < 0) {  // re-seed from the middle of long, rare SMEMs (memchain.c:76-85)
+        if (V && !done && pass == 2 && sx < 0 && q2n >= 0) {  // re-seeding positions queued by pass 1
+          if (q2n > 0) {
+            const int e = (int)(q2 & 0xffff);
+            q2 >>= 16; --q2n;
+            sx = e >> 7; smin = e & 127; c = S2_Q(sx);
+          } else { pass = 3; x = 0; }
+        } else if (!done && pass == 2 && sx < 0) {  // re-seed from the middle of long, rare SMEMs (memchain.c:76-85)
           while (k2 < old_n) {
             const bsq_pk_t p = out[k2++];
             const int start = bsq_pk_beg(p), end = bsq_pk_end(p);
@@ -201,11 +235,12 @@ __global__ void __launch_bounds__(128, BSQ_SEED_CTAS) k_seed2(const __grid_const
     uint64_t x0 = ik0, x1 = ik1, x2 = ik2;
     int p_end = 0;
     if (isb) {
-      const bsq_pk_t p = lst.get(top, j);
+      bsq_pk_t p;
+      if (V && nxt_ok) p = nxt; else p = lst.get(top, j);
       x0 = bsq_pk_x0(p); x1 = bsq_pk_x1(p); x2 = bsq_pk_x2(p); p_end = bsq_pk_end(p);
-      if (PF && c <= 3 && j + 1 < n_prev && j + 1 < CAP) {  // entry j + 1 is untouched: the compaction writes entries <= j
-        const bsq_pk_t q = lst.get(top, j + 1);
-        bsq_prefetch_2occ(ix.fm[par], bsq_pk_x0(q), bsq_pk_x2(q));
+      if (V) {  // entry j + 1 is untouched by this step: the in-place compaction writes entries <= j
+        nxt_ok = j + 1 < n_prev;  // false at the last candidate of a column, so a new column / sweep starts clean
+        if (nxt_ok) nxt = lst.get(top, j + 1);
       }
     }
     const bool issue = act && c <= 3;
@@ -224,7 +259,6 @@ __global__ void __launch_bounds__(128, BSQ_SEED_CTAS) k_seed2(const __grid_const
       if (isb) {  // bwt.c:349-360
         if (o2 < (uint64_t)min_intv) S2_BWD_STOP(x0, x1, x2, p_end);
         else if (n_curr == 0 || o2 != last_x2) {
-          if (PF && n_curr == 0 && j + 1 < n_prev) bsq_prefetch_2occ(ix.fm[par], o0, o2);  // first candidate of the next column
           lst.set(top, n_curr++, bsq_pk_make(o0, o1, o2, 0, p_end));  // entry n_curr <= j: in-place compaction
           last_x2 = o2;
         }

@@ -1,4 +1,4 @@
-"""A/B of the k_seed2 L2 prefetch (BSQ_SEED_PREFETCH=1/0) inside one process, on the default bench workload:
+"""A/B of the k_seed2 variants (BSQ_SEED_VARIANT=1/0, list in AB_MODES) inside one process, on the default bench workload:
     python tools/ab_seed.py [ref_mb] [pairs]
 prints the per-kernel device times of warm runs for both settings and checks that the regions are identical."""
 import json
@@ -22,8 +22,8 @@ bsq = capi.load()
 dx = bsq.build_index(pac, len(nt4), names, offs, lens, device=0)
 al = capi.Aligner(dx, bsq.default_opt())
 out, ref = [], None
-for pf in (1, 0, 1, 0):
-    os.environ["BSQ_SEED_PREFETCH"] = str(pf)
+for pf in [int(x) for x in os.environ.get("AB_MODES", "1,0,1,0").split(",")]:
+    os.environ["BSQ_SEED_VARIANT"] = str(pf)
     for it in range(3):
         regs, off = al.phase1(seqs, tl, par)
         c = al.counters()
@@ -32,7 +32,7 @@ for pf in (1, 0, 1, 0):
         ref = (regs.tobytes(), off.tobytes())
     else:
         same = ref == (regs.tobytes(), off.tobytes())
-    row = {"prefetch": pf, "identical_to_first": same, **dict(zip(["k_seed", "k_sa", "k_chain", "k_region", "scan", "all"], [int(x) for x in c[5:11]]))}
+    row = {"variant": pf, "identical_to_first": same, **dict(zip(["k_seed", "k_sa", "k_chain", "k_region", "scan", "all"], [int(x) for x in c[5:11]]))}
     out.append(row)
     print(json.dumps(row), flush=True)
 al.close()
