@@ -265,7 +265,6 @@ def bench_pileup(args):
         kus += pl.counters()[4:6]
     barrier()
     dt = time.perf_counter() - t0
-    clocks = sampler.stop()
     c = pl.counters()
     barrier()
     t1 = time.perf_counter()
@@ -274,6 +273,7 @@ def bench_pileup(args):
         recs = pl.fetch(pl.run(conf, 1, L))
     barrier()
     dt_e2e = time.perf_counter() - t1
+    clocks = sampler.stop()  # sampled over both timed regions: the kernel-only one lasts a few tens of milliseconds
     kus /= args.steps
     # the one collective of the path: per-contig methylation statistics -> every rank (NCCL over NVLink)
     reduce_ms = None
@@ -349,6 +349,15 @@ def bench_pileup(args):
     # reads (packed SEQ, QUAL, record fields), reference, one flag per locus, one 88-byte record per emitted locus;
     # the per-locus counters stay in shared memory
     alg = rd["n_reads"] * (75 + 150 + 48) + (L - 1) * (1 + 4) + n_loci * 88
+    # dram__bytes_read.sum + dram__bytes_write.sum of k_plp_win from the committed ncu capture of this same command
+    # (profiles/ncu_summary_r01_v7.json: one 8 Mi-locus tile), scaled to the loci of one step; null for other workloads
+    plp_traffic = None
+    try:
+        if args.plp_mb == 20.0 and args.plp_depth == 30:
+            with open(os.path.join(ROOT, "profiles", "ncu_summary_r01_v7.json")) as fh:
+                plp_traffic = json.load(fh)["kernels"]["k_plp_win"]["dram_bytes_per_locus"] * (L - 1)
+    except Exception:  # noqa: BLE001
+        plp_traffic = None
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         import oracle_plp
@@ -376,7 +385,7 @@ def bench_pileup(args):
             "e2e_cli": cli,
             "gpu_launches": 3 * args.steps * ((L + (8 << 20) - 1) // (8 << 20)),
             "roofline": {"bound": "hbm", "kernel": "k_plp_win", "achieved": alg / (kus[0] * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": alg / (kus[0] * 1e-6) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": alg / (kus[0] * 1e-6) / 1e9 / peak, "traffic": plp_traffic, "peak_source": peak_src,
                          "kernel_ms": kus[0] / 1000, "locus_kernels_ms": kus[1] / 1000, "events": int(c[3])},
             "cpu_baseline": cpu}
     emit(line)
@@ -534,6 +543,7 @@ def main():
         stage(); run(); fetch()
     barrier()
     dt_e2e = time.perf_counter() - t1
+    clocks = sampler.stop()  # sampled over both timed regions: the kernel-only one lasts a few tens of milliseconds
     d2h = int(n_regs.value) * 56 + (n_tasks + 1) * 8
     # --- end to end, whole batch boundary (mem_process_seqs equivalent): host nt4 reads in, SAM text out ---
     hostlib = C.CDLL(os.path.join(capi.HERE, "host", "libbiscuit_host.so"))
