@@ -102,6 +102,7 @@ typedef struct {
   /* phase 2 writes the SAM text of a batch into one buffer per worker thread; .sam then points into it
    * (sam_in_slab) and the buffers hang off the first read of the batch */
   uint8_t sam_in_slab;
+  size_t sam_off; /* phase-2 workers format straight into their slab: offset of this read's text until the batch is done */
   int n_sam_slabs;
   char **sam_slabs;
 } bq_read_t;
@@ -125,6 +126,7 @@ typedef struct {
 typedef struct {
   size_t n, m, n_pri;
   bq_reg_t *a;
+  int pooled; /* a[] is a slice of a batch pool / a stack array: never freed, copied out by the first push beyond m */
 } bq_regv_t;
 
 typedef struct {
@@ -219,6 +221,10 @@ typedef struct bq_fastq bq_fastq_t;
 bq_fastq_t *bq_fastq_open(const char *fn);
 void bq_fastq_close(bq_fastq_t *f);
 bq_read_t *bq_read_batch(int chunk_size, int has_bc, int keep_comment, int *n, bq_fastq_t *f1, bq_fastq_t *f2);
+/* large per-batch buffers (read slabs, SAM slabs, region pools) are recycled between batches: fresh memory costs a
+ * page fault per 4 KB, and under a hypervisor those faults are slow and serialise the worker threads */
+void *bq_big_alloc(size_t n, size_t *cap);
+void bq_big_free(void *p);
 void bq_reads_free(bq_read_t *seqs, int n); /* reads of one batch incl. their .sam strings and the array itself */
 void bq_print_sam_hdr(const bq_ref_t *ref, const char *hdr_line, const char *pg_line);
 void bq_fatal(const char *fmt, ...);

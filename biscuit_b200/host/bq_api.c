@@ -81,7 +81,8 @@ static bq_read_t *make_reads(int64_t n_processed, int n, const uint8_t *seqs, in
   bq_read_t *rd = calloc((size_t)n + 1, sizeof(bq_read_t));
   size_t tot = 0;
   for (int i = 0; i < n; ++i) tot += 24 + 2 * ((size_t)lens[i] + 1);
-  char *slab = malloc(tot + 16), *p = slab;
+  size_t cap_ = 0;
+  char *slab = bq_big_alloc(tot + 16, &cap_), *p = slab;
   for (int i = 0; i < n; ++i) {
     rd[i].name = p; p += 1 + sprintf(p, "r%lld", (long long)((n_processed + i) >> 1));
     rd[i].l_seq = rd[i].l_seq0 = lens[i];
@@ -91,7 +92,7 @@ static bq_read_t *make_reads(int64_t n_processed, int n, const uint8_t *seqs, in
     p[lens[i]] = 0; p += lens[i] + 1;
     rd[i].id = i; rd[i].in_slab = 1;
   }
-  if (n > 0) rd[0].slab = slab; else free(slab);
+  if (n > 0) rd[0].slab = slab; else bq_big_free(slab);
   return rd;
 }
 

@@ -394,11 +394,24 @@ uint32_t *bq_gen_cigar(const int8_t mat[25], int o_del, int e_del, int o_ins, in
   if (n_cigar) *n_cigar = 0;
   if (NM) *NM = -1;
   if (l_query <= 0 || rb >= re || (rb < l_pac && re > l_pac)) return 0;
-  uint8_t *rseq = bq_get_seq(l_pac, pac, rb, re, &rlen);
-  if (re - rb != rlen) { free(rseq); return 0; }
+  /* this runs once or twice per read: the reference window, the single-M CIGAR and the MD text live on the stack
+   * whenever they fit, and the returned block is allocated once */
+  uint8_t rbuf[1024], *rseq;
+  uint32_t one_m = 0;
+  int cigar_local = 0;
+  if (re - rb <= (int64_t)sizeof rbuf && rb >= 0 && re <= l_pac << 1) { /* bq_get_seq without the allocation (bntseq.c:402-422) */
+    rseq = rbuf; rlen = re - rb;
+    int64_t l = 0;
+    if (rb >= l_pac) {
+      const int64_t beg_f = (l_pac << 1) - 1 - re, end_f = (l_pac << 1) - 1 - rb;
+      for (int64_t k = end_f; k > beg_f; --k) rseq[l++] = 3 - PAC(pac, k);
+    } else
+      for (int64_t k = rb; k < re; ++k) rseq[l++] = PAC(pac, k);
+  } else rseq = bq_get_seq(l_pac, pac, rb, re, &rlen);
+  if (re - rb != rlen) { if (rseq != rbuf) free(rseq); return 0; }
   if (rb >= l_pac) { rev_bytes(l_query, query); rev_bytes((int)rlen, rseq); } /* left-align indels on the forward strand */
   if (l_query == re - rb && w_ == 0) { /* ungapped: one M, no DP (bwa.c:314-322) */
-    if (n_cigar) { cigar = malloc(4); cigar[0] = (uint32_t)l_query << 4; *n_cigar = 1; }
+    if (n_cigar) { one_m = (uint32_t)l_query << 4; cigar = &one_m; cigar_local = 1; *n_cigar = 1; }
     for (i = 0, *score = 0; i < l_query; ++i) *score += mat[rseq[i] * 5 + query[i]];
   } else {
     int max_ins = (int)((double)(((l_query + 1) >> 1) * mat[0] - o_ins) / e_ins + 1.);
@@ -413,7 +426,12 @@ uint32_t *bq_gen_cigar(const int8_t mat[25], int o_del, int e_del, int o_ins, in
   }
   if (NM && n_cigar) {
     int k, x = 0, y = 0, u = 0, n_mm = 0, n_gap = 0, n_conv_ct = 0, n_ret_c = 0, n_conv_ga = 0, n_ret_g = 0;
+    char mdbuf[2048];
     bq_str_t md = {0, 0, 0};
+    /* a mismatch costs the digits of the run before it (at most run + 1 characters) and a letter, a deletion '^' and
+     * its bases: fewer than 3 characters per reference base and CIGAR operation */
+    const int md_on_stack = 3 * (size_t)(rlen + *n_cigar) + 32 < sizeof mdbuf;
+    if (md_on_stack) { md.s = mdbuf; md.m = sizeof mdbuf; mdbuf[0] = 0; }
     const char *int2base = rb < l_pac ? "ACGTN" : "TGCAN";
     for (k = 0; k < *n_cigar; ++k) {
       const int op = cigar[k] & 0xf, len = (int)(cigar[k] >> 4);
@@ -439,15 +457,18 @@ uint32_t *bq_gen_cigar(const int8_t mat[25], int o_del, int e_del, int o_ins, in
       } else if (op == 1) { x += len; n_gap += len; }
     }
     bq_kputw(&md, u);
-    cigar = realloc(cigar, (size_t)*n_cigar * 4 + md.l + 1); /* MD string stored right behind the CIGAR words */
+    /* MD string stored right behind the CIGAR words; 8 spare bytes for the two clipping operations set_sam may add */
+    if (cigar_local) { cigar = malloc((size_t)*n_cigar * 4 + md.l + 1 + 8); cigar[0] = one_m; cigar_local = 0; }
+    else cigar = realloc(cigar, (size_t)*n_cigar * 4 + md.l + 1 + 8);
     memcpy((char *)(cigar + *n_cigar), md.s, md.l + 1);
-    free(md.s);
+    if (!md_on_stack) free(md.s);
     *NM = n_mm + n_gap;
     *ZC = parent ? (uint32_t)n_conv_ct : (uint32_t)n_conv_ga;
     *ZR = parent ? (uint32_t)n_ret_c : (uint32_t)n_ret_g;
     *bss_u = (n_conv_ct == 0 && n_conv_ga == 0) ? 1 : 0;
   }
   if (rb >= l_pac) rev_bytes(l_query, query);
-  free(rseq);
+  if (rseq != rbuf) free(rseq);
+  if (cigar_local) { cigar = malloc(4); cigar[0] = one_m; } /* caller did not ask for NM / MD */
   return cigar;
 }

@@ -157,11 +157,54 @@ static void to_read_slab(bq_fastq_t *f, bq_read_t *s, bq_str_t *slab, size_t off
   s->in_slab = 1;
 }
 
+/* ---------------- recycled large buffers ---------------- */
+#include <malloc.h>
+#include <pthread.h>
+#define BQ_BIG_SLOTS 48
+#define BQ_BIG_MIN (256u << 10) /* smaller blocks go back to malloc */
+static pthread_mutex_t g_big_mu = PTHREAD_MUTEX_INITIALIZER;
+static struct { void *p; size_t cap; } g_big[BQ_BIG_SLOTS];
+
+void *bq_big_alloc(size_t n, size_t *cap) {
+  void *p = 0;
+  pthread_mutex_lock(&g_big_mu);
+  int best = -1;
+  for (int i = 0; i < BQ_BIG_SLOTS; ++i)
+    if (g_big[i].p && g_big[i].cap >= n && (best < 0 || g_big[i].cap < g_big[best].cap)) best = i;
+  if (best >= 0 && g_big[best].cap <= 4 * n + (1u << 20)) { p = g_big[best].p; *cap = g_big[best].cap; g_big[best].p = 0; }
+  pthread_mutex_unlock(&g_big_mu);
+  if (!p) {
+    size_t want = n + (n >> 3) + 64;
+    p = malloc(want);
+    if (!p) bq_fatal("out of memory (%zu bytes)", want);
+    *cap = malloc_usable_size(p);
+  }
+  return p;
+}
+
+void bq_big_free(void *p) {
+  if (!p) return;
+  const size_t cap = malloc_usable_size(p);
+  if (cap >= BQ_BIG_MIN) {
+    pthread_mutex_lock(&g_big_mu);
+    int slot = -1, smallest = -1;
+    for (int i = 0; i < BQ_BIG_SLOTS; ++i) {
+      if (!g_big[i].p) { slot = i; break; }
+      if (smallest < 0 || g_big[i].cap < g_big[smallest].cap) smallest = i;
+    }
+    if (slot < 0 && g_big[smallest].cap < cap) { void *q = g_big[smallest].p; g_big[smallest].p = p; g_big[smallest].cap = cap; p = q; }
+    else if (slot >= 0) { g_big[slot].p = p; g_big[slot].cap = cap; p = 0; }
+    pthread_mutex_unlock(&g_big_mu);
+  }
+  free(p);
+}
+
 bq_read_t *bq_read_batch(int chunk_size, int has_bc, int keep_comment, int *n_, bq_fastq_t *f1, bq_fastq_t *f2) { /* bis_bseq_read, bwa.c:817-850 */
   int size = 0, m = 0, n = 0;
   bq_read_t *seqs = 0;
   const int use_slab = !has_bc && !keep_comment;
   bq_str_t slab = {0, 0, 0};
+  if (use_slab) { slab.s = bq_big_alloc((size_t)chunk_size * 2 + ((size_t)chunk_size >> 2) + 4096, &slab.m); slab.s[0] = 0; }
   size_t *offs = 0;
   while (fq_read(f1) >= 0) {
     if (f2 && fq_read(f2) < 0) { fprintf(stderr, "[W::bis_bseq_read] the 2nd file has fewer sequences.\n"); break; }
@@ -190,7 +233,7 @@ bq_read_t *bq_read_batch(int chunk_size, int has_bc, int keep_comment, int *n_, 
       seqs[i].qual = offs[3 * (size_t)i + 2] == (size_t)-1 ? 0 : slab.s + offs[3 * (size_t)i + 2];
     }
     seqs[0].slab = slab.s;
-  } else free(slab.s);
+  } else bq_big_free(slab.s);
   free(offs);
   *n_ = n;
   return seqs;
@@ -206,9 +249,9 @@ void bq_reads_free(bq_read_t *seqs, int n) {
     free(seqs[i].comment); free(seqs[i].barcode); free(seqs[i].umi);
     if (!seqs[i].sam_in_slab) free(seqs[i].sam);
   }
-  for (int k = 0; k < n_sam_slabs; ++k) free(sam_slabs[k]);
+  for (int k = 0; k < n_sam_slabs; ++k) bq_big_free(sam_slabs[k]);
   free(sam_slabs);
-  free(slab);
+  bq_big_free(slab);
   free(seqs);
 }
 

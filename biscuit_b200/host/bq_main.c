@@ -45,7 +45,7 @@ static void sam_sink(void *ctx, bq_read_t *seqs, int n) {
 static void free_sub_sam(bq_read_t *sub, int n) {
   if (n <= 0) return;
   for (int i = 0; i < n; ++i) if (!sub[i].sam_in_slab) free(sub[i].sam);
-  for (int k = 0; k < sub[0].n_sam_slabs; ++k) free(sub[0].sam_slabs[k]);
+  for (int k = 0; k < sub[0].n_sam_slabs; ++k) bq_big_free(sub[0].sam_slabs[k]);
   free(sub[0].sam_slabs);
 }
 
@@ -293,6 +293,7 @@ int bq_main_align(int argc, char **argv) {
     }
   }
   if (!no_hdr) bq_print_sam_hdr(&idx.ref, hdr_line, getenv("BISCUIT_PG_LINE"));
+  if (getenv("BQ_CHUNK_SIZE")) opt.chunk_size = atoi(getenv("BQ_CHUNK_SIZE")); /* test hook: bases per thread and batch */
   const int chunk = opt.chunk_size * opt.n_threads;
   if (seq1) { /* -1/-2: literal reads (align.c:77-81) */
     int n = seq2 ? 2 : 1;

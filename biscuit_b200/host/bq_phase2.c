@@ -20,7 +20,15 @@ static double bq_now(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, 
 #define MAXV(a, b) ((a) > (b) ? (a) : (b))
 
 static void regv_push(bq_regv_t *v, const bq_reg_t *r) {
-  if (v->n == v->m) { v->m = v->m ? v->m << 1 : 4; v->a = realloc(v->a, v->m * sizeof(bq_reg_t)); }
+  if (v->n == v->m) {
+    const size_t m = v->m ? v->m << 1 : 4;
+    if (v->pooled) { /* leave the pool slice / stack array behind */
+      bq_reg_t *na = malloc(m * sizeof(bq_reg_t));
+      memcpy(na, v->a, v->n * sizeof(bq_reg_t));
+      v->a = na; v->pooled = 0;
+    } else v->a = realloc(v->a, m * sizeof(bq_reg_t));
+    v->m = m;
+  }
   v->a[v->n++] = *r;
 }
 
@@ -213,13 +221,13 @@ static void matesw_core(const bq_opt_t *opt, const bq_ref_t *ref, bq_pestat_t pe
     int64_t is;
     if (reg_isize(ref, reg, &mregs->a[i], &is) && is >= pes.low && is <= pes.high) return;
   }
-  uint8_t *rev = malloc((size_t)l_ms + 1);
+  uint8_t revbuf[512], *rev = l_ms < (int)sizeof revbuf ? revbuf : malloc((size_t)l_ms + 1);
   for (i = 0; i < l_ms; ++i) rev[l_ms - 1 - i] = ms[i] < 4 ? 3 - ms[i] : 4;
   int64_t rb = MAXV(0, reg->rb + pes.low - l_ms), re = MINV(l_pac << 1, reg->rb + pes.high);
   uint8_t *rseq = 0;
   int rid = -1;
   if (rb < re) rseq = bq_fetch_seq(ref, &rb, (rb + re) >> 1, &re, &rid);
-  if (reg->rid != rid || re - rb < opt->min_seed_len) { free(rev); free(rseq); return; }
+  if (reg->rid != rid || re - rb < opt->min_seed_len) { if (rev != revbuf) free(rev); free(rseq); return; }
   const uint8_t parent = reg->bss ^ (reg->rb < l_pac);
   const int xtra = BQ_XSUBO | BQ_XSTART | (l_ms * opt->a < 250 ? BQ_XBYTE : 0) | (opt->min_seed_len * opt->a);
   bq_swr_t aln = bq_local_align(l_ms, rev, (int)(re - rb), rseq, parent ? opt->gamat : opt->ctmat, opt->o_del, opt->e_del, opt->o_ins,
@@ -241,11 +249,13 @@ static void matesw_core(const bq_opt_t *opt, const bq_ref_t *ref, bq_pestat_t pe
     mregs->a[i] = b;
     sort_dedup(opt, 0, 0, mregs);
   }
-  free(rev); free(rseq);
+  if (rev != revbuf) free(rev);
+  free(rseq);
 }
 
 void bq_matesw(const bq_opt_t *opt, const bq_ref_t *ref, bq_pestat_t pes, bq_read_t s[2], bq_regv_t regs[2]) {
-  bq_regv_t good[2] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+  bq_reg_t gbuf[2][8];
+  bq_regv_t good[2] = {{0, 8, 0, gbuf[0], 1}, {0, 8, 0, gbuf[1], 1}};
   int i;
   size_t j;
   for (i = 0; i < 2; ++i)
@@ -254,7 +264,7 @@ void bq_matesw(const bq_opt_t *opt, const bq_ref_t *ref, bq_pestat_t pes, bq_rea
   for (i = 0; i < 2; ++i)
     for (j = 0; j < good[i].n && (int)j < opt->max_matesw; ++j)
       matesw_core(opt, ref, pes, &good[i].a[j], s[!i].l_seq, s[!i].seq, &regs[!i]);
-  free(good[0].a); free(good[1].a);
+  for (i = 0; i < 2; ++i) if (!good[i].pooled) free(good[i].a);
 }
 
 /* ---------------- primary marking: mem_alnreg.c:242-380 ---------------- */
@@ -306,7 +316,7 @@ void bq_mark_primary(const bq_opt_t *opt, bq_regv_t *regs, int64_t id) {
     if (!p->is_alt) ++regs->n_pri;
   }
   bq_introsort(regs->a, regs->n, sizeof(bq_reg_t), lt_hash);
-  int *z = malloc(sizeof(int) * (regs->n + 1));
+  int zbuf[64], *z = regs->n < 64 ? zbuf : malloc(sizeof(int) * (regs->n + 1));
   mark_core(opt, (int)regs->n, regs, z, &nz);
   for (i = 0; (size_t)i < regs->n; ++i) {
     bq_reg_t *p = regs->a + i;
@@ -326,7 +336,7 @@ void bq_mark_primary(const bq_opt_t *opt, bq_regv_t *regs, int64_t id) {
     mark_core(opt, (int)regs->n_pri, regs, z, &nz);
   } else
     for (i = 0; (size_t)i < regs->n; ++i) regs->a[i].secondary_all = regs->a[i].secondary;
-  free(z);
+  if (z != zbuf) free(z);
 }
 
 /* ---------------- mapQ: bwamem.c:134-157 ---------------- */
@@ -364,9 +374,9 @@ static int lt_xy2(const void *a_, const void *b_) { const pair_t *a = a_, *b = b
 static void pair_regs(const bq_opt_t *opt, const bq_ref_t *ref, bq_pestat_t pes, bq_regv_t regs[2], int id, int *score, int *sub, int *n_sub,
                       int z[2]) {
   const int64_t l_pac = ref->l_pac;
-  size_t nv = regs[0].n_pri + regs[1].n_pri, n = 0, np = 0, mp = 0;
-  trio_t *v = malloc(sizeof(trio_t) * (nv + 1));
-  pair_t *pp = 0;
+  size_t nv = regs[0].n_pri + regs[1].n_pri, n = 0, np = 0, mp = 16;
+  trio_t vbuf[64], *v = nv < 64 ? vbuf : malloc(sizeof(trio_t) * (nv + 1));
+  pair_t pbuf[16], *pp = pbuf;
   int i, k, r;
   for (r = 0; r < 2; ++r)
     for (i = 0; (size_t)i < regs[r].n_pri; ++i) {
@@ -389,7 +399,11 @@ static void pair_regs(const bq_opt_t *opt, const bq_ref_t *ref, bq_pestat_t pes,
         double zscore = (is - pes.avg) / pes.std;
         int sc = (int)((v[i].y >> 32) + (v[k].y >> 32) + .721 * log(2. * erfc(fabs(zscore) * M_SQRT1_2)) * opt->a + .499);
         sc = MAXV(0, sc);
-        if (np == mp) { mp = mp ? mp << 1 : 8; pp = realloc(pp, mp * sizeof(pair_t)); }
+        if (np == mp) {
+          mp <<= 1;
+          if (pp == pbuf) { pp = malloc(mp * sizeof(pair_t)); memcpy(pp, pbuf, np * sizeof(pair_t)); }
+          else pp = realloc(pp, mp * sizeof(pair_t));
+        }
         pp[np].y = (uint64_t)k << 32 | (uint64_t)i;
         pp[np].x = (uint64_t)sc << 32 | (bq_hash64(pp[np].y ^ (uint64_t)(int64_t)(id << 8)) & 0xffffffffU);
         ++np;
@@ -410,7 +424,8 @@ static void pair_regs(const bq_opt_t *opt, const bq_ref_t *ref, bq_pestat_t pes,
     for (long u = (long)np - 2; u >= 0; --u)
       if (*sub - (int)(pp[u].x >> 32) <= tmp) ++*n_sub;
   } else { *score = 0; *sub = 0; *n_sub = 0; z[0] = z[1] = -1; }
-  free(pp); free(v);
+  if (pp != pbuf) free(pp);
+  if (v != vbuf) free(v);
 }
 
 /* ---------------- SAM: mem_alnreg_format.c ---------------- */
@@ -431,7 +446,7 @@ static int get_rlen(int n_cigar, const uint32_t *cigar) {
 /* mem_alnreg_setSAM (:40-123): final CIGAR with band doubling, position, clipping */
 static void set_sam(const bq_opt_t *opt, const bq_ref_t *ref, bq_read_t *s, bq_reg_t *reg) {
   if (reg->n_cigar > 0) return;
-  uint8_t *query = malloc((size_t)s->l_seq + 1);
+  uint8_t qbuf[512], *query = s->l_seq < (int)sizeof qbuf ? qbuf : malloc((size_t)s->l_seq + 1);
   int i;
   for (i = 0; i < s->l_seq; ++i) query[i] = s->seq[i] < 5 ? s->seq[i] : 4;
   int w1 = infer_bw(reg->qe - reg->qb, (int)(reg->re - reg->rb), reg->truesc, opt->a, opt->o_del, opt->e_del);
@@ -472,7 +487,7 @@ static void set_sam(const bq_opt_t *opt, const bq_ref_t *ref, bq_read_t *s, bq_r
     if (clip5) { memmove(cigar + 1, cigar, (size_t)n_cigar * 4 + l_MD); cigar[0] = (uint32_t)clip5 << 4 | 3; ++n_cigar; }
     if (clip3) { memmove(cigar + n_cigar + 1, cigar + n_cigar, (size_t)l_MD); cigar[n_cigar++] = (uint32_t)clip3 << 4 | 3; }
   }
-  free(query);
+  if (query != qbuf) free(query);
   reg->n_cigar = n_cigar;
   if (reg->n_cigar > 0) reg->cigar = cigar; else free(cigar);
   reg->pos = (int)(rpos - ref->anns[reg->rid].offset);
@@ -630,9 +645,28 @@ static void format_sam(const bq_opt_t *opt, const bq_ref_t *ref, bq_str_t *str, 
   bq_kputc(str, '\n');
 }
 
+/* Where the SAM text of a read goes: phase-2 workers point tl_sam_slab at their own slab and the text is formatted
+ * in place (offset kept in sam_off, pointers fixed up when the batch is done); without it (direct callers of
+ * bq_reg2sam_*) every read gets its own string as in the reference. */
+static __thread bq_str_t *tl_sam_slab;
+typedef struct { bq_str_t own, *str; size_t off0; } sam_out_t;
+static bq_str_t *sam_out_begin(sam_out_t *o, const bq_read_t *s) {
+  o->own.l = o->own.m = 0; o->own.s = 0;
+  o->str = tl_sam_slab ? tl_sam_slab : &o->own;
+  o->off0 = o->str->l;
+  bq_str_reserve(o->str, 2 * (size_t)s->l_seq0 + 400);
+  return o->str;
+}
+static void sam_out_end(sam_out_t *o, bq_read_t *s) {
+  if (o->str == &o->own) { s->sam = o->own.s; return; }
+  bq_str_reserve(o->str, 1);
+  o->str->s[o->str->l++] = 0; /* keep the terminating NUL inside the slab */
+  s->sam = 0; s->sam_in_slab = 1; s->sam_off = o->off0;
+}
+
 /* mem_alnreg_select_format (:445-488) */
-static int *select_format(const bq_opt_t *opt, const bq_ref_t *ref, bq_read_t *s, bq_regv_t *regs, int *n_out) {
-  int *out = malloc(sizeof(int) * (regs->n + 1)), l = 0;
+static int *select_format(const bq_opt_t *opt, const bq_ref_t *ref, bq_read_t *s, bq_regv_t *regs, int *n_out, int *buf, int n_buf) {
+  int *out = regs->n < (size_t)n_buf ? buf : malloc(sizeof(int) * (regs->n + 1)), l = 0;
   for (size_t k = 0; k < regs->n; ++k) {
     bq_reg_t *p = regs->a + k;
     if (p->rb < 0 || p->re < 0) continue;
@@ -651,26 +685,28 @@ static int *select_format(const bq_opt_t *opt, const bq_ref_t *ref, bq_read_t *s
 }
 
 void bq_reg2sam_se(const bq_opt_t *opt, const bq_ref_t *ref, bq_read_t *s, bq_regv_t *regs, const char *rg_id) {
-  bq_str_t str = {0, 0, 0};
-  bq_str_reserve(&str, 2 * (size_t)s->l_seq0 + 400);
-  int n, *to = select_format(opt, ref, s, regs, &n);
-  if (n > 0) for (int i = 0; i < n; ++i) format_sam(opt, ref, &str, s, &regs->a[to[i]], 0, regs, !i, 0, rg_id);
+  sam_out_t so;
+  bq_str_t *str = sam_out_begin(&so, s);
+  int tobuf[64];
+  int n, *to = select_format(opt, ref, s, regs, &n, tobuf, 64);
+  if (n > 0) for (int i = 0; i < n; ++i) format_sam(opt, ref, str, s, &regs->a[to[i]], 0, regs, !i, 0, rg_id);
   else {
     bq_reg_t reg;
     memset(&reg, 0, sizeof reg);
     reg.rid = -1; reg.flag = 0x4;
-    format_sam(opt, ref, &str, s, &reg, 0, regs, 1, 0, rg_id);
+    format_sam(opt, ref, str, s, &reg, 0, regs, 1, 0, rg_id);
   }
-  s->sam = str.s;
-  free(to);
+  sam_out_end(&so, s);
+  if (to != tobuf) free(to);
 }
 
 static void reg2sam_pe_nopairing(const bq_opt_t *opt, const bq_ref_t *ref, bq_read_t s[2], bq_regv_t regs[2], bq_pestat_t pes,
                                  const char *rg_id) {
   bq_reg_t *best[2] = {0, 0}, unmapped[2];
+  int tobuf[2][64];
   int *to[2], n_to[2], i;
   for (i = 0; i < 2; ++i) {
-    to[i] = select_format(opt, ref, &s[i], &regs[i], &n_to[i]);
+    to[i] = select_format(opt, ref, &s[i], &regs[i], &n_to[i], tobuf[i], 64);
     if (n_to[i] > 0) best[i] = &regs[i].a[to[i][0]];
     else {
       memset(&unmapped[i], 0, sizeof(bq_reg_t));
@@ -679,14 +715,14 @@ static void reg2sam_pe_nopairing(const bq_opt_t *opt, const bq_ref_t *ref, bq_re
     }
   }
   for (i = 0; i < 2; ++i) {
-    bq_str_t str = {0, 0, 0};
-    bq_str_reserve(&str, 2 * (size_t)s[i].l_seq0 + 400);
+    sam_out_t so;
+    bq_str_t *str = sam_out_begin(&so, &s[i]);
     if (n_to[i]) {
-      for (int j = 0; j < n_to[i]; ++j) format_sam(opt, ref, &str, &s[i], &regs[i].a[to[i][j]], best[!i], &regs[i], !j, &pes, rg_id);
-    } else format_sam(opt, ref, &str, &s[i], best[i], best[!i], 0, 1, &pes, rg_id);
-    s[i].sam = str.s;
+      for (int j = 0; j < n_to[i]; ++j) format_sam(opt, ref, str, &s[i], &regs[i].a[to[i][j]], best[!i], &regs[i], !j, &pes, rg_id);
+    } else format_sam(opt, ref, str, &s[i], best[i], best[!i], 0, 1, &pes, rg_id);
+    sam_out_end(&so, &s[i]);
   }
-  free(to[0]); free(to[1]);
+  for (i = 0; i < 2; ++i) if (to[i] != tobuf[i]) free(to[i]);
 }
 
 #define RAW_MAPQ(diff, a) ((int)(6.02 * (diff) / (a) + .499))
@@ -746,19 +782,19 @@ void bq_reg2sam_pe(const bq_opt_t *opt, const bq_ref_t *ref, uint64_t id, bq_rea
   for (i = 0; i < 2; ++i) set_sam(opt, ref, &s[i], &regs[i].a[z[i]]);
   if (g_prof > 0) { const double q3 = bq_now(); pthread_mutex_lock(&g_prof_mu); g_t_setsam += q3 - q2; pthread_mutex_unlock(&g_prof_mu); }
   for (i = 0; i < 2; ++i) {
-    bq_str_t str = {0, 0, 0};
+    sam_out_t so;
     bq_regv_t *r = &regs[i];
-    bq_str_reserve(&str, 2 * (size_t)s[i].l_seq0 + 400);  /* one allocation for the usual single-line record */
-    format_sam(opt, ref, &str, &s[i], r->a + z[i], regs[!i].a + z[!i], r, 1, &pes, rg_id);
+    bq_str_t *str = sam_out_begin(&so, &s[i]);
+    format_sam(opt, ref, str, &s[i], r->a + z[i], regs[!i].a + z[!i], r, 1, &pes, rg_id);
     if (r->n_pri < r->n) {
       bq_reg_t *p = &r->a[r->n_pri];
       if (p->score >= opt->T && p->secondary < 0) {
         p->flag |= 0x800;
         set_sam(opt, ref, &s[i], p);
-        format_sam(opt, ref, &str, &s[i], p, 0, r, 0, &pes, rg_id);
+        format_sam(opt, ref, str, &s[i], p, 0, r, 0, &pes, rg_id);
       }
     }
-    s[i].sam = str.s;
+    sam_out_end(&so, &s[i]);
   }
 }
 
@@ -803,8 +839,10 @@ void bq_read_clipping(bq_read_t *s, const uint8_t *adaptor, int l_adaptor, const
 typedef struct {
   const bq_opt_t *opt; const bq_ref_t *ref; bq_read_t *seqs; bq_regv_t *regs; bq_pestat_t pes; int64_t n_processed;
   const char *rg_id; int n_items, n_threads, pe, stage;
+  long next_item; /* work distribution (thr_main) */
   const bsq_reg *dev_regs; const int64_t *reg_off; const int64_t *task_of_read; /* first task of each read */
   const uint8_t *n_task_of_read;
+  bq_reg_t *reg_pool; const int64_t *pool_off; /* regions of read i: reg_pool[pool_off[i] .. pool_off[i + 1]) */
   bq_str_t *sam_slab;   /* per worker thread: SAM text of the reads it formatted */
   size_t *sam_off;      /* per read: offset of its text in its thread's slab */
   uint8_t *sam_thr;     /* per read: which thread's slab */
@@ -819,22 +857,24 @@ static void reg_from_dev(const bsq_reg *d, bq_reg_t *r) {
 static void work_item(work_t *w, long i, int tid) {
   if (w->stage == 1) { /* gather the regions of read i in the reference's order and merge them */
     bq_regv_t *rv = &w->regs[i];
-    rv->n = rv->m = rv->n_pri = 0; rv->a = 0;
-    {
-      size_t tot = 0;
-      for (int t = 0; t < w->n_task_of_read[i]; ++t) tot += (size_t)(w->reg_off[w->task_of_read[i] + t + 1] - w->reg_off[w->task_of_read[i] + t]);
-      if (tot) { rv->m = tot + 2; rv->a = malloc(rv->m * sizeof(bq_reg_t)); }  /* one allocation (+2: mate rescue may add hits) */
-    }
+    rv->n = rv->n_pri = 0;
+    /* the regions of read i live in a slice of the batch's pool: room for every device region of its tasks + 2
+     * (mate rescue may add hits; a push beyond that moves the vector to the heap, regv_push) */
+    rv->a = w->reg_pool + w->pool_off[i]; rv->m = (size_t)(w->pool_off[i + 1] - w->pool_off[i]); rv->pooled = 1;
     for (int t = 0; t < w->n_task_of_read[i]; ++t) {
       const int64_t task = w->task_of_read[i] + t;
       for (int64_t k = w->reg_off[task]; k < w->reg_off[task + 1]; ++k) { bq_reg_t r; reg_from_dev(&w->dev_regs[k], &r); regv_push(rv, &r); }
     }
     bq_merge_regions(w->opt, w->ref, w->seqs[i].seq, w->seqs[i].l_seq, rv);
   } else if (!w->pe) {
+    tl_sam_slab = &w->sam_slab[tid];
+    if (tl_sam_slab->m == 0) { tl_sam_slab->s = bq_big_alloc((size_t)(w->n_items / w->n_threads + 1) * (2 * (size_t)w->seqs[i].l_seq0 + 256), &tl_sam_slab->m); tl_sam_slab->s[0] = 0; }
     bq_mark_primary(w->opt, &w->regs[i], w->n_processed + i);
     for (size_t k = 0; k < w->regs[i].n; ++k) w->regs[i].a[k].flag = 0;
     bq_reg2sam_se(w->opt, w->ref, &w->seqs[i], &w->regs[i], w->rg_id);
   } else {
+    tl_sam_slab = &w->sam_slab[tid];
+    if (tl_sam_slab->m == 0) { tl_sam_slab->s = bq_big_alloc((size_t)(w->n_items / w->n_threads + 1) * 2 * (2 * (size_t)w->seqs[i << 1].l_seq0 + 256), &tl_sam_slab->m); tl_sam_slab->s[0] = 0; }
     const double p0 = g_prof > 0 ? bq_now() : 0;
     if (!(w->opt->flag & BQ_F_NO_RESCUE)) bq_matesw(w->opt, w->ref, w->pes, &w->seqs[i << 1], &w->regs[i << 1]);
     const double p1 = g_prof > 0 ? bq_now() : 0;
@@ -853,12 +893,13 @@ static void work_item(work_t *w, long i, int tid) {
   }
   if (w->stage == 2) { /* the regions of this item are done with: release them here, on the worker */
     const long lo = w->pe ? i << 1 : i, hi = w->pe ? (i << 1) + 2 : i + 1;
-    for (long r = lo; r < hi; ++r) { /* move the text into this thread's slab (allocated and freed by the same thread) */
+    tl_sam_slab = 0;
+    for (long r = lo; r < hi; ++r) { /* the text is already in this thread's slab (sam_out_end); a stray own string is moved there */
       bq_read_t *rd = &w->seqs[r];
+      if (rd->sam_in_slab) { w->sam_off[r] = rd->sam_off; w->sam_thr[r] = (uint8_t)tid; continue; }
       if (!rd->sam) continue;
       bq_str_t *sl = &w->sam_slab[tid];
       const size_t l = strlen(rd->sam);
-      if (sl->m == 0) bq_str_reserve(sl, (size_t)(w->n_items / w->n_threads + 1) * (w->pe ? 2 : 1) * (l + 64));
       w->sam_off[r] = sl->l; w->sam_thr[r] = (uint8_t)tid;
       bq_kputsn(sl, rd->sam, l + 1); /* with the terminating NUL */
       free(rd->sam);
@@ -866,24 +907,88 @@ static void work_item(work_t *w, long i, int tid) {
     }
     for (long r = lo; r < hi; ++r) {
       for (size_t k = 0; k < w->regs[r].n; ++k) if (w->regs[r].a[k].n_cigar > 0) free(w->regs[r].a[k].cigar);
-      free(w->regs[r].a);
+      if (!w->regs[r].pooled) free(w->regs[r].a);
       w->regs[r].a = 0; w->regs[r].n = 0;
     }
   }
 }
 
 typedef struct { work_t *w; int tid; } thr_t;
+/* Items are handed out in chunks of neighbouring reads: neighbours share cache lines in the per-read arrays (regs,
+ * seqs, sam_off), so a strided split makes every thread write into every other thread's lines.  Which thread
+ * formats a read does not show in the output (the text is found through sam_thr / sam_off). */
+#define BQ_WORK_CHUNK 64
 static void *thr_main(void *a) {
   thr_t *t = a;
-  for (long i = t->tid; i < t->w->n_items; i += t->w->n_threads) work_item(t->w, i, t->tid);
+  work_t *w = t->w;
+  for (;;) {
+    const long lo = __atomic_fetch_add(&w->next_item, BQ_WORK_CHUNK, __ATOMIC_RELAXED);
+    if (lo >= w->n_items) break;
+    const long hi = lo + BQ_WORK_CHUNK < w->n_items ? lo + BQ_WORK_CHUNK : w->n_items;
+    for (long i = lo; i < hi; ++i) work_item(w, i, t->tid);
+  }
   return 0;
 }
+/* Worker threads are created once and parked between calls: a batch runs two parallel sections (region merge, then
+ * pairing + SAM), and creating the threads for each of them costs milliseconds per thread where mmap / clone are slow
+ * (measured 4 ms per pthread_create in a micro-VM), i.e. more than the work itself for small batches. */
+static struct {
+  pthread_mutex_t user;            /* one parallel section at a time */
+  pthread_mutex_t mu; pthread_cond_t go, done;
+  pthread_t th[256]; thr_t arg[256];
+  int n, active, running; unsigned long gen; work_t *w; /* active: pool threads taking part in the current section */
+} g_tp = {PTHREAD_MUTEX_INITIALIZER, PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER, {0}, {{0, 0}}, 0, 0, 0, 0, 0};
+
+static void *pool_main(void *a) {
+  thr_t *t = a;
+  unsigned long seen = 0;
+  for (;;) {
+    pthread_mutex_lock(&g_tp.mu);
+    while (g_tp.gen == seen) pthread_cond_wait(&g_tp.go, &g_tp.mu);
+    seen = g_tp.gen;
+    t->w = g_tp.w;
+    const int take_part = t->tid <= g_tp.active; /* a section may use fewer threads than the pool holds */
+    pthread_mutex_unlock(&g_tp.mu);
+    if (!take_part) continue;
+    thr_main(t);
+    pthread_mutex_lock(&g_tp.mu);
+    if (--g_tp.running == 0) pthread_cond_signal(&g_tp.done);
+    pthread_mutex_unlock(&g_tp.mu);
+  }
+  return 0;
+}
+
 static void run_threads(work_t *w, int n_items) {
   w->n_items = n_items;
+  w->next_item = 0;
   int nt = w->n_threads < 1 ? 1 : w->n_threads;
   if (nt > 255) nt = 255;
   w->n_threads = nt;
   if (nt == 1) { for (long i = 0; i < n_items; ++i) work_item(w, i, 0); return; }
+  if (pthread_mutex_trylock(&g_tp.user) == 0) {
+    /* workers 1 .. nt-1 come from the pool (grown on demand), the caller is worker 0 */
+    pthread_mutex_lock(&g_tp.mu);
+    while (g_tp.n < nt - 1) {
+      g_tp.arg[g_tp.n].tid = g_tp.n + 1; g_tp.arg[g_tp.n].w = 0;
+      if (pthread_create(&g_tp.th[g_tp.n], 0, pool_main, &g_tp.arg[g_tp.n]) != 0) break;
+      pthread_detach(g_tp.th[g_tp.n]);
+      ++g_tp.n;
+    }
+    const int have = g_tp.n >= nt - 1;
+    if (have) { g_tp.w = w; g_tp.active = nt - 1; g_tp.running = nt - 1; ++g_tp.gen; pthread_cond_broadcast(&g_tp.go); }
+    pthread_mutex_unlock(&g_tp.mu);
+    if (have) {
+      thr_t me = {w, 0};
+      thr_main(&me);
+      pthread_mutex_lock(&g_tp.mu);
+      while (g_tp.running > 0) pthread_cond_wait(&g_tp.done, &g_tp.mu);
+      pthread_mutex_unlock(&g_tp.mu);
+      pthread_mutex_unlock(&g_tp.user);
+      return;
+    }
+    pthread_mutex_unlock(&g_tp.user);
+  }
+  /* pool busy (another caller inside a parallel section) or it could not be built: threads for this call only */
   pthread_t *th = malloc(sizeof(pthread_t) * (size_t)nt);
   thr_t *ta = malloc(sizeof(thr_t) * (size_t)nt);
   for (int t = 0; t < nt; ++t) { ta[t].w = w; ta[t].tid = t; pthread_create(&th[t], 0, thr_main, &ta[t]); }
@@ -1024,13 +1129,46 @@ bq_batch_t *bq_batch_gpu(const bq_opt_t *opt, bsq_aligner *al, int64_t n_process
   return b;
 }
 
+/* the region pool of the last batch is kept for the next one (its pages are already mapped) */
+static pthread_mutex_t g_pool_mu = PTHREAD_MUTEX_INITIALIZER;
+static bq_reg_t *g_pool;
+static size_t g_pool_cap;
+static bq_reg_t *pool_take(size_t n, size_t *cap) {
+  bq_reg_t *p = 0;
+  pthread_mutex_lock(&g_pool_mu);
+  if (g_pool && g_pool_cap >= n) { p = g_pool; *cap = g_pool_cap; g_pool = 0; g_pool_cap = 0; }
+  pthread_mutex_unlock(&g_pool_mu);
+  if (!p) { *cap = n + (n >> 3); p = malloc(*cap * sizeof(bq_reg_t)); }
+  return p;
+}
+static void pool_give(bq_reg_t *p, size_t cap) {
+  pthread_mutex_lock(&g_pool_mu);
+  if (!g_pool || g_pool_cap < cap) { bq_reg_t *old = g_pool; g_pool = p; g_pool_cap = cap; p = old; }
+  pthread_mutex_unlock(&g_pool_mu);
+  free(p);
+}
+
 void bq_batch_finish(const bq_opt_t *opt, const bq_ref_t *ref, bq_batch_t *b, const bq_pestat_t *pes0, const char *rg_id) {
   const int pe = (opt->flag & BQ_F_PE) != 0, n = b->n;
   work_t w;
   memset(&w, 0, sizeof w);
   w.opt = opt; w.ref = ref; w.seqs = b->seqs; w.n_processed = b->n_processed; w.rg_id = rg_id; w.n_threads = opt->n_threads; w.pe = pe;
-  w.regs = calloc((size_t)n + 1, sizeof(bq_regv_t));
+  size_t regs_cap_ = 0;
+  w.regs = bq_big_alloc(((size_t)n + 1) * sizeof(bq_regv_t), &regs_cap_);
+  memset(w.regs, 0, ((size_t)n + 1) * sizeof(bq_regv_t));
   w.dev_regs = b->dregs; w.reg_off = b->reg_off; w.task_of_read = b->task_of_read; w.n_task_of_read = b->n_task;
+  /* one pool for the host regions of the whole batch instead of one allocation per read (the per-read vectors were
+   * allocated by one worker and freed by another, which glibc's per-thread caches cannot serve) */
+  int64_t *pool_off = malloc(sizeof(int64_t) * (size_t)(n + 1));
+  pool_off[0] = 0;
+  for (int i = 0; i < n; ++i) {
+    int64_t tot = 2;
+    for (int t = 0; t < b->n_task[i]; ++t) tot += b->reg_off[b->task_of_read[i] + t + 1] - b->reg_off[b->task_of_read[i] + t];
+    pool_off[i + 1] = pool_off[i] + tot;
+  }
+  size_t pool_cap = 0;
+  w.reg_pool = pool_take((size_t)pool_off[n] + 1, &pool_cap);
+  w.pool_off = pool_off;
   w.stage = 1;
   double t0_ = getenv("BQ_TIMING") ? bq_now() : 0;
   run_threads(&w, n);
@@ -1061,7 +1199,9 @@ void bq_batch_finish(const bq_opt_t *opt, const bq_ref_t *ref, bq_batch_t *b, co
   if (t0_ > 0) fprintf(stderr, " pestat %.3f phase2 %.3f s\n", t1_ - tm_, bq_now() - t1_);
   if (g_prof > 0) fprintf(stderr, "[bq_prof] thread-seconds: matesw %.3f mark_primary %.3f reg2sam %.3f (pair %.3f set_sam %.3f format %.3f)\n",
                           g_t_mate, g_t_mark, g_t_sam, g_t_pair, g_t_setsam, g_t_fmt);
-  free(w.regs);
+  bq_big_free(w.regs);
+  pool_give(w.reg_pool, pool_cap);
+  free(pool_off);
   batch_free(b);
 }
 
