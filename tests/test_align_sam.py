@@ -54,8 +54,9 @@ def hard_set(tmp_path_factory):
     return fa, f1, f2
 
 
-def _sam(binary, args):
-    out = subprocess.run([binary, "align"] + args, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout
+def _sam(binary, args, env=None):
+    out = subprocess.run([binary, "align"] + args, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True,
+                         env=dict(os.environ, **env) if env else None).stdout
     return b"\n".join(ln for ln in out.split(b"\n") if not ln.startswith(b"@PG"))
 
 
@@ -68,6 +69,15 @@ def test_sam_identical_hostemu(hard_set, extra):
     fa, f1, f2 = hard_set
     args = ["-@", "4"] + extra + [fa, f1, f2]
     assert _sam(build_emu_bin(), args) == _sam(refprobe.REF_BIN, args)
+
+
+def test_sam_many_small_batches_hostemu(hard_set):
+    """Eleven batches instead of one (BQ_CHUNK_SIZE test hook): with the insert-size distribution given (-I) nothing in
+    the output depends on where batches end, so the text must still equal the reference's single-batch run.  Exercises
+    the buffers that are recycled from batch to batch (region pool, SAM slabs, read slabs) and the parked workers."""
+    fa, f1, f2 = hard_set
+    args = ["-@", "4", "-I", "450,40", fa, f1, f2]
+    assert _sam(build_emu_bin(), args, env={"BQ_CHUNK_SIZE": "20000"}) == _sam(refprobe.REF_BIN, args)
 
 
 def test_sam_identical_single_end_hostemu(hard_set):
@@ -89,7 +99,7 @@ def _interleave(f1, f2, out):
     return out
 
 
-@pytest.mark.parametrize("extra", [[], ["-K", "70000"], ["-I", "450,40"]], ids=["default", "small batches", "-I"])
+@pytest.mark.parametrize("extra", [[], ["-K", "70000"], ["-I", "450,40"]], ids=["default", "adaptor -K", "-I"])
 def test_sam_identical_smart_pairing_hostemu(hard_set, tmp_path, extra):
     """-p (MEM_F_SMARTPE, align.c:109-143): interleaved input, pairs by equal neighbouring names, the rest single-end."""
     fa, f1, f2 = hard_set
@@ -169,7 +179,7 @@ def repeat_set(tmp_path_factory):
     return fa, f1, f2
 
 
-@pytest.mark.parametrize("extra", [[], ["-a"], ["-K", "60000"]], ids=["default", "-a", "small batches"])
+@pytest.mark.parametrize("extra", [[], ["-a"], ["-K", "60000"]], ids=["default", "-a", "adaptor -K"])
 def test_sam_identical_repeats_hostemu(repeat_set, extra):
     fa, f1, f2 = repeat_set
     args = ["-@", "3"] + extra + [fa, f1, f2]
@@ -182,7 +192,7 @@ def test_sam_identical_repeats_hostemu(repeat_set, extra):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("extra", [[], ["-K", "60000"]], ids=["default", "small batches"])
+@pytest.mark.parametrize("extra", [[], ["-K", "60000"]], ids=["default", "adaptor -K"])
 def test_sam_identical_repeats_gpu(repeat_set, extra):
     fa, f1, f2 = repeat_set
     args = ["-@", "3"] + extra + [fa, f1, f2]
