@@ -25,9 +25,14 @@ def build_hostemu() -> str:
     src = os.path.join(ROOT, "tests", "hostemu", "hostemu.cpp")
     out = os.path.join(ROOT, "tests", "hostemu", "libbsq_hostemu.so")
     cs = os.path.join(ROOT, "biscuit_b200", "csrc")
-    deps = [src] + [os.path.join(cs, f) for f in os.listdir(cs) if f.endswith(".h")]
+    # the pileup half of the emulation is the oracle's restatement (test-only library: it may link the oracle)
+    orc = os.path.join(ROOT, "oracle", "bsq_oracle_pileup.c")
+    deps = [src, orc, os.path.join(ROOT, "oracle", "bsq_oracle.h"), os.path.join(ROOT, "include", "bsq.h")]
+    deps += [os.path.join(cs, f) for f in os.listdir(cs) if f.endswith(".h")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", out, src])
+        obj = os.path.join(ROOT, "tests", "hostemu", "bsq_oracle_pileup.o")
+        subprocess.check_call(["gcc", "-O2", "-g", "-std=gnu11", "-fPIC", "-c", "-o", obj, orc])
+        subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", out, src, obj, "-lm"])
     return out
 
 

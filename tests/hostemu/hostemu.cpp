@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <vector>
 #include "../../include/bsq.h"
 #include "../../biscuit_b200/csrc/bsq_task.h"
@@ -222,19 +223,102 @@ int bsq_host_alloc(void **p, size_t bytes) { *p = malloc(bytes ? bytes : 1); ret
 void bsq_host_free(void *p) { free(p); }
 }
 
-// Entry points that only exist on the GPU (index construction, pinned memory, staged execution, pileup):
+// Entry points that only exist on the GPU (index construction, pinned memory, staged execution):
 // the host emulation says so instead of pretending.
 extern "C" {
 int bsq_index_build(const uint8_t *, int64_t, int32_t, const int64_t *, const int32_t *, const int32_t *, int, bsq_index **) { return BSQ_ENODEV; }
 int bsq_index_sizes(const bsq_index *, uint64_t *, uint64_t *, uint64_t *, uint64_t *, int64_t *) { return BSQ_ENODEV; }
 int bsq_index_download(const bsq_index *, int, uint32_t *, uint64_t *) { return BSQ_ENODEV; }
-// pileup has no host emulation: the kernels are checked on the GPU box against oracle/bsq_oracle_pileup.c
-void bsq_plp_conf_default(bsq_plp_conf *c) { memset(c, 0, sizeof *c); }
-int bsq_plp_create(int, int, bsq_plp **) { return BSQ_ENODEV; }
-void bsq_plp_destroy(bsq_plp *) {}
-int bsq_plp_set_contig(bsq_plp *, const uint8_t *, int32_t) { return BSQ_ENODEV; }
-int bsq_plp_stage(bsq_plp *, const bsq_plp_reads *) { return BSQ_ENODEV; }
-int bsq_plp_run(bsq_plp *, const bsq_plp_conf *, int32_t, int32_t, int64_t *) { return BSQ_ENODEV; }
-int bsq_plp_fetch(bsq_plp *, bsq_plp_rec *) { return BSQ_ENODEV; }
-int bsq_plp_counters(const bsq_plp *, int64_t *, int) { return BSQ_ENODEV; }
+// Pileup: the device kernels have no per-task host form, so the emulation hands the staged reads to the oracle's
+// restatement (oracle/bsq_oracle_pileup.c, linked into this test-only library; same record layouts).  What that
+// checks on a machine without a GPU is everything around the kernels: BGZF/BAM/BAI/FASTA readers, chunking and the
+// carry-over of reads between chunks, VCF text, methylation averages (biscuit_b200/host/bq_pileup.c, bq_bam.c).
+// The kernels themselves are compared with the same oracle on the GPU box (tests/test_pileup.py).
+}  // extern "C"
+extern "C" {
+#include "../../oracle/bsq_oracle.h"
+}
+struct bsq_plp {
+  int n_bams = 1;
+  std::vector<uint8_t> ref;
+  // deep copy of the staged reads (bsq_plp_stage is a host->device copy: the caller may reuse its buffers)
+  int64_t n = 0;
+  std::vector<int32_t> pos, mpos, mate_rlen, l_qseq, nm, as, n_cigar;
+  std::vector<uint16_t> flag;
+  std::vector<uint8_t> mapq, sid, seq, qual;
+  std::vector<int8_t> bss_tag;
+  std::vector<int64_t> cigar_off, seq_off, qual_off;
+  std::vector<uint32_t> cigar;
+  std::vector<bsq_plp_rec> out;
+  int64_t n_out = 0, counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+extern "C" {
+void bsq_plp_conf_default(bsq_plp_conf *c) {
+  static_assert(sizeof(bsq_plp_conf) == sizeof(bsqo_plp_conf) && sizeof(bsq_plp_rec) == sizeof(bsqo_plp_rec) &&
+                sizeof(bsq_plp_reads) == sizeof(bsqo_plp_reads), "oracle and ABI layouts differ");
+  bsqo_plp_conf_default(reinterpret_cast<bsqo_plp_conf *>(c));
+}
+int bsq_plp_create(int, int n_bams, bsq_plp **out) {
+  if (!out || n_bams < 1) return BSQ_EINVAL;
+  *out = new bsq_plp();
+  (*out)->n_bams = n_bams;
+  return 0;
+}
+void bsq_plp_destroy(bsq_plp *p) { delete p; }
+int bsq_plp_set_contig(bsq_plp *p, const uint8_t *ref_nt4, int32_t ref_len) {
+  if (!p || !ref_nt4 || ref_len <= 0) return BSQ_EINVAL;
+  p->ref.assign(ref_nt4, ref_nt4 + ref_len);
+  return 0;
+}
+int bsq_plp_stage(bsq_plp *p, const bsq_plp_reads *r) {
+  if (!p || !r || r->n_reads < 0) return BSQ_EINVAL;
+  const int64_t n = r->n_reads;
+  int64_t cig = 0, sq = 0, ql = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    if (r->sid[i] >= p->n_bams || r->n_cigar[i] < 0) return BSQ_EINVAL;
+    cig = std::max(cig, r->cigar_off[i] + r->n_cigar[i]);
+    sq = std::max(sq, r->seq_off[i] + (r->l_qseq[i] + 1) / 2);
+    ql = std::max(ql, r->qual_off[i] + r->l_qseq[i]);
+  }
+  p->n = n;
+  p->pos.assign(r->pos, r->pos + n); p->mpos.assign(r->mpos, r->mpos + n); p->mate_rlen.assign(r->mate_rlen, r->mate_rlen + n);
+  p->l_qseq.assign(r->l_qseq, r->l_qseq + n); p->nm.assign(r->nm, r->nm + n); p->as.assign(r->as, r->as + n);
+  p->flag.assign(r->flag, r->flag + n); p->mapq.assign(r->mapq, r->mapq + n); p->bss_tag.assign(r->bss_tag, r->bss_tag + n);
+  p->sid.assign(r->sid, r->sid + n); p->n_cigar.assign(r->n_cigar, r->n_cigar + n);
+  p->cigar_off.assign(r->cigar_off, r->cigar_off + n); p->seq_off.assign(r->seq_off, r->seq_off + n); p->qual_off.assign(r->qual_off, r->qual_off + n);
+  p->cigar.assign(r->cigar, r->cigar + cig); p->seq.assign(r->seq, r->seq + sq); p->qual.assign(r->qual, r->qual + ql);
+  p->counters[0] = n;
+  return 0;
+}
+int bsq_plp_run(bsq_plp *p, const bsq_plp_conf *cf, int32_t beg, int32_t end, int64_t *n_loci) {
+  if (!p || !cf || !n_loci || p->ref.empty()) return BSQ_EINVAL;
+  const int32_t ref_len = (int32_t)p->ref.size();
+  if (end > ref_len) end = ref_len;  // the last base of a contig is never piled (as in the CUDA library)
+  if (beg < 1) beg = 1;
+  *n_loci = 0; p->n_out = 0;
+  if (end <= beg) return 0;
+  bsqo_plp_reads rd;
+  rd.n_reads = p->n; rd.pos = p->pos.data(); rd.mpos = p->mpos.data(); rd.mate_rlen = p->mate_rlen.data(); rd.l_qseq = p->l_qseq.data();
+  rd.nm = p->nm.data(); rd.as = p->as.data(); rd.flag = p->flag.data(); rd.mapq = p->mapq.data(); rd.bss_tag = p->bss_tag.data();
+  rd.sid = p->sid.data(); rd.n_cigar = p->n_cigar.data(); rd.cigar_off = p->cigar_off.data(); rd.cigar = p->cigar.data();
+  rd.seq_off = p->seq_off.data(); rd.seq = p->seq.data(); rd.qual_off = p->qual_off.data(); rd.qual = p->qual.data();
+  const int64_t cap = (int64_t)end - beg;
+  p->out.resize((size_t)cap * p->n_bams);
+  const int64_t n = bsqo_plp_region(reinterpret_cast<const bsqo_plp_conf *>(cf), p->ref.data(), ref_len, beg, end, &rd, p->n_bams,
+                                    reinterpret_cast<bsqo_plp_rec *>(p->out.data()), cap);
+  if (n < 0) return BSQ_EOVERFLOW;
+  p->n_out = n; *n_loci = n;
+  p->counters[1] = cap; p->counters[2] = n;
+  return 0;
+}
+int bsq_plp_fetch(bsq_plp *p, bsq_plp_rec *out) {
+  if (!p || !out) return BSQ_EINVAL;
+  memcpy(out, p->out.data(), (size_t)p->n_out * p->n_bams * sizeof(bsq_plp_rec));
+  return 0;
+}
+int bsq_plp_counters(const bsq_plp *p, int64_t *c, int n) {
+  if (!p || !c) return BSQ_EINVAL;
+  for (int i = 0; i < n && i < 8; ++i) c[i] = p->counters[i];
+  return 0;
+}
 }
