@@ -385,6 +385,20 @@ bq_swr_t bq_local_align(int qlen, uint8_t *query, int tlen, uint8_t *target, con
 
 /* ---------------- CIGAR + MD + NM/ZC/ZR (bis_bwa_gen_cigar2, bwa.c:290-428) ---------------- */
 
+/* forward bases [beg, end) of the 2-bit packed reference, four per table lookup (same values as PAC()) */
+static void pac_decode(const uint8_t *pac, int64_t beg, int64_t end, uint8_t *out) {
+  static uint32_t lut[256];
+  static int lut_ready;
+  if (!__atomic_load_n(&lut_ready, __ATOMIC_ACQUIRE)) { /* idempotent: racing threads write the same values */
+    for (int v = 0; v < 256; ++v) lut[v] = (uint32_t)(v >> 6 & 3) | (uint32_t)(v >> 4 & 3) << 8 | (uint32_t)(v >> 2 & 3) << 16 | (uint32_t)(v & 3) << 24;
+    __atomic_store_n(&lut_ready, 1, __ATOMIC_RELEASE);
+  }
+  int64_t k = beg;
+  for (; k < end && (k & 3); ++k) *out++ = PAC(pac, k);
+  for (; k + 4 <= end; k += 4, out += 4) { const uint32_t w = lut[pac[k >> 2]]; memcpy(out, &w, 4); } /* little endian: first base in the low byte */
+  for (; k < end; ++k) *out++ = PAC(pac, k);
+}
+
 uint32_t *bq_gen_cigar(const int8_t mat[25], int o_del, int e_del, int o_ins, int e_ins, int w_, int64_t l_pac, const uint8_t *pac,
                        int l_query, uint8_t *query, int64_t rb, int64_t re, int *score, int *n_cigar, int *NM, uint32_t *ZC, uint32_t *ZR,
                        int *bss_u, uint8_t parent) {
@@ -401,12 +415,12 @@ uint32_t *bq_gen_cigar(const int8_t mat[25], int o_del, int e_del, int o_ins, in
   int cigar_local = 0;
   if (re - rb <= (int64_t)sizeof rbuf && rb >= 0 && re <= l_pac << 1) { /* bq_get_seq without the allocation (bntseq.c:402-422) */
     rseq = rbuf; rlen = re - rb;
-    int64_t l = 0;
-    if (rb >= l_pac) {
+    if (rb >= l_pac) { /* reverse strand: forward bases (beg_f, end_f] read backwards and complemented */
       const int64_t beg_f = (l_pac << 1) - 1 - re, end_f = (l_pac << 1) - 1 - rb;
-      for (int64_t k = end_f; k > beg_f; --k) rseq[l++] = 3 - PAC(pac, k);
-    } else
-      for (int64_t k = rb; k < re; ++k) rseq[l++] = PAC(pac, k);
+      pac_decode(pac, beg_f + 1, end_f + 1, rseq);
+      for (int64_t a = 0, b = rlen - 1; a < b; ++a, --b) { const uint8_t t = rseq[a]; rseq[a] = 3 - rseq[b]; rseq[b] = 3 - t; }
+      if (rlen & 1) rseq[rlen >> 1] = 3 - rseq[rlen >> 1];
+    } else pac_decode(pac, rb, re, rseq);
   } else rseq = bq_get_seq(l_pac, pac, rb, re, &rlen);
   if (re - rb != rlen) { if (rseq != rbuf) free(rseq); return 0; }
   if (rb >= l_pac) { rev_bytes(l_query, query); rev_bytes((int)rlen, rseq); } /* left-align indels on the forward strand */
