@@ -157,6 +157,49 @@ static void to_read_slab(bq_fastq_t *f, bq_read_t *s, bq_str_t *slab, size_t off
   s->in_slab = 1;
 }
 
+/* The common record -- four lines, '@name[ comment]', bases, '+...', as many quality characters, all inside the read
+ * buffer -- goes from the buffer into the slab in one pass.  Anything else (multi-line records, FASTA, CR/LF, a
+ * record cut by the end of the buffer, the last record of a file without a newline) returns 0 with nothing
+ * consumed and takes the general kseq path (fq_read + to_read_slab); both produce the same bytes. */
+static int fq_fast_slab(bq_fastq_t *f, bq_read_t *s, bq_str_t *slab, size_t off[3]) {
+  static int off_switch = -1;
+  if (off_switch < 0) off_switch = getenv("BQ_FQ_SLOW") != 0; /* test hook: general path only */
+  if (off_switch || f->last_char != 0 || f->beg >= f->end) return 0;
+  const unsigned char *p = f->buf + f->beg, *e = f->buf + f->end;
+  if (p[0] != '@') return 0;
+  const unsigned char *nl1 = memchr(p, '\n', (size_t)(e - p));
+  if (!nl1) return 0;
+  const unsigned char *ne = p + 1;
+  while (ne < nl1 && !isspace(*ne)) ++ne;
+  const unsigned char *q = nl1 + 1;
+  if (q >= e || *q == '+' || *q == '>' || *q == '@' || *q == '\n') return 0;
+  const unsigned char *nl2 = memchr(q, '\n', (size_t)(e - q));
+  if (!nl2 || nl2[-1] == '\r') return 0;
+  const unsigned char *r = nl2 + 1;
+  if (r >= e || *r != '+') return 0;
+  const unsigned char *nl3 = memchr(r, '\n', (size_t)(e - r));
+  if (!nl3) return 0;
+  const unsigned char *u = nl3 + 1;
+  const size_t l_seq = (size_t)(nl2 - q);
+  if ((size_t)(e - u) <= l_seq || u[l_seq] != '\n' || memchr(u, '\n', l_seq) || u[l_seq - 1] == '\r') return 0;
+  size_t l_name = (size_t)(ne - (p + 1));
+  if (l_name > 2 && p[1 + l_name - 2] == '/' && isdigit(p[1 + l_name - 1])) l_name -= 2; /* trim_readno */
+  const uint8_t *t = nt4_table();
+  memset(s, 0, sizeof *s);
+  bq_str_reserve(slab, l_name + 1 + 2 * (l_seq + 1) + 16);
+  char *d = slab->s + slab->l;
+  off[0] = slab->l; memcpy(d, p + 1, l_name); d[l_name] = 0; d += l_name + 1;
+  off[1] = (size_t)(d - slab->s);
+  for (size_t i = 0; i < l_seq; ++i) d[i] = (char)t[q[i]];
+  d += l_seq + 1;
+  off[2] = (size_t)(d - slab->s); memcpy(d, u, l_seq); d[l_seq] = 0; d += l_seq + 1;
+  slab->l = (size_t)(d - slab->s);
+  s->l_seq = s->l_seq0 = (int)l_seq;
+  s->in_slab = 1;
+  f->beg = (int)(u + l_seq + 1 - f->buf);
+  return 1;
+}
+
 /* ---------------- recycled large buffers ---------------- */
 #include <malloc.h>
 #include <pthread.h>
@@ -206,20 +249,28 @@ bq_read_t *bq_read_batch(int chunk_size, int has_bc, int keep_comment, int *n_, 
   bq_str_t slab = {0, 0, 0};
   if (use_slab) { slab.s = bq_big_alloc((size_t)chunk_size * 2 + ((size_t)chunk_size >> 2) + 4096, &slab.m); slab.s[0] = 0; }
   size_t *offs = 0;
-  while (fq_read(f1) >= 0) {
-    if (f2 && fq_read(f2) < 0) { fprintf(stderr, "[W::bis_bseq_read] the 2nd file has fewer sequences.\n"); break; }
+  for (;;) {
     if (n + 2 > m) {
       m = m ? m << 1 : 256;
       seqs = realloc(seqs, (size_t)m * sizeof(bq_read_t));
       if (use_slab) offs = realloc(offs, (size_t)m * 3 * sizeof(size_t));
     }
-    trim_readno(&f1->name);
-    if (use_slab) to_read_slab(f1, &seqs[n], &slab, offs + 3 * (size_t)n); else to_read(f1, &seqs[n], has_bc, keep_comment);
+    /* the read of file 1, then (paired input) the read of file 2: fast path first, general path otherwise */
+    const int fast1 = use_slab && fq_fast_slab(f1, &seqs[n], &slab, offs + 3 * (size_t)n);
+    if (!fast1 && fq_read(f1) < 0) break;
+    const int fast2 = f2 && use_slab && fq_fast_slab(f2, &seqs[n + 1], &slab, offs + 3 * (size_t)(n + 1));
+    if (f2 && !fast2 && fq_read(f2) < 0) { fprintf(stderr, "[W::bis_bseq_read] the 2nd file has fewer sequences.\n"); break; }
+    if (!fast1) {
+      trim_readno(&f1->name);
+      if (use_slab) to_read_slab(f1, &seqs[n], &slab, offs + 3 * (size_t)n); else to_read(f1, &seqs[n], has_bc, keep_comment);
+    }
     seqs[n].id = n;
     size += seqs[n++].l_seq;
     if (f2) {
-      trim_readno(&f2->name);
-      if (use_slab) to_read_slab(f2, &seqs[n], &slab, offs + 3 * (size_t)n); else to_read(f2, &seqs[n], has_bc, keep_comment);
+      if (!fast2) {
+        trim_readno(&f2->name);
+        if (use_slab) to_read_slab(f2, &seqs[n], &slab, offs + 3 * (size_t)n); else to_read(f2, &seqs[n], has_bc, keep_comment);
+      }
       seqs[n].id = n;
       size += seqs[n++].l_seq;
     }

@@ -80,6 +80,39 @@ def test_sam_many_small_batches_hostemu(hard_set):
     assert _sam(build_emu_bin(), args, env={"BQ_CHUNK_SIZE": "20000"}) == _sam(refprobe.REF_BIN, args)
 
 
+def test_fastq_shapes_hostemu(hard_set, tmp_path):
+    """FASTQ records the fast path of the reader must leave to the general kseq path -- comments after the name,
+    CR/LF line ends, sequences and qualities folded over several lines, FASTA records without qualities, a last
+    record without a newline -- mixed with ordinary ones: same SAM as the reference, and the same with the fast path
+    switched off (BQ_FQ_SLOW)."""
+    fa, f1, f2 = hard_set
+    out = []
+    for k, fn in enumerate((f1, f2)):
+        lines = open(fn).read().split("\n")
+        recs = [lines[4 * i:4 * i + 4] for i in range(400)]
+        txt = []
+        for i, (nm, sq, pl, ql) in enumerate(recs):
+            if i % 7 == 1:
+                nm += " a comment"
+            if i % 11 == 2:
+                txt.append("\r\n".join((nm, sq, pl, ql)) + "\r\n")
+            elif i % 13 == 3:
+                txt.append("\n".join((nm, sq[:70], sq[70:], "+" + nm[1:], ql[:40], ql[40:])) + "\n")
+            elif i % 17 == 4:
+                txt.append(">" + nm[1:] + "\n" + sq + "\n")
+            else:
+                txt.append("\n".join((nm, sq, pl, ql)) + "\n")
+        body = "".join(txt)
+        o = str(tmp_path / f"odd{k}.fq")
+        open(o, "w").write(body[:-1])  # no newline after the last record
+        out.append(o)
+    args = ["-@", "2", fa] + out
+    mine = _sam(build_emu_bin(), args)
+    assert mine == _sam(refprobe.REF_BIN, args)
+    assert mine == _sam(build_emu_bin(), args, env={"BQ_FQ_SLOW": "1"})
+    assert mine.count(b"\n") > 800
+
+
 def test_sam_identical_single_end_hostemu(hard_set):
     fa, f1, _ = hard_set
     args = ["-@", "4", fa, f1]
