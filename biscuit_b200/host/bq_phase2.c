@@ -863,7 +863,7 @@ static void work_item(work_t *w, long i, int tid) {
     rv->a = w->reg_pool + w->pool_off[i]; rv->m = (size_t)(w->pool_off[i + 1] - w->pool_off[i]); rv->pooled = 1;
     for (int t = 0; t < w->n_task_of_read[i]; ++t) {
       const int64_t task = w->task_of_read[i] + t;
-      for (int64_t k = w->reg_off[task]; k < w->reg_off[task + 1]; ++k) { bq_reg_t r; reg_from_dev(&w->dev_regs[k], &r); regv_push(rv, &r); }
+      for (int64_t k = w->reg_off[task]; k < w->reg_off[task + 1]; ++k) reg_from_dev(&w->dev_regs[k], &rv->a[rv->n++]); /* the slice has room for all of them */
     }
     bq_merge_regions(w->opt, w->ref, w->seqs[i].seq, w->seqs[i].l_seq, rv);
   } else if (!w->pe) {
