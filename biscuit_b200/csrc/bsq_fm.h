@@ -10,7 +10,17 @@ struct bsq_block_t {
 
 BSQ_HD void bsq_load_block(const uint32_t *blocks, uint64_t blk, bsq_block_t &b) {
   BSQ_CTR(BSQ_CTR_BLOCKS, 1);
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(BSQ_LDG256)
+  // Experiment for the next round (not built by default, not yet measured): one 64-byte block as two 256-bit loads
+  // (LDG.E.256 on sm_100a) instead of four 128-bit ones.  k_seed2 slowed down by 20 % when two to four LSU
+  // instructions per step were added (profiles/README.md, r01 v7), so halving the block-fetch instructions may pay.
+  // Build: nvcc ... -DBSQ_LDG256 -o libbsq_ldg256.so; compare with tools/kbench.py libbsq.so,libbsq_ldg256.so.
+  const uint32_t *p = blocks + blk * 16;
+  asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(b.w[0]), "=r"(b.w[1]), "=r"(b.w[2]), "=r"(b.w[3]), "=r"(b.w[4]), "=r"(b.w[5]), "=r"(b.w[6]), "=r"(b.w[7]) : "l"(p));
+  asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(b.w[8]), "=r"(b.w[9]), "=r"(b.w[10]), "=r"(b.w[11]), "=r"(b.w[12]), "=r"(b.w[13]), "=r"(b.w[14]), "=r"(b.w[15]) : "l"(p + 8));
+#elif defined(__CUDA_ARCH__)
   const uint4 *p = reinterpret_cast<const uint4 *>(blocks) + blk * 4;
   uint4 a0 = __ldg(p), a1 = __ldg(p + 1), a2 = __ldg(p + 2), a3 = __ldg(p + 3);
   b.w[0] = a0.x; b.w[1] = a0.y; b.w[2] = a0.z; b.w[3] = a0.w;
