@@ -107,6 +107,7 @@ __device__ __forceinline__ unsigned long long plp_read_events(const DevReads &rd
   const uint32_t pos1 = (uint32_t)rd.pos[i] + 1;
   // quick reject: the read cannot touch [beg,end) -- only an optimisation, the per-base test below decides
   int bsstrand = rd.bss_tag[i];
+  const int lq = rd.l_qseq[i];
   // ---- pass A: strand inference + retention count (warp reductions over aligned bases) ----
   int nC2T = 0, nG2A = 0, nCC = 0, nGG = 0;
   uint32_t read_length = 0;
@@ -117,7 +118,7 @@ __device__ __forceinline__ unsigned long long plp_read_events(const DevReads &rd
       if (op == 0 || op == 7 || op == 8) {
         for (uint32_t j = lane; j < ol; j += 32) {
           const uint32_t p = rpos + j;
-          if (p < 1 || p > (uint32_t)ref_len) continue;
+          if (p < 1 || p > (uint32_t)ref_len || qpos + j >= (uint32_t)lq) continue;
           const int rb = ref[p - 1], qb = rd_base(seq, qpos + j);
           if (rb == 1 && qb == 1) nCC++;
           if (rb == 2 && qb == 2) nGG++;
@@ -126,7 +127,7 @@ __device__ __forceinline__ unsigned long long plp_read_events(const DevReads &rd
           if (rb == 2 && qb == 0) nG2A++;
         }
         rpos += ol; qpos += ol; read_length += ol;
-      } else if (op == 1 || op == 4 || op == 5) qpos += ol;
+      } else if (op == 1 || op == 4 || op == 5) qpos += ol;  // H advances qpos like the reference (pileup.c:822); bases past SEQ are guarded below
       else if (op == 2) { rpos += ol; read_length += ol; }
       else if (op == 3) read_length += ol;
     }
@@ -138,7 +139,6 @@ __device__ __forceinline__ unsigned long long plp_read_events(const DevReads &rd
   }
   // ---- read-level filters (pileup.c:713-729) ----
   if (rd.mapq[i] < cf.min_mapq) return 0;
-  const int lq = rd.l_qseq[i];
   if (lq < 0 || lq < cf.min_read_len) return 0;
   if (flag > 0) {
     if (cf.filter_secondary && (flag & 0x100)) return 0;
@@ -168,10 +168,11 @@ __device__ __forceinline__ unsigned long long plp_read_events(const DevReads &rd
         const uint32_t p = rpos + j;
         if (p < (uint32_t)beg || p >= (uint32_t)end) continue;
         if (dbl && p >= ov_lo && p <= ov_hi) continue;
-        const int rb = ref[p - 1], qb = rd_base(seq, qpos + j);
         int *lc = cnt + ((int64_t)(p - beg) * n_bams + sid) * PLP_NCNT;
         atomicAdd(lc + 10, 1);  // DP: every event
         ++ev;
+        if (qpos + j >= (uint32_t)lq) continue;  // past SEQ after a leading H: the reference's 3'-distance rule drops it from the counts
+        const int rb = ref[p - 1], qb = rd_base(seq, qpos + j);
         int meth, base;
         if (bsstrand) { meth = rb == 2 ? (qb == 0 ? M_CONV : qb == 2 ? M_RET : M_NA) : M_NA; base = qb == 0 ? B_R : qb; }
         else { meth = rb == 1 ? (qb == 3 ? M_CONV : qb == 1 ? M_RET : M_NA) : M_NA; base = qb == 3 ? B_Y : qb; }
@@ -182,7 +183,7 @@ __device__ __forceinline__ unsigned long long plp_read_events(const DevReads &rd
         atomicAdd(lc + 3 + base, 1);
       }
       rpos += ol; qpos += ol;
-    } else if (op == 1 || op == 4 || op == 5) qpos += ol;
+    } else if (op == 1 || op == 4 || op == 5) qpos += ol;  // H advances qpos like the reference (pileup.c:822); bases past SEQ are guarded below
     else if (op == 2) rpos += ol;
   }
   return ev;

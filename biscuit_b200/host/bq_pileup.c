@@ -721,8 +721,9 @@ int bq_main_pileup(int argc, char **argv) {
 
   bq_plp_fmt_t fcf;
   fcf.n_bams = nb; fcf.is_nome = conf.is_nome; fcf.n_threads = conf.n_threads; fcf.error = conf.error; fcf.contam = conf.contam;
-  fcf.prior0 = conf.prior0 = 1.0 - conf.prior1 - conf.prior2; fcf.prior1 = conf.prior1; fcf.prior2 = conf.prior2;
-  if (fcf.prior0 < 0 || fcf.prior1 < 0 || fcf.prior2 < 0) bq_fatal("[Error] genotype priors must be from 0 to 1.\n");
+  /* prior0 is the value set with the defaults (1 - 0.33333 - 0.33333): the reference derives it in pileup_conf_init
+   * (src/pileup.c:955), before -P / -Q are parsed, and never again -- kept, so that GL1/GQ agree when they are given */
+  fcf.prior0 = conf.prior0; fcf.prior1 = conf.prior1; fcf.prior2 = conf.prior2;
 
   /* chunk = a whole number of windows */
   /* about a million loci per chunk: small enough that decode, GPU and text overlap well and that the page-locked

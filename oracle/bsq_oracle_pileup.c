@@ -12,7 +12,16 @@
  *   fivenuc_context             src/bisc_utils.c:33-74
  * Per-window dispatch (pileup.c:1189-1199) is folded into one [beg,end) range: every read contributes
  * every one of its in-range bases exactly once either way.
- * parity unpinned: nothing here touches utils/stats.h; see bsq_oracle.h. */
+ * PINNED against the reference itself: oracle/_ref/biscuit_ref_src is the unmodified src/pileup.c + src/bisc_utils.c
+ * compiled over header stand-ins (oracle/ref_shim_src), and tests/test_pileup_ref.py compares VCF bodies byte for byte.
+ * Hard clips: the reference advances qpos on H (pileup.c:822-824, bisc_utils.c:108), so after a leading H it pairs
+ * reference positions with SEQ bases shifted by the clip length and indexes SEQ/QUAL past their ends for the last ones.
+ * Those out-of-range events can never reach the counts (d->rlen < d->qpos + min_dist_end_3p holds for every qpos >
+ * l_qseq, pileup.c:383) but they are counted in DP (pileup.c:572).  That behaviour is reproduced exactly, without the
+ * out-of-range memory reads.  The only undefined case left is strand inference / retention counting over such bases
+ * (reads without YD/ZS/XG tags, or -t given): there the out-of-range bases are skipped here, whereas the reference
+ * compares whatever bytes follow SEQ in the record.
+ * Nothing here touches utils/stats.h; see bsq_oracle.h. */
 #include <limits.h>
 #include <stdlib.h>
 #include <string.h>
@@ -63,13 +72,14 @@ int64_t bsqo_plp_region(const bsqo_plp_conf *cf, const uint8_t *ref, int32_t ref
         if (op == 0 || op == 7 || op == 8) {
           for (j = 0; j < ol; ++j) {
             if (rpos + j < 1 || rpos + j > (uint32_t)ref_len) continue;
+            if (qpos + j >= (uint32_t)rd->l_qseq[i]) continue;
             int rb = ref[rpos + j - 1], qb = read_base(rd, i, qpos + j);
             if (qual[qpos + j] < (uint32_t)cf->min_base_qual) continue;
             if (rb == 1 && qb == 3) nC2T++;
             if (rb == 2 && qb == 0) nG2A++;
           }
           rpos += ol; qpos += ol;
-        } else if (op == 1 || op == 4 || op == 5) qpos += ol;
+        } else if (op == 1 || op == 4 || op == 5) qpos += ol; /* H advances qpos like the reference; note at the top */
         else if (op == 2) rpos += ol;
         else { free(cnt); free(touched); return -2; } /* the reference abort()s on N/P */
       }
@@ -93,11 +103,12 @@ int64_t bsqo_plp_region(const bsqo_plp_conf *cf, const uint8_t *ref, int32_t ref
         if (op == 0 || op == 7 || op == 8) {
           for (j = 0; j < ol; ++j) {
             if (rpos + j < 1 || rpos + j > (uint32_t)ref_len) continue;
+            if (qpos + j >= (uint32_t)rd->l_qseq[i]) continue;
             int rb = ref[rpos + j - 1], qb = read_base(rd, i, qpos + j);
             if (bsstrand) { if (rb == 1 && qb == 1) c++; } else { if (rb == 2 && qb == 2) c++; }
           }
           rpos += ol; qpos += ol;
-        } else if (op == 1 || op == 4 || op == 5) qpos += ol;
+        } else if (op == 1 || op == 4 || op == 5) qpos += ol; /* H advances qpos like the reference; note at the top */
         else if (op == 2) rpos += ol;
         else { free(cnt); free(touched); return -2; }
       }
@@ -114,11 +125,12 @@ int64_t bsqo_plp_region(const bsqo_plp_conf *cf, const uint8_t *ref, int32_t ref
           for (j = 0; j < ol; ++j) {
             uint32_t p = rpos + j;
             if (p < (uint32_t)beg || p >= (uint32_t)end) continue;
-            int rb = ref[p - 1], qb = read_base(rd, i, qpos + j);
             if (cf->filter_doublecnt && (flag & 0x80) && p >= (rpos > rmpos ? rpos : rmpos) && p <= (rend < rmend ? rend : rmend)) continue;
             locus_cnt *lc = &cnt[(int64_t)(p - beg) * n_bams + sid];
             touched[p - beg] = 1;
             lc->dp++;
+            if (qpos + j >= (uint32_t)rd->l_qseq[i]) continue; /* past SEQ (leading H): an event for DP, never counted (rlen < qpos + 3') */
+            int rb = ref[p - 1], qb = read_base(rd, i, qpos + j);
             int meth, base;
             if (bsstrand) { /* BSC */
               meth = rb == 2 ? (qb == 0 ? M_CONV : qb == 2 ? M_RET : M_NA) : M_NA;
@@ -134,7 +146,7 @@ int64_t bsqo_plp_region(const bsqo_plp_conf *cf, const uint8_t *ref, int32_t ref
             lc->meth[meth]++; lc->base[base]++;
           }
           rpos += ol; qpos += ol;
-        } else if (op == 1 || op == 4 || op == 5) qpos += ol;
+        } else if (op == 1 || op == 4 || op == 5) qpos += ol; /* H advances qpos like the reference; note at the top */
         else if (op == 2) rpos += ol;
       }
     }

@@ -162,13 +162,29 @@ def test_sam_clean_1m_hostemu(ds_1m, tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("extra", [[], ["-b", "1"], ["-5", "4", "-3", "7", "-z", "15"]], ids=["default", "-b 1", "clip"])
+@pytest.mark.parametrize("extra", CASES, ids=[" ".join(c) or "default" for c in CASES])
 def test_sam_identical_gpu(hard_set, extra):
+    """The same ten option sets as the host-side suite, through the CUDA build."""
     if not os.path.exists(GPU_BIN):
         pytest.fail("biscuit_b200/host/biscuit not built: run __graft_entry__.build()")
     fa, f1, f2 = hard_set
     args = ["-@", "4"] + extra + [fa, f1, f2]
     assert _sam(GPU_BIN, args) == _sam(refprobe.REF_BIN, args)
+
+
+@pytest.mark.gpu
+def test_sam_identical_single_end_gpu(hard_set):
+    fa, f1, _ = hard_set
+    args = ["-@", "4", fa, f1]
+    assert _sam(GPU_BIN, args) == _sam(refprobe.REF_BIN, args)
+
+
+@pytest.mark.gpu
+def test_sam_many_small_batches_gpu(hard_set):
+    """Eleven batches through the CUDA build (device buffers, page-locked slots and SAM slabs recycled batch to batch)."""
+    fa, f1, f2 = hard_set
+    args = ["-@", "4", "-I", "450,40", fa, f1, f2]
+    assert _sam(GPU_BIN, args, env={"BQ_CHUNK_SIZE": "20000"}) == _sam(refprobe.REF_BIN, args)
 
 
 @pytest.mark.gpu
@@ -225,7 +241,7 @@ def test_sam_identical_repeats_hostemu(repeat_set, extra):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("extra", [[], ["-K", "60000"]], ids=["default", "adaptor -K"])
+@pytest.mark.parametrize("extra", [[], ["-a"], ["-K", "60000"]], ids=["default", "-a", "adaptor -K"])
 def test_sam_identical_repeats_gpu(repeat_set, extra):
     fa, f1, f2 = repeat_set
     args = ["-@", "3"] + extra + [fa, f1, f2]

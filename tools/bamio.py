@@ -185,6 +185,9 @@ def write_bam_from_soa(path: str, contigs, per_contig_reads, sid: int | None = N
                     tags += tag_a("YD", "fr"[b])
                 elif tag_style == "ZS":
                     tags += tag_z("ZS", "+-"[b] + "+")
+                elif tag_style == "none":  # no strand tag at all: the reader must infer (bisc_utils.c:163-205) ...
+                    if cigar[0][1] == 5:  # ... except after a leading H, where the reference's inference indexes past SEQ (undefined)
+                        tags += tag_a("YD", "fr"[b])
                 else:
                     tags += tag_z("XG", ("CT", "GA")[b])
             rec, end = encode_record(tid, int(rd["pos"][i]), int(rd["mapq"][i]), int(rd["flag"][i]), cigar, nt16[:lq].tolist(),

@@ -48,7 +48,7 @@ def make_reads(contig_nt4: np.ndarray, n_pairs: int, seed: int = 5, noise: bool 
                 elif u < 0.32:
                     r["bss"] = -1
                 elif u < 0.42:  # indel / clip CIGARs with the same query length
-                    k = int(rng.integers(0, 4))
+                    k = int(rng.integers(0, 6))
                     L = read_len
                     if k == 0:
                         r["cigar"] = [(5, 4), (L - 5, 0)]
@@ -56,8 +56,12 @@ def make_reads(contig_nt4: np.ndarray, n_pairs: int, seed: int = 5, noise: bool 
                         r["cigar"] = [(40, 0), (3, 1), (L - 43, 0)]
                     elif k == 2:
                         r["cigar"] = [(60, 0), (7, 2), (L - 70, 0), (10, 4)]
-                    else:
+                    elif k == 3:  # leading hard clip: the reference advances qpos over it (pileup.c:822-824)
                         r["cigar"] = [(10, 5), (L, 0)]
+                    elif k == 4:
+                        r["cigar"] = [(L, 0), (25, 5)]
+                    else:
+                        r["cigar"] = [(20, 5), (50, 0), (2, 2), (L - 50, 0)]
             rows.append(r)
     rows.sort(key=lambda r: r["pos"])
     n = len(rows)
