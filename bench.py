@@ -11,8 +11,12 @@ The reference index is synthetic (iid ACGT, --ref-mb megabases, GRCh38-like cont
 built on the GPU by bsq_index_build in the reference's own layout.
 
   value : reads/s, kernels only, inputs resident in HBM (CUDA-event/sync bracketed, max over ranks)
-  e2e   : reads/s through the C ABI with pinned HOST buffers: H2D of the reads + kernels + D2H of
-          the regions inside the timed region
+  e2e   : reads/s through the whole batch boundary (mem_process_seqs equivalent): host reads in, H2D, kernels,
+          D2H, host phase 2, SAM text out
+  parity_at_scale : the first --cpu-pairs pairs through both arms on the same 3.1 Gb index, SAM compared
+  index_check     : sampled suffix-order / LF-inversion checks of that index (half the ranks above 2^32)
+  pileup : the pileup leg (tools/bench_pileup.py): one chr1-sized contig per GPU at 30x, its own value / e2e /
+          roofline / cpu_baseline (the reference's pileup) / parity
   --impl reference : the UNMODIFIED reference (oracle/_ref, mem_process_seqs, all host threads) on a
           bounded sample of the same workload.  NB it runs the reference's WHOLE batch API (phase 1 +
           pairing + SAM text), i.e. more work per read than the GPU arm currently covers; stated in
@@ -169,8 +173,9 @@ def write_index_files(dx, prefix, pac, l_pac, names, offs, lens):
         fh.write(f"{l_pac} {len(names)} 0\n")
 
 
-def reference_run(prefix, reads, n_threads, steps, warmup):
-    """mem_process_seqs of the unmodified reference on `reads` (2P,150), timed per step."""
+def reference_run(prefix, reads, n_threads, steps, warmup, sam_cap=0):
+    """mem_process_seqs of the unmodified reference on `reads` (2P,150), timed per step.  With sam_cap > 0 the SAM text
+    of the last step is returned as well (for the parity check at bench scale)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import refprobe
     rp = refprobe.RefProbe(prefix)
@@ -178,54 +183,26 @@ def reference_run(prefix, reads, n_threads, steps, warmup):
     n = len(reads)
     lens = np.full(n, reads.shape[1], np.int32)
     times = []
+    buf = C.create_string_buffer(sam_cap) if sam_cap else None
+    tot = 0
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        rp.lib.refp_process_seqs(rp.h, C.c_int(n_threads), C.c_int64(0), C.c_int(n), reads.ctypes.data_as(C.c_void_p),
-                                 C.c_int(reads.shape[1]), lens.ctypes.data_as(C.c_void_p), None, None, C.c_int64(0))
+        tot = rp.lib.refp_process_seqs(rp.h, C.c_int(n_threads), C.c_int64(0), C.c_int(n), reads.ctypes.data_as(C.c_void_p),
+                                       C.c_int(reads.shape[1]), lens.ctypes.data_as(C.c_void_p), None, buf, C.c_int64(sam_cap))
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
     rp.close()
+    if sam_cap:
+        return times, (buf.raw[:tot] if tot < sam_cap else None)
     return times
 
 
-def plp_make_reads(nt4, n_pairs, seed):
-    """Vectorised coordinate-sorted alignments (150M CIGARs, YD/NM/AS/MC tags present) for the pileup path."""
-    import synth
-    out = []
-    chunk = 250_000
-    for c0 in range(0, n_pairs, chunk):
-        p = synth.simulate_pairs([("c", nt4)], min(chunk, n_pairs - c0), seed=seed + c0, qual="mixed")
-        _, pos, bsc, flen = p["truth"]
-        rc = lambda a: np.where(a[:, ::-1] < 4, 3 - a[:, ::-1], 4).astype(np.uint8)  # noqa: E731
-        left, right = pos.astype(np.int64), (pos + flen - 150).astype(np.int64)
-        b = bsc[:, None]
-        seq_a = np.where(b, rc(p["r1"]), p["r1"]); qual_a = np.where(b, p["q1"][:, ::-1], p["q1"])
-        seq_b = np.where(b, p["r2"], rc(p["r2"])); qual_b = np.where(b, p["q2"], p["q2"][:, ::-1])
-        pos_a = np.where(bsc, right, left); pos_b = np.where(bsc, left, right)
-        flag_a = np.where(bsc, 83, 99); flag_b = np.where(bsc, 163, 147)
-        out.append((np.concatenate([pos_a, pos_b]), np.concatenate([pos_b, pos_a]), np.concatenate([flag_a, flag_b]),
-                    np.concatenate([bsc, bsc]).astype(np.int8), np.concatenate([seq_a, seq_b]), np.concatenate([qual_a, qual_b])))
-    pos = np.concatenate([o[0] for o in out]); mpos = np.concatenate([o[1] for o in out]); flag = np.concatenate([o[2] for o in out])
-    bss = np.concatenate([o[3] for o in out]); seq = np.concatenate([o[4] for o in out]); qual = np.concatenate([o[5] for o in out])
-    order = np.argsort(pos, kind="stable")
-    pos, mpos, flag, bss, seq, qual = pos[order], mpos[order], flag[order], bss[order], seq[order], qual[order]
-    n = len(pos)
-    nt16 = np.array([1, 2, 4, 8, 15], np.uint8)[np.minimum(seq, 4)]
-    return dict(n_reads=n, pos=pos.astype(np.int32), mpos=mpos.astype(np.int32), mate_rlen=np.full(n, 150, np.int32),
-                l_qseq=np.full(n, 150, np.int32), nm=np.full(n, 1, np.int32), as_=np.full(n, 140, np.int32), flag=flag.astype(np.uint16),
-                mapq=np.full(n, 60, np.uint8), bss_tag=bss, sid=np.zeros(n, np.uint8), n_cigar=np.ones(n, np.int32),
-                cigar_off=np.arange(n, dtype=np.int64), cigar=np.full(n, (150 << 4), np.uint32),
-                seq=((nt16[:, 0::2] << 4) | nt16[:, 1::2]).astype(np.uint8).reshape(-1), seq_off=np.arange(n, dtype=np.int64) * 75,
-                qual=(qual.astype(np.int16) - 33).astype(np.uint8).reshape(-1), qual_off=np.arange(n, dtype=np.int64) * 150)
-
-
 def bench_pileup(args):
-    """`--path pileup`: loci/s of the methylation caller over a 30x synthetic WGBS contig."""
+    """`--path pileup`: the pileup leg alone (tools/bench_pileup.py), as its own JSON line."""
     import torch
     import torch.distributed as dist
-    from biscuit_b200 import capi, plp
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import bench_pileup as bp
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -233,163 +210,10 @@ def bench_pileup(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     peak, peak_src = load_peaks()
-    L = int(args.plp_mb * 1_000_000)
-    # one contig per rank (pileup shards by contig / window); weak scaling
-    rng = np.random.default_rng(7 + rank)
-    nt4 = rng.integers(0, 4, size=L, dtype=np.uint8)
-    n_pairs = int(L * args.plp_depth / 300)
-    t0 = time.time()
-    rd = plp_make_reads(nt4, n_pairs, 31 + 1000 * rank)
-    log(f"pileup rank {rank}: {rd['n_reads']} reads over {L / 1e6:.0f} Mb ({args.plp_depth}x) simulated in {time.time() - t0:.1f}s")
-    bsq = capi.load()
-    pl = plp.Pileup(bsq, 1, device=local_rank)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-    conf = pl.default_conf()
-    pl.set_contig(nt4)
-    pl.stage(rd)
-    n_loci = pl.run(conf, 1, L)
-    for _ in range(args.warmup):
-        pl.run(conf, 1, L)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    barrier()
-    t0 = time.perf_counter()
-    kus = np.zeros(2)
-    for _ in range(args.steps):
-        pl.run(conf, 1, L)
-        kus += pl.counters()[4:6]
-    barrier()
-    dt = time.perf_counter() - t0
-    c = pl.counters()
-    barrier()
-    t1 = time.perf_counter()
-    for _ in range(args.steps):
-        pl.stage(rd)
-        recs = pl.fetch(pl.run(conf, 1, L))
-    barrier()
-    dt_e2e = time.perf_counter() - t1
-    clocks = sampler.stop()  # sampled over both timed regions: the kernel-only one lasts a few tens of milliseconds
-    kus /= args.steps
-    # the one collective of the path: per-contig methylation statistics -> every rank (NCCL over NVLink)
-    reduce_ms = None
-    if world > 1:
-        cnt_all = np.zeros((world, 1, 6), np.int64)
-        beta_all = np.zeros((world, 1, 6))
-        cnt_all[rank], beta_all[rank] = plp.context_stats(recs[recs["pos"] <= 2_000_000], 1)
-        barrier()
-        t6 = time.perf_counter()
-        cnt_m, beta_m = plp.merge_stats(cnt_all, beta_all, device=f"cuda:{local_rank}")
-        barrier()
-        reduce_ms = 1000 * (time.perf_counter() - t6)
-        assert (cnt_m[rank] == cnt_all[rank]).all() and int((cnt_m.sum(axis=(1, 2)) > 0).sum()) == world
-        tt = torch.tensor([dt, dt_e2e], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt, dt_e2e = float(tt[0]), float(tt[1])
-    if rank != 0:
-        pl.close()
-        dist.barrier()
-        dist.destroy_process_group()
-        return 0
-    # --- the command line itself: coordinate-sorted BAM + FASTA in, VCF text out (BGZF inflate, BAM decode, GPU, text) ---
-    cli = None
-    try:
-        if world > 1:
-            raise RuntimeError("CLI leg runs at N=1 only")
-        if args.no_cli:
-            raise RuntimeError("skipped (--no-cli)")
-        import bamio
-        import tempfile
-        with tempfile.TemporaryDirectory() as d:
-            t3 = time.perf_counter()
-            with open(os.path.join(d, "ref.fa"), "w") as fh:
-                fh.write(">chrS\n")
-                txt = np.frombuffer(b"ACGT", np.uint8)[nt4].tobytes().decode()
-                fh.write("\n".join(txt[i:i + 100] for i in range(0, L, 100)) + "\n")
-            bamio.write_bam_fixed(os.path.join(d, "in.bam"), "chrS", L, rd)
-            bam_bytes = os.path.getsize(os.path.join(d, "in.bam"))
-            log(f"pileup: FASTA + BAM ({bam_bytes / 1e6:.0f} MB) written in {time.perf_counter() - t3:.1f}s")
-            exe = os.path.join(ROOT, "biscuit_b200", "host", "biscuit")
-            ncores = os.cpu_count() or 1
-            t4 = time.perf_counter()
-            subprocess.run([exe, "pileup", "-@", str(ncores), "-o", os.path.join(d, "out.vcf"), os.path.join(d, "ref.fa"),
-                            os.path.join(d, "in.bam")], check=True, env=dict(os.environ, BSQ_PLP_TIMING="1"))
-            dt_cli = time.perf_counter() - t4
-            vcf_bytes = os.path.getsize(os.path.join(d, "out.vcf"))
-            cli = {"value": (L - 1) / dt_cli, "unit": "loci/s", "seconds": dt_cli, "bam_bytes": bam_bytes, "vcf_bytes": vcf_bytes,
-                   "host_threads": ncores, "note": "biscuit pileup: process start, FASTA load, BGZF inflate + BAM decode, GPU, VCF text, file write"}
-            if not args.no_cpu_baseline:
-                import oracle_plp
-                sys.path.insert(0, os.path.join(ROOT, "tests"))
-                from test_pileup_cli import oracle_vcf
-                sub = min(L, 2_000_000)
-                keep = rd["pos"] < sub
-                rs = {k: (v[keep] if isinstance(v, np.ndarray) and len(v) == rd["n_reads"] else v) for k, v in rd.items()}
-                rs["n_reads"] = int(keep.sum())
-                t5 = time.perf_counter()
-                exp_txt = oracle_vcf(oracle_plp.region(conf, nt4, rs, 1, sub - 200), "chrS", 1)[0]
-                dt_oracle_cli = time.perf_counter() - t5
-                got_lines = []
-                with open(os.path.join(d, "out.vcf"), "rb") as fh:
-                    for line in fh:
-                        if line[:1] == b"#":
-                            continue
-                        if int(line.split(b"\t", 2)[1]) >= sub - 200:
-                            break
-                        got_lines.append(line)
-                cli["identical_to_oracle_text"] = b"".join(got_lines) == exp_txt
-                cli["oracle_loci_per_s"] = (sub - 200) / dt_oracle_cli
-    except Exception as e:  # noqa: BLE001
-        log("pileup CLI leg failed:", e)
-    h2d = sum(int(np.asarray(v).nbytes) for k, v in rd.items() if k != "n_reads")
-    # reads (packed SEQ, QUAL, record fields), reference, one flag per locus, one 88-byte record per emitted locus;
-    # the per-locus counters stay in shared memory
-    alg = rd["n_reads"] * (75 + 150 + 48) + (L - 1) * (1 + 4) + n_loci * 88
-    # dram__bytes_read.sum + dram__bytes_write.sum of k_plp_win from the committed ncu capture of this same command
-    # (profiles/ncu_summary_r01_v7.json: one 8 Mi-locus tile), scaled to the loci of one step; null for other workloads
-    plp_traffic = None
-    try:
-        if args.plp_mb == 20.0 and args.plp_depth == 30:
-            with open(os.path.join(ROOT, "profiles", "ncu_summary_r01_v7.json")) as fh:
-                plp_traffic = json.load(fh)["kernels"]["k_plp_win"]["dram_bytes_per_locus"] * (L - 1)
-    except Exception:  # noqa: BLE001
-        plp_traffic = None
-    cpu = None
-    if not args.no_cpu_baseline and world == 1:
-        import oracle_plp
-        sub = min(L, 2_000_000)
-        keep = rd["pos"] < sub
-        rs = {k: (v[keep] if isinstance(v, np.ndarray) and len(v) == rd["n_reads"] else v) for k, v in rd.items()}
-        rs["n_reads"] = int(keep.sum())
-        t2 = time.perf_counter()
-        exp = oracle_plp.region(conf, nt4, rs, 1, sub - 200)
-        dtc = time.perf_counter() - t2
-        got = recs[recs["pos"] < sub - 200]
-        ok = got.tobytes() == exp.tobytes()
-        cpu = {"value": (sub - 200) / dtc, "unit": "loci/s", "cores": 1, "kind": "port",
-               "sample": f"first {sub / 1e6:.0f} Mb through oracle/bsq_oracle_pileup.c (single thread); identical to GPU output: {ok}"}
-    line = {"metric": "wgbs_pileup_loci_per_s", "value": world * (L - 1) * args.steps / dt, "unit": "loci/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int32", "data": "synthetic",
-            "config": {"workload": f"pileup {args.plp_depth}x synthetic WGBS, coordinate-sorted decoded BAM records, {L / 1e6:.0f} Mb contig, "
-                                   "CpG/CHG/CHH extraction", "reads": int(rd["n_reads"]), "emitted_loci": int(n_loci),
-                       "l2": "inputs larger than L2 (reads + counters)"},
-            "clocks": clocks, "stats_reduce_ms": reduce_ms,
-            "e2e": {"value": world * (L - 1) * args.steps / dt_e2e, "unit": "loci/s", "h2d_bytes_per_step": h2d,
-                                      "d2h_bytes_per_step": int(n_loci) * 88,
-                                      "note": "C ABI with host buffers: stage (H2D) + kernels + fetch (D2H) per pass"},
-            "e2e_cli": cli,
-            "gpu_launches": 3 * args.steps * ((L + (8 << 20) - 1) // (8 << 20)),
-            "roofline": {"bound": "hbm", "kernel": "k_plp_win", "achieved": alg / (kus[0] * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": alg / (kus[0] * 1e-6) / 1e9 / peak, "traffic": plp_traffic, "peak_source": peak_src,
-                         "kernel_ms": kus[0] / 1000, "locus_kernels_ms": kus[1] / 1000, "events": int(c[3])},
-            "cpu_baseline": cpu}
-    emit(line)
-    pl.close()
+    rec = bp.run(args, log, torch, dist, rank, local_rank, world, peak, peak_src, ClockSampler)
+    if rank == 0:
+        rec["vs_baseline"] = None
+        emit(rec)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -404,7 +228,9 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--path", default="align", choices=["align", "pileup"])
-    ap.add_argument("--plp-mb", type=float, default=20.0)
+    ap.add_argument("--plp-mb", type=float, default=float(os.environ.get("BSQ_BENCH_PLP_MB", "248")), help="pileup: contig size per GPU (chr1-sized by default)")
+    ap.add_argument("--plp-sample-mb", type=float, default=8.0, help="pileup: size of the BAM sample for the command-line / reference legs")
+    ap.add_argument("--no-pileup", action="store_true", help="align line only (profiling runs)")
     ap.add_argument("--plp-depth", type=int, default=30)
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -414,6 +240,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=int(os.environ.get("BSQ_BENCH_PAIRS", "100000")))
     ap.add_argument("--cpu-pairs", type=int, default=int(os.environ.get("BSQ_BENCH_CPU_PAIRS", "10000")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-index-check", action="store_true")
     ap.add_argument("--no-cli", action="store_true", help="pileup: skip the command-line leg (profiling runs)")
     args = ap.parse_args()
     if args.path == "pileup":
@@ -447,6 +274,15 @@ def main():
     t_index = time.time() - t0
     log(f"rank {rank}: FM-indices built on GPU in {t_index:.1f}s (stats {dx.sizes()['stats'].tolist()})")
     workload = f"align 2x150bp synthetic bisulfite pairs vs {L / 1e6:.0f} Mb synthetic reference (GRCh38-sized = 3100 Mb)"
+    index_check = None
+    if rank == 0 and args.impl == "ours" and not args.no_index_check:
+        # nobody can run the reference's `biscuit index` at this size (hours): sampled suffix-order / LF-inversion
+        # checks of the index both arms are about to use, half of the ranks above 2^32 (tools/indexcheck.py)
+        import indexcheck
+        t0 = time.time()
+        index_check = indexcheck.check_index(dx, nt4, n_samples=2000, seed=5, totals=False)
+        index_check["seconds"] = time.time() - t0
+        log("index check:", index_check)
 
     if args.impl == "reference":
         import tempfile
@@ -580,7 +416,6 @@ def main():
         raise RuntimeError(f"bq_session_align_stream: {r}")
     barrier()
     dt_full = time.perf_counter() - t2
-    hostlib.bq_session_destroy(sess)
     if world > 1:
         t = torch.tensor([dt, dt_e2e, dt_full], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -657,17 +492,39 @@ def main():
                 "peak_source": peak_src, "kernel_ms": kern_us[dom] / 1000, "share_of_step": float(kern_us[dom] / max(kern_us[5], 1)),
                 "work_per_task": work, "by_kernel": by_kernel, "full_sa_resident": int(counters[1]) == 2 if work else None}
         cpu = None
+        parity = None
         if not args.no_cpu_baseline:
             try:
                 import tempfile
-                creads = reads[: 2 * args.cpu_pairs]
+                creads = np.ascontiguousarray(reads[: 2 * args.cpu_pairs])
+                cap = 700 * len(creads) + (1 << 20)
                 with tempfile.TemporaryDirectory() as d:
                     prefix = os.path.join(d, "ref.fa")
                     write_index_files(dx, prefix, pac, L, names, offs, lens)
-                    times = reference_run(prefix, creads, ncores, 1, 0)
+                    times, ref_sam = reference_run(prefix, creads, ncores, 1, 0, sam_cap=cap)
                 v = len(creads) / times[0]
                 cpu = {"value": v, "unit": "reads/s", "cores": ncores, "kind": "reference",
                        "sample": f"{len(creads) // 2} pairs, one mem_process_seqs call of oracle/_ref (phase 1 + pairing + SAM text)"}
+                # parity at the bench's own scale: the same batch through the product's mem_process_seqs equivalent
+                # (GPU phase 1 + host phase 2) on the same 3.1 Gb index; SAM text compared byte for byte
+                buf = C.create_string_buffer(cap)
+                clens = np.full(len(creads), creads.shape[1], np.int32)
+                tot = hostlib.bq_session_align(sess, C.c_int64(0), C.c_int(len(creads)), creads.ctypes.data_as(C.c_void_p), C.c_int(creads.shape[1]),
+                                               clens.ctypes.data_as(C.c_void_p), None, buf, C.c_int64(cap))
+                ours_sam = buf.raw[:tot] if 0 <= tot < cap else None
+                same = ours_sam is not None and ref_sam is not None and ours_sam == ref_sam
+                parity = {"identical": bool(same), "pairs": len(creads) // 2, "sam_bytes": int(tot),
+                          "what": "SAM text of bq_session_align (GPU phase 1 + host phase 2) vs mem_process_seqs of oracle/_ref, same batch, "
+                                  f"same {L / 1e6:.0f} Mb index"}
+                if not same and ours_sam is not None and ref_sam is not None:
+                    la, lb = ours_sam.split(b"\n"), ref_sam.split(b"\n")
+                    bad = [i for i, (x, y) in enumerate(zip(la, lb)) if x != y]
+                    parity["first_diff_line"] = bad[0] if bad else min(len(la), len(lb))
+                    parity["n_diff_lines"] = len(bad) + abs(len(la) - len(lb))
+                    log("PARITY FAILURE at bench scale; first differing records:")
+                    for i in bad[:3]:
+                        log("  ours:", la[i][:300]); log("  ref: ", lb[i][:300])
+                log("parity_at_scale:", parity)
             except Exception as e:  # noqa: BLE001
                 log("cpu baseline failed:", e)
                 cpu = {"value": None, "unit": "reads/s", "cores": ncores, "kind": "reference", "sample": f"failed: {e}"}
@@ -686,13 +543,33 @@ def main():
                 "clocks": clocks, "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                                           "sam_bytes_per_step": int(sam_bytes), "host_threads": ncores},
                 "e2e_phase1": {"value": e2e_phase1, "unit": "reads/s", "note": "C ABI with pinned host buffers: H2D + kernels + D2H of regions"},
-                "gpu_launches": 12 * args.steps, "roofline": roof, "cpu_baseline": cpu,
+                "gpu_launches": 12 * args.steps, "roofline": roof, "cpu_baseline": cpu, "parity_at_scale": parity, "index_check": index_check,
                 "kernel_us_per_step": dict(zip(stage_names, [float(x) for x in kern_us]))}
+    hostlib.bq_session_destroy(sess)
+    # ---- pileup leg (BASELINE.json configs[2] shape, one chr1-sized contig per GPU): every rank takes part ----
+    al.close()
+    dx.close()
+    del reads, seqs, reads_c, nt4, pac
+    rc = 0
+    if not args.no_pileup:
+        import bench_pileup as bp
+        if world > 1:
+            dist.barrier()
+        try:
+            rec = bp.run(args, log, torch, dist, rank, local_rank, world, peak, peak_src, ClockSampler)
+        except Exception as e:  # noqa: BLE001
+            log("pileup leg failed:", e)
+            rec = {"error": str(e)}
+        if rank == 0:
+            line["pileup"] = rec
+    if rank == 0:
         emit(line)
+        if line.get("parity_at_scale") and not line["parity_at_scale"]["identical"]:
+            rc = 3  # results differ from the reference: the numbers above are not to be trusted
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    return 0
+    return rc
 
 
 if __name__ == "__main__":

@@ -109,3 +109,28 @@ def test_index_properties_large(cuda):
         # the rank of text position 0 is the primary
         assert dx.sa_lookup(which, np.array([sz["primary"][which]], np.uint64))[0] == 0
     dx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("full_sa", ["0", "1"])
+def test_index_beyond_2p32(cuda, full_sa, monkeypatch):
+    """Doubled text longer than 2^32 symbols (L = 2.2 Gb, the regime of the GRCh38-sized bench index: ranks, `primary`
+    corrections and SA entries that no longer fit 32 bits).  Sampled ranks, half of them above 2^32: suffix order of
+    consecutive ranks, SA[LF(k)] = SA[k] - 1 with LF from occ4 + L2 (bwt_invPsi, lib/aln/bwt.c:54-60), symbol totals.
+    full_sa=0 answers bsq_sa_lookup by the LF walk over the sampled SA (bwt_sa, bwt.c:87-97), full_sa=1 from the
+    builder's full suffix array."""
+    import indexcheck
+    L = 2_200_000_000
+    rng = np.random.default_rng(13)
+    nt4 = rng.integers(0, 4, size=L, dtype=np.uint8)
+    n_contigs = 12
+    base = L // n_contigs
+    lens = np.full(n_contigs, base, np.int32)
+    lens[-1] = L - base * (n_contigs - 1)
+    offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
+    pac = pack.pack_pac(nt4)
+    monkeypatch.setenv("BSQ_FULL_SA", full_sa)
+    dx = cuda.build_index(pac, L, [f"c{i}" for i in range(n_contigs)], offs, lens)
+    r = indexcheck.check_index(dx, nt4, n_samples=3000, seed=3, totals=(full_sa == "0"))
+    assert r["ranks_above_2p32"] >= 2000 and r["lf_checked"] >= 5000 and r["order_pairs"] >= 700
+    dx.close()
