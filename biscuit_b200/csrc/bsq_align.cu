@@ -163,7 +163,7 @@ struct bsq_seed_scratch_dev {
 };
 
 #ifndef BSQ_SEED_CAP
-#define BSQ_SEED_CAP 16  // shared-memory candidates per lane: 32 KB per 128-thread CTA
+#define BSQ_SEED_CAP 8   // shared-memory candidates per lane (16 KB per 128-thread CTA); 16 measured 7 % slower: the smaller slice leaves more of the SM's 256 KB to L1, which the FM-index gathers use (profiles/README.md, r02)
 #endif
 #ifndef BSQ_SEED_CTAS
 #define BSQ_SEED_CTAS 5   // resident CTAs per SM (registers: 96 per thread)
@@ -297,6 +297,12 @@ __global__ void __launch_bounds__(128) k_chain(const __grid_constant__ bsq_devop
   fb_flag[t] = 2;
 }
 
+static inline int bsq_sm_count() {  // SMs of the current device (148 on a B200)
+  static int n_sm = 0;
+  if (!n_sm) { int dev = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm < 1) n_sm = 148; }
+  return n_sm;
+}
+
 // warp policy of bsq_chain_warp
 struct bsq_cw_warp {
   __device__ static int lane() { return threadIdx.x & 31; }
@@ -305,10 +311,63 @@ struct bsq_cw_warp {
   __device__ static int first_true(bool p) { unsigned b = __ballot_sync(0xffffffffu, p); return b ? __ffs(b) - 1 : -1; }
   __device__ static bool any(bool p) { return __any_sync(0xffffffffu, p); }
   __device__ static int sum(int v) { return __reduce_add_sync(0xffffffffu, v); }
-  // bitonic sort of n <= BSQ_CW_CAP keys in shared memory (keys are unique, so the result is the total order)
+  __device__ static int min(int v) { return __reduce_min_sync(0xffffffffu, v); }
+  __device__ static int scan_excl(int v, int &total) {  // exclusive prefix sum over the lanes (small non-negative values)
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((threadIdx.x & 31) >= o) incl += u;
+    }
+    total = __shfl_sync(0xffffffffu, incl, 31);
+    return incl - v;
+  }
+  // bitonic sort of n keys (unique, so the result is the total order).  Up to 256 keys are sorted in registers: key i
+  // sits in register i / 32 of lane i % 32, partners at distance >= 32 are registers of the same lane, partners at
+  // distance < 32 come by shuffle -- no shared-memory round trip and no barrier per stage.  Larger tasks (the 1024-seed
+  // tier) sort in shared memory.
+  template <int R>
+  __device__ static void sort_regs(uint64_t *k, int n) {
+    const int lane = threadIdx.x & 31;
+    uint64_t v[R];
+#pragma unroll
+    for (int m = 0; m < R; ++m) { const int i = m * 32 + lane; v[m] = i < n ? k[i] : ~0ull; }
+#pragma unroll
+    for (int kk = 2; kk <= 32 * R; kk <<= 1) {
+#pragma unroll
+      for (int j = kk >> 1; j > 0; j >>= 1) {
+        if (j >= 32) {
+#pragma unroll
+          for (int m = 0; m < R; ++m) {
+            const int x = m ^ (j >> 5);
+            if (x > m) {
+              const bool up = ((m * 32) & kk) == 0;
+              const uint64_t a = v[m], b = v[x];
+              if ((a > b) == up) { v[m] = b; v[x] = a; }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int m = 0; m < R; ++m) {
+            const uint64_t o = __shfl_xor_sync(0xffffffffu, v[m], j);
+            const bool up = ((m * 32 + lane) & kk) == 0, lower = (lane & j) == 0;
+            v[m] = (up == lower) ? (v[m] < o ? v[m] : o) : (v[m] > o ? v[m] : o);
+          }
+        }
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < R; ++m) { const int i = m * 32 + lane; if (i < n) k[i] = v[m]; }
+    __syncwarp();
+  }
   __device__ static void sort_keys(uint64_t *k, int n) {
     const int lane = threadIdx.x & 31;
-    int P = 32;
+    if (n <= 32) { sort_regs<1>(k, n); return; }
+    if (n <= 64) { sort_regs<2>(k, n); return; }
+    if (n <= 128) { sort_regs<4>(k, n); return; }
+    if (n <= 256) { sort_regs<8>(k, n); return; }
+    int P = 512;
     while (P < n) P <<= 1;
     for (int i = n + lane; i < P; i += 32) k[i] = ~0ull;
     __syncwarp();
@@ -358,21 +417,29 @@ __global__ void __launch_bounds__(32 * WPB) k_chain_warp(const __grid_constant__
                                                     const uint8_t *parent, const bsq_pk_t *intv, const int32_t *n_intv,
                                                     const int32_t *n_sa, const int64_t *sa_off, const uint64_t *pos, bsq_chain_t *ochains,
                                                     bsq_seed_t *oseeds, int32_t *n_chains, float *frac_rep, uint8_t *fb_flag,
-                                                    unsigned long long *n_fallback) {
+                                                    unsigned long long *n_fallback, unsigned long long *cursor) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   typedef bsq_cw_smem_tt<CAP> S;
-  const int64_t wi = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (wi >= (int64_t)*tier_cnt) return;  // whole warps leave together
-  const int64_t t = tier_list[wi];
-  const int ns = n_sa[t];
   S *sm = reinterpret_cast<S *>(smem_raw) + (threadIdx.x >> 5);
-  const int64_t wo = ws_off(sa_off, t);
-  bsq_chain_result_t r;
-  const int rc = bsq_chain_warp<bsq_cw_warp>(opt, ix, parent[t], lens[t], intv + t * BSQ_MAX_INTV, n_intv[t], pos + sa_off[t], ns, *sm,
-                                             ochains + wo, oseeds + wo, r);
-  if ((threadIdx.x & 31) == 0) {
-    if (rc == BSQ_CW_OK) { n_chains[t] = r.n_chains; frac_rep[t] = r.frac_rep; fb_flag[t] = 0; }
-    else { fb_flag[t] = 1; atomicAdd(n_fallback, 1ull); }
+  const int64_t n_tier = (int64_t)*tier_cnt;
+  // persistent warps: the grid is one wave of resident CTAs and every warp pulls the next task of the tier when it is
+  // done (tasks differ by an order of magnitude in work; a CTA that waits for its slowest warp leaves slots idle)
+  for (;;) {
+    unsigned long long wi_ = 0;
+    if ((threadIdx.x & 31) == 0) wi_ = atomicAdd(cursor, 1ull);
+    const int64_t wi = (int64_t)__shfl_sync(0xffffffffu, wi_, 0);
+    if (wi >= n_tier) return;  // whole warps leave together
+    const int64_t t = tier_list[wi];
+    const int ns = n_sa[t];
+    const int64_t wo = ws_off(sa_off, t);
+    bsq_chain_result_t r;
+    const int rc = bsq_chain_warp<bsq_cw_warp>(opt, ix, parent[t], lens[t], intv + t * BSQ_MAX_INTV, n_intv[t], pos + sa_off[t], ns, *sm,
+                                               ochains + wo, oseeds + wo, r);
+    if ((threadIdx.x & 31) == 0) {
+      if (rc == BSQ_CW_OK) { n_chains[t] = r.n_chains; frac_rep[t] = r.frac_rep; fb_flag[t] = 0; }
+      else { fb_flag[t] = 1; atomicAdd(n_fallback, 1ull); }
+    }
+    __syncwarp();  // the next task reuses the warp's shared-memory slice
   }
 }
 
@@ -381,12 +448,17 @@ static int launch_chain_warp(cudaStream_t s, const bsq_devopt_t &opt, const bsq_
                              const unsigned long long *tier_cnt, const int32_t *lens,
                              const uint8_t *parent, const bsq_pk_t *intv, const int32_t *n_intv, const int32_t *n_sa, const int64_t *sa_off,
                              const uint64_t *pos, bsq_chain_t *ochains, bsq_seed_t *oseeds, int32_t *n_chains, float *frac_rep, uint8_t *fb_flag,
-                             unsigned long long *n_fallback) {
-  static bool attr_set = false;
+                             unsigned long long *n_fallback, unsigned long long *cursor) {
+  static int resident = 0;  // CTAs of this instantiation per SM
   const size_t smem = WPB * sizeof(bsq_cw_smem_tt<CAP>);
-  if (!attr_set) { CK(cudaFuncSetAttribute(k_chain_warp<CAP, WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
-  k_chain_warp<CAP, WPB><<<(unsigned)((n + WPB - 1) / WPB), 32 * WPB, smem, s>>>(opt, ix, n, tier_list, tier_cnt, lens, parent, intv, n_intv, n_sa, sa_off, pos, ochains,
-                                                                              oseeds, n_chains, frac_rep, fb_flag, n_fallback);
+  if (!resident) {
+    CK(cudaFuncSetAttribute(k_chain_warp<CAP, WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_chain_warp<CAP, WPB>, 32 * WPB, smem));
+    if (resident < 1) resident = 1;
+  }
+  const int64_t want = (n + WPB - 1) / WPB, wave = (int64_t)bsq_sm_count() * resident;
+  k_chain_warp<CAP, WPB><<<(unsigned)(want < wave ? want : wave), 32 * WPB, smem, s>>>(opt, ix, n, tier_list, tier_cnt, lens, parent, intv, n_intv, n_sa, sa_off, pos,
+                                                                                    ochains, oseeds, n_chains, frac_rep, fb_flag, n_fallback, cursor);
   CK(cudaGetLastError());
   return 0;
 }
@@ -399,14 +471,18 @@ static int launch_chain_warp(cudaStream_t s, const bsq_devopt_t &opt, const bsq_
 __global__ void __launch_bounds__(128, BSQ_REGION_CTAS) k_region(const __grid_constant__ bsq_devopt_t opt, const __grid_constant__ bsq_devidx_t ix, int64_t n_tasks, const uint8_t *seqs, int stride,
                                                 const int32_t *lens, const uint8_t *parent, const int64_t *sa_off,
                                                 const bsq_chain_t *ochains, const bsq_seed_t *oseeds, const int32_t *n_chains,
-                                                const float *frac_rep, uint64_t *srt, bsq_reg_t *regs_tmp, int32_t *n_regs) {
+                                                const float *frac_rep, uint64_t *srt, bsq_reg_t *regs_tmp, int32_t *n_regs, unsigned long long *cursor) {
   bsq_gap_tab_init(opt);
-  const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (t >= n_tasks) return;  // whole warps leave together
-  const int64_t wo = ws_off(sa_off, t);
-  const int n = bsq_chain2region<bsq_warp_policy>(opt, ix, parent[t], lens[t], seqs + t * stride, ochains + wo, n_chains[t], oseeds + wo,
-                                                  frac_rep[t], srt + wo, nullptr, regs_tmp + wo);
-  if ((threadIdx.x & 31) == 0) n_regs[t] = n;
+  for (;;) {  // persistent warps: one wave of resident CTAs, every warp pulls the next task (see k_chain_warp)
+    unsigned long long t_ = 0;
+    if ((threadIdx.x & 31) == 0) t_ = atomicAdd(cursor, 1ull);
+    const int64_t t = (int64_t)__shfl_sync(0xffffffffu, t_, 0);
+    if (t >= n_tasks) return;  // whole warps leave together
+    const int64_t wo = ws_off(sa_off, t);
+    const int n = bsq_chain2region<bsq_warp_policy>(opt, ix, parent[t], lens[t], seqs + t * stride, ochains + wo, n_chains[t], oseeds + wo,
+                                                    frac_rep[t], srt + wo, nullptr, regs_tmp + wo);
+    if ((threadIdx.x & 31) == 0) n_regs[t] = n;
+  }
 }
 
 __global__ void k_compact_regs(int64_t n_tasks, const int64_t *sa_off, const int32_t *n_regs, const int64_t *reg_off,
@@ -439,6 +515,7 @@ __global__ void __launch_bounds__(128) k_extend_warp(const __grid_constant__ bsq
 // ------------------------------------------------------------------------------------------
 
 static inline unsigned nblk(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
 
 // k_seed is persistent (lanes pull tasks from a counter): one wave of 148 SMs x 3 resident CTAs of 128
 // shared memory of k_seed: candidate lists + the converted reads (4 bits per base, as many words as the longest row needs)
@@ -705,11 +782,11 @@ static int phase1_device(bsq_aligner *al, int64_t n, int32_t stride, int64_t *to
   cudaStream_t s = al->stream;
   int rc;
 #define RES(buf, bytes) if ((rc = al->buf.reserve(bytes))) return rc
-  RES(intv, (size_t)n * BSQ_MAX_INTV * sizeof(bsq_pk_t)); RES(scalars, 128);
+  RES(intv, (size_t)n * BSQ_MAX_INTV * sizeof(bsq_pk_t)); RES(scalars, 256);
   RES(n_intv, n * 4); RES(n_sa, n * 4); RES(sa_off, (n + 1) * 8); RES(status, 4);
   RES(n_chains, n * 4); RES(frac_rep, n * 4); RES(n_regs, n * 4); RES(reg_off, (n + 1) * 8);
   CK(cudaMemsetAsync(al->status.p, 0, 4, s));
-  CK(cudaMemsetAsync(al->scalars.p, 0, 128, s));
+  CK(cudaMemsetAsync(al->scalars.p, 0, 256, s));
   SNAP(11);
   CK(cudaEventRecord(al->ev[0], s));
   if (seed_v1())
@@ -756,17 +833,19 @@ static int phase1_device(bsq_aligner *al, int64_t n, int32_t stride, int64_t *to
 #define CW_LAUNCH(CAP, WPB, Q, STREAM) if ((rc = launch_chain_warp<CAP, WPB>(STREAM, opt, ix, n, al->tiers.as<int32_t>() + (size_t)(Q) * n, tcnt + (Q), al->lens.as<int32_t>(), al->parent.as<uint8_t>(),  \
                 al->intv.as<bsq_pk_t>(), al->n_intv.as<int32_t>(), al->n_sa.as<int32_t>(), al->sa_off.as<int64_t>(), al->pos.as<uint64_t>(), \
                 al->ochains.as<bsq_chain_t>(), al->oseeds.as<bsq_seed_t>(), al->n_chains.as<int32_t>(), al->frac_rep.as<float>(),           \
-                al->fb_flag.as<uint8_t>(), al->scalars.as<unsigned long long>() + 1))) return rc
+                al->fb_flag.as<uint8_t>(), al->scalars.as<unsigned long long>() + 1, al->scalars.as<unsigned long long>() + 16 + (Q)))) return rc
     CK(cudaEventRecord(al->ev_fork, s));
     CK(cudaStreamWaitEvent(al->stream2, al->ev_fork, 0));
-    CW_LAUNCH(1024, 2, 6, al->stream2);  // the few large tasks run beside the small tiers: their long tail is hidden
-    CK(cudaEventRecord(al->ev_join, al->stream2));
+    // two streams: the kernels are persistent (one wave each), so the CTAs of one tier fill the SMs that the tail of
+    // another leaves idle; the few large tasks (1024-seed tier) start first
+    CW_LAUNCH(1024, 2, 6, al->stream2);
     CW_LAUNCH(256, 4, 5, s);
-    CW_LAUNCH(192, 4, 4, s);
+    CW_LAUNCH(192, 4, 4, al->stream2);
     CW_LAUNCH(160, 4, 3, s);
-    CW_LAUNCH(128, 4, 2, s);
+    CW_LAUNCH(128, 4, 2, al->stream2);
     CW_LAUNCH(96, 4, 1, s);
-    CW_LAUNCH(64, 4, 0, s);
+    CW_LAUNCH(64, 4, 0, al->stream2);
+    CK(cudaEventRecord(al->ev_join, al->stream2));
     CK(cudaStreamWaitEvent(s, al->ev_join, 0));
 #undef CW_LAUNCH
     CK(cudaEventRecord(al->ev[7], s));
@@ -795,10 +874,13 @@ static int phase1_device(bsq_aligner *al, int64_t n, int32_t stride, int64_t *to
     CK(cudaStreamSynchronize(s));
   }
   CK(cudaEventRecord(al->ev[4], s));
-  k_region<<<nblk(n * 32, 128), 128, 0, s>>>(opt, ix, n, al->seqs.as<uint8_t>(), stride, al->lens.as<int32_t>(), al->parent.as<uint8_t>(),
-                                         al->sa_off.as<int64_t>(), al->ochains.as<bsq_chain_t>(), al->oseeds.as<bsq_seed_t>(),
-                                         al->n_chains.as<int32_t>(), al->frac_rep.as<float>(), al->srt.as<uint64_t>(),
-                                         al->regs_tmp.as<bsq_reg_t>(), al->n_regs.as<int32_t>());
+  {
+    const unsigned want = nblk(n * 32, 128), wave = (unsigned)(bsq_sm_count() * BSQ_REGION_CTAS);
+    k_region<<<want < wave ? want : wave, 128, 0, s>>>(opt, ix, n, al->seqs.as<uint8_t>(), stride, al->lens.as<int32_t>(), al->parent.as<uint8_t>(),
+                                                       al->sa_off.as<int64_t>(), al->ochains.as<bsq_chain_t>(), al->oseeds.as<bsq_seed_t>(),
+                                                       al->n_chains.as<int32_t>(), al->frac_rep.as<float>(), al->srt.as<uint64_t>(),
+                                                       al->regs_tmp.as<bsq_reg_t>(), al->n_regs.as<int32_t>(), al->scalars.as<unsigned long long>() + 24);
+  }
   CK(cudaGetLastError());
   CK(cudaEventRecord(al->ev[5], s));
   if ((rc = scan_counts(al, al->n_regs.as<int32_t>(), al->reg_off.as<int64_t>(), n, total_regs))) return rc;

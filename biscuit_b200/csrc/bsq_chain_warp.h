@@ -14,8 +14,11 @@
 //  3. inside a cluster the reference's sequential rule is replayed in arrival order against a small sorted
 //     list of the cluster's chains (lane 0; the list is a handful of entries);
 //  4. weights, the introsort by weight (partitions: exact comparison sequence on lane 0; final insertion sort: a
-//     parallel stable sort) and the greedy overlap filter, whose
-//     inner loop over the kept chains is spread over the lanes (first "drop" position by ballot).
+//     parallel stable sort) and the greedy overlap filter, turned inside out: instead of walking every candidate over
+//     the kept chains (memchain.c:427-457), every newly kept chain sweeps all later candidates that are still alive,
+//     one candidate per lane.  A candidate meets the kept chains in the same order as in the reference and stops at the
+//     same one, so `first`, `kept` and the kept list come out identical, in (kept chains) x (candidates / 32) steps
+//     instead of (candidates) steps with mostly idle lanes.
 //
 // Exactness guard: the decomposition is only equivalent when (F1) no interval has more than max_occ occurrences
 // (otherwise the reference's `count` cap couples clusters, memchain.c:325-326), (F2) the task fits the
@@ -63,6 +66,8 @@ struct bsq_cw_scalar {
   BSQ_HD static int first_true(bool p) { return p ? 0 : -1; }
   BSQ_HD static bool any(bool p) { return p; }
   BSQ_HD static int sum(int v) { return v; }
+  BSQ_HD static int min(int v) { return v; }
+  BSQ_HD static int scan_excl(int v, int &total) { total = v; return 0; }  // exclusive prefix sum over the lanes
   BSQ_HD static void sort_keys(uint64_t *k, int n) {
     for (int i = 1; i < n; ++i) { uint64_t v = k[i]; int j = i; while (j > 0 && k[j - 1] > v) { k[j] = k[j - 1]; --j; } k[j] = v; }
   }
@@ -200,16 +205,21 @@ BSQ_HD int bsq_chain_warp(const bsq_devopt_t &opt, const bsq_devidx_t &ix, int p
   }
   if (W::any(dup)) return BSQ_CW_FALLBACK;
   W::sync();
-  if (lane == 0) {  // compaction (destination never passes the source)
-    int k = 0;
-    for (int u = 0; u < n_valid; ++u) {
-      const int nc = s.keep[u];
-      for (int c = 0; c < nc; ++c) s.clist[k++] = s.clist[u + c];
+  {  // compaction of the per-cluster chain lists into position order: prefix sums of keep[], copy through ord[]
+    int base = 0;
+    for (int u0 = 0; u0 < n_valid; u0 += NL) {
+      const int u = u0 + lane;
+      const int nc = u < n_valid ? s.keep[u] : 0;
+      int tot;
+      const int off = base + W::scan_excl(nc, tot);
+      for (int c = 0; c < nc; ++c) s.ord[off + c] = s.clist[u + c];
+      base += tot;
     }
-    s.pub[0] = k;
+    n_ch = base;
+    W::sync();
+    for (int c = lane; c < n_ch; c += NL) s.clist[c] = s.ord[c];
+    W::sync();
   }
-  W::sync();
-  n_ch = s.pub[0];
   // ---- 4a. weights (one chain per lane), then the order for the filter ----
   for (int c = lane; c < n_ch; c += NL) {
     const int a = s.clist[c];
@@ -227,17 +237,23 @@ BSQ_HD int bsq_chain_warp(const bsq_devopt_t &opt, const bsq_devidx_t &ix, int p
   // whatever the partition phase left": lane 0 replays only the partitions (exact comparison/swap sequence), all
   // lanes then sort (weight descending, slot after partitioning) keys, which are unique.
   uint32_t *k32 = reinterpret_cast<uint32_t *>(s.c_last_rbeg);  // free since step 3; s.key takes the 64-bit keys
-  if (lane == 0) {
-    int k = 0;
-    for (int c = 0; c < n_ch; ++c) {
-      const int a = s.clist[c];
-      if (s.c_w[a] >= opt.min_chain_weight) k32[k++] = (uint32_t)s.c_w[a] << 16 | (uint32_t)a;
+  {
+    int base = 0;
+    for (int c0 = 0; c0 < n_ch; c0 += NL) {
+      const int c = c0 + lane;
+      const int a = c < n_ch ? s.clist[c] : 0;
+      const int ok = c < n_ch && s.c_w[a] >= opt.min_chain_weight;
+      int tot;
+      const int off = base + W::scan_excl(ok, tot);
+      if (ok) k32[off] = (uint32_t)s.c_w[a] << 16 | (uint32_t)a;
+      base += tot;
     }
-    bsq_introsort<false>(k32, (int64_t)k, bsq_cw_by_weight());
-    s.pub[0] = k;
+    n_ch = base;
+    W::sync();
+    // (the whole range is partitioned once whatever its size, ksort.h:196-221: only sub-ranges of <= 16 are left alone)
+    if (lane == 0) bsq_introsort<false>(k32, (int64_t)n_ch, bsq_cw_by_weight());
+    W::sync();
   }
-  W::sync();
-  n_ch = s.pub[0];
   for (int c = lane; c < n_ch; c += NL) {
     const uint32_t v = k32[c];
     s.key[c] = (uint64_t)(0xffffu - (v >> 16)) << 32 | (uint64_t)c << 16 | (uint64_t)(v & 0xffffu);
@@ -249,71 +265,92 @@ BSQ_HD int bsq_chain_warp(const bsq_devopt_t &opt, const bsq_devidx_t &ix, int p
   if (lane == 0 && n_ch > 0) { s.c_kept[(uint16_t)(s.key[0] & 0xffffu)] = 3; s.keep[0] = 0; }
   W::sync();
   if (n_ch == 0) return BSQ_CW_OK;
-  // ---- 4b. greedy overlap filter (memchain.c:427-457); inner loop over the kept chains spread over the lanes ----
+  // ---- 4b. greedy overlap filter (memchain.c:427-457), one sweep per kept chain over the later candidates ----
+  // key[i] (free after the sort) = query begin | query end << 16 | weight << 32 | is_alt << 48 of candidate i;
+  // clist[i] (free after 4a) = bit 0: dropped, bit 1: has a significant overlap with a kept chain
+  for (int i = lane; i < n_ch; i += NL) {
+    const int c = s.ord[i];
+    const uint64_t beg = s.qbeg[c], end = (uint64_t)s.c_last_q[c] + s.c_last_len[c];
+    s.key[i] = beg | end << 16 | (uint64_t)(uint32_t)s.c_w[c] << 32 | (uint64_t)(s.c_alt[c] != 0) << 48;
+    s.clist[i] = 0;
+  }
+  W::sync();
   int n_keep = 1;
-  for (int i = 1; i < n_ch; ++i) {
-    const int ci = s.ord[i];
-    const int ci_beg = s.qbeg[ci], ci_end = s.c_last_q[ci] + s.c_last_len[ci], ci_w = s.c_w[ci];
-    const bool ci_alt = s.c_alt[ci] != 0;
-    bool large_overlap = false;
-    int K = n_keep;
-    for (int base = 0; base < n_keep && K == n_keep; base += NL) {
-      const int k = base + lane;
-      bool large = false, drop = false;
-      int ck = 0;
-      if (k < n_keep) {
-        ck = s.ord[s.keep[k]];
-        const int ck_beg = s.qbeg[ck], ck_end = s.c_last_q[ck] + s.c_last_len[ck];
-        const int b_max = ck_beg > ci_beg ? ck_beg : ci_beg, e_min = ck_end < ci_end ? ck_end : ci_end;
-        const bool ck_alt = s.c_alt[ck] != 0;
-        if (e_min > b_max && (!ck_alt || ci_alt)) {
-          const int li = ci_end - ci_beg, lj = ck_end - ck_beg, min_l = li < lj ? li : lj;
-          const float thr = (float)min_l * opt.mask_level;
-          if ((float)(e_min - b_max) >= thr && min_l < opt.max_chain_gap) {
-            large = true;
-            const float wk = (float)s.c_w[ck] * opt.drop_ratio;
-            drop = (float)ci_w < wk && s.c_w[ck] - ci_w >= (opt.min_seed_len << 1);
-          }
+  for (int cur = 0;;) {
+    const uint64_t kk = s.key[cur];
+    const int ck = s.ord[cur];
+    const int ck_beg = (int)(kk & 0xffff), ck_end = (int)(kk >> 16 & 0xffff), ck_w = (int)(kk >> 32 & 0xffff);
+    const bool ck_alt = (kk >> 48 & 1) != 0;
+    const float wk = (float)ck_w * opt.drop_ratio;
+    int first_i = 0x7fffffff, next = 0x7fffffff;
+    for (int i = cur + 1 + lane; i < n_ch; i += NL) {
+      int fl = s.clist[i];
+      if (fl & 1) continue;
+      const uint64_t ki = s.key[i];
+      const int ci_beg = (int)(ki & 0xffff), ci_end = (int)(ki >> 16 & 0xffff), ci_w = (int)(ki >> 32 & 0xffff);
+      const bool ci_alt = (ki >> 48 & 1) != 0;
+      const int b_max = ck_beg > ci_beg ? ck_beg : ci_beg, e_min = ck_end < ci_end ? ck_end : ci_end;
+      if (e_min > b_max && (!ck_alt || ci_alt)) {
+        const int li = ci_end - ci_beg, lj = ck_end - ck_beg, min_l = li < lj ? li : lj;
+        const float thr = (float)min_l * opt.mask_level;
+        if ((float)(e_min - b_max) >= thr && min_l < opt.max_chain_gap) {
+          fl |= 2;
+          first_i = first_i < i ? first_i : i;
+          if ((float)ci_w < wk && ck_w - ci_w >= (opt.min_seed_len << 1)) fl |= 1;
+          s.clist[i] = (uint16_t)fl;
         }
       }
-      const int fl = W::first_true(drop);
-      const int last = fl >= 0 ? base + fl : base + NL - 1;  // side effects up to and including the dropping chain
-      const bool eff = k < n_keep && k <= last && large;
-      if (eff && s.c_first[ck] < 0) s.c_first[ck] = (int16_t)i;
-      large_overlap = W::any(eff) || large_overlap;
-      if (fl >= 0) K = base + fl;
+      if (!(fl & 1)) next = next < i ? next : i;  // i ascends per lane: the first survivor of this lane
     }
+    first_i = W::min(first_i);
+    next = W::min(next);
+    W::sync();  // the flags written by the other lanes are visible to lane 0
+    if (lane == 0 && first_i != 0x7fffffff && s.c_first[ck] < 0) s.c_first[ck] = (int16_t)first_i;
+    if (next == 0x7fffffff) break;
+    // the smallest survivor has now met every chain kept before it: it is kept itself
+    if (lane == 0) { s.keep[n_keep] = (uint16_t)next; s.c_kept[s.ord[next]] = (s.clist[next] & 2) ? 2 : 3; }
+    ++n_keep;
+    cur = next;
     W::sync();
-    if (K == n_keep) {
-      if (lane == 0) { s.keep[n_keep] = (uint16_t)i; s.c_kept[ci] = large_overlap ? 2 : 3; }
-      ++n_keep;
+  }
+  W::sync();
+  // ---- 4c. kept = 1 for shadowed firsts, max_chain_extend (memchain.c:459-473), output slots ----
+  for (int i = lane; i < n_keep; i += NL) {
+    const int c = s.ord[s.keep[i]];
+    if (s.c_first[c] >= 0) s.c_kept[s.ord[s.c_first[c]]] = 1;  // several kept chains may shadow the same one: same value
+  }
+  W::sync();
+  {
+    int cnt = 0;
+    for (int i = lane; i < n_ch; i += NL) { const int kept = s.c_kept[s.ord[i]]; cnt += kept == 1 || kept == 2; }
+    if ((uint32_t)W::sum(cnt) >= (uint32_t)opt.max_chain_extend) {  // only with -X given: the reference's sequential rule
+      W::sync();
+      if (lane == 0) {
+        int i; uint32_t kk = 0;
+        for (i = 0; i < n_ch; ++i) {
+          const int kept = s.c_kept[s.ord[i]];
+          if (kept == 0 || kept == 3) continue;
+          if (++kk >= (uint32_t)opt.max_chain_extend) break;
+        }
+        for (; i < n_ch; ++i) if (s.c_kept[s.ord[i]] < 3) s.c_kept[s.ord[i]] = 0;
+      }
       W::sync();
     }
   }
-  // ---- 4c. kept = 1 for shadowed firsts, max_chain_extend, emit (lane 0) ----
-  if (lane == 0) {
-    for (int i = 0; i < n_keep; ++i) {
-      const int c = s.ord[s.keep[i]];
-      if (s.c_first[c] >= 0) s.c_kept[s.ord[s.c_first[c]]] = 1;
+  // output slots: keep[o] = chain, iv_off[o] = first seed slot of output chain o (prefix sums in filter order)
+  {
+    int n_out_ = 0, s_out_ = 0;
+    for (int i0 = 0; i0 < n_ch; i0 += NL) {
+      const int i = i0 + lane;
+      const int c = i < n_ch ? s.ord[i] : 0;
+      const int live = i < n_ch && s.c_kept[c] != 0;
+      const int ns = live ? s.c_n[c] + s.c_xn[c] : 0;
+      int t1, t2;
+      const int o1 = n_out_ + W::scan_excl(live, t1), o2 = s_out_ + W::scan_excl(ns, t2);
+      if (live) { s.keep[o1] = (uint16_t)c; s.iv_off[o1] = (uint16_t)o2; }
+      n_out_ += t1; s_out_ += t2;
     }
-    {
-      int i; uint32_t kk = 0;
-      for (i = 0; i < n_ch; ++i) {
-        const int kept = s.c_kept[s.ord[i]];
-        if (kept == 0 || kept == 3) continue;
-        if (++kk >= (uint32_t)opt.max_chain_extend) break;
-      }
-      for (; i < n_ch; ++i) if (s.c_kept[s.ord[i]] < 3) s.c_kept[s.ord[i]] = 0;
-    }
-    // output slots: keep[o] = chain, iv_off[o] = first seed slot of output chain o
-    int n_out = 0, s_out = 0;
-    for (int i = 0; i < n_ch; ++i) {
-      const int c = s.ord[i];
-      if (s.c_kept[c] == 0) continue;
-      s.keep[n_out] = (uint16_t)c; s.iv_off[n_out] = (uint16_t)s_out;
-      ++n_out; s_out += s.c_n[c] + s.c_xn[c];
-    }
-    s.pub[1] = n_out; s.pub[2] = s_out;
+    if (lane == 0) { s.pub[1] = n_out_; s.pub[2] = s_out_; }
   }
   W::sync();
   const int n_out = s.pub[1];
