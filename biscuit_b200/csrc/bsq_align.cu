@@ -297,6 +297,8 @@ __global__ void __launch_bounds__(128) k_chain(const __grid_constant__ bsq_devop
   fb_flag[t] = 2;
 }
 
+// per-device one-time set-up (function attributes are per device; one host thread drives one device)
+static inline int bsq_cur_device() { int dev = 0; cudaGetDevice(&dev); return dev < 0 || dev >= 64 ? 0 : dev; }
 static inline int bsq_sm_count() {  // SMs of the current device (148 on a B200)
   static int n_sm = 0;
   if (!n_sm) { int dev = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm < 1) n_sm = 148; }
@@ -449,12 +451,14 @@ static int launch_chain_warp(cudaStream_t s, const bsq_devopt_t &opt, const bsq_
                              const uint8_t *parent, const bsq_pk_t *intv, const int32_t *n_intv, const int32_t *n_sa, const int64_t *sa_off,
                              const uint64_t *pos, bsq_chain_t *ochains, bsq_seed_t *oseeds, int32_t *n_chains, float *frac_rep, uint8_t *fb_flag,
                              unsigned long long *n_fallback, unsigned long long *cursor) {
-  static int resident = 0;  // CTAs of this instantiation per SM
+  static int resident_[64];  // CTAs of this instantiation per SM, per device
+  int &resident = resident_[bsq_cur_device()];
   const size_t smem = WPB * sizeof(bsq_cw_smem_tt<CAP>);
   if (!resident) {
     CK(cudaFuncSetAttribute(k_chain_warp<CAP, WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_chain_warp<CAP, WPB>, 32 * WPB, smem));
-    if (resident < 1) resident = 1;
+    int r = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, k_chain_warp<CAP, WPB>, 32 * WPB, smem));
+    resident = r < 1 ? 1 : r;
   }
   const int64_t want = (n + WPB - 1) / WPB, wave = (int64_t)bsq_sm_count() * resident;
   k_chain_warp<CAP, WPB><<<(unsigned)(want < wave ? want : wave), 32 * WPB, smem, s>>>(opt, ix, n, tier_list, tier_cnt, lens, parent, intv, n_intv, n_sa, sa_off, pos,
@@ -535,7 +539,8 @@ static void launch_seed2(int variant, unsigned grid, cudaStream_t s, const bsq_d
 }
 static inline bool seed_v1() { static int v = -1; if (v < 0) { const char *e = getenv("BSQ_SEED_V1"); v = e && atoi(e) != 0; } return v != 0; }
 static inline unsigned seed_grid(int64_t n) {
-  static bool attr_set = false;
+  static bool attr_set_[64];
+  bool &attr_set = attr_set_[bsq_cur_device()];
   if (!attr_set) {
     cudaFuncSetAttribute(k_seed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seed_smem_bytes(BSQ_MAX_READ_LEN + 8));
     cudaFuncSetAttribute(k_seed2<BSQ_SEED_CAP, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seed_smem_bytes(BSQ_MAX_READ_LEN + 8));
@@ -897,7 +902,11 @@ static int phase1_device(bsq_aligner *al, int64_t n, int32_t stride, int64_t *to
   al->counters[14] = (int64_t)n_fb;  // tasks chained by the exact fallback kernel
   { float w_ms = 0; cudaEventElapsedTime(&w_ms, al->ev[3], al->ev[7]); al->counters[15] = (int64_t)(w_ms * 1000); }
 #undef RES
-  if (st) { snprintf(g_err, sizeof g_err, "device status 0x%x (1: interval list, 2: chain workspace, 4: fallback pool)", st); return BSQ_EOVERFLOW; }
+  // bit 0: a (read, conversion) task produced more than BSQ_MAX_INTV SMEM intervals.  That task is left without seeds
+  // (n_intv = 0, so the read may come out unaligned for that conversion) and the batch goes on; the caller reads
+  // counters[3] and warns -- one pathological read must not take the whole run down.  The other bits are real errors.
+  al->counters[3] = st & 1;
+  if (st & ~1) { snprintf(g_err, sizeof g_err, "device status 0x%x (2: chain workspace, 4: fallback pool)", st); return BSQ_EOVERFLOW; }
   float ms[6];
   for (int i = 0; i < 6; ++i) cudaEventElapsedTime(&ms[i], al->ev[i], al->ev[i + 1]);
   { float tot; cudaEventElapsedTime(&tot, al->ev[0], al->ev[6]); al->counters[10] = (int64_t)(tot * 1000); }

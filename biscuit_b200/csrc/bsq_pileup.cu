@@ -485,7 +485,9 @@ int bsq_plp_run(bsq_plp *p, const bsq_plp_conf *cf, int32_t beg, int32_t end, in
                                                     p->wr1.as<int64_t>());
       CKP(cudaGetLastError());
       const size_t smem = (size_t)W * nb * PLP_NCNT * sizeof(int);
-      static bool attr_set = false;
+      static bool attr_set_[64];  // per device
+      int dev_ = 0; cudaGetDevice(&dev_);
+      bool &attr_set = attr_set_[dev_ < 0 || dev_ >= 64 ? 0 : dev_];
       if (!attr_set) { CKP(cudaFuncSetAttribute(k_plp_win, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr_set = true; }
       k_plp_win<<<(unsigned)n_win, 256, smem, s>>>(p->dr, p->wr0.as<int64_t>(), p->wr1.as<int64_t>(), *cf, p->ref.as<uint8_t>(), p->ref_len, (int32_t)tb,
                                                     (int32_t)te, W, nb, p->flags.as<int32_t>(), p->dense.as<bsq_plp_rec>(),

@@ -209,7 +209,8 @@ void bq_batch_finish(const bq_opt_t *opt, const bq_ref_t *ref, bq_batch_t *b, co
  * sink receives the reads with .sam filled and frees them (n < 0: the batch failed, free only). */
 typedef bq_read_t *(*bq_source_fn)(void *ctx, int *n);
 typedef void (*bq_sink_fn)(void *ctx, bq_read_t *seqs, int n);
-int bq_pipeline_run(const bq_opt_t *opt, const bq_ref_t *ref, bsq_aligner *al, bsq_aligner *al2 /* optional second GPU context */,
+#define BQ_MAX_LANES 16 /* aligner contexts (GPUs) one pipeline can drive */
+int bq_pipeline_run(const bq_opt_t *opt, const bq_ref_t *ref, bsq_aligner *const *als, int n_al /* one lane per aligner context: batches round-robin */,
                     bq_source_fn src, void *src_ctx, bq_sink_fn sink, void *sink_ctx, const bq_pestat_t *pes0, const char *rg_id);
 
 /* bq_io.c */

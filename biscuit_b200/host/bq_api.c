@@ -119,6 +119,7 @@ int64_t bq_session_align_stream(bq_session *s, int n_batches, int n, const uint8
   stream_t st;
   memset(&st, 0, sizeof st);
   st.n_batches = n_batches; st.n = n; st.stride = stride; st.seqs = seqs; st.quals = quals; st.lens = lens;
-  const int rc = bq_pipeline_run(&s->opt, &s->ref, s->al, s->al2, stream_source, &st, stream_sink, &st, 0, "");
+  bsq_aligner *als[2] = {s->al, s->al2};
+  const int rc = bq_pipeline_run(&s->opt, &s->ref, als, s->al2 ? 2 : 1, stream_source, &st, stream_sink, &st, 0, "");
   return rc ? rc : st.sam_bytes;
 }

@@ -91,7 +91,7 @@ static double now(void) { struct timeval tv; gettimeofday(&tv, 0); return tv.tv_
 static int align_usage(void) {
   fprintf(stderr, "\nUsage: biscuit align [options] <fai-index base> <in1.fq> [in2.fq]\n\n"
                   "Options follow `biscuit align` of BISCUIT %s: -@ -b -f -k -w -d -r -y -c -D -W -m -S -P -e -9 -A -B -O -E -L -U\n"
-                  "    -1 -2 -i -R -H -j -q -T -g -a -C -V -Y -M -I -v -J -K -z -5 -3 -p, plus\n    -G INT   CUDA device [0]\n\n", BQ_VERSION);
+                  "    -1 -2 -i -R -H -j -q -T -g -a -C -V -Y -M -I -v -J -K -z -5 -3 -p, plus\n    -G LIST  CUDA device(s), e.g. 0, 0-7 or 0,2,5: FASTQ batches are dealt to them round-robin [0]\n\n", BQ_VERSION);
   return 1;
 }
 
@@ -145,7 +145,8 @@ int bq_main_align(int argc, char **argv) {
   bq_opt_init(&opt);
   opt.flag |= BQ_F_NO_MULTI; /* align.c:334 */
   memset(&set, 0, sizeof set);
-  int c, i, ignore_alt = 0, auto_alt = 1, copy_comment = 0, no_hdr = 0, device = 0, smart_pe = 0;
+  int c, i, ignore_alt = 0, auto_alt = 1, copy_comment = 0, no_hdr = 0, smart_pe = 0;
+  int devices[BQ_MAX_LANES] = {0}, n_dev = 1;
   char *p, *rg_line = 0, *hdr_line = 0, *seq1 = 0, *seq2 = 0, rg_id[256] = "";
   bq_pestat_t *pes0 = 0;
   const uint8_t *t4 = 0;
@@ -185,7 +186,17 @@ int bq_main_align(int argc, char **argv) {
     else if (c == 'W') opt.min_chain_weight = atoi(optarg);
     else if (c == 'y') opt.max_mem_intv = (uint64_t)atol(optarg);
     else if (c == 'C') copy_comment = 1;
-    else if (c == 'G') device = atoi(optarg); /* the reference's hidden -G (max_chain_gap) is not exposed; here: CUDA device */
+    else if (c == 'G') { /* the reference's hidden -G (max_chain_gap) is not exposed; here: CUDA device(s): "3", "0-7", "0,2,5" */
+      n_dev = 0;
+      for (p = optarg; *p && n_dev < BQ_MAX_LANES;) {
+        const int a = (int)strtol(p, &p, 10);
+        int b = a;
+        if (*p == '-') b = (int)strtol(p + 1, &p, 10);
+        for (int d = a; d <= b && n_dev < BQ_MAX_LANES; ++d) devices[n_dev++] = d;
+        if (*p == ',') ++p; else break;
+      }
+      if (n_dev < 1) { devices[0] = 0; n_dev = 1; }
+    }
     else if (c == 'J' || c == 'K') {
       int l = (int)strlen(optarg);
       uint8_t *a = calloc((size_t)l + 1, 1);
@@ -271,16 +282,22 @@ int bq_main_align(int argc, char **argv) {
   if (bq_index_load(argv[optind], &idx)) { fprintf(stderr, "[E::main_align] fail to locate the index files\n"); return 1; }
   if (auto_alt) infer_alt(&idx.ref);
   if (ignore_alt) for (i = 0; i < idx.ref.n_seqs; ++i) idx.ref.anns[i].is_alt = 0;
-  bsq_index *dx = 0;
-  int rc = bq_index_to_device(&idx, device, &dx);
-  if (rc) bq_fatal("cannot stage the index on CUDA device %d: %s (%s)", device, bsq_strerror(rc), bsq_last_error());
+  /* one index replica and one aligner context per device: FASTQ batches are dealt to the devices round-robin by the
+   * pipeline (bq_pipe.c), no data moves between GPUs */
+  bsq_index *dxs[BQ_MAX_LANES] = {0};
+  bsq_aligner *als[BQ_MAX_LANES] = {0};
   bsq_opt dopt;
   bq_opt_to_dev(&opt, &dopt);
-  bsq_aligner *al = 0;
-  if ((rc = bsq_aligner_create(dx, &dopt, &al))) bq_fatal("bsq_aligner_create: %s", bsq_strerror(rc));
-  bsq_aligner *al2 = 0; /* second GPU context of the batch pipeline (bq_pipe.c) */
-  if (!getenv("BQ_TWO_CONTEXTS") || bsq_aligner_create(dx, &dopt, &al2)) al2 = 0; /* off by default: measured no gain */
-  if (bq_verbose >= 3) fprintf(stderr, "[M::main_align] index loaded and staged on GPU %d in %.3f sec\n", device, now() - t0);
+  int rc = 0;
+  for (i = 0; i < n_dev; ++i) {
+    if ((rc = bq_index_to_device(&idx, devices[i], &dxs[i])))
+      bq_fatal("cannot stage the index on CUDA device %d: %s (%s)", devices[i], bsq_strerror(rc), bsq_last_error());
+    if ((rc = bsq_aligner_create(dxs[i], &dopt, &als[i]))) bq_fatal("bsq_aligner_create (device %d): %s", devices[i], bsq_strerror(rc));
+  }
+  bsq_aligner *al = als[0];
+  int n_al = n_dev;
+  if (n_dev == 1 && getenv("BQ_TWO_CONTEXTS") && !bsq_aligner_create(dxs[0], &dopt, &als[1])) n_al = 2; /* off by default: measured no gain */
+  if (bq_verbose >= 3) fprintf(stderr, "[M::main_align] index loaded and staged on %d GPU(s) in %.3f sec\n", n_dev, now() - t0);
 
   bq_fastq_t *f1 = 0, *f2 = 0;
   if (!seq1) {
@@ -313,12 +330,11 @@ int bq_main_align(int argc, char **argv) {
     src_ctx_t sc = {&opt, f1, f2, chunk, copy_comment};
     if (smart_pe) {
       if ((rc = align_smart_pairing(&opt, &idx.ref, al, &sc, pes0, rg_id))) bq_fatal("alignment batch failed: %s (%s)", bsq_strerror(rc), bsq_last_error());
-    } else if ((rc = bq_pipeline_run(&opt, &idx.ref, al, al2, fastq_source, &sc, sam_sink, 0, pes0, rg_id)))
+    } else if ((rc = bq_pipeline_run(&opt, &idx.ref, als, n_al, fastq_source, &sc, sam_sink, 0, pes0, rg_id)))
       bq_fatal("alignment batch failed: %s (%s)", bsq_strerror(rc), bsq_last_error());
   }
-  bsq_aligner_destroy(al);
-  if (al2) bsq_aligner_destroy(al2);
-  bsq_index_free(dx);
+  for (i = 0; i < BQ_MAX_LANES; ++i) if (als[i]) bsq_aligner_destroy(als[i]);
+  for (i = 0; i < BQ_MAX_LANES; ++i) if (dxs[i]) bsq_index_free(dxs[i]);
   bq_index_free(&idx);
   bq_fastq_close(f1); bq_fastq_close(f2);
   free(hdr_line); free(pes0); free(opt.adaptor1); free(opt.adaptor2);

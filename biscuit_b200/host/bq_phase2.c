@@ -1051,12 +1051,30 @@ bq_batch_t *bq_batch_prep(const bq_opt_t *opt, int64_t n_processed, int n, bq_re
   const int pe = (opt->flag & BQ_F_PE) != 0;
   int i, max_len = 1;
   if (rc_out) *rc_out = 0;
+  /* paired reads must carry the same name, or names that differ in a trailing 1 / 2 (check_paired_read_names,
+   * bwamem.c:210-216, called first thing in bis_worker1): desynchronised FASTQ files must not be paired silently */
+  if (pe)
+    for (i = 0; i + 1 < n; i += 2) {
+      const char *n1 = seqs[i].name, *n2 = seqs[i + 1].name;
+      if (strcmp(n1, n2) == 0) continue;
+      const size_t l = strlen(n1);
+      if (l > 0 && n1[l - 1] == '1' && strlen(n2) >= l && n2[l - 1] == '2' && strncmp(n1, n2, l - 1) == 0) continue;
+      bq_fatal("[check_paired_read_names] paired reads have different names: \"%s\", \"%s\"\n", n1, n2);
+    }
   /* clipping (bwamem.c:322,343-344) */
+  int n_long = 0;
+  const char *first_long = 0;
   for (i = 0; i < n; ++i) {
     const int second = pe && (i & 1);
     bq_read_clipping(&seqs[i], second ? opt->adaptor2 : opt->adaptor1, second ? opt->l_adaptor2 : opt->l_adaptor1, opt);
+    if (seqs[i].l_seq > BSQ_MAX_READ_LEN) { if (!n_long++) first_long = seqs[i].name; continue; }
     if (seqs[i].l_seq > max_len) max_len = seqs[i].l_seq;
   }
+  /* reads beyond the device kernels' length limit get no tasks: they come out as unaligned records (their mates are
+   * aligned as usual) instead of failing the batch -- and with it a run that may already have written output */
+  if (n_long)
+    fprintf(stderr, "[W::%s] %d read(s) longer than %d bases after clipping (first: %s) are reported unaligned: the GPU kernels take reads up to "
+            "that length\n", __func__, n_long, BSQ_MAX_READ_LEN, first_long);
   /* (read, conversion) tasks in the order bis_worker1 runs them (bwamem.c:325-372) */
   bq_batch_t *b = calloc(1, sizeof *b);
   b->n = n; b->n_processed = n_processed; b->seqs = seqs;
@@ -1067,6 +1085,7 @@ bq_batch_t *bq_batch_prep(const bq_opt_t *opt, int64_t n_processed, int n, bq_re
   for (i = 0; i < n; ++i) {
     b->task_of_read[i] = nt;
     int k0 = (int)nt;
+    if (seqs[i].l_seq > BSQ_MAX_READ_LEN) { b->n_task[i] = 0; continue; }
     if (!pe) {
       if (!(opt->parent & 1) || opt->parent >> 1) par[nt++] = 0;
       if (!(opt->parent & 1) || !(opt->parent >> 1)) par[nt++] = 1;
@@ -1104,6 +1123,12 @@ int bq_batch_run(bsq_aligner *al, bq_batch_t *b) {
   const double t2 = t0 > 0 ? bq_now() : 0;
   if ((rc = slot_reserve(&b->slot->regs, &b->slot->regs_cap, (size_t)(n_regs + 1) * sizeof(bsq_reg)))) return rc;
   if ((rc = bsq_aligner_fetch(al, b->slot->regs, b->reg_off))) return rc;
+  {
+    int64_t c[16];
+    if (bsq_aligner_counters(al, c, 16) == 0 && c[3])
+      fprintf(stderr, "[W::%s] reads %lld..%lld: a read with more than %d SMEM intervals was left unseeded for that conversion\n", __func__,
+              (long long)b->n_processed, (long long)(b->n_processed + b->n - 1), BSQ_MAX_INTV);
+  }
   if (t0 > 0) {
     int64_t c[16];
     bsq_aligner_counters(al, c, 16);

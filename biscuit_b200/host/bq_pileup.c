@@ -605,7 +605,18 @@ int bq_main_pileup(int argc, char **argv) {
   char *reg = 0, *tum = 0, *nor = 0, *outfn = 0, *statsfn = 0;
   plp_conf_t conf;
   conf_init(&conf);
+  /* Multi-GPU: one process per GPU, launched like any one-rank-per-GPU job (RANK / WORLD_SIZE / LOCAL_RANK in the
+   * environment, e.g. under torchrun; BSQ_RANK / BSQ_WORLD override).  Contigs (in name order) are dealt to the ranks
+   * round-robin, each rank piles up its own on its own device, and rank 0 merges: VCF bodies concatenated in contig-name
+   * order, per-contig methylation statistics added in rank order (every entry has a single contributor, so the sums
+   * equal a one-process run bit for bit).  The merge goes through files next to the output: KBs per rank. */
   int device = 0, rank = 0, world = 1;
+  if (getenv("WORLD_SIZE")) world = atoi(getenv("WORLD_SIZE"));
+  if (getenv("RANK")) rank = atoi(getenv("RANK"));
+  if (getenv("BSQ_WORLD")) world = atoi(getenv("BSQ_WORLD"));
+  if (getenv("BSQ_RANK")) rank = atoi(getenv("BSQ_RANK"));
+  if (world < 1 || rank < 0 || rank >= world) bq_fatal("[pileup] bad rank %d of %d\n", rank, world);
+  if (world > 1 && getenv("LOCAL_RANK")) device = atoi(getenv("LOCAL_RANK"));
   if (getenv("BSQ_DEVICE")) device = atoi(getenv("BSQ_DEVICE"));
   if (argc < 2) return usage(&conf);
   while ((c = getopt(argc, argv, ":o:w:g:@:5:3:b:s:E:M:x:C:P:Q:t:n:m:a:l:T:I:SNrcdupv:h")) >= 0) {
@@ -682,23 +693,28 @@ int bq_main_pileup(int argc, char **argv) {
   const double t_fa = now_s();
 
   FILE *out = stdout;
+  char *partfn = 0;
+  const char *run_id = getenv("TORCHELASTIC_RUN_ID") ? getenv("TORCHELASTIC_RUN_ID") : (getenv("MASTER_PORT") ? getenv("MASTER_PORT") : "0");
+  if (world > 1) {
+    if (!outfn) bq_fatal("[pileup] with several ranks the output must be a file (-o)\n");
+    partfn = calloc(strlen(outfn) + strlen(run_id) + 64, 1);
+    sprintf(partfn, "%s.%s.done%d", outfn, run_id, rank);
+    remove(partfn); /* a marker left by an earlier, interrupted run */
+    sprintf(partfn, "%s.%s.part%d", outfn, run_id, rank);
+  }
   if (outfn) {
-    out = fopen(outfn, "w");
-    if (!out) { fprintf(stderr, "[%s:%d] Cannot open output file: %s\nAbort.\n", __func__, __LINE__, outfn); exit(1); }
+    out = fopen(partfn ? partfn : outfn, "w");
+    if (!out) { fprintf(stderr, "[%s:%d] Cannot open output file: %s\nAbort.\n", __func__, __LINE__, partfn ? partfn : outfn); exit(1); }
   }
   setvbuf(out, 0, _IOFBF, 1 << 22);
-  {
-    bq_str_t h = {0, 0, 0};
-    vcf_header(&h, reffn, targets, hdr.n_targets, argv, argc, &conf, in_fns, n_fns);
-    fputs(h.s, out);
-    free(h.s);
-  }
+  bq_str_t vcf_hdr = {0, 0, 0};
+  vcf_header(&vcf_hdr, reffn, targets, hdr.n_targets, argv, argc, &conf, in_fns, n_fns);
+  if (world == 1) fputs(vcf_hdr.s, out); /* sharded: rank 0 writes it when it merges */
 
   bsq_plp *plp = 0;
   int rc = bsq_plp_create(device, nb, &plp);
   if (rc) bq_fatal("[pileup] bsq_plp_create: %s (%s)\n", bsq_strerror(rc), bsq_last_error());
   const double t_cuda = now_s();
-  (void)rank; (void)world;
 
   /* work list: (target index, beg, end) with 1-based beg, exclusive end (src/pileup.c:1171-1200) */
   int n_work = 0;
@@ -709,10 +725,12 @@ int bq_main_pileup(int argc, char **argv) {
     beg++;
     if (beg <= 0) beg = 1;
     if (end > hdr.len[tid]) end = hdr.len[tid];
-    work[n_work].tid = tid; work[n_work].beg = beg; work[n_work].end = end; n_work++;
+    if (rank == 0) { work[n_work].tid = tid; work[n_work].beg = beg; work[n_work].end = end; n_work++; } /* a region is not sharded */
   } else {
-    for (int j = 0; j < hdr.n_targets; ++j) { work[n_work].tid = targets[j].tid; work[n_work].beg = 1; work[n_work].end = targets[j].len; n_work++; }
+    for (int j = 0; j < hdr.n_targets; ++j)
+      if (j % world == rank) { work[n_work].tid = targets[j].tid; work[n_work].beg = 1; work[n_work].end = targets[j].len; n_work++; }
   }
+  int64_t *seg_bytes = calloc((size_t)hdr.n_targets + 1, sizeof(int64_t)); /* VCF text bytes per BAM contig, this rank */
 
   /* statistics: [sid][tid][ctx] (write_func, src/pileup.c:160-185) */
   const int smpl_block = hdr.n_targets * BQ_NCTX;
@@ -788,6 +806,7 @@ int bq_main_pileup(int argc, char **argv) {
       text_msg_t *tm = pq_get(&P.q_free_text);
       tm->text.l = 0;
       bq_plp_format(&fcf, hdr.name[tid], recs, n_loci, cb, conf.step, n_win, &tm->text, wbeta, wcnt);
+      seg_bytes[tid] += (int64_t)tm->text.l;
       pq_put(&P.q_text, tm);
       for (int w = 0; w < n_win; ++w) /* one record per window, added in block order (write_func) */
         for (int s = 0; s < nb; ++s)
@@ -807,6 +826,67 @@ int bq_main_pileup(int argc, char **argv) {
   }
   pthread_join(th_dec, 0); pthread_join(th_wr, 0);
   const double t_dec = P.t_dec, t_wr = P.t_wr;
+
+  if (world > 1) { /* hand this rank's part over; rank 0 merges */
+    fclose(out); out = 0;
+    const size_t n_stat = (size_t)nb * smpl_block;
+    char *fn = calloc(strlen(outfn) + strlen(run_id) + 64, 1), *fn2 = calloc(strlen(outfn) + strlen(run_id) + 64, 1);
+    sprintf(fn, "%s.%s.stats%d", outfn, run_id, rank);
+    FILE *sf = fopen(fn, "wb");
+    if (!sf || fwrite(seg_bytes, sizeof(int64_t), (size_t)hdr.n_targets, sf) != (size_t)hdr.n_targets || fwrite(cnt, sizeof(int64_t), n_stat, sf) != n_stat ||
+        fwrite(betasum, sizeof(double), n_stat, sf) != n_stat || fclose(sf) != 0)
+      bq_fatal("[pileup] cannot write %s\n", fn);
+    sprintf(fn2, "%s.%s.done%d", outfn, run_id, rank);
+    if (rename(fn, fn2) != 0) bq_fatal("[pileup] cannot write %s\n", fn2);
+    if (rank != 0) { fprintf(stderr, "[main] Real time: %.3f sec (rank %d of %d)\n", now_s() - t_start, rank, world); fflush(stderr); _exit(0); }
+    /* rank 0: wait for every rank, add the statistics in rank order, concatenate the bodies in contig-name order */
+    double wait_max = getenv("BSQ_PLP_MERGE_TIMEOUT") ? atof(getenv("BSQ_PLP_MERGE_TIMEOUT")) : 86400.;
+    int64_t *segs = calloc((size_t)world * hdr.n_targets + 1, sizeof(int64_t)), *c2 = malloc(sizeof(int64_t) * (n_stat + 1));
+    double *b2 = malloc(sizeof(double) * (n_stat + 1));
+    memset(cnt, 0, n_stat * sizeof(int64_t)); memset(betasum, 0, n_stat * sizeof(double));
+    for (int r = 0; r < world; ++r) {
+      sprintf(fn2, "%s.%s.done%d", outfn, run_id, r);
+      const double tw = now_s();
+      FILE *df;
+      while (!(df = fopen(fn2, "rb"))) {
+        if (now_s() - tw > wait_max) bq_fatal("[pileup] rank %d did not finish within %.0f s (no %s)\n", r, wait_max, fn2);
+        struct timespec nap = {0, 20000000};
+        nanosleep(&nap, 0);
+      }
+      if (fread(segs + (size_t)r * hdr.n_targets, sizeof(int64_t), (size_t)hdr.n_targets, df) != (size_t)hdr.n_targets ||
+          fread(c2, sizeof(int64_t), n_stat, df) != n_stat || fread(b2, sizeof(double), n_stat, df) != n_stat)
+        bq_fatal("[pileup] truncated %s\n", fn2);
+      fclose(df);
+      for (size_t i = 0; i < n_stat; ++i) { cnt[i] += c2[i]; betasum[i] += b2[i]; }
+    }
+    out = fopen(outfn, "w");
+    if (!out) { fprintf(stderr, "[%s:%d] Cannot open output file: %s\nAbort.\n", __func__, __LINE__, outfn); exit(1); }
+    setvbuf(out, 0, _IOFBF, 1 << 22);
+    fputs(vcf_hdr.s, out);
+    FILE **pf = calloc((size_t)world, sizeof(FILE *));
+    for (int r = 0; r < world; ++r) {
+      sprintf(fn, "%s.%s.part%d", outfn, run_id, r);
+      if (!(pf[r] = fopen(fn, "rb"))) bq_fatal("[pileup] cannot read %s\n", fn);
+    }
+    char *buf = malloc(1 << 22);
+    for (int j = 0; j < hdr.n_targets; ++j) { /* each rank wrote its contigs in this same order */
+      const int r = reg ? 0 : j % world;
+      int64_t left = segs[(size_t)r * hdr.n_targets + targets[j].tid];
+      while (left > 0) {
+        const size_t want = left > (1 << 22) ? (size_t)(1 << 22) : (size_t)left;
+        if (fread(buf, 1, want, pf[r]) != want) bq_fatal("[pileup] truncated part of rank %d\n", r);
+        fwrite(buf, 1, want, out);
+        left -= (int64_t)want;
+      }
+    }
+    free(buf);
+    for (int r = 0; r < world; ++r) {
+      fclose(pf[r]);
+      sprintf(fn, "%s.%s.part%d", outfn, run_id, r); remove(fn);
+      sprintf(fn2, "%s.%s.done%d", outfn, run_id, r); remove(fn2);
+    }
+    free(pf); free(segs); free(c2); free(b2); free(fn); free(fn2);
+  }
 
   if (!statsfn && outfn) statsfn = strdup(outfn);
   if (statsfn) { /* src/pileup.c:201-222 */

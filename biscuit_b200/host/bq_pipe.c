@@ -1,9 +1,11 @@
-/* bq_pipe.c -- three-stage batch pipeline of `biscuit align` on one GPU:
+/* bq_pipe.c -- batch pipeline of `biscuit align` over one or several GPUs:
  *
  *   stage A (thread)  next batch of reads from the source + host preparation (clipping, task rows in page-locked memory)
- *   stage B (1-2 threads, one GPU context each, batches alternate) GPU: H2D, phase-1 kernels, D2H  (bq_batch_run);
- *                     with two contexts the copies and kernel tails of one batch overlap the kernels of the next
- *   stage C (caller)  host phase 2 on opt->n_threads threads
+ *   stage B (one thread per lane; a lane = one aligner context = one GPU with its index replica; batches go to the lanes
+ *                     round-robin) GPU: H2D, phase-1 kernels, D2H  (bq_batch_run).  `biscuit align -G 0-7` runs eight lanes:
+ *                     reads shard by batch with no exchange between GPUs; the batch is the unit
+ *                     because mem_pestat is per batch (bwamem.c:464-467), so the output equals a one-GPU run
+ *   stage C (caller)  host phase 2 on opt->n_threads threads, batches in sequence order
  *   stage D (thread)  the sink (SAM output, freeing the reads), batches in order
  *
  * The reference runs the same shape with kt_pipeline (read / mem_process_seqs / write, lib/aln/align.c:70-167,577);
@@ -43,11 +45,12 @@ static void q_get(q1_t *q, bq_batch_t **b, bq_read_t **seqs, int *n, int *rc, in
 
 typedef struct {
   const bq_opt_t *opt;
-  bsq_aligner *al[2]; /* two GPU contexts: the copies of one batch overlap the kernels of the other */
+  bsq_aligner *al[BQ_MAX_LANES];
   int n_al;
+  volatile int abort_; /* set on the first failure: the source stops reading, the lanes stop computing */
   bq_source_fn src;
   void *src_ctx;
-  q1_t qa[2], qb[2], qc;
+  q1_t qa[BQ_MAX_LANES], qb[BQ_MAX_LANES], qc;
   int64_t n_processed;
   double t_src, t_prep, t_gpu, t_sink;
   bq_sink_fn sink;
@@ -62,7 +65,7 @@ static void *stage_a(void *arg) {
     q1_t *qa = &p->qa[seq % p->n_al];
     int n = 0, rc = 0;
     double t0 = pnow();
-    bq_read_t *seqs = p->src(p->src_ctx, &n);
+    bq_read_t *seqs = p->abort_ ? 0 : p->src(p->src_ctx, &n); /* after a failure nothing more is read */
     p->t_src += pnow() - t0; t0 = pnow();
     if (!seqs || n <= 0) { /* end marker to every GPU lane, in sequence order */
       free(seqs);
@@ -73,6 +76,7 @@ static void *stage_a(void *arg) {
     p->t_prep += pnow() - t0;
     p->n_processed += n;
     if (!b) { /* preparation failed: report it on this lane, end the others */
+      p->abort_ = 1;
       q_put(qa, 0, seqs, n, rc, 1);
       for (int k = 1; k < p->n_al; ++k) q_put(&p->qa[(seq + k) % p->n_al], 0, 0, 0, 0, 1);
       return 0;
@@ -90,12 +94,12 @@ static void *stage_b(void *arg) {
   for (;;) {
     bq_batch_t *b; bq_read_t *seqs; int n, rc, end;
     q_get(&p->qa[L->lane], &b, &seqs, &n, &rc, &end);
-    if (b && !failed) {
+    if (b && !failed && !p->abort_) {
       const double t0 = pnow();
       rc = bq_batch_run(p->al[L->lane], b);
       L->t_gpu += pnow() - t0;
-      if (rc) failed = rc;
-    } else if (b) rc = failed;  /* after a failure the remaining batches are only drained */
+      if (rc) { failed = rc; p->abort_ = 1; }
+    } else if (b) rc = failed ? failed : BSQ_EINVAL;  /* after a failure (here or on another lane) batches are only drained */
     q_put(&p->qb[L->lane], b, seqs, n, rc, end);
     if (end) return 0;
   }
@@ -116,16 +120,19 @@ static void *stage_d(void *arg) {
   }
 }
 
-int bq_pipeline_run(const bq_opt_t *opt, const bq_ref_t *ref, bsq_aligner *al, bsq_aligner *al2, bq_source_fn src, void *src_ctx, bq_sink_fn sink,
+int bq_pipeline_run(const bq_opt_t *opt, const bq_ref_t *ref, bsq_aligner *const *als, int n_al, bq_source_fn src, void *src_ctx, bq_sink_fn sink,
                     void *sink_ctx, const bq_pestat_t *pes0, const char *rg_id) {
   pipe_ctx_t p;
   memset(&p, 0, sizeof p);
-  p.opt = opt; p.al[0] = al; p.al[1] = al2; p.n_al = al2 ? 2 : 1; p.src = src; p.src_ctx = src_ctx;
+  if (n_al < 1 || n_al > BQ_MAX_LANES) return BSQ_EINVAL;
+  p.opt = opt; p.n_al = n_al; p.src = src; p.src_ctx = src_ctx;
+  for (int k = 0; k < n_al; ++k) p.al[k] = als[k];
   p.sink = sink; p.sink_ctx = sink_ctx;
-  for (int k = 0; k < 2; ++k) { q_init(&p.qa[k]); q_init(&p.qb[k]); }
+  for (int k = 0; k < n_al; ++k) { q_init(&p.qa[k]); q_init(&p.qb[k]); }
   q_init(&p.qc);
-  pthread_t ta, tb[2], td;
-  lane_t lanes[2] = {{&p, 0, 0}, {&p, 1, 0}};
+  pthread_t ta, tb[BQ_MAX_LANES], td;
+  lane_t lanes[BQ_MAX_LANES];
+  for (int k = 0; k < n_al; ++k) { lanes[k].p = &p; lanes[k].lane = k; lanes[k].t_gpu = 0; }
   pthread_create(&ta, 0, stage_a, &p);
   for (int k = 0; k < p.n_al; ++k) pthread_create(&tb[k], 0, stage_b, &lanes[k]);
   pthread_create(&td, 0, stage_d, &p);
@@ -142,6 +149,7 @@ int bq_pipeline_run(const bq_opt_t *opt, const bq_ref_t *ref, bsq_aligner *al, b
       q_put(&p.qc, 0, seqs, n, 0, end);
     } else {
       if (rc && !ret) ret = rc;
+      if (rc) p.abort_ = 1;
       if (b) bq_batch_discard(b);
       q_put(&p.qc, 0, seqs, n, rc ? rc : -1, end); /* failed batch: the sink only frees */
     }
@@ -156,7 +164,7 @@ int bq_pipeline_run(const bq_opt_t *opt, const bq_ref_t *ref, bsq_aligner *al, b
   pthread_join(ta, 0);
   for (int k = 0; k < p.n_al; ++k) pthread_join(tb[k], 0);
   pthread_join(td, 0);
-  p.t_gpu = lanes[0].t_gpu + lanes[1].t_gpu;
+  for (int k = 0; k < p.n_al; ++k) p.t_gpu += lanes[k].t_gpu;
   if (getenv("BQ_TIMING"))
     fprintf(stderr, "[bq_pipeline] source %.3f prep %.3f | gpu %.3f | wait %.3f phase2 %.3f sink %.3f s\n", p.t_src, p.t_prep, p.t_gpu, t_wait, t_fin,
             p.t_sink);

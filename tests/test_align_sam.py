@@ -246,3 +246,61 @@ def test_sam_identical_repeats_gpu(repeat_set, extra):
     fa, f1, f2 = repeat_set
     args = ["-@", "3"] + extra + [fa, f1, f2]
     assert _sam(GPU_BIN, args) == _sam(refprobe.REF_BIN, args)
+
+
+def test_long_read_and_name_mismatch_hostemu(hard_set, tmp_path):
+    """A read beyond the device kernels' length limit does not fail the batch: it is reported unaligned with a warning and
+    every other pair is aligned as usual.  Desynchronised FASTQ files stop the run with the reference's message
+    (check_paired_read_names, lib/aln/bwamem.c:210-216)."""
+    fa, f1, f2 = hard_set
+    a, b = open(f1).read().split("\n"), open(f2).read().split("\n")
+    n = 200
+    a, b = a[:4 * n], b[:4 * n]
+    long_seq = (a[4 * 7 + 1] * 3)[:300]
+    a[4 * 7 + 1], a[4 * 7 + 3] = long_seq, "I" * 300
+    g1, g2 = str(tmp_path / "l1.fq"), str(tmp_path / "l2.fq")
+    open(g1, "w").write("\n".join(a) + "\n")
+    open(g2, "w").write("\n".join(b) + "\n")
+    r = subprocess.run([build_emu_bin(), "align", "-@", "2", fa, g1, g2], capture_output=True)
+    assert r.returncode == 0 and b"longer than 256 bases" in r.stderr
+    recs = [ln.split(b"\t") for ln in r.stdout.split(b"\n") if ln and not ln.startswith(b"@")]
+    name = a[4 * 7][1:].split("/")[0].encode()
+    mine = [f for f in recs if f[0] == name and int(f[1]) & 0x40]
+    assert len(mine) == 1 and int(mine[0][1]) & 0x4 and len(mine[0][9]) == 300
+    # all other pairs: same records as a reference run in which that read is an unalignable one of ordinary length (the
+    # pair keeps its place in the batch, so the read ids behind the hash tie-breaks are the same)
+    h1 = str(tmp_path / "k1.fq")
+    c = list(a)
+    c[4 * 7 + 1], c[4 * 7 + 3] = "ACGT" * 5 + "N" * 110 + "TGCA" * 5, "I" * 150
+    open(h1, "w").write("\n".join(c) + "\n")
+    ref = subprocess.run([refprobe.REF_BIN, "align", "-@", "2", "-I", "450,40", fa, h1, g2], capture_output=True, check=True).stdout
+    got = subprocess.run([build_emu_bin(), "align", "-@", "2", "-I", "450,40", fa, g1, g2], capture_output=True, check=True).stdout
+    strip = lambda out: [ln for ln in out.split(b"\n") if ln and not ln.startswith(b"@") and ln.split(b"\t")[0] != name]  # noqa: E731
+    assert strip(got) == strip(ref)
+    # names that do not match
+    b[4 * 3] = "@somebody_else/2"
+    open(g2, "w").write("\n".join(b) + "\n")
+    r = subprocess.run([build_emu_bin(), "align", "-@", "2", fa, f1, g2], capture_output=True)
+    assert r.returncode != 0 and b"paired reads have different names" in r.stderr
+
+
+def test_sam_identical_three_lanes_hostemu(hard_set):
+    """`-G 0,0,0`: three aligner contexts, batches dealt round-robin (the multi-GPU pipeline of bq_pipe.c, here over the
+    emulation).  Eleven small batches; with the insert-size distribution given nothing depends on the batch borders."""
+    fa, f1, f2 = hard_set
+    args = ["-@", "4", "-I", "450,40", fa, f1, f2]
+    assert _sam(build_emu_bin(), ["-G", "0,0,0"] + args, env={"BQ_CHUNK_SIZE": "20000"}) == _sam(refprobe.REF_BIN, args)
+
+
+@pytest.mark.gpu
+def test_sam_identical_two_gpus(hard_set):
+    """`biscuit align -G 0-1`: FASTQ batches dealt to two GPUs, output identical to the one-GPU run and to the reference."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    fa, f1, f2 = hard_set
+    args = ["-@", "4", fa, f1, f2]
+    two = _sam(GPU_BIN, ["-G", "0-1"] + args, env={"BQ_CHUNK_SIZE": "20000"})
+    assert two == _sam(GPU_BIN, args, env={"BQ_CHUNK_SIZE": "20000"})
+    args = ["-@", "4", "-I", "450,40", fa, f1, f2]
+    assert _sam(GPU_BIN, ["-G", "0,1"] + args, env={"BQ_CHUNK_SIZE": "20000"}) == _sam(refprobe.REF_BIN, args)

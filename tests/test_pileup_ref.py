@@ -223,3 +223,50 @@ def test_hard_clip_gpu(cuda):
         exp = oracle_plp.region(conf, ref, rd, 1, len(ref), 1)
         assert len(exp) > 20 and got.tobytes() == exp.tobytes()
     pl.close()
+
+
+def _run_ranks(prog, tmp, fa, bams, world, opts=(), devices=None):
+    out = os.path.join(tmp, f"w{world}.vcf")
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(devices[r] if devices else 0), MASTER_PORT="29512")
+        procs.append(subprocess.Popen([prog, "pileup", "-@", "2", "-o", out, *opts, fa, *bams], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE))
+    for p in procs:
+        _, err = p.communicate(timeout=600)
+        assert p.returncode == 0, err[-2000:]
+    left = [f for f in os.listdir(tmp) if ".part" in f or ".done" in f or ".stats" in f]
+    assert not left, left
+    return out
+
+
+def _check_sharded(prog, tmp, devices=None):
+    fa, bams, _, _ = _case(tmp, 2, scale=2)
+    one = os.path.join(tmp, "one.vcf")
+    subprocess.run([prog, "pileup", "-@", "2", "-o", one, fa] + bams, check=True, capture_output=True)
+    for world in (2, 3):
+        if devices and world > len(devices):
+            continue
+        out = _run_ranks(prog, tmp, fa, bams, world, devices=devices)
+        assert refsrc.split_vcf(open(out, "rb").read()) == refsrc.split_vcf(open(one, "rb").read())
+        assert open(out + "_meth_average.tsv", "rb").read() == open(one + "_meth_average.tsv", "rb").read()
+    # a region is not sharded: rank 0 does it, the result is the one-process result
+    reg = ["-g", "chr2:10,001-60000"]
+    subprocess.run([prog, "pileup", "-@", "2", "-o", one] + reg + [fa] + bams, check=True, capture_output=True)
+    out = _run_ranks(prog, tmp, fa, bams, 2, opts=reg, devices=devices)
+    assert refsrc.split_vcf(open(out, "rb").read())[1] == refsrc.split_vcf(open(one, "rb").read())[1]
+
+
+def test_pileup_ranks_host_side(tmp_path):
+    """`biscuit pileup` as one process per rank (RANK / WORLD_SIZE / LOCAL_RANK): contigs dealt round-robin, rank 0 merges the
+    VCF bodies in contig-name order and adds the per-contig statistics -- same files as a one-process run."""
+    _need(oracle_plp.SO)
+    _check_sharded(_emu(), str(tmp_path))
+
+
+@pytest.mark.gpu
+def test_pileup_two_gpus(tmp_path):
+    import torch
+    _need(BISCUIT)
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    _check_sharded(BISCUIT, str(tmp_path), devices=[0, 1])
