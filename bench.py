@@ -269,23 +269,16 @@ def main():
     L = len(nt4)
     log(f"rank {rank}: reference {L / 1e6:.0f} Mb, {len(names)} contigs generated in {time.time() - t0:.1f}s")
     bsq = capi.load()
-    t0 = time.time()
-    dx = bsq.build_index(pac, L, names, offs, lens, device=local_rank)
-    t_index = time.time() - t0
-    log(f"rank {rank}: FM-indices built on GPU in {t_index:.1f}s (stats {dx.sizes()['stats'].tolist()})")
-    workload = f"align 2x150bp synthetic bisulfite pairs vs {L / 1e6:.0f} Mb synthetic reference (GRCh38-sized = 3100 Mb)"
-    index_check = None
-    if rank == 0 and args.impl == "ours" and not args.no_index_check:
-        # nobody can run the reference's `biscuit index` at this size (hours): sampled suffix-order / LF-inversion
-        # checks of the index both arms are about to use, half of the ranks above 2^32 (tools/indexcheck.py)
-        import indexcheck
-        t0 = time.time()
-        index_check = indexcheck.check_index(dx, nt4, n_samples=2000, seed=5, totals=False)
-        index_check["seconds"] = time.time() - t0
-        log("index check:", index_check)
 
+    def build_main_index():
+        t0 = time.time()
+        dx_ = bsq.build_index(pac, L, names, offs, lens, device=local_rank)
+        log(f"rank {rank}: FM-indices built on GPU in {time.time() - t0:.1f}s (stats {dx_.sizes()['stats'].tolist()})")
+        return dx_, time.time() - t0
+    workload = f"align 2x150bp synthetic bisulfite pairs vs {L / 1e6:.0f} Mb synthetic reference (GRCh38-sized = 3100 Mb)"
     if args.impl == "reference":
         import tempfile
+        dx, t_index = build_main_index()
         reads = sim_batch(nt4, names, offs, lens, args.cpu_pairs, seed=2024)
         with tempfile.TemporaryDirectory() as d:
             prefix = os.path.join(d, "ref.fa")
@@ -308,14 +301,53 @@ def main():
         return 0
 
     # ---------------- ours ----------------
-    opt = bsq.default_opt()
-    al = capi.Aligner(dx, opt)
     t0 = time.time()
     reads = sim_batch(nt4, names, offs, lens, args.pairs, seed=2024 + 1000 * rank)
     seqs, tl, par = tasks_from_reads(reads)
     n_tasks = len(seqs)
     n_reads = len(reads)
     log(f"rank {rank}: {args.pairs} pairs simulated in {time.time() - t0:.1f}s")
+    # ---- algorithmic work of one step, from the instrumented build (untimed; rank 0, before anything else is resident) ----
+    work = None
+    if rank == 0:
+        try:
+            cb = capi.Bsq(os.path.join(capi.HERE, "csrc", "libbsq_count.so"))
+            # the instrumented library builds its own index copy (seconds), without the derived full suffix array so that
+            # the LF-walk blocks of bwt_sa are counted too, and counts the work of a bounded sub-batch of the same tasks
+            old = os.environ.get("BSQ_FULL_SA")
+            os.environ["BSQ_FULL_SA"] = "0"
+            dx2 = cb.build_index(pac, L, names, offs, lens, device=local_rank)
+            if old is None:
+                del os.environ["BSQ_FULL_SA"]
+            else:
+                os.environ["BSQ_FULL_SA"] = old
+            al2 = capi.Aligner(dx2, cb.default_opt())
+            nsub = min(n_tasks, 100_000)
+            w0 = np.zeros(8, np.uint64)
+            cb.lib.bsq_work_counters(w0.ctypes.data_as(C.c_void_p), C.c_int(8), C.c_int(1))
+            al2.phase1(seqs[:nsub], tl[:nsub], par[:nsub])
+            cb.lib.bsq_work_counters(w0.ctypes.data_as(C.c_void_p), C.c_int(8), C.c_int(1))
+            work = {k: float(w0[i]) / nsub for i, k in enumerate(["blocks", "extends", "ksw_calls", "cells", "ref_bases"])}
+            c2 = al2.counters()
+            work["seed_blocks"] = float(c2[12] - c2[11]) / nsub
+            work["sa_blocks"] = float(c2[13] - c2[12]) / nsub
+            work["sa_lookups"] = float(c2[2]) / nsub
+            al2.close()
+            dx2.close()
+        except Exception as e:  # noqa: BLE001
+            log("work counters unavailable:", e)
+    dx, t_index = build_main_index()
+    index_check = None
+    if rank == 0 and not args.no_index_check:
+        # nobody can run the reference's `biscuit index` at this size (hours): sampled suffix-order / LF-inversion
+        # checks of the index both arms are about to use, half of the ranks above 2^32 (tools/indexcheck.py)
+        import indexcheck
+        t0 = time.time()
+        index_check = indexcheck.check_index(dx, nt4, n_samples=2000, seed=5, totals=False)
+        index_check["seconds"] = time.time() - t0
+        log("index check:", index_check)
+    opt = bsq.default_opt()
+    al = capi.Aligner(dx, opt)
     lib = bsq.lib
 
     def pinned(arr):
@@ -427,29 +459,6 @@ def main():
         "chain fallback tasks", int(counters[14]), "k_chain_warp us", int(counters[15]))
 
     if rank == 0:
-        # ---- algorithmic work of one step, from the instrumented build (untimed) ----
-        work = None
-        try:
-            cb = capi.Bsq(os.path.join(capi.HERE, "csrc", "libbsq_count.so"))
-            # the instrumented library keeps its own index copy (built again, seconds) and counts the work of a
-            # bounded sub-batch of the same tasks
-            dx2 = cb.build_index(pac, L, names, offs, lens, device=local_rank)
-            if dx2 is not None:
-                al2 = capi.Aligner(dx2, cb.default_opt())
-                nsub = min(n_tasks, 100_000)
-                w0 = np.zeros(8, np.uint64)
-                cb.lib.bsq_work_counters(w0.ctypes.data_as(C.c_void_p), C.c_int(8), C.c_int(1))
-                al2.phase1(seqs[:nsub], tl[:nsub], par[:nsub])
-                cb.lib.bsq_work_counters(w0.ctypes.data_as(C.c_void_p), C.c_int(8), C.c_int(1))
-                work = {k: float(w0[i]) / nsub for i, k in enumerate(["blocks", "extends", "ksw_calls", "cells", "ref_bases"])}
-                c2 = al2.counters()
-                work["seed_blocks"] = float(c2[12] - c2[11]) / nsub
-                work["sa_blocks"] = float(c2[13] - c2[12]) / nsub
-                work["sa_lookups"] = float(c2[2]) / nsub
-                al2.close()
-                dx2.close()
-        except Exception as e:  # noqa: BLE001
-            log("work counters unavailable:", e)
         # dominant kernel by device time
         dom = int(np.argmax(kern_us[:4]))
         dom_name = stage_names[dom]

@@ -76,6 +76,13 @@ class Pileup:
             self.bsq.check(self.bsq.lib.bsq_plp_fetch(self.h, out.ctypes.data_as(C.c_void_p)), "bsq_plp_fetch")
         return out
 
+    def fetch_into(self, out: np.ndarray, n_loci: int) -> np.ndarray:
+        """bsq_plp_fetch into a caller-owned buffer (e.g. page-locked memory): no allocation, no clearing."""
+        assert out.dtype == REC_DTYPE and len(out) >= n_loci * self.n_bams
+        if n_loci:
+            self.bsq.check(self.bsq.lib.bsq_plp_fetch(self.h, out.ctypes.data_as(C.c_void_p)), "bsq_plp_fetch")
+        return out[: n_loci * self.n_bams]
+
     def counters(self) -> np.ndarray:
         c = np.zeros(8, np.int64)
         self.bsq.check(self.bsq.lib.bsq_plp_counters(self.h, c.ctypes.data_as(C.c_void_p), C.c_int(8)), "bsq_plp_counters")

@@ -188,13 +188,21 @@ def run(args, log, torch, dist, rank: int, local_rank: int, world: int, peak: fl
     barrier()
     dt = time.perf_counter() - t0
     c = pl.counters()
-    # --- the C ABI with host buffers: H2D of every read column + kernels + D2H of the records, per pass ---
-    e2e_steps = 2
+    # --- the C ABI with host buffers: H2D of every read column + kernels + D2H of the records, per pass.  The host
+    # buffers are page-locked (what `biscuit pileup` uses for its decoded batches, bq_bam.c), allocated outside the timing ---
+    t_pin = time.perf_counter()
+    rd_pin = {k: (torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy() if isinstance(v, np.ndarray) else v) for k, v in rd.items()}
+    out_pin = torch.empty((int(n_loci) + 1) * 88, dtype=torch.uint8).pin_memory().numpy().view(plp.REC_DTYPE)
+    log(f"pileup rank {rank}: page-locked staging buffers ({sum(v.nbytes for v in rd_pin.values() if isinstance(v, np.ndarray)) / 1e9:.1f} + "
+        f"{out_pin.nbytes / 1e9:.1f} GB) in {time.perf_counter() - t_pin:.1f}s")
+    pl.stage(rd_pin)
+    recs = pl.fetch_into(out_pin, pl.run(conf, 1, L))  # warm-up pass
+    e2e_steps = 3
     barrier()
     t1 = time.perf_counter()
     for _ in range(e2e_steps):
-        pl.stage(rd)
-        recs = pl.fetch(pl.run(conf, 1, L))
+        pl.stage(rd_pin)
+        recs = pl.fetch_into(out_pin, pl.run(conf, 1, L))
     barrier()
     dt_e2e = time.perf_counter() - t1
     clocks = sampler.stop()
@@ -213,7 +221,7 @@ def run(args, log, torch, dist, rank: int, local_rank: int, world: int, peak: fl
         tt = torch.tensor([dt, dt_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt, dt_e2e = float(tt[0]), float(tt[1])
-    del recs
+    del recs, out_pin, rd_pin
     pl.close()
     if rank != 0:
         return None
@@ -246,7 +254,7 @@ def run(args, log, torch, dist, rank: int, local_rank: int, world: int, peak: fl
                        "parallelism": f"contigs sharded over {world} rank(s); one NCCL reduce of the per-contig statistics"},
             "clocks": clocks, "stats_reduce_ms": reduce_ms,
             "e2e": {"value": world * (L - 1) * e2e_steps / dt_e2e, "unit": "loci/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(n_loci) * 88,
-                    "steps": e2e_steps, "note": "C ABI with host buffers: bsq_plp_stage (H2D) + bsq_plp_run + bsq_plp_fetch (D2H) per pass"},
+                    "steps": e2e_steps, "note": "C ABI with page-locked host buffers: bsq_plp_stage (H2D) + bsq_plp_run + bsq_plp_fetch (D2H) per pass"},
             "e2e_cli": cli, "parity": parity,
             "gpu_launches": 3 * steps * n_tiles,
             "roofline": {"bound": "hbm", "kernel": "k_plp_win", "achieved": alg / (kus[0] * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
