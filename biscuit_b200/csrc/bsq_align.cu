@@ -20,6 +20,7 @@
 static __device__ unsigned long long bsq_ctr[8];
 #endif
 #include "bsq_task.h"
+#include "bsq_seed3.cuh"
 #include "bsq_ksw_warp.cuh"
 #include "bsq_chain_warp.h"
 #include "bsq_opt_default.h"
@@ -77,6 +78,22 @@ void bsq_index_adopt(bsq_index *ix, void *p) {
   if (p && ix->n_allocs < 32) ix->allocs[ix->n_allocs++] = p;
 }
 
+int bsq_index_derive_b32(bsq_index *ix) {
+  for (int w = 0; w < 2; ++w) {
+    bsq_fm_t &f = ix->d.fm[w];
+    const uint64_t n_half = 2 * ((f.seq_len + 127) / 128);
+    uint32_t *b = nullptr;
+    CK(cudaMalloc(&b, (n_half + 1) * 32));
+    bsq_index_adopt(ix, b);
+    CK(cudaMemsetAsync(b + n_half * 8, 0, 32));
+    k_derive_b32<<<(unsigned)((n_half + 255) / 256), 256>>>(f.blocks, f.seq_len, n_half, b);
+    CK(cudaGetLastError());
+    f.b32 = b;
+  }
+  CK(cudaDeviceSynchronize());
+  return 0;
+}
+
 // grow-only device buffer
 struct DevBuf {
   void *p = nullptr;
@@ -98,8 +115,16 @@ struct DevBuf {
   template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+// workspace of the seeding kernels (bsq_seed3.cuh): candidate lists of the forward sweeps, work queues
+struct SeedWs {
+  DevBuf cand1, cand2, calls1, calls2, items, q;
+  int64_t calls1_cap = 0, calls2_cap = 0, items_cap = 0, cand2_cap = 0;  // grown when a batch needs more (the batch is re-seeded)
+  void release() { cand1.release(); cand2.release(); calls1.release(); calls2.release(); items.release(); q.release(); }
+};
+
 struct bsq_aligner {
   const bsq_index *idx;
+  SeedWs seed_ws;
   bsq_devopt_t opt;
   cudaStream_t stream, stream2;  // stream2: the large-task chaining tier, concurrent with the small tiers
   cudaEvent_t ev[8], ev_fork, ev_join;
@@ -109,6 +134,7 @@ struct bsq_aligner {
   int64_t counters[16];
   int64_t n_staged = 0, n_regs_total = -1;
   int64_t fb_cap = 0;  // entries of the fallback-chaining workspace pools
+  int64_t seed_fills[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // seeding work-queue fills of the last batch: pass-1 calls, pass-2 items, pass-2 calls, pass-2 candidate records, retries
   int32_t stride = 0;
 };
 
@@ -226,11 +252,12 @@ __global__ void __launch_bounds__(128, BSQ_SEED_CTAS) k_seed(const __grid_consta
 
 // Order each task's interval list (memchain.c:105) and count its SA lookups; one thread per task, all
 // lanes busy (inside k_seed a finishing lane would sort while 31 lanes wait).
-__global__ void __launch_bounds__(128) k_seed_sort(const __grid_constant__ bsq_devopt_t opt, int64_t n_tasks, bsq_pk_t *intv, const int32_t *n_intv, int32_t *n_sa) {
+__global__ void __launch_bounds__(128) k_seed_sort(const __grid_constant__ bsq_devopt_t opt, int64_t n_tasks, bsq_pk_t *intv, int32_t *n_intv, int32_t *n_sa, int32_t *status) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_tasks) return;
   uint32_t keys[BSQ_MAX_INTV];
-  const int n = n_intv[t];
+  int n = n_intv[t];
+  if (n > BSQ_MAX_INTV) { n = 0; n_intv[t] = 0; atomicOr(status, 1); }  // the seeding kernels count past the capacity without storing
   n_sa[t] = n > 0 ? bsq_seed_sort(opt, intv + t * BSQ_MAX_INTV, n, keys) : 0;
 }
 
@@ -259,11 +286,26 @@ __global__ void k_sa_plain(bsq_devidx_t ix, int which, int64_t n, const uint64_t
   pos[i] = bsq_sa(ix.fm[which], ranks[i]);
 }
 
+// bwt_occ4 (bwt.c:173-200) through the derived 32-byte blocks the seeding kernels use; cross-checked on the device against
+// the reference-layout blocks (a mismatch returns all ones, which no rank equals)
 __global__ void k_occ4(bsq_devidx_t ix, int which, int64_t n, const uint64_t *k, uint64_t *cnt) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint64_t c[4];
   bsq_occ4(ix.fm[which], k[i], c);
+  const bsq_fm_t &f = ix.fm[which];
+  if (f.b32 && k[i] != (uint64_t)-1) {
+    const uint64_t k2 = k[i] - (k[i] >= f.primary);
+    uint32_t w[8];
+    s3_ld256(f.b32 + (k2 >> 6) * 8, w);
+    uint64_t gt_prev = 0;
+    for (int s = 3; s >= 0; --s) {
+      uint64_t e, g;
+      s3_rank(w, k2, s3_sym(s), e, g);
+      if (e != c[s] || g != gt_prev) c[s] = ~0ull;
+      gt_prev += e;
+    }
+  }
   cnt[4 * i] = c[0]; cnt[4 * i + 1] = c[1]; cnt[4 * i + 2] = c[2]; cnt[4 * i + 3] = c[3];
 }
 
@@ -551,6 +593,59 @@ static inline unsigned seed_grid(int64_t n) {
   return (unsigned)(want < 148 * BSQ_SEED_CTAS ? want : 148 * BSQ_SEED_CTAS);
 }
 
+// BSQ_SEED_IMPL=2 selects the single-kernel state machine (k_seed2) instead of the per-pass kernels of bsq_seed3.cuh
+static inline int seed_impl() { const char *e = getenv("BSQ_SEED_IMPL"); return e ? atoi(e) : 3; }
+
+// mem_collect_intv for n tasks: unsorted interval lists in intv / n_intv (n_intv zeroed here).  Synchronises the stream
+// once (the queue fills come back to size the retry when a work queue was too small).
+static int seed3_run(SeedWs &ws, cudaStream_t s, const bsq_devopt_t &opt, const bsq_devidx_t &ix, int64_t n, const uint8_t *seqs, int stride,
+                     const int32_t *lens, const uint8_t *parent, int pipeline, bsq_pk_t *intv, int32_t *n_intv, int64_t *fills) {
+  int rc;
+  if (!ix.fm[0].b32 || !ix.fm[1].b32) { snprintf(g_err, sizeof g_err, "index without derived rank blocks"); return BSQ_EINVAL; }
+  if (ws.calls1_cap < 8 * n + 1024) ws.calls1_cap = 8 * n + 1024;
+  if (ws.items_cap < 4 * n + 1024) ws.items_cap = 4 * n + 1024;
+  if (ws.calls2_cap < ws.items_cap) ws.calls2_cap = ws.items_cap;
+  if (ws.cand2_cap < n * (int64_t)stride) ws.cand2_cap = n * (int64_t)stride;
+  { const char *e = getenv("BSQ_SEED_QCAP"); if (e && atoll(e) > 0 && fills) { ws.calls1_cap = ws.calls2_cap = ws.items_cap = atoll(e); ws.cand2_cap = 64 * atoll(e); } }  // test hook: force the retry path
+  const unsigned grid = (unsigned)((n + 127) / 128 < 148 * 8 ? (n + 127) / 128 : 148 * 8);
+  for (int attempt = 0; attempt < 12; ++attempt) {
+    if ((rc = ws.cand1.reserve((size_t)n * stride * 16))) return rc;
+    if ((rc = ws.cand2.reserve((size_t)ws.cand2_cap * 16))) return rc;
+    if ((rc = ws.calls1.reserve((size_t)ws.calls1_cap * sizeof(s3_call_t)))) return rc;
+    if ((rc = ws.calls2.reserve((size_t)ws.calls2_cap * sizeof(s3_call_t)))) return rc;
+    if ((rc = ws.items.reserve((size_t)ws.items_cap * sizeof(s3_item_t)))) return rc;
+    if ((rc = ws.q.reserve(sizeof(s3_q_t)))) return rc;
+    s3_q_t *q = ws.q.as<s3_q_t>();
+    CK(cudaMemsetAsync(q, 0, sizeof(s3_q_t), s));
+    CK(cudaMemsetAsync(n_intv, 0, (size_t)n * 4, s));
+    k_s3_fwd<1><<<grid, 128, 0, s>>>(opt, ix, n, seqs, stride, lens, parent, pipeline, ws.cand1.as<uint4>(), 0ull, nullptr, ws.calls1.as<s3_call_t>(),
+                                     (unsigned long long)ws.calls1_cap, ws.items.as<s3_item_t>(), (unsigned long long)ws.items_cap, q, intv, n_intv);
+    k_s3_greedy<<<grid, 128, 0, s>>>(opt, ix, n, seqs, stride, lens, parent, pipeline, q, intv, n_intv);
+    k_s3_bwd<<<grid, 128, 0, s>>>(opt, ix, seqs, stride, parent, ws.cand1.as<uint4>(), ws.calls1.as<s3_call_t>(), (unsigned long long)ws.calls1_cap, 1,
+                                  ws.items.as<s3_item_t>(), (unsigned long long)ws.items_cap, q, intv, n_intv);
+    k_s3_fwd<2><<<grid, 128, 0, s>>>(opt, ix, n, seqs, stride, lens, parent, pipeline, ws.cand2.as<uint4>(), (unsigned long long)ws.cand2_cap,
+                                     ws.items.as<s3_item_t>(), ws.calls2.as<s3_call_t>(), (unsigned long long)ws.calls2_cap, ws.items.as<s3_item_t>(),
+                                     (unsigned long long)ws.items_cap, q, intv, n_intv);
+    k_s3_bwd<<<grid, 128, 0, s>>>(opt, ix, seqs, stride, parent, ws.cand2.as<uint4>(), ws.calls2.as<s3_call_t>(), (unsigned long long)ws.calls2_cap, 2,
+                                  ws.items.as<s3_item_t>(), (unsigned long long)ws.items_cap, q, intv, n_intv);
+    CK(cudaGetLastError());
+    s3_q_t h;
+    CK(cudaMemcpyAsync(&h, q, sizeof h, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (fills) { fills[0] = (int64_t)h.n_calls1; fills[1] = (int64_t)h.n_items; fills[2] = (int64_t)h.n_calls2; fills[3] = (int64_t)h.cand2_used; fills[4] = attempt; }
+    if (!h.overflow) return 0;
+    // a queue was too small: size it from what this attempt asked for and seed the batch again
+    if ((int64_t)h.n_calls1 > ws.calls1_cap) ws.calls1_cap = (int64_t)h.n_calls1 + (int64_t)h.n_calls1 / 4;
+    if ((int64_t)h.n_items > ws.items_cap) ws.items_cap = (int64_t)h.n_items + (int64_t)h.n_items / 4;
+    if (ws.calls2_cap < ws.items_cap) ws.calls2_cap = ws.items_cap;
+    if ((int64_t)h.n_calls2 > ws.calls2_cap) ws.calls2_cap = (int64_t)h.n_calls2 + (int64_t)h.n_calls2 / 4;
+    if ((int64_t)h.cand2_used > ws.cand2_cap) ws.cand2_cap = (int64_t)h.cand2_used + (int64_t)h.cand2_used / 4;
+    if (h.overflow & 1ull) { ws.cand2_cap *= 2; }  // items were dropped, so cand2_used undercounts
+  }
+  snprintf(g_err, sizeof g_err, "seeding work queues still too small after 12 attempts");
+  return BSQ_EOVERFLOW;
+}
+
 extern "C" {
 
 const char *bsq_strerror(int code) {
@@ -596,6 +691,7 @@ int bsq_index_upload(const bsq_index_desc *h, int device, bsq_index **out) {
   if (!rc) rc = upload_array(ix, h->ann_len, (size_t)h->n_seqs * 4, (const void **)&ix->d.ann_len);
   if (!rc) rc = upload_array(ix, h->ann_is_alt, (size_t)h->n_seqs * 4, (const void **)&ix->d.ann_is_alt);
   ix->d.l_pac = h->l_pac; ix->d.n_seqs = h->n_seqs;
+  if (!rc) rc = bsq_index_derive_b32(ix);
   if (rc) { bsq_index_free(ix); return rc; }
   for (int w = 1; w >= 0; --w) {  // optional full SA (see bsq_want_full_sa)
     ix->d.fm[w].full_sa = nullptr;
@@ -673,9 +769,15 @@ int bsq_collect_intv(const bsq_index *ix, const bsq_opt *opt_, int64_t n, const 
   CK(cudaMemset(dst, 0, 4)); CK(cudaMemset(dnext, 0, 8));
   CK(cudaMemset(dpk, 0, n * BSQ_MAX_INTV * sizeof(bsq_pk_t)));
   if (seed_v1()) k_seed<<<seed_grid(n), 128, seed_smem_bytes(stride)>>>(opt, ix->d, n, dseq, stride, dlen, dpar, 0, dpk, dn, dst, dnext);
-  else launch_seed2(seed_variant(), seed_grid(n), 0, opt, ix->d, n, dseq, stride, dlen, dpar, 0, dpk, dn, dst, dnext);
+  else if (seed_impl() == 2) launch_seed2(seed_variant(), seed_grid(n), 0, opt, ix->d, n, dseq, stride, dlen, dpar, 0, dpk, dn, dst, dnext);
+  else {
+    SeedWs ws;
+    const int rc3 = seed3_run(ws, 0, opt, ix->d, n, dseq, stride, dlen, dpar, 0, dpk, dn, nullptr);
+    ws.release();
+    if (rc3) { cudaFree(dseq); cudaFree(dpar); cudaFree(dlen); cudaFree(dn); cudaFree(dnsa); cudaFree(dst); cudaFree(dpk); cudaFree(dint); cudaFree(dnext); return rc3; }
+  }
   CK(cudaGetLastError());
-  k_seed_sort<<<nblk(n, 128), 128>>>(opt, n, dpk, dn, dnsa);
+  k_seed_sort<<<nblk(n, 128), 128>>>(opt, n, dpk, dn, dnsa, dst);
   CK(cudaGetLastError());
   k_unpack_intv<<<nblk(n * BSQ_MAX_INTV, 256), 256>>>(n * BSQ_MAX_INTV, dpk, dint);
   CK(cudaGetLastError());
@@ -739,6 +841,7 @@ void bsq_aligner_destroy(bsq_aligner *al) {
                     &al->status, &al->snodes, &al->wchains, &al->bnodes, &al->order, &al->ochains, &al->oseeds, &al->n_chains,
                     &al->frac_rep, &al->srt, &al->regs_tmp, &al->n_regs, &al->reg_off, &al->regs, &al->cub_tmp, &al->scalars, &al->fb_flag, &al->tiers};
   for (DevBuf *b : bufs) b->release();
+  al->seed_ws.release();
   for (int i = 0; i < 8; ++i) cudaEventDestroy(al->ev[i]);
   cudaStreamDestroy(al->stream);
   cudaStreamDestroy(al->stream2); cudaEventDestroy(al->ev_fork); cudaEventDestroy(al->ev_join);
@@ -798,11 +901,14 @@ static int phase1_device(bsq_aligner *al, int64_t n, int32_t stride, int64_t *to
     k_seed<<<seed_grid(n), 128, seed_smem_bytes(stride), s>>>(opt, ix, n, al->seqs.as<uint8_t>(), stride, al->lens.as<int32_t>(), al->parent.as<uint8_t>(), 1,
                                                               al->intv.as<bsq_pk_t>(), al->n_intv.as<int32_t>(), al->status.as<int32_t>(),
                                                               al->scalars.as<unsigned long long>());
-  else
+  else if (seed_impl() == 2)
     launch_seed2(seed_variant(), seed_grid(n), s, opt, ix, n, al->seqs.as<uint8_t>(), stride, al->lens.as<int32_t>(), al->parent.as<uint8_t>(), 1,
                  al->intv.as<bsq_pk_t>(), al->n_intv.as<int32_t>(), al->status.as<int32_t>(), al->scalars.as<unsigned long long>());
+  else if ((rc = seed3_run(al->seed_ws, s, opt, ix, n, al->seqs.as<uint8_t>(), stride, al->lens.as<int32_t>(), al->parent.as<uint8_t>(), 1,
+                           al->intv.as<bsq_pk_t>(), al->n_intv.as<int32_t>(), al->seed_fills)))
+    return rc;
   CK(cudaGetLastError());
-  k_seed_sort<<<nblk(n, 128), 128, 0, s>>>(opt, n, al->intv.as<bsq_pk_t>(), al->n_intv.as<int32_t>(), al->n_sa.as<int32_t>());
+  k_seed_sort<<<nblk(n, 128), 128, 0, s>>>(opt, n, al->intv.as<bsq_pk_t>(), al->n_intv.as<int32_t>(), al->n_sa.as<int32_t>(), al->status.as<int32_t>());
   CK(cudaGetLastError());
   CK(cudaEventRecord(al->ev[1], s));
   SNAP(12);

@@ -86,6 +86,8 @@ struct bsq_fm_t {
   const uint64_t *sa;  // sampled SA, sa[0] = (u64)-1 (bwt.c:84,450)
   const uint64_t *full_sa;  // optional: SA of every rank, derived in HBM (180 GB make room for 2 x 8 B x 6.2 G);
                             // replaces the ~31-step LF walk of bwt_sa by one gather; same values by construction
+  const uint32_t *b32;      // derived in HBM: the same ranks as 32-byte blocks (3 x 40-bit cumulative counts + 64 symbols,
+                            // one DRAM sector per lookup), used by the seeding kernels (bsq_seed3.cuh)
   uint64_t primary, seq_len;
   uint64_t L2[5];
   int32_t sa_intv, pad_;

@@ -456,6 +456,7 @@ extern "C" int bsq_index_build(const uint8_t *pac, int64_t l_pac, int32_t n_seqs
     bsq_index_adopt(ix, a); bsq_index_adopt(ix, b); bsq_index_adopt(ix, full);
   }
   ix->build_stats[0] = stats[0]; ix->build_stats[1] = stats[1]; ix->build_stats[2] = stats[2];
+  if ((rc = bsq_index_derive_b32(ix))) goto done;
   *out = ix; ix = nullptr;
 done:
   cudaFree(d_pac);

@@ -28,7 +28,7 @@ def build_hostemu() -> str:
     # the pileup half of the emulation is the oracle's restatement (test-only library: it may link the oracle)
     orc = os.path.join(ROOT, "oracle", "bsq_oracle_pileup.c")
     deps = [src, orc, os.path.join(ROOT, "oracle", "bsq_oracle.h"), os.path.join(ROOT, "include", "bsq.h")]
-    deps += [os.path.join(cs, f) for f in os.listdir(cs) if f.endswith(".h")]
+    deps += [os.path.join(cs, f) for f in os.listdir(cs) if f.endswith((".h", ".cuh"))]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         obj = os.path.join(ROOT, "tests", "hostemu", "bsq_oracle_pileup.o")
         subprocess.check_call(["gcc", "-O2", "-g", "-std=gnu11", "-fPIC", "-c", "-o", obj, orc])

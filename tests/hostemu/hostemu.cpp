@@ -12,6 +12,8 @@
 #include "../../include/bsq.h"
 #include "../../biscuit_b200/csrc/bsq_task.h"
 #include "../../biscuit_b200/csrc/bsq_chain_warp.h"
+#define BSQ_SEED3_HOSTEMU 1
+#include "../../biscuit_b200/csrc/bsq_seed3.cuh"
 
 static_assert(sizeof(bsq_intv) == sizeof(bsq_intv_t), "abi");
 static_assert(sizeof(bsq_reg) == sizeof(bsq_reg_t), "abi");
@@ -69,19 +71,67 @@ int bsq_sa_lookup(const bsq_index *ix, int which, int64_t n, const uint64_t *k, 
   for (int64_t i = 0; i < n; ++i) pos[i] = bsq_sa(ix->d.fm[which], k[i]);
   return 0;
 }
+// the per-pass seeding kernels of bsq_seed3.cuh, each run as one sequential lane: unsorted interval lists
+static int seed3_emulate(const bsq_devidx_t &ix0, const bsq_devopt_t &opt, int64_t n, const uint8_t *seqs, int32_t stride, const int32_t *lens,
+                         const uint8_t *parent, int pipeline, std::vector<bsq_pk_t> &intv, std::vector<int32_t> &n_intv) {
+  bsq_devidx_t ix = ix0;
+  std::vector<uint32_t> b32[2];
+  for (int w = 0; w < 2; ++w) {
+    const uint64_t n_half = 2 * ((ix.fm[w].seq_len + 127) / 128);
+    b32[w].assign((n_half + 1) * 8, 0);
+    blockDim.x = 1; threadIdx.x = 0;
+    for (uint64_t h = 0; h < n_half; ++h) { blockIdx.x = (unsigned)h; k_derive_b32(ix.fm[w].blocks, ix.fm[w].seq_len, n_half, b32[w].data()); }
+    ix.fm[w].b32 = b32[w].data();
+  }
+  long long qcap = 8 * n + 64;
+  if (const char *e = getenv("BSQ_SEED_QCAP")) if (atoll(e) > 0) qcap = atoll(e);
+  intv.assign((size_t)n * BSQ_MAX_INTV, bsq_pk_t());
+  for (int attempt = 0; attempt < 30; ++attempt) {
+    std::vector<uint4> cand1((size_t)n * stride + 1), cand2((size_t)qcap * 8 + 1);
+    std::vector<s3_call_t> calls1(qcap), calls2(qcap);
+    std::vector<s3_item_t> items(qcap);
+    s3_q_t q; memset(&q, 0, sizeof q);
+    n_intv.assign(n, 0);
+    k_s3_fwd<1>(opt, ix, n, seqs, stride, lens, parent, pipeline, cand1.data(), 0ull, nullptr, calls1.data(), (unsigned long long)qcap, items.data(),
+                (unsigned long long)qcap, &q, intv.data(), n_intv.data());
+    k_s3_greedy(opt, ix, n, seqs, stride, lens, parent, pipeline, &q, intv.data(), n_intv.data());
+    k_s3_bwd(opt, ix, seqs, stride, parent, cand1.data(), calls1.data(), (unsigned long long)qcap, 1, items.data(), (unsigned long long)qcap, &q,
+             intv.data(), n_intv.data());
+    k_s3_fwd<2>(opt, ix, n, seqs, stride, lens, parent, pipeline, cand2.data(), (unsigned long long)qcap * 8, items.data(), calls2.data(),
+                (unsigned long long)qcap, items.data(), (unsigned long long)qcap, &q, intv.data(), n_intv.data());
+    k_s3_bwd(opt, ix, seqs, stride, parent, cand2.data(), calls2.data(), (unsigned long long)qcap, 2, items.data(), (unsigned long long)qcap, &q,
+             intv.data(), n_intv.data());
+    if (!q.overflow) return 0;
+    qcap *= 2;  // same policy as the CUDA library: grow the queues and seed the batch again
+  }
+  return BSQ_EOVERFLOW;
+}
+
+static bool pk_less(const bsq_pk_t &a, const bsq_pk_t &b) { return a.w1 != b.w1 ? a.w1 < b.w1 : a.w0 < b.w0; }
+
+// Seeds every task twice -- with the sequential state machine (bsq_seed.h) and with the per-pass kernels the GPU runs
+// (bsq_seed3.cuh) -- and refuses to answer when the two interval multisets differ.
 int bsq_collect_intv(const bsq_index *ix, const bsq_opt *opt_, int64_t n_tasks, const uint8_t *seqs, int32_t stride,
                      const int32_t *lens, const uint8_t *parent, bsq_intv *out, int32_t *n_out) {
   bsq_devopt_t opt; memcpy(&opt, opt_, sizeof opt);
   bsq_seed_scratch_t *scr = new bsq_seed_scratch_t();
   int rc = 0;
-  for (int64_t t = 0; t < n_tasks; ++t) {
-    if (lens[t] > BSQ_MAX_READ_LEN) { rc = BSQ_EINVAL; break; }
+  for (int64_t t = 0; t < n_tasks && !rc; ++t) if (lens[t] > BSQ_MAX_READ_LEN) rc = BSQ_EINVAL;
+  std::vector<bsq_pk_t> intv3; std::vector<int32_t> n3;
+  if (!rc) rc = seed3_emulate(ix->d, opt, n_tasks, seqs, stride, lens, parent, 0, intv3, n3);
+  for (int64_t t = 0; t < n_tasks && !rc; ++t) {
     int32_t n_sa;
     bsq_pk_t pk[BSQ_MAX_INTV];
     int n = bsq_task_seed(opt, ix->d, seqs + t * stride, lens[t], parent[t], false, *scr, pk, &n_sa);
     if (n < 0) { rc = BSQ_EOVERFLOW; break; }
     for (int i = 0; i < n; ++i) ((bsq_intv_t *)out)[t * BSQ_MAX_INTV + i] = bsq_pk_unpack(pk[i]);
     n_out[t] = n;
+    std::vector<bsq_pk_t> a(pk, pk + n), b;
+    if (n3[t] <= BSQ_MAX_INTV) b.assign(intv3.begin() + t * BSQ_MAX_INTV, intv3.begin() + t * BSQ_MAX_INTV + n3[t]);
+    std::sort(a.begin(), a.end(), pk_less); std::sort(b.begin(), b.end(), pk_less);
+    bool same = n3[t] == n;
+    for (int i = 0; same && i < n; ++i) same = a[i].w0 == b[i].w0 && a[i].w1 == b[i].w1;
+    if (!same) { fprintf(stderr, "hostemu: task %lld: per-pass seeding kernels give %d intervals, the state machine %d (or different records)\n", (long long)t, n3[t], n); rc = BSQ_EINVAL; }
   }
   delete scr;
   return rc;

@@ -25,6 +25,10 @@ reads = bench.sim_batch(nt4, names, offs, lens, pairs, seed=2024)
 seqs, tl, par = bench.tasks_from_reads(reads)
 first = None
 for lib in libs:
+    # "lib.so@NAME=VALUE[@NAME=VALUE]" sets environment switches the library reads at launch time (e.g. BSQ_SEED_IMPL=2)
+    lib, *envs = lib.split("@")
+    for kv in envs:
+        os.environ[kv.split("=")[0]] = kv.split("=")[1]
     path = lib if os.path.isabs(lib) else os.path.join(ROOT, lib)
     try:
         bsq = capi.Bsq(path)
@@ -40,10 +44,12 @@ for lib in libs:
             first = dig
         rows = np.array(rows)
         names_k = ["k_seed", "k_sa", "k_chain", "k_region", "scan", "all"]
-        print(json.dumps({"lib": os.path.basename(lib), "identical": dig == first, "n_regs": int(len(regs)),
+        print(json.dumps({"lib": os.path.basename(lib) + "".join("@" + e for e in envs), "identical": dig == first, "n_regs": int(len(regs)),
                           "min_us": dict(zip(names_k, rows.min(axis=0).tolist())), "median_us": dict(zip(names_k, np.median(rows, axis=0).astype(int).tolist()))}),
               flush=True)
         al.close()
         dx.close()
     except Exception as e:  # noqa: BLE001
         print(json.dumps({"lib": os.path.basename(lib), "error": str(e)}), flush=True)
+    for kv in envs:
+        os.environ.pop(kv.split("=")[0], None)
