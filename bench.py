@@ -327,7 +327,7 @@ def main():
             cb.lib.bsq_work_counters(w0.ctypes.data_as(C.c_void_p), C.c_int(8), C.c_int(1))
             al2.phase1(seqs[:nsub], tl[:nsub], par[:nsub])
             cb.lib.bsq_work_counters(w0.ctypes.data_as(C.c_void_p), C.c_int(8), C.c_int(1))
-            work = {k: float(w0[i]) / nsub for i, k in enumerate(["blocks", "extends", "ksw_calls", "cells", "ref_bases"])}
+            work = {k: float(w0[i]) / nsub for i, k in enumerate(["blocks", "extends", "ksw_calls", "cells", "ref_bases", "seed_blocks32"])}
             c2 = al2.counters()
             work["seed_blocks"] = float(c2[12] - c2[11]) / nsub
             work["sa_blocks"] = float(c2[13] - c2[12]) / nsub
@@ -469,7 +469,10 @@ def main():
             # blocks counted over the whole pipeline: seeding extends fetch 1-2 blocks each, every LF step 1 block
             # (instrumented run reports totals; split: SA blocks = total - seed blocks is not separable here, so the
             # roofline of the dominant kernel uses all FM-index block traffic when it is k_seed or k_sa)
-            per_task_bytes["k_seed"] = 64.0 * work["seed_blocks"] + 150 + 32 * 10
+            # seeding gathers 32-byte derived rank blocks (bsq_seed3.cuh): one sector per distinct block of an extension, plus the
+            # read in and the interval records out.  work["seed_blocks"] stays what the same extensions touch in the reference's
+            # 64-byte layout (N_occblk); no credit is taken for those bytes.
+            per_task_bytes["k_seed"] = 32.0 * work["seed_blocks32"] + 150 + 16 * 30
             # with the full suffix array resident (counters[1] == 2) a lookup is rank in, one 8-byte SA entry, position out:
             # no credit for the LF-walk blocks that are no longer fetched
             full_sa = int(counters[1]) == 2
@@ -496,7 +499,21 @@ def main():
                     traffic = kk["dram_read_bytes"] + kk["dram_write_bytes"]
         except Exception:  # noqa: BLE001
             traffic = None
+        # what the memory system delivers for the access pattern of the FM-index kernels: dependent random one-sector gathers
+        # over a footprint of the index's size (measured here, a few hundred ms; tools/micro/gather_peak.cu has the sweep)
+        gather = None
+        try:
+            g = C.c_double()
+            if bsq.lib.bsq_measure_gather(C.c_int(local_rank), C.c_uint64(int(6.2e9)), C.byref(g)) == 0:
+                gather = {"sectors_per_s": g.value, "GBps": g.value * 32 / 1e9, "footprint_gb": 6.2,
+                          "what": "dependent random 32-byte gathers (LDG.E.256), 32 warps/SM, 2 in flight per thread"}
+        except Exception as e:  # noqa: BLE001
+            log("gather probe unavailable:", e)
+        if gather and by_kernel:
+            for k in ("k_seed", "k_expand+k_sa"):
+                by_kernel[k]["frac_of_random_gather_rate"] = by_kernel[k]["alg_GBps"] / gather["GBps"]
         roof = {"bound": "hbm", "kernel": dom_name, "achieved": (alg_bytes / dom_s / 1e9) if alg_bytes else None, "peak": peak,
+                "random_gather": gather,
                 "unit": "GB/s", "frac": (alg_bytes / dom_s / 1e9 / peak) if alg_bytes else None, "traffic": traffic,
                 "peak_source": peak_src, "kernel_ms": kern_us[dom] / 1000, "share_of_step": float(kern_us[dom] / max(kern_us[5], 1)),
                 "work_per_task": work, "by_kernel": by_kernel, "full_sa_resident": int(counters[1]) == 2 if work else None}

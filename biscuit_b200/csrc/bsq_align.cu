@@ -130,7 +130,7 @@ struct bsq_aligner {
   cudaEvent_t ev[8], ev_fork, ev_join;
   DevBuf seqs, lens, parent, intv, n_intv, n_sa, sa_off, ranks, pos, status;
   DevBuf snodes, wchains, bnodes, order, ochains, oseeds, n_chains, frac_rep, srt, regs_tmp, n_regs, reg_off, regs;
-  DevBuf cub_tmp, scalars, fb_flag, tiers;
+  DevBuf cub_tmp, scalars, fb_flag, tiers, spans, aflag;
   int64_t counters[16];
   int64_t n_staged = 0, n_regs_total = -1;
   int64_t fb_cap = 0;  // entries of the fallback-chaining workspace pools
@@ -509,6 +509,47 @@ static int launch_chain_warp(cudaStream_t s, const bsq_devopt_t &opt, const bsq_
   return 0;
 }
 
+// Inputs of k_region that do not depend on the regions found so far, computed one chain / one seed per lane (k_region runs
+// its control flow redundantly in the 32 lanes of the task's warp, so everything done here costs a fraction of what it cost
+// there; measured shares of k_region before: chain loop 14 %, seed sort 7 %, asymmetric filter 13 %, profiles/README.md r02):
+//   spans[2 c], spans[2 c + 1]   reference window of chain c (mem_chain_reference_span + bns_fetch_seq clipping)
+//   srt[seed_off ..]             seed order of mem_chain2region1 (memchain.c:750-757: by score = len, then index; the keys are
+//                                unique, so any sort gives the reference's order), backup seeds behind the main ones
+//   aflag[seed]                  verdict of asymmetric_flt_seed (memchain.c:138-149), one seed per lane
+__global__ void __launch_bounds__(128) k_region_prep(const __grid_constant__ bsq_devopt_t opt, const __grid_constant__ bsq_devidx_t ix, int64_t n_tasks,
+                                                     const uint8_t *seqs, int stride, const int32_t *lens, const int64_t *sa_off, const bsq_chain_t *ochains,
+                                                     const bsq_seed_t *oseeds, const int32_t *n_chains, uint64_t *srt, int64_t *spans, uint8_t *aflag) {
+  bsq_gap_tab_init(opt);
+  struct u64_less { __device__ bool operator()(uint64_t a, uint64_t b) const { return a < b; } };
+  const int lane = threadIdx.x & 31;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_tasks; t += n_warps) {
+    const int64_t wo = ws_off(sa_off, t);
+    const int nc = n_chains[t], lq = lens[t];
+    const uint8_t *query = seqs + t * stride;
+    int n_seeds_task = 0;  // the chains' seed slices tile the task's seed pool from 0
+    for (int ci = lane; ci < nc; ci += 32) {
+      const bsq_chain_t c = ochains[wo + ci];
+      if (c.n_seeds == 0) continue;
+      const bsq_seed_t *cs = oseeds + wo + c.seed_off;
+      const int e = c.seed_off + c.n_seeds + c.n_extra;
+      n_seeds_task = n_seeds_task > e ? n_seeds_task : e;
+      int64_t r0, r1;
+      bsq_chain_span<bsq_warp_policy>(opt, ix, lq, c, cs, r0, r1);
+      spans[2 * (wo + ci)] = r0; spans[2 * (wo + ci) + 1] = r1;
+      for (int part = 0; part < 2; ++part) {
+        const bsq_seed_t *sd = part ? cs + c.n_seeds : cs;
+        const int n = part ? c.n_extra : c.n_seeds;
+        uint64_t *keys = srt + wo + c.seed_off + (part ? c.n_seeds : 0);
+        for (int i = 0; i < n; ++i) keys[i] = (uint64_t)(uint32_t)sd[i].len << 32 | (uint32_t)i;
+        if (n > 1) bsq_introsort(keys, (int64_t)n, u64_less());
+      }
+    }
+    n_seeds_task = __reduce_max_sync(0xffffffffu, n_seeds_task);
+    for (int j = lane; j < n_seeds_task; j += 32) aflag[wo + j] = bsq_asym_seed(ix, oseeds[wo + j], query) ? 1 : 0;
+  }
+}
+
 // Chains -> regions, one WARP per task: the control flow of mem_chain2region runs uniformly in all
 // lanes, every banded extension is spread over the lanes (bsq_ksw_warp.cuh), lane 0 stores.
 #ifndef BSQ_REGION_CTAS
@@ -517,7 +558,8 @@ static int launch_chain_warp(cudaStream_t s, const bsq_devopt_t &opt, const bsq_
 __global__ void __launch_bounds__(128, BSQ_REGION_CTAS) k_region(const __grid_constant__ bsq_devopt_t opt, const __grid_constant__ bsq_devidx_t ix, int64_t n_tasks, const uint8_t *seqs, int stride,
                                                 const int32_t *lens, const uint8_t *parent, const int64_t *sa_off,
                                                 const bsq_chain_t *ochains, const bsq_seed_t *oseeds, const int32_t *n_chains,
-                                                const float *frac_rep, uint64_t *srt, bsq_reg_t *regs_tmp, int32_t *n_regs, unsigned long long *cursor) {
+                                                const float *frac_rep, uint64_t *srt, const int64_t *spans, const uint8_t *aflag, bsq_reg_t *regs_tmp, int32_t *n_regs,
+                                                unsigned long long *cursor) {
   bsq_gap_tab_init(opt);
   for (;;) {  // persistent warps: one wave of resident CTAs, every warp pulls the next task (see k_chain_warp)
     unsigned long long t_ = 0;
@@ -525,8 +567,8 @@ __global__ void __launch_bounds__(128, BSQ_REGION_CTAS) k_region(const __grid_co
     const int64_t t = (int64_t)__shfl_sync(0xffffffffu, t_, 0);
     if (t >= n_tasks) return;  // whole warps leave together
     const int64_t wo = ws_off(sa_off, t);
-    const int n = bsq_chain2region<bsq_warp_policy>(opt, ix, parent[t], lens[t], seqs + t * stride, ochains + wo, n_chains[t], oseeds + wo,
-                                                    frac_rep[t], srt + wo, nullptr, regs_tmp + wo);
+    const int n = bsq_chain2region<bsq_warp_policy, true>(opt, ix, parent[t], lens[t], seqs + t * stride, ochains + wo, n_chains[t], oseeds + wo,
+                                                          frac_rep[t], srt + wo, nullptr, regs_tmp + wo, spans + 2 * wo, aflag + wo);
     if ((threadIdx.x & 31) == 0) n_regs[t] = n;
   }
 }
@@ -607,7 +649,7 @@ static int seed3_run(SeedWs &ws, cudaStream_t s, const bsq_devopt_t &opt, const 
   if (ws.calls2_cap < ws.items_cap) ws.calls2_cap = ws.items_cap;
   if (ws.cand2_cap < n * (int64_t)stride) ws.cand2_cap = n * (int64_t)stride;
   { const char *e = getenv("BSQ_SEED_QCAP"); if (e && atoll(e) > 0 && fills) { ws.calls1_cap = ws.calls2_cap = ws.items_cap = atoll(e); ws.cand2_cap = 64 * atoll(e); } }  // test hook: force the retry path
-  const unsigned grid = (unsigned)((n + 127) / 128 < 148 * 8 ? (n + 127) / 128 : 148 * 8);
+  const unsigned grid = (unsigned)((n + 127) / 128 < 148 * BSQ_S3_CTAS ? (n + 127) / 128 : 148 * BSQ_S3_CTAS);
   for (int attempt = 0; attempt < 12; ++attempt) {
     if ((rc = ws.cand1.reserve((size_t)n * stride * 16))) return rc;
     if ((rc = ws.cand2.reserve((size_t)ws.cand2_cap * 16))) return rc;
@@ -839,7 +881,7 @@ void bsq_aligner_destroy(bsq_aligner *al) {
   cudaSetDevice(al->idx->device);
   DevBuf *bufs[] = {&al->seqs, &al->lens, &al->parent, &al->intv, &al->n_intv, &al->n_sa, &al->sa_off, &al->ranks, &al->pos,
                     &al->status, &al->snodes, &al->wchains, &al->bnodes, &al->order, &al->ochains, &al->oseeds, &al->n_chains,
-                    &al->frac_rep, &al->srt, &al->regs_tmp, &al->n_regs, &al->reg_off, &al->regs, &al->cub_tmp, &al->scalars, &al->fb_flag, &al->tiers};
+                    &al->frac_rep, &al->srt, &al->regs_tmp, &al->n_regs, &al->reg_off, &al->regs, &al->cub_tmp, &al->scalars, &al->fb_flag, &al->tiers, &al->spans, &al->aflag};
   for (DevBuf *b : bufs) b->release();
   al->seed_ws.release();
   for (int i = 0; i < 8; ++i) cudaEventDestroy(al->ev[i]);
@@ -924,7 +966,7 @@ static int phase1_device(bsq_aligner *al, int64_t n, int32_t stride, int64_t *to
   RES(snodes, fb_cap * sizeof(bsq_snode_t)); RES(wchains, fb_cap * sizeof(bsq_wchain_t));
   RES(bnodes, fb_cap * sizeof(bsq_bnode_t)); RES(order, fb_cap * 4);
   RES(ochains, pool * sizeof(bsq_chain_t)); RES(oseeds, pool * sizeof(bsq_seed_t));
-  RES(srt, pool * 8); RES(regs_tmp, pool * sizeof(bsq_reg_t));
+  RES(srt, pool * 8); RES(regs_tmp, pool * sizeof(bsq_reg_t)); RES(spans, pool * 16); RES(aflag, pool);
   CK(cudaEventRecord(al->ev[2], s));
   k_expand<<<nblk(n, 128), 128, 0, s>>>(opt, n, al->intv.as<bsq_pk_t>(), al->n_intv.as<int32_t>(), al->parent.as<uint8_t>(),
                                          al->sa_off.as<int64_t>(), al->ranks.as<uint64_t>());
@@ -987,9 +1029,12 @@ static int phase1_device(bsq_aligner *al, int64_t n, int32_t stride, int64_t *to
   CK(cudaEventRecord(al->ev[4], s));
   {
     const unsigned want = nblk(n * 32, 128), wave = (unsigned)(bsq_sm_count() * BSQ_REGION_CTAS);
+    k_region_prep<<<nblk(n * 32, 128), 128, 0, s>>>(opt, ix, n, al->seqs.as<uint8_t>(), stride, al->lens.as<int32_t>(), al->sa_off.as<int64_t>(),
+                                                    al->ochains.as<bsq_chain_t>(), al->oseeds.as<bsq_seed_t>(), al->n_chains.as<int32_t>(),
+                                                    al->srt.as<uint64_t>(), al->spans.as<int64_t>(), al->aflag.as<uint8_t>());
     k_region<<<want < wave ? want : wave, 128, 0, s>>>(opt, ix, n, al->seqs.as<uint8_t>(), stride, al->lens.as<int32_t>(), al->parent.as<uint8_t>(),
                                                        al->sa_off.as<int64_t>(), al->ochains.as<bsq_chain_t>(), al->oseeds.as<bsq_seed_t>(),
-                                                       al->n_chains.as<int32_t>(), al->frac_rep.as<float>(), al->srt.as<uint64_t>(),
+                                                       al->n_chains.as<int32_t>(), al->frac_rep.as<float>(), al->srt.as<uint64_t>(), al->spans.as<int64_t>(), al->aflag.as<uint8_t>(),
                                                        al->regs_tmp.as<bsq_reg_t>(), al->n_regs.as<int32_t>(), al->scalars.as<unsigned long long>() + 24);
   }
   CK(cudaGetLastError());
@@ -1098,6 +1143,43 @@ int bsq_work_counters(uint64_t *out, int n, int reset) {
   snprintf(g_err, sizeof g_err, "libbsq.so is not instrumented; use libbsq_count.so");
   return BSQ_EINVAL;
 #endif
+}
+
+__global__ void __launch_bounds__(128) k_gather_probe(const uint32_t *buf, uint64_t n_units, int iters, uint32_t *out) {
+  uint64_t s = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull + 12345;
+  uint32_t acc = 0;
+  for (int it = 0; it < iters; ++it) {
+    uint32_t w0[8], w1[8];
+    s = s * 6364136223846793005ull + 1442695040888963407ull;
+    s3_ld256(buf + ((s >> 20) % n_units) * 8, w0);
+    s = s * 6364136223846793005ull + 1442695040888963407ull;
+    s3_ld256(buf + ((s >> 20) % n_units) * 8, w1);
+    acc ^= w0[0] + w0[7] + w1[0] + w1[7];
+    s += acc & 1;  // the next addresses depend on the data, like an FM-index walk
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+int bsq_measure_gather(int device, uint64_t bytes, double *gathers_per_s) {
+  if (!gathers_per_s || bytes < (1u << 20)) return BSQ_EINVAL;
+  CK(cudaSetDevice(device));
+  uint32_t *buf = nullptr, *out = nullptr;
+  const int grid = bsq_sm_count() * 8, iters = 1000;
+  CK(cudaMalloc(&buf, bytes));
+  CK(cudaMalloc(&out, (size_t)grid * 128 * 4));
+  CK(cudaMemset(buf, 1, bytes));
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+  k_gather_probe<<<grid, 128>>>(buf, bytes / 32, iters / 10, out);
+  CK(cudaEventRecord(a));
+  k_gather_probe<<<grid, 128>>>(buf, bytes / 32, iters, out);
+  CK(cudaEventRecord(b));
+  CK(cudaEventSynchronize(b));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, a, b));
+  *gathers_per_s = (double)grid * 128 * iters * 2 / (ms * 1e-3);
+  cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(buf); cudaFree(out);
+  return 0;
 }
 
 int bsq_host_alloc(void **p, size_t bytes) {

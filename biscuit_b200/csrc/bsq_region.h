@@ -67,22 +67,44 @@ struct bsq_scalar_policy {
   }
 };
 
+// What k_region_prep (bsq_align.cu) computes ahead of k_region, one chain / one seed per lane instead of redundantly in all
+// 32 lanes of the task's warp: the seed order of mem_chain2region1 (keys of one chain in srt[seed_off ..], backup seeds
+// behind the main ones), the verdict of asymmetric_flt_seed for every seed (aflag[], indexed like the seeds), and the
+// chain's reference span.
+
+// asymmetric_flt_seed (memchain.c:138-149) for one seed, one thread: ref T under read C, or ref A under read G
+BSQ_HD bool bsq_asym_seed(const bsq_devidx_t &ix, const bsq_seed_t &s, const uint8_t *query) {
+  const bool rev = s.rbeg >= ix.l_pac;  // a seed never spans the strand boundary (memchain.c:339)
+  int64_t f = rev ? (ix.l_pac << 1) - 1 - s.rbeg : s.rbeg;  // forward coordinate of the first base; the reverse strand reads backwards
+  const int step = rev ? -1 : 1, comp = rev ? 3 : 0;
+  const uint8_t *q = query + s.qbeg;
+  for (int b = 0; b < s.len; ++b, f += step) {
+    const int r = (ix.pac[f >> 2] >> ((~f & 3) << 1) & 3) ^ comp, qv = q[b];
+    if ((r == 3 && qv == 1) || (r == 0 && qv == 2)) return true;
+  }
+  return false;
+}
+
 // mem_chain2region1 for one seed list.  regs[reg0..*n_regs) are the regions of this task so far.
-template <typename X>
+// PREP: srt[0..n_seeds) already holds the sorted keys and aflag[i] the asymmetric-filter verdict of seeds[i].
+template <typename X, bool PREP = false>
 BSQ_HD void bsq_chain2region1(const bsq_devopt_t &opt, const bsq_devidx_t &ix, int64_t rmax0, int64_t rmax1, int rid,
                               int l_query, const uint8_t *query, const bsq_seed_t *seeds, int n_seeds, int parent,
-                              float frac_rep, uint64_t *srt, bsq_ksw_scratch_t *ksw, bsq_reg_t *regs, int *n_regs) {
+                              float frac_rep, uint64_t *srt, bsq_ksw_scratch_t *ksw, bsq_reg_t *regs, int *n_regs, const uint8_t *aflag = nullptr) {
   const int8_t *mat = parent ? opt.ctmat : opt.gamat;
   struct u64_less { BSQ_HD bool operator()(uint64_t a, uint64_t b) const { return a < b; } };
-  if (X::leader()) {
-    for (int i = 0; i < n_seeds; ++i) srt[i] = (uint64_t)(uint32_t)seeds[i].len << 32 | (uint32_t)i;  // score == len
-    bsq_introsort(srt, (int64_t)n_seeds, u64_less());
+  if (!PREP) {
+    if (X::leader()) {
+      for (int i = 0; i < n_seeds; ++i) srt[i] = (uint64_t)(uint32_t)seeds[i].len << 32 | (uint32_t)i;  // score == len
+      bsq_introsort(srt, (int64_t)n_seeds, u64_less());
+    }
+    X::sync();
   }
-  X::sync();
   for (int k = n_seeds - 1; k >= 0; --k) {
-    const bsq_seed_t &s = seeds[(uint32_t)srt[k]];
+    const uint64_t key = srt[k];
+    const bsq_seed_t &s = seeds[(uint32_t)key];
     // asymmetric_flt_seed: reject ref T/read C and ref A/read G inside the seed
-    if (X::asym_conflict(ix, s, query)) continue;
+    if (PREP ? aflag[(uint32_t)key] != 0 : X::asym_conflict(ix, s, query)) continue;
     // was this seed already covered by an earlier extension?
     int u;
     for (u = 0; u < *n_regs; ++u) {
@@ -185,18 +207,12 @@ BSQ_HD void bsq_chain2region1(const bsq_devopt_t &opt, const bsq_devidx_t &ix, i
   }
 }
 
-// mem_chain2region for one task.  Returns the number of regions written to regs[].
+// mem_chain_reference_span (memchain.c:585-605) + the clipping of bns_fetch_seq (bntseq.c:428-452) for one chain
 template <typename X>
-BSQ_HD int bsq_chain2region(const bsq_devopt_t &opt, const bsq_devidx_t &ix, int parent, int l_query, const uint8_t *query,
-                            const bsq_chain_t *chains, int n_chains, const bsq_seed_t *seeds, float frac_rep,
-                            uint64_t *srt, bsq_ksw_scratch_t *ksw, bsq_reg_t *regs) {
-  int n_regs = 0;
+BSQ_HD void bsq_chain_span(const bsq_devopt_t &opt, const bsq_devidx_t &ix, int l_query, const bsq_chain_t &c, const bsq_seed_t *cs, int64_t &rmax0_out,
+                           int64_t &rmax1_out) {
   const int64_t l_pac = ix.l_pac;
-  for (int ci = 0; ci < n_chains; ++ci) {
-    const bsq_chain_t &c = chains[ci];
-    if (c.n_seeds == 0) continue;
-    const bsq_seed_t *cs = seeds + c.seed_off;
-    // mem_chain_reference_span
+  {
     int64_t rmax0 = l_pac << 1, rmax1 = 0;
     for (int i = 0; i < c.n_seeds; ++i) {
       const bsq_seed_t &s = cs[i];
@@ -222,11 +238,31 @@ BSQ_HD int bsq_chain2region(const bsq_devopt_t &opt, const bsq_devidx_t &ix, int
     }
     rmax0 = rmax0 > far_beg ? rmax0 : far_beg;
     rmax1 = rmax1 < far_end ? rmax1 : far_end;
+    rmax0_out = rmax0; rmax1_out = rmax1;
+  }
+}
+
+// mem_chain2region for one task.  Returns the number of regions written to regs[].
+// PREP: spans[2 ci], spans[2 ci + 1] and the srt slices of every chain were filled by k_region_prep.
+template <typename X, bool PREP = false>
+BSQ_HD int bsq_chain2region(const bsq_devopt_t &opt, const bsq_devidx_t &ix, int parent, int l_query, const uint8_t *query,
+                            const bsq_chain_t *chains, int n_chains, const bsq_seed_t *seeds, float frac_rep,
+                            uint64_t *srt, bsq_ksw_scratch_t *ksw, bsq_reg_t *regs, const int64_t *spans = nullptr, const uint8_t *aflag = nullptr) {
+  int n_regs = 0;
+  for (int ci = 0; ci < n_chains; ++ci) {
+    const bsq_chain_t &c = chains[ci];
+    if (c.n_seeds == 0) continue;
+    const bsq_seed_t *cs = seeds + c.seed_off;
+    int64_t rmax0, rmax1;
+    if (PREP) { rmax0 = spans[2 * ci]; rmax1 = spans[2 * ci + 1]; }
+    else bsq_chain_span<X>(opt, ix, l_query, c, cs, rmax0, rmax1);
+    const int rid = c.rid;
     const int n0 = n_regs;
-    bsq_chain2region1<X>(opt, ix, rmax0, rmax1, rid, l_query, query, cs, c.n_seeds, parent, frac_rep, srt, ksw, regs, &n_regs);
+    bsq_chain2region1<X, PREP>(opt, ix, rmax0, rmax1, rid, l_query, query, cs, c.n_seeds, parent, frac_rep, PREP ? srt + c.seed_off : srt, ksw, regs,
+                               &n_regs, PREP ? aflag + c.seed_off : nullptr);
     if (n_regs == n0 && c.n_extra > 0)
-      bsq_chain2region1<X>(opt, ix, rmax0, rmax1, rid, l_query, query, cs + c.n_seeds, c.n_extra, parent, frac_rep, srt, ksw,
-                        regs, &n_regs);
+      bsq_chain2region1<X, PREP>(opt, ix, rmax0, rmax1, rid, l_query, query, cs + c.n_seeds, c.n_extra, parent, frac_rep,
+                                 PREP ? srt + c.seed_off + c.n_seeds : srt, ksw, regs, &n_regs, PREP ? aflag + c.seed_off + c.n_seeds : nullptr);
   }
   return n_regs;
 }

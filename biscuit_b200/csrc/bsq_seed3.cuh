@@ -53,6 +53,11 @@ template <typename T> static inline T __ldg(const T *p) { return *p; }
 static inline bool __all_sync(unsigned, bool p) { return p; }
 #endif
 
+#ifndef BSQ_S3_CTAS
+#define BSQ_S3_CTAS 4  // resident CTAs of 128 threads per SM the seeding kernels run with.  Measured 8: 33.2, 7: 30.5, 6: 27.9, 5: 25.7, 4: 23.7, 3: 25.4 ms per 400 k tasks
+                       // (profiles/kab_r02_l.jsonl, _m): the kernels sit at the random-sector rate of the DRAM (tools/micro/gather_peak.cu), and with fewer lanes in flight
+                       // the candidate lists are re-read from L2 before the index traffic evicts them
+#endif
 #define BSQ_CTR_BLOCKS32 5  // 32-byte derived blocks fetched (distinct per extension)
 
 // ---- derived block: w[0..2] = low words of S1,S2,S3 (S_c = number of symbols >= c before the block), w[3] = their
@@ -158,6 +163,7 @@ __device__ __forceinline__ void s3_extend(const s3_fm_t &f, uint64_t L2c1 /* L2[
   s3_ld256(f.b32 + (l2 >> 6) * 8, wl);
   BSQ_CTR(BSQ_CTR_EXTENDS, 1);
   BSQ_CTR(BSQ_CTR_BLOCKS32, 1 + ((k2 >> 6) != (l2 >> 6)));
+  BSQ_CTR(BSQ_CTR_BLOCKS, 1 + ((k2 >> 7) != (l2 >> 7)));  // what bwt_2occ4 touches in the reference's 64-byte layout (N_occblk)
   const s3_sym_t s = s3_sym(c);
   uint64_t ek, gk, el, gl;
   s3_rank(wk, k2, s, ek, gk);
@@ -193,18 +199,62 @@ struct s3_q_t {
   unsigned long long next_task, n_calls1, next_call1, n_items, next_item, cand2_used, next_task3, overflow, n_calls2, next_call2;
 };
 
-// base i of the read as it is searched: in-silico conversion of bseq_bsconvert (bwamem.c:161-178)
+// base i of the read as it is searched: in-silico conversion of bseq_bsconvert (bwamem.c:161-178); 4 outside the read
 __device__ __forceinline__ int s3_q(const uint8_t *row, int i, int par) {
   const int c = __ldg(row + i);
   return par ? (c == 1 ? 3 : c) : (c == 2 ? 0 : c);
 }
+__device__ __forceinline__ int s3_qs(const uint8_t *row, int i, int len, int par) { return i >= 0 && i < len ? s3_q(row, i, par) : 4; }
 
-// an SMEM of the task: appended to its list; pass 1 also queues the re-seeding of long, rare SMEMs (memchain.c:79-81)
-__device__ __forceinline__ void s3_emit(const bsq_devopt_t &opt, bsq_pk_t *intv, int32_t *n_intv, uint32_t t, uint64_t x0, uint64_t x1, uint64_t x2,
-                                        int beg, int end, bool pass1, s3_item_t *items, unsigned long long items_cap, s3_q_t *q) {
+// Atomics whose result is not needed at once.  A lane that reserves a slot (interval list of a task, work queue) does
+// so from divergent code; if the reservation were used on the spot the whole warp would sit out the round trip to L2
+// in every iteration (measured: a third of the stall samples of the first version, profiles/README.md r02).  The
+// reservation is issued, the record kept in registers, and the store done at the top of the next iteration, by which
+// time the FM-index gather of that iteration has covered the latency.  (Inline PTX: the compiler would turn
+// atomicAdd on a common address into a warp-aggregated one whose shuffle needs the result immediately.)
+__device__ __forceinline__ int s3_reserve32(int32_t *p) {
+#if defined(__CUDACC__)
+  int r;
+  asm volatile("atom.global.add.s32 %0, [%1], 1;" : "=r"(r) : "l"(p) : "memory");
+  return r;
+#else
+  return (*p)++;
+#endif
+}
+__device__ __forceinline__ unsigned long long s3_reserve64(unsigned long long *p) {
+#if defined(__CUDACC__)
+  unsigned long long r;
+  asm volatile("atom.global.add.u64 %0, [%1], 1;" : "=l"(r) : "l"(p) : "memory");
+  return r;
+#else
+  return (*p)++;
+#endif
+}
+
+// an SMEM waiting for its slot in the task's interval list
+struct s3_pend_t {
+  bsq_pk_t rec;
+  uint32_t task;
+  int slot;
+  bool on;
+};
+__device__ __forceinline__ void s3_pend_flush(s3_pend_t &pe, bsq_pk_t *intv) {
+  if (pe.on) {
+    if (pe.slot < BSQ_MAX_INTV) intv[(size_t)pe.task * BSQ_MAX_INTV + pe.slot] = pe.rec;
+    pe.on = false;
+  }
+}
+
+// an SMEM of the task [beg, end): reserve its slot (stored by s3_pend_flush); pass 1 also queues the re-seeding of long,
+// rare SMEMs (memchain.c:79-81)
+__device__ __forceinline__ void s3_emit(const bsq_devopt_t &opt, s3_pend_t &pe, bsq_pk_t *intv, int32_t *n_intv, uint32_t t, uint64_t x0, uint64_t x1,
+                                        uint64_t x2, int beg, int end, bool pass1, s3_item_t *items, unsigned long long items_cap, s3_q_t *q) {
   if (end - beg < opt.min_seed_len) return;  // memchain.c:69-71
-  const int slot = atomicAdd(n_intv + t, 1);
-  if (slot < BSQ_MAX_INTV) intv[(size_t)t * BSQ_MAX_INTV + slot] = bsq_pk_make(x0, x1, x2, beg, end);
+  s3_pend_flush(pe, intv);
+  pe.slot = s3_reserve32(n_intv + t);
+  pe.rec = bsq_pk_make(x0, x1, x2, beg, end);
+  pe.task = t;
+  pe.on = true;
   if (pass1 && end - beg >= opt.split_len && x2 <= (uint64_t)opt.split_width) {
     const unsigned long long k = atomicAdd(&q->n_items, 1ull);
     if (k < items_cap) { s3_item_t it; it.task = t; it.xm = (uint32_t)((beg + end) >> 1) | (uint32_t)(x2 + 1) << 9; items[k] = it; }
@@ -215,24 +265,35 @@ __device__ __forceinline__ void s3_emit(const bsq_devopt_t &opt, bsq_pk_t *intv,
 // Forward sweep(s) (bwt.c:324-343).  PASS 1: one lane per task runs the forward sweeps of all its bwt_smem1a calls
 // back to back (memchain.c:65-73).  PASS 2: one lane per re-seeding item.  A call whose backward sweep is trivial
 // (x == 0 or an ambiguous base at x - 1: every candidate stops at once and only the longest is kept,
-// bwt.c:350-356) emits its SMEM here.
+// bwt.c:350-356) emits its SMEM here.  The base of the next step is loaded one step ahead.
 template <int PASS>
-__global__ void __launch_bounds__(128, 8) k_s3_fwd(const __grid_constant__ bsq_devopt_t opt, const __grid_constant__ bsq_devidx_t ix, int64_t n_tasks,
+__global__ void __launch_bounds__(128, BSQ_S3_CTAS) k_s3_fwd(const __grid_constant__ bsq_devopt_t opt, const __grid_constant__ bsq_devidx_t ix, int64_t n_tasks,
                                                    const uint8_t *seqs, int stride, const int32_t *lens, const uint8_t *parent, int pipeline,
                                                    uint4 *cand, unsigned long long cand_cap, const s3_item_t *items_in, s3_call_t *calls,
                                                    unsigned long long calls_cap, s3_item_t *items, unsigned long long items_cap, s3_q_t *q,
                                                    bsq_pk_t *intv, int32_t *n_intv) {
   unsigned long long *const n_calls = PASS == 1 ? &q->n_calls1 : &q->n_calls2;
   const int start_width = opt.self_ovlp ? 2 : 1;
-  bool need = true, exhausted = false;
+  bool need = true, exhausted = false, triv = false;
   int64_t t = -1;
-  int len = 0, par = 0, x = 0, i = 0, ik_end = 0, npush = 0, min_intv = 1;
+  int len = 0, par = 0, x = 0, i = 0, ik_end = 0, npush = 0, min_intv = 1, c_cur = 4, c_nx = 4;
   uint64_t ik0 = 0, ik1 = 0, ik2 = 0, cbase = 0;
   const uint8_t *row = nullptr;
   s3_fm_t f; f.b32 = nullptr; f.primary = 0;
+  s3_pend_t pe; pe.on = false; pe.slot = 0; pe.task = 0; pe.rec.w0 = pe.rec.w1 = 0;
+  // a call waiting for its slot in the queue
+  bool cl_on = false;
+  unsigned long long cl_k = 0;
+  s3_call_t cl; cl.task = 0; cl.xt = 0; cl.cand = 0;
   unsigned long long n_in = 0;
   if (PASS == 2) n_in = q->n_items < items_cap ? q->n_items : items_cap;
   for (;;) {
+    s3_pend_flush(pe, intv);
+    if (cl_on) {
+      if (cl_k < calls_cap) calls[cl_k] = cl;
+      else atomicOr(&q->overflow, PASS == 1 ? 4ull : 8ull);
+      cl_on = false;
+    }
     if (need && !exhausted) {  // ---- refill (divergent): next call of the task, or the next task / item
       for (;;) {
         if (t < 0) {
@@ -262,6 +323,8 @@ __global__ void __launch_bounds__(128, 8) k_s3_fwd(const __grid_constant__ bsq_d
         if (x >= len || c > 3) { t = -1; continue; }
         ik0 = ix.fm[par].L2[c] + 1; ik2 = ix.fm[par].L2[c + 1] - ix.fm[par].L2[c]; ik1 = ix.fm[!par].L2[3 - c] + 1;  // bwt_set_intv
         ik_end = x + 1; i = x + 1; npush = 0;
+        triv = x == 0 || s3_q(row, x - 1, par) > 3;
+        c_cur = s3_qs(row, i, len, par); c_nx = s3_qs(row, i + 1, len, par);
         need = false;
         break;
       }
@@ -269,9 +332,8 @@ __global__ void __launch_bounds__(128, 8) k_s3_fwd(const __grid_constant__ bsq_d
     if (__all_sync(0xffffffffu, exhausted)) break;
     // ---- one forward step (convergent)
     const bool act = !need;
-    int c = 4;
-    if (act && i < len) c = s3_q(row, i, par);
-    const bool ext = act && c <= 3;
+    const int c = act ? c_cur : 4;
+    const bool ext = c <= 3;
     uint64_t o0 = 0, o1 = 0, o2 = 0;
     if (ext) s3_extend(f, ix.fm[!par].L2[3 - c] + 1, ik1, ik0, ik2, 3 - c, o1, o0, o2);
     if (act) {
@@ -281,17 +343,16 @@ __global__ void __launch_bounds__(128, 8) k_s3_fwd(const __grid_constant__ bsq_d
         ++npush;
         fin = !ext || o2 < (uint64_t)min_intv;
       }
-      if (!fin) { ik0 = o0; ik1 = o1; ik2 = o2; ik_end = i + 1; ++i; }
-      else {
-        const bool trivial = x == 0 || s3_q(row, x - 1, par) > 3;
-        if (trivial) s3_emit(opt, intv, n_intv, (uint32_t)t, ik0, ik1, ik2, x, ik_end, PASS == 1, items, items_cap, q);
+      if (!fin) {
+        ik0 = o0; ik1 = o1; ik2 = o2; ik_end = i + 1; ++i;
+        c_cur = c_nx; c_nx = s3_qs(row, i + 1, len, par);
+      } else {
+        if (triv) s3_emit(opt, pe, intv, n_intv, (uint32_t)t, ik0, ik1, ik2, x, ik_end, PASS == 1, items, items_cap, q);
         else {
-          const unsigned long long k = atomicAdd(n_calls, 1ull);
-          if (k < calls_cap) {
-            s3_call_t cl; cl.task = (uint32_t)t; cl.cand = (cbase + (uint64_t)x) | (uint64_t)min_intv << 40;
-            cl.xt = (uint32_t)x | (uint32_t)npush << 9 | (PASS == 2 ? 1u << 31 : 0u);
-            calls[k] = cl;
-          } else atomicOr(&q->overflow, 4ull);
+          cl_k = s3_reserve64(n_calls);
+          cl.task = (uint32_t)t; cl.cand = (cbase + (uint64_t)x) | (uint64_t)min_intv << 40;
+          cl.xt = (uint32_t)x | (uint32_t)npush << 9 | (PASS == 2 ? 1u << 31 : 0u);
+          cl_on = true;
         }
         need = true;
         if (PASS == 1) x = ik_end; else t = -1;  // bwt.c:343: the next call starts where this sweep stopped
@@ -301,8 +362,10 @@ __global__ void __launch_bounds__(128, 8) k_s3_fwd(const __grid_constant__ bsq_d
 }
 
 // Backward sweep of one call (bwt.c:346-364): candidates, longest match first, are extended to the left column by
-// column; the list is compacted in place (entry n_curr <= j is written after entry j was read).
-__global__ void __launch_bounds__(128, 8) k_s3_bwd(const __grid_constant__ bsq_devopt_t opt, const __grid_constant__ bsq_devidx_t ix,
+// column; the list is compacted in place (entry n_curr <= j is written after entry j was read).  The next candidate
+// of a column is loaded one step ahead, the first candidate of the next column is the first record kept in this one
+// (held in registers), and the base of the next column is loaded when the current column starts.
+__global__ void __launch_bounds__(128, BSQ_S3_CTAS) k_s3_bwd(const __grid_constant__ bsq_devopt_t opt, const __grid_constant__ bsq_devidx_t ix,
                                                    const uint8_t *seqs, int stride, const uint8_t *parent, uint4 *cand, const s3_call_t *calls,
                                                    unsigned long long calls_cap, int pass, s3_item_t *items,
                                                    unsigned long long items_cap, s3_q_t *q, bsq_pk_t *intv, int32_t *n_intv) {
@@ -310,15 +373,17 @@ __global__ void __launch_bounds__(128, 8) k_s3_bwd(const __grid_constant__ bsq_d
   const unsigned long long n_made = pass == 1 ? q->n_calls1 : q->n_calls2;
   bool need = true, exhausted = false, pass1 = true, any = false;
   uint32_t t = 0;
-  int par = 0, i = 0, j = 0, n_prev = 0, n_curr = 0, top = 0, last_beg = 0, min_intv = 1, c = 4;
+  int par = 0, i = 0, j = 0, n_prev = 0, n_curr = 0, top = 0, last_beg = 0, min_intv = 1, c = 4, c_nx = 4;
   uint64_t last_x2 = 0;
   uint4 *lst = nullptr;
   const uint8_t *row = nullptr;
   s3_fm_t f; f.b32 = nullptr; f.primary = 0;
-  uint4 nxt = make_uint4(0, 0, 0, 0);
+  uint4 nxt = make_uint4(0, 0, 0, 0), first = make_uint4(0, 0, 0, 0);
   bool nxt_ok = false;
+  s3_pend_t pe; pe.on = false; pe.slot = 0; pe.task = 0; pe.rec.w0 = pe.rec.w1 = 0;
   const unsigned long long n_calls = n_made < calls_cap ? n_made : calls_cap;
   for (;;) {
+    s3_pend_flush(pe, intv);
     if (need && !exhausted) {
       const unsigned long long k = atomicAdd(next_call, 1ull);
       if (k >= n_calls) exhausted = true;
@@ -333,6 +398,7 @@ __global__ void __launch_bounds__(128, 8) k_s3_bwd(const __grid_constant__ bsq_d
         f.b32 = ix.fm[par].b32; f.primary = ix.fm[par].primary;
         i = x - 1; j = 0; n_prev = top; n_curr = 0; any = false; nxt_ok = false;
         c = s3_q(row, i, par);  // x >= 1: trivial calls never get here
+        c_nx = i > 0 ? s3_q(row, i - 1, par) : 4;
         need = false;
       }
     }
@@ -351,35 +417,43 @@ __global__ void __launch_bounds__(128, 8) k_s3_bwd(const __grid_constant__ bsq_d
     if (act) {
       if (!ext || o2 < (uint64_t)min_intv) {  // cannot be extended: an SMEM unless contained in a longer one (bwt.c:350-356)
         if (n_curr == 0 && (!any || i + 1 < last_beg)) {
-          s3_emit(opt, intv, n_intv, t, x0, x1, x2, i + 1, s3_end(p), pass1, items, items_cap, q);
+          s3_emit(opt, pe, intv, n_intv, t, x0, x1, x2, i + 1, s3_end(p), pass1, items, items_cap, q);
           last_beg = i + 1; any = true;
         }
       } else if (n_curr == 0 || o2 != last_x2) {
-        lst[top - 1 - n_curr] = s3_pack(o0, o1, o2, s3_end(p));
+        const uint4 rec = s3_pack(o0, o1, o2, s3_end(p));
+        lst[top - 1 - n_curr] = rec;
+        if (n_curr == 0) first = rec;
         ++n_curr; last_x2 = o2;
       }
       ++j;
       if (j == n_prev) {  // next column (bwt.c:362-363)
         if (n_curr == 0) need = true;
-        else { n_prev = n_curr; n_curr = 0; --i; j = 0; nxt_ok = false; c = i >= 0 ? s3_q(row, i, par) : 4; }
+        else {
+          n_prev = n_curr; n_curr = 0; --i; j = 0;
+          nxt = first; nxt_ok = true;
+          c = c_nx; c_nx = i > 0 ? s3_q(row, i - 1, par) : 4;
+        }
       }
     }
   }
 }
 
 // Pass 3: greedy forward seeds (memchain.c:88-103 over bwt_seed_strategy1, bwt.c:376-396).
-__global__ void __launch_bounds__(128, 8) k_s3_greedy(const __grid_constant__ bsq_devopt_t opt, const __grid_constant__ bsq_devidx_t ix, int64_t n_tasks,
+__global__ void __launch_bounds__(128, BSQ_S3_CTAS) k_s3_greedy(const __grid_constant__ bsq_devopt_t opt, const __grid_constant__ bsq_devidx_t ix, int64_t n_tasks,
                                                       const uint8_t *seqs, int stride, const int32_t *lens, const uint8_t *parent, int pipeline,
                                                       s3_q_t *q, bsq_pk_t *intv, int32_t *n_intv) {
   bool need = true, exhausted = false;
   int64_t t = -1;
-  int len = 0, par = 0, x = 0, i = 0;
+  int len = 0, par = 0, x = 0, i = 0, c_cur = 4, c_nx = 4;
   uint64_t ik0 = 0, ik1 = 0, ik2 = 0;
   const uint8_t *row = nullptr;
   s3_fm_t f; f.b32 = nullptr; f.primary = 0;
+  s3_pend_t pe; pe.on = false; pe.slot = 0; pe.task = 0; pe.rec.w0 = pe.rec.w1 = 0;
   const int min_seed_len = opt.min_seed_len, max_mem_intv = opt.max_mem_intv;
   if (max_mem_intv <= 0) return;
   for (;;) {
+    s3_pend_flush(pe, intv);
     if (need && !exhausted) {
       for (;;) {
         if (t < 0) {
@@ -396,26 +470,31 @@ __global__ void __launch_bounds__(128, 8) k_s3_greedy(const __grid_constant__ bs
         if (x >= len) { t = -1; continue; }
         ik0 = ix.fm[par].L2[c] + 1; ik2 = ix.fm[par].L2[c + 1] - ix.fm[par].L2[c]; ik1 = ix.fm[!par].L2[3 - c] + 1;
         i = x + 1;
+        c_cur = s3_qs(row, i, len, par); c_nx = s3_qs(row, i + 1, len, par);
         need = false;
         break;
       }
     }
     if (__all_sync(0xffffffffu, exhausted)) break;
     const bool act = !need;
-    int c = 4;
-    if (act && i < len) c = s3_q(row, i, par);
-    const bool ext = act && c <= 3;
+    const int c = act ? c_cur : 4;
+    const bool ext = c <= 3;
     uint64_t o0 = 0, o1 = 0, o2 = 0;
     if (ext) s3_extend(f, ix.fm[!par].L2[3 - c] + 1, ik1, ik0, ik2, 3 - c, o1, o0, o2);
     if (act) {
       if (!ext) { x = i == len ? len : i + 1; need = true; }  // read end / ambiguous base: no seed from x (bwt.c:393-395)
       else if (o2 < (uint64_t)max_mem_intv && i - x >= min_seed_len) {
         if (o2 > 0) {  // memchain.c:95
-          const int slot = atomicAdd(n_intv + t, 1);
-          if (slot < BSQ_MAX_INTV) intv[(size_t)t * BSQ_MAX_INTV + slot] = bsq_pk_make(o0, o1, o2, x, i + 1);
+          pe.slot = s3_reserve32(n_intv + t);
+          pe.rec = bsq_pk_make(o0, o1, o2, x, i + 1);
+          pe.task = (uint32_t)t;
+          pe.on = true;
         }
         x = i + 1; need = true;
-      } else { ik0 = o0; ik1 = o1; ik2 = o2; ++i; }
+      } else {
+        ik0 = o0; ik1 = o1; ik2 = o2; ++i;
+        c_cur = c_nx; c_nx = s3_qs(row, i + 1, len, par);
+      }
     }
   }
 }

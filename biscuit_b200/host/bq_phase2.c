@@ -543,12 +543,26 @@ static void tag_sa(const bq_ref_t *ref, const bq_reg_t *p0, const bq_regv_t *reg
   free(str.s);
 }
 
-static void put_cigar(const bq_opt_t *opt, const bq_reg_t *r, int is_primary, bq_str_t *str) {
+/* Fixed-layout part of a SAM record written through a bare pointer: the caller reserves an upper bound once, so the ~100
+ * pieces of a record cost no capacity check and no terminator each (they were a third of format_sam's time). */
+static inline char *fw_num(char *w, long v) {
+  char b[24];
+  int n = 0;
+  unsigned long u = v < 0 ? 0ul - (unsigned long)v : (unsigned long)v;
+  do { b[n++] = (char)('0' + u % 10); u /= 10; } while (u);
+  if (v < 0) *w++ = '-';
+  while (n) *w++ = b[--n];
+  return w;
+}
+static inline char *fw_str(char *w, const char *p) { const size_t n = strlen(p); memcpy(w, p, n); return w + n; }
+static inline char *fw_mem(char *w, const char *p, size_t n) { memcpy(w, p, n); return w + n; }
+static char *fw_cigar(char *w, const bq_opt_t *opt, const bq_reg_t *r, int is_primary) {
   for (int i = 0; i < r->n_cigar; ++i) {
     int c = r->cigar[i] & 0xf;
     if (!(opt->flag & BQ_F_SOFTCLIP) && !r->is_alt && (c == 3 || c == 4)) c = is_primary ? 3 : 4;
-    bq_kputw(str, (int)(r->cigar[i] >> 4)); bq_kputc(str, "MIDSH"[c]);
+    w = fw_num(w, (long)(r->cigar[i] >> 4)); *w++ = "MIDSH"[c];
   }
+  return w;
 }
 
 /* mem_alnreg_formatSAM (:237-436) */
@@ -564,31 +578,39 @@ static void format_sam(const bq_opt_t *opt, const bq_ref_t *ref, bq_str_t *str, 
   if (p.rid < 0 && m0 && m.rid >= 0) { p.rid = m.rid; p.pos = m.pos; p.is_rev = m.is_rev; p.n_cigar = 0; }
   if (m0 && m.rid < 0 && p.rid >= 0) { m.rid = p.rid; m.pos = p.pos; m.is_rev = p.is_rev; m.n_cigar = 0; }
   p.flag |= m0 && m.is_rev ? 0x20 : 0;
-  bq_kputs(str, s->name);
-  if (s->comment) { bq_kputc(str, '_'); bq_kputs(str, s->comment); }
-  bq_kputc(str, '\t');
-  bq_kputw(str, (p.flag & 0xffff) | (p.flag & 0x10000 ? 0x100 : 0)); bq_kputc(str, '\t');
+  /* upper bound of everything up to and including the RG tag: names, eleven numbers of at most 20 digits, both CIGARs,
+   * sequence and qualities, MD text, tag names */
+  const char *md = p.n_cigar ? (const char *)(p.cigar + p.n_cigar) : "";
+  const size_t l_name = strlen(s->name), l_cmt = s->comment ? strlen(s->comment) : 0, l_md = strlen(md);
+  const size_t l_rn = p.rid >= 0 ? strlen(ref->anns[p.rid].name) : 1, l_mn = m0 && m.rid >= 0 ? strlen(ref->anns[m.rid].name) : 1;
+  const size_t l_rg = rg_id ? strlen(rg_id) : 0;
+  bq_str_reserve(str, l_name + l_cmt + l_rn + l_mn + l_md + l_rg + 2 * (size_t)s->l_seq0 + 12 * ((size_t)p.n_cigar + 1) + 400);
+  char *w = str->s + str->l;
+  w = fw_mem(w, s->name, l_name);
+  if (s->comment) { *w++ = '_'; w = fw_mem(w, s->comment, l_cmt); }
+  *w++ = '\t';
+  w = fw_num(w, (p.flag & 0xffff) | (p.flag & 0x10000 ? 0x100 : 0)); *w++ = '\t';
   if (p.rid >= 0) {
-    bq_kputs(str, ref->anns[p.rid].name); bq_kputc(str, '\t');
-    bq_kputl(str, p.pos + 1); bq_kputc(str, '\t');
-    bq_kputw(str, (int)p.mapq); bq_kputc(str, '\t');
-    if (p.n_cigar) put_cigar(opt, &p, is_primary, str);
-    else bq_kputc(str, '*');
-  } else bq_kputsn(str, "*\t0\t0\t*", 7);
-  bq_kputc(str, '\t');
+    w = fw_mem(w, ref->anns[p.rid].name, l_rn); *w++ = '\t';
+    w = fw_num(w, p.pos + 1); *w++ = '\t';
+    w = fw_num(w, (int)p.mapq); *w++ = '\t';
+    if (p.n_cigar) w = fw_cigar(w, opt, &p, is_primary);
+    else *w++ = '*';
+  } else w = fw_mem(w, "*\t0\t0\t*", 7);
+  *w++ = '\t';
   if (m0 && m.rid >= 0) {
-    if (p.rid == m.rid) bq_kputc(str, '='); else bq_kputs(str, ref->anns[m.rid].name);
-    bq_kputc(str, '\t'); bq_kputl(str, m.pos + 1); bq_kputc(str, '\t');
+    if (p.rid == m.rid) *w++ = '='; else w = fw_mem(w, ref->anns[m.rid].name, l_mn);
+    *w++ = '\t'; w = fw_num(w, m.pos + 1); *w++ = '\t';
     if (p.rid == m.rid) { /* biscuit-specific TLEN (:304-311) */
       int64_t q0 = -1, q1 = -1;
       if (p.is_rev) q1 = p.pos + get_rlen(p.n_cigar, p.cigar) - 1; else q0 = p.pos;
       if (m.is_rev) q1 = m.pos + get_rlen(m.n_cigar, m.cigar) - 1; else q0 = m.pos;
-      if (p.n_cigar > 0 && m.n_cigar > 0 && q0 >= 0 && q1 >= 0) bq_kputl(str, (long)(q1 - q0 + 1));
-      else bq_kputc(str, '0');
-    } else bq_kputc(str, '0');
-  } else bq_kputsn(str, "*\t0\t0", 5);
-  bq_kputc(str, '\t');
-  if (p.flag & 0x100) bq_kputsn(str, "*\t*", 3);
+      if (p.n_cigar > 0 && m.n_cigar > 0 && q0 >= 0 && q1 >= 0) w = fw_num(w, (long)(q1 - q0 + 1));
+      else *w++ = '0';
+    } else *w++ = '0';
+  } else w = fw_mem(w, "*\t0\t0", 5);
+  *w++ = '\t';
+  if (p.flag & 0x100) w = fw_mem(w, "*\t*", 3);
   else {
     int i, qb = 0, qe = s->l_seq0;
     const int hard = p.n_cigar && !is_primary && !(opt->flag & BQ_F_SOFTCLIP) && !p.is_alt;
@@ -597,34 +619,33 @@ static void format_sam(const bq_opt_t *opt, const bq_ref_t *ref, bq_str_t *str, 
         if ((p.cigar[0] & 0xf) == 4 || (p.cigar[0] & 0xf) == 3) qe -= (int)(p.cigar[0] >> 4);
         if ((p.cigar[p.n_cigar - 1] & 0xf) == 4 || (p.cigar[p.n_cigar - 1] & 0xf) == 3) qb += (int)(p.cigar[p.n_cigar - 1] >> 4);
       }
-      bq_str_reserve(str, (size_t)(qe - qb) * 2 + 4);
-      for (i = qe - 1; i >= qb; --i) str->s[str->l++] = "TGCAN"[(int)s->seq0[i]];
-      str->s[str->l] = 0;
-      bq_kputc(str, '\t');
-      if (s->qual) { for (i = qe - 1; i >= qb; --i) str->s[str->l++] = s->qual[i]; str->s[str->l] = 0; }
-      else bq_kputc(str, '*');
+      for (i = qe - 1; i >= qb; --i) *w++ = "TGCAN"[(int)s->seq0[i]];
+      *w++ = '\t';
+      if (s->qual) { for (i = qe - 1; i >= qb; --i) *w++ = s->qual[i]; }
+      else *w++ = '*';
     } else {
       if (hard) {
         if ((p.cigar[0] & 0xf) == 4 || (p.cigar[0] & 0xf) == 3) qb += (int)(p.cigar[0] >> 4);
         if ((p.cigar[p.n_cigar - 1] & 0xf) == 4 || (p.cigar[p.n_cigar - 1] & 0xf) == 3) qe -= (int)(p.cigar[p.n_cigar - 1] >> 4);
       }
-      bq_str_reserve(str, (size_t)(qe - qb) * 2 + 4);
-      for (i = qb; i < qe; ++i) str->s[str->l++] = "ACGTN"[(int)s->seq0[i]];
-      str->s[str->l] = 0;
-      bq_kputc(str, '\t');
-      if (s->qual) { for (i = qb; i < qe; ++i) str->s[str->l++] = s->qual[i]; str->s[str->l] = 0; }
-      else bq_kputc(str, '*');
+      for (i = qb; i < qe; ++i) *w++ = "ACGTN"[(int)s->seq0[i]];
+      *w++ = '\t';
+      if (s->qual) { if (qe > qb) w = fw_mem(w, s->qual + qb, (size_t)(qe - qb)); }
+      else *w++ = '*';
     }
   }
   if (p.n_cigar) {
-    bq_kputsn(str, "\tNM:i:", 6); bq_kputw(str, p.NM);
-    bq_kputsn(str, "\tMD:Z:", 6); bq_kputs(str, (char *)(p.cigar + p.n_cigar));
-    bq_kputsn(str, "\tZC:i:", 6); bq_kputw(str, (int)p.ZC);
-    bq_kputsn(str, "\tZR:i:", 6); bq_kputw(str, (int)p.ZR);
+    w = fw_mem(w, "\tNM:i:", 6); w = fw_num(w, p.NM);
+    w = fw_mem(w, "\tMD:Z:", 6); w = fw_mem(w, md, l_md);
+    w = fw_mem(w, "\tZC:i:", 6); w = fw_num(w, (int)p.ZC);
+    w = fw_mem(w, "\tZR:i:", 6); w = fw_num(w, (int)p.ZR);
   }
-  if (p.score >= 0) { bq_kputsn(str, "\tAS:i:", 6); bq_kputw(str, p.score); }
-  if (p.sub >= 0) { bq_kputsn(str, "\tXS:i:", 6); bq_kputw(str, MAXV(p.sub, p.csub)); }
-  if (rg_id && rg_id[0]) { bq_kputsn(str, "\tRG:Z:", 6); bq_kputs(str, rg_id); }
+  if (p.score >= 0) { w = fw_mem(w, "\tAS:i:", 6); w = fw_num(w, p.score); }
+  if (p.sub >= 0) { w = fw_mem(w, "\tXS:i:", 6); w = fw_num(w, MAXV(p.sub, p.csub)); }
+  if (rg_id && rg_id[0]) { w = fw_mem(w, "\tRG:Z:", 6); w = fw_mem(w, rg_id, l_rg); }
+  *w = 0;
+  str->l = (size_t)(w - str->s);
+  /* variable-length tails through the checked writers */
   if (regs0) tag_sa(ref, p0, regs0, str);
   if (is_primary && p.alt_sc > 0) { char b[64]; snprintf(b, sizeof b, "\tPA:f:%.3f", (double)p.score / p.alt_sc); bq_kputs(str, b); }
   bq_kputsn(str, "\tXL:i:", 6); bq_kputw(str, s->l_seq);
@@ -637,12 +658,16 @@ static void format_sam(const bq_opt_t *opt, const bq_ref_t *ref, bq_str_t *str, 
   }
   if (s->barcode) { bq_kputsn(str, "\tCB:Z:", 6); bq_kputs(str, s->barcode); }
   if (s->umi) { bq_kputsn(str, "\tRX:Z:", 6); bq_kputs(str, s->umi); }
-  bq_kputsn(str, "\tMC:Z:", 6);
-  if (m.n_cigar) put_cigar(opt, &m, is_primary, str); else bq_kputc(str, '*');
-  bq_kputsn(str, "\tMQ:i:", 6); bq_kputw(str, (int)m.mapq);
-  bq_kputsn(str, "\tYD:A:", 6);
-  if (p.bss_u) bq_kputc(str, 'u'); else bq_kputc(str, "fr"[p.bss]);
-  bq_kputc(str, '\n');
+  bq_str_reserve(str, 12 * ((size_t)m.n_cigar + 1) + 64);
+  w = str->s + str->l;
+  w = fw_mem(w, "\tMC:Z:", 6);
+  if (m.n_cigar) w = fw_cigar(w, opt, &m, is_primary); else *w++ = '*';
+  w = fw_mem(w, "\tMQ:i:", 6); w = fw_num(w, (int)m.mapq);
+  w = fw_mem(w, "\tYD:A:", 6);
+  *w++ = p.bss_u ? 'u' : "fr"[p.bss];
+  *w++ = '\n';
+  *w = 0;
+  str->l = (size_t)(w - str->s);
 }
 
 /* Where the SAM text of a read goes: phase-2 workers point tl_sam_slab at their own slab and the text is formatted

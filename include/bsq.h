@@ -148,8 +148,13 @@ int bsq_aligner_fetch(bsq_aligner *al, bsq_reg *regs, int64_t *reg_off);
 int bsq_host_alloc(void **p, size_t bytes);
 /* work counters for the roofline arithmetic: only the instrumented build (libbsq_count.so) has them,
  * libbsq.so returns BSQ_EINVAL.  out[0]=64-B index blocks fetched, [1]=bwt_extend calls,
- * [2]=ksw_extend2 calls, [3]=DP cells, [4]=reference bases decoded */
+ * [2]=ksw_extend2 calls, [3]=DP cells, [4]=reference bases decoded, [5]=32-byte derived rank blocks fetched by the
+ * seeding kernels ([0] then counts what the same extensions touch in the reference's 64-byte layout, bwt.c:204-236) */
 int bsq_work_counters(uint64_t *out, int n, int reset);
+/* Measurement aid for the roofline: rate of dependent random 32-byte gathers (one DRAM sector each, the access pattern
+ * of bwt_occ over the derived rank blocks) from a scratch buffer of `bytes` bytes on `device`, all SMs busy.
+ * *gathers_per_s = sectors per second.  Not used by any alignment path. */
+int bsq_measure_gather(int device, uint64_t bytes, double *gathers_per_s);
 void bsq_host_free(void *p);
 
 /* counters of the last bsq_align_phase1 call (for the roofline arithmetic in bench.py):

@@ -3,7 +3,7 @@ csv.field_size_limit(10**9)
 want_kernel = sys.argv[1]; top=int(sys.argv[2]) if len(sys.argv)>2 else 25
 cur_file=None; cur_fn=None; hdr=None
 agg=collections.defaultdict(lambda:[0,0,0,0,0,""])  # samples, inst, thr_inst, long_sb, short_sb
-with open('/tmp/p1_src_all.csv') as f:
+with open(sys.argv[3] if len(sys.argv) > 3 else '/tmp/p1_src_all.csv') as f:
     for r in csv.reader(f):
         if not r: continue
         if r[0]=="File Path": cur_file=r[1].split('/')[-1]; continue
