@@ -405,6 +405,95 @@ struct bsq_cw_warp {
     for (int m = 0; m < R; ++m) { const int i = m * 32 + lane; if (i < n) k[i] = v[m]; }
     __syncwarp();
   }
+  // The partition phase of ks_introsort (ksort.h:184-221; bsq_introsort<false> is the sequential statement), with every
+  // Hoare partition done by the whole warp.  Sequentially the i scan stops at the positions x > s with !(a[x] < pivot), in
+  // ascending order, the j scan at the positions x < t with !(pivot < a[x]), in descending order; both scans only ever
+  // look at values nobody has swapped yet, except that the i scan also stops at the position of the last swap's right
+  // element.  So swap number k exchanges the k-th stop of i (I_k) with the k-th stop of j (J_k) as long as I_k < J_k, the
+  // number of swaps K is the count of such k (the predicate is monotone), and the scan ends at i = min(I_{K+1}, J_K)
+  // (the pivot, parked at t, is the last I).  The stops come from ballots, 32 positions at a time; the swaps are disjoint.
+  // a[] and the two position lists live in shared memory; all lanes hold the same control state.
+  __device__ static void weight_partitions(uint32_t *a, int n, uint16_t *scratch) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    bsq_cw_by_weight lt;
+    if (n < 1) return;
+#ifdef BSQ_CW_SEQ_PARTITION  // A/B switch: the sequential replay on lane 0
+    if (lane == 0) bsq_introsort<false>(a, (int64_t)n, lt);
+    __syncwarp();
+    return;
+#endif
+    if (n == 2) {
+      if (lane == 0 && lt(a[1], a[0])) { const uint32_t x = a[0]; a[0] = a[1]; a[1] = x; }
+      __syncwarp();
+      return;
+    }
+    uint16_t *ipos = scratch, *jpos = scratch + n + 1;
+    int d = 2;
+    while ((1u << d) < (unsigned)n) ++d;
+    int st_l[40], st_r[40], st_d[40], top = 0;
+    int s = 0, t = n - 1;
+    d <<= 1;
+    __syncwarp();
+    for (;;) {
+      if (s < t) {
+        if (--d == 0) {  // depth limit: comb sort of the range (ksort.h:198-202), sequential
+          if (lane == 0) bsq_combsort(a + s, (int64_t)(t - s + 1), lt);
+          __syncwarp();
+          t = s;
+          continue;
+        }
+        int k = s + ((t - s) >> 1) + 1;
+        if (lt(a[k], a[s])) { if (lt(a[k], a[t])) k = t; }
+        else k = lt(a[t], a[s]) ? s : t;
+        const uint32_t rp = a[k];
+        __syncwarp();
+        if (k != t && lane == 0) { a[k] = a[t]; a[t] = rp; }
+        __syncwarp();
+        int n_i = 0, n_j = 0;
+        for (int x0 = s + 1; x0 <= t; x0 += 32) {
+          const int x = x0 + lane;
+          const bool g = x <= t && !lt(a[x], rp);  // true at x == t (the pivot)
+          const unsigned m = __ballot_sync(0xffffffffu, g);
+          if (g) ipos[n_i + __popc(m & lt_mask)] = (uint16_t)x;
+          n_i += __popc(m);
+        }
+        for (int x0 = t - 1; x0 > s; x0 -= 32) {
+          const int x = x0 - lane;
+          const bool l = x > s && !lt(rp, a[x]);
+          const unsigned m = __ballot_sync(0xffffffffu, l);
+          if (l) jpos[n_j + __popc(m & lt_mask)] = (uint16_t)x;
+          n_j += __popc(m);
+        }
+        __syncwarp();
+        const int n_min = n_i < n_j ? n_i : n_j;
+        int K = 0;
+        for (int k0 = 0; k0 < n_min; k0 += 32) {
+          const int kk = k0 + lane;
+          const unsigned m = __ballot_sync(0xffffffffu, kk < n_min && ipos[kk] < jpos[kk]);
+          K += __popc(m);
+          if (m != 0xffffffffu) break;
+        }
+        int i = ipos[K];  // K < n_i: the pivot's position t is the last stop of i and no stop of j is right of it
+        if (K > 0) { const int jl = jpos[K - 1]; i = i < jl ? i : jl; }
+        for (int kk = lane; kk < K; kk += 32) { const int xi = ipos[kk], xj = jpos[kk]; const uint32_t v = a[xi]; a[xi] = a[xj]; a[xj] = v; }
+        __syncwarp();
+        if (lane == 0) { const uint32_t v = a[i]; a[i] = a[t]; a[t] = v; }
+        __syncwarp();
+        if (i - s > t - i) {
+          if (i - s > 16) { st_l[top] = s; st_r[top] = i - 1; st_d[top] = d; ++top; }
+          s = t - i > 16 ? i + 1 : t;
+        } else {
+          if (t - i > 16) { st_l[top] = i + 1; st_r[top] = t; st_d[top] = d; ++top; }
+          t = i - s > 16 ? i - 1 : s;
+        }
+      } else {
+        if (top == 0) return;
+        --top;
+        s = st_l[top]; t = st_r[top]; d = st_d[top];
+      }
+    }
+  }
   __device__ static void sort_keys(uint64_t *k, int n) {
     const int lane = threadIdx.x & 31;
     if (n <= 32) { sort_regs<1>(k, n); return; }

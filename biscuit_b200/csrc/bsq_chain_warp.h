@@ -71,6 +71,8 @@ struct bsq_cw_scalar {
   BSQ_HD static void sort_keys(uint64_t *k, int n) {
     for (int i = 1; i < n; ++i) { uint64_t v = k[i]; int j = i; while (j > 0 && k[j - 1] > v) { k[j] = k[j - 1]; --j; } k[j] = v; }
   }
+  // the partition phase of ks_introsort over (weight << 16 | chain) keys, compared by weight only (defined below)
+  BSQ_HD static void weight_partitions(uint32_t *k32, int n, uint16_t *scratch);
 };
 
 // filter order: sort (weight << 16 | chain) by weight only, descending -- the chain id rides along but takes no part
@@ -78,6 +80,8 @@ struct bsq_cw_scalar {
 struct bsq_cw_by_weight {  // 32-bit keys: weight (at most the read length) << 16 | chain
   BSQ_HD bool operator()(uint32_t a, uint32_t b) const { return (a >> 16) > (b >> 16); }
 };
+
+BSQ_HD void bsq_cw_scalar::weight_partitions(uint32_t *k32, int n, uint16_t *) { bsq_introsort<false>(k32, (int64_t)n, bsq_cw_by_weight()); }
 
 // merge_seed_to_chain (memchain.c:227-256) against chain L (created by seed L)
 template <typename S>
@@ -251,7 +255,7 @@ BSQ_HD int bsq_chain_warp(const bsq_devopt_t &opt, const bsq_devidx_t &ix, int p
     n_ch = base;
     W::sync();
     // (the whole range is partitioned once whatever its size, ksort.h:196-221: only sub-ranges of <= 16 are left alone)
-    if (lane == 0) bsq_introsort<false>(k32, (int64_t)n_ch, bsq_cw_by_weight());
+    W::weight_partitions(k32, n_ch, reinterpret_cast<uint16_t *>(s.key));  // s.key is free between steps 3 and 4b
     W::sync();
   }
   for (int c = lane; c < n_ch; c += NL) {
