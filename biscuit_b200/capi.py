@@ -65,7 +65,8 @@ class Bsq:
 
     SYMBOLS = ["bsq_opt_default", "bsq_strerror", "bsq_last_error", "bsq_index_upload", "bsq_index_free", "bsq_occ4",
                "bsq_sa_lookup", "bsq_collect_intv", "bsq_extend_batch", "bsq_aligner_create", "bsq_aligner_destroy",
-               "bsq_align_phase1", "bsq_free", "bsq_aligner_counters"]
+               "bsq_align_phase1", "bsq_free", "bsq_aligner_counters", "bsq_dp_create", "bsq_dp_destroy", "bsq_dp_set_reads",
+               "bsq_dp_sync", "bsq_dp_cigar_submit", "bsq_dp_cigar_wait", "bsq_dp_matesw_submit", "bsq_dp_matesw_wait", "bsq_dp_counters"]
 
     def __init__(self, path: str = LIB_PATH):
         if not os.path.exists(path):
@@ -80,6 +81,10 @@ class Bsq:
         L.bsq_free.argtypes = [C.c_void_p]
         L.bsq_index_free.argtypes = [C.c_void_p]
         L.bsq_aligner_destroy.argtypes = [C.c_void_p]
+        L.bsq_dp_destroy.argtypes = [C.c_void_p]
+        for f in ("bsq_dp_sync", "bsq_dp_matesw_wait"):
+            getattr(L, f).argtypes = [C.c_void_p]
+        L.bsq_dp_cigar_wait.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
 
     def build_index(self, pac: np.ndarray, l_pac: int, names, ann_offset, ann_len, ann_is_alt=None, device: int = 0) -> "DevIndex":
         """GPU `biscuit index`: both FM-indices from the forward 2-bit pac; the result stays on the device."""
@@ -235,6 +240,65 @@ class Aligner:
     def counters(self) -> np.ndarray:
         c = np.zeros(16, dtype=np.int64)
         self.bsq.check(self.bsq.lib.bsq_aligner_counters(self.h, _p(c), C.c_int(16)), "bsq_aligner_counters")
+        return c
+
+
+CIGAR_JOB_DTYPE = np.dtype([("rb", "<i8"), ("re", "<i8"), ("row", "<i4"), ("qb", "<i4"), ("qe", "<i4"), ("w", "<i4"), ("truesc", "<i4"),
+                            ("clip5", "<i4"), ("clip3", "<i4"), ("parent", "u1"), ("pad_", "u1", (3,))])
+CIGAR_RES_DTYPE = np.dtype([("n_cigar", "<i4"), ("NM", "<i4"), ("ZC", "<i4"), ("ZR", "<i4"), ("score", "<i4"), ("lead_del", "<i4"),
+                            ("bss_u", "<i4"), ("off", "<u4")])
+MATESW_JOB_DTYPE = np.dtype([("rb", "<i8"), ("re", "<i8"), ("row", "<i4"), ("xtra", "<i4"), ("use_ga", "u1"), ("pad_", "u1", (7,))])
+MATESW_RES_DTYPE = np.dtype([("score", "<i4"), ("te", "<i4"), ("qe", "<i4"), ("score2", "<i4"), ("te2", "<i4"), ("tb", "<i4"),
+                             ("qb", "<i4"), ("pad_", "<i4")])
+assert CIGAR_JOB_DTYPE.itemsize == 48 and CIGAR_RES_DTYPE.itemsize == 32 and MATESW_JOB_DTYPE.itemsize == 32 and MATESW_RES_DTYPE.itemsize == 32
+
+
+class Dp:
+    """bsq_dp: the batched phase-2 dynamic programming (final CIGAR/MD, mate-rescue local alignment)."""
+
+    def __init__(self, idx: DevIndex, opt: Opt):
+        self.idx, self.bsq, self.opt = idx, idx.bsq, opt
+        h = C.c_void_p()
+        self.bsq.check(self.bsq.lib.bsq_dp_create(idx.h, C.byref(opt), C.byref(h)), "bsq_dp_create")
+        self.h = h
+        self._keep = None
+
+    def close(self):
+        if self.h:
+            self.bsq.lib.bsq_dp_destroy(self.h)
+            self.h = None
+
+    def set_reads(self, seqs: np.ndarray, lens: np.ndarray):
+        seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+        lens = np.ascontiguousarray(lens, dtype=np.int32)
+        self._keep = (seqs, lens)
+        self.bsq.check(self.bsq.lib.bsq_dp_set_reads(self.h, C.c_int64(seqs.shape[0]), _p(seqs), C.c_int32(seqs.shape[1]), _p(lens)),
+                       "bsq_dp_set_reads")
+        self.bsq.check(self.bsq.lib.bsq_dp_sync(self.h), "bsq_dp_sync")
+
+    def cigar(self, jobs: np.ndarray):
+        """Returns (results, blob as uint32 array)."""
+        jobs = np.ascontiguousarray(jobs, dtype=CIGAR_JOB_DTYPE)
+        res = np.zeros(len(jobs), dtype=CIGAR_RES_DTYPE)
+        self.bsq.check(self.bsq.lib.bsq_dp_cigar_submit(self.h, C.c_int64(len(jobs)), _p(jobs), _p(res)), "bsq_dp_cigar_submit")
+        blob_p, words = C.c_void_p(), C.c_int64()
+        self.bsq.check(self.bsq.lib.bsq_dp_cigar_wait(self.h, C.byref(blob_p), C.byref(words)), "bsq_dp_cigar_wait")
+        if words.value:
+            blob = np.frombuffer((C.c_char * (words.value * 4)).from_address(blob_p.value), dtype=np.uint32).copy()
+        else:
+            blob = np.zeros(0, dtype=np.uint32)
+        return res, blob
+
+    def matesw(self, jobs: np.ndarray) -> np.ndarray:
+        jobs = np.ascontiguousarray(jobs, dtype=MATESW_JOB_DTYPE)
+        res = np.zeros(len(jobs), dtype=MATESW_RES_DTYPE)
+        self.bsq.check(self.bsq.lib.bsq_dp_matesw_submit(self.h, C.c_int64(len(jobs)), _p(jobs), _p(res)), "bsq_dp_matesw_submit")
+        self.bsq.check(self.bsq.lib.bsq_dp_matesw_wait(self.h), "bsq_dp_matesw_wait")
+        return res
+
+    def counters(self) -> np.ndarray:
+        c = np.zeros(8, dtype=np.int64)
+        self.bsq.check(self.bsq.lib.bsq_dp_counters(self.h, _p(c), C.c_int(8)), "bsq_dp_counters")
         return c
 
 

@@ -121,6 +121,10 @@ typedef struct {
   uint32_t ZC, ZR;
   int bss_u;
   uint32_t *cigar; /* n_cigar words followed by the NUL-terminated MD string */
+  /* batched phase-2 DP on the GPU (bsq_dp_*): 1 + index of the CIGAR job predicted for this region (0 = none), and
+   * whether .cigar points into the batch's result blob (not owned by the region) */
+  int dp_job;
+  uint8_t cigar_ext;
 } bq_reg_t;
 
 typedef struct {
@@ -194,23 +198,39 @@ void bq_reg2sam_pe(const bq_opt_t *opt, const bq_ref_t *ref, uint64_t id, bq_rea
                    const char *rg_id);
 void bq_read_clipping(bq_read_t *s, const uint8_t *adaptor, int l_adaptor, const bq_opt_t *opt);
 /* mem_process_seqs (lib/aln/bwamem.c:432-476) on top of the GPU aligner: fills seqs[i].sam */
-int bq_process_seqs(const bq_opt_t *opt, bsq_aligner *al, const bq_ref_t *ref, int64_t n_processed, int n, bq_read_t *seqs,
+int bq_process_seqs(const bq_opt_t *opt, bsq_aligner *al, bsq_dp *dp, const bq_ref_t *ref, int64_t n_processed, int n, bq_read_t *seqs,
                     const bq_pestat_t *pes0, const char *rg_id);
 
 typedef struct bq_batch bq_batch_t;
 /* GPU half (clipping, task list, bsq_align_phase1) and host half (merge, pestat, phase 2, SAM) of one batch */
 bq_batch_t *bq_batch_prep(const bq_opt_t *opt, int64_t n_processed, int n, bq_read_t *seqs, int *rc);
-int bq_batch_run(bsq_aligner *al, bq_batch_t *b);
+int bq_batch_run(bsq_aligner *al, bsq_dp *dp, bq_batch_t *b);
 void bq_batch_discard(bq_batch_t *b);
-bq_batch_t *bq_batch_gpu(const bq_opt_t *opt, bsq_aligner *al, int64_t n_processed, int n, bq_read_t *seqs, int *rc);
-void bq_batch_finish(const bq_opt_t *opt, const bq_ref_t *ref, bq_batch_t *b, const bq_pestat_t *pes0, const char *rg_id);
+bq_batch_t *bq_batch_gpu(const bq_opt_t *opt, bsq_aligner *al, bsq_dp *dp, int64_t n_processed, int n, bq_read_t *seqs, int *rc);
+/* Host phase 2 in two halves around the batched DP of the batch's bsq_dp context (NULL: everything on the host):
+ *   _a  region merge, insert-size statistics, mate rescue (its local alignments as one bsq_dp_matesw batch), primary
+ *       marking; predicts which regions will need a final CIGAR and submits them as one bsq_dp_cigar batch (asynchronous)
+ *   _wait  blocks until the CIGARs are back
+ *   _b  pairing, mapQ, SAM text (mem_alnreg_setSAM looks its CIGAR up; anything not predicted is done on the host)
+ * bq_batch_finish = the three in a row.  A pipeline runs _a of batch k+1 between _wait and _b of batch k, so that the
+ * CIGAR kernel of one batch overlaps the SAM formatting of the one before (bq_pipe.c). */
+int bq_batch_finish_a(const bq_opt_t *opt, const bq_ref_t *ref, bq_batch_t *b, const bq_pestat_t *pes0);
+int bq_batch_finish_wait(bq_batch_t *b);
+void bq_batch_finish_b(const bq_opt_t *opt, const bq_ref_t *ref, bq_batch_t *b, const char *rg_id);
+int bq_batch_finish(const bq_opt_t *opt, const bq_ref_t *ref, bq_batch_t *b, const bq_pestat_t *pes0, const char *rg_id);
+void bq_batch_abandon(bq_batch_t *b); /* after a failed _a / _wait: releases the batch (not the reads) */
+/* counters of the batched DP since the start: [0] CIGAR jobs sent to the GPU, [1] setSAM calls answered from them, [2] setSAM
+ * calls done on the host (not predicted / outside the kernel's limits), [3] mate-rescue alignments sent to the GPU,
+ * [4] used from there, [5] done on the host */
+void bq_dp_stats(int64_t out[6]);
 
 /* bq_pipe.c: source -> prep | GPU | phase 2 -> sink, batches in order.  src returns the next batch (NULL / n <= 0 at the end);
  * sink receives the reads with .sam filled and frees them (n < 0: the batch failed, free only). */
 typedef bq_read_t *(*bq_source_fn)(void *ctx, int *n);
 typedef void (*bq_sink_fn)(void *ctx, bq_read_t *seqs, int n);
 #define BQ_MAX_LANES 16 /* aligner contexts (GPUs) one pipeline can drive */
-int bq_pipeline_run(const bq_opt_t *opt, const bq_ref_t *ref, bsq_aligner *const *als, int n_al /* one lane per aligner context: batches round-robin */,
+int bq_pipeline_run(const bq_opt_t *opt, const bq_ref_t *ref, bsq_aligner *const *als, bsq_dp *const *dps /* one per lane, or NULL */,
+                    int n_al /* one lane per aligner context: batches round-robin */,
                     bq_source_fn src, void *src_ctx, bq_sink_fn sink, void *sink_ctx, const bq_pestat_t *pes0, const char *rg_id);
 
 /* bq_io.c */

@@ -11,6 +11,7 @@ typedef struct {
   bq_opt_t opt;
   bq_ref_t ref;
   bsq_aligner *al, *al2;
+  bsq_dp *dp, *dp2; /* batched phase-2 DP of the same device */
 } bq_session;
 
 bq_session *bq_session_create(bsq_index *dx, const uint8_t *pac, int64_t l_pac, int n_seqs, const char *const *names, const int64_t *offs,
@@ -30,12 +31,15 @@ bq_session *bq_session_create(bsq_index *dx, const uint8_t *pac, int64_t l_pac, 
   bsq_opt d;
   bq_opt_to_dev(&s->opt, &d);
   if (bsq_aligner_create(dx, &d, &s->al)) { free(s->ref.anns); free(s); return 0; }
-  if (!getenv("BQ_TWO_CONTEXTS") || bsq_aligner_create(dx, &d, &s->al2)) s->al2 = 0; /* measured: no gain from a second context */
+  if (bsq_dp_create(dx, &d, &s->dp)) { bsq_aligner_destroy(s->al); free(s->ref.anns); free(s); return 0; }
+  if (!getenv("BQ_TWO_CONTEXTS") || bsq_aligner_create(dx, &d, &s->al2) || bsq_dp_create(dx, &d, &s->dp2)) s->al2 = 0; /* measured: no gain from a second context */
   return s;
 }
 
 void bq_session_destroy(bq_session *s) {
   if (!s) return;
+  bsq_dp_destroy(s->dp);
+  if (s->dp2) bsq_dp_destroy(s->dp2);
   bsq_aligner_destroy(s->al);
   if (s->al2) bsq_aligner_destroy(s->al2);
   for (int i = 0; i < s->ref.n_seqs; ++i) { free(s->ref.anns[i].name); free(s->ref.anns[i].anno); }
@@ -60,7 +64,7 @@ int64_t bq_session_align(bq_session *s, int64_t n_processed, int n, const uint8_
     rd[i].name = strdup(nm);
     rd[i].id = i;
   }
-  int rc = bq_process_seqs(&s->opt, s->al, &s->ref, n_processed, n, rd, 0, "");
+  int rc = bq_process_seqs(&s->opt, s->al, s->dp, &s->ref, n_processed, n, rd, 0, "");
   int64_t tot = 0;
   for (int i = 0; i < n; ++i) {
     int64_t l = rd[i].sam ? (int64_t)strlen(rd[i].sam) : 0;
@@ -120,6 +124,10 @@ int64_t bq_session_align_stream(bq_session *s, int n_batches, int n, const uint8
   memset(&st, 0, sizeof st);
   st.n_batches = n_batches; st.n = n; st.stride = stride; st.seqs = seqs; st.quals = quals; st.lens = lens;
   bsq_aligner *als[2] = {s->al, s->al2};
-  const int rc = bq_pipeline_run(&s->opt, &s->ref, als, s->al2 ? 2 : 1, stream_source, &st, stream_sink, &st, 0, "");
+  bsq_dp *dps[2] = {s->dp, s->dp2};
+  const int rc = bq_pipeline_run(&s->opt, &s->ref, als, dps, s->al2 ? 2 : 1, stream_source, &st, stream_sink, &st, 0, "");
   return rc ? rc : st.sam_bytes;
 }
+
+/* counters of the batched phase-2 DP since the library was loaded (bq_dp_stats) */
+void bq_session_dp_stats(int64_t out[6]) { bq_dp_stats(out); }

@@ -49,7 +49,8 @@ static void free_sub_sam(bq_read_t *sub, int n) {
   free(sub[0].sam_slabs);
 }
 
-static int align_smart_pairing(const bq_opt_t *opt, const bq_ref_t *ref, bsq_aligner *al, src_ctx_t *sc, const bq_pestat_t *pes0, const char *rg_id) {
+static int align_smart_pairing(const bq_opt_t *opt, const bq_ref_t *ref, bsq_aligner *al, bsq_dp *dp, src_ctx_t *sc, const bq_pestat_t *pes0,
+                               const char *rg_id) {
   int64_t n_processed = 0;
   for (;;) {
     int n = 0, i, has_last, m[2] = {0, 0};
@@ -71,7 +72,7 @@ static int align_smart_pairing(const bq_opt_t *opt, const bq_ref_t *ref, bsq_ali
       bq_opt_t tmp = *opt;
       if (k) tmp.flag |= BQ_F_PE; else tmp.flag &= ~BQ_F_PE;
       for (i = 0; i < m[k]; ++i) { sep[k][i].slab = 0; sep[k][i].sam = 0; sep[k][i].sam_slabs = 0; sep[k][i].n_sam_slabs = 0; sep[k][i].sam_in_slab = 0; }
-      const int rc = bq_process_seqs(&tmp, al, ref, n_processed + (k ? m[0] : 0), m[k], sep[k], k ? pes0 : 0, rg_id);
+      const int rc = bq_process_seqs(&tmp, al, dp, ref, n_processed + (k ? m[0] : 0), m[k], sep[k], k ? pes0 : 0, rg_id);
       if (rc) return rc;
       for (i = 0; i < m[k]; ++i) sam[sep[k][i].id] = sep[k][i].sam;
     }
@@ -286,6 +287,7 @@ int bq_main_align(int argc, char **argv) {
    * pipeline (bq_pipe.c), no data moves between GPUs */
   bsq_index *dxs[BQ_MAX_LANES] = {0};
   bsq_aligner *als[BQ_MAX_LANES] = {0};
+  bsq_dp *dps[BQ_MAX_LANES] = {0}; /* batched phase-2 DP (final CIGARs, mate-rescue alignments), one context per lane */
   bsq_opt dopt;
   bq_opt_to_dev(&opt, &dopt);
   int rc = 0;
@@ -293,10 +295,11 @@ int bq_main_align(int argc, char **argv) {
     if ((rc = bq_index_to_device(&idx, devices[i], &dxs[i])))
       bq_fatal("cannot stage the index on CUDA device %d: %s (%s)", devices[i], bsq_strerror(rc), bsq_last_error());
     if ((rc = bsq_aligner_create(dxs[i], &dopt, &als[i]))) bq_fatal("bsq_aligner_create (device %d): %s", devices[i], bsq_strerror(rc));
+    if ((rc = bsq_dp_create(dxs[i], &dopt, &dps[i]))) bq_fatal("bsq_dp_create (device %d): %s", devices[i], bsq_strerror(rc));
   }
   bsq_aligner *al = als[0];
   int n_al = n_dev;
-  if (n_dev == 1 && getenv("BQ_TWO_CONTEXTS") && !bsq_aligner_create(dxs[0], &dopt, &als[1])) n_al = 2; /* off by default: measured no gain */
+  if (n_dev == 1 && getenv("BQ_TWO_CONTEXTS") && !bsq_aligner_create(dxs[0], &dopt, &als[1]) && !bsq_dp_create(dxs[0], &dopt, &dps[1])) n_al = 2; /* off by default: measured no gain */
   if (bq_verbose >= 3) fprintf(stderr, "[M::main_align] index loaded and staged on %d GPU(s) in %.3f sec\n", n_dev, now() - t0);
 
   bq_fastq_t *f1 = 0, *f2 = 0;
@@ -323,16 +326,23 @@ int bq_main_align(int argc, char **argv) {
       for (int k = 0; k < seqs[i].l_seq; ++k) seqs[i].seq[k] = t4[(unsigned char)lit[i][k]];
     }
     if (seq2) opt.flag |= BQ_F_PE;
-    if ((rc = bq_process_seqs(&opt, al, &idx.ref, 0, n, seqs, pes0, rg_id))) bq_fatal("alignment failed: %s (%s)", bsq_strerror(rc), bsq_last_error());
+    if ((rc = bq_process_seqs(&opt, al, dps[0], &idx.ref, 0, n, seqs, pes0, rg_id))) bq_fatal("alignment failed: %s (%s)", bsq_strerror(rc), bsq_last_error());
     for (i = 0; i < n; ++i) if (seqs[i].sam) fputs(seqs[i].sam, stdout);
     bq_reads_free(seqs, n);
   } else {
     src_ctx_t sc = {&opt, f1, f2, chunk, copy_comment};
     if (smart_pe) {
-      if ((rc = align_smart_pairing(&opt, &idx.ref, al, &sc, pes0, rg_id))) bq_fatal("alignment batch failed: %s (%s)", bsq_strerror(rc), bsq_last_error());
-    } else if ((rc = bq_pipeline_run(&opt, &idx.ref, als, n_al, fastq_source, &sc, sam_sink, 0, pes0, rg_id)))
+      if ((rc = align_smart_pairing(&opt, &idx.ref, al, dps[0], &sc, pes0, rg_id))) bq_fatal("alignment batch failed: %s (%s)", bsq_strerror(rc), bsq_last_error());
+    } else if ((rc = bq_pipeline_run(&opt, &idx.ref, als, dps, n_al, fastq_source, &sc, sam_sink, 0, pes0, rg_id)))
       bq_fatal("alignment batch failed: %s (%s)", bsq_strerror(rc), bsq_last_error());
   }
+  if (getenv("BQ_TIMING") || bq_verbose >= 4) {
+    int64_t st[6];
+    bq_dp_stats(st);
+    fprintf(stderr, "[M::main_align] phase-2 DP on the GPU: %lld CIGAR jobs, %lld used, %lld setSAM calls on the host; mate rescue: %lld jobs, %lld used, %lld on the host\n",
+            (long long)st[0], (long long)st[1], (long long)st[2], (long long)st[3], (long long)st[4], (long long)st[5]);
+  }
+  for (i = 0; i < BQ_MAX_LANES; ++i) if (dps[i]) bsq_dp_destroy(dps[i]);
   for (i = 0; i < BQ_MAX_LANES; ++i) if (als[i]) bsq_aligner_destroy(als[i]);
   for (i = 0; i < BQ_MAX_LANES; ++i) if (dxs[i]) bsq_index_free(dxs[i]);
   bq_index_free(&idx);

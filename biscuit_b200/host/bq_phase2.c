@@ -213,25 +213,61 @@ bq_pestat_t bq_pestat(const bq_opt_t *opt, const bq_ref_t *ref, int n, const bq_
 
 /* ---------------- mate rescue: mem_alnreg.c:395-513 ---------------- */
 
+/* counters of the batched DP (bq_dp_stats) */
+static int64_t g_dp_stat[6];
+void bq_dp_stats(int64_t out[6]) { for (int i = 0; i < 6; ++i) out[i] = __atomic_load_n(&g_dp_stat[i], __ATOMIC_RELAXED); }
+
+/* does the mate already have a hit at a proper distance from reg?  (mem_alnreg.c:401-407) */
+static int mate_in_range(const bq_ref_t *ref, bq_pestat_t pes, const bq_reg_t *reg, const bq_regv_t *mregs) {
+  for (size_t i = 0; i < mregs->n; ++i) {
+    int64_t is;
+    if (reg_isize(ref, reg, &mregs->a[i], &is) && is >= pes.low && is <= pes.high) return 1;
+  }
+  return 0;
+}
+
+/* the reference window searched for the mate of reg (mem_alnreg.c:418-427): bns_fetch_seq's clipping to the contig of the
+ * window's middle (bntseq.c:428-452) without fetching the bases; 0 when there is nothing to search */
+static int matesw_window(const bq_opt_t *opt, const bq_ref_t *ref, bq_pestat_t pes, const bq_reg_t *reg, int l_ms, int64_t *rb_, int64_t *re_) {
+  const int64_t l_pac = ref->l_pac;
+  int64_t rb = MAXV(0, reg->rb + pes.low - l_ms), re = MINV(l_pac << 1, reg->rb + pes.high);
+  if (rb >= re) return 0;
+  int is_rev;
+  const int rid = bq_pos2rid(ref, bq_depos(ref, (rb + re) >> 1, &is_rev));
+  int64_t far_beg = ref->anns[rid].offset, far_end = far_beg + ref->anns[rid].len;
+  if (is_rev) { int64_t t = far_beg; far_beg = (l_pac << 1) - far_end; far_end = (l_pac << 1) - t; }
+  if (rb < far_beg) rb = far_beg;
+  if (re > far_end) re = far_end;
+  if (reg->rid != rid || re - rb < opt->min_seed_len) return 0;
+  *rb_ = rb; *re_ = re;
+  return 1;
+}
+static inline int matesw_xtra(const bq_opt_t *opt, int l_ms) { return BQ_XSUBO | BQ_XSTART | (l_ms * opt->a < 250 ? BQ_XBYTE : 0) | (opt->min_seed_len * opt->a); }
+
+/* pre: the local alignment of this call computed on the GPU (bsq_dp_matesw), or NULL: computed here */
 static void matesw_core(const bq_opt_t *opt, const bq_ref_t *ref, bq_pestat_t pes, const bq_reg_t *reg, int l_ms, const uint8_t *ms,
-                        bq_regv_t *mregs) {
+                        bq_regv_t *mregs, const bsq_matesw_res *pre) {
   const int64_t l_pac = ref->l_pac;
   int i;
-  for (i = 0; (size_t)i < mregs->n; ++i) {
-    int64_t is;
-    if (reg_isize(ref, reg, &mregs->a[i], &is) && is >= pes.low && is <= pes.high) return;
-  }
-  uint8_t revbuf[512], *rev = l_ms < (int)sizeof revbuf ? revbuf : malloc((size_t)l_ms + 1);
-  for (i = 0; i < l_ms; ++i) rev[l_ms - 1 - i] = ms[i] < 4 ? 3 - ms[i] : 4;
-  int64_t rb = MAXV(0, reg->rb + pes.low - l_ms), re = MINV(l_pac << 1, reg->rb + pes.high);
-  uint8_t *rseq = 0;
-  int rid = -1;
-  if (rb < re) rseq = bq_fetch_seq(ref, &rb, (rb + re) >> 1, &re, &rid);
-  if (reg->rid != rid || re - rb < opt->min_seed_len) { if (rev != revbuf) free(rev); free(rseq); return; }
+  if (mate_in_range(ref, pes, reg, mregs)) return;
+  int64_t rb, re;
+  if (!matesw_window(opt, ref, pes, reg, l_ms, &rb, &re)) return;
   const uint8_t parent = reg->bss ^ (reg->rb < l_pac);
-  const int xtra = BQ_XSUBO | BQ_XSTART | (l_ms * opt->a < 250 ? BQ_XBYTE : 0) | (opt->min_seed_len * opt->a);
-  bq_swr_t aln = bq_local_align(l_ms, rev, (int)(re - rb), rseq, parent ? opt->gamat : opt->ctmat, opt->o_del, opt->e_del, opt->o_ins,
-                                opt->e_ins, xtra);
+  bq_swr_t aln;
+  if (pre && !pre->pad_) {
+    aln.score = pre->score; aln.te = pre->te; aln.qe = pre->qe; aln.score2 = pre->score2; aln.te2 = pre->te2; aln.tb = pre->tb; aln.qb = pre->qb;
+    __atomic_fetch_add(&g_dp_stat[4], 1, __ATOMIC_RELAXED);
+  } else {
+    uint8_t revbuf[512], *rev = l_ms < (int)sizeof revbuf ? revbuf : malloc((size_t)l_ms + 1);
+    for (i = 0; i < l_ms; ++i) rev[l_ms - 1 - i] = ms[i] < 4 ? 3 - ms[i] : 4;
+    int rid = -1;
+    uint8_t *rseq = bq_fetch_seq(ref, &rb, (rb + re) >> 1, &re, &rid);
+    aln = bq_local_align(l_ms, rev, (int)(re - rb), rseq, parent ? opt->gamat : opt->ctmat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins,
+                         matesw_xtra(opt, l_ms));
+    if (rev != revbuf) free(rev);
+    free(rseq);
+    __atomic_fetch_add(&g_dp_stat[5], 1, __ATOMIC_RELAXED);
+  }
   if (aln.score >= opt->min_seed_len && aln.qb >= 0) {
     bq_reg_t b;
     memset(&b, 0, sizeof b);
@@ -249,22 +285,58 @@ static void matesw_core(const bq_opt_t *opt, const bq_ref_t *ref, bq_pestat_t pe
     mregs->a[i] = b;
     sort_dedup(opt, 0, 0, mregs);
   }
-  if (rev != revbuf) free(rev);
-  free(rseq);
 }
 
-void bq_matesw(const bq_opt_t *opt, const bq_ref_t *ref, bq_pestat_t pes, bq_read_t s[2], bq_regv_t regs[2]) {
+/* The rescue attempts of one pair in the reference's order (mem_alnreg.c:495-513).  Three uses:
+ *   jobs == NULL, pre == NULL  the reference's loop, every local alignment computed on the host (bq_matesw);
+ *   jobs != NULL               planning: nothing is changed; every attempt that the state of the pair BEFORE any rescue
+ *                              does not rule out is written as one bsq_dp_matesw job (row[] = device rows of the two reads)
+ *                              with its (end, rank) key; returns the number of jobs (jobs may be a counting dummy, n_max 0);
+ *   pre != NULL                replay with the results of those jobs.  An attempt is ruled out dynamically when the mate
+ *                              gained a hit in range from an earlier rescue, so the planned set is a superset of what is
+ *                              used -- except when region de-duplication removed the hit that ruled an attempt out at
+ *                              planning time; such an attempt finds no job and is computed on the host. */
+typedef struct { const bsq_matesw_res *res; const uint32_t *key; int64_t cur, end; } ms_pre_t;
+static int matesw_pair(const bq_opt_t *opt, const bq_ref_t *ref, bq_pestat_t pes, bq_read_t s[2], bq_regv_t regs[2], ms_pre_t *pre,
+                       bsq_matesw_job *jobs, uint32_t *keys, const int64_t row[2], int fill) {
   bq_reg_t gbuf[2][8];
   bq_regv_t good[2] = {{0, 8, 0, gbuf[0], 1}, {0, 8, 0, gbuf[1], 1}};
-  int i;
+  int i, n_jobs = 0;
   size_t j;
+  const int plan = row != 0;
   for (i = 0; i < 2; ++i)
     for (j = 0; j < regs[i].n; ++j)
       if (regs[i].a[j].score >= regs[i].a[0].score - opt->pen_unpaired) regv_push(&good[i], &regs[i].a[j]);
   for (i = 0; i < 2; ++i)
-    for (j = 0; j < good[i].n && (int)j < opt->max_matesw; ++j)
-      matesw_core(opt, ref, pes, &good[i].a[j], s[!i].l_seq, s[!i].seq, &regs[!i]);
+    for (j = 0; j < good[i].n && (int)j < opt->max_matesw; ++j) {
+      const bq_reg_t *reg = &good[i].a[j];
+      if (plan) {
+        int64_t rb, re;
+        if (mate_in_range(ref, pes, reg, &regs[!i]) || !matesw_window(opt, ref, pes, reg, s[!i].l_seq, &rb, &re)) continue;
+        if (fill) {
+          bsq_matesw_job *jb = &jobs[n_jobs];
+          memset(jb, 0, sizeof *jb);
+          jb->rb = rb; jb->re = re; jb->row = (int32_t)row[!i]; jb->xtra = matesw_xtra(opt, s[!i].l_seq);
+          jb->use_ga = (uint8_t)(reg->bss ^ (reg->rb < ref->l_pac));
+          keys[n_jobs] = (uint32_t)i << 16 | (uint32_t)j;
+        }
+        ++n_jobs;
+        continue;
+      }
+      const bsq_matesw_res *r = 0;
+      if (pre) {
+        const uint32_t key = (uint32_t)i << 16 | (uint32_t)j;
+        while (pre->cur < pre->end && pre->key[pre->cur] < key) ++pre->cur; /* jobs of attempts that were skipped */
+        if (pre->cur < pre->end && pre->key[pre->cur] == key) r = &pre->res[pre->cur++];
+      }
+      matesw_core(opt, ref, pes, reg, s[!i].l_seq, s[!i].seq, &regs[!i], r);
+    }
   for (i = 0; i < 2; ++i) if (!good[i].pooled) free(good[i].a);
+  return n_jobs;
+}
+
+void bq_matesw(const bq_opt_t *opt, const bq_ref_t *ref, bq_pestat_t pes, bq_read_t s[2], bq_regv_t regs[2]) {
+  matesw_pair(opt, ref, pes, s, regs, 0, 0, 0, 0, 0);
 }
 
 /* ---------------- primary marking: mem_alnreg.c:242-380 ---------------- */
@@ -443,16 +515,42 @@ static int get_rlen(int n_cigar, const uint32_t *cigar) {
   return l;
 }
 
-/* mem_alnreg_setSAM (:40-123): final CIGAR with band doubling, position, clipping */
-static void set_sam(const bq_opt_t *opt, const bq_ref_t *ref, bq_read_t *s, bq_reg_t *reg) {
-  if (reg->n_cigar > 0) return;
-  uint8_t qbuf[512], *query = s->l_seq < (int)sizeof qbuf ? qbuf : malloc((size_t)s->l_seq + 1);
-  int i;
-  for (i = 0; i < s->l_seq; ++i) query[i] = s->seq[i] < 5 ? s->seq[i] : 4;
+/* the first band of mem_alnreg_setSAM (:46-51) */
+static int set_sam_band(const bq_opt_t *opt, const bq_reg_t *reg) {
   int w1 = infer_bw(reg->qe - reg->qb, (int)(reg->re - reg->rb), reg->truesc, opt->a, opt->o_del, opt->e_del);
   int w2 = infer_bw(reg->qe - reg->qb, (int)(reg->re - reg->rb), reg->truesc, opt->a, opt->o_ins, opt->e_ins);
   int w = MAXV(w1, w2);
   if (w > opt->w) w = MINV(w, reg->w);
+  return w;
+}
+
+/* CIGARs of the batch computed on the GPU (bsq_dp_cigar): set by the phase-2 workers around reg2sam */
+typedef struct { const bsq_cigar_res *res; const uint32_t *blob; int64_t n; } dp_cig_t;
+static __thread const dp_cig_t *tl_dp_cig;
+
+/* mem_alnreg_setSAM (:40-123): final CIGAR with band doubling, position, clipping */
+static void set_sam(const bq_opt_t *opt, const bq_ref_t *ref, bq_read_t *s, bq_reg_t *reg) {
+  if (reg->n_cigar > 0) return;
+  if (tl_dp_cig && reg->dp_job > 0 && reg->dp_job <= tl_dp_cig->n && tl_dp_cig->res[reg->dp_job - 1].n_cigar > 0) {
+    /* the band loop, the global alignment, MD / NM / ZC / ZR and the clean-up of the CIGAR were done by k_cigar on the
+     * job built from this region (cigar_job); what is left is the position */
+    const bsq_cigar_res *r = &tl_dp_cig->res[reg->dp_job - 1];
+    int is_rev;
+    int64_t rpos = bq_depos(ref, reg->rb < ref->l_pac ? reg->rb : reg->re - 1, &is_rev);
+    reg->is_rev = is_rev;
+    reg->flag |= reg->is_rev ? 0x10 : 0;
+    reg->NM = r->NM; reg->ZC = (uint32_t)r->ZC; reg->ZR = (uint32_t)r->ZR; reg->bss_u = r->bss_u;
+    reg->n_cigar = r->n_cigar;
+    reg->cigar = (uint32_t *)(tl_dp_cig->blob + r->off); reg->cigar_ext = 1; /* read-only from here on */
+    reg->pos = (int)(rpos + r->lead_del - ref->anns[reg->rid].offset);
+    __atomic_fetch_add(&g_dp_stat[1], 1, __ATOMIC_RELAXED);
+    return;
+  }
+  if (tl_dp_cig) __atomic_fetch_add(&g_dp_stat[2], 1, __ATOMIC_RELAXED);
+  uint8_t qbuf[512], *query = s->l_seq < (int)sizeof qbuf ? qbuf : malloc((size_t)s->l_seq + 1);
+  int i;
+  for (i = 0; i < s->l_seq; ++i) query[i] = s->seq[i] < 5 ? s->seq[i] : 4;
+  int w = set_sam_band(opt, reg);
   uint32_t *cigar = 0;
   int n_cigar = 0, score = 0, last_sc = -(1 << 30);
   for (i = 0; i < 3; ++i, w <<= 1, last_sc = score) {
@@ -497,6 +595,55 @@ static int get_pri_idx(double XA_drop_ratio, const bq_reg_t *a, int i) { /* mem_
   int k = a[i].secondary_all;
   if (k >= 0 && a[i].score >= a[k].score * XA_drop_ratio) return k;
   return -1;
+}
+
+/* One bsq_dp_cigar job = the set_sam call on this region (row = device row of the read) */
+static void cigar_job(const bq_opt_t *opt, const bq_ref_t *ref, const bq_read_t *s, const bq_reg_t *reg, int64_t row, bsq_cigar_job *jb) {
+  memset(jb, 0, sizeof *jb);
+  jb->rb = reg->rb; jb->re = reg->re; jb->row = (int32_t)row; jb->qb = reg->qb; jb->qe = reg->qe;
+  jb->w = set_sam_band(opt, reg); jb->truesc = reg->truesc; jb->parent = reg->parent;
+  const int is_rev = reg->rb >= ref->l_pac; /* what bns_depos says for rb (forward) / re - 1 (reverse), mem_alnreg.c:77 */
+  if (reg->qb != 0 || reg->qe != s->l_seq || s->clip5 || s->clip3) { /* mem_alnreg.c:96-108 */
+    jb->clip5 = is_rev ? s->l_seq - reg->qe + s->clip3 : reg->qb + s->clip5;
+    jb->clip3 = is_rev ? reg->qb + s->clip5 : s->l_seq - reg->qe + s->clip3;
+  }
+}
+
+/* Which regions of a read will mem_alnreg_setSAM be called on?  Decided after primary marking, before pairing: every
+ * region that can be printed as a record of its own (not a secondary, score >= T; with -a the secondaries that pass
+ * the drop ratio too: mem_alnreg_select_format :445-488, mem_reg2sam_pe :680-693) and the secondaries listed in an XA
+ * tag (mem_alnreg_format.c:91-134).  Pairing may still pick a secondary that is in neither group (mem_pair); set_sam then
+ * finds no job and does that one on the host.  jobs == NULL: count only. */
+static int predict_cigar_jobs(const bq_opt_t *opt, const bq_ref_t *ref, const bq_read_t *s, bq_regv_t *regs, int64_t row, bsq_cigar_job *jobs,
+                              int64_t first) {
+  int n = 0;
+  /* number of XA candidates per primary (tag_xaxb prints the tag only up to max_XA_hits) */
+  uint16_t cbuf[2][128], *cnt_pri = cbuf[0], *cnt_alt = cbuf[1];
+  const int xa = !(opt->flag & BQ_F_ALL) && regs->n > 1;
+  if (xa) {
+    if (regs->n > 128) { cnt_pri = malloc(sizeof(uint16_t) * 2 * regs->n); cnt_alt = cnt_pri + regs->n; }
+    memset(cnt_pri, 0, sizeof(uint16_t) * regs->n); memset(cnt_alt, 0, sizeof(uint16_t) * regs->n);
+    for (size_t i = 0; i < regs->n; ++i) {
+      const int r = get_pri_idx(opt->XA_drop_ratio, regs->a, (int)i);
+      if (r >= 0 && (size_t)r < regs->n) { uint16_t *c = regs->a[i].is_alt ? &cnt_alt[r] : &cnt_pri[r]; if (*c < 0xffff) ++*c; }
+    }
+  }
+  for (size_t k = 0; k < regs->n; ++k) {
+    bq_reg_t *p = &regs->a[k];
+    int want = 0;
+    if (p->rb < 0 || p->re < 0 || p->rid < 0) continue;
+    if (p->secondary < 0) want = p->score >= opt->T;
+    else if ((opt->flag & BQ_F_ALL) && !p->is_alt) want = p->score >= opt->T && (p->secondary >= INT_MAX || p->score >= regs->a[p->secondary].score * opt->drop_ratio);
+    if (!want && xa) { /* XA of its primary, if that one prints the tag at all */
+      const int r = get_pri_idx(opt->XA_drop_ratio, regs->a, (int)k);
+      if (r >= 0 && (size_t)r < regs->n && regs->a[r].score >= opt->T) want = cnt_pri[r] <= opt->max_XA_hits && cnt_alt[r] <= opt->max_XA_hits_alt;
+    }
+    if (!want) continue;
+    if (jobs) { cigar_job(opt, ref, s, p, row, &jobs[n]); p->dp_job = (int)(first + n + 1); }
+    ++n;
+  }
+  if (cnt_pri != cbuf[0]) free(cnt_pri);
+  return n;
 }
 
 static void tag_xaxb(const bq_opt_t *opt, const bq_ref_t *ref, bq_read_t *s, const bq_reg_t *p0, const bq_regv_t *regs0, bq_str_t *out) {
@@ -861,6 +1008,9 @@ void bq_read_clipping(bq_read_t *s, const uint8_t *adaptor, int l_adaptor, const
 /* ---------------- the batch driver: mem_process_seqs (bwamem.c:432-476) ---------------- */
 
 
+/* stages of the host phase 2 (one parallel section each, items = reads or pairs) */
+enum { ST_MERGE = 1, ST_MS_COUNT, ST_MS_FILL, ST_MARK, ST_CIG_FILL, ST_SAM };
+
 typedef struct {
   const bq_opt_t *opt; const bq_ref_t *ref; bq_read_t *seqs; bq_regv_t *regs; bq_pestat_t pes; int64_t n_processed;
   const char *rg_id; int n_items, n_threads, pe, stage;
@@ -871,6 +1021,13 @@ typedef struct {
   bq_str_t *sam_slab;   /* per worker thread: SAM text of the reads it formatted */
   size_t *sam_off;      /* per read: offset of its text in its thread's slab */
   uint8_t *sam_thr;     /* per read: which thread's slab */
+  /* batched DP on the GPU (bsq_dp_*), when the batch has a context */
+  int use_dp;
+  int64_t *ms_first;            /* per pair (+1): its mate-rescue jobs [ms_first[p], ms_first[p+1]) */
+  bsq_matesw_job *mjobs; bsq_matesw_res *mres; uint32_t *mkeys;
+  int64_t *cg_first;            /* per item (+1): its CIGAR jobs */
+  bsq_cigar_job *cjobs; bsq_cigar_res *cres;
+  dp_cig_t cig;                 /* results as set_sam sees them */
 } work_t;
 
 static void reg_from_dev(const bsq_reg *d, bq_reg_t *r) {
@@ -880,7 +1037,8 @@ static void reg_from_dev(const bsq_reg *d, bq_reg_t *r) {
 }
 
 static void work_item(work_t *w, long i, int tid) {
-  if (w->stage == 1) { /* gather the regions of read i in the reference's order and merge them */
+  switch (w->stage) {
+  case ST_MERGE: { /* gather the regions of read i in the reference's order and merge them */
     bq_regv_t *rv = &w->regs[i];
     rv->n = rv->n_pri = 0;
     /* the regions of read i live in a slice of the batch's pool: room for every device region of its tasks + 2
@@ -891,34 +1049,80 @@ static void work_item(work_t *w, long i, int tid) {
       for (int64_t k = w->reg_off[task]; k < w->reg_off[task + 1]; ++k) reg_from_dev(&w->dev_regs[k], &rv->a[rv->n++]); /* the slice has room for all of them */
     }
     bq_merge_regions(w->opt, w->ref, w->seqs[i].seq, w->seqs[i].l_seq, rv);
-  } else if (!w->pe) {
-    tl_sam_slab = &w->sam_slab[tid];
-    if (tl_sam_slab->m == 0) { tl_sam_slab->s = bq_big_alloc((size_t)(w->n_items / w->n_threads + 1) * (2 * (size_t)w->seqs[i].l_seq0 + 256), &tl_sam_slab->m); tl_sam_slab->s[0] = 0; }
-    bq_mark_primary(w->opt, &w->regs[i], w->n_processed + i);
-    for (size_t k = 0; k < w->regs[i].n; ++k) w->regs[i].a[k].flag = 0;
-    bq_reg2sam_se(w->opt, w->ref, &w->seqs[i], &w->regs[i], w->rg_id);
-  } else {
-    tl_sam_slab = &w->sam_slab[tid];
-    if (tl_sam_slab->m == 0) { tl_sam_slab->s = bq_big_alloc((size_t)(w->n_items / w->n_threads + 1) * 2 * (2 * (size_t)w->seqs[i << 1].l_seq0 + 256), &tl_sam_slab->m); tl_sam_slab->s[0] = 0; }
+    return;
+  }
+  case ST_MS_COUNT: case ST_MS_FILL: { /* pair i: its mate-rescue alignments as jobs of one bsq_dp_matesw batch */
+    const int64_t row[2] = {w->task_of_read[i << 1], w->task_of_read[(i << 1) + 1]};
+    if (w->n_task_of_read[i << 1] == 0 || w->n_task_of_read[(i << 1) + 1] == 0) { if (w->stage == ST_MS_COUNT) w->ms_first[i + 1] = 0; return; }
+    if (w->stage == ST_MS_COUNT)
+      w->ms_first[i + 1] = matesw_pair(w->opt, w->ref, w->pes, &w->seqs[i << 1], &w->regs[i << 1], 0, 0, 0, row, 0);
+    else if (w->ms_first[i + 1] > w->ms_first[i])
+      matesw_pair(w->opt, w->ref, w->pes, &w->seqs[i << 1], &w->regs[i << 1], 0, w->mjobs + w->ms_first[i], w->mkeys + w->ms_first[i], row, 1);
+    return;
+  }
+  case ST_MARK: { /* mate rescue (replaying the GPU's alignments), primary marking; number of CIGAR jobs of the item */
     const double p0 = g_prof > 0 ? bq_now() : 0;
-    if (!(w->opt->flag & BQ_F_NO_RESCUE)) bq_matesw(w->opt, w->ref, w->pes, &w->seqs[i << 1], &w->regs[i << 1]);
+    if (!w->pe) {
+      bq_mark_primary(w->opt, &w->regs[i], w->n_processed + i);
+      for (size_t k = 0; k < w->regs[i].n; ++k) w->regs[i].a[k].flag = 0;
+      if (w->use_dp) w->cg_first[i + 1] = w->n_task_of_read[i] ? predict_cigar_jobs(w->opt, w->ref, &w->seqs[i], &w->regs[i], 0, 0, 0) : 0;
+      return;
+    }
+    if (!(w->opt->flag & BQ_F_NO_RESCUE)) {
+      ms_pre_t pre = {w->mres, w->mkeys, 0, 0};
+      if (w->ms_first) { pre.cur = w->ms_first[i]; pre.end = w->ms_first[i + 1]; }
+      matesw_pair(w->opt, w->ref, w->pes, &w->seqs[i << 1], &w->regs[i << 1], w->ms_first ? &pre : 0, 0, 0, 0, 0);
+    }
     const double p1 = g_prof > 0 ? bq_now() : 0;
     bq_mark_primary(w->opt, &w->regs[i << 1 | 0], i << 1 | 0); /* PE ids lack n_processed (bwamem.c:408,413) */
     bq_mark_primary(w->opt, &w->regs[i << 1 | 1], i << 1 | 1);
     for (int e = 0; e < 2; ++e)
       for (size_t k = 0; k < w->regs[i << 1 | e].n; ++k) w->regs[i << 1 | e].a[k].flag = 0;
+    if (w->use_dp) {
+      int n = 0;
+      for (int e = 0; e < 2; ++e)
+        if (w->n_task_of_read[i << 1 | e]) n += predict_cigar_jobs(w->opt, w->ref, &w->seqs[i << 1 | e], &w->regs[i << 1 | e], 0, 0, 0);
+      w->cg_first[i + 1] = n;
+    }
+    if (g_prof > 0) {
+      const double p2 = bq_now();
+      pthread_mutex_lock(&g_prof_mu);
+      g_t_mate += p1 - p0; g_t_mark += p2 - p1;
+      pthread_mutex_unlock(&g_prof_mu);
+    }
+    return;
+  }
+  case ST_CIG_FILL: { /* the CIGAR jobs of the item, at the offsets the counts gave */
+    int64_t at = w->cg_first[i];
+    if (at == w->cg_first[i + 1]) return;
+    const long lo = w->pe ? i << 1 : i, hi = w->pe ? (i << 1) + 2 : i + 1;
+    for (long r = lo; r < hi; ++r)
+      if (w->n_task_of_read[r]) at += predict_cigar_jobs(w->opt, w->ref, &w->seqs[r], &w->regs[r], w->task_of_read[r], w->cjobs + at, at);
+    return;
+  }
+  default: break;
+  }
+  /* ST_SAM: pairing, mapQ, SAM text */
+  tl_sam_slab = &w->sam_slab[tid];
+  tl_dp_cig = w->use_dp ? &w->cig : 0;
+  if (!w->pe) {
+    if (tl_sam_slab->m == 0) { tl_sam_slab->s = bq_big_alloc((size_t)(w->n_items / w->n_threads + 1) * (2 * (size_t)w->seqs[i].l_seq0 + 256), &tl_sam_slab->m); tl_sam_slab->s[0] = 0; }
+    bq_reg2sam_se(w->opt, w->ref, &w->seqs[i], &w->regs[i], w->rg_id);
+  } else {
+    if (tl_sam_slab->m == 0) { tl_sam_slab->s = bq_big_alloc((size_t)(w->n_items / w->n_threads + 1) * 2 * (2 * (size_t)w->seqs[i << 1].l_seq0 + 256), &tl_sam_slab->m); tl_sam_slab->s[0] = 0; }
     const double p2 = g_prof > 0 ? bq_now() : 0;
     bq_reg2sam_pe(w->opt, w->ref, (uint64_t)((w->n_processed >> 1) + i), &w->seqs[i << 1], &w->regs[i << 1], w->pes, w->rg_id);
     if (g_prof > 0) {
       const double p3 = bq_now();
       pthread_mutex_lock(&g_prof_mu);
-      g_t_mate += p1 - p0; g_t_mark += p2 - p1; g_t_sam += p3 - p2;
+      g_t_sam += p3 - p2;
       pthread_mutex_unlock(&g_prof_mu);
     }
   }
-  if (w->stage == 2) { /* the regions of this item are done with: release them here, on the worker */
+  { /* the regions of this item are done with: release them here, on the worker */
     const long lo = w->pe ? i << 1 : i, hi = w->pe ? (i << 1) + 2 : i + 1;
     tl_sam_slab = 0;
+    tl_dp_cig = 0;
     for (long r = lo; r < hi; ++r) { /* the text is already in this thread's slab (sam_out_end); a stray own string is moved there */
       bq_read_t *rd = &w->seqs[r];
       if (rd->sam_in_slab) { w->sam_off[r] = rd->sam_off; w->sam_thr[r] = (uint8_t)tid; continue; }
@@ -931,7 +1135,7 @@ static void work_item(work_t *w, long i, int tid) {
       rd->sam = 0; rd->sam_in_slab = 1;
     }
     for (long r = lo; r < hi; ++r) {
-      for (size_t k = 0; k < w->regs[r].n; ++k) if (w->regs[r].a[k].n_cigar > 0) free(w->regs[r].a[k].cigar);
+      for (size_t k = 0; k < w->regs[r].n; ++k) if (w->regs[r].a[k].n_cigar > 0 && !w->regs[r].a[k].cigar_ext) free(w->regs[r].a[k].cigar);
       if (!w->regs[r].pooled) free(w->regs[r].a);
       w->regs[r].a = 0; w->regs[r].n = 0;
     }
@@ -1027,6 +1231,7 @@ static void run_threads(work_t *w, int n_items) {
 typedef struct bq_slot {
   void *tseq; size_t tseq_cap;   /* page-locked task rows */
   void *regs; size_t regs_cap;   /* page-locked regions */
+  void *mjobs, *mres, *cjobs, *cres; size_t mjobs_cap, mres_cap, cjobs_cap, cres_cap; /* page-locked DP jobs / results */
   struct bq_slot *next;
 } bq_slot_t;
 static pthread_mutex_t slot_mu = PTHREAD_MUTEX_INITIALIZER;
@@ -1070,6 +1275,9 @@ struct bq_batch {
   int32_t *tlen;
   uint8_t *par;
   bq_slot_t *slot;
+  /* host phase 2 between its two halves (bq_batch_finish_a / _b) */
+  bsq_dp *dp;
+  struct bq_fin *fin;
 };
 
 bq_batch_t *bq_batch_prep(const bq_opt_t *opt, int64_t n_processed, int n, bq_read_t *seqs, int *rc_out) {
@@ -1137,9 +1345,10 @@ bq_batch_t *bq_batch_prep(const bq_opt_t *opt, int64_t n_processed, int n, bq_re
 }
 
 /* GPU part: H2D of the task rows, the phase-1 kernels, D2H of the regions (all through page-locked memory) */
-int bq_batch_run(bsq_aligner *al, bq_batch_t *b) {
+int bq_batch_run(bsq_aligner *al, bsq_dp *dp, bq_batch_t *b) {
   int rc;
   int64_t n_regs = 0;
+  b->dp = dp;
   if (b->nt == 0) { b->reg_off[0] = 0; return 0; }
   const double t0 = getenv("BQ_TIMING") ? bq_now() : 0;
   if ((rc = bsq_aligner_stage(al, b->nt, b->slot->tseq, b->stride, b->tlen, b->par))) return rc;
@@ -1171,10 +1380,10 @@ static void batch_free(bq_batch_t *b) {
 
 void bq_batch_discard(bq_batch_t *b) { if (b) batch_free(b); }
 
-bq_batch_t *bq_batch_gpu(const bq_opt_t *opt, bsq_aligner *al, int64_t n_processed, int n, bq_read_t *seqs, int *rc_out) {
+bq_batch_t *bq_batch_gpu(const bq_opt_t *opt, bsq_aligner *al, bsq_dp *dp, int64_t n_processed, int n, bq_read_t *seqs, int *rc_out) {
   int rc = 0;
   bq_batch_t *b = bq_batch_prep(opt, n_processed, n, seqs, &rc);
-  if (b && (rc = bq_batch_run(al, b))) { batch_free(b); b = 0; }
+  if (b && (rc = bq_batch_run(al, dp, b))) { batch_free(b); b = 0; }
   if (rc_out) *rc_out = rc;
   return b;
 }
@@ -1198,15 +1407,34 @@ static void pool_give(bq_reg_t *p, size_t cap) {
   free(p);
 }
 
-void bq_batch_finish(const bq_opt_t *opt, const bq_ref_t *ref, bq_batch_t *b, const bq_pestat_t *pes0, const char *rg_id) {
-  const int pe = (opt->flag & BQ_F_PE) != 0, n = b->n;
+/* what the first half of phase 2 leaves for the second */
+typedef struct bq_fin {
   work_t w;
-  memset(&w, 0, sizeof w);
-  w.opt = opt; w.ref = ref; w.seqs = b->seqs; w.n_processed = b->n_processed; w.rg_id = rg_id; w.n_threads = opt->n_threads; w.pe = pe;
+  size_t pool_cap;
+  int64_t *pool_off;
+  int64_t n_cjobs;
+  int cig_submitted;
+  double t0, t_a;
+} bq_fin_t;
+
+static int64_t prefix_counts(int64_t *first, int n_items) { /* first[i + 1] holds the count of item i on entry */
+  first[0] = 0;
+  for (int i = 0; i < n_items; ++i) first[i + 1] += first[i];
+  return first[n_items];
+}
+
+int bq_batch_finish_a(const bq_opt_t *opt, const bq_ref_t *ref, bq_batch_t *b, const bq_pestat_t *pes0) {
+  const int pe = (opt->flag & BQ_F_PE) != 0, n = b->n;
+  int rc = 0;
+  bq_fin_t *f = calloc(1, sizeof *f);
+  work_t *w = &f->w;
+  b->fin = f;
+  w->opt = opt; w->ref = ref; w->seqs = b->seqs; w->n_processed = b->n_processed; w->n_threads = opt->n_threads; w->pe = pe;
+  w->use_dp = b->dp != 0 && b->nt > 0;
   size_t regs_cap_ = 0;
-  w.regs = bq_big_alloc(((size_t)n + 1) * sizeof(bq_regv_t), &regs_cap_);
-  memset(w.regs, 0, ((size_t)n + 1) * sizeof(bq_regv_t));
-  w.dev_regs = b->dregs; w.reg_off = b->reg_off; w.task_of_read = b->task_of_read; w.n_task_of_read = b->n_task;
+  w->regs = bq_big_alloc(((size_t)n + 1) * sizeof(bq_regv_t), &regs_cap_);
+  memset(w->regs, 0, ((size_t)n + 1) * sizeof(bq_regv_t));
+  w->dev_regs = b->dregs; w->reg_off = b->reg_off; w->task_of_read = b->task_of_read; w->n_task_of_read = b->n_task;
   /* one pool for the host regions of the whole batch instead of one allocation per read (the per-read vectors were
    * allocated by one worker and freed by another, which glibc's per-thread caches cannot serve) */
   int64_t *pool_off = malloc(sizeof(int64_t) * (size_t)(n + 1));
@@ -1216,50 +1444,140 @@ void bq_batch_finish(const bq_opt_t *opt, const bq_ref_t *ref, bq_batch_t *b, co
     for (int t = 0; t < b->n_task[i]; ++t) tot += b->reg_off[b->task_of_read[i] + t + 1] - b->reg_off[b->task_of_read[i] + t];
     pool_off[i + 1] = pool_off[i] + tot;
   }
-  size_t pool_cap = 0;
-  w.reg_pool = pool_take((size_t)pool_off[n] + 1, &pool_cap);
-  w.pool_off = pool_off;
-  w.stage = 1;
-  double t0_ = getenv("BQ_TIMING") ? bq_now() : 0;
-  run_threads(&w, n);
-  const double tm_ = t0_ > 0 ? bq_now() : 0;
-  if (t0_ > 0) fprintf(stderr, "[bq_finish] merge %.3f", tm_ - t0_);
-  slot_put(b->slot); b->slot = 0; b->dregs = 0;  /* the regions now live in w.regs */
-  if (pe) { if (pes0) w.pes = *pes0; else w.pes = bq_pestat(opt, ref, n, w.regs); }
-  w.stage = 2;
-  double t1_ = t0_ > 0 ? bq_now() : 0;
+  w->reg_pool = pool_take((size_t)pool_off[n] + 1, &f->pool_cap);
+  w->pool_off = f->pool_off = pool_off;
+  f->t0 = getenv("BQ_TIMING") ? bq_now() : 0;
+  /* the read rows go to the DP context while the regions are merged (asynchronous copy from the page-locked rows) */
+  if (w->use_dp && (rc = bsq_dp_set_reads(b->dp, b->nt, b->slot->tseq, b->stride, b->tlen))) return rc;
+  w->stage = ST_MERGE;
+  run_threads(w, n);
+  const double tm_ = f->t0 > 0 ? bq_now() : 0;
+  if (pe) { if (pes0) w->pes = *pes0; else w->pes = bq_pestat(opt, ref, n, w->regs); }
+  const double tp_ = f->t0 > 0 ? bq_now() : 0;
   if (g_prof < 0) g_prof = getenv("BQ_PROF") != 0;
   g_t_mate = g_t_mark = g_t_sam = g_t_pair = g_t_setsam = g_t_fmt = 0;
+  const int n_items = pe ? n >> 1 : n;
+  int64_t n_mjobs = 0;
+  if (w->use_dp && pe && !(opt->flag & BQ_F_NO_RESCUE)) { /* mate rescue: plan, one kernel, replay (in ST_MARK) */
+    w->ms_first = calloc((size_t)n_items + 2, sizeof(int64_t));
+    w->stage = ST_MS_COUNT;
+    run_threads(w, n_items);
+    n_mjobs = prefix_counts(w->ms_first, n_items);
+    if (n_mjobs > 0) {
+      bq_slot_t *sl = b->slot;
+      if ((rc = slot_reserve(&sl->mjobs, &sl->mjobs_cap, (size_t)n_mjobs * sizeof(bsq_matesw_job))) ||
+          (rc = slot_reserve(&sl->mres, &sl->mres_cap, (size_t)n_mjobs * sizeof(bsq_matesw_res))))
+        return rc;
+      w->mjobs = sl->mjobs; w->mres = sl->mres;
+      w->mkeys = malloc(sizeof(uint32_t) * (size_t)n_mjobs);
+      w->stage = ST_MS_FILL;
+      run_threads(w, n_items);
+      if ((rc = bsq_dp_matesw_submit(b->dp, n_mjobs, w->mjobs, w->mres)) || (rc = bsq_dp_matesw_wait(b->dp))) return rc;
+      __atomic_fetch_add(&g_dp_stat[3], n_mjobs, __ATOMIC_RELAXED);
+    }
+  }
+  const double tr_ = f->t0 > 0 ? bq_now() : 0;
+  double ts_ = 0;
+  if (w->use_dp) w->cg_first = calloc((size_t)n_items + 2, sizeof(int64_t));
+  w->stage = ST_MARK;
+  run_threads(w, n_items);
+  if (w->use_dp) { /* the final CIGARs of the batch as one asynchronous kernel; _b picks them up */
+    f->n_cjobs = prefix_counts(w->cg_first, n_items);
+    bq_slot_t *sl = b->slot;
+    if ((rc = slot_reserve(&sl->cjobs, &sl->cjobs_cap, (size_t)(f->n_cjobs + 1) * sizeof(bsq_cigar_job))) ||
+        (rc = slot_reserve(&sl->cres, &sl->cres_cap, (size_t)(f->n_cjobs + 1) * sizeof(bsq_cigar_res))))
+      return rc;
+    w->cjobs = sl->cjobs; w->cres = sl->cres;
+    w->stage = ST_CIG_FILL;
+    run_threads(w, n_items);
+    ts_ = f->t0 > 0 ? bq_now() : 0;
+    if ((rc = bsq_dp_cigar_submit(b->dp, f->n_cjobs, w->cjobs, w->cres))) return rc;
+    ts_ = f->t0 > 0 ? bq_now() - ts_ : 0;
+    f->cig_submitted = 1;
+    __atomic_fetch_add(&g_dp_stat[0], f->n_cjobs, __ATOMIC_RELAXED);
+  }
+  if (f->t0 > 0) {
+    f->t_a = bq_now() - f->t0;
+    fprintf(stderr, "[bq_finish_a] merge %.3f pestat %.3f rescue jobs %lld (%.3f s) mark+predict %.3f s, cigar jobs %lld (submit %.3f s)\n", tm_ - f->t0, tp_ - tm_,
+            (long long)n_mjobs, tr_ - tp_, bq_now() - tr_ - ts_, (long long)f->n_cjobs, ts_);
+  }
+  return 0;
+}
+
+int bq_batch_finish_wait(bq_batch_t *b) {
+  bq_fin_t *f = b->fin;
+  if (!f || !f->cig_submitted) return 0;
+  f->cig_submitted = 0;
+  const uint32_t *blob = 0;
+  int64_t words = 0;
+  const int rc = bsq_dp_cigar_wait(b->dp, &blob, &words);
+  if (rc) return rc;
+  f->w.cig.res = f->w.cres; f->w.cig.blob = blob; f->w.cig.n = f->n_cjobs;
+  return 0;
+}
+
+void bq_batch_finish_b(const bq_opt_t *opt, const bq_ref_t *ref, bq_batch_t *b, const char *rg_id) {
+  bq_fin_t *f = b->fin;
+  work_t *w = &f->w;
+  const int pe = w->pe, n = b->n;
+  const double t1_ = f->t0 > 0 ? bq_now() : 0;
+  w->rg_id = rg_id;
   {
     const int nt = opt->n_threads < 1 ? 1 : (opt->n_threads > 255 ? 255 : opt->n_threads);
-    w.sam_slab = calloc((size_t)nt, sizeof(bq_str_t));
-    w.sam_off = malloc(sizeof(size_t) * (size_t)(n + 1));
-    w.sam_thr = malloc((size_t)n + 1);
+    w->sam_slab = calloc((size_t)nt, sizeof(bq_str_t));
+    w->sam_off = malloc(sizeof(size_t) * (size_t)(n + 1));
+    w->sam_thr = malloc((size_t)n + 1);
   }
-  run_threads(&w, pe ? n >> 1 : n);
+  w->stage = ST_SAM;
+  run_threads(w, pe ? n >> 1 : n);
   if (n > 0) { /* .sam pointers into the (now final) slabs; the slabs belong to the first read of the batch */
-    const int nt = w.n_threads;
+    const int nt = w->n_threads;
     for (int i = 0; i < n; ++i)
-      if (b->seqs[i].sam_in_slab) b->seqs[i].sam = w.sam_slab[w.sam_thr[i]].s + w.sam_off[i];
+      if (b->seqs[i].sam_in_slab) b->seqs[i].sam = w->sam_slab[w->sam_thr[i]].s + w->sam_off[i];
     b->seqs[0].sam_slabs = malloc(sizeof(char *) * (size_t)nt);
     b->seqs[0].n_sam_slabs = nt;
-    for (int k = 0; k < nt; ++k) b->seqs[0].sam_slabs[k] = w.sam_slab[k].s;
+    for (int k = 0; k < nt; ++k) b->seqs[0].sam_slabs[k] = w->sam_slab[k].s;
   }
-  free(w.sam_slab); free(w.sam_off); free(w.sam_thr);
-  if (t0_ > 0) fprintf(stderr, " pestat %.3f phase2 %.3f s\n", t1_ - tm_, bq_now() - t1_);
+  free(w->sam_slab); free(w->sam_off); free(w->sam_thr);
+  if (f->t0 > 0) fprintf(stderr, "[bq_finish_b] pairing + SAM %.3f s\n", bq_now() - t1_);
   if (g_prof > 0) fprintf(stderr, "[bq_prof] thread-seconds: matesw %.3f mark_primary %.3f reg2sam %.3f (pair %.3f set_sam %.3f format %.3f)\n",
                           g_t_mate, g_t_mark, g_t_sam, g_t_pair, g_t_setsam, g_t_fmt);
-  bq_big_free(w.regs);
-  pool_give(w.reg_pool, pool_cap);
-  free(pool_off);
+  bq_big_free(w->regs);
+  pool_give(w->reg_pool, f->pool_cap);
+  free(f->pool_off); free(w->ms_first); free(w->mkeys); free(w->cg_first);
+  free(f);
+  b->fin = 0;
   batch_free(b);
 }
 
-int bq_process_seqs(const bq_opt_t *opt, bsq_aligner *al, const bq_ref_t *ref, int64_t n_processed, int n, bq_read_t *seqs,
+static void fin_abandon(bq_batch_t *b) { /* a DP call failed: release what _a built (the reads stay with the caller) */
+  bq_fin_t *f = b->fin;
+  if (f) {
+    if (f->cig_submitted) { const uint32_t *bl; int64_t wd; bsq_dp_cigar_wait(b->dp, &bl, &wd); }
+    work_t *w = &f->w;
+    for (int r = 0; r < b->n; ++r) if (w->regs[r].a && !w->regs[r].pooled) free(w->regs[r].a);
+    bq_big_free(w->regs);
+    pool_give(w->reg_pool, f->pool_cap);
+    free(f->pool_off); free(w->ms_first); free(w->mkeys); free(w->cg_first);
+    free(f);
+    b->fin = 0;
+  }
+  batch_free(b);
+}
+void bq_batch_abandon(bq_batch_t *b) { if (b) fin_abandon(b); }
+
+int bq_batch_finish(const bq_opt_t *opt, const bq_ref_t *ref, bq_batch_t *b, const bq_pestat_t *pes0, const char *rg_id) {
+  int rc = bq_batch_finish_a(opt, ref, b, pes0);
+  if (!rc) rc = bq_batch_finish_wait(b);
+  if (rc) { fin_abandon(b); return rc; }
+  bq_batch_finish_b(opt, ref, b, rg_id);
+  return 0;
+}
+
+int bq_process_seqs(const bq_opt_t *opt, bsq_aligner *al, bsq_dp *dp, const bq_ref_t *ref, int64_t n_processed, int n, bq_read_t *seqs,
                     const bq_pestat_t *pes0, const char *rg_id) {
   int rc = 0;
-  bq_batch_t *b = bq_batch_gpu(opt, al, n_processed, n, seqs, &rc);
+  bq_batch_t *b = bq_batch_gpu(opt, al, dp, n_processed, n, seqs, &rc);
   if (!b) return rc ? rc : BSQ_ENOMEM;
-  bq_batch_finish(opt, ref, b, pes0, rg_id);
-  return 0;
+  return bq_batch_finish(opt, ref, b, pes0, rg_id);
 }

@@ -46,6 +46,7 @@ static void q_get(q1_t *q, bq_batch_t **b, bq_read_t **seqs, int *n, int *rc, in
 typedef struct {
   const bq_opt_t *opt;
   bsq_aligner *al[BQ_MAX_LANES];
+  bsq_dp *dp[BQ_MAX_LANES]; /* batched phase-2 DP of the lane's device (or NULL) */
   int n_al;
   volatile int abort_; /* set on the first failure: the source stops reading, the lanes stop computing */
   bq_source_fn src;
@@ -96,7 +97,7 @@ static void *stage_b(void *arg) {
     q_get(&p->qa[L->lane], &b, &seqs, &n, &rc, &end);
     if (b && !failed && !p->abort_) {
       const double t0 = pnow();
-      rc = bq_batch_run(p->al[L->lane], b);
+      rc = bq_batch_run(p->al[L->lane], p->dp[L->lane], b);
       L->t_gpu += pnow() - t0;
       if (rc) { failed = rc; p->abort_ = 1; }
     } else if (b) rc = failed ? failed : BSQ_EINVAL;  /* after a failure (here or on another lane) batches are only drained */
@@ -120,13 +121,13 @@ static void *stage_d(void *arg) {
   }
 }
 
-int bq_pipeline_run(const bq_opt_t *opt, const bq_ref_t *ref, bsq_aligner *const *als, int n_al, bq_source_fn src, void *src_ctx, bq_sink_fn sink,
-                    void *sink_ctx, const bq_pestat_t *pes0, const char *rg_id) {
+int bq_pipeline_run(const bq_opt_t *opt, const bq_ref_t *ref, bsq_aligner *const *als, bsq_dp *const *dps, int n_al, bq_source_fn src, void *src_ctx,
+                    bq_sink_fn sink, void *sink_ctx, const bq_pestat_t *pes0, const char *rg_id) {
   pipe_ctx_t p;
   memset(&p, 0, sizeof p);
   if (n_al < 1 || n_al > BQ_MAX_LANES) return BSQ_EINVAL;
   p.opt = opt; p.n_al = n_al; p.src = src; p.src_ctx = src_ctx;
-  for (int k = 0; k < n_al; ++k) p.al[k] = als[k];
+  for (int k = 0; k < n_al; ++k) { p.al[k] = als[k]; p.dp[k] = dps ? dps[k] : 0; }
   p.sink = sink; p.sink_ctx = sink_ctx;
   for (int k = 0; k < n_al; ++k) { q_init(&p.qa[k]); q_init(&p.qb[k]); }
   q_init(&p.qc);
@@ -138,20 +139,35 @@ int bq_pipeline_run(const bq_opt_t *opt, const bq_ref_t *ref, bsq_aligner *const
   pthread_create(&td, 0, stage_d, &p);
   int ret = 0;
   double t_wait = 0, t_fin = 0;
+  /* Stage C is software-pipelined around the asynchronous CIGAR kernel of the batch's DP context: the first half of
+   * phase 2 of batch k (merge .. primary marking, CIGAR jobs submitted) runs before the second half of batch k-1
+   * (pairing, SAM text), so the kernel of k overlaps the formatting of k-1.  `held` = batch k-1 between its halves. */
+  struct { bq_batch_t *b; bq_read_t *seqs; int n; } held = {0, 0, 0};
+#define FLUSH_HELD(END) do { if (held.b) { bq_batch_finish_b(opt, ref, held.b, rg_id); q_put(&p.qc, 0, held.seqs, held.n, 0, END); held.b = 0; } } while (0)
   for (int seq = 0;; ++seq) { /* batches come back in sequence order: lane seq % n_al */
     bq_batch_t *b; bq_read_t *seqs; int n, rc, end;
     double t0 = pnow();
     q_get(&p.qb[seq % p.n_al], &b, &seqs, &n, &rc, &end);
     t_wait += pnow() - t0; t0 = pnow();
-    if (b && rc == 0) {
-      bq_batch_finish(opt, ref, b, pes0, rg_id);
+    int rcw;
+    if (held.b && (rcw = bq_batch_finish_wait(held.b))) { /* its CIGARs did not come back: the batch fails */
+      if (!ret) ret = rcw;
+      p.abort_ = 1;
+      bq_batch_abandon(held.b);
+      q_put(&p.qc, 0, held.seqs, held.n, rcw, 0);
+      held.b = 0;
+    }
+    if (b && rc == 0 && (rc = bq_batch_finish_a(opt, ref, b, pes0)) == 0) {
+      FLUSH_HELD(0);
+      held.b = b; held.seqs = seqs; held.n = n;
       t_fin += pnow() - t0;
-      q_put(&p.qc, 0, seqs, n, 0, end);
     } else {
+      FLUSH_HELD(0);
+      t_fin += pnow() - t0;
       if (rc && !ret) ret = rc;
       if (rc) p.abort_ = 1;
-      if (b) bq_batch_discard(b);
-      q_put(&p.qc, 0, seqs, n, rc ? rc : -1, end); /* failed batch: the sink only frees */
+      if (b) { if (rc) bq_batch_abandon(b); else bq_batch_discard(b); }
+      q_put(&p.qc, 0, seqs, n, rc ? rc : -1, end); /* failed batch / end marker: the sink only frees */
     }
     if (end) { /* drain the end markers of the other lanes */
       for (int k = 1; k < p.n_al; ++k) {
@@ -161,6 +177,7 @@ int bq_pipeline_run(const bq_opt_t *opt, const bq_ref_t *ref, bsq_aligner *const
       break;
     }
   }
+#undef FLUSH_HELD
   pthread_join(ta, 0);
   for (int k = 0; k < p.n_al; ++k) pthread_join(tb[k], 0);
   pthread_join(td, 0);

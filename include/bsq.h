@@ -167,6 +167,63 @@ void bsq_host_free(void *p);
  * c[15] = microseconds of k_chain_warp alone (c[7] = both chaining kernels) */
 int bsq_aligner_counters(const bsq_aligner *al, int64_t *c, int n);
 
+/* ---- the two dynamic-programming steps of phase 2 (after pairing), batched on the GPU ----
+ *   bsq_dp_cigar   <- mem_alnreg_setSAM's band loop  lib/aln/mem_alnreg.c:40-75  around
+ *                     bis_bwa_gen_cigar2             lib/aln/bwa.c:290-428 (ksw_global2, lib/aln/ksw.c:504-606; MD/NM/ZC/ZR)
+ *   bsq_dp_matesw  <- ksw_align2                     lib/aln/ksw.c:343-365 (ksw_u8 :111-220, ksw_i16 :222-334) as called
+ *                     by mem_matesw                  lib/aln/mem_alnreg.c:395-493
+ * A bsq_dp context belongs to one device; it has its own stream and buffers and may be driven by another host thread
+ * than the bsq_aligner of the same device.  Reads are the nt4 rows of a batch (the rows handed to bsq_aligner_stage
+ * serve: row r at seqs + r*stride, lens[r] bases); jobs refer to them by row. */
+typedef struct bsq_dp bsq_dp;
+
+/* one final CIGAR (+MD) = one mem_alnreg_setSAM call: query = bases [qb,qe) of `row` (codes > 4 read as 4), reference
+ * [rb,re) in forward-reverse coordinates, first band w, doubled up to three times while the global score stays below
+ * truesc - a (mem_alnreg.c:60-70); clip5 / clip3 = soft-clip lengths to put in front / behind (0 = none) */
+typedef struct {
+  int64_t rb, re;
+  int32_t row, qb, qe, w, truesc, clip5, clip3;
+  uint8_t parent, pad_[3];
+} bsq_cigar_job;
+
+/* n_cigar < 0: the job is outside the kernel's limits (reference span > 1024) and must be done by the caller;
+ * n_cigar == 0: bis_bwa_gen_cigar2 returned no alignment.  Otherwise blob[off .. off+n_cigar) holds the final CIGAR
+ * words (BAM encoding; a leading / trailing deletion already removed, lead_del = length of the removed leading one;
+ * clips added) directly followed by the NUL-terminated MD text. */
+typedef struct {
+  int32_t n_cigar, NM, ZC, ZR, score, lead_del, bss_u;
+  uint32_t off; /* in 4-byte words */
+} bsq_cigar_res;
+
+/* one ksw_align2 call of mate rescue: query = reverse complement of `row` (l_ms = its length), target = reference
+ * [rb,re) in forward-reverse coordinates, matrix = use_ga ? gamat : ctmat, xtra as in ksw.h:34-37 */
+typedef struct {
+  int64_t rb, re;
+  int32_t row, xtra;
+  uint8_t use_ga, pad_[7];
+} bsq_matesw_job;
+
+/* kswr_t (lib/aln/ksw.h:39-43) */
+typedef struct { int32_t score, te, qe, score2, te2, tb, qb, pad_; } bsq_matesw_res;
+
+int bsq_dp_create(const bsq_index *idx, const bsq_opt *opt, bsq_dp **out);
+void bsq_dp_destroy(bsq_dp *dp);
+/* host->device copy of the rows (asynchronous on the context's stream; the host buffer must stay valid until the next
+ * bsq_dp_*_wait or bsq_dp_sync) */
+int bsq_dp_set_reads(bsq_dp *dp, int64_t n_rows, const uint8_t *seqs, int32_t stride, const int32_t *lens);
+int bsq_dp_sync(bsq_dp *dp);
+/* submit = H2D of the jobs + kernel + D2H of the results, all asynchronous; wait = block until they are back.
+ * res (n_jobs entries) is caller memory; the CIGAR/MD blob belongs to the context and stays valid until the next
+ * bsq_dp_cigar_wait on it (a new submission does not disturb it).  One submission of each kind may be in flight
+ * per context. */
+int bsq_dp_cigar_submit(bsq_dp *dp, int64_t n_jobs, const bsq_cigar_job *jobs, bsq_cigar_res *res);
+int bsq_dp_cigar_wait(bsq_dp *dp, const uint32_t **blob, int64_t *blob_words);
+int bsq_dp_matesw_submit(bsq_dp *dp, int64_t n_jobs, const bsq_matesw_job *jobs, bsq_matesw_res *res);
+int bsq_dp_matesw_wait(bsq_dp *dp);
+/* c[0] = CIGAR jobs, c[1] = of those ungapped, c[2] = DP cells of ksw_global2, c[3] = microseconds of the last k_cigar,
+ * c[4] = mate-rescue jobs, c[5] = microseconds of the last k_matesw, c[6] = blob re-runs (capacity grown) */
+int bsq_dp_counters(const bsq_dp *dp, int64_t *c, int n);
+
 /* ================= pileup (methylation caller) =================
  * Replaces the per-window hot loop of process_func (src/pileup.c:707-831: read filters, bisulfite-strand
  * inference, mate-overlap skip, per-base retention/conversion events), plp_getcnts (src/pileup.c:372-387)

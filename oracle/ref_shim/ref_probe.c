@@ -254,3 +254,37 @@ int64_t refp_process_seqs(refp_t *h, int n_threads, int64_t n_processed, int n, 
   free(bs);
   return tot;
 }
+
+/* bis_bwa_gen_cigar2 (bwa.c:290) on the loaded index; out = {score, n_cigar, NM, ZC, ZR, bss_u}; the CIGAR words
+ * go to cig (cap words), the MD text (stored behind the CIGAR by the reference) to md (cap_md bytes).
+ * Returns 1 when a CIGAR came back, 0 otherwise.  The query is modified and restored by the callee. */
+int refp_gen_cigar2(refp_t *h, const int8_t *mat, int o_del, int e_del, int o_ins, int e_ins, int w, int l_query, uint8_t *query,
+                    int64_t rb, int64_t re, uint8_t parent, int *out, uint32_t *cig, int cap, char *md, int cap_md) {
+  int score = 0, n_cigar = 0, NM = -1, bss_u = 0, i;
+  uint32_t ZC = 0, ZR = 0;
+  uint32_t *c = bis_bwa_gen_cigar2(mat, o_del, e_del, o_ins, e_ins, w, h->idx->bns->l_pac, h->idx->pac, l_query, query, rb, re, &score,
+                                   &n_cigar, &NM, &ZC, &ZR, &bss_u, parent);
+  out[0] = score; out[1] = n_cigar; out[2] = NM; out[3] = (int)ZC; out[4] = (int)ZR; out[5] = bss_u;
+  if (!c) return 0;
+  for (i = 0; i < n_cigar && i < cap; ++i) cig[i] = c[i];
+  strncpy(md, (char *)(c + n_cigar), cap_md - 1);
+  md[cap_md - 1] = 0;
+  free(c);
+  return 1;
+}
+
+/* ksw_align2 (ksw.c:343); out = {score, te, qe, score2, te2, tb, qb}.  query / target are modified and restored by the callee. */
+void refp_align2(int qlen, uint8_t *query, int tlen, uint8_t *target, const int8_t *mat, int o_del, int e_del, int o_ins, int e_ins,
+                 int xtra, int *out) {
+  kswr_t r = ksw_align2(qlen, query, tlen, target, 5, mat, o_del, e_del, o_ins, e_ins, xtra, 0);
+  out[0] = r.score; out[1] = r.te; out[2] = r.qe; out[3] = r.score2; out[4] = r.te2; out[5] = r.tb; out[6] = r.qb;
+}
+
+/* bns_get_seq (bntseq.c:402): bases [beg,end) in forward-reverse coordinates */
+int refp_get_seq(refp_t *h, int64_t beg, int64_t end, uint8_t *out, int cap) {
+  int64_t len = 0;
+  uint8_t *s = bns_get_seq(h->idx->bns->l_pac, h->idx->pac, beg, end, &len);
+  memcpy(out, s, len < cap ? len : cap);
+  free(s);
+  return (int)len;
+}

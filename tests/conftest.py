@@ -27,12 +27,21 @@ def build_hostemu() -> str:
     cs = os.path.join(ROOT, "biscuit_b200", "csrc")
     # the pileup half of the emulation is the oracle's restatement (test-only library: it may link the oracle)
     orc = os.path.join(ROOT, "oracle", "bsq_oracle_pileup.c")
-    deps = [src, orc, os.path.join(ROOT, "oracle", "bsq_oracle.h"), os.path.join(ROOT, "include", "bsq.h")]
+    dpc = os.path.join(ROOT, "tests", "hostemu", "hostemu_dp.c")
+    core = os.path.join(ROOT, "biscuit_b200", "host", "bq_core.c")
+    deps = [src, orc, dpc, core, os.path.join(ROOT, "biscuit_b200", "host", "bq.h"), os.path.join(ROOT, "oracle", "bsq_oracle.h"),
+            os.path.join(ROOT, "include", "bsq.h")]
     deps += [os.path.join(cs, f) for f in os.listdir(cs) if f.endswith((".h", ".cuh"))]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         obj = os.path.join(ROOT, "tests", "hostemu", "bsq_oracle_pileup.o")
         subprocess.check_call(["gcc", "-O2", "-g", "-std=gnu11", "-fPIC", "-c", "-o", obj, orc])
-        subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", out, src, obj, "-lm"])
+        # the phase-2 DP entry points (bsq_dp_*) answered by the host's scalar routines (test-only stand-in for bsq_dp.cu)
+        objs = [obj]
+        for c in (dpc, core):
+            o = os.path.join(ROOT, "tests", "hostemu", os.path.basename(c)[:-2] + ".o")
+            subprocess.check_call(["gcc", "-O2", "-g", "-std=gnu11", "-fPIC", "-c", "-o", o, c])
+            objs.append(o)
+        subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", out, src] + objs + ["-lm"])
     return out
 
 

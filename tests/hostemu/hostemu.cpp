@@ -246,6 +246,9 @@ int64_t hostemu_chain(const bsq_index *ixp, const bsq_opt *opt_, int parent, int
 }
 }  // extern "C"
 
+// for the C half of the emulation (hostemu_dp.c)
+extern "C" const uint8_t *hostemu_index_pac(const bsq_index *ix, int64_t *l_pac) { *l_pac = ix->d.l_pac; return ix->d.pac; }
+
 // staged execution on top of bsq_align_phase1 (plain host memory stands in for page-locked memory)
 extern "C" {
 int bsq_aligner_stage(bsq_aligner *al, int64_t n, const uint8_t *seqs, int32_t stride, const int32_t *lens, const uint8_t *parent) {
