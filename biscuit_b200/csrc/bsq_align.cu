@@ -131,6 +131,12 @@ struct bsq_aligner {
   DevBuf seqs, lens, parent, intv, n_intv, n_sa, sa_off, ranks, pos, status;
   DevBuf snodes, wchains, bnodes, order, ochains, oseeds, n_chains, frac_rep, srt, regs_tmp, n_regs, reg_off, regs;
   DevBuf cub_tmp, scalars, fb_flag, tiers, spans, aflag;
+  // results live in one of two slots (regs / reg_off and regs2 / reg_off2), alternating from run to run, so that a pipelined
+  // caller can copy the regions of batch k to the host (bsq_aligner_fetch_slot, own stream) while batch k+1 is being run
+  DevBuf regs2, reg_off2;
+  cudaStream_t stream_out;
+  int out_slot = 0;
+  int64_t out_tasks[2] = {0, 0}, out_regs[2] = {-1, -1};
   int64_t counters[16];
   int64_t n_staged = 0, n_regs_total = -1;
   int64_t fb_cap = 0;  // entries of the fallback-chaining workspace pools
@@ -959,6 +965,7 @@ int bsq_aligner_create(const bsq_index *ix, const bsq_opt *opt, bsq_aligner **ou
   memset(al->counters, 0, sizeof al->counters);
   CK(cudaStreamCreateWithFlags(&al->stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&al->stream2, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&al->stream_out, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&al->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&al->ev_join, cudaEventDisableTiming));
   for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&al->ev[i]));
   *out = al;
@@ -970,11 +977,12 @@ void bsq_aligner_destroy(bsq_aligner *al) {
   cudaSetDevice(al->idx->device);
   DevBuf *bufs[] = {&al->seqs, &al->lens, &al->parent, &al->intv, &al->n_intv, &al->n_sa, &al->sa_off, &al->ranks, &al->pos,
                     &al->status, &al->snodes, &al->wchains, &al->bnodes, &al->order, &al->ochains, &al->oseeds, &al->n_chains,
-                    &al->frac_rep, &al->srt, &al->regs_tmp, &al->n_regs, &al->reg_off, &al->regs, &al->cub_tmp, &al->scalars, &al->fb_flag, &al->tiers, &al->spans, &al->aflag};
+                    &al->frac_rep, &al->srt, &al->regs_tmp, &al->n_regs, &al->reg_off, &al->regs, &al->cub_tmp, &al->scalars, &al->fb_flag, &al->tiers, &al->spans, &al->aflag, &al->regs2, &al->reg_off2};
   for (DevBuf *b : bufs) b->release();
   al->seed_ws.release();
   for (int i = 0; i < 8; ++i) cudaEventDestroy(al->ev[i]);
   cudaStreamDestroy(al->stream);
+  cudaStreamDestroy(al->stream_out);
   cudaStreamDestroy(al->stream2); cudaEventDestroy(al->ev_fork); cudaEventDestroy(al->ev_join);
   delete al;
 }
@@ -1128,10 +1136,12 @@ static int phase1_device(bsq_aligner *al, int64_t n, int32_t stride, int64_t *to
   }
   CK(cudaGetLastError());
   CK(cudaEventRecord(al->ev[5], s));
-  if ((rc = scan_counts(al, al->n_regs.as<int32_t>(), al->reg_off.as<int64_t>(), n, total_regs))) return rc;
-  RES(regs, (*total_regs + 1) * sizeof(bsq_reg_t));
-  k_compact_regs<<<nblk(n, 128), 128, 0, s>>>(n, al->sa_off.as<int64_t>(), al->n_regs.as<int32_t>(), al->reg_off.as<int64_t>(),
-                                               al->regs_tmp.as<bsq_reg_t>(), al->regs.as<bsq_reg_t>());
+  DevBuf &out_regs = al->out_slot ? al->regs2 : al->regs, &out_off = al->out_slot ? al->reg_off2 : al->reg_off;  // this run's result slot
+  if ((rc = out_off.reserve((n + 1) * 8))) return rc;
+  if ((rc = scan_counts(al, al->n_regs.as<int32_t>(), out_off.as<int64_t>(), n, total_regs))) return rc;
+  if ((rc = out_regs.reserve((*total_regs + 1) * sizeof(bsq_reg_t)))) return rc;
+  k_compact_regs<<<nblk(n, 128), 128, 0, s>>>(n, al->sa_off.as<int64_t>(), al->n_regs.as<int32_t>(), out_off.as<int64_t>(),
+                                               al->regs_tmp.as<bsq_reg_t>(), out_regs.as<bsq_reg_t>());
   CK(cudaGetLastError());
   CK(cudaEventRecord(al->ev[6], s));
   int32_t st = 0;
@@ -1181,10 +1191,39 @@ int bsq_aligner_run(bsq_aligner *al, int64_t *n_regs) {
   if (al->n_staged == 0) { if (n_regs) *n_regs = 0; al->n_regs_total = 0; return 0; }
   CK(cudaSetDevice(al->idx->device));
   int64_t total = 0;
+  al->out_slot ^= 1;
+  al->out_regs[al->out_slot] = -1;
   int rc = phase1_device(al, al->n_staged, al->stride, &total);
   if (rc) return rc;
   al->n_regs_total = total;
+  al->out_tasks[al->out_slot] = al->n_staged; al->out_regs[al->out_slot] = total;
   if (n_regs) *n_regs = total;
+  return 0;
+}
+
+int bsq_aligner_result_slot(const bsq_aligner *al, int *slot, int64_t *n_tasks, int64_t *n_regs) {
+  if (!al || !slot || al->n_regs_total < 0) return BSQ_EINVAL;
+  *slot = al->out_slot;
+  if (n_tasks) *n_tasks = al->n_staged;
+  if (n_regs) *n_regs = al->n_regs_total;
+  return 0;
+}
+
+int bsq_aligner_fetch_slot(bsq_aligner *al, int slot, bsq_reg *regs, int64_t *reg_off) {
+  if (!al || slot < 0 || slot > 1 || al->out_regs[slot] < 0 || !reg_off) return BSQ_EINVAL;
+  const int64_t n = al->out_tasks[slot], nr = al->out_regs[slot];
+  if (n == 0) { reg_off[0] = 0; return 0; }
+  CK(cudaSetDevice(al->idx->device));
+  // the run that filled the slot has completed (bsq_aligner_run returns after its stream is idle): plain copies on the
+  // result stream, beside whatever the aligner's own streams are doing for the next batch
+  cudaStream_t s = al->stream_out;
+  const DevBuf &r = slot ? al->regs2 : al->regs, &o = slot ? al->reg_off2 : al->reg_off;
+  if (nr > 0) {
+    if (!regs) return BSQ_EINVAL;
+    CK(cudaMemcpyAsync(regs, r.p, (size_t)nr * sizeof(bsq_reg), cudaMemcpyDeviceToHost, s));
+  }
+  CK(cudaMemcpyAsync(reg_off, o.p, (n + 1) * 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
   return 0;
 }
 
@@ -1194,11 +1233,12 @@ int bsq_aligner_fetch(bsq_aligner *al, bsq_reg *regs, int64_t *reg_off) {
   if (n == 0) { reg_off[0] = 0; return 0; }
   CK(cudaSetDevice(al->idx->device));
   cudaStream_t s = al->stream;
+  const DevBuf &r = al->out_slot ? al->regs2 : al->regs, &o = al->out_slot ? al->reg_off2 : al->reg_off;
   if (al->n_regs_total > 0) {
     if (!regs) return BSQ_EINVAL;
-    CK(cudaMemcpyAsync(regs, al->regs.p, (size_t)al->n_regs_total * sizeof(bsq_reg), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(regs, r.p, (size_t)al->n_regs_total * sizeof(bsq_reg), cudaMemcpyDeviceToHost, s));
   }
-  CK(cudaMemcpyAsync(reg_off, al->reg_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(reg_off, o.p, (n + 1) * 8, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   return 0;
 }

@@ -45,27 +45,11 @@ struct bsq_tacc_t {
   BSQ_HD int operator()(int i) const { return ix ? bsq_ref_base(*ix, p0 + (int64_t)i * step) : buf[i]; }
 };
 
-// Execution policy of the region builder.  The scalar policy runs everything in the calling thread
-// (host emulation, k_extend).  The CUDA warp policy (bsq_ksw_warp.cuh) runs the control flow
+// Execution policy of the region builder.  The CUDA warp policy (bsq_ksw_warp.cuh) runs the control flow
 // redundantly and uniformly in all 32 lanes, lets lane 0 do the stores, and spreads each DP row
 // over the lanes.
-struct bsq_scalar_policy {
-  BSQ_HD static bool leader() { return true; }
-  BSQ_HD static int max_gap(const bsq_devopt_t &opt, int qlen) { return bsq_cal_max_gap(opt, qlen); }
-  BSQ_HD static void sync() {}
-  // asymmetric_flt_seed (memchain.c:138-149): ref T under read C, or ref A under read G, inside the seed
-  BSQ_HD static bool asym_conflict(const bsq_devidx_t &ix, const bsq_seed_t &s, const uint8_t *query) {
-    for (int i = 0; i < s.len; ++i) {
-      const int r = bsq_ref_base(ix, s.rbeg + i), qv = query[s.qbeg + i];
-      if ((r == 3 && qv == 1) || (r == 0 && qv == 2)) return true;
-    }
-    return false;
-  }
-  BSQ_HD static bsq_ext_result_t extend(int qlen, bsq_qacc_t qget, int tlen, bsq_tacc_t tget, const int8_t *mat, int o_del, int e_del, int o_ins,
-                                        int e_ins, int w, int end_bonus, int zdrop, int h0, bsq_ksw_scratch_t *scr) {
-    return bsq_ksw_extend(qlen, qget, tlen, tget, mat, o_del, e_del, o_ins, e_ins, w, end_bonus, zdrop, h0, *scr);
-  }
-};
+// (A scalar policy that runs everything in the calling thread exists for the test-only host emulation:
+// tests/hostemu/bsq_ksw_scalar.h.)
 
 // What k_region_prep (bsq_align.cu) computes ahead of k_region, one chain / one seed per lane instead of redundantly in all
 // 32 lanes of the task's warp: the seed order of mem_chain2region1 (keys of one chain in srt[seed_off ..], backup seeds

@@ -154,22 +154,36 @@ static int cal_sub(const bq_opt_t *opt, const bq_regv_t *regs) {
 
 static int lt_i64(const void *a, const void *b) { return *(const int64_t *)a < *(const int64_t *)b; }
 
+/* the insert size a pair contributes to the statistics, if any (mem_pair.c:84-100) */
+static int pestat_candidate(const bq_opt_t *opt, const bq_ref_t *ref, const bq_regv_t *r0, const bq_regv_t *r1, int64_t *is_out) {
+  int64_t is;
+  if (r0->n == 0 || r1->n == 0) return 0;
+  if (cal_sub(opt, r0) > 0.8 * r0->a[0].score) return 0; /* MIN_RATIO, mem_pair.c:35 */
+  if (cal_sub(opt, r1) > 0.8 * r1->a[0].score) return 0;
+  if (r0->a[0].rid != r1->a[0].rid) return 0;
+  if (r0->a[0].bss != r1->a[0].bss) return 0;
+  if (!reg_isize(ref, &r0->a[0], &r1->a[0], &is)) return 0;
+  if (!(is <= opt->max_ins && is >= -opt->max_ins)) return 0;
+  *is_out = is;
+  return 1;
+}
+
+static bq_pestat_t pestat_finish(const bq_opt_t *opt, int64_t *isz, size_t n_is);
+
 bq_pestat_t bq_pestat(const bq_opt_t *opt, const bq_ref_t *ref, int n, const bq_regv_t *regs) {
   int64_t *isz = malloc(sizeof(int64_t) * (size_t)(n / 2 + 1));
   size_t n_is = 0;
+  for (int i = 0; i < n >> 1; ++i) {
+    int64_t is;
+    if (pestat_candidate(opt, ref, &regs[i << 1], &regs[i << 1 | 1], &is)) isz[n_is++] = is;
+  }
+  return pestat_finish(opt, isz, n_is);
+}
+
+/* isz: the candidate insert sizes in any order (they are sorted here); freed */
+static bq_pestat_t pestat_finish(const bq_opt_t *opt, int64_t *isz, size_t n_is) {
   bq_pestat_t pes;
   memset(&pes, 0, sizeof pes);
-  for (int i = 0; i < n >> 1; ++i) {
-    const bq_regv_t *r0 = &regs[i << 1], *r1 = &regs[i << 1 | 1];
-    int64_t is;
-    if (r0->n == 0 || r1->n == 0) continue;
-    if (cal_sub(opt, r0) > 0.8 * r0->a[0].score) continue; /* MIN_RATIO, mem_pair.c:35 */
-    if (cal_sub(opt, r1) > 0.8 * r1->a[0].score) continue;
-    if (r0->a[0].rid != r1->a[0].rid) continue;
-    if (r0->a[0].bss != r1->a[0].bss) continue;
-    if (reg_isize(ref, &r0->a[0], &r1->a[0], &is))
-      if (is <= opt->max_ins && is >= -opt->max_ins) isz[n_is++] = is;
-  }
   if (bq_verbose >= 3) fprintf(stderr, "[M::mem_pestat] # candidate unique pairs: %ld\n", (long)n_is);
   if (n_is < 10) {
     fprintf(stderr, "[M:mem_pestat] There are not enough pairs for insert size inference\n");
@@ -1009,7 +1023,8 @@ void bq_read_clipping(bq_read_t *s, const uint8_t *adaptor, int l_adaptor, const
 
 
 /* stages of the host phase 2 (one parallel section each, items = reads or pairs) */
-enum { ST_MERGE = 1, ST_MS_COUNT, ST_MS_FILL, ST_MARK, ST_CIG_FILL, ST_SAM };
+enum { ST_GENERIC = 0, ST_MERGE, ST_PESTAT, ST_MS_COUNT, ST_MS_FILL, ST_MARK, ST_CIG_FILL, ST_SAM };
+#define PES_NONE INT64_MIN
 
 typedef struct {
   const bq_opt_t *opt; const bq_ref_t *ref; bq_read_t *seqs; bq_regv_t *regs; bq_pestat_t pes; int64_t n_processed;
@@ -1021,6 +1036,8 @@ typedef struct {
   bq_str_t *sam_slab;   /* per worker thread: SAM text of the reads it formatted */
   size_t *sam_off;      /* per read: offset of its text in its thread's slab */
   uint8_t *sam_thr;     /* per read: which thread's slab */
+  int64_t *pes_is;      /* per pair: the insert size it contributes to mem_pestat, or PES_NONE */
+  void (*gen_fn)(void *ctx, long i); void *gen_ctx; int no_spawn; /* ST_GENERIC: a plain parallel loop (batch preparation) */
   /* batched DP on the GPU (bsq_dp_*), when the batch has a context */
   int use_dp;
   int64_t *ms_first;            /* per pair (+1): its mate-rescue jobs [ms_first[p], ms_first[p+1]) */
@@ -1038,6 +1055,7 @@ static void reg_from_dev(const bsq_reg *d, bq_reg_t *r) {
 
 static void work_item(work_t *w, long i, int tid) {
   switch (w->stage) {
+  case ST_GENERIC: w->gen_fn(w->gen_ctx, i); return;
   case ST_MERGE: { /* gather the regions of read i in the reference's order and merge them */
     bq_regv_t *rv = &w->regs[i];
     rv->n = rv->n_pri = 0;
@@ -1049,6 +1067,11 @@ static void work_item(work_t *w, long i, int tid) {
       for (int64_t k = w->reg_off[task]; k < w->reg_off[task + 1]; ++k) reg_from_dev(&w->dev_regs[k], &rv->a[rv->n++]); /* the slice has room for all of them */
     }
     bq_merge_regions(w->opt, w->ref, w->seqs[i].seq, w->seqs[i].l_seq, rv);
+    return;
+  }
+  case ST_PESTAT: { /* pair i: its candidate for the insert-size statistics (the serial part only sorts and sums) */
+    int64_t is;
+    w->pes_is[i] = pestat_candidate(w->opt, w->ref, &w->regs[i << 1], &w->regs[i << 1 | 1], &is) ? is : PES_NONE;
     return;
   }
   case ST_MS_COUNT: case ST_MS_FILL: { /* pair i: its mate-rescue alignments as jobs of one bsq_dp_matesw batch */
@@ -1194,7 +1217,9 @@ static void run_threads(work_t *w, int n_items) {
   if (nt > 255) nt = 255;
   w->n_threads = nt;
   if (nt == 1) { for (long i = 0; i < n_items; ++i) work_item(w, i, 0); return; }
-  if (pthread_mutex_trylock(&g_tp.user) == 0) {
+  /* the batch preparation (no_spawn) only borrows the pool when it is free; phase 2 waits for it (a preparation loop
+   * takes a few milliseconds) rather than paying for threads of its own */
+  if (w->no_spawn ? pthread_mutex_trylock(&g_tp.user) == 0 : pthread_mutex_lock(&g_tp.user) == 0) {
     /* workers 1 .. nt-1 come from the pool (grown on demand), the caller is worker 0 */
     pthread_mutex_lock(&g_tp.mu);
     while (g_tp.n < nt - 1) {
@@ -1217,6 +1242,7 @@ static void run_threads(work_t *w, int n_items) {
     }
     pthread_mutex_unlock(&g_tp.user);
   }
+  if (w->no_spawn) { for (long i = 0; i < n_items; ++i) work_item(w, i, 0); return; } /* pool busy: not worth threads of its own */
   /* pool busy (another caller inside a parallel section) or it could not be built: threads for this call only */
   pthread_t *th = malloc(sizeof(pthread_t) * (size_t)nt);
   thr_t *ta = malloc(sizeof(thr_t) * (size_t)nt);
@@ -1276,9 +1302,35 @@ struct bq_batch {
   uint8_t *par;
   bq_slot_t *slot;
   /* host phase 2 between its two halves (bq_batch_finish_a / _b) */
+  bsq_aligner *al; int out_slot; /* where the regions wait on the device (bq_batch_fetch) */
   bsq_dp *dp;
   struct bq_fin *fin;
 };
+
+/* the two per-read loops of the preparation run on the phase-2 workers when those are idle (the start of a run, a
+ * GPU-bound pipeline), otherwise on the calling thread */
+typedef struct { const bq_opt_t *opt; bq_read_t *seqs; int pe; uint8_t *tseq; int stride; const int64_t *task_of_read; const uint8_t *n_task; int32_t *tlen; } prep_t;
+static void prep_clip(void *ctx, long i) {
+  prep_t *p = ctx;
+  const int second = p->pe && (i & 1);
+  bq_read_clipping(&p->seqs[i], second ? p->opt->adaptor2 : p->opt->adaptor1, second ? p->opt->l_adaptor2 : p->opt->l_adaptor1, p->opt);
+}
+static void prep_rows(void *ctx, long i) {
+  prep_t *p = ctx;
+  for (int t = 0; t < p->n_task[i]; ++t) {
+    uint8_t *row = p->tseq + (size_t)(p->task_of_read[i] + t) * p->stride;
+    memcpy(row, p->seqs[i].seq, (size_t)p->seqs[i].l_seq);
+    memset(row + p->seqs[i].l_seq, 0, (size_t)(p->stride - p->seqs[i].l_seq));
+    p->tlen[p->task_of_read[i] + t] = p->seqs[i].l_seq;
+  }
+}
+static void prep_loop(const bq_opt_t *opt, prep_t *p, int n, void (*fn)(void *, long)) {
+  work_t w;
+  memset(&w, 0, sizeof w);
+  w.stage = ST_GENERIC; w.gen_fn = fn; w.gen_ctx = p; w.no_spawn = 1;
+  w.n_threads = opt->n_threads > 8 ? 8 : opt->n_threads; /* memory-bound loops: a few threads are enough */
+  run_threads(&w, n);
+}
 
 bq_batch_t *bq_batch_prep(const bq_opt_t *opt, int64_t n_processed, int n, bq_read_t *seqs, int *rc_out) {
   const int pe = (opt->flag & BQ_F_PE) != 0;
@@ -1294,12 +1346,14 @@ bq_batch_t *bq_batch_prep(const bq_opt_t *opt, int64_t n_processed, int n, bq_re
       if (l > 0 && n1[l - 1] == '1' && strlen(n2) >= l && n2[l - 1] == '2' && strncmp(n1, n2, l - 1) == 0) continue;
       bq_fatal("[check_paired_read_names] paired reads have different names: \"%s\", \"%s\"\n", n1, n2);
     }
+  prep_t pp;
+  memset(&pp, 0, sizeof pp);
+  pp.opt = opt; pp.seqs = seqs; pp.pe = pe;
   /* clipping (bwamem.c:322,343-344) */
+  prep_loop(opt, &pp, n, prep_clip);
   int n_long = 0;
   const char *first_long = 0;
   for (i = 0; i < n; ++i) {
-    const int second = pe && (i & 1);
-    bq_read_clipping(&seqs[i], second ? opt->adaptor2 : opt->adaptor1, second ? opt->l_adaptor2 : opt->l_adaptor1, opt);
     if (seqs[i].l_seq > BSQ_MAX_READ_LEN) { if (!n_long++) first_long = seqs[i].name; continue; }
     if (seqs[i].l_seq > max_len) max_len = seqs[i].l_seq;
   }
@@ -1330,33 +1384,29 @@ bq_batch_t *bq_batch_prep(const bq_opt_t *opt, int64_t n_processed, int n, bq_re
   b->slot = slot_get();
   const int rc = slot_reserve(&b->slot->tseq, &b->slot->tseq_cap, (size_t)nt * stride + 16);
   if (rc) { if (rc_out) *rc_out = rc; slot_put(b->slot); free(par); free(b->task_of_read); free(b->n_task); free(b); return 0; }
-  uint8_t *tseq = b->slot->tseq;
   int32_t *tlen = malloc(sizeof(int32_t) * (size_t)(nt + 1));
-  for (i = 0; i < n; ++i)
-    for (int t = 0; t < b->n_task[i]; ++t) {
-      uint8_t *row = tseq + (size_t)(b->task_of_read[i] + t) * stride;
-      memcpy(row, seqs[i].seq, (size_t)seqs[i].l_seq);
-      memset(row + seqs[i].l_seq, 0, (size_t)(stride - seqs[i].l_seq));
-      tlen[b->task_of_read[i] + t] = seqs[i].l_seq;
-    }
+  pp.tseq = b->slot->tseq; pp.stride = stride; pp.task_of_read = b->task_of_read; pp.n_task = b->n_task; pp.tlen = tlen;
+  prep_loop(opt, &pp, n, prep_rows);
   b->reg_off = malloc(sizeof(int64_t) * (size_t)(nt + 1));
   b->nt = nt; b->stride = stride; b->tlen = tlen; b->par = par;
   return b;
 }
 
-/* GPU part: H2D of the task rows, the phase-1 kernels, D2H of the regions (all through page-locked memory) */
+/* GPU part: H2D of the task rows and the phase-1 kernels.  The regions stay in one of the aligner's two result slots;
+ * they are copied to the host (page-locked memory) by bq_batch_fetch at the start of the host phase 2, on another
+ * thread and another stream, while this lane already stages and runs the next batch. */
 int bq_batch_run(bsq_aligner *al, bsq_dp *dp, bq_batch_t *b) {
   int rc;
   int64_t n_regs = 0;
-  b->dp = dp;
+  b->dp = dp; b->al = al; b->out_slot = -1;
   if (b->nt == 0) { b->reg_off[0] = 0; return 0; }
   const double t0 = getenv("BQ_TIMING") ? bq_now() : 0;
   if ((rc = bsq_aligner_stage(al, b->nt, b->slot->tseq, b->stride, b->tlen, b->par))) return rc;
   const double t1 = t0 > 0 ? bq_now() : 0;
   if ((rc = bsq_aligner_run(al, &n_regs))) return rc;
   const double t2 = t0 > 0 ? bq_now() : 0;
+  if ((rc = bsq_aligner_result_slot(al, &b->out_slot, 0, 0))) return rc;
   if ((rc = slot_reserve(&b->slot->regs, &b->slot->regs_cap, (size_t)(n_regs + 1) * sizeof(bsq_reg)))) return rc;
-  if ((rc = bsq_aligner_fetch(al, b->slot->regs, b->reg_off))) return rc;
   {
     int64_t c[16];
     if (bsq_aligner_counters(al, c, 16) == 0 && c[3])
@@ -1366,8 +1416,16 @@ int bq_batch_run(bsq_aligner *al, bsq_dp *dp, bq_batch_t *b) {
   if (t0 > 0) {
     int64_t c[16];
     bsq_aligner_counters(al, c, 16);
-    fprintf(stderr, "[bq_batch_run] stage %.4f run %.4f (kernels %.4f) fetch %.4f s\n", t1 - t0, t2 - t1, c[10] * 1e-6, bq_now() - t2);
+    fprintf(stderr, "[bq_batch_run] stage %.4f run %.4f (kernels %.4f) s\n", t1 - t0, t2 - t1, c[10] * 1e-6);
   }
+  return 0;
+}
+
+/* D2H of the regions of the batch from its result slot (a no-op when there is nothing to fetch or it is done) */
+static int bq_batch_fetch(bq_batch_t *b) {
+  if (b->dregs || b->nt == 0 || b->out_slot < 0) return 0;
+  const int rc = bsq_aligner_fetch_slot(b->al, b->out_slot, b->slot->regs, b->reg_off);
+  if (rc) return rc;
   b->dregs = b->slot->regs;
   return 0;
 }
@@ -1426,6 +1484,7 @@ static int64_t prefix_counts(int64_t *first, int n_items) { /* first[i + 1] hold
 int bq_batch_finish_a(const bq_opt_t *opt, const bq_ref_t *ref, bq_batch_t *b, const bq_pestat_t *pes0) {
   const int pe = (opt->flag & BQ_F_PE) != 0, n = b->n;
   int rc = 0;
+  if ((rc = bq_batch_fetch(b))) return rc;
   bq_fin_t *f = calloc(1, sizeof *f);
   work_t *w = &f->w;
   b->fin = f;
@@ -1452,7 +1511,18 @@ int bq_batch_finish_a(const bq_opt_t *opt, const bq_ref_t *ref, bq_batch_t *b, c
   w->stage = ST_MERGE;
   run_threads(w, n);
   const double tm_ = f->t0 > 0 ? bq_now() : 0;
-  if (pe) { if (pes0) w->pes = *pes0; else w->pes = bq_pestat(opt, ref, n, w->regs); }
+  if (pe) {
+    if (pes0) w->pes = *pes0;
+    else { /* mem_pestat (mem_pair.c:74-138): candidates collected on the workers, then the serial sort + moments */
+      w->pes_is = malloc(sizeof(int64_t) * (size_t)(n / 2 + 1));
+      w->stage = ST_PESTAT;
+      run_threads(w, n >> 1);
+      size_t n_is = 0;
+      for (int i = 0; i < n >> 1; ++i) if (w->pes_is[i] != PES_NONE) w->pes_is[n_is++] = w->pes_is[i];
+      w->pes = pestat_finish(opt, w->pes_is, n_is); /* frees the array */
+      w->pes_is = 0;
+    }
+  }
   const double tp_ = f->t0 > 0 ? bq_now() : 0;
   if (g_prof < 0) g_prof = getenv("BQ_PROF") != 0;
   g_t_mate = g_t_mark = g_t_sam = g_t_pair = g_t_setsam = g_t_fmt = 0;

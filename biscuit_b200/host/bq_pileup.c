@@ -667,6 +667,11 @@ int bq_main_pileup(int argc, char **argv) {
   if (conf.step < 1) bq_fatal("[pileup] -s must be positive\n");
   if (optind + 2 > argc) { usage(&conf); bq_fatal("Reference or bam input is missing\n"); }
   const char *reffn = argv[optind++];
+  /* the genotype fields rest on a restatement of a header that is absent from the reference tree (see the top of this
+   * file): say so on every run instead of printing them as if they were verified against upstream */
+  if (rank == 0 && !getenv("BSQ_PLP_QUIET"))
+    fprintf(stderr, "[W::pileup] QUAL, FILTER, GT, GL1 and GQ are computed from a restatement of huishenlab/utils stats.h (not part of the "
+                    "reference tree): these VCF fields are not verified against an upstream build; all other fields are\n");
   int n_fns = argc - optind;
   char **in_fns = argv + optind;
   if (n_fns > 8) bq_fatal("[pileup] at most 8 BAM files\n");

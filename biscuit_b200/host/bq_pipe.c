@@ -34,6 +34,12 @@ static void q_put(q1_t *q, bq_batch_t *b, bq_read_t *seqs, int n, int rc, int en
   pthread_cond_broadcast(&q->cv);
   pthread_mutex_unlock(&q->mu);
 }
+static int q_ready(q1_t *q) { /* is there something to get right now? */
+  pthread_mutex_lock(&q->mu);
+  const int r = q->full;
+  pthread_mutex_unlock(&q->mu);
+  return r;
+}
 static void q_get(q1_t *q, bq_batch_t **b, bq_read_t **seqs, int *n, int *rc, int *end) {
   pthread_mutex_lock(&q->mu);
   while (!q->full) pthread_cond_wait(&q->cv, &q->mu);
@@ -139,9 +145,11 @@ int bq_pipeline_run(const bq_opt_t *opt, const bq_ref_t *ref, bsq_aligner *const
   pthread_create(&td, 0, stage_d, &p);
   int ret = 0;
   double t_wait = 0, t_fin = 0;
-  /* Stage C is software-pipelined around the asynchronous CIGAR kernel of the batch's DP context: the first half of
-   * phase 2 of batch k (merge .. primary marking, CIGAR jobs submitted) runs before the second half of batch k-1
-   * (pairing, SAM text), so the kernel of k overlaps the formatting of k-1.  `held` = batch k-1 between its halves. */
+  /* Stage C around the asynchronous CIGAR kernel of the batch's DP context.  When the next batch is already waiting
+   * (the host is the slower side), the first half of phase 2 of batch k+1 (merge .. primary marking, CIGAR jobs
+   * submitted) runs before the second half of batch k (pairing, SAM text), so the kernel of k+1 overlaps the formatting
+   * of k; `held` = batch k between its halves.  When nothing is waiting (the GPU is the slower side) batch k is
+   * finished at once: this thread would idle anyway, and the output leaves one batch earlier. */
   struct { bq_batch_t *b; bq_read_t *seqs; int n; } held = {0, 0, 0};
 #define FLUSH_HELD(END) do { if (held.b) { bq_batch_finish_b(opt, ref, held.b, rg_id); q_put(&p.qc, 0, held.seqs, held.n, 0, END); held.b = 0; } } while (0)
   for (int seq = 0;; ++seq) { /* batches come back in sequence order: lane seq % n_al */
@@ -160,6 +168,15 @@ int bq_pipeline_run(const bq_opt_t *opt, const bq_ref_t *ref, bsq_aligner *const
     if (b && rc == 0 && (rc = bq_batch_finish_a(opt, ref, b, pes0)) == 0) {
       FLUSH_HELD(0);
       held.b = b; held.seqs = seqs; held.n = n;
+      if (!q_ready(&p.qb[(seq + 1) % p.n_al])) { /* nothing to overlap with: finish this batch now */
+        if ((rcw = bq_batch_finish_wait(held.b))) {
+          if (!ret) ret = rcw;
+          p.abort_ = 1;
+          bq_batch_abandon(held.b);
+          q_put(&p.qc, 0, held.seqs, held.n, rcw, 0);
+          held.b = 0;
+        } else FLUSH_HELD(0);
+      }
       t_fin += pnow() - t0;
     } else {
       FLUSH_HELD(0);

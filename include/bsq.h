@@ -16,6 +16,10 @@
  *   bsq_occ4                <- bwt_occ4()                          lib/aln/bwt.c:173-200
  *   bsq_sa_lookup           <- bwt_sa()                            lib/aln/bwt.c:87-97
  *   bsq_extend_batch        <- ksw_extend2()                       lib/aln/ksw.c:380-479
+ *   bsq_dp_cigar_*          <- mem_alnreg_setSAM() band loop       lib/aln/mem_alnreg.c:40-123 around
+ *                              bis_bwa_gen_cigar2()                 lib/aln/bwa.c:290-428 (ksw_global2, ksw.c:504-606)
+ *   bsq_dp_matesw_*         <- ksw_align2()                        lib/aln/ksw.c:343-365, called by mem_matesw()
+ *                                                                  lib/aln/mem_alnreg.c:395-493
  *   bsq_plp_*               <- process_func() hot loop + plp_getcnts  src/pileup.c:707-831, :372-387
  */
 #ifndef BSQ_H
@@ -145,6 +149,13 @@ int bsq_aligner_stage(bsq_aligner *al, int64_t n_tasks, const uint8_t *seqs, int
                       const uint8_t *parent);
 int bsq_aligner_run(bsq_aligner *al, int64_t *n_regs);
 int bsq_aligner_fetch(bsq_aligner *al, bsq_reg *regs, int64_t *reg_off);
+/* Deferred fetch for pipelined callers.  bsq_aligner_run leaves its regions in one of two device-side result slots,
+ * alternating from run to run; bsq_aligner_result_slot names the slot of the last run (with its task and region
+ * counts).  bsq_aligner_fetch_slot copies that slot to the host on a stream of its own and may be called from another
+ * thread while the next batch is staged and run on the same context -- but before the run after that one, which
+ * reuses the slot. */
+int bsq_aligner_result_slot(const bsq_aligner *al, int *slot, int64_t *n_tasks, int64_t *n_regs);
+int bsq_aligner_fetch_slot(bsq_aligner *al, int slot, bsq_reg *regs, int64_t *reg_off);
 int bsq_host_alloc(void **p, size_t bytes);
 /* work counters for the roofline arithmetic: only the instrumented build (libbsq_count.so) has them,
  * libbsq.so returns BSQ_EINVAL.  out[0]=64-B index blocks fetched, [1]=bwt_extend calls,

@@ -29,7 +29,7 @@ def build_hostemu() -> str:
     orc = os.path.join(ROOT, "oracle", "bsq_oracle_pileup.c")
     dpc = os.path.join(ROOT, "tests", "hostemu", "hostemu_dp.c")
     core = os.path.join(ROOT, "biscuit_b200", "host", "bq_core.c")
-    deps = [src, orc, dpc, core, os.path.join(ROOT, "biscuit_b200", "host", "bq.h"), os.path.join(ROOT, "oracle", "bsq_oracle.h"),
+    deps = [src, orc, dpc, core, os.path.join(ROOT, "tests", "hostemu", "bsq_ksw_scalar.h"), os.path.join(ROOT, "biscuit_b200", "host", "bq.h"), os.path.join(ROOT, "oracle", "bsq_oracle.h"),
             os.path.join(ROOT, "include", "bsq.h")]
     deps += [os.path.join(cs, f) for f in os.listdir(cs) if f.endswith((".h", ".cuh"))]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):

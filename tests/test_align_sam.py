@@ -172,6 +172,36 @@ def test_sam_identical_gpu(hard_set, extra):
     assert _sam(GPU_BIN, args) == _sam(refprobe.REF_BIN, args)
 
 
+def _dp_stats(binary, args):
+    """Counters of the batched phase-2 DP as `biscuit align` reports them under BQ_TIMING."""
+    import re
+    err = subprocess.run([binary, "align"] + args, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, check=True,
+                         env=dict(os.environ, BQ_TIMING="1")).stderr.decode()
+    m = re.search(r"phase-2 DP on the GPU: (\d+) CIGAR jobs, (\d+) used, (\d+) setSAM calls on the host; mate rescue: (\d+) jobs, (\d+) used, (\d+) on the host", err)
+    assert m, err[-2000:]
+    return [int(x) for x in m.groups()]
+
+
+def _check_dp_used(binary, hard_set):
+    """The final CIGARs and the mate-rescue alignments come from the bsq_dp_* calls, not from the host routines that
+    remain for regions the prediction misses (noisy set: 10 % unrelated mates, indels)."""
+    fa, f1, f2 = hard_set
+    cig_jobs, cig_used, cig_host, ms_jobs, ms_used, ms_host = _dp_stats(binary, ["-@", "4", fa, f1, f2])
+    assert cig_used > 5000 and cig_jobs >= cig_used
+    assert cig_host <= 0.02 * cig_used, (cig_used, cig_host)
+    assert ms_used > 100 and ms_jobs >= ms_used
+    assert ms_host <= 0.02 * ms_used + 5, (ms_used, ms_host)
+
+
+def test_phase2_dp_is_used_hostemu(hard_set):
+    _check_dp_used(build_emu_bin(), hard_set)
+
+
+@pytest.mark.gpu
+def test_phase2_dp_is_used_gpu(hard_set):
+    _check_dp_used(GPU_BIN, hard_set)
+
+
 @pytest.mark.gpu
 def test_sam_identical_single_end_gpu(hard_set):
     fa, f1, _ = hard_set
