@@ -9,6 +9,8 @@
 // Buffers between the stages are sized exactly from device-side prefix sums, so nothing is
 // truncated; capacity violations raise BSQ_EOVERFLOW.
 #include <cuda_runtime.h>
+#include <condition_variable>
+#include <mutex>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -137,6 +139,10 @@ struct bsq_aligner {
   cudaStream_t stream_out;
   int out_slot = 0;
   int64_t out_tasks[2] = {0, 0}, out_regs[2] = {-1, -1};
+  // a slot named by bsq_aligner_result_slot is claimed until it is fetched (or released): the run that would overwrite it waits
+  std::mutex slot_mu;
+  std::condition_variable slot_cv;
+  bool claimed[2] = {false, false};
   int64_t counters[16];
   int64_t n_staged = 0, n_regs_total = -1;
   int64_t fb_cap = 0;  // entries of the fallback-chaining workspace pools
@@ -1191,8 +1197,12 @@ int bsq_aligner_run(bsq_aligner *al, int64_t *n_regs) {
   if (al->n_staged == 0) { if (n_regs) *n_regs = 0; al->n_regs_total = 0; return 0; }
   CK(cudaSetDevice(al->idx->device));
   int64_t total = 0;
-  al->out_slot ^= 1;
-  al->out_regs[al->out_slot] = -1;
+  {
+    std::unique_lock<std::mutex> lk(al->slot_mu);
+    al->slot_cv.wait(lk, [&] { return !al->claimed[al->out_slot ^ 1]; });  // its previous content is still to be fetched by another thread
+    al->out_slot ^= 1;
+    al->out_regs[al->out_slot] = -1;
+  }
   int rc = phase1_device(al, al->n_staged, al->stride, &total);
   if (rc) return rc;
   al->n_regs_total = total;
@@ -1201,16 +1211,37 @@ int bsq_aligner_run(bsq_aligner *al, int64_t *n_regs) {
   return 0;
 }
 
-int bsq_aligner_result_slot(const bsq_aligner *al, int *slot, int64_t *n_tasks, int64_t *n_regs) {
+int bsq_aligner_result_slot(bsq_aligner *al, int *slot, int64_t *n_tasks, int64_t *n_regs) {
   if (!al || !slot || al->n_regs_total < 0) return BSQ_EINVAL;
+  {
+    std::lock_guard<std::mutex> lk(al->slot_mu);
+    al->claimed[al->out_slot] = true;
+  }
   *slot = al->out_slot;
   if (n_tasks) *n_tasks = al->n_staged;
   if (n_regs) *n_regs = al->n_regs_total;
   return 0;
 }
 
+int bsq_aligner_release_slot(bsq_aligner *al, int slot) {
+  if (!al || slot < 0 || slot > 1) return BSQ_EINVAL;
+  {
+    std::lock_guard<std::mutex> lk(al->slot_mu);
+    al->claimed[slot] = false;
+  }
+  al->slot_cv.notify_all();
+  return 0;
+}
+
+static int fetch_slot_copy(bsq_aligner *al, int slot, bsq_reg *regs, int64_t *reg_off);
 int bsq_aligner_fetch_slot(bsq_aligner *al, int slot, bsq_reg *regs, int64_t *reg_off) {
   if (!al || slot < 0 || slot > 1 || al->out_regs[slot] < 0 || !reg_off) return BSQ_EINVAL;
+  const int rc = fetch_slot_copy(al, slot, regs, reg_off);
+  bsq_aligner_release_slot(al, slot);
+  return rc;
+}
+
+static int fetch_slot_copy(bsq_aligner *al, int slot, bsq_reg *regs, int64_t *reg_off) {
   const int64_t n = al->out_tasks[slot], nr = al->out_regs[slot];
   if (n == 0) { reg_off[0] = 0; return 0; }
   CK(cudaSetDevice(al->idx->device));

@@ -1431,6 +1431,7 @@ static int bq_batch_fetch(bq_batch_t *b) {
 }
 
 static void batch_free(bq_batch_t *b) {
+  if (b->al && b->out_slot >= 0 && !b->dregs && b->nt > 0) bsq_aligner_release_slot(b->al, b->out_slot); /* never fetched (a failed batch) */
   slot_put(b->slot);
   free(b->task_of_read); free(b->n_task); free(b->reg_off); free(b->tlen); free(b->par);
   free(b);

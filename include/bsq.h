@@ -150,12 +150,14 @@ int bsq_aligner_stage(bsq_aligner *al, int64_t n_tasks, const uint8_t *seqs, int
 int bsq_aligner_run(bsq_aligner *al, int64_t *n_regs);
 int bsq_aligner_fetch(bsq_aligner *al, bsq_reg *regs, int64_t *reg_off);
 /* Deferred fetch for pipelined callers.  bsq_aligner_run leaves its regions in one of two device-side result slots,
- * alternating from run to run; bsq_aligner_result_slot names the slot of the last run (with its task and region
- * counts).  bsq_aligner_fetch_slot copies that slot to the host on a stream of its own and may be called from another
- * thread while the next batch is staged and run on the same context -- but before the run after that one, which
- * reuses the slot. */
-int bsq_aligner_result_slot(const bsq_aligner *al, int *slot, int64_t *n_tasks, int64_t *n_regs);
+ * alternating from run to run.  bsq_aligner_result_slot names the slot of the last run (with its task and region
+ * counts) and CLAIMS it: the run that would overwrite it blocks until the slot has been fetched or released.
+ * bsq_aligner_fetch_slot copies the slot to the host on a stream of its own and releases it; it may be called from
+ * another thread while later batches are staged and run on the same context.  A claimed slot that will not be fetched
+ * (a failed batch) must be given back with bsq_aligner_release_slot. */
+int bsq_aligner_result_slot(bsq_aligner *al, int *slot, int64_t *n_tasks, int64_t *n_regs);
 int bsq_aligner_fetch_slot(bsq_aligner *al, int slot, bsq_reg *regs, int64_t *reg_off);
+int bsq_aligner_release_slot(bsq_aligner *al, int slot);
 int bsq_host_alloc(void **p, size_t bytes);
 /* work counters for the roofline arithmetic: only the instrumented build (libbsq_count.so) has them,
  * libbsq.so returns BSQ_EINVAL.  out[0]=64-B index blocks fetched, [1]=bwt_extend calls,

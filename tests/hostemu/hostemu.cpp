@@ -8,6 +8,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <condition_variable>
+#include <mutex>
 #include <vector>
 #include "../../include/bsq.h"
 #include "../../biscuit_b200/csrc/bsq_task.h"
@@ -27,6 +29,7 @@ struct bsq_aligner {
   std::vector<uint8_t> st_seqs, st_par; std::vector<int32_t> st_lens; int32_t st_stride = 0; int64_t st_n = 0;
   bsq_reg *res_regs = nullptr; std::vector<int64_t> res_off; int64_t res_n = -1;
   // the two result slots of the deferred fetch (bsq_aligner_result_slot / _fetch_slot)
+  std::mutex slot_mu; std::condition_variable slot_cv; bool claimed[2] = {false, false};
   int out_slot = 0; std::vector<bsq_reg> slot_regs[2]; std::vector<int64_t> slot_off[2]; int64_t slot_tasks[2] = {0, 0}, slot_n[2] = {-1, -1};
 };
 
@@ -267,13 +270,24 @@ int bsq_aligner_run(bsq_aligner *al, int64_t *n_regs) {
   if (rc) return rc;
   al->res_n = al->res_off[al->st_n];
   if (n_regs) *n_regs = al->res_n;
-  al->out_slot ^= 1;
+  {
+    std::unique_lock<std::mutex> lk(al->slot_mu);
+    al->slot_cv.wait(lk, [&] { return !al->claimed[al->out_slot ^ 1]; });
+    al->out_slot ^= 1;
+  }
   const int sl = al->out_slot;
   al->slot_regs[sl].assign(al->res_regs, al->res_regs + al->res_n); al->slot_off[sl] = al->res_off; al->slot_tasks[sl] = al->st_n; al->slot_n[sl] = al->res_n;
   return 0;
 }
-int bsq_aligner_result_slot(const bsq_aligner *al, int *slot, int64_t *n_tasks, int64_t *n_regs) {
+int bsq_aligner_release_slot(bsq_aligner *al, int slot) {
+  if (!al || slot < 0 || slot > 1) return BSQ_EINVAL;
+  { std::lock_guard<std::mutex> lk(al->slot_mu); al->claimed[slot] = false; }
+  al->slot_cv.notify_all();
+  return 0;
+}
+int bsq_aligner_result_slot(bsq_aligner *al, int *slot, int64_t *n_tasks, int64_t *n_regs) {
   if (!al || !slot || al->res_n < 0) return BSQ_EINVAL;
+  { std::lock_guard<std::mutex> lk(al->slot_mu); al->claimed[al->out_slot] = true; }
   *slot = al->out_slot;
   if (n_tasks) *n_tasks = al->st_n;
   if (n_regs) *n_regs = al->res_n;
@@ -281,9 +295,10 @@ int bsq_aligner_result_slot(const bsq_aligner *al, int *slot, int64_t *n_tasks, 
 }
 int bsq_aligner_fetch_slot(bsq_aligner *al, int slot, bsq_reg *regs, int64_t *reg_off) {
   if (!al || slot < 0 || slot > 1 || al->slot_n[slot] < 0 || !reg_off) return BSQ_EINVAL;
-  if (al->slot_tasks[slot] == 0) { reg_off[0] = 0; return 0; }
+  if (al->slot_tasks[slot] == 0) { reg_off[0] = 0; bsq_aligner_release_slot(al, slot); return 0; }
   if (al->slot_n[slot] > 0) memcpy(regs, al->slot_regs[slot].data(), (size_t)al->slot_n[slot] * sizeof(bsq_reg));
   memcpy(reg_off, al->slot_off[slot].data(), (size_t)(al->slot_tasks[slot] + 1) * 8);
+  bsq_aligner_release_slot(al, slot);
   return 0;
 }
 int bsq_aligner_fetch(bsq_aligner *al, bsq_reg *regs, int64_t *reg_off) {

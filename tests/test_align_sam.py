@@ -172,6 +172,33 @@ def test_sam_identical_gpu(hard_set, extra):
     assert _sam(GPU_BIN, args) == _sam(refprobe.REF_BIN, args)
 
 
+def _truncated_pair_files(hard_set, tmp_path, which):
+    """Copies of the two FASTQ files with the last 37 records of one of them cut off."""
+    fa, f1, f2 = hard_set
+    out = []
+    for k, f in enumerate((f1, f2)):
+        lines = open(f).read().split("\n")
+        if k == which:
+            lines = lines[:len(lines) - 1 - 4 * 37] + [""]
+        o = str(tmp_path / f"t{k}.fq")
+        open(o, "w").write("\n".join(lines))
+        out.append(o)
+    return fa, out[0], out[1]
+
+
+@pytest.mark.parametrize("which", [0, 1], ids=["first shorter", "second shorter"])
+def test_unequal_pair_files_hostemu(hard_set, tmp_path, which):
+    """One file of the pair ends early (bis_bseq_read, bwa.c:831-846: warn, align what is paired): same records as the
+    reference, with the second file parsed ahead by the helper thread and with it switched off."""
+    fa, f1, f2 = _truncated_pair_files(hard_set, tmp_path, which)
+    args = ["-@", "3", fa, f1, f2]
+    ref = _sam(refprobe.REF_BIN, args)
+    assert _sam(build_emu_bin(), args) == ref
+    assert _sam(build_emu_bin(), args, env={"BQ_FQ_NO_AHEAD": "1"}) == ref
+    # many small batches: the helper runs across batch boundaries; same text with and without it
+    assert _sam(build_emu_bin(), args, env={"BQ_CHUNK_SIZE": "9000"}) == _sam(build_emu_bin(), args, env={"BQ_CHUNK_SIZE": "9000", "BQ_FQ_NO_AHEAD": "1"})
+
+
 def _dp_stats(binary, args):
     """Counters of the batched phase-2 DP as `biscuit align` reports them under BQ_TIMING."""
     import re
