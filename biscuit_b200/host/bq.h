@@ -219,6 +219,8 @@ int bq_batch_finish_wait(bq_batch_t *b);
 void bq_batch_finish_b(const bq_opt_t *opt, const bq_ref_t *ref, bq_batch_t *b, const char *rg_id);
 int bq_batch_finish(const bq_opt_t *opt, const bq_ref_t *ref, bq_batch_t *b, const bq_pestat_t *pes0, const char *rg_id);
 void bq_batch_abandon(bq_batch_t *b); /* after a failed _a / _wait: releases the batch (not the reads) */
+/* fn(ctx, i) for i in [0, n) on the phase-2 worker pool when it is idle (at most 8 threads), else on the calling thread */
+void bq_parallel_for(int n_threads, long n, void (*fn)(void *ctx, long i), void *ctx);
 /* counters of the batched DP since the start: [0] CIGAR jobs sent to the GPU, [1] setSAM calls answered from them, [2] setSAM
  * calls done on the host (not predicted / outside the kernel's limits), [3] mate-rescue alignments sent to the GPU,
  * [4] used from there, [5] done on the host */

@@ -78,32 +78,38 @@ int64_t bq_session_align(bq_session *s, int64_t n_processed, int n, const uint8_
 
 /* n_batches batches of the same n reads through the three-stage pipeline of the CLI (bq_pipe.c).
  * Returns the SAM bytes of the last batch (negative BSQ_E* on error). */
-typedef struct { int n_batches, b, n, stride; const uint8_t *seqs, *quals; const int32_t *lens; int64_t sam_bytes; } stream_t;
+typedef struct { int n_batches, b, n, stride, n_threads; const uint8_t *seqs, *quals; const int32_t *lens; int64_t sam_bytes; } stream_t;
 
-static bq_read_t *make_reads(int64_t n_processed, int n, const uint8_t *seqs, int stride, const int32_t *lens, const uint8_t *quals) {
-  /* what bq_read_batch produces for a FASTQ batch: one slab with name, nt4 sequence and quality of every read */
+/* what bq_read_batch produces for a FASTQ batch: one slab with name, nt4 sequence and quality of every read */
+typedef struct { bq_read_t *rd; char *slab; int64_t n_processed; const uint8_t *seqs, *quals; const int32_t *lens; int stride; size_t rec; } mk_t;
+static void make_read(void *ctx, long i) {
+  mk_t *m = ctx;
+  bq_read_t *r = &m->rd[i];
+  char *p = m->slab + (size_t)i * m->rec;
+  r->name = p; sprintf(p, "r%lld", (long long)((m->n_processed + i) >> 1)); p += 24;
+  r->l_seq = r->l_seq0 = m->lens[i];
+  r->seq = r->seq0 = (uint8_t *)p; memcpy(p, m->seqs + (size_t)i * m->stride, (size_t)m->lens[i]); p += m->lens[i] + 1;
+  r->qual = p;
+  if (m->quals) memcpy(p, m->quals + (size_t)i * m->stride, (size_t)m->lens[i]); else memset(p, 'I', (size_t)m->lens[i]);
+  p[m->lens[i]] = 0;
+  r->id = (int)i; r->in_slab = 1;
+}
+static bq_read_t *make_reads(int n_threads, int64_t n_processed, int n, const uint8_t *seqs, int stride, const int32_t *lens, const uint8_t *quals) {
   bq_read_t *rd = calloc((size_t)n + 1, sizeof(bq_read_t));
-  size_t tot = 0;
-  for (int i = 0; i < n; ++i) tot += 24 + 2 * ((size_t)lens[i] + 1);
+  int max_len = 0;
+  for (int i = 0; i < n; ++i) if (lens[i] > max_len) max_len = lens[i];
+  mk_t m = {rd, 0, n_processed, seqs, quals, lens, stride, 24 + 2 * ((size_t)max_len + 1)}; /* fixed record size: the reads fill in parallel */
   size_t cap_ = 0;
-  char *slab = bq_big_alloc(tot + 16, &cap_), *p = slab;
-  for (int i = 0; i < n; ++i) {
-    rd[i].name = p; p += 1 + sprintf(p, "r%lld", (long long)((n_processed + i) >> 1));
-    rd[i].l_seq = rd[i].l_seq0 = lens[i];
-    rd[i].seq = rd[i].seq0 = (uint8_t *)p; memcpy(p, seqs + (size_t)i * stride, (size_t)lens[i]); p += lens[i] + 1;
-    rd[i].qual = p;
-    if (quals) memcpy(p, quals + (size_t)i * stride, (size_t)lens[i]); else memset(p, 'I', (size_t)lens[i]);
-    p[lens[i]] = 0; p += lens[i] + 1;
-    rd[i].id = i; rd[i].in_slab = 1;
-  }
-  if (n > 0) rd[0].slab = slab; else bq_big_free(slab);
+  m.slab = bq_big_alloc((size_t)n * m.rec + 16, &cap_);
+  bq_parallel_for(n_threads, n, make_read, &m);
+  if (n > 0) rd[0].slab = m.slab; else bq_big_free(m.slab);
   return rd;
 }
 
 static bq_read_t *stream_source(void *ctx, int *n) {
   stream_t *st = ctx;
   if (st->b >= st->n_batches) { *n = 0; return 0; }
-  bq_read_t *rd = make_reads((int64_t)st->b * st->n, st->n, st->seqs, st->stride, st->lens, st->quals);
+  bq_read_t *rd = make_reads(st->n_threads, (int64_t)st->b * st->n, st->n, st->seqs, st->stride, st->lens, st->quals);
   st->b++;
   *n = st->n;
   return rd;
@@ -122,7 +128,7 @@ static void stream_sink(void *ctx, bq_read_t *rd, int n) {
 int64_t bq_session_align_stream(bq_session *s, int n_batches, int n, const uint8_t *seqs, int stride, const int32_t *lens, const uint8_t *quals) {
   stream_t st;
   memset(&st, 0, sizeof st);
-  st.n_batches = n_batches; st.n = n; st.stride = stride; st.seqs = seqs; st.quals = quals; st.lens = lens;
+  st.n_batches = n_batches; st.n = n; st.stride = stride; st.seqs = seqs; st.quals = quals; st.lens = lens; st.n_threads = s->opt.n_threads;
   bsq_aligner *als[2] = {s->al, s->al2};
   bsq_dp *dps[2] = {s->dp, s->dp2};
   const int rc = bq_pipeline_run(&s->opt, &s->ref, als, dps, s->al2 ? 2 : 1, stream_source, &st, stream_sink, &st, 0, "");

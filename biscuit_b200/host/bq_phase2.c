@@ -1324,13 +1324,14 @@ static void prep_rows(void *ctx, long i) {
     p->tlen[p->task_of_read[i] + t] = p->seqs[i].l_seq;
   }
 }
-static void prep_loop(const bq_opt_t *opt, prep_t *p, int n, void (*fn)(void *, long)) {
+void bq_parallel_for(int n_threads, long n, void (*fn)(void *ctx, long i), void *ctx) {
   work_t w;
   memset(&w, 0, sizeof w);
-  w.stage = ST_GENERIC; w.gen_fn = fn; w.gen_ctx = p; w.no_spawn = 1;
-  w.n_threads = opt->n_threads > 8 ? 8 : opt->n_threads; /* memory-bound loops: a few threads are enough */
-  run_threads(&w, n);
+  w.stage = ST_GENERIC; w.gen_fn = fn; w.gen_ctx = ctx; w.no_spawn = 1;
+  w.n_threads = n_threads > 8 ? 8 : n_threads; /* memory-bound loops: a few threads are enough */
+  run_threads(&w, (int)n);
 }
+static void prep_loop(const bq_opt_t *opt, prep_t *p, int n, void (*fn)(void *, long)) { bq_parallel_for(opt->n_threads, n, fn, p); }
 
 bq_batch_t *bq_batch_prep(const bq_opt_t *opt, int64_t n_processed, int n, bq_read_t *seqs, int *rc_out) {
   const int pe = (opt->flag & BQ_F_PE) != 0;
