@@ -706,12 +706,19 @@ static void tag_sa(const bq_ref_t *ref, const bq_reg_t *p0, const bq_regv_t *reg
 
 /* Fixed-layout part of a SAM record written through a bare pointer: the caller reserves an upper bound once, so the ~100
  * pieces of a record cost no capacity check and no terminator each (they were a third of format_sam's time). */
-static inline char *fw_num(char *w, long v) {
+static const char fw_dig2[201] =
+  "0001020304050607080910111213141516171819202122232425262728293031323334353637383940414243444546474849"
+  "5051525354555657585960616263646566676869707172737475767778798081828384858687888990919293949596979899";
+static inline char *fw_num(char *w, long v) { /* decimal, two digits per division */
   char b[24];
   int n = 0;
   unsigned long u = v < 0 ? 0ul - (unsigned long)v : (unsigned long)v;
-  do { b[n++] = (char)('0' + u % 10); u /= 10; } while (u);
   if (v < 0) *w++ = '-';
+  while (u >> 32) { const unsigned r = (unsigned)(u % 100); u /= 100; b[n++] = fw_dig2[2 * r + 1]; b[n++] = fw_dig2[2 * r]; }
+  unsigned x = (unsigned)u;
+  while (x >= 100) { const unsigned r = x % 100; x /= 100; b[n++] = fw_dig2[2 * r + 1]; b[n++] = fw_dig2[2 * r]; }
+  if (x >= 10) { b[n++] = fw_dig2[2 * x + 1]; b[n++] = fw_dig2[2 * x]; }
+  else b[n++] = (char)('0' + x);
   while (n) *w++ = b[--n];
   return w;
 }
@@ -725,6 +732,48 @@ static char *fw_cigar(char *w, const bq_opt_t *opt, const bq_reg_t *r, int is_pr
   }
   return w;
 }
+
+/* SEQ / QUAL of a record: nt4 codes to letters (reverse-complemented for a reverse-strand hit), qualities copied or
+ * reversed.  16 bases per step with a byte shuffle where the CPU has one (a third of format_sam's time went into the
+ * byte loops); the plain loops otherwise and for the tails. */
+static char *seq_out_plain(char *w, const uint8_t *s, int qb, int qe, int rev) {
+  if (rev) for (int i = qe - 1; i >= qb; --i) *w++ = "TGCAN"[s[i]];
+  else for (int i = qb; i < qe; ++i) *w++ = "ACGTN"[s[i]];
+  return w;
+}
+static char *qual_rev_plain(char *w, const char *q, int qb, int qe) {
+  for (int i = qe - 1; i >= qb; --i) *w++ = q[i];
+  return w;
+}
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <tmmintrin.h>
+__attribute__((target("ssse3"))) static char *seq_out_ssse3(char *w, const uint8_t *s, int qb, int qe, int rev) {
+  const __m128i fw = _mm_setr_epi8('A', 'C', 'G', 'T', 'N', 'N', 'N', 'N', 'N', 'N', 'N', 'N', 'N', 'N', 'N', 'N');
+  const __m128i rc = _mm_setr_epi8('T', 'G', 'C', 'A', 'N', 'N', 'N', 'N', 'N', 'N', 'N', 'N', 'N', 'N', 'N', 'N');
+  const __m128i flip = _mm_setr_epi8(15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0);
+  if (!rev) {
+    int i = qb;
+    for (; i + 16 <= qe; i += 16, w += 16) _mm_storeu_si128((__m128i *)w, _mm_shuffle_epi8(fw, _mm_loadu_si128((const __m128i *)(s + i))));
+    return seq_out_plain(w, s, i, qe, 0);
+  }
+  int e = qe;
+  for (; e - 16 >= qb; e -= 16, w += 16)
+    _mm_storeu_si128((__m128i *)w, _mm_shuffle_epi8(_mm_shuffle_epi8(rc, _mm_loadu_si128((const __m128i *)(s + e - 16))), flip));
+  return seq_out_plain(w, s, qb, e, 1);
+}
+__attribute__((target("ssse3"))) static char *qual_rev_ssse3(char *w, const char *q, int qb, int qe) {
+  const __m128i flip = _mm_setr_epi8(15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0);
+  int e = qe;
+  for (; e - 16 >= qb; e -= 16, w += 16) _mm_storeu_si128((__m128i *)w, _mm_shuffle_epi8(_mm_loadu_si128((const __m128i *)(q + e - 16)), flip));
+  return qual_rev_plain(w, q, qb, e);
+}
+static int have_ssse3(void) { static int v = -1; if (v < 0) v = __builtin_cpu_supports("ssse3") ? 1 : 0; return v; }
+static inline char *seq_out(char *w, const uint8_t *s, int qb, int qe, int rev) { return have_ssse3() ? seq_out_ssse3(w, s, qb, qe, rev) : seq_out_plain(w, s, qb, qe, rev); }
+static inline char *qual_rev(char *w, const char *q, int qb, int qe) { return have_ssse3() ? qual_rev_ssse3(w, q, qb, qe) : qual_rev_plain(w, q, qb, qe); }
+#else
+#define seq_out seq_out_plain
+#define qual_rev qual_rev_plain
+#endif
 
 /* mem_alnreg_formatSAM (:237-436) */
 static void format_sam(const bq_opt_t *opt, const bq_ref_t *ref, bq_str_t *str, bq_read_t *s, const bq_reg_t *p0, const bq_reg_t *m0,
@@ -773,23 +822,23 @@ static void format_sam(const bq_opt_t *opt, const bq_ref_t *ref, bq_str_t *str, 
   *w++ = '\t';
   if (p.flag & 0x100) w = fw_mem(w, "*\t*", 3);
   else {
-    int i, qb = 0, qe = s->l_seq0;
+    int qb = 0, qe = s->l_seq0;
     const int hard = p.n_cigar && !is_primary && !(opt->flag & BQ_F_SOFTCLIP) && !p.is_alt;
     if (p.is_rev) {
       if (hard) {
         if ((p.cigar[0] & 0xf) == 4 || (p.cigar[0] & 0xf) == 3) qe -= (int)(p.cigar[0] >> 4);
         if ((p.cigar[p.n_cigar - 1] & 0xf) == 4 || (p.cigar[p.n_cigar - 1] & 0xf) == 3) qb += (int)(p.cigar[p.n_cigar - 1] >> 4);
       }
-      for (i = qe - 1; i >= qb; --i) *w++ = "TGCAN"[(int)s->seq0[i]];
+      w = seq_out(w, s->seq0, qb, qe, 1);
       *w++ = '\t';
-      if (s->qual) { for (i = qe - 1; i >= qb; --i) *w++ = s->qual[i]; }
+      if (s->qual) w = qual_rev(w, s->qual, qb, qe);
       else *w++ = '*';
     } else {
       if (hard) {
         if ((p.cigar[0] & 0xf) == 4 || (p.cigar[0] & 0xf) == 3) qb += (int)(p.cigar[0] >> 4);
         if ((p.cigar[p.n_cigar - 1] & 0xf) == 4 || (p.cigar[p.n_cigar - 1] & 0xf) == 3) qe -= (int)(p.cigar[p.n_cigar - 1] >> 4);
       }
-      for (i = qb; i < qe; ++i) *w++ = "ACGTN"[(int)s->seq0[i]];
+      w = seq_out(w, s->seq0, qb, qe, 0);
       *w++ = '\t';
       if (s->qual) { if (qe > qb) w = fw_mem(w, s->qual + qb, (size_t)(qe - qb)); }
       else *w++ = '*';
