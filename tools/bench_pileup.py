@@ -149,8 +149,26 @@ def run(args, log, torch, dist, rank: int, local_rank: int, world: int, peak: fl
     """Returns the pileup record on rank 0, None elsewhere."""
     sys.path.insert(0, ROOT)
     from biscuit_b200 import capi, plp
-    L = int(args.plp_mb * 1_000_000)
     dev = torch.device("cuda", local_rank)
+    # Host memory: a rank keeps the read columns (57 B per locus at 30x), their page-locked copy and the page-locked output
+    # (48 B per locus), about 0.18 GB per Mb of contig.  All ranks of a node share its RAM: when the requested contig
+    # size does not fit in 60 % of what is available, every rank shrinks it by the same factor (rank 0 decides) and the
+    # record says so -- a rank that dies of memory pressure would leave the others waiting in a collective.
+    plp_mb, shrunk = float(args.plp_mb), None
+    try:
+        import psutil
+        avail_gb = psutil.virtual_memory().available / 1e9
+        t = torch.tensor([avail_gb], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.broadcast(t, src=0)
+        fit_mb = 0.6 * float(t[0]) / world / 0.18
+        if fit_mb < plp_mb:
+            shrunk = {"requested_mb": plp_mb, "host_ram_available_gb": float(t[0])}
+            plp_mb = max(8.0, float(int(fit_mb)))
+            log(f"pileup rank {rank}: contig shrunk to {plp_mb:.0f} Mb per GPU to fit the node's host memory ({float(t[0]):.0f} GB available, {world} ranks)")
+    except Exception as e:  # noqa: BLE001
+        log("host memory check skipped:", e)
+    L = int(plp_mb * 1_000_000)
     g = torch.Generator(device=dev)
     g.manual_seed(7 + rank)
     t0 = time.time()
@@ -191,8 +209,23 @@ def run(args, log, torch, dist, rank: int, local_rank: int, world: int, peak: fl
     # --- the C ABI with host buffers: H2D of every read column + kernels + D2H of the records, per pass.  The host
     # buffers are page-locked (what `biscuit pileup` uses for its decoded batches, bq_bam.c), allocated outside the timing ---
     t_pin = time.perf_counter()
-    rd_pin = {k: (torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy() if isinstance(v, np.ndarray) else v) for k, v in rd.items()}
-    out_pin = torch.empty((int(n_loci) + 1) * 88, dtype=torch.uint8).pin_memory().numpy().view(plp.REC_DTYPE)
+    pin_ok = 1
+    try:
+        rd_pin = {k: (torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy() if isinstance(v, np.ndarray) else v) for k, v in rd.items()}
+        out_pin = torch.empty((int(n_loci) + 1) * 88, dtype=torch.uint8).pin_memory().numpy().view(plp.REC_DTYPE)
+    except Exception as e:  # noqa: BLE001
+        log(f"pileup rank {rank}: page-locking the staging buffers failed ({e}); pageable buffers instead")
+        pin_ok = 0
+    if world > 1:  # all ranks take the same path
+        tp = torch.tensor([pin_ok], device=dev, dtype=torch.int32)
+        dist.all_reduce(tp, op=dist.ReduceOp.MIN)
+        pin_ok = int(tp[0])
+    h2d = sum(int(np.asarray(v).nbytes) for k, v in rd.items() if k != "n_reads")
+    if not pin_ok:
+        rd_pin = rd
+        out_pin = np.zeros(int(n_loci) + 1, dtype=plp.REC_DTYPE)
+    elif world > 1:
+        rd = {"n_reads": rd["n_reads"]}  # the pageable copy is only needed by the command-line legs (N = 1)
     log(f"pileup rank {rank}: page-locked staging buffers ({sum(v.nbytes for v in rd_pin.values() if isinstance(v, np.ndarray)) / 1e9:.1f} + "
         f"{out_pin.nbytes / 1e9:.1f} GB) in {time.perf_counter() - t_pin:.1f}s")
     pl.stage(rd_pin)
@@ -232,7 +265,6 @@ def run(args, log, torch, dist, rank: int, local_rank: int, world: int, peak: fl
             cli, cpu, parity = sample_legs(log, nt4, rd, args.plp_sample_mb, ncores, not args.no_cpu_baseline)
         except Exception as e:  # noqa: BLE001
             log("pileup sample legs failed:", e)
-    h2d = sum(int(np.asarray(v).nbytes) for k, v in rd.items() if k != "n_reads")
     # reads (packed SEQ, QUAL, 48 B of record fields), reference base + flag per locus, one 88-byte record per emitted
     # locus; the per-locus counters stay in shared memory
     alg = rd["n_reads"] * (75 + 150 + 48) + (L - 1) * (1 + 4) + n_loci * 88
@@ -254,7 +286,9 @@ def run(args, log, torch, dist, rank: int, local_rank: int, world: int, peak: fl
                        "parallelism": f"contigs sharded over {world} rank(s); one NCCL reduce of the per-contig statistics"},
             "clocks": clocks, "stats_reduce_ms": reduce_ms,
             "e2e": {"value": world * (L - 1) * e2e_steps / dt_e2e, "unit": "loci/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(n_loci) * 88,
-                    "steps": e2e_steps, "note": "C ABI with page-locked host buffers: bsq_plp_stage (H2D) + bsq_plp_run + bsq_plp_fetch (D2H) per pass"},
+                    "steps": e2e_steps, "note": ("C ABI with page-locked host buffers" if pin_ok else "C ABI with PAGEABLE host buffers (page-locking failed)") +
+                    ": bsq_plp_stage (H2D) + bsq_plp_run + bsq_plp_fetch (D2H) per pass"},
+            "contig_shrunk_to_fit_host_memory": shrunk,
             "e2e_cli": cli, "parity": parity,
             "gpu_launches": 3 * steps * n_tiles,
             "roofline": {"bound": "hbm", "kernel": "k_plp_win", "achieved": alg / (kus[0] * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
