@@ -121,9 +121,10 @@ typedef struct {
   uint32_t ZC, ZR;
   int bss_u;
   uint32_t *cigar; /* n_cigar words followed by the NUL-terminated MD string */
-  /* batched phase-2 DP on the GPU (bsq_dp_*): 1 + index of the CIGAR job predicted for this region (0 = none), and
-   * whether .cigar points into the batch's result blob (not owned by the region) */
-  int dp_job;
+  /* batched phase-2 DP on the GPU (bsq_dp_*): the CIGAR job predicted for this region, 0 = none, else
+   * 1 + (worker thread << 24 | index in that thread's job list); and whether .cigar points into the batch's result
+   * blob (not owned by the region) */
+  uint32_t dp_job;
   uint8_t cigar_ext;
 } bq_reg_t;
 

@@ -539,16 +539,24 @@ static int set_sam_band(const bq_opt_t *opt, const bq_reg_t *reg) {
 }
 
 /* CIGARs of the batch computed on the GPU (bsq_dp_cigar): set by the phase-2 workers around reg2sam */
-typedef struct { const bsq_cigar_res *res; const uint32_t *blob; int64_t n; } dp_cig_t;
+typedef struct { const bsq_cigar_res *res; const uint32_t *blob; int64_t n; const int64_t *thr_base; int n_thr; } dp_cig_t;
+/* result of the job a region carries, or NULL */
+static inline const bsq_cigar_res *dp_cig_find(const dp_cig_t *d, uint32_t dp_job) {
+  if (!d || !dp_job) return 0;
+  const uint32_t x = dp_job - 1, tid = x >> 24, local = x & 0xffffffu;
+  if ((int)tid >= d->n_thr) return 0;
+  const int64_t k = d->thr_base[tid] + local;
+  return k < d->thr_base[tid + 1] && k < d->n ? &d->res[k] : 0;
+}
 static __thread const dp_cig_t *tl_dp_cig;
 
 /* mem_alnreg_setSAM (:40-123): final CIGAR with band doubling, position, clipping */
 static void set_sam(const bq_opt_t *opt, const bq_ref_t *ref, bq_read_t *s, bq_reg_t *reg) {
   if (reg->n_cigar > 0) return;
-  if (tl_dp_cig && reg->dp_job > 0 && reg->dp_job <= tl_dp_cig->n && tl_dp_cig->res[reg->dp_job - 1].n_cigar > 0) {
+  const bsq_cigar_res *r = dp_cig_find(tl_dp_cig, reg->dp_job);
+  if (r && r->n_cigar > 0) {
     /* the band loop, the global alignment, MD / NM / ZC / ZR and the clean-up of the CIGAR were done by k_cigar on the
      * job built from this region (cigar_job); what is left is the position */
-    const bsq_cigar_res *r = &tl_dp_cig->res[reg->dp_job - 1];
     int is_rev;
     int64_t rpos = bq_depos(ref, reg->rb < ref->l_pac ? reg->rb : reg->re - 1, &is_rev);
     reg->is_rev = is_rev;
@@ -627,9 +635,9 @@ static void cigar_job(const bq_opt_t *opt, const bq_ref_t *ref, const bq_read_t 
  * region that can be printed as a record of its own (not a secondary, score >= T; with -a the secondaries that pass
  * the drop ratio too: mem_alnreg_select_format :445-488, mem_reg2sam_pe :680-693) and the secondaries listed in an XA
  * tag (mem_alnreg_format.c:91-134).  Pairing may still pick a secondary that is in neither group (mem_pair); set_sam then
- * finds no job and does that one on the host.  jobs == NULL: count only. */
-static int predict_cigar_jobs(const bq_opt_t *opt, const bq_ref_t *ref, const bq_read_t *s, bq_regv_t *regs, int64_t row, bsq_cigar_job *jobs,
-                              int64_t first) {
+ * finds no job and does that one on the host.  The jobs go to the calling worker's list. */
+typedef struct { bsq_cigar_job *a; int64_t n, m; } cj_vec_t; /* the CIGAR jobs one worker thread found */
+static int predict_cigar_jobs(const bq_opt_t *opt, const bq_ref_t *ref, const bq_read_t *s, bq_regv_t *regs, int64_t row, cj_vec_t *jobs, int tid) {
   int n = 0;
   /* number of XA candidates per primary (tag_xaxb prints the tag only up to max_XA_hits) */
   uint16_t cbuf[2][128], *cnt_pri = cbuf[0], *cnt_alt = cbuf[1];
@@ -653,7 +661,11 @@ static int predict_cigar_jobs(const bq_opt_t *opt, const bq_ref_t *ref, const bq
       if (r >= 0 && (size_t)r < regs->n && regs->a[r].score >= opt->T) want = cnt_pri[r] <= opt->max_XA_hits && cnt_alt[r] <= opt->max_XA_hits_alt;
     }
     if (!want) continue;
-    if (jobs) { cigar_job(opt, ref, s, p, row, &jobs[n]); p->dp_job = (int)(first + n + 1); }
+    if (jobs->n == jobs->m) { jobs->m = jobs->m ? jobs->m << 1 : 4096; jobs->a = realloc(jobs->a, (size_t)jobs->m * sizeof(bsq_cigar_job)); }
+    if (jobs->n >= (1 << 24)) continue; /* beyond what the region's tag can address: this one is done on the host */
+    cigar_job(opt, ref, s, p, row, &jobs->a[jobs->n]);
+    p->dp_job = ((uint32_t)tid << 24 | (uint32_t)jobs->n) + 1;
+    ++jobs->n;
     ++n;
   }
   if (cnt_pri != cbuf[0]) free(cnt_pri);
@@ -1072,7 +1084,7 @@ void bq_read_clipping(bq_read_t *s, const uint8_t *adaptor, int l_adaptor, const
 
 
 /* stages of the host phase 2 (one parallel section each, items = reads or pairs) */
-enum { ST_GENERIC = 0, ST_MERGE, ST_PESTAT, ST_MS_COUNT, ST_MS_FILL, ST_MARK, ST_CIG_FILL, ST_SAM };
+enum { ST_GENERIC = 0, ST_MERGE, ST_PESTAT, ST_PLAN, ST_MS_FILL, ST_MARK, ST_SAM };
 #define PES_NONE INT64_MIN
 
 typedef struct {
@@ -1091,7 +1103,8 @@ typedef struct {
   int use_dp;
   int64_t *ms_first;            /* per pair (+1): its mate-rescue jobs [ms_first[p], ms_first[p+1]) */
   bsq_matesw_job *mjobs; bsq_matesw_res *mres; uint32_t *mkeys;
-  int64_t *cg_first;            /* per item (+1): its CIGAR jobs */
+  cj_vec_t tjobs[256];          /* per worker thread: the CIGAR jobs it found (regions carry thread << 24 | index) */
+  int64_t thr_base[257];        /* where each thread's jobs start in cjobs / cres */
   bsq_cigar_job *cjobs; bsq_cigar_res *cres;
   dp_cig_t cig;                 /* results as set_sam sees them */
 } work_t;
@@ -1100,6 +1113,26 @@ static void reg_from_dev(const bsq_reg *d, bq_reg_t *r) {
   memset(r, 0, sizeof *r);
   r->rb = d->rb; r->re = d->re; r->qb = d->qb; r->qe = d->qe; r->rid = d->rid; r->score = d->score; r->truesc = d->truesc; r->w = d->w;
   r->seedcov = d->seedcov; r->seedlen0 = d->seedlen0; r->frac_rep = d->frac_rep; r->bss = d->bss; r->parent = d->parent;
+}
+
+/* primary marking of an item (read or pair) and, with a DP context, its CIGAR jobs into the calling worker's list */
+static void mark_and_predict(work_t *w, long i, int tid) {
+  const double p1 = g_prof > 0 ? bq_now() : 0;
+  if (!w->pe) {
+    bq_mark_primary(w->opt, &w->regs[i], w->n_processed + i);
+    for (size_t k = 0; k < w->regs[i].n; ++k) w->regs[i].a[k].flag = 0;
+    if (w->use_dp && w->n_task_of_read[i]) predict_cigar_jobs(w->opt, w->ref, &w->seqs[i], &w->regs[i], w->task_of_read[i], &w->tjobs[tid], tid);
+  } else {
+    bq_mark_primary(w->opt, &w->regs[i << 1 | 0], i << 1 | 0); /* PE ids lack n_processed (bwamem.c:408,413) */
+    bq_mark_primary(w->opt, &w->regs[i << 1 | 1], i << 1 | 1);
+    for (int e = 0; e < 2; ++e)
+      for (size_t k = 0; k < w->regs[i << 1 | e].n; ++k) w->regs[i << 1 | e].a[k].flag = 0;
+    if (w->use_dp)
+      for (int e = 0; e < 2; ++e)
+        if (w->n_task_of_read[i << 1 | e])
+          predict_cigar_jobs(w->opt, w->ref, &w->seqs[i << 1 | e], &w->regs[i << 1 | e], w->task_of_read[i << 1 | e], &w->tjobs[tid], tid);
+  }
+  if (g_prof > 0) { const double p2 = bq_now(); pthread_mutex_lock(&g_prof_mu); g_t_mark += p2 - p1; pthread_mutex_unlock(&g_prof_mu); }
 }
 
 static void work_item(work_t *w, long i, int tid) {
@@ -1123,53 +1156,33 @@ static void work_item(work_t *w, long i, int tid) {
     w->pes_is[i] = pestat_candidate(w->opt, w->ref, &w->regs[i << 1], &w->regs[i << 1 | 1], &is) ? is : PES_NONE;
     return;
   }
-  case ST_MS_COUNT: case ST_MS_FILL: { /* pair i: its mate-rescue alignments as jobs of one bsq_dp_matesw batch */
+  case ST_PLAN: case ST_MS_FILL: { /* pair i: its mate-rescue alignments as jobs of one bsq_dp_matesw batch */
     const int64_t row[2] = {w->task_of_read[i << 1], w->task_of_read[(i << 1) + 1]};
-    if (w->n_task_of_read[i << 1] == 0 || w->n_task_of_read[(i << 1) + 1] == 0) { if (w->stage == ST_MS_COUNT) w->ms_first[i + 1] = 0; return; }
-    if (w->stage == ST_MS_COUNT)
-      w->ms_first[i + 1] = matesw_pair(w->opt, w->ref, w->pes, &w->seqs[i << 1], &w->regs[i << 1], 0, 0, 0, row, 0);
-    else if (w->ms_first[i + 1] > w->ms_first[i])
-      matesw_pair(w->opt, w->ref, w->pes, &w->seqs[i << 1], &w->regs[i << 1], 0, w->mjobs + w->ms_first[i], w->mkeys + w->ms_first[i], row, 1);
-    return;
-  }
-  case ST_MARK: { /* mate rescue (replaying the GPU's alignments), primary marking; number of CIGAR jobs of the item */
-    const double p0 = g_prof > 0 ? bq_now() : 0;
-    if (!w->pe) {
-      bq_mark_primary(w->opt, &w->regs[i], w->n_processed + i);
-      for (size_t k = 0; k < w->regs[i].n; ++k) w->regs[i].a[k].flag = 0;
-      if (w->use_dp) w->cg_first[i + 1] = w->n_task_of_read[i] ? predict_cigar_jobs(w->opt, w->ref, &w->seqs[i], &w->regs[i], 0, 0, 0) : 0;
+    const int both = w->n_task_of_read[i << 1] != 0 && w->n_task_of_read[(i << 1) + 1] != 0;
+    if (w->stage == ST_MS_FILL) {
+      if (both && w->ms_first[i + 1] > w->ms_first[i])
+        matesw_pair(w->opt, w->ref, w->pes, &w->seqs[i << 1], &w->regs[i << 1], 0, w->mjobs + w->ms_first[i], w->mkeys + w->ms_first[i], row, 1);
       return;
     }
-    if (!(w->opt->flag & BQ_F_NO_RESCUE)) {
-      ms_pre_t pre = {w->mres, w->mkeys, 0, 0};
-      if (w->ms_first) { pre.cur = w->ms_first[i]; pre.end = w->ms_first[i + 1]; }
-      matesw_pair(w->opt, w->ref, w->pes, &w->seqs[i << 1], &w->regs[i << 1], w->ms_first ? &pre : 0, 0, 0, 0, 0);
-    }
-    const double p1 = g_prof > 0 ? bq_now() : 0;
-    bq_mark_primary(w->opt, &w->regs[i << 1 | 0], i << 1 | 0); /* PE ids lack n_processed (bwamem.c:408,413) */
-    bq_mark_primary(w->opt, &w->regs[i << 1 | 1], i << 1 | 1);
-    for (int e = 0; e < 2; ++e)
-      for (size_t k = 0; k < w->regs[i << 1 | e].n; ++k) w->regs[i << 1 | e].a[k].flag = 0;
-    if (w->use_dp) {
-      int n = 0;
-      for (int e = 0; e < 2; ++e)
-        if (w->n_task_of_read[i << 1 | e]) n += predict_cigar_jobs(w->opt, w->ref, &w->seqs[i << 1 | e], &w->regs[i << 1 | e], 0, 0, 0);
-      w->cg_first[i + 1] = n;
-    }
-    if (g_prof > 0) {
-      const double p2 = bq_now();
-      pthread_mutex_lock(&g_prof_mu);
-      g_t_mate += p1 - p0; g_t_mark += p2 - p1;
-      pthread_mutex_unlock(&g_prof_mu);
-    }
+    const int n_ms = both ? matesw_pair(w->opt, w->ref, w->pes, &w->seqs[i << 1], &w->regs[i << 1], 0, 0, 0, row, 0) : 0;
+    w->ms_first[i + 1] = n_ms;
+    /* nothing to try for this pair (every attempt is ruled out by the state the pair is in, which no rescue will change):
+     * primary marking and the CIGAR jobs follow at once, while the pair's regions are in cache */
+    if (n_ms == 0) mark_and_predict(w, i, tid);
     return;
   }
-  case ST_CIG_FILL: { /* the CIGAR jobs of the item, at the offsets the counts gave */
-    int64_t at = w->cg_first[i];
-    if (at == w->cg_first[i + 1]) return;
-    const long lo = w->pe ? i << 1 : i, hi = w->pe ? (i << 1) + 2 : i + 1;
-    for (long r = lo; r < hi; ++r)
-      if (w->n_task_of_read[r]) at += predict_cigar_jobs(w->opt, w->ref, &w->seqs[r], &w->regs[r], w->task_of_read[r], w->cjobs + at, at);
+  case ST_MARK: { /* mate rescue (replaying the GPU's alignments) for the pairs that had attempts planned, then as above;
+                   * without a DP context / without rescue: every item */
+    if (w->pe && w->ms_first) {
+      if (w->ms_first[i] == w->ms_first[i + 1]) return; /* done in ST_PLAN */
+      ms_pre_t pre = {w->mres, w->mkeys, w->ms_first[i], w->ms_first[i + 1]};
+      matesw_pair(w->opt, w->ref, w->pes, &w->seqs[i << 1], &w->regs[i << 1], &pre, 0, 0, 0, 0);
+    } else if (w->pe && !(w->opt->flag & BQ_F_NO_RESCUE)) {
+      const double p0 = g_prof > 0 ? bq_now() : 0;
+      matesw_pair(w->opt, w->ref, w->pes, &w->seqs[i << 1], &w->regs[i << 1], 0, 0, 0, 0, 0);
+      if (g_prof > 0) { const double p1 = bq_now(); pthread_mutex_lock(&g_prof_mu); g_t_mate += p1 - p0; pthread_mutex_unlock(&g_prof_mu); }
+    }
+    mark_and_predict(w, i, tid);
     return;
   }
   default: break;
@@ -1579,9 +1592,10 @@ int bq_batch_finish_a(const bq_opt_t *opt, const bq_ref_t *ref, bq_batch_t *b, c
   g_t_mate = g_t_mark = g_t_sam = g_t_pair = g_t_setsam = g_t_fmt = 0;
   const int n_items = pe ? n >> 1 : n;
   int64_t n_mjobs = 0;
-  if (w->use_dp && pe && !(opt->flag & BQ_F_NO_RESCUE)) { /* mate rescue: plan, one kernel, replay (in ST_MARK) */
+  const int plan = w->use_dp && pe && !(opt->flag & BQ_F_NO_RESCUE);
+  if (plan) { /* mate rescue: plan (pairs with nothing to try are finished in the same pass), one kernel, replay (ST_MARK) */
     w->ms_first = calloc((size_t)n_items + 2, sizeof(int64_t));
-    w->stage = ST_MS_COUNT;
+    w->stage = ST_PLAN;
     run_threads(w, n_items);
     n_mjobs = prefix_counts(w->ms_first, n_items);
     if (n_mjobs > 0) {
@@ -1599,18 +1613,25 @@ int bq_batch_finish_a(const bq_opt_t *opt, const bq_ref_t *ref, bq_batch_t *b, c
   }
   const double tr_ = f->t0 > 0 ? bq_now() : 0;
   double ts_ = 0;
-  if (w->use_dp) w->cg_first = calloc((size_t)n_items + 2, sizeof(int64_t));
-  w->stage = ST_MARK;
-  run_threads(w, n_items);
+  if (!plan || n_mjobs > 0) { /* what ST_PLAN could not finish: the pairs with rescue attempts -- or, without planning, every item */
+    w->stage = ST_MARK;
+    run_threads(w, n_items);
+  }
   if (w->use_dp) { /* the final CIGARs of the batch as one asynchronous kernel; _b picks them up */
-    f->n_cjobs = prefix_counts(w->cg_first, n_items);
+    const int nthr = w->n_threads < 1 ? 1 : (w->n_threads > 255 ? 255 : w->n_threads);
+    w->thr_base[0] = 0;
+    for (int t = 0; t < 256; ++t) w->thr_base[t + 1] = w->thr_base[t] + w->tjobs[t].n;
+    f->n_cjobs = w->thr_base[256];
     bq_slot_t *sl = b->slot;
     if ((rc = slot_reserve(&sl->cjobs, &sl->cjobs_cap, (size_t)(f->n_cjobs + 1) * sizeof(bsq_cigar_job))) ||
         (rc = slot_reserve(&sl->cres, &sl->cres_cap, (size_t)(f->n_cjobs + 1) * sizeof(bsq_cigar_res))))
       return rc;
     w->cjobs = sl->cjobs; w->cres = sl->cres;
-    w->stage = ST_CIG_FILL;
-    run_threads(w, n_items);
+    for (int t = 0; t < 256; ++t) { /* the threads' lists, one behind the other, into the page-locked job array */
+      if (w->tjobs[t].n) memcpy(w->cjobs + w->thr_base[t], w->tjobs[t].a, (size_t)w->tjobs[t].n * sizeof(bsq_cigar_job));
+      free(w->tjobs[t].a); w->tjobs[t].a = 0; w->tjobs[t].m = 0;
+    }
+    (void)nthr;
     ts_ = f->t0 > 0 ? bq_now() : 0;
     if ((rc = bsq_dp_cigar_submit(b->dp, f->n_cjobs, w->cjobs, w->cres))) return rc;
     ts_ = f->t0 > 0 ? bq_now() - ts_ : 0;
@@ -1619,8 +1640,8 @@ int bq_batch_finish_a(const bq_opt_t *opt, const bq_ref_t *ref, bq_batch_t *b, c
   }
   if (f->t0 > 0) {
     f->t_a = bq_now() - f->t0;
-    fprintf(stderr, "[bq_finish_a] merge %.3f pestat %.3f rescue jobs %lld (%.3f s) mark+predict %.3f s, cigar jobs %lld (submit %.3f s)\n", tm_ - f->t0, tp_ - tm_,
-            (long long)n_mjobs, tr_ - tp_, bq_now() - tr_ - ts_, (long long)f->n_cjobs, ts_);
+    fprintf(stderr, "[bq_finish_a] merge %.3f pestat %.3f rescue plan + primary marking %.3f s (%lld rescue jobs) replay + job list %.3f s, cigar jobs %lld (submit %.3f s)\n", tm_ - f->t0, tp_ - tm_,
+            tr_ - tp_, (long long)n_mjobs, bq_now() - tr_ - ts_, (long long)f->n_cjobs, ts_);
   }
   return 0;
 }
@@ -1633,7 +1654,7 @@ int bq_batch_finish_wait(bq_batch_t *b) {
   int64_t words = 0;
   const int rc = bsq_dp_cigar_wait(b->dp, &blob, &words);
   if (rc) return rc;
-  f->w.cig.res = f->w.cres; f->w.cig.blob = blob; f->w.cig.n = f->n_cjobs;
+  f->w.cig.res = f->w.cres; f->w.cig.blob = blob; f->w.cig.n = f->n_cjobs; f->w.cig.thr_base = f->w.thr_base; f->w.cig.n_thr = 256;
   return 0;
 }
 
@@ -1665,7 +1686,7 @@ void bq_batch_finish_b(const bq_opt_t *opt, const bq_ref_t *ref, bq_batch_t *b, 
                           g_t_mate, g_t_mark, g_t_sam, g_t_pair, g_t_setsam, g_t_fmt);
   bq_big_free(w->regs);
   pool_give(w->reg_pool, f->pool_cap);
-  free(f->pool_off); free(w->ms_first); free(w->mkeys); free(w->cg_first);
+  free(f->pool_off); free(w->ms_first); free(w->mkeys);
   free(f);
   b->fin = 0;
   batch_free(b);
@@ -1679,7 +1700,8 @@ static void fin_abandon(bq_batch_t *b) { /* a DP call failed: release what _a bu
     for (int r = 0; r < b->n; ++r) if (w->regs[r].a && !w->regs[r].pooled) free(w->regs[r].a);
     bq_big_free(w->regs);
     pool_give(w->reg_pool, f->pool_cap);
-    free(f->pool_off); free(w->ms_first); free(w->mkeys); free(w->cg_first);
+    free(f->pool_off); free(w->ms_first); free(w->mkeys);
+    for (int t = 0; t < 256; ++t) free(w->tjobs[t].a);
     free(f);
     b->fin = 0;
   }
