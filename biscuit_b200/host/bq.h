@@ -107,25 +107,25 @@ typedef struct {
   char **sam_slabs;
 } bq_read_t;
 
-/* ---- alignment region: mem_alnreg_t (lib/aln/mem_alnreg.h:34-66) ---- */
+/* ---- alignment region: mem_alnreg_t (lib/aln/mem_alnreg.h:34-66) ----
+ * Same fields and meanings; laid out in 128 bytes (two cache lines): a batch holds about 1.7 M of them and every stage of
+ * phase 2 streams through them, so the flags are bytes, seedlen0 is 16 bits, and the reference's bookkeeping fields that
+ * nothing reads (n_comp, sam_set, read_in_pair) are left out. */
 typedef struct {
   int64_t rb, re;
-  int qb, qe, rid, score, truesc, sub, alt_sc, csub, sub_n, w, seedcov, secondary, secondary_all, seedlen0;
-  int n_comp, is_alt;
-  float frac_rep;
   uint64_t hash;
-  uint8_t bss, parent, read_in_pair;
+  uint32_t *cigar; /* n_cigar words followed by the NUL-terminated MD string */
+  int qb, qe, rid, score, truesc, sub, alt_sc, csub, sub_n, w, seedcov, secondary, secondary_all;
   int pos, flag, NM, n_cigar;
-  int is_rev, sam_set;
+  float frac_rep;
   unsigned mapq;
   uint32_t ZC, ZR;
-  int bss_u;
-  uint32_t *cigar; /* n_cigar words followed by the NUL-terminated MD string */
   /* batched phase-2 DP on the GPU (bsq_dp_*): the CIGAR job predicted for this region, 0 = none, else
-   * 1 + (worker thread << 24 | index in that thread's job list); and whether .cigar points into the batch's result
-   * blob (not owned by the region) */
+   * 1 + (worker thread << 24 | index in that thread's job list) */
   uint32_t dp_job;
-  uint8_t cigar_ext;
+  int16_t seedlen0;
+  uint8_t bss, parent, is_alt, is_rev, bss_u;
+  uint8_t cigar_ext; /* .cigar points into the batch's result blob (not owned by the region) */
 } bq_reg_t;
 
 typedef struct {

@@ -16,6 +16,7 @@ static double g_t_mate, g_t_mark, g_t_sam, g_t_pair, g_t_setsam, g_t_fmt;
 static pthread_mutex_t g_prof_mu = PTHREAD_MUTEX_INITIALIZER;
 static double bq_now(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + ts.tv_nsec * 1e-9; }
 
+_Static_assert(sizeof(bq_reg_t) == 128, "bq_reg_t is laid out to fill two cache lines");
 #define MINV(a, b) ((a) < (b) ? (a) : (b))
 #define MAXV(a, b) ((a) > (b) ? (a) : (b))
 
@@ -91,7 +92,6 @@ static void sort_dedup(const bq_opt_t *opt, const bq_ref_t *ref, uint8_t *query,
   if (regs->n <= 1) return;
   bq_introsort(regs->a, regs->n, sizeof(bq_reg_t), lt_re);
   int i, m;
-  for (i = 0; (size_t)i < regs->n; ++i) regs->a[i].n_comp = 1;
   for (i = 1; (size_t)i < regs->n; ++i) {
     bq_reg_t *p = regs->a + i;
     for (int j = i - 1; j >= 0 && p->rid == regs->a[j].rid && p->rb < regs->a[j].re + opt->max_chain_gap; --j) {
@@ -104,7 +104,6 @@ static void sort_dedup(const bq_opt_t *opt, const bq_ref_t *ref, uint8_t *query,
         if (p->score < q->score) { p->qe = p->qb; break; }
         else q->qe = q->qb;
       } else if (q->rb < p->rb && (score = test_concatenation(opt, ref, query, q, p, &w)) > 0) {
-        p->n_comp += q->n_comp + 1;
         p->seedcov = p->seedcov > q->seedcov ? p->seedcov : q->seedcov;
         p->sub = MAXV(p->sub, q->sub);
         p->csub = MAXV(p->csub, q->csub);
@@ -561,7 +560,7 @@ static void set_sam(const bq_opt_t *opt, const bq_ref_t *ref, bq_read_t *s, bq_r
     int64_t rpos = bq_depos(ref, reg->rb < ref->l_pac ? reg->rb : reg->re - 1, &is_rev);
     reg->is_rev = is_rev;
     reg->flag |= reg->is_rev ? 0x10 : 0;
-    reg->NM = r->NM; reg->ZC = (uint32_t)r->ZC; reg->ZR = (uint32_t)r->ZR; reg->bss_u = r->bss_u;
+    reg->NM = r->NM; reg->ZC = (uint32_t)r->ZC; reg->ZR = (uint32_t)r->ZR; reg->bss_u = (uint8_t)r->bss_u;
     reg->n_cigar = r->n_cigar;
     reg->cigar = (uint32_t *)(tl_dp_cig->blob + r->off); reg->cigar_ext = 1; /* read-only from here on */
     reg->pos = (int)(rpos + r->lead_del - ref->anns[reg->rid].offset);
@@ -574,17 +573,18 @@ static void set_sam(const bq_opt_t *opt, const bq_ref_t *ref, bq_read_t *s, bq_r
   for (i = 0; i < s->l_seq; ++i) query[i] = s->seq[i] < 5 ? s->seq[i] : 4;
   int w = set_sam_band(opt, reg);
   uint32_t *cigar = 0;
-  int n_cigar = 0, score = 0, last_sc = -(1 << 30);
+  int n_cigar = 0, score = 0, last_sc = -(1 << 30), bss_u_ = 0;
   for (i = 0; i < 3; ++i, w <<= 1, last_sc = score) {
     free(cigar);
     w = MINV(w, opt->w << 2);
     cigar = bq_gen_cigar(reg->parent ? opt->ctmat : opt->gamat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, w, ref->l_pac, ref->pac,
-                         reg->qe - reg->qb, &query[reg->qb], reg->rb, reg->re, &score, &n_cigar, &reg->NM, &reg->ZC, &reg->ZR, &reg->bss_u,
+                         reg->qe - reg->qb, &query[reg->qb], reg->rb, reg->re, &score, &n_cigar, &reg->NM, &reg->ZC, &reg->ZR, &bss_u_,
                          reg->parent);
     if (score == last_sc) break;
     if (w == opt->w << 2) break;
     if (score >= reg->truesc - opt->a) break;
   }
+  reg->bss_u = (uint8_t)bss_u_;
   int l_MD = cigar ? (int)strlen((char *)(cigar + n_cigar)) + 1 : 0;
   int is_rev;
   int64_t rpos = bq_depos(ref, reg->rb < ref->l_pac ? reg->rb : reg->re - 1, &is_rev);
@@ -1112,7 +1112,7 @@ typedef struct {
 static void reg_from_dev(const bsq_reg *d, bq_reg_t *r) {
   memset(r, 0, sizeof *r);
   r->rb = d->rb; r->re = d->re; r->qb = d->qb; r->qe = d->qe; r->rid = d->rid; r->score = d->score; r->truesc = d->truesc; r->w = d->w;
-  r->seedcov = d->seedcov; r->seedlen0 = d->seedlen0; r->frac_rep = d->frac_rep; r->bss = d->bss; r->parent = d->parent;
+  r->seedcov = d->seedcov; r->seedlen0 = (int16_t)d->seedlen0; r->frac_rep = d->frac_rep; r->bss = d->bss; r->parent = d->parent;
 }
 
 /* primary marking of an item (read or pair) and, with a DP context, its CIGAR jobs into the calling worker's list */
@@ -1519,7 +1519,7 @@ static bq_reg_t *pool_take(size_t n, size_t *cap) {
   pthread_mutex_lock(&g_pool_mu);
   if (g_pool && g_pool_cap >= n) { p = g_pool; *cap = g_pool_cap; g_pool = 0; g_pool_cap = 0; }
   pthread_mutex_unlock(&g_pool_mu);
-  if (!p) { *cap = n + (n >> 3); p = malloc(*cap * sizeof(bq_reg_t)); }
+  if (!p) { *cap = n + (n >> 3); p = aligned_alloc(64, *cap * sizeof(bq_reg_t)); } /* regions on cache-line boundaries (128 bytes each) */
   return p;
 }
 static void pool_give(bq_reg_t *p, size_t cap) {
