@@ -263,6 +263,8 @@ def main():
     ncores = os.cpu_count() or 1
     if args.impl == "ours":
         ncores = max(1, ncores // world)  # the host cores are shared by the ranks of the node
+    if os.environ.get("BSQ_BENCH_THREADS"):  # experiments: the host threads of one rank of a larger node on a one-GPU box
+        ncores = max(1, int(os.environ["BSQ_BENCH_THREADS"]))
 
     t0 = time.time()
     nt4, pac, names, offs, lens = gen_reference(args.ref_mb)

@@ -1548,6 +1548,7 @@ static int64_t prefix_counts(int64_t *first, int n_items) { /* first[i + 1] hold
 int bq_batch_finish_a(const bq_opt_t *opt, const bq_ref_t *ref, bq_batch_t *b, const bq_pestat_t *pes0) {
   const int pe = (opt->flag & BQ_F_PE) != 0, n = b->n;
   int rc = 0;
+  const double t_in_ = getenv("BQ_TIMING") ? bq_now() : 0;
   if ((rc = bq_batch_fetch(b))) return rc;
   bq_fin_t *f = calloc(1, sizeof *f);
   work_t *w = &f->w;
@@ -1640,8 +1641,8 @@ int bq_batch_finish_a(const bq_opt_t *opt, const bq_ref_t *ref, bq_batch_t *b, c
   }
   if (f->t0 > 0) {
     f->t_a = bq_now() - f->t0;
-    fprintf(stderr, "[bq_finish_a] merge %.3f pestat %.3f rescue plan + primary marking %.3f s (%lld rescue jobs) replay + job list %.3f s, cigar jobs %lld (submit %.3f s)\n", tm_ - f->t0, tp_ - tm_,
-            tr_ - tp_, (long long)n_mjobs, bq_now() - tr_ - ts_, (long long)f->n_cjobs, ts_);
+    fprintf(stderr, "[bq_finish_a] merge %.3f pestat %.3f rescue plan + primary marking %.3f s (%lld rescue jobs) replay + job list %.3f s, cigar jobs %lld (submit %.3f s); fetch + set-up %.3f, total %.3f s\n", tm_ - f->t0, tp_ - tm_,
+            tr_ - tp_, (long long)n_mjobs, bq_now() - tr_ - ts_, (long long)f->n_cjobs, ts_, f->t0 - t_in_, bq_now() - t_in_);
   }
   return 0;
 }
@@ -1681,12 +1682,13 @@ void bq_batch_finish_b(const bq_opt_t *opt, const bq_ref_t *ref, bq_batch_t *b, 
     for (int k = 0; k < nt; ++k) b->seqs[0].sam_slabs[k] = w->sam_slab[k].s;
   }
   free(w->sam_slab); free(w->sam_off); free(w->sam_thr);
-  if (f->t0 > 0) fprintf(stderr, "[bq_finish_b] pairing + SAM %.3f s\n", bq_now() - t1_);
+  const double t2_ = f->t0 > 0 ? bq_now() : 0;
   if (g_prof > 0) fprintf(stderr, "[bq_prof] thread-seconds: matesw %.3f mark_primary %.3f reg2sam %.3f (pair %.3f set_sam %.3f format %.3f)\n",
                           g_t_mate, g_t_mark, g_t_sam, g_t_pair, g_t_setsam, g_t_fmt);
   bq_big_free(w->regs);
   pool_give(w->reg_pool, f->pool_cap);
   free(f->pool_off); free(w->ms_first); free(w->mkeys);
+  if (f->t0 > 0) fprintf(stderr, "[bq_finish_b] pairing + SAM %.3f s, total %.3f s\n", t2_ - t1_, bq_now() - t1_);
   free(f);
   b->fin = 0;
   batch_free(b);
