@@ -301,6 +301,7 @@ static void *pinned_grow(void *old, size_t old_bytes, size_t new_bytes, int pinn
     if ((n) + (extra) > (cap)) {                                                                              \
       int64_t ncap_ = ((n) + (extra)) * 5 / 4 + (1 << 16);                                                     \
       if (pin_ && ncap_ < (int64_t)(1 << 20)) ncap_ = (int64_t)(1 << 20); /* page-locking is slow: few, large steps */ \
+      if (pin_ && ncap_ < 2 * (int64_t)(cap)) ncap_ = 2 * (int64_t)(cap);                                          \
       (ptr) = pinned_grow((ptr), (size_t)(n) * sizeof *(ptr), (size_t)ncap_ * sizeof *(ptr), pin_);                 \
       (cap) = ncap_;                                                                                          \
     }                                                                                                         \
@@ -433,6 +434,12 @@ int bq_plp_batch_fill(bq_plp_batch_t *B, bq_bgzf_t *b, int sid, int tid, int64_t
         R(qual_off); R(end);
 #undef R
         B->cap = ncap;
+        if (pin_) { /* page-locked payload arrays in one step each, sized from what the records of this window carry per read */
+          const int64_t room = ncap - B->n;
+          GROW(B->cigar, B->n_cig, B->cap_cig, n_cig * room / n + 1);
+          GROW(B->seq, B->n_seq, B->cap_seq, n_seq * room / n + 1);
+          GROW(B->qual, B->n_qual, B->cap_qual, n_qual * room / n + 1);
+        }
       }
       GROW(B->cigar, B->n_cig, B->cap_cig, n_cig);
       GROW(B->seq, B->n_seq, B->cap_seq, n_seq);

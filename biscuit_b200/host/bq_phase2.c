@@ -1135,20 +1135,33 @@ static void mark_and_predict(work_t *w, long i, int tid) {
   if (g_prof > 0) { const double p2 = bq_now(); pthread_mutex_lock(&g_prof_mu); g_t_mark += p2 - p1; pthread_mutex_unlock(&g_prof_mu); }
 }
 
+static __thread bq_reg_t *tl_scr; /* per worker: where the regions of one read are gathered and merged */
+static __thread size_t tl_scr_cap;
+
 static void work_item(work_t *w, long i, int tid) {
   switch (w->stage) {
   case ST_GENERIC: w->gen_fn(w->gen_ctx, i); return;
   case ST_MERGE: { /* gather the regions of read i in the reference's order and merge them */
     bq_regv_t *rv = &w->regs[i];
     rv->n = rv->n_pri = 0;
-    /* the regions of read i live in a slice of the batch's pool: room for every device region of its tasks + 2
-     * (mate rescue may add hits; a push beyond that moves the vector to the heap, regv_push) */
-    rv->a = w->reg_pool + w->pool_off[i]; rv->m = (size_t)(w->pool_off[i + 1] - w->pool_off[i]); rv->pooled = 1;
+    /* The regions of read i live in a slice of the batch's pool: room for every device region of its tasks + 2 (mate
+     * rescue may add hits; a push beyond that moves the vector to the heap, regv_push).  Gathering and merging run in a
+     * scratch array of the worker that stays in cache -- two thirds of the device regions do not survive the merge --
+     * and only the survivors are written to the slice. */
+    bq_reg_t *slice = w->reg_pool + w->pool_off[i];
+    const size_t room = (size_t)(w->pool_off[i + 1] - w->pool_off[i]);
+    if (tl_scr_cap < room) {
+      free(tl_scr);
+      tl_scr_cap = room * 2 + 64;
+      tl_scr = aligned_alloc(64, tl_scr_cap * sizeof(bq_reg_t));
+    }
+    rv->a = tl_scr; rv->m = room; rv->pooled = 1;
     for (int t = 0; t < w->n_task_of_read[i]; ++t) {
       const int64_t task = w->task_of_read[i] + t;
-      for (int64_t k = w->reg_off[task]; k < w->reg_off[task + 1]; ++k) reg_from_dev(&w->dev_regs[k], &rv->a[rv->n++]); /* the slice has room for all of them */
+      for (int64_t k = w->reg_off[task]; k < w->reg_off[task + 1]; ++k) reg_from_dev(&w->dev_regs[k], &rv->a[rv->n++]); /* there is room for all of them */
     }
     bq_merge_regions(w->opt, w->ref, w->seqs[i].seq, w->seqs[i].l_seq, rv);
+    if (rv->a == tl_scr) { memcpy(slice, tl_scr, rv->n * sizeof(bq_reg_t)); rv->a = slice; } /* else: moved to the heap by a push (not expected here) */
     return;
   }
   case ST_PESTAT: { /* pair i: its candidate for the insert-size statistics (the serial part only sorts and sums) */
