@@ -774,7 +774,7 @@ static int seed3_run(SeedWs &ws, cudaStream_t s, const bsq_devopt_t &opt, const 
     CK(cudaGetLastError());
     s3_q_t h;
     CK(cudaMemcpyAsync(&h, q, sizeof h, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    CK(bsq_stream_wait(s));
     if (fills) { fills[0] = (int64_t)h.n_calls1; fills[1] = (int64_t)h.n_items; fills[2] = (int64_t)h.n_calls2; fills[3] = (int64_t)h.cand2_used; fills[4] = attempt; }
     if (!h.overflow) return 0;
     // a queue was too small: size it from what this attempt asked for and seed the batch again
@@ -1011,7 +1011,7 @@ static int scan_counts(bsq_aligner *al, const int32_t *d_counts, int64_t *d_off,
   CK(cudaMemsetAsync(d_off, 0, 8, al->stream));
   CK(cub::DeviceScan::InclusiveSum(al->cub_tmp.p, tmp, d_counts, d_off + 1, (int)n, al->stream));
   CK(cudaMemcpyAsync(total, d_off + n, 8, cudaMemcpyDeviceToHost, al->stream));
-  CK(cudaStreamSynchronize(al->stream));
+  CK(bsq_stream_wait(al->stream));
   return 0;
 }
 
@@ -1117,7 +1117,7 @@ static int phase1_device(bsq_aligner *al, int64_t n, int32_t stride, int64_t *to
     CK(cudaGetLastError());
     int32_t st_now = 0;
     CK(cudaMemcpyAsync(&st_now, al->status.p, 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    CK(bsq_stream_wait(s));
     if (!(st_now & 4)) break;
     if (pass == 1) { snprintf(g_err, sizeof g_err, "fallback chaining workspace exhausted twice"); return BSQ_EOVERFLOW; }
     // many flagged tasks (e.g. repeats with more than max_occ occurrences): give the fallback the full-size pool and redo the rest
@@ -1127,7 +1127,7 @@ static int phase1_device(bsq_aligner *al, int64_t n, int32_t stride, int64_t *to
     st_now &= ~4;
     CK(cudaMemcpyAsync(al->status.p, &st_now, 4, cudaMemcpyHostToDevice, s));
     CK(cudaMemsetAsync(fb_cursor, 0, 8, s));
-    CK(cudaStreamSynchronize(s));
+    CK(bsq_stream_wait(s));
   }
   CK(cudaEventRecord(al->ev[4], s));
   {
@@ -1154,7 +1154,7 @@ static int phase1_device(bsq_aligner *al, int64_t n, int32_t stride, int64_t *to
   unsigned long long n_fb = 0;
   CK(cudaMemcpyAsync(&st, al->status.p, 4, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(&n_fb, al->scalars.as<unsigned long long>() + 1, 8, cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
+  CK(bsq_stream_wait(s));
   al->counters[14] = (int64_t)n_fb;  // tasks chained by the exact fallback kernel
   { float w_ms = 0; cudaEventElapsedTime(&w_ms, al->ev[3], al->ev[7]); al->counters[15] = (int64_t)(w_ms * 1000); }
 #undef RES
@@ -1254,7 +1254,7 @@ static int fetch_slot_copy(bsq_aligner *al, int slot, bsq_reg *regs, int64_t *re
     CK(cudaMemcpyAsync(regs, r.p, (size_t)nr * sizeof(bsq_reg), cudaMemcpyDeviceToHost, s));
   }
   CK(cudaMemcpyAsync(reg_off, o.p, (n + 1) * 8, cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
+  CK(bsq_stream_wait(s));
   return 0;
 }
 
@@ -1270,7 +1270,7 @@ int bsq_aligner_fetch(bsq_aligner *al, bsq_reg *regs, int64_t *reg_off) {
     CK(cudaMemcpyAsync(regs, r.p, (size_t)al->n_regs_total * sizeof(bsq_reg), cudaMemcpyDeviceToHost, s));
   }
   CK(cudaMemcpyAsync(reg_off, o.p, (n + 1) * 8, cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
+  CK(bsq_stream_wait(s));
   return 0;
 }
 

@@ -617,7 +617,7 @@ int bsq_dp_set_reads(bsq_dp *dp, int64_t n_rows, const uint8_t *seqs, int32_t st
 int bsq_dp_sync(bsq_dp *dp) {
   if (!dp) return BSQ_EINVAL;
   CKD(cudaSetDevice(dp->idx->device));
-  CKD(cudaStreamSynchronize(dp->stream));
+  CKD(bsq_stream_wait(dp->stream));
   return 0;
 }
 
@@ -647,13 +647,13 @@ int bsq_dp_cigar_wait(bsq_dp *dp, const uint32_t **blob, int64_t *blob_words) {
   if (blob_words) *blob_words = 0;
   if (dp->c_n == 0) return 0;
   CKD(cudaSetDevice(dp->idx->device));
-  CKD(cudaStreamSynchronize(dp->stream));
+  CKD(bsq_stream_wait(dp->stream));
   const DpCtr *hc = (const DpCtr *)dp->h_ctr.p;
   if (hc->blob_used > dp->blob.cap / 4) {  // the CIGAR/MD text did not fit: grow the blob to what was asked for and run again
     int rc = dp->blob.reserve((size_t)hc->blob_used * 4 + 4096);
     if (rc) return rc;
     if ((rc = dp_launch_cigar(dp))) return rc;
-    CKD(cudaStreamSynchronize(dp->stream));
+    CKD(bsq_stream_wait(dp->stream));
     dp->counters[6]++;
     if (hc->blob_used > dp->blob.cap / 4) { bsq_set_error("k_cigar: blob overflow after growing"); return BSQ_EOVERFLOW; }
   }
@@ -665,7 +665,7 @@ int bsq_dp_cigar_wait(bsq_dp *dp, const uint32_t **blob, int64_t *blob_words) {
   if (rc) return rc;
   if (bytes) {
     CKD(cudaMemcpyAsync(dp->h_blob.p, dp->blob.p, bytes, cudaMemcpyDeviceToHost, dp->stream));
-    CKD(cudaStreamSynchronize(dp->stream));
+    CKD(bsq_stream_wait(dp->stream));
   }
   if (blob) *blob = (const uint32_t *)dp->h_blob.p;
   if (blob_words) *blob_words = (int64_t)hc->blob_used;
@@ -704,7 +704,7 @@ int bsq_dp_matesw_wait(bsq_dp *dp) {
   dp->m_pending = false;
   if (dp->m_n == 0) return 0;
   CKD(cudaSetDevice(dp->idx->device));
-  CKD(cudaStreamSynchronize(dp->stream));
+  CKD(bsq_stream_wait(dp->stream));
   float ms = 0;
   cudaEventElapsedTime(&ms, dp->ev[2], dp->ev[3]);
   dp->counters[5] = (int64_t)(ms * 1000);

@@ -20,3 +20,29 @@ void bsq_index_adopt(bsq_index *ix, void *dev_ptr);  // freed by bsq_index_free
 bool bsq_want_full_sa(uint64_t n, int halves_left);
 // 32-byte rank blocks of both halves (bsq_fm_t::b32), derived on the device from the reference-layout blocks
 int bsq_index_derive_b32(bsq_index *ix);
+
+// Host-side wait for a stream.  Default: cudaStreamSynchronize (spins).  BSQ_SPIN_WAIT=0 waits on an event created with
+// cudaEventBlockingSync instead, which gives the core back while the kernels run.  Measured on one B200 with a 16-core
+// host (profiles/README.md, call AC): with 16 phase-2 workers keeping every core busy the sleeping lane thread is woken
+// late at each of the ~10 waits of a batch (GPU stage 75 -> 93 ms, end to end 2.45 -> 2.01 M reads/s); with 4 workers
+// and idle cores the blocking wait is 6 % faster end to end.  Hence the switch, and spinning as the default.
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+static inline cudaError_t bsq_stream_wait(cudaStream_t s) {
+  static int spin = -1;
+  if (spin < 0) { const char *e = getenv("BSQ_SPIN_WAIT"); spin = !(e && atoi(e) == 0); }
+  if (spin) return cudaStreamSynchronize(s);
+  static thread_local cudaEvent_t ev[64];
+  static thread_local bool have[64];
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaStreamSynchronize(s);
+  if (!have[dev]) {
+    if ((e = cudaEventCreateWithFlags(&ev[dev], cudaEventBlockingSync | cudaEventDisableTiming)) != cudaSuccess) return e;
+    have[dev] = true;
+  }
+  if ((e = cudaEventRecord(ev[dev], s)) != cudaSuccess) return e;
+  return cudaEventSynchronize(ev[dev]);
+}
+#endif
