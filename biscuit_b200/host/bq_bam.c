@@ -287,12 +287,37 @@ static int32_t mc_rlen(const char *mc) {
 /* The batch arrays are page-locked (bsq_host_alloc) so that bsq_plp_stage copies them at full PCIe speed; they only
  * ever grow and batches are reused, so the (slow) pinned allocations amortise. */
 static int g_pinned = 1; /* bamdump (no device involved) switches to plain memory */
-static void batch_mem_free(void *p, int pinned) { if (!p) return; if (pinned) bsq_host_free(p); else free(p); }
+/* Page-locking is a heavy call whatever the size (the three batches of a run hold 18 arrays each), so the arrays are
+ * carved out of a few large page-locked slabs: a bump allocator whose blocks are never returned one by one (the arrays
+ * only grow, geometrically, so what a regrown array leaves behind is bounded by its final size); the slabs live until
+ * the process ends. */
+#define PIN_SLAB_MIN ((size_t)96 << 20)
+static struct { char *base; size_t cap, used; } g_pin_slab[64];
+static int g_n_pin_slab;
+static pthread_mutex_t g_pin_mu = PTHREAD_MUTEX_INITIALIZER;
+static void *pinned_carve(size_t bytes) {
+  bytes = (bytes + 255) & ~(size_t)255;
+  pthread_mutex_lock(&g_pin_mu);
+  int k = g_n_pin_slab - 1;
+  if (k < 0 || g_pin_slab[k].used + bytes > g_pin_slab[k].cap) {
+    if (g_n_pin_slab == 64) { pthread_mutex_unlock(&g_pin_mu); return 0; }
+    size_t cap = bytes > PIN_SLAB_MIN ? bytes : PIN_SLAB_MIN;
+    void *p = 0;
+    if (bsq_host_alloc(&p, cap) != 0) { pthread_mutex_unlock(&g_pin_mu); return 0; }
+    k = g_n_pin_slab++;
+    g_pin_slab[k].base = p; g_pin_slab[k].cap = cap; g_pin_slab[k].used = 0;
+  }
+  void *r = g_pin_slab[k].base + g_pin_slab[k].used;
+  g_pin_slab[k].used += bytes;
+  pthread_mutex_unlock(&g_pin_mu);
+  return r;
+}
+static void batch_mem_free(void *p, int pinned) { if (!p) return; if (!pinned) free(p); /* page-locked blocks stay in their slab */ }
 #define BATCH_PINNED(B) (g_pinned && !(B)->plain)
 static void *pinned_grow(void *old, size_t old_bytes, size_t new_bytes, int pinned) {
   void *p = 0;
   if (!pinned) { p = malloc(new_bytes); if (!p) bq_fatal("[pileup] out of memory\n"); }
-  else if (bsq_host_alloc(&p, new_bytes) != 0) bq_fatal("[pileup] cannot allocate %zu bytes of page-locked memory: %s\n", new_bytes, bsq_last_error());
+  else if (!(p = pinned_carve(new_bytes))) bq_fatal("[pileup] cannot allocate %zu bytes of page-locked memory: %s\n", new_bytes, bsq_last_error());
   if (old) { memcpy(p, old, old_bytes); batch_mem_free(old, pinned); }
   return p;
 }
