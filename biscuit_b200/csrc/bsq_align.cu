@@ -44,6 +44,9 @@ static thread_local char g_err[512] = "";
     }                                                                                              \
   } while (0)
 
+int g_bsq_wait_blocking = 0;
+extern "C" void bsq_set_wait_mode(int blocking) { g_bsq_wait_blocking = blocking != 0; }
+
 void bsq_set_error(const char *fmt, ...) {
   va_list ap;
   va_start(ap, fmt);

@@ -25,12 +25,16 @@ int bsq_index_derive_b32(bsq_index *ix);
 // cudaEventBlockingSync instead, which gives the core back while the kernels run.  Measured on one B200 with a 16-core
 // host (profiles/README.md, call AC): with 16 phase-2 workers keeping every core busy the sleeping lane thread is woken
 // late at each of the ~10 waits of a batch (GPU stage 75 -> 93 ms, end to end 2.45 -> 2.01 M reads/s); with 4 workers
-// and idle cores the blocking wait is 6 % faster end to end.  Hence the switch, and spinning as the default.
+// the host is the slower side, the GPU stage's latency does not matter and the blocking wait is 6 % faster end to end.
+// Hence a mode the caller sets (bsq_set_wait_mode): the batch pipeline of the host code switches to blocking waits while
+// its phase 2 is the slower side and back to spinning when it has to wait for the GPU.
 #if defined(__CUDACC__)
 #include <cuda_runtime.h>
+extern int g_bsq_wait_blocking;  // set through bsq_set_wait_mode (bsq_align.cu): the caller knows which side of its pipeline is the slower one
 static inline cudaError_t bsq_stream_wait(cudaStream_t s) {
-  static int spin = -1;
-  if (spin < 0) { const char *e = getenv("BSQ_SPIN_WAIT"); spin = !(e && atoi(e) == 0); }
+  static int forced = -2;  // BSQ_SPIN_WAIT=1: always spin, =0: always block, unset: what the caller asked for (default: spin)
+  if (forced == -2) { const char *e = getenv("BSQ_SPIN_WAIT"); forced = e ? (atoi(e) != 0) : -1; }
+  const int spin = forced >= 0 ? forced : !g_bsq_wait_blocking;
   if (spin) return cudaStreamSynchronize(s);
   static thread_local cudaEvent_t ev[64];
   static thread_local bool have[64];

@@ -145,6 +145,7 @@ int bq_pipeline_run(const bq_opt_t *opt, const bq_ref_t *ref, bsq_aligner *const
   pthread_create(&td, 0, stage_d, &p);
   int ret = 0;
   double t_wait = 0, t_fin = 0;
+  const int adaptive_wait = getenv("BQ_ADAPTIVE_WAIT") && atoi(getenv("BQ_ADAPTIVE_WAIT")) != 0;
   /* Stage C around the asynchronous CIGAR kernel of the batch's DP context.  When the next batch is already waiting
    * (the host is the slower side), the first half of phase 2 of batch k+1 (merge .. primary marking, CIGAR jobs
    * submitted) runs before the second half of batch k (pairing, SAM text), so the kernel of k+1 overlaps the formatting
@@ -156,6 +157,15 @@ int bq_pipeline_run(const bq_opt_t *opt, const bq_ref_t *ref, bsq_aligner *const
     bq_batch_t *b; bq_read_t *seqs; int n, rc, end;
     double t0 = pnow();
     q_get(&p.qb[seq % p.n_al], &b, &seqs, &n, &rc, &end);
+    /* which side is the slower one?  If this thread had to wait for the GPU lane, the lane's waits should be as short
+     * as they can (spinning); if the batch was already there, phase 2 is the slower side and its workers need the core
+     * a spinning lane thread would hold (the lane then sleeps on an event).  Two batches of hysteresis. */
+    if (adaptive_wait) { /* BQ_ADAPTIVE_WAIT=1: measured once, on different boxes, without a clear gain (profiles/README.md): off by default */
+      static int host_bound = 0;
+      const double waited = pnow() - t0;
+      if (waited < 0.002) { if (host_bound < 2 && ++host_bound == 2) bsq_set_wait_mode(1); }
+      else if (host_bound > 0 && --host_bound == 0) bsq_set_wait_mode(0);
+    }
     t_wait += pnow() - t0; t0 = pnow();
     int rcw;
     if (held.b && (rcw = bq_batch_finish_wait(held.b))) { /* its CIGARs did not come back: the batch fails */

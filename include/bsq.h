@@ -158,6 +158,9 @@ int bsq_aligner_fetch(bsq_aligner *al, bsq_reg *regs, int64_t *reg_off);
 int bsq_aligner_result_slot(bsq_aligner *al, int *slot, int64_t *n_tasks, int64_t *n_regs);
 int bsq_aligner_fetch_slot(bsq_aligner *al, int slot, bsq_reg *regs, int64_t *reg_off);
 int bsq_aligner_release_slot(bsq_aligner *al, int slot);
+/* How this library's calls wait for the GPU: 0 = spinning (cudaStreamSynchronize; lowest latency, holds a core), 1 = sleeping
+ * on an event (gives the core to the caller's other threads).  Process-wide; BSQ_SPIN_WAIT=0/1 in the environment overrides. */
+void bsq_set_wait_mode(int blocking);
 int bsq_host_alloc(void **p, size_t bytes);
 /* work counters for the roofline arithmetic: only the instrumented build (libbsq_count.so) has them,
  * libbsq.so returns BSQ_EINVAL.  out[0]=64-B index blocks fetched, [1]=bwt_extend calls,

@@ -307,6 +307,7 @@ int bsq_aligner_fetch(bsq_aligner *al, bsq_reg *regs, int64_t *reg_off) {
   memcpy(reg_off, al->res_off.data(), (size_t)(al->st_n + 1) * 8);
   return 0;
 }
+void bsq_set_wait_mode(int) {}
 int bsq_host_alloc(void **p, size_t bytes) { *p = malloc(bytes ? bytes : 1); return *p ? 0 : BSQ_ENOMEM; }
 void bsq_host_free(void *p) { free(p); }
 }
