@@ -242,6 +242,29 @@ class Aligner:
         self.bsq.check(self.bsq.lib.bsq_aligner_counters(self.h, _p(c), C.c_int(16)), "bsq_aligner_counters")
         return c
 
+    # staged execution with the deferred fetch (bsq_aligner_stage / _run / _result_slot / _fetch_slot / _release_slot)
+    def stage_run(self, seqs: np.ndarray, lens: np.ndarray, parent: np.ndarray):
+        """Stage and run one batch; returns (slot, n_tasks, n_regs) with the result slot claimed."""
+        seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+        lens = np.ascontiguousarray(lens, dtype=np.int32)
+        parent = np.ascontiguousarray(parent, dtype=np.uint8)
+        L = self.bsq.lib
+        self.bsq.check(L.bsq_aligner_stage(self.h, C.c_int64(seqs.shape[0]), _p(seqs), C.c_int32(seqs.shape[1]), _p(lens), _p(parent)), "bsq_aligner_stage")
+        n_regs = C.c_int64()
+        self.bsq.check(L.bsq_aligner_run(self.h, C.byref(n_regs)), "bsq_aligner_run")
+        slot, nt, nr = C.c_int(), C.c_int64(), C.c_int64()
+        self.bsq.check(L.bsq_aligner_result_slot(self.h, C.byref(slot), C.byref(nt), C.byref(nr)), "bsq_aligner_result_slot")
+        return slot.value, nt.value, nr.value
+
+    def fetch_slot(self, slot: int, n_tasks: int, n_regs: int):
+        regs = np.zeros(max(n_regs, 1), dtype=REG_DTYPE)
+        reg_off = np.zeros(n_tasks + 1, dtype=np.int64)
+        self.bsq.check(self.bsq.lib.bsq_aligner_fetch_slot(self.h, C.c_int(slot), _p(regs), _p(reg_off)), "bsq_aligner_fetch_slot")
+        return regs[:n_regs], reg_off
+
+    def release_slot(self, slot: int):
+        self.bsq.check(self.bsq.lib.bsq_aligner_release_slot(self.h, C.c_int(slot)), "bsq_aligner_release_slot")
+
 
 CIGAR_JOB_DTYPE = np.dtype([("rb", "<i8"), ("re", "<i8"), ("row", "<i4"), ("qb", "<i4"), ("qe", "<i4"), ("w", "<i4"), ("truesc", "<i4"),
                             ("clip5", "<i4"), ("clip3", "<i4"), ("parent", "u1"), ("pad_", "u1", (3,))])

@@ -1632,7 +1632,6 @@ int bq_batch_finish_a(const bq_opt_t *opt, const bq_ref_t *ref, bq_batch_t *b, c
     run_threads(w, n_items);
   }
   if (w->use_dp) { /* the final CIGARs of the batch as one asynchronous kernel; _b picks them up */
-    const int nthr = w->n_threads < 1 ? 1 : (w->n_threads > 255 ? 255 : w->n_threads);
     w->thr_base[0] = 0;
     for (int t = 0; t < 256; ++t) w->thr_base[t + 1] = w->thr_base[t] + w->tjobs[t].n;
     f->n_cjobs = w->thr_base[256];
@@ -1645,7 +1644,6 @@ int bq_batch_finish_a(const bq_opt_t *opt, const bq_ref_t *ref, bq_batch_t *b, c
       if (w->tjobs[t].n) memcpy(w->cjobs + w->thr_base[t], w->tjobs[t].a, (size_t)w->tjobs[t].n * sizeof(bsq_cigar_job));
       free(w->tjobs[t].a); w->tjobs[t].a = 0; w->tjobs[t].m = 0;
     }
-    (void)nthr;
     ts_ = f->t0 > 0 ? bq_now() : 0;
     if ((rc = bsq_dp_cigar_submit(b->dp, f->n_cjobs, w->cjobs, w->cres))) return rc;
     ts_ = f->t0 > 0 ? bq_now() - ts_ : 0;

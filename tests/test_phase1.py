@@ -164,3 +164,42 @@ def test_abi_symbols():
     lib = C.CDLL(capi.LIB_PATH)
     missing = [n for n in sorted(names) if not hasattr(lib, n)]
     assert not missing, missing
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_deferred_fetch_slots(ctx, backend, request):
+    """The two result slots of the aligner: a batch can be fetched after the next one has run; a third run waits until a
+    claimed slot has been fetched or released (bsq_aligner_result_slot / _fetch_slot / _release_slot)."""
+    import threading
+    ds, hi, rp = ctx
+    bsq = request.getfixturevalue(backend)
+    dx = bsq.upload(hi)
+    opt = bsq.default_opt()
+    reads, mat, lens = _reads(ds, extra_short=False)
+    n = min(len(reads), 120)
+    a_in = (mat[:n // 2], lens[:n // 2], np.ones(n // 2, np.uint8))
+    b_in = (mat[n // 2:n], lens[n // 2:n], np.zeros(n - n // 2, np.uint8))
+    al = capi.Aligner(dx, opt)
+    exp_a = al.phase1(*a_in)
+    exp_b = al.phase1(*b_in)
+    sa = al.stage_run(*a_in)
+    sb = al.stage_run(*b_in)          # the other slot: A's regions are still on the device
+    assert sa[0] != sb[0]
+    done = threading.Event()
+
+    def third():
+        sc = al.stage_run(*a_in)      # would overwrite A's slot: blocks until A has been fetched
+        al.release_slot(sc[0])
+        done.set()
+
+    th = threading.Thread(target=third)
+    th.start()
+    assert not done.wait(1.0), "the run that reuses a claimed slot did not wait"
+    got_a = al.fetch_slot(*sa)
+    assert done.wait(60.0), "the waiting run was not released by the fetch"
+    th.join()
+    got_b = al.fetch_slot(*sb)
+    for got, exp in ((got_a, exp_a), (got_b, exp_b)):
+        assert (got[1] == exp[1]).all() and got[0].tobytes() == exp[0].tobytes()
+    al.close()
+    dx.close()
