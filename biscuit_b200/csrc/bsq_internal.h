@@ -24,10 +24,10 @@ int bsq_index_derive_b32(bsq_index *ix);
 // Host-side wait for a stream.  Default: cudaStreamSynchronize (spins).  BSQ_SPIN_WAIT=0 waits on an event created with
 // cudaEventBlockingSync instead, which gives the core back while the kernels run.  Measured on one B200 with a 16-core
 // host (profiles/README.md, call AC): with 16 phase-2 workers keeping every core busy the sleeping lane thread is woken
-// late at each of the ~10 waits of a batch (GPU stage 75 -> 93 ms, end to end 2.45 -> 2.01 M reads/s); with 4 workers
-// the host is the slower side, the GPU stage's latency does not matter and the blocking wait is 6 % faster end to end.
-// Hence a mode the caller sets (bsq_set_wait_mode): the batch pipeline of the host code switches to blocking waits while
-// its phase 2 is the slower side and back to spinning when it has to wait for the GPU.
+// late at each of the ~10 waits of a batch (GPU stage 75 -> 93 ms, end to end 2.45 -> 2.01 M reads/s); with 4 workers,
+// where the host is the slower side, the two are equal within the run-to-run spread (call AJ: 1.44 vs 1.40 M reads/s).
+// The mode is the caller's to set (bsq_set_wait_mode); the host code's pipeline can drive it (BQ_ADAPTIVE_WAIT=1, off by
+// default: no measured gain).
 #if defined(__CUDACC__)
 #include <cuda_runtime.h>
 extern int g_bsq_wait_blocking;  // set through bsq_set_wait_mode (bsq_align.cu): the caller knows which side of its pipeline is the slower one
