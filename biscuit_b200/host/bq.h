@@ -103,6 +103,7 @@ typedef struct {
    * (sam_in_slab) and the buffers hang off the first read of the batch */
   uint8_t sam_in_slab;
   size_t sam_off; /* phase-2 workers format straight into their slab: offset of this read's text until the batch is done */
+  size_t sam_len; /* length of .sam when phase 2 knows it (0 = unknown: use strlen), so that the sinks need not scan the text */
   int n_sam_slabs;
   char **sam_slabs;
 } bq_read_t;

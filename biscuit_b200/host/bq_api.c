@@ -120,7 +120,7 @@ static void stream_sink(void *ctx, bq_read_t *rd, int n) {
   const int ok = n >= 0;
   if (n < 0) n = -n;
   int64_t tot = 0;
-  for (int i = 0; i < n; ++i) tot += rd[i].sam ? (int64_t)strlen(rd[i].sam) : 0;
+  for (int i = 0; i < n; ++i) tot += rd[i].sam ? (int64_t)(rd[i].sam_len ? rd[i].sam_len : strlen(rd[i].sam)) : 0;
   bq_reads_free(rd, n);
   if (ok) st->sam_bytes = tot;
 }

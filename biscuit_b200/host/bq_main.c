@@ -80,7 +80,7 @@ static void sam_sink(void *ctx, bq_read_t *seqs, int n) {
   if (n < 0) n = -n;
   if (ok)
     for (int i = 0; i < n; ++i)
-      if (seqs[i].sam) fputs(seqs[i].sam, stdout);
+      if (seqs[i].sam) { if (seqs[i].sam_len) fwrite(seqs[i].sam, 1, seqs[i].sam_len, stdout); else fputs(seqs[i].sam, stdout); }
   bq_reads_free(seqs, n);
   if (ok && bq_verbose >= 3) fprintf(stderr, "[M::mem_process_seqs] Processed %d reads\n", n);
 }

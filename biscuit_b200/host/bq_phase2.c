@@ -905,8 +905,9 @@ static bq_str_t *sam_out_begin(sam_out_t *o, const bq_read_t *s) {
   return o->str;
 }
 static void sam_out_end(sam_out_t *o, bq_read_t *s) {
-  if (o->str == &o->own) { s->sam = o->own.s; return; }
+  if (o->str == &o->own) { s->sam = o->own.s; s->sam_len = o->own.l; return; }
   bq_str_reserve(o->str, 1);
+  s->sam_len = o->str->l - o->off0;
   o->str->s[o->str->l++] = 0; /* keep the terminating NUL inside the slab */
   s->sam = 0; s->sam_in_slab = 1; s->sam_off = o->off0;
 }
