@@ -312,18 +312,16 @@ static void matesw_core(const bq_opt_t *opt, const bq_ref_t *ref, bq_pestat_t pe
 typedef struct { const bsq_matesw_res *res; const uint32_t *key; int64_t cur, end; } ms_pre_t;
 static int matesw_pair(const bq_opt_t *opt, const bq_ref_t *ref, bq_pestat_t pes, bq_read_t s[2], bq_regv_t regs[2], ms_pre_t *pre,
                        bsq_matesw_job *jobs, uint32_t *keys, const int64_t row[2], int fill) {
-  bq_reg_t gbuf[2][8];
-  bq_regv_t good[2] = {{0, 8, 0, gbuf[0], 1}, {0, 8, 0, gbuf[1], 1}};
   int i, n_jobs = 0;
   size_t j;
   const int plan = row != 0;
-  for (i = 0; i < 2; ++i)
-    for (j = 0; j < regs[i].n; ++j)
-      if (regs[i].a[j].score >= regs[i].a[0].score - opt->pen_unpaired) regv_push(&good[i], &regs[i].a[j]);
-  for (i = 0; i < 2; ++i)
-    for (j = 0; j < good[i].n && (int)j < opt->max_matesw; ++j) {
-      const bq_reg_t *reg = &good[i].a[j];
-      if (plan) {
+  if (plan) { /* nothing changes while planning: the candidates are read in place (rank j = position among the good ones) */
+    for (i = 0; i < 2; ++i) {
+      size_t rank = 0;
+      for (j = 0; j < regs[i].n && (int)rank < opt->max_matesw; ++j) {
+        const bq_reg_t *reg = &regs[i].a[j];
+        if (reg->score < regs[i].a[0].score - opt->pen_unpaired) continue;
+        const size_t jr = rank++;
         int64_t rb, re;
         if (mate_in_range(ref, pes, reg, &regs[!i]) || !matesw_window(opt, ref, pes, reg, s[!i].l_seq, &rb, &re)) continue;
         if (fill) {
@@ -331,11 +329,21 @@ static int matesw_pair(const bq_opt_t *opt, const bq_ref_t *ref, bq_pestat_t pes
           memset(jb, 0, sizeof *jb);
           jb->rb = rb; jb->re = re; jb->row = (int32_t)row[!i]; jb->xtra = matesw_xtra(opt, s[!i].l_seq);
           jb->use_ga = (uint8_t)(reg->bss ^ (reg->rb < ref->l_pac));
-          keys[n_jobs] = (uint32_t)i << 16 | (uint32_t)j;
+          keys[n_jobs] = (uint32_t)i << 16 | (uint32_t)jr;
         }
         ++n_jobs;
-        continue;
       }
+    }
+    return n_jobs;
+  }
+  bq_reg_t gbuf[2][8];
+  bq_regv_t good[2] = {{0, 8, 0, gbuf[0], 1}, {0, 8, 0, gbuf[1], 1}};
+  for (i = 0; i < 2; ++i)
+    for (j = 0; j < regs[i].n; ++j)
+      if (regs[i].a[j].score >= regs[i].a[0].score - opt->pen_unpaired) regv_push(&good[i], &regs[i].a[j]);
+  for (i = 0; i < 2; ++i)
+    for (j = 0; j < good[i].n && (int)j < opt->max_matesw; ++j) {
+      const bq_reg_t *reg = &good[i].a[j];
       const bsq_matesw_res *r = 0;
       if (pre) {
         const uint32_t key = (uint32_t)i << 16 | (uint32_t)j;
