@@ -602,6 +602,11 @@ def main():
                         "what": "phase-2 DP since the session started: final CIGAR/MD (k_cigar) and mate-rescue local alignments (k_matesw)"}
         except Exception as e:  # noqa: BLE001
             log("dp stats unavailable:", e)
+        # bytes the phase-2 DP context moves per step: the task rows a second time and one 48-byte job per final CIGAR in, one
+        # 32-byte result and the CIGAR/MD text (about 70 B, profiles/dpbench_r02_u.json) per job out
+        jobs_per_step = (dp_stats["cigar_jobs_gpu"] / max(1, 1 + max(6, args.warmup) + args.steps)) if dp_stats else 0
+        h2d_dp = int(h_seqs.nbytes + h_len.nbytes + 48 * jobs_per_step)
+        d2h_dp = int((32 + 70) * jobs_per_step)
         value = world * n_reads * args.steps / dt
         e2e_phase1 = world * n_reads * args.steps / dt_e2e
         e2e = world * n_reads * args.steps / dt_full
@@ -614,7 +619,9 @@ def main():
                                     f"{ncores} threads, SAM text out)",
                            "l2": "inputs larger than L2 (FM-index gathers over the whole index)", "index_build_s": t_index,
                            "parallelism": f"dp{world} (reads sharded, index replicated)"},
-                "clocks": clocks, "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "clocks": clocks, "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d + h2d_dp, "d2h_bytes_per_step": d2h + d2h_dp,
+                                          "bytes_note": f"phase 1: {h2d} B of task rows in, {d2h} B of regions out; phase-2 DP context: the rows again + "
+                                                        f"48 B per CIGAR job in ({h2d_dp} B), 32 B per result + CIGAR/MD text out (~{d2h_dp} B)",
                                           "sam_bytes_per_step": int(sam_bytes), "host_threads": ncores},
                 "e2e_phase1": {"value": e2e_phase1, "unit": "reads/s", "note": "C ABI with pinned host buffers: H2D + kernels + D2H of regions"},
                 "gpu_launches": 21 * args.steps,  # own kernels of one phase-1 step (profiles/launches_r02_u.csv): 5 seeding passes + k_seed_sort, k_expand, k_sa, k_chain_tiers, 7 k_chain_warp tiers, k_chain, k_region_prep, k_region, k_compact_regs
