@@ -113,6 +113,25 @@ def test_fastq_shapes_hostemu(hard_set, tmp_path):
     assert mine.count(b"\n") > 800
 
 
+def test_gzip_pair_files_hostemu(hard_set, tmp_path):
+    """gzip-compressed pair files (kseq over gzread in the reference): the second file is inflated and parsed by the
+    reader's helper thread, the batches are read two ahead of the pipeline -- same SAM as the reference, with the helper
+    and without it."""
+    import gzip
+    import shutil
+    fa, f1, f2 = hard_set
+    gz = []
+    for k, fn in enumerate((f1, f2)):
+        o = str(tmp_path / f"p{k}.fq.gz")
+        with open(fn, "rb") as fi, gzip.open(o, "wb", compresslevel=1) as fo:
+            shutil.copyfileobj(fi, fo)
+        gz.append(o)
+    args = ["-@", "3", fa] + gz
+    ref = _sam(refprobe.REF_BIN, args)
+    assert _sam(build_emu_bin(), args) == ref
+    assert _sam(build_emu_bin(), args, env={"BQ_FQ_NO_AHEAD": "1"}) == ref
+
+
 def test_sam_identical_single_end_hostemu(hard_set):
     fa, f1, _ = hard_set
     args = ["-@", "4", fa, f1]
