@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "bq.h"
+#include "bq_sort.h"
 #include <pthread.h>
 #include <time.h>
 /* BQ_PROF=1: thread-seconds per part of phase 2, printed per batch (diagnostics) */
@@ -64,6 +65,8 @@ static int lt_score_rb_qb(const void *a_, const void *b_) {
   const bq_reg_t *a = a_, *b = b_;
   return a->score > b->score || (a->score == b->score && (a->rb < b->rb || (a->rb == b->rb && a->qb < b->qb)));
 }
+BQ_INTROSORT_DEFINE(sort_regs_re, bq_reg_t, lt_re)
+BQ_INTROSORT_DEFINE(sort_regs_score, bq_reg_t, lt_score_rb_qb)
 
 /* score of joining two colinear regions through a global alignment, 0 when they should stay apart */
 static int test_concatenation(const bq_opt_t *opt, const bq_ref_t *ref, uint8_t *query, const bq_reg_t *a, const bq_reg_t *b, int *w_out) {
@@ -90,7 +93,7 @@ static int test_concatenation(const bq_opt_t *opt, const bq_ref_t *ref, uint8_t 
 
 static void sort_dedup(const bq_opt_t *opt, const bq_ref_t *ref, uint8_t *query, bq_regv_t *regs) {
   if (regs->n <= 1) return;
-  bq_introsort(regs->a, regs->n, sizeof(bq_reg_t), lt_re);
+  sort_regs_re(regs->a, regs->n);
   int i, m;
   for (i = 1; (size_t)i < regs->n; ++i) {
     bq_reg_t *p = regs->a + i;
@@ -116,7 +119,7 @@ static void sort_dedup(const bq_opt_t *opt, const bq_ref_t *ref, uint8_t *query,
   for (i = 0, m = 0; (size_t)i < regs->n; ++i)
     if (regs->a[i].qe > regs->a[i].qb) { if (m != i) regs->a[m++] = regs->a[i]; else ++m; }
   regs->n = (size_t)m;
-  bq_introsort(regs->a, regs->n, sizeof(bq_reg_t), lt_score_rb_qb);
+  sort_regs_score(regs->a, regs->n);
   for (i = 1; (size_t)i < regs->n; ++i)
     if (regs->a[i].score == regs->a[i - 1].score && regs->a[i].rb == regs->a[i - 1].rb && regs->a[i].qb == regs->a[i - 1].qb)
       regs->a[i].qe = regs->a[i].qb;
@@ -370,6 +373,8 @@ static int lt_hash2(const void *a_, const void *b_) {
   const bq_reg_t *a = a_, *b = b_;
   return a->is_alt < b->is_alt || (a->is_alt == b->is_alt && (a->score > b->score || (a->score == b->score && a->hash < b->hash)));
 }
+BQ_INTROSORT_DEFINE(sort_regs_hash, bq_reg_t, lt_hash)
+BQ_INTROSORT_DEFINE(sort_regs_hash2, bq_reg_t, lt_hash2)
 
 static void mark_core(const bq_opt_t *opt, int n_mark, bq_regv_t *regs, int *z, int *nz) {
   int tmp = opt->a + opt->b;
@@ -408,7 +413,7 @@ void bq_mark_primary(const bq_opt_t *opt, bq_regv_t *regs, int64_t id) {
     p->hash = bq_hash64((uint64_t)(id + i));
     if (!p->is_alt) ++regs->n_pri;
   }
-  bq_introsort(regs->a, regs->n, sizeof(bq_reg_t), lt_hash);
+  sort_regs_hash(regs->a, regs->n);
   int zbuf[64], *z = regs->n < 64 ? zbuf : malloc(sizeof(int) * (regs->n + 1));
   mark_core(opt, (int)regs->n, regs, z, &nz);
   for (i = 0; (size_t)i < regs->n; ++i) {
@@ -417,7 +422,7 @@ void bq_mark_primary(const bq_opt_t *opt, bq_regv_t *regs, int64_t id) {
     if (!p->is_alt && p->secondary >= 0 && regs->a[p->secondary].is_alt) p->alt_sc = regs->a[p->secondary].score;
   }
   if (regs->n_pri > 0 && regs->n_pri < regs->n) {
-    bq_introsort(regs->a, regs->n, sizeof(bq_reg_t), lt_hash2);
+    sort_regs_hash2(regs->a, regs->n);
     for (i = 0; (size_t)i < regs->n; ++i) z[regs->a[i].secondary_all] = i;
     for (i = 0; (size_t)i < regs->n; ++i) {
       if (regs->a[i].secondary >= 0) {
@@ -463,6 +468,8 @@ typedef struct { uint64_t x, y, z; } trio_t;
 typedef struct { uint64_t x, y; } pair_t;
 static int lt_xy3(const void *a_, const void *b_) { const trio_t *a = a_, *b = b_; return a->x < b->x || (a->x == b->x && a->y < b->y); }
 static int lt_xy2(const void *a_, const void *b_) { const pair_t *a = a_, *b = b_; return a->x < b->x || (a->x == b->x && a->y < b->y); }
+BQ_INTROSORT_DEFINE(sort_trio, trio_t, lt_xy3)
+BQ_INTROSORT_DEFINE(sort_pair, pair_t, lt_xy2)
 
 static void pair_regs(const bq_opt_t *opt, const bq_ref_t *ref, bq_pestat_t pes, bq_regv_t regs[2], int id, int *score, int *sub, int *n_sub,
                       int z[2]) {
@@ -479,7 +486,7 @@ static void pair_regs(const bq_opt_t *opt, const bq_ref_t *ref, bq_pestat_t pes,
       v[n].z = (uint64_t)(p->qe - p->qb);
       ++n;
     }
-  bq_introsort(v, n, sizeof(trio_t), lt_xy3);
+  sort_trio(v, n);
   for (i = 0; (size_t)i < n; ++i)
     for (k = i - 1; k >= 0; --k) {
       if (v[i].x >> 32 != v[k].x >> 32) break;
@@ -503,7 +510,7 @@ static void pair_regs(const bq_opt_t *opt, const bq_ref_t *ref, bq_pestat_t pes,
       }
     }
   if (np) {
-    bq_introsort(pp, np, sizeof(pair_t), lt_xy2);
+    sort_pair(pp, np);
     i = (int)(pp[np - 1].y >> 32);
     k = (int)(pp[np - 1].y << 32 >> 32);
     z[v[i].y & 1] = (int)(v[i].y << 32 >> 34);

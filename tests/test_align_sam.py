@@ -23,7 +23,7 @@ def build_emu_bin():
     import conftest
     conftest.build_hostemu()
     srcs = [os.path.join(HOST, f) for f in ("bq_core.c", "bq_phase2.c", "bq_pipe.c", "bq_io.c", "bq_main.c", "bq_bam.c", "bq_pileup.c", "bq_vcf2bed.c", "bq_sortbam.c")]
-    deps = srcs + [os.path.join(HOST, "bq.h"), os.path.join(HOST, "bq_plp.h"), os.path.join(ROOT, "tests", "hostemu", "libbsq_hostemu.so")]
+    deps = srcs + [os.path.join(HOST, "bq.h"), os.path.join(HOST, "bq_sort.h"), os.path.join(HOST, "bq_plp.h"), os.path.join(ROOT, "tests", "hostemu", "libbsq_hostemu.so")]
     if not os.path.exists(EMU_BIN) or any(os.path.getmtime(d) > os.path.getmtime(EMU_BIN) for d in deps):
         subprocess.check_call(["gcc", "-O2", "-g", "-std=gnu11", "-o", EMU_BIN] + srcs +
                               ["-L" + os.path.dirname(EMU_BIN), "-lbsq_hostemu", "-Wl,-rpath,$ORIGIN", "-lz", "-lpthread", "-lm"])

@@ -125,3 +125,16 @@ def test_repeats_take_the_exact_fallback(repeat_case, backend, fb_pool, request,
         assert c[14] > 0  # some tasks really went through k_chain
     al.close()
     dx.close()
+
+
+def test_typed_introsort_matches_generic(tmp_path):
+    """biscuit_b200/host/bq_sort.h (typed instances used by phase 2) against bq_introsort (the exact klib sequence): same
+    order of equal keys on 6000 random / patterned arrays (tests/hostemu/sort_check.c)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "sort_check")
+    subprocess.check_call(["gcc", "-O2", "-std=gnu11", "-o", exe, os.path.join(root, "tests", "hostemu", "sort_check.c"),
+                           os.path.join(root, "biscuit_b200", "host", "bq_core.c"), "-lm"])
+    out = subprocess.run([exe], stdout=subprocess.PIPE, check=True).stdout
+    assert out.startswith(b"ok ")
