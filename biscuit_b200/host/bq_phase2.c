@@ -471,6 +471,16 @@ static int lt_xy2(const void *a_, const void *b_) { const pair_t *a = a_, *b = b
 BQ_INTROSORT_DEFINE(sort_trio, trio_t, lt_xy3)
 BQ_INTROSORT_DEFINE(sort_pair, pair_t, lt_xy2)
 
+/* The insert-size term of the pair score (mem_pair.c:174-176): .721 * log(2 * erfc(|z| / sqrt 2)) * a, a function of the
+ * insert size alone once the batch's statistics are known.  Phase 2 tabulates it once per batch over [low, high] (the only
+ * values that reach it) instead of two libm calls per candidate pair; the entries are the doubles the expression gives. */
+typedef struct { int low, high; const double *term; } pair_tab_t;
+static __thread const pair_tab_t *tl_pair_tab;
+static inline double pair_term(const bq_opt_t *opt, const bq_pestat_t *pes, int64_t is) {
+  const double zscore = (is - pes->avg) / pes->std;
+  return .721 * log(2. * erfc(fabs(zscore) * M_SQRT1_2)) * opt->a;
+}
+
 static void pair_regs(const bq_opt_t *opt, const bq_ref_t *ref, bq_pestat_t pes, bq_regv_t regs[2], int id, int *score, int *sub, int *n_sub,
                       int z[2]) {
   const int64_t l_pac = ref->l_pac;
@@ -496,8 +506,9 @@ static void pair_regs(const bq_opt_t *opt, const bq_ref_t *ref, bq_pestat_t pes,
       int64_t is = 0;
       if (infer_isize((int64_t)v[k].x, (int64_t)v[i].x, (v[k].y >> 1) & 1, (v[i].y >> 1) & 1, (int64_t)v[k].z, (int64_t)v[i].z, &is) &&
           is >= pes.low && is <= pes.high) {
-        double zscore = (is - pes.avg) / pes.std;
-        int sc = (int)((v[i].y >> 32) + (v[k].y >> 32) + .721 * log(2. * erfc(fabs(zscore) * M_SQRT1_2)) * opt->a + .499);
+        const pair_tab_t *pt = tl_pair_tab;
+        const double term = pt && is >= pt->low && is <= pt->high ? pt->term[is - pt->low] : pair_term(opt, &pes, is);
+        int sc = (int)((v[i].y >> 32) + (v[k].y >> 32) + term + .499);
         sc = MAXV(0, sc);
         if (np == mp) {
           mp <<= 1;
@@ -1123,6 +1134,7 @@ typedef struct {
   int64_t thr_base[257];        /* where each thread's jobs start in cjobs / cres */
   bsq_cigar_job *cjobs; bsq_cigar_res *cres;
   dp_cig_t cig;                 /* results as set_sam sees them */
+  pair_tab_t pair_tab; double *pair_term; /* insert-size term of the pair score, tabulated per batch */
 } work_t;
 
 static void reg_from_dev(const bsq_reg *d, bq_reg_t *r) {
@@ -1219,6 +1231,7 @@ static void work_item(work_t *w, long i, int tid) {
   /* ST_SAM: pairing, mapQ, SAM text */
   tl_sam_slab = &w->sam_slab[tid];
   tl_dp_cig = w->use_dp ? &w->cig : 0;
+  tl_pair_tab = w->pair_term ? &w->pair_tab : 0;
   if (!w->pe) {
     if (tl_sam_slab->m == 0) { tl_sam_slab->s = bq_big_alloc((size_t)(w->n_items / w->n_threads + 1) * (2 * (size_t)w->seqs[i].l_seq0 + 256), &tl_sam_slab->m); tl_sam_slab->s[0] = 0; }
     bq_reg2sam_se(w->opt, w->ref, &w->seqs[i], &w->regs[i], w->rg_id);
@@ -1237,6 +1250,7 @@ static void work_item(work_t *w, long i, int tid) {
     const long lo = w->pe ? i << 1 : i, hi = w->pe ? (i << 1) + 2 : i + 1;
     tl_sam_slab = 0;
     tl_dp_cig = 0;
+    tl_pair_tab = 0;
     for (long r = lo; r < hi; ++r) { /* the text is already in this thread's slab (sam_out_end); a stray own string is moved there */
       bq_read_t *rd = &w->seqs[r];
       if (rd->sam_in_slab) { w->sam_off[r] = rd->sam_off; w->sam_thr[r] = (uint8_t)tid; continue; }
@@ -1698,8 +1712,15 @@ void bq_batch_finish_b(const bq_opt_t *opt, const bq_ref_t *ref, bq_batch_t *b, 
     w->sam_off = malloc(sizeof(size_t) * (size_t)(n + 1));
     w->sam_thr = malloc((size_t)n + 1);
   }
+  if (pe && !w->pes.failed && w->pes.high >= w->pes.low && w->pes.high - w->pes.low < (1 << 16) && w->pes.std > 0) {
+    const int nt_ = w->pes.high - w->pes.low + 1;
+    w->pair_term = malloc(sizeof(double) * (size_t)nt_);
+    for (int k = 0; k < nt_; ++k) w->pair_term[k] = pair_term(opt, &w->pes, (int64_t)w->pes.low + k);
+    w->pair_tab.low = w->pes.low; w->pair_tab.high = w->pes.high; w->pair_tab.term = w->pair_term;
+  }
   w->stage = ST_SAM;
   run_threads(w, pe ? n >> 1 : n);
+  free(w->pair_term); w->pair_term = 0;
   if (n > 0) { /* .sam pointers into the (now final) slabs; the slabs belong to the first read of the batch */
     const int nt = w->n_threads;
     for (int i = 0; i < n; ++i)
